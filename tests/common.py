@@ -1,0 +1,52 @@
+"""Shared helpers for the test-suite (no reference imports; runs on the GPU box too)."""
+import os
+import sys
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def seeded_state(shapes, seed):
+    """Deterministic, portable weights for a state_dict described by {key: shape}.
+
+    conv weights ~ N(0, 2/fan_in); biases 0.1*N; BN gamma U(0.5,1.5), running_var U(0.5,1.5),
+    running_mean 0.1*N; PReLU slope 0.1..0.35.  Generated in key order from one PCG64 stream.
+    """
+    rng = np.random.default_rng(seed)
+    out = {}
+    for k, shp in shapes.items():
+        shp = tuple(int(s) for s in shp)
+        if k.endswith('num_batches_tracked'):
+            out[k] = np.zeros(shp, dtype=np.int64)
+        elif k.endswith('running_var'):
+            out[k] = rng.uniform(0.5, 1.5, shp).astype(np.float32)
+        elif k.endswith('running_mean'):
+            out[k] = (0.1 * rng.standard_normal(shp)).astype(np.float32)
+        elif len(shp) >= 2:
+            fan_in = int(np.prod(shp[1:]))
+            out[k] = (rng.standard_normal(shp) * np.sqrt(2.0 / fan_in)).astype(np.float32)
+        elif k.endswith('.weight') and shp == (1,):
+            out[k] = rng.uniform(0.1, 0.35, shp).astype(np.float32)
+        elif k.endswith('.weight'):
+            out[k] = rng.uniform(0.5, 1.5, shp).astype(np.float32)
+        else:
+            out[k] = (0.1 * rng.standard_normal(shp)).astype(np.float32)
+    return out
+
+
+def gold(name):
+    return np.load(os.path.join(GOLD, name + '.npz'), allow_pickle=False)
+
+
+def weights_of(g, prefix='w.'):
+    return {k[len(prefix):]: g[k] for k in g.files if k.startswith(prefix)}
+
+
+def rel_err(y, ref):
+    """Parity metric of SURVEY 8(c): (max|d|/max|ref|, rel-L2)."""
+    y = np.asarray(y, dtype=np.float64); ref = np.asarray(ref, dtype=np.float64)
+    d = np.abs(y - ref)
+    return float(d.max() / max(np.abs(ref).max(), 1e-30)), float(np.linalg.norm(y - ref) / max(np.linalg.norm(ref), 1e-30))

@@ -1,0 +1,106 @@
+"""Pin the CPU oracle (oracle/topaz_oracle.py) against goldens produced by the real reference
+(tools/make_goldens.py).  fp32 CPU vs fp32 CPU: tolerance 2e-5 relative (op re-association only)."""
+import numpy as np
+import pytest
+import torch
+
+from common import gold, weights_of, seeded_state, rel_err
+from oracle import topaz_oracle as O
+
+TOL = 2e-5
+
+
+def _close(y, ref, tol=TOL):
+    m, l2 = rel_err(y, ref)
+    assert m <= tol and l2 <= tol, (m, l2)
+
+
+def test_resnet8_u32_pretrained_dense_and_crops():
+    g = gold('resnet8_u32_pretrained'); sd = weights_of(g)
+    assert O.resnet_width(O.resnet_spec('resnet8', 32)) == int(g['width']) == 71
+    _close(O.classifier_forward(sd, g['x'], 'resnet8', 32, filled=True).numpy(), g['y_dense'])
+    _close(O.classifier_forward(sd, g['crops'], 'resnet8', 32, filled=False).numpy(), g['y_crops'])
+
+
+def test_resnet8_u32_patched_scoring_matches_reference():
+    g = gold('resnet8_u32_pretrained'); sd = weights_of(g)
+    fwd = lambda p: O.classifier_forward(sd, p, 'resnet8', 32, filled=True)
+    y = O.score_in_patches(fwd, torch.from_numpy(g['xp']), 64 + 2 * 35, 35)
+    assert y.dtype == np.float64
+    _close(y, g['y_patch'])
+
+
+def test_nms_bit_exact_on_reference_scores():
+    g = gold('resnet8_u32_pretrained')
+    s, c = O.nms(g['y_full'][0, 0], 6, -6.0)
+    assert np.array_equal(c, g['nms_coords']) and np.array_equal(s, g['nms_scores'])
+
+
+def test_resnet8_u64_pretrained_dense():
+    g = gold('resnet8_u64_pretrained')
+    _close(O.classifier_forward(weights_of(g), g['x'], 'resnet8', 64, filled=True).numpy(), g['y_dense'])
+
+
+@pytest.mark.parametrize('name,arch,units,scaling,bn', [
+    ('resnet16_u16', 'resnet16', 16, 1, False),
+    ('resnet8_u16_bn', 'resnet8', 16, 1, True),
+    ('conv31_u16x2', 'conv31', 16, 2, True),
+    ('conv63_u32x2', 'conv63', 32, 2, True),
+    ('conv63_u16_nobn', 'conv63', 16, 1, False),
+])
+def test_seeded_classifiers(name, arch, units, scaling, bn):
+    g = gold('cls_' + name)
+    # shapes are recovered by building the product-independent shape table from the oracle spec
+    from common_shapes import classifier_shapes
+    shapes = classifier_shapes(arch, units, scaling, bn)
+    assert list(shapes.keys()) == [str(k) for k in g['keys']]
+    sd = seeded_state(shapes, int(g['seed']))
+    _close(O.classifier_forward(sd, g['xc'], arch, units, False, bn, scaling).numpy(), g['yc'])
+    _close(O.classifier_forward(sd, g['xd'], arch, units, True, bn, scaling).numpy(), g['yd'])
+
+
+def test_unet_pretrained():
+    g = gold('unet_pretrained'); sd = weights_of(g)
+    _close(O.unet_forward(sd, g['x']).numpy(), g['y'])
+    _close(O.unet_forward(sd, g['xo']).numpy(), g['yo'])
+    _close(O.denoise_call(sd, g['img']), g['y_call'])
+    _close(O.denoise(sd, g['img'], patch_size=64, padding=24), g['y_pat'])
+
+
+def test_unet_seeded_and_3d():
+    from common_shapes import unet_shapes
+    g = gold('unet_seeded_nf16')
+    sh = unet_shapes(16, 7, 3, 2)
+    assert list(sh.keys()) == [str(k) for k in g['keys']]
+    _close(O.unet_forward(seeded_state(sh, int(g['seed'])), g['x']).numpy(), g['y'])
+    g = gold('unet3d_seeded')
+    sh = unet_shapes(48, 7, 3, 3)
+    assert list(sh.keys()) == [str(k) for k in g['keys']]
+    sd = seeded_state(sh, int(g['seed']))
+    _close(O.unet_forward(sd, g['x']).numpy(), g['y'])
+    _close(O.denoise3d(sd, g['tomo'], 16, 8), g['y_tomo'], 5e-5)
+
+
+def test_ge_binomial_three_steps():
+    g = gold('ge_binomial_u32'); sd = weights_of(gold('resnet8_u32_pretrained'))
+    B = int(g['B'])
+    Xs = [np.random.default_rng(4000 + s).standard_normal((B, 71, 71)).astype(np.float32) for s in range(3)]
+    outs, grads, final = O.ge_binomial_steps(sd, Xs, [g['Y']] * 3, 'resnet8', 32, float(g['pi']))
+    np.testing.assert_allclose(np.array(outs), g['outs'], rtol=2e-4, atol=1e-6)
+    for k in sd:
+        _close(grads[0][k], g['g1.' + k], 2e-4)
+        _close(final[k], g['p3.' + k], 1e-5)
+
+
+def test_filters():
+    g = gold('filters')
+    _close(O.gaussian_denoise(g['img'], 1.5), g['gauss'])
+    n, mu, std = O.affine_normalize(g['img'])
+    _close(n, g['norm']); assert abs(mu - float(g['mu'])) < 1e-6 and abs(std - float(g['std'])) < 1e-6
+
+
+def test_log_binom_matches_scipy():
+    scipy_stats = pytest.importorskip('scipy.stats')
+    for N, pi in [(240, 0.035), (60, 0.2), (1, 0.5)]:
+        ref = scipy_stats.binom.logpmf(np.arange(N + 1), N, pi).astype(np.float32)
+        np.testing.assert_allclose(O.log_binom_pmf(N, pi), ref, rtol=2e-6, atol=1e-5)
