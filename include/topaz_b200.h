@@ -1,0 +1,112 @@
+/* topaz_b200 C ABI — B200 (sm_100a) kernels for the Topaz dense-CNN hot path.
+ *
+ * The reference (tbepler/topaz) has no native/FFI layer: its seam is torch.nn (cuDNN/ATen library calls).
+ * Each entry point below names the reference call site(s) it replaces.  Conventions:
+ *   - every function returns 0 on success, non-zero on error; tpz_last_error() gives the message
+ *     (thread-local); nothing falls back to the CPU;
+ *   - all pointers are DEVICE pointers unless named host_*; the library never frees or retains them;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are asynchronous;
+ *   - activations are channels-last fp16: [N][D][H][W][C] (2-D: D = 1), `ld` = channel stride in elements;
+ *   - image-like endpoints (network input / logit or denoised output) are dense fp32 [N][D][H][W].
+ */
+#ifndef TOPAZ_B200_H
+#define TOPAZ_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef uint16_t tpz_half; /* IEEE fp16 bits */
+
+const char* tpz_last_error(void);
+/* Device / build info: writes SM count, cc major, cc minor. */
+int tpz_device_info(int* num_sms, int* cc_major, int* cc_minor);
+
+/* ---- tcgen05 implicit-GEMM convolution (stride 1, arbitrary dilation, 2-D/3-D, up to two input sources) ----
+ * Replaces nn.Conv2d/Conv3d + bias (+BN eval affine folded by the caller) + ReLU/LeakyReLU/PReLU
+ * + cropped residual add + 1x1 proj + 1x1 classifier at:
+ *   topaz/model/features/resnet.py:101-105 (BasicConv.forward), :178-204 (ResidA.forward),
+ *   topaz/model/features/basic.py:101-111, topaz/model/classifier.py:64-66,
+ *   topaz/denoising/models.py:130-175 (UDenoiseNet.forward), :508-564 (UDenoiseNet3D.forward).     */
+#define TPZ_TC_MAX_KB 256
+typedef struct {
+  int16_t dx, dy, dz; /* input offset of this k-block's tap (tap index * dilation), elements */
+  int16_t c0;         /* first input channel of the chunk                                     */
+  int32_t src;        /* which source (0/1)                                                    */
+} TcKBlock;
+
+typedef struct {
+  const tpz_half* ptr; /* [N][D][H][W][ld] fp16 */
+  int N, D, H, W, C, ld;
+  int org[3];          /* (x,y,z) offset added to the output coordinate: -padding or +crop */
+} TpzTcSrc;
+
+typedef struct {
+  int nsrc;
+  TpzTcSrc src[2];
+  const tpz_half* weights; /* [nkb][Co][KC] fp16, k-block order == kb[] order */
+  int KC;                  /* channels per k-block: 64 or 32 */
+  int nkb;
+  TcKBlock kb[TPZ_TC_MAX_KB];
+  int N, Do, Ho, Wo, Co;   /* output geometry */
+  int TW, TH;              /* pixel tile, TW*TH == 128, TW % 8 == 0 */
+  const float* bias;       /* [Co] or NULL */
+  float neg_slope;         /* activation: v>0 ? v : v*neg_slope (0 = ReLU, 1 = linear, 0.1 = LeakyReLU) */
+  const tpz_half* res;     /* optional residual, added before the activation */
+  const float* res_scale;  /* optional per-channel scale of the residual (BN after the add) */
+  int res_ld, res_D, res_H, res_W, res_org[3];
+  tpz_half* out;           /* [N][Do][Ho][Wo][out_ld] (+out_coff) or NULL */
+  int out_ld, out_coff;
+  const float* dot_w;      /* optional fused 1x1 "classifier": dot_out = sum_c act(.)*dot_w[c] + dot_b */
+  float dot_b;
+  float* dot_out;          /* [N][Do][Ho][Wo] fp32 or NULL */
+} TpzTcConvArgs;
+
+int tpz_tc_conv(const TpzTcConvArgs* host_args, void* stream);
+
+/* ---- direct (SIMT) convolutions for the thin ends and for validation ----
+ * tpz_conv_first: Cin = 1 conv from a dense fp32 image, fp32 math, fused bias + activation, fp16 NDHWC out.
+ *   Replaces the first BasicConv 7x7 (resnet.py:66,102), conv31/63/127 layer 0 (basic.py:47-52) and the
+ *   U-Net enc1 11x11 / 7x7x7 conv (denoising/models.py:79,457).  `pad` = zero padding on every side,
+ *   weights fp32 [Co][kd][kh][kw], optional fused 2x max-pool (`pool` = 1/2).                        */
+int tpz_conv_first(const float* x, int N, int D, int H, int W, const float* w, const float* bias, int Co,
+                   int kd, int kh, int kw, int dil, int pad, float neg_slope, int pool, tpz_half* out,
+                   int out_ld, void* stream);
+/* tpz_conv_last: Cout = 1 conv from fp16 NDHWC to dense fp32 (classifier 1x1, classifier.py:65; U-Net
+ *   dec1.4, denoising/models.py:127,505).  out = (sum + bias) * out_scale + out_shift, then, if
+ *   affine_stats (device float[2] = mean,std) is given, out = out*std + mean (denoise.py:295 de-normalise).               */
+int tpz_conv_last(const tpz_half* x, int N, int D, int H, int W, int C, int ld, const float* w, float bias,
+                  int kd, int kh, int kw, int dil, int pad, float out_scale, float out_shift,
+                  const float* affine_stats, float* out, void* stream);
+/* tpz_conv_generic: reference-quality fp32-accumulate conv on fp16 NDHWC tensors with stride support;
+ *   used for validation of tpz_tc_conv and for shapes the tensor-core kernel does not cover.
+ *   weights fp32 [Co][Ci][kd][kh][kw] (reference OIHW layout). Two sources are concatenated on channels. */
+int tpz_conv_generic(const tpz_half* x0, int C0, int ld0, const tpz_half* x1, int C1, int ld1, int N, int D,
+                     int H, int W, const float* w, const float* bias, int Co, int kd, int kh, int kw,
+                     int stride, int dil, int pad, float neg_slope, const tpz_half* res, int res_ld,
+                     int res_org, tpz_half* out, int out_ld, int Do, int Ho, int Wo, void* stream);
+
+/* ---- pooling / resampling (F.max_pool2d/3d(2), F.interpolate(mode='nearest') + torch.cat) ----
+ *   denoising/models.py:82-97 (MaxPool), :140-171 (interpolate + cat).                                */
+int tpz_maxpool2(const tpz_half* x, int N, int D, int H, int W, int C, int ld, int dims, tpz_half* out,
+                 int out_ld, void* stream);
+int tpz_upsample_nearest(const tpz_half* x, int N, int D, int H, int W, int C, int ld, int Do, int Ho, int Wo,
+                         tpz_half* out, int out_ld, int out_coff, void* stream);
+
+/* ---- normalisation prologue (denoise.py:283-284 torch mean / unbiased std; stats.py:36-46) ----
+ * stats[0]=mean, stats[1]=std (unbiased if `unbiased`), computed on device in fp64 accumulators;
+ * y = (x-mean)/std written as fp32 (y may alias x).  `stats` is a device float[2], `work4` a device double[4] scratch.                  */
+int tpz_meanstd(const float* x, long long n, int unbiased, float* stats, double* work4, void* stream);
+int tpz_affine(const float* x, long long n, const float* stats, int inverse, float* y, void* stream);
+
+/* ---- hardware probe used by tests/bring-up (UMMA descriptor row-offset behaviour), not on the product path ---- */
+int tpz_lab_umma(const tpz_half* A, int rowsA, const tpz_half* B, int N, int shift, int sbo_rows, int base_off_mode,
+                 float* D, void* stream);
+
+/* ---- layout helpers ---- */
+int tpz_f32_to_f16(const float* x, long long n, tpz_half* y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

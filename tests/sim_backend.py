@@ -1,0 +1,111 @@
+"""CPU *simulation* of the kernel semantics, used only by the not-gpu tests to validate host logic
+(weight packing, k-block tables, offsets, channel padding, BN folding, network wiring) without a GPU.
+It interprets exactly the arguments the real launchers receive.  Test infrastructure, never shipped."""
+import contextlib
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from topaz_b200 import ops
+
+
+def _gather(src, org, d, out_shape, c0, kc):
+    """src [N,D,H,W,C] fp16 -> fp32 [N,Do,Ho,Wo,kc] window starting at (org+d) with zero fill."""
+    N, Do, Ho, Wo = out_shape
+    _, D, H, W, _ = src.shape
+    ox, oy, oz = org[0] + d[0], org[1] + d[1], org[2] + d[2]
+    out = torch.zeros((N, Do, Ho, Wo, kc), dtype=torch.float32)
+    z0, z1 = max(0, oz), min(D, oz + Do)
+    y0, y1 = max(0, oy), min(H, oy + Ho)
+    x0, x1 = max(0, ox), min(W, ox + Wo)
+    if z1 > z0 and y1 > y0 and x1 > x0:
+        out[:, z0 - oz:z1 - oz, y0 - oy:y1 - oy, x0 - ox:x1 - ox] = src[:, z0:z1, y0:y1, x0:x1, c0:c0 + kc].float()
+    return out
+
+
+def tc_conv(plan, srcs, out_shape, out=None, res=None, res_org=(0, 0, 0), dot_out=None, out_coff=0):
+    N, Do, Ho, Wo = out_shape
+    acc = torch.zeros((N, Do, Ho, Wo, plan.Co), dtype=torch.float32)
+    for kb, (dx, dy, dz, c0, si) in enumerate(plan.kblocks):
+        A = _gather(srcs[si], plan.orgs[si], (dx, dy, dz), out_shape, c0, plan.KC)
+        acc += A @ plan.weights[kb].float().t()
+    v = acc + plan.bias
+    if res is not None:
+        r = res[:, res_org[2]:res_org[2] + Do, res_org[1]:res_org[1] + Ho, res_org[0]:res_org[0] + Wo, :plan.Co].float()
+        v = v + (r * plan.res_scale if plan.res_scale is not None else r)
+    v = torch.where(v > 0, v, v * plan.neg_slope)
+    if dot_out is not None:
+        dot_out.copy_((v * plan.dot_w).sum(-1) + plan.dot_b)
+    if out is not None:
+        out[..., out_coff:out_coff + plan.Co] = v.half()
+
+
+def conv_first(x, w, bias, dil, pad, neg_slope, out_ld):
+    N, D, H, W = x.shape
+    Co, kd, kh, kw = w.shape
+    if kd > 1:
+        y = F.conv3d(x[:, None], w[:, None], bias, dilation=dil, padding=pad)
+    else:
+        y = F.conv2d(x.reshape(N * D, 1, H, W), w, bias, dilation=dil, padding=pad)
+        y = y.reshape(N, D, Co, y.shape[-2], y.shape[-1]).permute(0, 2, 1, 3, 4)
+    y = torch.where(y > 0, y, y * neg_slope)
+    out = torch.zeros((N,) + tuple(y.shape[2:]) + (out_ld,), dtype=torch.float16)
+    out[..., :Co] = y.permute(0, 2, 3, 4, 1).half()
+    return out
+
+
+def conv_last(x, c_real, w, bias, kdhw, dil, pad, stats=None, out_scale=1.0, out_shift=0.0):
+    N, D, H, W, ld = x.shape
+    kd, kh, kw = kdhw
+    C = w.shape[1]
+    wt = w.t().reshape(1, C, kd, kh, kw)
+    xi = x[..., :C].float().permute(0, 4, 1, 2, 3)
+    y = F.conv3d(xi, wt, None, dilation=dil, padding=(pad if kd > 1 else 0, pad, pad))[:, 0]
+    y = (y + bias) * out_scale + out_shift
+    if stats is not None:
+        y = y * stats[1] + stats[0]
+    return y
+
+
+def maxpool2(x, dims):
+    xi = x.float().permute(0, 4, 1, 2, 3)
+    y = F.max_pool3d(xi, (2 if dims == 3 else 1, 2, 2))
+    return y.permute(0, 2, 3, 4, 1).half().contiguous()
+
+
+def upsample_nearest(x, size):
+    N, D, H, W, C = x.shape
+    Do, Ho, Wo = size
+    def idx(n_in, n_out):
+        scale = np.float32(n_in) / np.float32(n_out)
+        return torch.tensor([min(int(math.floor(np.float32(i) * scale)), n_in - 1) for i in range(n_out)])
+    return x[:, idx(D, Do)][:, :, idx(H, Ho)][:, :, :, idx(W, Wo)].contiguous()
+
+
+def meanstd(x, unbiased):
+    xd = x.double()
+    return torch.stack([xd.mean(), xd.std(unbiased=unbiased)]).float()
+
+
+def affine(x, stats, inverse=False, out=None):
+    y = x * stats[1] + stats[0] if inverse else (x - stats[0]) / stats[1]
+    if out is not None:
+        out.copy_(y); return out
+    return y
+
+
+@contextlib.contextmanager
+def patched():
+    names = ['tc_conv', 'conv_first', 'conv_last', 'maxpool2', 'upsample_nearest', 'meanstd', 'affine']
+    saved = {n: getattr(ops, n) for n in names}
+    saved['require_cuda'] = ops.require_cuda
+    try:
+        for n in names:
+            setattr(ops, n, globals()[n])
+        ops.require_cuda = lambda t, what: None
+        yield
+    finally:
+        for n, f in saved.items():
+            setattr(ops, n, f)

@@ -1,0 +1,109 @@
+"""not-gpu tests of the host side: the C-ABI library loads and exports every declared symbol, and the
+Python engine (weight packing, k-block tables, BN folding, U-Net wiring, patch logic) reproduces the
+reference goldens when its kernel launches are replaced by the CPU simulation in tests/sim_backend.py."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from common import ROOT, gold, weights_of, seeded_state, rel_err
+from common_shapes import classifier_shapes, unet_shapes
+import sim_backend
+
+TOL = 1e-3   # fp16 operand rounding is simulated, so the north-star tolerance applies (pretrained weights)
+TOL_SEEDED = 3e-3   # He-normal random weights amplify the 2^-11 operand rounding through 9-16 layers
+
+
+def _load(model, sd):
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    return model
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as g
+    g.build()
+    from topaz_b200 import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'topaz_b200.h')).read()
+    declared = set(re.findall(r'\b(tpz_[a-z0-9_]+)\s*\(', hdr))
+    assert declared, 'no declarations found'
+    l = _lib.lib()
+    for name in declared:
+        assert hasattr(l, name), f'{name} declared in include/topaz_b200.h but not exported'
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+
+
+def test_cpu_tensor_is_rejected():
+    from topaz_b200.model.factory import get_feature_extractor
+    from topaz_b200.model.classifier import LinearClassifier
+    m = LinearClassifier(get_feature_extractor('resnet8', units=16, bn=False)); m.eval(); m.fill()
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 1, 80, 80))
+
+
+def _classifier(arch, units, scaling, bn):
+    from topaz_b200.model.factory import get_feature_extractor
+    from topaz_b200.model.classifier import LinearClassifier
+    kw = dict(units=units, bn=bn)
+    if arch.startswith('conv'):
+        kw['unit_scaling'] = scaling
+    return LinearClassifier(get_feature_extractor(arch, **kw))
+
+
+def test_dense_resnet8_pretrained_sim():
+    g = gold('resnet8_u32_pretrained')
+    m = _load(_classifier('resnet8', 32, 1, False), weights_of(g)); m.eval()
+    assert m.width == int(g['width'])
+    assert m.fill() == 4
+    with sim_backend.patched(), torch.no_grad():
+        y = m(torch.from_numpy(g['x'])).numpy()
+    mx, l2 = rel_err(y, g['y_dense'])
+    assert y.shape == g['y_dense'].shape and mx < TOL and l2 < TOL, (mx, l2)
+
+
+@pytest.mark.parametrize('name,arch,units,scaling,bn', [
+    ('resnet16_u16', 'resnet16', 16, 1, False),
+    ('resnet8_u16_bn', 'resnet8', 16, 1, True),
+    ('conv31_u16x2', 'conv31', 16, 2, True),
+    ('conv63_u32x2', 'conv63', 32, 2, True),
+    ('conv63_u16_nobn', 'conv63', 16, 1, False),
+])
+def test_dense_seeded_classifiers_sim(name, arch, units, scaling, bn):
+    g = gold('cls_' + name)
+    m = _classifier(arch, units, scaling, bn)
+    assert [k for k in m.state_dict().keys()] == [str(k) for k in g['keys']]
+    _load(m, seeded_state(classifier_shapes(arch, units, scaling, bn), int(g['seed']))); m.eval()
+    assert m.width == int(g['width']) and m.fill() == int(g['fill_stride'])
+    with sim_backend.patched(), torch.no_grad():
+        y = m(torch.from_numpy(g['xd'])).numpy()
+    mx, l2 = rel_err(y, g['yd'])
+    assert mx < TOL_SEEDED and l2 < TOL_SEEDED, (mx, l2)
+
+
+def test_unet_sim_pretrained_and_seeded():
+    from topaz_b200.denoising.models import UDenoiseNet, UDenoiseNet3D
+    g = gold('unet_pretrained')
+    m = _load(UDenoiseNet(base_width=11, top_width=5), weights_of(g)); m.eval()
+    with sim_backend.patched(), torch.no_grad():
+        y = m(torch.from_numpy(g['x'])).numpy()
+        yo = m(torch.from_numpy(g['xo'])).numpy()
+    for a, b in ((y, g['y']), (yo, g['yo'])):
+        mx, l2 = rel_err(a, b)
+        assert mx < 2e-3 and l2 < 2e-3, (mx, l2)
+    g = gold('unet_seeded_nf16')
+    m = UDenoiseNet(nf=16, base_width=7, top_width=3)
+    assert list(m.state_dict().keys()) == [str(k) for k in g['keys']]
+    _load(m, seeded_state(unet_shapes(16, 7, 3, 2), int(g['seed']))); m.eval()
+    with sim_backend.patched(), torch.no_grad():
+        y = m(torch.from_numpy(g['x'])).numpy()
+    mx, l2 = rel_err(y, g['y'])
+    assert mx < 2e-3 and l2 < 2e-3, (mx, l2)
+    g = gold('unet3d_seeded')
+    m = UDenoiseNet3D(nf=48, base_width=7, top_width=3)
+    assert list(m.state_dict().keys()) == [str(k) for k in g['keys']]
+    _load(m, seeded_state(unet_shapes(48, 7, 3, 3), int(g['seed']))); m.eval()
+    with sim_backend.patched(), torch.no_grad():
+        y = m(torch.from_numpy(g['x'])).numpy()
+    mx, l2 = rel_err(y, g['y'])
+    assert mx < 2e-3 and l2 < 2e-3, (mx, l2)

@@ -1,0 +1,76 @@
+"""ctypes binding of libtopaz_b200.so (the C ABI declared in include/topaz_b200.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a).  There is no CPU fallback:
+if the shared library is missing, or a call fails, a RuntimeError is raised.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libtopaz_b200.so')
+TPZ_TC_MAX_KB = 256
+
+
+class TcKBlock(C.Structure):
+    _fields_ = [('dx', C.c_int16), ('dy', C.c_int16), ('dz', C.c_int16), ('c0', C.c_int16), ('src', C.c_int32)]
+
+
+class TpzTcSrc(C.Structure):
+    _fields_ = [('ptr', C.c_void_p), ('N', C.c_int), ('D', C.c_int), ('H', C.c_int), ('W', C.c_int),
+                ('C', C.c_int), ('ld', C.c_int), ('org', C.c_int * 3)]
+
+
+class TpzTcConvArgs(C.Structure):
+    _fields_ = [
+        ('nsrc', C.c_int), ('src', TpzTcSrc * 2), ('weights', C.c_void_p), ('KC', C.c_int), ('nkb', C.c_int),
+        ('kb', TcKBlock * TPZ_TC_MAX_KB),
+        ('N', C.c_int), ('Do', C.c_int), ('Ho', C.c_int), ('Wo', C.c_int), ('Co', C.c_int),
+        ('TW', C.c_int), ('TH', C.c_int),
+        ('bias', C.c_void_p), ('neg_slope', C.c_float),
+        ('res', C.c_void_p), ('res_scale', C.c_void_p),
+        ('res_ld', C.c_int), ('res_D', C.c_int), ('res_H', C.c_int), ('res_W', C.c_int), ('res_org', C.c_int * 3),
+        ('out', C.c_void_p), ('out_ld', C.c_int), ('out_coff', C.c_int),
+        ('dot_w', C.c_void_p), ('dot_b', C.c_float), ('dot_out', C.c_void_p),
+    ]
+
+
+_lib = None
+
+_I, _F, _P, _LL = C.c_int, C.c_float, C.c_void_p, C.c_longlong
+_PROTOS = {
+    'tpz_last_error': (C.c_char_p, []),
+    'tpz_device_info': (_I, [C.POINTER(_I)] * 3),
+    'tpz_tc_conv': (_I, [C.POINTER(TpzTcConvArgs), _P]),
+    'tpz_conv_first': (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _I, _P]),
+    'tpz_conv_last': (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _F, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P]),
+    'tpz_conv_generic': (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F,
+                              _P, _I, _I, _P, _I, _I, _I, _I, _P]),
+    'tpz_maxpool2': (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P]),
+    'tpz_upsample_nearest': (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P]),
+    'tpz_meanstd': (_I, [_P, _LL, _I, _P, _P, _P]),
+    'tpz_affine': (_I, [_P, _LL, _P, _I, _P, _P]),
+    'tpz_f32_to_f16': (_I, [_P, _LL, _P, _P]),
+    'tpz_lab_umma': (_I, [_P, _I, _P, _I, _I, _I, _I, _P, _P]),
+}
+EXPORTS = tuple(_PROTOS.keys())
+
+
+def lib():
+    """Load the shared library (once).  Raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f'topaz_b200: native library {LIB_PATH} is missing; run '
+                               f'`python -c "import __graft_entry__ as g; g.build()"` (no CPU fallback exists)')
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(l, name)       # AttributeError if the symbol is not exported
+            fn.restype, fn.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().tpz_last_error()
+        raise RuntimeError(f'topaz_b200 native call failed ({rc}): {msg.decode() if msg else "?"}')

@@ -1,0 +1,436 @@
+// Direct (SIMT) kernels for the thin ends of the networks and for validation:
+//   Cin=1 first convs, Cout=1 tails, a generic reference-quality conv, 2x max-pool, nearest upsample,
+//   mean/std normalisation.  All fp32 math; activations fp16 channels-last.
+#include "tpz_common.cuh"
+#include "../../include/topaz_b200.h"
+
+namespace {
+
+__device__ __forceinline__ float act(float v, float slope) { return v > 0.f ? v : v * slope; }
+
+// -------------------------------------------------------------------------------------------------
+// Cin = 1 first conv.  Block = 256 threads = 16 x-groups (4 px each) x 16 rows -> 64x16 output tile of
+// one (n,z) plane.  Input halo tile + all weights staged in smem; each thread keeps 4 px x 16 ch
+// accumulators and walks the taps with a sliding register window along x.
+// -------------------------------------------------------------------------------------------------
+constexpr int FT_W = 64, FT_H = 16, FPX = 4, FCG = 16;
+
+__global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ x, int N, int D, int H, int W,
+                                                         const float* __restrict__ w, const float* __restrict__ bias,
+                                                         int Co, int kd, int kh, int kw, int dil, int pad,
+                                                         float slope, __half* __restrict__ out, int out_ld, int Do,
+                                                         int Ho, int Wo, int CoPad) {
+  extern __shared__ float sm[];
+  const int tw = FT_W + (kw - 1) * dil, th = FT_H + (kh - 1) * dil;
+  float* s_in = sm;                       // [kd][th][tw]
+  float* s_w = sm + (size_t)kd * th * tw; // [kd*kh*kw][CoPad]
+  const int ntaps = kd * kh * kw;
+  const int plane = blockIdx.z;
+  const int n = plane / Do, z = plane - n * Do;
+  const int x0 = blockIdx.x * FT_W, y0 = blockIdx.y * FT_H;
+
+  for (int i = threadIdx.x; i < ntaps * CoPad; i += 256) {
+    const int t = i / CoPad, c = i - t * CoPad;
+    s_w[i] = (c < Co) ? w[(size_t)c * ntaps + t] : 0.f;
+  }
+  for (int i = threadIdx.x; i < kd * th * tw; i += 256) {
+    const int q = i / (th * tw), r = i - q * th * tw;
+    const int yy = r / tw, xx = r - yy * tw;
+    const int gz = z - pad * (kd > 1) + q * dil, gy = y0 - pad + yy, gx = x0 - pad + xx;
+    float v = 0.f;
+    if (gz >= 0 && gz < D && gy >= 0 && gy < H && gx >= 0 && gx < W)
+      v = x[(((size_t)n * D + gz) * H + gy) * W + gx];
+    s_in[i] = v;
+  }
+  __syncthreads();
+
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int lx = tx * FPX;
+  for (int cg = 0; cg < CoPad; cg += FCG) {
+    float acc[FPX][FCG];
+#pragma unroll
+    for (int pxi = 0; pxi < FPX; ++pxi)
+#pragma unroll
+      for (int c = 0; c < FCG; ++c) acc[pxi][c] = 0.f;
+    for (int q = 0; q < kd; ++q) {
+      for (int r = 0; r < kh; ++r) {
+        const float* row = s_in + ((size_t)q * th + ty + r * dil) * tw + lx;
+        const float* wr = s_w + (size_t)((q * kh + r) * kw) * CoPad + cg;
+        for (int s = 0; s < kw; ++s) {
+          float iv[FPX];
+#pragma unroll
+          for (int pxi = 0; pxi < FPX; ++pxi) iv[pxi] = row[pxi + s * dil];
+          const float4* w4 = reinterpret_cast<const float4*>(wr + (size_t)s * CoPad);
+#pragma unroll
+          for (int c4 = 0; c4 < FCG / 4; ++c4) {
+            const float4 wv = w4[c4];
+#pragma unroll
+            for (int pxi = 0; pxi < FPX; ++pxi) {
+              acc[pxi][c4 * 4 + 0] = fmaf(iv[pxi], wv.x, acc[pxi][c4 * 4 + 0]);
+              acc[pxi][c4 * 4 + 1] = fmaf(iv[pxi], wv.y, acc[pxi][c4 * 4 + 1]);
+              acc[pxi][c4 * 4 + 2] = fmaf(iv[pxi], wv.z, acc[pxi][c4 * 4 + 2]);
+              acc[pxi][c4 * 4 + 3] = fmaf(iv[pxi], wv.w, acc[pxi][c4 * 4 + 3]);
+            }
+          }
+        }
+      }
+    }
+    const int gy = y0 + ty;
+    if (gy < Ho) {
+#pragma unroll
+      for (int pxi = 0; pxi < FPX; ++pxi) {
+        const int gx = x0 + lx + pxi;
+        if (gx < Wo) {
+          __half* o = out + ((((size_t)n * Do + z) * Ho + gy) * Wo + gx) * out_ld + cg;
+          uint4 u[2];
+          __half2* h = reinterpret_cast<__half2*>(u);
+#pragma unroll
+          for (int c = 0; c < FCG; c += 2) {
+            const float b0 = (cg + c < Co && bias) ? bias[cg + c] : 0.f;
+            const float b1 = (cg + c + 1 < Co && bias) ? bias[cg + c + 1] : 0.f;
+            float v0 = act(acc[pxi][c] + b0, slope), v1 = act(acc[pxi][c + 1] + b1, slope);
+            if (cg + c >= Co) v0 = 0.f;
+            if (cg + c + 1 >= Co) v1 = 0.f;
+            h[c / 2] = __floats2half2_rn(v0, v1);
+          }
+          reinterpret_cast<uint4*>(o)[0] = u[0];
+          reinterpret_cast<uint4*>(o)[1] = u[1];
+        }
+      }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Cout = 1 tail conv: one thread per output pixel, 8-channel (16 B) vector loads.
+// -------------------------------------------------------------------------------------------------
+__global__ void conv_last_kernel(const __half* __restrict__ x, int N, int D, int H, int W, int C, int ld,
+                                 const float* __restrict__ w /*[taps][C]*/, float bias, int kd, int kh, int kw,
+                                 int dil, int pad, float oscale, float oshift, const float* __restrict__ stats,
+                                 float* __restrict__ out) {
+  const size_t total = (size_t)N * D * H * W;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int gx = idx % W;
+  size_t r = idx / W;
+  const int gy = r % H; r /= H;
+  const int gz = r % D;
+  const int n = r / D;
+  float acc = 0.f;
+  const int pz = (kd > 1) ? pad : 0;
+  for (int q = 0; q < kd; ++q) {
+    const int iz = gz - pz + q * dil;
+    if (iz < 0 || iz >= D) continue;
+    for (int rr = 0; rr < kh; ++rr) {
+      const int iy = gy - pad + rr * dil;
+      if (iy < 0 || iy >= H) continue;
+      for (int s = 0; s < kw; ++s) {
+        const int ix = gx - pad + s * dil;
+        if (ix < 0 || ix >= W) continue;
+        const __half* px = x + ((((size_t)n * D + iz) * H + iy) * W + ix) * ld;
+        const float* wt = w + (size_t)((q * kh + rr) * kw + s) * C;
+        for (int c = 0; c < C; c += 8) {
+          const uint4 u = *reinterpret_cast<const uint4*>(px + c);
+          const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(h[e]);
+            acc = fmaf(f.x, __ldg(wt + c + 2 * e), acc);
+            acc = fmaf(f.y, __ldg(wt + c + 2 * e + 1), acc);
+          }
+        }
+      }
+    }
+  }
+  float v = (acc + bias) * oscale + oshift;
+  if (stats) v = v * stats[1] + stats[0];
+  out[idx] = v;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Generic conv (validation / uncovered shapes): one thread per (output pixel, 8 output channels).
+// -------------------------------------------------------------------------------------------------
+__global__ void conv_generic_kernel(const __half* __restrict__ x0, int C0, int ld0, const __half* __restrict__ x1,
+                                    int C1, int ld1, int N, int D, int H, int W, const float* __restrict__ w,
+                                    const float* __restrict__ bias, int Co, int kd, int kh, int kw, int stride,
+                                    int dil, int pad, float slope, const __half* __restrict__ res, int res_ld,
+                                    int res_org, __half* __restrict__ out, int out_ld, int Do, int Ho, int Wo) {
+  const int cgs = (Co + 7) / 8;
+  const size_t total = (size_t)N * Do * Ho * Wo * cgs;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cg = idx % cgs;
+  size_t r = idx / cgs;
+  const int ox = r % Wo; r /= Wo;
+  const int oy = r % Ho; r /= Ho;
+  const int oz = r % Do;
+  const int n = r / Do;
+  const int Ci = C0 + C1, taps = kd * kh * kw;
+  const int pz = (kd > 1) ? pad : 0, sz = (kd > 1) ? stride : 1;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int q = 0; q < kd; ++q) {
+    const int iz = oz * sz - pz + q * dil;
+    if (iz < 0 || iz >= D) continue;
+    for (int rr = 0; rr < kh; ++rr) {
+      const int iy = oy * stride - pad + rr * dil;
+      if (iy < 0 || iy >= H) continue;
+      for (int s = 0; s < kw; ++s) {
+        const int ix = ox * stride - pad + s * dil;
+        if (ix < 0 || ix >= W) continue;
+        const size_t pix = (((size_t)n * D + iz) * H + iy) * W + ix;
+        const int t = (q * kh + rr) * kw + s;
+        for (int c = 0; c < Ci; ++c) {
+          const float v = (c < C0) ? __half2float(x0[pix * ld0 + c]) : __half2float(x1[pix * ld1 + (c - C0)]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int co = cg * 8 + j;
+            if (co < Co) acc[j] = fmaf(v, __ldg(w + ((size_t)co * Ci + c) * taps + t), acc[j]);
+          }
+        }
+      }
+    }
+  }
+  const size_t opix = (((size_t)n * Do + oz) * Ho + oy) * Wo + ox;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int co = cg * 8 + j;
+    if (co >= Co) break;
+    float v = acc[j] + (bias ? bias[co] : 0.f);
+    if (res) {
+      const size_t rp = (((size_t)n * D + (oz * sz + (kd > 1 ? res_org : 0))) * H + (oy * stride + res_org)) * W +
+                        (ox * stride + res_org);
+      v += __half2float(res[rp * res_ld + co]);
+    }
+    out[opix * out_ld + co] = __float2half_rn(act(v, slope));
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// 2x max pool (floor) and nearest upsample on fp16 NDHWC, 8-channel vectors.
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 hmax8(uint4 a, uint4 b) {
+  uint4 r;
+  __half2* ra = reinterpret_cast<__half2*>(&a);
+  __half2* rb = reinterpret_cast<__half2*>(&b);
+  __half2* rr = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) rr[e] = __hmax2(ra[e], rb[e]);
+  return r;
+}
+
+__global__ void maxpool2_kernel(const __half* __restrict__ x, int N, int D, int H, int W, int C, int ld, int dims,
+                                __half* __restrict__ out, int out_ld, int Do, int Ho, int Wo) {
+  const int cv = C / 8;
+  const size_t total = (size_t)N * Do * Ho * Wo * cv;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (idx % cv) * 8;
+  size_t r = idx / cv;
+  const int ox = r % Wo; r /= Wo;
+  const int oy = r % Ho; r /= Ho;
+  const int oz = r % Do;
+  const int n = r / Do;
+  const int nz = (dims == 3) ? 2 : 1;
+  uint4 m;
+  bool first = true;
+  for (int q = 0; q < nz; ++q)
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        const int iz = (dims == 3) ? oz * 2 + q : oz;
+        const uint4 v = *reinterpret_cast<const uint4*>(
+            x + ((((size_t)n * D + iz) * H + (oy * 2 + a)) * W + (ox * 2 + b)) * ld + c);
+        m = first ? v : hmax8(m, v);
+        first = false;
+      }
+  *reinterpret_cast<uint4*>(out + ((((size_t)n * Do + oz) * Ho + oy) * Wo + ox) * out_ld + c) = m;
+}
+
+// torch nearest: src = min(int(floorf(dst * (float)in / out)), in - 1)   (F.interpolate(size=...), ATen
+// UpSample.h nearest_neighbor_compute_source_index)
+__device__ __forceinline__ int nn_src(int dst, int in, int out) {
+  const float scale = (float)in / (float)out;
+  const int s = (int)floorf(dst * scale);
+  return s < in - 1 ? s : in - 1;
+}
+
+__global__ void upsample_kernel(const __half* __restrict__ x, int N, int D, int H, int W, int C, int ld, int Do,
+                                int Ho, int Wo, __half* __restrict__ out, int out_ld, int out_coff) {
+  const int cv = C / 8;
+  const size_t total = (size_t)N * Do * Ho * Wo * cv;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (idx % cv) * 8;
+  size_t r = idx / cv;
+  const int ox = r % Wo; r /= Wo;
+  const int oy = r % Ho; r /= Ho;
+  const int oz = r % Do;
+  const int n = r / Do;
+  const int iz = nn_src(oz, D, Do), iy = nn_src(oy, H, Ho), ix = nn_src(ox, W, Wo);
+  const uint4 v = *reinterpret_cast<const uint4*>(x + ((((size_t)n * D + iz) * H + iy) * W + ix) * ld + c);
+  *reinterpret_cast<uint4*>(out + ((((size_t)n * Do + oz) * Ho + oy) * Wo + ox) * out_ld + out_coff + c) = v;
+}
+
+// -------------------------------------------------------------------------------------------------
+// mean / std (fp64 accumulation) and affine (de)normalisation
+// -------------------------------------------------------------------------------------------------
+__global__ void zero2_kernel(double* w) { if (threadIdx.x < 2) w[threadIdx.x] = 0.0; }
+
+__global__ void sums_kernel(const float* __restrict__ x, long long n, double* __restrict__ work) {
+  double s = 0.0, ss = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double v = x[i];
+    s += v; ss += v * v;
+  }
+  __shared__ double sh[2][32];
+  for (int o = 16; o; o >>= 1) { s += __shfl_xor_sync(~0u, s, o); ss += __shfl_xor_sync(~0u, ss, o); }
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = ss; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? sh[0][threadIdx.x] : 0.0;
+    ss = threadIdx.x < (blockDim.x >> 5) ? sh[1][threadIdx.x] : 0.0;
+    for (int o = 16; o; o >>= 1) { s += __shfl_xor_sync(~0u, s, o); ss += __shfl_xor_sync(~0u, ss, o); }
+    if (threadIdx.x == 0) { atomicAdd(&work[0], s); atomicAdd(&work[1], ss); }
+  }
+}
+
+// second pass for the variance around the mean (numerically safe for large offsets, e.g. raw micrographs)
+__global__ void var_kernel(const float* __restrict__ x, long long n, double* __restrict__ work) {
+  const double mean = work[0] / (double)n;
+  double ss = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double d = (double)x[i] - mean;
+    ss += d * d;
+  }
+  __shared__ double sh[32];
+  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(~0u, ss, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    ss = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(~0u, ss, o);
+    if (threadIdx.x == 0) atomicAdd(&work[2], ss);
+  }
+}
+
+__global__ void finalize_kernel(const double* work, long long n, int unbiased, float* stats) {
+  const double mean = work[0] / (double)n;
+  const double var = work[2] / (double)(unbiased ? n - 1 : n);
+  stats[0] = (float)mean;
+  stats[1] = (float)sqrt(var);
+}
+
+__global__ void affine_kernel(const float* __restrict__ x, long long n, const float* __restrict__ stats, int inverse,
+                              float* __restrict__ y) {
+  const float mu = stats[0], sd = stats[1];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = inverse ? x[i] * sd + mu : (x[i] - mu) / sd;
+}
+
+__global__ void f32_to_f16_kernel(const float* __restrict__ x, long long n, __half* __restrict__ y) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = __float2half_rn(x[i]);
+}
+
+}  // namespace
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+#define HP(p) reinterpret_cast<__half*>(p)
+#define HCP(p) reinterpret_cast<const __half*>(p)
+
+extern "C" int tpz_conv_first(const float* x, int N, int D, int H, int W, const float* w, const float* bias, int Co,
+                              int kd, int kh, int kw, int dil, int pad, float neg_slope, int pool, tpz_half* out,
+                              int out_ld, void* stream) {
+  TPZ_CHECK(pool == 1, "tpz_conv_first: fused pooling not available (pool=%d)", pool);
+  TPZ_CHECK(out_ld % 16 == 0, "tpz_conv_first: out_ld=%d must be a multiple of 16", out_ld);
+  const int CoPad = out_ld;  // channels [Co, out_ld) are written as zeros (channel padding of the fp16 layout)
+  TPZ_CHECK(Co <= out_ld, "tpz_conv_first: Co=%d exceeds out_ld=%d", Co, out_ld);
+  const int Do = (kd > 1) ? D + 2 * pad - (kd - 1) * dil : D;
+  const int Ho = H + 2 * pad - (kh - 1) * dil, Wo = W + 2 * pad - (kw - 1) * dil;
+  TPZ_CHECK(Do > 0 && Ho > 0 && Wo > 0, "tpz_conv_first: empty output");
+  const int tw = FT_W + (kw - 1) * dil, th = FT_H + (kh - 1) * dil;
+  const size_t smem = ((size_t)kd * th * tw + (size_t)kd * kh * kw * CoPad) * sizeof(float);
+  TPZ_CHECK(smem <= 220 * 1024, "tpz_conv_first: filter too large for shared memory (%zu B)", smem);
+  TPZ_CUDA(cudaFuncSetAttribute(conv_first_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(tpz_div_up(Wo, FT_W), tpz_div_up(Ho, FT_H), N * Do);
+  conv_first_kernel<<<grid, 256, smem, ST(stream)>>>(x, N, D, H, W, w, bias, Co, kd, kh, kw, dil, pad, neg_slope,
+                                                     HP(out), out_ld, Do, Ho, Wo, CoPad);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tpz_conv_last(const tpz_half* x, int N, int D, int H, int W, int C, int ld, const float* w, float bias,
+                             int kd, int kh, int kw, int dil, int pad, float out_scale, float out_shift,
+                             const float* affine_stats, float* out, void* stream) {
+  TPZ_CHECK(C % 8 == 0 && ld % 8 == 0, "tpz_conv_last: C=%d / ld=%d must be multiples of 8", C, ld);
+  const size_t total = (size_t)N * D * H * W;
+  conv_last_kernel<<<tpz_div_up(total, 128), 128, 0, ST(stream)>>>(HCP(x), N, D, H, W, C, ld, w, bias, kd, kh, kw,
+                                                                   dil, pad, out_scale, out_shift, affine_stats, out);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tpz_conv_generic(const tpz_half* x0, int C0, int ld0, const tpz_half* x1, int C1, int ld1, int N, int D,
+                                int H, int W, const float* w, const float* bias, int Co, int kd, int kh, int kw,
+                                int stride, int dil, int pad, float neg_slope, const tpz_half* res, int res_ld,
+                                int res_org, tpz_half* out, int out_ld, int Do, int Ho, int Wo, void* stream) {
+  const size_t total = (size_t)N * Do * Ho * Wo * ((Co + 7) / 8);
+  conv_generic_kernel<<<tpz_div_up(total, 128), 128, 0, ST(stream)>>>(
+      HCP(x0), C0, ld0, HCP(x1), C1, ld1, N, D, H, W, w, bias, Co, kd, kh, kw, stride, dil, pad, neg_slope, HCP(res),
+      res_ld, res_org, HP(out), out_ld, Do, Ho, Wo);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tpz_maxpool2(const tpz_half* x, int N, int D, int H, int W, int C, int ld, int dims, tpz_half* out,
+                            int out_ld, void* stream) {
+  TPZ_CHECK(C % 8 == 0 && ld % 8 == 0 && out_ld % 8 == 0, "tpz_maxpool2: channel counts must be multiples of 8");
+  const int Do = dims == 3 ? D / 2 : D, Ho = H / 2, Wo = W / 2;
+  const size_t total = (size_t)N * Do * Ho * Wo * (C / 8);
+  if (total == 0) return 0;
+  maxpool2_kernel<<<tpz_div_up(total, 256), 256, 0, ST(stream)>>>(HCP(x), N, D, H, W, C, ld, dims, HP(out), out_ld,
+                                                                  Do, Ho, Wo);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tpz_upsample_nearest(const tpz_half* x, int N, int D, int H, int W, int C, int ld, int Do, int Ho,
+                                    int Wo, tpz_half* out, int out_ld, int out_coff, void* stream) {
+  TPZ_CHECK(C % 8 == 0 && ld % 8 == 0 && out_ld % 8 == 0 && out_coff % 8 == 0,
+            "tpz_upsample_nearest: channel counts must be multiples of 8");
+  const size_t total = (size_t)N * Do * Ho * Wo * (C / 8);
+  upsample_kernel<<<tpz_div_up(total, 256), 256, 0, ST(stream)>>>(HCP(x), N, D, H, W, C, ld, Do, Ho, Wo, HP(out),
+                                                                  out_ld, out_coff);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tpz_meanstd(const float* x, long long n, int unbiased, float* stats, double* work, void* stream) {
+  TPZ_CHECK(n > 1, "tpz_meanstd: need n > 1");
+  int grid = tpz_div_up(n, 256 * 8);
+  if (grid > 148 * 8) grid = 148 * 8;
+  zero2_kernel<<<1, 32, 0, ST(stream)>>>(work);
+  zero2_kernel<<<1, 32, 0, ST(stream)>>>(work + 2);
+  sums_kernel<<<grid, 256, 0, ST(stream)>>>(x, n, work);
+  var_kernel<<<grid, 256, 0, ST(stream)>>>(x, n, work);
+  finalize_kernel<<<1, 1, 0, ST(stream)>>>(work, n, unbiased, stats);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tpz_affine(const float* x, long long n, const float* stats, int inverse, float* y, void* stream) {
+  int grid = tpz_div_up(n, 256 * 4);
+  if (grid > 148 * 16) grid = 148 * 16;
+  affine_kernel<<<grid, 256, 0, ST(stream)>>>(x, n, stats, inverse, y);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tpz_f32_to_f16(const float* x, long long n, tpz_half* y, void* stream) {
+  int grid = tpz_div_up(n, 256 * 4);
+  if (grid > 148 * 16) grid = 148 * 16;
+  f32_to_f16_kernel<<<grid, 256, 0, ST(stream)>>>(x, n, HP(y));
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,146 @@
+"""Drop-in mirror of the denoising pipeline objects of topaz/denoise.py: Denoise (:245-332), Denoise3D
+(:336-377), denoise_image (:382-416).  Normalisation statistics, normalise / de-normalise and the network
+all run on the GPU; the only host synchronisation per call is the final device->host copy."""
+from __future__ import absolute_import, division, print_function
+
+import sys
+from typing import List, Union
+
+import numpy as np
+import torch
+
+from topaz_b200 import engine, ops
+from topaz_b200.denoising.models import load_model
+
+
+class Denoise():
+    ''' Object for micrograph denoising utilities (reference denoise.py:245-332). '''
+    def __init__(self, model: Union[torch.nn.Module, str], use_cuda=True, dims=2):
+        if isinstance(model, torch.nn.Module):
+            self.model = model
+        elif type(model) == str:
+            try:
+                self.model = load_model(model)
+            except NotImplementedError:
+                raise
+            except Exception:
+                raise ValueError('Unable to load model: ' + model)
+        else:
+            raise TypeError('Unrecognized model:' + str(model))
+        if not use_cuda:
+            raise RuntimeError('topaz_b200: Denoise requires use_cuda=True; this build has no CPU path')
+        self.model = self.model.cuda()
+        self.device = next(iter(self.model.parameters())).device
+        self.dims = dims
+        self.use_cuda = use_cuda
+
+    def __call__(self, input):
+        return self._denoise(input)
+
+    @torch.no_grad()
+    def _denoise_device(self, input: torch.Tensor) -> torch.Tensor:
+        """_denoise without the final host copy: returns the de-normalised prediction on the device."""
+        self.model.eval()
+        x = input.to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
+        stats = ops.meanstd(x, unbiased=True)            # torch .mean() / .std() (denoise.py:283)
+        xn = ops.affine(x, stats)                        # (x - mu) / std (denoise.py:284)
+        if xn.dim() == self.dims:
+            xn = xn[None, None]
+        elif xn.dim() == self.dims + 1:
+            xn = xn.unsqueeze(1)
+        pred = engine.unet_forward(self.model, xn, denorm_stats=stats)   # pred*std+mu fused (denoise.py:295)
+        return pred.squeeze()
+
+    @torch.no_grad()
+    def _denoise(self, input: Union[np.ndarray, torch.Tensor]) -> np.ndarray:
+        '''Call stored denoising model (reference denoise.py:274-296).'''
+        input = torch.from_numpy(input) if type(input) == np.ndarray else input
+        return self._denoise_device(input).cpu().numpy()
+
+    @torch.no_grad()
+    def denoise_patches(self, x: Union[np.ndarray, torch.Tensor], patch_size: int, padding: int = 128) -> np.ndarray:
+        ''' Denoise 2D micrograph patches (reference denoise.py:299-324).  The micrograph is uploaded once;
+        patches are cropped, denoised and pasted on the device, one download at the end.'''
+        x = torch.from_numpy(x) if type(x) == np.ndarray else x
+        xd = x.to(self.device, dtype=torch.float32, non_blocking=True)
+        y = torch.zeros_like(xd)
+        H, W = xd.shape[0], xd.shape[1]
+        for i in range(0, H, patch_size):
+            for j in range(0, W, patch_size):
+                si, ei = max(0, i - padding), min(H, i + patch_size + padding)
+                sj, ej = max(0, j - padding), min(W, j + patch_size + padding)
+                yij = self._denoise_device(xd[si:ei, sj:ej])
+                oi, oj = i - si, j - sj
+                y[i:i + patch_size, j:j + patch_size] = yij[oi:oi + patch_size, oj:oj + patch_size]
+        return y.cpu().numpy()
+
+    @torch.no_grad()
+    def denoise(self, x: Union[np.ndarray, torch.Tensor], patch_size=-1, padding=128):
+        s = patch_size + padding
+        use_patch = (patch_size > 0) and (s < x.shape[0] or s < x.shape[1])
+        return self.denoise_patches(x, patch_size, padding=padding) if use_patch else self._denoise(x)
+
+
+class Denoise3D(Denoise):
+    ''' Object for denoising tomograms (reference denoise.py:336-377). '''
+    def __init__(self, model, use_cuda=True, dims=3):
+        super().__init__(model, use_cuda=use_cuda, dims=dims)
+
+    @torch.no_grad()
+    def denoise(self, tomo: np.ndarray, patch_size: int = 96, padding: int = 48, batch_size: int = 1,
+                volume_num: int = 1, total_volumes: int = 1, verbose: bool = True,
+                patch_range=None) -> np.ndarray:
+        """``patch_range=(start, stop)`` restricts the work to a slice of the patch list (multi-GPU sharding);
+        voxels of other patches stay zero."""
+        denoised = np.zeros_like(tomo)
+        mu, std = tomo.mean(), tomo.std()
+        if patch_size < 1:
+            denoised[:] = Denoise._denoise(self, tomo)
+            return denoised
+        td = torch.from_numpy(tomo).to(self.device)
+        out_d = torch.zeros_like(td)
+        pz = [int(np.ceil(n / patch_size)) for n in tomo.shape]
+        total = int(np.prod(pz))
+        lo, hi = (0, total) if patch_range is None else patch_range
+        d = patch_size + 2 * padding
+        mu32, std32 = np.float32(mu), np.float32(std)
+        count = 0
+        for p in range(lo, hi):
+            i, j, k = (int(v) * patch_size for v in np.unravel_index(p, pz))
+            # zero-padded (p+2*pad)^3 crop (reference PatchDataset.__getitem__, datasets.py:426-468)
+            x = torch.zeros((d, d, d), dtype=torch.float32, device=self.device)
+            si, ei = max(0, i - padding), min(tomo.shape[0], i + patch_size + padding)
+            sj, ej = max(0, j - padding), min(tomo.shape[1], j + patch_size + padding)
+            sk, ek = max(0, k - padding), min(tomo.shape[2], k + patch_size + padding)
+            sic, sjc, skc = padding - i + si, padding - j + sj, padding - k + sk
+            x[sic:sic + ei - si, sjc:sjc + ej - sj, skc:skc + ek - sk] = td[si:ei, sj:ej, sk:ek]
+            xb = (x[None] - mu32) / std32                     # batch of 1 (DataLoader(batch_size=1))
+            y = self._denoise_device(xb) * std32 + mu32
+            dz, dy, dx = out_d[i:i + patch_size, j:j + patch_size, k:k + patch_size].shape
+            out_d[i:i + patch_size, j:j + patch_size, k:k + patch_size] = \
+                y[padding:padding + dz, padding:padding + dy, padding:padding + dx]
+            count += 1
+            if verbose:
+                print(f'# [{volume_num}/{total_volumes}] {round(count*100/max(1, hi-lo))}%', file=sys.stderr, end='\r')
+        if verbose:
+            print(' ' * 100, file=sys.stderr, end='\r')
+        denoised[:] = out_d.cpu().numpy()
+        return denoised
+
+
+def denoise_image(mic: np.ndarray, models: List[Denoise], lowpass=1, cutoff=0, gaus=None, inv_gaus=None,
+                  deconvolve=False, deconv_patch=1, patch_size=-1, padding=0, normalize=False, use_cuda=True) -> np.ndarray:
+    ''' reference denoise.py:382-416 with the optional lowpass / gaussian / deconvolve pre-filters
+    outside the hot path (off in every BASELINE config).'''
+    if lowpass > 1 or gaus is not None or inv_gaus is not None or deconvolve:
+        raise NotImplementedError('topaz_b200: lowpass/gaussian/deconvolve pre-filters are outside the B200 hot path')
+    mu, std = mic.mean(), mic.std()
+    x = (mic - mu) / std
+    if cutoff > 0:
+        x[(x < -cutoff) | (x > cutoff)] = 0
+    mic = sum([model.denoise(x, patch_size=patch_size, padding=padding) for model in models]) / len(models)
+    if normalize:
+        mic = (mic - mic.mean()) / mic.std()
+    else:
+        mic = std * mic + mu
+    return mic

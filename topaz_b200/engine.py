@@ -1,0 +1,356 @@
+"""Execution engine: turns the drop-in nn.Modules into sequences of sm_100a kernel launches.
+
+Dense ("filled") classifier forward and the U-Net denoiser forward run in fp16 operands / fp32 accumulation
+on the tcgen05 implicit-GEMM kernel (same 11-bit significand as the TF32 cuDNN path the reference uses on
+GPU).  The strided (training) classifier forward/backward lives in ``topaz_b200.train_engine``.
+
+Plans (packed weights, k-block tables) are cached per module and invalidated when any parameter/buffer
+changes (data_ptr or in-place version bump), or when fill()/unfill()/train()/eval() changes the geometry.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .ops import ConvPart
+
+
+def _rup(c: int, m: int = 32) -> int:
+    return (c + m - 1) // m * m
+
+
+def _slope_of(act) -> float:
+    if isinstance(act, nn.ReLU):
+        return 0.0
+    if isinstance(act, nn.LeakyReLU):
+        return float(act.negative_slope)
+    if isinstance(act, nn.PReLU):
+        if act.weight.numel() != 1:
+            raise NotImplementedError('topaz_b200: per-channel PReLU is not supported')
+        return float(act.weight.detach().reshape(-1)[0])
+    if isinstance(act, nn.Identity):
+        return 1.0
+    raise NotImplementedError(f'topaz_b200: unsupported activation {type(act).__name__}')
+
+
+def _bn_affine(bn: Optional[nn.Module], co: int):
+    """eval-mode BatchNorm as y = a*x + b (a = gamma/sqrt(var+eps), b = beta - a*mean)."""
+    if bn is None:
+        return None, None
+    a = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    b = bn.bias.detach().float() - a * bn.running_mean.detach().float()
+    return a.cpu(), b.cpu()
+
+
+def _state_key(module: nn.Module, extra=()):
+    ks = [(p.data_ptr(), p._version) for p in module.parameters()]
+    ks += [(b.data_ptr(), b._version) for b in module.buffers()]
+    return (tuple(ks), module.training) + tuple(extra)
+
+
+def _cached(module: nn.Module, name: str, key, build):
+    cache = module.__dict__.setdefault('_tpz_plans', {})
+    hit = cache.get(name)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    plan = build()
+    cache[name] = (key, plan)
+    return plan
+
+
+# ------------------------------------------------------------------------------------------------
+# classifier (ResNet8/16, conv31/63/127) dense forward
+# ------------------------------------------------------------------------------------------------
+def _feature_blocks(features) -> List[dict]:
+    """Describe the feature extractor's layers in their CURRENT geometry (after fill()/unfill())."""
+    from .model.features import resnet as R, basic as B
+    blocks = []
+    if isinstance(features, R.ResNet):
+        for mod in features.features.children():
+            if isinstance(mod, R.BasicConv):
+                blocks.append(dict(kind='conv', w=mod.conv.weight, b=mod.conv.bias, bn=getattr(mod, 'bn', None),
+                                   dil=mod.conv.dilation[0], stride=mod.conv.stride[0], slope=_slope_of(mod.act)))
+            elif isinstance(mod, R.ResidA):
+                blocks.append(dict(kind='resid', w0=mod.conv0.weight, b0=mod.conv0.bias, bn0=getattr(mod, 'bn0', None),
+                                   w1=mod.conv1.weight, b1=mod.conv1.bias, bn1=getattr(mod, 'bn1', None),
+                                   proj=mod.proj.weight if hasattr(mod, 'proj') else None,
+                                   d0=mod.conv0.dilation[0], d1=mod.conv1.dilation[0], stride=mod.conv1.stride[0],
+                                   slope0=_slope_of(mod.act0), slope1=_slope_of(mod.act1)))
+            elif isinstance(mod, nn.Dropout):
+                if features.training and mod.p > 0:
+                    raise NotImplementedError('topaz_b200: dropout in training mode is not supported')
+            else:
+                raise NotImplementedError(f'topaz_b200: unsupported ResNet child {type(mod).__name__}')
+    elif isinstance(features, B.BasicConv):
+        mods = list(features.features.children())
+        i = 0
+        while i < len(mods):
+            conv = mods[i]; i += 1
+            if isinstance(conv, nn.Dropout):
+                continue
+            assert isinstance(conv, (nn.Conv2d, nn.Conv3d)), type(conv)
+            bn = None
+            if i < len(mods) and isinstance(mods[i], (nn.BatchNorm2d, nn.BatchNorm3d)):
+                bn = mods[i]; i += 1
+            act = mods[i]; i += 1
+            blocks.append(dict(kind='conv', w=conv.weight, b=conv.bias, bn=bn, dil=conv.dilation[0],
+                               stride=conv.stride[0], slope=_slope_of(act)))
+    else:
+        raise NotImplementedError(f'topaz_b200: unsupported feature extractor {type(features).__name__}')
+    return blocks
+
+
+def is_filled(features) -> bool:
+    return bool(getattr(features, 'pad', False) or getattr(features, 'filled', False))
+
+
+def _build_dense_plan(features, classifier: Optional[nn.Module], device):
+    if getattr(features, 'dims', 2) != 2:
+        raise NotImplementedError('topaz_b200: 3-D classifiers are outside the B200 hot path')
+    blocks = _feature_blocks(features)
+    if features.training and any(b.get('bn') is not None or b.get('bn0') is not None for b in blocks):
+        raise NotImplementedError('topaz_b200: dense forward with BatchNorm requires eval() mode')
+    steps = []
+    first = blocks[0]
+    assert first['kind'] == 'conv' and first['w'].shape[1] == 1, 'first layer must be a Cin=1 conv'
+    if any(b['stride'] != 1 for b in blocks):
+        raise RuntimeError('topaz_b200: dense plan requested on an unfilled (strided) model')
+    a, sh = _bn_affine(first['bn'], first['w'].shape[0])
+    w = first['w'].detach().float().cpu()
+    b = first['b'].detach().float().cpu() if first['b'] is not None else torch.zeros(w.shape[0])
+    if a is not None:
+        w = w * a.view(-1, 1, 1, 1); b = b * a + sh
+    c_real = w.shape[0]
+    steps.append(dict(op='first', w=w[:, 0][:, None].contiguous().to(device), b=b.to(device), dil=first['dil'],
+                      pad=features.width // 2, slope=first['slope'], out_ld=_rup(c_real)))
+    c_store = _rup(c_real)
+    nblk = len(blocks)
+    for bi, blk in enumerate(blocks[1:], 1):
+        last = (bi == nblk - 1)
+        if blk['kind'] == 'conv':
+            w = blk['w']; co = w.shape[0]
+            a, sh = _bn_affine(blk['bn'], co)
+            bias = blk['b'].detach().float().cpu() if blk['b'] is not None else torch.zeros(co)
+            if a is not None:
+                bias = bias * a + sh
+            fuse = last and classifier is not None
+            plan = ops.pack_tc_conv([ConvPart(w, c_store, blk['dil'])], bias, _rup(co), blk['slope'], device,
+                                    out_scale=a,
+                                    dot_w=classifier.weight if fuse else None,
+                                    dot_b=float(classifier.bias.detach()[0]) if fuse else 0.0)
+            k = w.shape[-1]
+            steps.append(dict(op='tc', plan=plan, shrink=(k - 1) * blk['dil'], src='cur', dot=fuse, save_in=False))
+            c_store = _rup(co)
+        else:
+            w0, w1 = blk['w0'], blk['w1']
+            ch, co = w0.shape[0], w1.shape[0]
+            a0, s0 = _bn_affine(blk['bn0'], ch)
+            b0 = blk['b0'].detach().float().cpu() if blk['b0'] is not None else torch.zeros(ch)
+            if a0 is not None:
+                b0 = b0 * a0 + s0
+            p0 = ops.pack_tc_conv([ConvPart(w0, c_store, blk['d0'])], b0, _rup(ch), blk['slope0'], device, out_scale=a0)
+            steps.append(dict(op='tc', plan=p0, shrink=2 * blk['d0'], src='cur', dot=False, save_in=True))
+            a1, s1 = _bn_affine(blk['bn1'], co)
+            b1 = blk['b1'].detach().float().cpu() if blk['b1'] is not None else torch.zeros(co)
+            if a1 is not None:
+                b1 = b1 * a1 + s1
+            edge = blk['d0'] + blk['d1']
+            parts = [ConvPart(w1, _rup(ch), blk['d1'])]
+            if blk['proj'] is not None:
+                parts.append(ConvPart(blk['proj'], c_store, 1, (edge, edge, 0)))
+                p1 = ops.pack_tc_conv(parts, b1, _rup(co), blk['slope1'], device, out_scale=a1)
+                steps.append(dict(op='tc', plan=p1, shrink=2 * blk['d1'], src='cur+saved', dot=False, save_in=False))
+            else:
+                p1 = ops.pack_tc_conv(parts, b1, _rup(co), blk['slope1'], device, out_scale=a1, res_scale=a1)
+                steps.append(dict(op='tc', plan=p1, shrink=2 * blk['d1'], src='cur', res=True, edge=edge, dot=False,
+                                  save_in=False))
+            c_store = _rup(co)
+    return dict(steps=steps, c_out=blocks[-1]['w'].shape[0] if blocks[-1]['kind'] == 'conv' else blocks[-1]['w1'].shape[0])
+
+
+def _run_dense(plan, x: torch.Tensor, want_features: bool):
+    """x: fp32 [B, H, W] contiguous on device.  Returns fp32 [B,H,W] logits (dot fused) or fp16 NDHWC features."""
+    B, H, W = x.shape
+    cur = None
+    saved = None
+    out = None
+    for st in plan['steps']:
+        if st['op'] == 'first':
+            cur = ops.conv_first(x.view(B, 1, H, W), st['w'], st['b'], st['dil'], st['pad'], st['slope'], st['out_ld'])
+            continue
+        p = st['plan']
+        N, D, Hc, Wc, _ = cur.shape
+        Ho, Wo = Hc - st['shrink'], Wc - st['shrink']
+        if st['save_in']:
+            saved = cur
+        srcs = [cur, saved] if st['src'] == 'cur+saved' else [cur]
+        res = saved if st.get('res') else None
+        res_org = (st['edge'], st['edge'], 0) if st.get('res') else (0, 0, 0)
+        if st['dot'] and not want_features:
+            out = torch.empty((N, D, Ho, Wo), dtype=torch.float32, device=x.device)
+            ops.tc_conv(p, srcs, (N, D, Ho, Wo), out=None, res=res, res_org=res_org, dot_out=out)
+            cur = None
+        else:
+            nxt = torch.empty((N, D, Ho, Wo, p.Co), dtype=torch.float16, device=x.device)
+            ops.tc_conv(p, srcs, (N, D, Ho, Wo), out=nxt, res=res, res_org=res_org)
+            cur = nxt
+    return out if out is not None else cur
+
+
+def _as_image_batch(x: torch.Tensor, dims: int) -> torch.Tensor:
+    ops.require_cuda(x, 'classifier input')
+    if x.dim() < dims + 2:
+        x = x.unsqueeze(1)
+    if x.shape[1] != 1:
+        raise ValueError('topaz_b200: expected a single input channel')
+    return x[:, 0].contiguous().float()
+
+
+def classifier_forward(model, x: torch.Tensor) -> torch.Tensor:
+    """LinearClassifier.forward (reference classifier.py:48-66)."""
+    feats = model.features
+    if not is_filled(feats):
+        from . import train_engine
+        return train_engine.classifier_forward(model, x)
+    xi = _as_image_batch(x, 2)
+    key = _state_key(model, ('dense', str(xi.device)))
+    plan = _cached(model, 'dense_cls', key, lambda: _build_dense_plan(feats, model.classifier, xi.device))
+    y = _run_dense(plan, xi, want_features=False)      # [B, 1(D), H, W]
+    return y.view(xi.shape[0], 1, y.shape[2], y.shape[3])
+
+
+def features_forward(features, x: torch.Tensor) -> torch.Tensor:
+    """ResNet.forward / BasicConv.forward without the classifier head: NCHW fp32 feature map."""
+    if not is_filled(features):
+        from . import train_engine
+        return train_engine.features_forward(features, x)
+    xi = _as_image_batch(x, 2)
+    key = _state_key(features, ('dense_feat', str(xi.device)))
+    plan = _cached(features, 'dense_feat', key, lambda: _build_dense_plan(features, None, xi.device))
+    z = _run_dense(plan, xi, want_features=True)        # [B,1,H,W,Cstore] fp16
+    return z[:, 0, :, :, :plan['c_out']].permute(0, 3, 1, 2).float().contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# U-Net denoisers (UDenoiseNet / UDenoiseNet3D / UDenoiseNetSmall)
+# ------------------------------------------------------------------------------------------------
+def _conv_of(seq, idx):
+    c = seq[idx]
+    assert isinstance(c, (nn.Conv2d, nn.Conv3d))
+    return c
+
+
+def _build_unet_plan(model, device):
+    enc = [getattr(model, f'enc{i}') for i in range(1, 10) if hasattr(model, f'enc{i}')]
+    ndec = len(enc) - 1
+    dec = {l: getattr(model, f'dec{l}') for l in range(ndec, 0, -1)}
+    dims = 3 if isinstance(enc[0][0], nn.Conv3d) else 2
+    nf = enc[0][0].weight.shape[0]
+    slope = 0.1
+
+    def same_org(k):
+        p = k // 2
+        return (-p, -p, -p if dims == 3 else 0)
+
+    plan = dict(dims=dims, nf=nf, nenc=len(enc))
+    c1 = enc[0][0]
+    plan['first'] = dict(w=c1.weight.detach().float().reshape((nf,) + ((1,) if dims == 2 else ()) + tuple(c1.weight.shape[2:])).contiguous().to(device),
+                         b=c1.bias.detach().float().to(device), pad=c1.weight.shape[-1] // 2, out_ld=_rup(nf),
+                         pool=len(enc[0]) > 2)
+    plan['enc'] = []
+    for e in enc[1:]:
+        c = e[0]
+        k = c.weight.shape[-1]
+        p = ops.pack_tc_conv([ConvPart(c.weight, _rup(nf), 1, same_org(k))], c.bias, _rup(c.weight.shape[0]), slope, device)
+        plan['enc'].append(dict(plan=p, pool=len(e) > 2))
+    plan['dec'] = {}
+    up_c = nf
+    for l in range(ndec, 0, -1):
+        d = dec[l]
+        ca, cb = d[0], d[2]
+        k = ca.weight.shape[-1]
+        if l > 1:
+            skip_c = nf
+            parts = [ConvPart(ca.weight[:, :up_c], _rup(up_c), 1, same_org(k)),
+                     ConvPart(ca.weight[:, up_c:], _rup(skip_c), 1, same_org(k))]
+            pa = ops.pack_tc_conv(parts, ca.bias, _rup(ca.weight.shape[0]), slope, device)
+            pb = ops.pack_tc_conv([ConvPart(cb.weight, _rup(ca.weight.shape[0]), 1, same_org(cb.weight.shape[-1]))],
+                                  cb.bias, _rup(cb.weight.shape[0]), slope, device)
+            plan['dec'][l] = dict(a=pa, b=pb)
+            up_c = cb.weight.shape[0]
+        else:
+            # dec1: [upsampled (up_c ch), raw image (1 ch)] -> conv,lrelu,conv,lrelu,conv
+            ntap = k ** dims
+            wraw = ca.weight[:, up_c].reshape(ca.weight.shape[0], ntap)         # [Co, taps]
+            raw_part = ConvPart(wraw.reshape(wraw.shape[0], ntap, 1, 1, 1), _rup(ntap), 1, (0, 0, 0))
+            parts = [ConvPart(ca.weight[:, :up_c], _rup(up_c), 1, same_org(k)), raw_part]
+            pa = ops.pack_tc_conv(parts, ca.bias, _rup(ca.weight.shape[0]), slope, device)
+            onehot = torch.eye(ntap, dtype=torch.float32).reshape((ntap,) + ((1,) if dims == 2 else ()) + (k,) * dims)
+            pb = ops.pack_tc_conv([ConvPart(cb.weight, _rup(ca.weight.shape[0]), 1, same_org(cb.weight.shape[-1]))],
+                                  cb.bias, _rup(cb.weight.shape[0]), slope, device)
+            cc = d[4]
+            kl = cc.weight.shape[-1]
+            cin = cc.weight.shape[1]
+            wl = torch.zeros((kl ** dims, _rup(cin)), dtype=torch.float32)
+            wl[:, :cin] = cc.weight.detach().float().cpu()[0].reshape(cin, -1).t()
+            plan['dec'][1] = dict(a=pa, b=pb, onehot=onehot.contiguous().to(device), k=k, ntap_store=_rup(ntap),
+                                  last_w=wl.contiguous().to(device), last_b=float(cc.bias.detach()[0]),
+                                  last_k=(kl if dims == 3 else 1, kl, kl), last_pad=kl // 2, last_c=cin)
+    return plan
+
+
+def unet_forward(model, x: torch.Tensor, denorm_stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """UDenoiseNet(3D).forward (reference denoising/models.py:130-175, 508-564).
+    x: fp32 [N,1,(D),H,W] on device.  If ``denorm_stats`` (device float[2]) is given the output is
+    de-normalised (y*std+mean) inside the last kernel (denoise.py:295)."""
+    ops.require_cuda(x, 'denoiser input')
+    key = _state_key(model, ('unet', str(x.device)))
+    plan = _cached(model, 'unet', key, lambda: _build_unet_plan(model, x.device))
+    dims = plan['dims']
+    if x.dim() != dims + 2 or x.shape[1] != 1:
+        raise ValueError(f'topaz_b200: expected input [N,1,{"D,H,W" if dims == 3 else "H,W"}], got {tuple(x.shape)}')
+    xi = x[:, 0].contiguous().float()
+    if dims == 2:
+        xi = xi[:, None]                                  # [N, 1, H, W]
+    f = plan['first']
+    h = ops.conv_first(xi, f['w'], f['b'], 1, f['pad'], 0.1, f['out_ld'])
+    skips = []
+    if f['pool']:
+        h = ops.maxpool2(h, dims)
+    skips.append(h)
+    for e in plan['enc']:
+        N, D, H, W, _ = h.shape
+        o = torch.empty((N, D, H, W, e['plan'].Co), dtype=torch.float16, device=x.device)
+        ops.tc_conv(e['plan'], [h], (N, D, H, W), out=o)
+        h = ops.maxpool2(o, dims) if e['pool'] else o
+        if e['pool']:
+            skips.append(h)
+    # skips = [p1, ..., p_{n-1}]; decoder level l joins p_{l-1} (level 1 joins the raw image)
+    ndec = plan['nenc'] - 1
+    for l in range(ndec, 0, -1):
+        d = plan['dec'][l]
+        if l > 1:
+            skip = skips[l - 2]
+            N, D, H, W, _ = skip.shape
+            up = ops.upsample_nearest(h, (D, H, W))
+            o = torch.empty((N, D, H, W, d['a'].Co), dtype=torch.float16, device=x.device)
+            ops.tc_conv(d['a'], [up, skip], (N, D, H, W), out=o)
+            o2 = torch.empty((N, D, H, W, d['b'].Co), dtype=torch.float16, device=x.device)
+            ops.tc_conv(d['b'], [o], (N, D, H, W), out=o2)
+            h = o2
+        else:
+            N, D, H, W = xi.shape
+            up = ops.upsample_nearest(h, (D, H, W))
+            raw = ops.conv_first(xi, d['onehot'], None, 1, d['k'] // 2, 1.0, d['ntap_store'])
+            o = torch.empty((N, D, H, W, d['a'].Co), dtype=torch.float16, device=x.device)
+            ops.tc_conv(d['a'], [up, raw], (N, D, H, W), out=o)
+            o2 = torch.empty((N, D, H, W, d['b'].Co), dtype=torch.float16, device=x.device)
+            ops.tc_conv(d['b'], [o], (N, D, H, W), out=o2)
+            y = ops.conv_last(o2, d['last_c'], d['last_w'], d['last_b'], d['last_k'], 1, d['last_pad'],
+                              stats=denorm_stats)
+    if dims == 2:
+        return y.view(y.shape[0], 1, y.shape[2], y.shape[3])
+    return y.view(y.shape[0], 1, y.shape[1], y.shape[2], y.shape[3])

@@ -1,0 +1,233 @@
+"""Thin Python wrappers over the C ABI.  torch tensors are containers only (device memory + streams);
+every arithmetic op on the hot path is a kernel from libtopaz_b200.so.  Activations are channels-last fp16
+tensors of shape [N, D, H, W, C] (2-D: D == 1)."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import TcKBlock, TpzTcConvArgs, check
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f'topaz_b200: {what} must live on a CUDA device; this build has no CPU path')
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core conv plans
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class ConvPart:
+    """One input source of a conv: weights [Co, Ci_real, kd, kh, kw] (fp32 torch, any device)."""
+    w: torch.Tensor
+    c_store: int                 # stored channels of the source tensor (>= Ci_real, multiple of KC)
+    dil: int = 1
+    org: Tuple[int, int, int] = (0, 0, 0)   # (x, y, z) offset of tap 0 relative to the output pixel
+
+
+@dataclass
+class TcConvPlan:
+    KC: int
+    Co: int                      # stored output channels (multiple of 16)
+    kblocks: List[Tuple[int, int, int, int, int]]   # (dx, dy, dz, c0, src)
+    orgs: List[Tuple[int, int, int]]
+    c_stores: List[int]
+    weights: torch.Tensor        # [nkb, Co, KC] fp16 (device)
+    bias: torch.Tensor           # [Co] fp32 (device)
+    neg_slope: float
+    dot_w: Optional[torch.Tensor] = None
+    dot_b: float = 0.0
+    res_scale: Optional[torch.Tensor] = None
+    TW: int = 16
+    TH: int = 8
+
+
+def pack_tc_conv(parts: Sequence[ConvPart], bias: Optional[torch.Tensor], co_store: int, neg_slope: float,
+                 device, KC: Optional[int] = None, dot_w=None, dot_b: float = 0.0, res_scale=None,
+                 out_scale: Optional[torch.Tensor] = None) -> TcConvPlan:
+    """Repack OIHW fp32 weights into the kernel's [k-block][Co][KC] fp16 layout.
+
+    k-blocks are ordered (source, tap, chunk); all-zero blocks (channel padding) are dropped.
+    ``out_scale`` ([Co_real]) multiplies the weight rows (BN eval-mode folding)."""
+    if KC is None:
+        KC = 64 if all(p.c_store % 64 == 0 for p in parts) else 32
+    co_real = parts[0].w.shape[0]
+    assert co_store % 16 == 0 and co_store >= co_real
+    kbs, blocks = [], []
+    for si, p in enumerate(parts):
+        assert p.c_store % KC == 0, (p.c_store, KC)
+        w = p.w.detach().to(torch.float32).cpu()
+        if w.dim() == 4:
+            w = w[:, :, None]
+        if out_scale is not None:
+            w = w * out_scale.detach().cpu().view(-1, 1, 1, 1, 1)
+        co, ci, kd, kh, kw = w.shape
+        wp = torch.zeros((co_store, p.c_store, kd, kh, kw), dtype=torch.float32)
+        wp[:co, :ci] = w
+        for q in range(kd):
+            for r in range(kh):
+                for s in range(kw):
+                    for c0 in range(0, p.c_store, KC):
+                        blk = wp[:, c0:c0 + KC, q, r, s]
+                        if not bool(blk.any()):
+                            continue
+                        kbs.append((s * p.dil, r * p.dil, q * p.dil, c0, si))
+                        blocks.append(blk)
+    if not blocks:      # degenerate all-zero conv: keep one block so the kernel has work
+        kbs.append((0, 0, 0, 0, 0)); blocks.append(torch.zeros((co_store, KC)))
+    if len(kbs) > _lib.TPZ_TC_MAX_KB:
+        raise RuntimeError(f'topaz_b200: conv needs {len(kbs)} k-blocks (max {_lib.TPZ_TC_MAX_KB})')
+    wt = torch.stack(blocks).to(torch.float16).contiguous().to(device)
+    b = torch.zeros(co_store, dtype=torch.float32)
+    if bias is not None:
+        b[:co_real] = bias.detach().to(torch.float32).cpu()
+    dw = None
+    if dot_w is not None:
+        dw = torch.zeros(co_store, dtype=torch.float32)
+        dw[:co_real] = dot_w.detach().to(torch.float32).cpu().reshape(-1)
+        dw = dw.to(device)
+    rs = None
+    if res_scale is not None:
+        rs = torch.ones(co_store, dtype=torch.float32)
+        rs[:co_real] = res_scale.detach().to(torch.float32).cpu()
+        rs = rs.to(device)
+    return TcConvPlan(KC=KC, Co=co_store, kblocks=kbs, orgs=[tuple(p.org) for p in parts],
+                      c_stores=[p.c_store for p in parts], weights=wt, bias=b.to(device),
+                      neg_slope=float(neg_slope), dot_w=dw, dot_b=float(dot_b), res_scale=rs)
+
+
+def fill_tc_args(plan: TcConvPlan, srcs: Sequence[torch.Tensor], out_shape: Tuple[int, int, int, int],
+                 out: Optional[torch.Tensor], res: Optional[torch.Tensor] = None,
+                 res_org: Tuple[int, int, int] = (0, 0, 0), dot_out: Optional[torch.Tensor] = None,
+                 out_coff: int = 0) -> TpzTcConvArgs:
+    a = TpzTcConvArgs()
+    a.nsrc = len(srcs)
+    for i, t in enumerate(srcs):
+        N, D, H, W, ld = t.shape
+        s = a.src[i]
+        s.ptr = t.data_ptr(); s.N, s.D, s.H, s.W = N, D, H, W
+        s.C = plan.c_stores[i]; s.ld = ld
+        for j in range(3):
+            s.org[j] = plan.orgs[i][j]
+    a.weights = plan.weights.data_ptr()
+    a.KC = plan.KC
+    a.nkb = len(plan.kblocks)
+    for i, (dx, dy, dz, c0, si) in enumerate(plan.kblocks):
+        k = a.kb[i]
+        k.dx, k.dy, k.dz, k.c0, k.src = dx, dy, dz, c0, si
+    a.N, a.Do, a.Ho, a.Wo = out_shape
+    a.Co = plan.Co
+    a.TW, a.TH = plan.TW, plan.TH
+    a.bias = plan.bias.data_ptr()
+    a.neg_slope = plan.neg_slope
+    if res is not None:
+        a.res = res.data_ptr(); a.res_ld = res.shape[4]
+        a.res_D, a.res_H, a.res_W = res.shape[1], res.shape[2], res.shape[3]
+        for j in range(3):
+            a.res_org[j] = res_org[j]
+        if plan.res_scale is not None:
+            a.res_scale = plan.res_scale.data_ptr()
+    if out is not None:
+        a.out = out.data_ptr(); a.out_ld = out.shape[4]; a.out_coff = out_coff
+    if dot_out is not None:
+        a.dot_w = plan.dot_w.data_ptr(); a.dot_b = plan.dot_b; a.dot_out = dot_out.data_ptr()
+    return a
+
+
+def tc_conv(plan: TcConvPlan, srcs, out_shape, out=None, res=None, res_org=(0, 0, 0), dot_out=None, out_coff=0):
+    a = fill_tc_args(plan, srcs, out_shape, out, res, res_org, dot_out, out_coff)
+    check(_lib.lib().tpz_tc_conv(C.byref(a), _stream()))
+
+
+# ------------------------------------------------------------------------------------------------
+# direct kernels
+# ------------------------------------------------------------------------------------------------
+def conv_first(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], dil: int, pad: int,
+               neg_slope: float, out_ld: int) -> torch.Tensor:
+    """x: fp32 [N, D, H, W]; w: fp32 [Co, kd, kh, kw] (device).  Returns fp16 [N, Do, Ho, Wo, out_ld]."""
+    N, D, H, W = x.shape
+    Co, kd, kh, kw = w.shape
+    Do = D + 2 * pad - (kd - 1) * dil if kd > 1 else D
+    Ho, Wo = H + 2 * pad - (kh - 1) * dil, W + 2 * pad - (kw - 1) * dil
+    out = torch.empty((N, Do, Ho, Wo, out_ld), dtype=torch.float16, device=x.device)
+    check(_lib.lib().tpz_conv_first(_ptr(x), N, D, H, W, _ptr(w), _ptr(bias), Co, kd, kh, kw, dil, pad,
+                                    float(neg_slope), 1, _ptr(out), out_ld, _stream()))
+    return out
+
+
+def conv_last(x: torch.Tensor, c_real: int, w: torch.Tensor, bias: float, kdhw, dil: int, pad: int,
+              stats: Optional[torch.Tensor] = None, out_scale: float = 1.0, out_shift: float = 0.0) -> torch.Tensor:
+    """x: fp16 [N,D,H,W,ld]; w: fp32 [taps, C] (device) with C = c_real rounded up to 8. Returns fp32 [N,D,H,W]."""
+    N, D, H, W, ld = x.shape
+    kd, kh, kw = kdhw
+    out = torch.empty((N, D, H, W), dtype=torch.float32, device=x.device)
+    check(_lib.lib().tpz_conv_last(_ptr(x), N, D, H, W, w.shape[1], ld, _ptr(w), float(bias), kd, kh, kw, dil, pad,
+                                   float(out_scale), float(out_shift), _ptr(stats), _ptr(out), _stream()))
+    return out
+
+
+def conv_generic(x0, c0, x1, c1, w, bias, stride, dil, pad, neg_slope, out_ld, res=None, res_org=0):
+    """Validation conv: x0/x1 fp16 NDHWC (x1 optional), w fp32 [Co, C0+C1, kd, kh, kw] device."""
+    N, D, H, W, ld0 = x0.shape
+    Co, Ci, kd, kh, kw = w.shape
+    assert Ci == c0 + c1
+    def osz(n, k, three):
+        return (n + 2 * pad - (k - 1) * dil - 1) // stride + 1 if three else n
+    Do = osz(D, kd, kd > 1); Ho = osz(H, kh, True); Wo = osz(W, kw, True)
+    out = torch.zeros((N, Do, Ho, Wo, out_ld), dtype=torch.float16, device=x0.device)
+    check(_lib.lib().tpz_conv_generic(_ptr(x0), c0, ld0, _ptr(x1), c1, x1.shape[4] if x1 is not None else 0,
+                                      N, D, H, W, _ptr(w), _ptr(bias), Co, kd, kh, kw, stride, dil, pad,
+                                      float(neg_slope), _ptr(res), res.shape[4] if res is not None else 0, res_org,
+                                      _ptr(out), out_ld, Do, Ho, Wo, _stream()))
+    return out
+
+
+def maxpool2(x: torch.Tensor, dims: int) -> torch.Tensor:
+    N, D, H, W, ld = x.shape
+    Do = D // 2 if dims == 3 else D
+    out = torch.empty((N, Do, H // 2, W // 2, ld), dtype=torch.float16, device=x.device)
+    check(_lib.lib().tpz_maxpool2(_ptr(x), N, D, H, W, ld, ld, dims, _ptr(out), ld, _stream()))
+    return out
+
+
+def upsample_nearest(x: torch.Tensor, size: Tuple[int, int, int]) -> torch.Tensor:
+    N, D, H, W, ld = x.shape
+    Do, Ho, Wo = size
+    out = torch.empty((N, Do, Ho, Wo, ld), dtype=torch.float16, device=x.device)
+    check(_lib.lib().tpz_upsample_nearest(_ptr(x), N, D, H, W, ld, ld, Do, Ho, Wo, _ptr(out), ld, 0, _stream()))
+    return out
+
+
+def meanstd(x: torch.Tensor, unbiased: bool) -> torch.Tensor:
+    """Device float[2] = (mean, std) of a contiguous fp32 tensor; no host synchronisation."""
+    stats = torch.empty(2, dtype=torch.float32, device=x.device)
+    work = torch.empty(4, dtype=torch.float64, device=x.device)
+    check(_lib.lib().tpz_meanstd(_ptr(x), x.numel(), int(unbiased), _ptr(stats), _ptr(work), _stream()))
+    return stats
+
+
+def affine(x: torch.Tensor, stats: torch.Tensor, inverse: bool = False, out: Optional[torch.Tensor] = None):
+    y = torch.empty_like(x) if out is None else out
+    check(_lib.lib().tpz_affine(_ptr(x), x.numel(), _ptr(stats), int(inverse), _ptr(y), _stream()))
+    return y
+
+
+def lab_umma(A: torch.Tensor, B: torch.Tensor, shift: int, sbo_rows: int, base_off_mode: int) -> torch.Tensor:
+    D = torch.zeros((128, B.shape[0]), dtype=torch.float32, device=A.device)
+    check(_lib.lib().tpz_lab_umma(_ptr(A), A.shape[0], _ptr(B), B.shape[0], shift, sbo_rows, base_off_mode,
+                                  _ptr(D), _stream()))
+    return D
