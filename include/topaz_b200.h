@@ -39,6 +39,7 @@ typedef struct {
   const tpz_half* ptr; /* [N][D][H][W][ld] fp16 */
   int N, D, H, W, C, ld;
   int org[3];          /* (x,y,z) offset added to the output coordinate: -padding or +crop */
+  int kw, kh;          /* in-plane tap grid of this source (taps at multiples of `lattice`)  */
 } TpzTcSrc;
 
 typedef struct {
@@ -49,7 +50,8 @@ typedef struct {
   int nkb;
   TcKBlock kb[TPZ_TC_MAX_KB];
   int N, Do, Ho, Wo, Co;   /* output geometry */
-  int TW, TH;              /* pixel tile, TW*TH == 128, TW % 8 == 0 */
+  int TW, TH;              /* pixel tile of the per-tap kernel, TW*TH == 128, TW % 8 == 0 */
+  int lattice;             /* in-plane dilation shared by all taps (halo-resident kernel); 0 = per-tap kernel only */
   const float* bias;       /* [Co] or NULL */
   float neg_slope;         /* activation: v>0 ? v : v*neg_slope (0 = ReLU, 1 = linear, 0.1 = LeakyReLU) */
   const tpz_half* res;     /* optional residual, added before the activation */
@@ -62,7 +64,10 @@ typedef struct {
   float* dot_out;          /* [N][Do][Ho][Wo] fp32 or NULL */
 } TpzTcConvArgs;
 
-int tpz_tc_conv(const TpzTcConvArgs* host_args, void* stream);
+int tpz_tc_conv(const TpzTcConvArgs* host_args, void* stream);   /* dispatches: halo-resident kernel when
+                                                                     eligible, else the per-tap kernel   */
+int tpz_tc_conv_v1(const TpzTcConvArgs* host_args, void* stream);/* per-tap TMA loads (one A tile per k-block) */
+int tpz_tc_conv_v2(const TpzTcConvArgs* host_args, void* stream);/* halo-resident A tile + poly-phase lattice  */
 
 /* ---- direct (SIMT) convolutions for the thin ends and for validation ----
  * tpz_conv_first: Cin = 1 conv from a dense fp32 image, fp32 math, fused bias + activation, fp16 NDHWC out.
@@ -101,7 +106,8 @@ int tpz_affine(const float* x, long long n, const float* stats, int inverse, flo
 
 /* ---- hardware probe used by tests/bring-up (UMMA descriptor row-offset behaviour), not on the product path ---- */
 int tpz_lab_umma(const tpz_half* A, int rowsA, const tpz_half* B, int N, int shift, int sbo_rows, int base_off_mode,
-                 float* D, void* stream);
+                 int kc, float* D, void* stream);
+int tpz_lab_tma_stride(const tpz_half* A, int rowsA, int start, int stride, int nrows, tpz_half* out, void* stream);
 
 /* ---- layout helpers ---- */
 int tpz_f32_to_f16(const float* x, long long n, tpz_half* y, void* stream);

@@ -25,7 +25,7 @@ def _gather(src, org, d, out_shape, c0, kc):
     return out
 
 
-def tc_conv(plan, srcs, out_shape, out=None, res=None, res_org=(0, 0, 0), dot_out=None, out_coff=0):
+def tc_conv(plan, srcs, out_shape, out=None, res=None, res_org=(0, 0, 0), dot_out=None, out_coff=0, tag=None):
     N, Do, Ho, Wo = out_shape
     acc = torch.zeros((N, Do, Ho, Wo, plan.Co), dtype=torch.float32)
     for kb, (dx, dy, dz, c0, si) in enumerate(plan.kblocks):

@@ -22,26 +22,27 @@ def log(*a):
 def lab():
     res = {}
     g = torch.Generator().manual_seed(0)
-    A = torch.randn(512, 64, generator=g).half()
-    B = torch.randn(64, 64, generator=g).half()
-    Ad, Bd = A.cuda(), B.cuda()
-    for sbo in (8, 10, 18, 24):
-        for shift in (0, 1, 2, 3, 4, 5, 7, 8, 9, 16, 18, 20):
-            for bo in (0, 1):
+    for kc in (64, 32):
+        A = torch.randn(512, kc, generator=g).half()
+        B = torch.randn(64, kc, generator=g).half()
+        Ad, Bd = A.cuda(), B.cuda()
+        for sbo in (8, 10, 12):
+            for shift in (0, 1, 3, 5, 13):
                 rows = torch.tensor([shift + (m // 8) * sbo + (m % 8) for m in range(128)])
-                if rows.max() >= 512:
-                    continue
                 exp = A[rows].float() @ B.float().t()
-                try:
-                    D = ops.lab_umma(Ad, Bd, shift, sbo, bo); torch.cuda.synchronize()
-                    err = (D.cpu() - exp).abs().max().item() / exp.abs().max().item()
-                except Exception as e:
-                    err = f'EXC {e}'
-                res[f'sbo{sbo}_shift{shift}_bo{bo}'] = err
-                log(f'lab sbo={sbo} shift={shift} base_off_mode={bo}: rel err {err}')
-                if isinstance(err, str):
-                    json.dump(res, open(os.path.join(ROOT, 'gpurun_out', 'lab.json'), 'w'), indent=1)
-                    return res
+                D = ops.lab_umma(Ad, Bd, shift, sbo, 0, kc); torch.cuda.synchronize()
+                err = (D.cpu() - exp).abs().max().item() / exp.abs().max().item()
+                res[f'kc{kc}_sbo{sbo}_shift{shift}'] = err
+                log(f'lab kc={kc} sbo={sbo} shift={shift}: rel err {err:.2e}', 'OK' if err < 1e-3 else 'FAIL')
+    # TMA element-stride probe: which rows land in smem?
+    A = torch.arange(600).float()[:, None].repeat(1, 64).half()      # row r holds the value r
+    for stride, start, nrows in ((1, 5, 20), (2, 3, 20), (4, 7, 40), (8, 2, 30)):
+        raw = ops.lab_tma_stride(A.cuda(), start, stride, nrows); torch.cuda.synchronize()
+        got = raw.cpu().float()[:, 0].tolist()
+        exp = [float(start + i * stride) for i in range(nrows)]
+        ok = got == exp
+        res[f'tma_stride{stride}'] = ok
+        log(f'lab tma stride={stride} start={start}: rows {got[:8]}... expected {exp[:8]}...', 'OK' if ok else 'FAIL')
     json.dump(res, open(os.path.join(ROOT, 'gpurun_out', 'lab.json'), 'w'), indent=1)
     return res
 
@@ -134,8 +135,13 @@ def main():
         ('16-ch out', lambda: tc_case('co16', 1, 1, 20, 24, [32], 16, 3, 1, 1)),
         ('big', lambda: tc_case('big', 1, 1, 300, 420, [64], 128, 3, 4, 0)),
     ]
-    for name, fn in stages:
+    runs = [('lab', stages[0][1], 'auto')]
+    for name, fn in stages[1:]:
+        runs.append((name + ' [v2]', fn, 'v2'))
+    runs.append(('big [v1]', stages[-1][1], 'v1'))
+    for name, fn, variant in runs:
         t0 = time.time()
+        ops.TC_VARIANT = variant
         try:
             fn()
         except Exception:

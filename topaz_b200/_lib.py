@@ -17,7 +17,7 @@ class TcKBlock(C.Structure):
 
 class TpzTcSrc(C.Structure):
     _fields_ = [('ptr', C.c_void_p), ('N', C.c_int), ('D', C.c_int), ('H', C.c_int), ('W', C.c_int),
-                ('C', C.c_int), ('ld', C.c_int), ('org', C.c_int * 3)]
+                ('C', C.c_int), ('ld', C.c_int), ('org', C.c_int * 3), ('kw', C.c_int), ('kh', C.c_int)]
 
 
 class TpzTcConvArgs(C.Structure):
@@ -25,7 +25,7 @@ class TpzTcConvArgs(C.Structure):
         ('nsrc', C.c_int), ('src', TpzTcSrc * 2), ('weights', C.c_void_p), ('KC', C.c_int), ('nkb', C.c_int),
         ('kb', TcKBlock * TPZ_TC_MAX_KB),
         ('N', C.c_int), ('Do', C.c_int), ('Ho', C.c_int), ('Wo', C.c_int), ('Co', C.c_int),
-        ('TW', C.c_int), ('TH', C.c_int),
+        ('TW', C.c_int), ('TH', C.c_int), ('lattice', C.c_int),
         ('bias', C.c_void_p), ('neg_slope', C.c_float),
         ('res', C.c_void_p), ('res_scale', C.c_void_p),
         ('res_ld', C.c_int), ('res_D', C.c_int), ('res_H', C.c_int), ('res_W', C.c_int), ('res_org', C.c_int * 3),
@@ -41,6 +41,8 @@ _PROTOS = {
     'tpz_last_error': (C.c_char_p, []),
     'tpz_device_info': (_I, [C.POINTER(_I)] * 3),
     'tpz_tc_conv': (_I, [C.POINTER(TpzTcConvArgs), _P]),
+    'tpz_tc_conv_v1': (_I, [C.POINTER(TpzTcConvArgs), _P]),
+    'tpz_tc_conv_v2': (_I, [C.POINTER(TpzTcConvArgs), _P]),
     'tpz_conv_first': (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _I, _P]),
     'tpz_conv_last': (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _F, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P]),
     'tpz_conv_generic': (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F,
@@ -50,7 +52,8 @@ _PROTOS = {
     'tpz_meanstd': (_I, [_P, _LL, _I, _P, _P, _P]),
     'tpz_affine': (_I, [_P, _LL, _P, _I, _P, _P]),
     'tpz_f32_to_f16': (_I, [_P, _LL, _P, _P]),
-    'tpz_lab_umma': (_I, [_P, _I, _P, _I, _I, _I, _I, _P, _P]),
+    'tpz_lab_umma': (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _P]),
+    'tpz_lab_tma_stride': (_I, [_P, _I, _I, _I, _I, _P, _P]),
 }
 EXPORTS = tuple(_PROTOS.keys())
 

@@ -16,12 +16,13 @@ __device__ __forceinline__ bool lab_try(uint64_t* bar, uint32_t parity) {
 
 __global__ void __launch_bounds__(128, 1) lab_kernel(const __grid_constant__ CUtensorMap tmA,
                                                      const __grid_constant__ CUtensorMap tmB, int rowsA, int N,
-                                                     int shift, int sbo_rows, int base_off_mode, float* D) {
+                                                     int shift, int sbo_rows, int base_off_mode, int rowb, float* D) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
-  const int a_bytes = rowsA * 128, b_bytes = N * 128;
+  const int a_bytes = rowsA * rowb, b_bytes = N * rowb;
+  const uint32_t layout = rowb == 128 ? 2u : 4u;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + a_bytes + b_bytes);
   uint64_t* done = bar + 1;
   uint32_t* slot = reinterpret_cast<uint32_t*>(done + 1);
@@ -38,17 +39,17 @@ __global__ void __launch_bounds__(128, 1) lab_kernel(const __grid_constant__ CUt
   const uint32_t tmem = *slot;
   if (threadIdx.x == 0) {
     ptx::mbar_expect_tx(bar, (uint32_t)(a_bytes + b_bytes));
-    for (int r = 0; r < rowsA; r += 256) ptx::tma_load_2d(smem + r * 128, &tmA, bar, 0, r);
+    for (int r = 0; r < rowsA; r += 256) ptx::tma_load_2d(smem + r * rowb, &tmA, bar, 0, r);
     ptx::tma_load_2d(smem + a_bytes, &tmB, bar, 0, 0);
     while (!lab_try(bar, 0)) {}
     ptx::tc_fence_after();
-    const uint32_t a_addr = base + shift * 128;
+    const uint32_t a_addr = base + shift * rowb;
     const uint32_t b_addr = base + a_bytes;
     const uint32_t bo = base_off_mode ? ((a_addr >> 7) & 7) : 0;
     const uint32_t idesc = ptx::umma_idesc_f16(128, N);
-    for (int k = 0; k < 4; ++k) {
-      const uint64_t da = ptx::umma_desc(a_addr + k * 32, sbo_rows * 128, 2, bo);
-      const uint64_t db = ptx::umma_desc(b_addr + k * 32, 1024, 2, 0);
+    for (int k = 0; k < rowb / 32; ++k) {
+      const uint64_t da = ptx::umma_desc(a_addr + k * 32, sbo_rows * rowb, layout, bo);
+      const uint64_t db = ptx::umma_desc(b_addr + k * 32, 8 * rowb, layout, 0);
       ptx::umma_f16(tmem, da, db, idesc, k != 0);
     }
     ptx::umma_commit(done);
@@ -69,24 +70,67 @@ __global__ void __launch_bounds__(128, 1) lab_kernel(const __grid_constant__ CUt
 }
 }  // namespace
 
-// A: device fp16 [rowsA][64], B: device fp16 [N][64], D: device fp32 [128][N]
+// A: device fp16 [rowsA][kc], B: device fp16 [N][kc], D: device fp32 [128][N]; kc = 64 (SW128) or 32 (SW64)
 extern "C" int tpz_lab_umma(const tpz_half* A, int rowsA, const tpz_half* B, int N, int shift, int sbo_rows,
-                            int base_off_mode, float* D, void* stream) {
+                            int base_off_mode, int kc, float* D, void* stream) {
+  TPZ_CHECK(kc == 64 || kc == 32, "tpz_lab_umma: kc must be 32 or 64");
+  const int rowb = kc * 2;
   TPZ_CHECK(rowsA % 8 == 0 && rowsA <= 1024 && N % 16 == 0 && N <= 256, "tpz_lab_umma: bad sizes");
   CUtensorMap tmA, tmB;
-  uint64_t dA[2] = {64, (uint64_t)rowsA}, sA[1] = {128};
-  uint32_t bA[2] = {64, (uint32_t)(rowsA < 256 ? rowsA : 256)}, es[2] = {1, 1};
+  uint64_t dA[2] = {(uint64_t)kc, (uint64_t)rowsA}, sA[1] = {(uint64_t)rowb};
+  uint32_t bA[2] = {(uint32_t)kc, (uint32_t)(rowsA < 256 ? rowsA : 256)}, es[2] = {1, 1};
   TPZ_CHECK(rowsA <= 256 || rowsA % 256 == 0, "tpz_lab_umma: rowsA > 256 must be a multiple of 256");
-  int rc = tpz_encode_tmap(&tmA, A, 2, dA, sA, bA, es, 128);
+  int rc = tpz_encode_tmap(&tmA, A, 2, dA, sA, bA, es, rowb);
   if (rc) return rc;
-  uint64_t dB[2] = {64, (uint64_t)N};
-  uint32_t bB[2] = {64, (uint32_t)N};
-  rc = tpz_encode_tmap(&tmB, B, 2, dB, sA, bB, es, 128);
+  uint64_t dB[2] = {(uint64_t)kc, (uint64_t)N};
+  uint32_t bB[2] = {(uint32_t)kc, (uint32_t)N};
+  rc = tpz_encode_tmap(&tmB, B, 2, dB, sA, bB, es, rowb);
   if (rc) return rc;
-  const int smem = rowsA * 128 + N * 128 + 1024 + 256;
+  const int smem = rowsA * rowb + N * rowb + 1024 + 256;
   TPZ_CUDA(cudaFuncSetAttribute(lab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   lab_kernel<<<1, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tmA, tmB, rowsA, N, shift, sbo_rows,
-                                                                       base_off_mode, D);
+                                                                       base_off_mode, rowb, D);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---- probe 2: TMA tiled load with an element (traversal) stride: which rows land in shared memory? ----
+namespace {
+__global__ void lab_tma_stride_kernel(const __grid_constant__ CUtensorMap tm, int start, int nrows, __half* out) {
+  extern __shared__ uint8_t smem_raw2[];
+  const uint32_t raw = ptx::smem_u32(smem_raw2);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw2 + (base - raw);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + nrows * 128);
+  for (int i = threadIdx.x; i < nrows * 64; i += blockDim.x) reinterpret_cast<__half*>(smem)[i] = __float2half(-777.f);
+  if (threadIdx.x == 0) { ptx::mbar_init(bar, 1); ptx::fence_barrier_init(); }
+  ptx::fence_proxy_async();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ptx::mbar_expect_tx(bar, (uint32_t)(nrows * 128));
+    ptx::tma_load_2d(smem, &tm, bar, 0, start);
+  }
+  __syncthreads();
+  int spins = 0;
+  while (!lab_try(bar, 0) && ++spins < (1 << 22)) {}
+  for (int i = threadIdx.x; i < nrows * 64; i += blockDim.x) out[i] = reinterpret_cast<__half*>(smem)[i];
+}
+}  // namespace
+
+// A: device fp16 [rowsA][64].  Loads a box of `nrows` rows starting at row `start` with element stride `stride`
+// along the row dimension (box extent (nrows-1)*stride+1) and copies the raw (swizzled) smem image to out.
+extern "C" int tpz_lab_tma_stride(const tpz_half* A, int rowsA, int start, int stride, int nrows, tpz_half* out,
+                                  void* stream) {
+  CUtensorMap tm;
+  uint64_t d[2] = {64, (uint64_t)rowsA}, s[1] = {128};
+  uint32_t b[2] = {64, (uint32_t)((nrows - 1) * stride + 1)}, es[2] = {1, (uint32_t)stride};
+  TPZ_CHECK(b[1] <= 256, "tpz_lab_tma_stride: box too large");
+  int rc = tpz_encode_tmap(&tm, A, 2, d, s, b, es, 128);
+  if (rc) return rc;
+  const int smem = nrows * 128 + 2048;
+  TPZ_CUDA(cudaFuncSetAttribute(lab_tma_stride_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  lab_tma_stride_kernel<<<1, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tm, start, nrows,
+                                                                                  reinterpret_cast<__half*>(out));
   TPZ_CUDA(cudaGetLastError());
   return 0;
 }

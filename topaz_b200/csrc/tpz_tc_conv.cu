@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
 // -------------------------------------------------------------------------------------------------
 static int g_num_sms = 0;
 
-extern "C" int tpz_tc_conv(const TpzTcConvArgs* a, void* stream_) {
+extern "C" int tpz_tc_conv_v1(const TpzTcConvArgs* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   TPZ_CHECK(a != nullptr, "tpz_tc_conv: null args");
   TPZ_CHECK(a->KC == 64 || a->KC == 32, "tpz_tc_conv: KC must be 32 or 64 (got %d)", a->KC);

@@ -1,0 +1,502 @@
+// tcgen05 implicit-GEMM convolution, halo-resident variant ("v2") for sm_100a.
+//
+// Same math and epilogue as tpz_tc_conv.cu (see there for the reference call sites), different data movement:
+//   * poly-phase lattice: a conv with in-plane dilation L touches, for one output pixel, only input pixels
+//     on the same residue class mod L.  A CTA tile is therefore 8 x 32 points of ONE lattice (pixels L apart),
+//     fetched with TMA element strides (1, L, L); on that lattice every tap is a shift by ONE point.
+//   * halo-resident A: per (source, channel chunk, z-tap) the (8+kw-1) x (32+kh-1) lattice halo is loaded
+//     ONCE; each (r,s) tap is an MMA whose A descriptor starts at row r*HX+s of that tile (128B-swizzled
+//     operands may start at any row; 8-row groups are HX rows apart -> SBO = HX*row_bytes).  Verified on
+//     B200 by tools/bringup.py (lab): arbitrary start row / SBO with base_offset = 0.
+//   * two M=128 accumulators per CTA (rows 0-15 / 16-31 of the tile) share every B (weight) block, halving
+//     weight traffic; small weight sets stay resident in shared memory for the whole persistent kernel.
+// Warp roles: warp0 = A (activation) TMA producer, warp3 = B (weight) TMA producer, warp1 = MMA issuer,
+// warp2 = TMEM allocator, warps4-7 = epilogue.
+#include "tpz_common.cuh"
+#include "tpz_tc_conv.h"
+#include <stdlib.h>
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kTmemCols = 512;
+constexpr int T2W = 8, T2H = 32;
+constexpr int kMaxGroups = 40;
+constexpr int kMaxAStages = 4, kMaxBStages = 8;
+
+struct Tc2Group {
+  int16_t src, c0, dz, ntaps;
+  int32_t tap_begin;
+};
+struct Tc2Tap {
+  uint16_t kb, row_off;
+};
+
+struct Tc2Params {
+  CUtensorMap tmA[2];
+  CUtensorMap tmB;
+  int nsrc;
+  int org[2][3];
+  int hx[2], rows_loaded[2], split_rows[2];
+  int L;
+  int N, Do, Ho, Wo, Co, CS;
+  int tiles_x, tiles_y, num_tiles;
+  int ngroups, nkb;
+  int a_stages, b_stages, b_resident, acc_stages;
+  int a_stage_bytes, b_block_bytes;
+  const float* bias;
+  float neg_slope;
+  const __half* res;
+  const float* res_scale;
+  int res_ld, res_D, res_H, res_W, res_org[3];
+  __half* out;
+  int out_ld, out_coff;
+  const float* dot_w;
+  float dot_b;
+  float* dot_out;
+  Tc2Group groups[kMaxGroups];
+  Tc2Tap taps[TPZ_TC_MAX_KB];
+};
+
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(ptx::smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try(bar, parity)) {
+  }
+}
+
+struct TileCoord {
+  int n, z, x_first, y_first;
+};
+__device__ __forceinline__ TileCoord decode_tile(const Tc2Params& p, int tile) {
+  const int LL = p.L * p.L;
+  const int ph = tile % LL;
+  int rest = tile / LL;
+  const int txq = rest % p.tiles_x;
+  rest /= p.tiles_x;
+  const int tyq = rest % p.tiles_y;
+  const int plane = rest / p.tiles_y;
+  TileCoord t;
+  t.n = plane / p.Do;
+  t.z = plane - t.n * p.Do;
+  t.x_first = txq * T2W * p.L + (ph % p.L);
+  t.y_first = tyq * T2H * p.L + (ph / p.L);
+  return t;
+}
+
+template <int KC>
+__global__ void __launch_bounds__(kThreads, 1) tc_conv2_kernel(const __grid_constant__ Tc2Params p) {
+  constexpr int ROWB = KC * 2;
+  constexpr uint32_t LAYOUT = (KC == 64) ? 2u : 4u;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+
+  const int AS = p.a_stages, BS = p.b_stages;
+  const uint32_t a_base = base;
+  const uint32_t b_base = base + (uint32_t)AS * p.a_stage_bytes;
+  const int b_region = p.b_resident ? p.nkb * p.b_block_bytes : BS * p.b_block_bytes;
+  uint8_t* tail = smem + (size_t)AS * p.a_stage_bytes + b_region;
+  uint64_t* afull = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* aempty = afull + kMaxAStages;
+  uint64_t* bfull = aempty + kMaxAStages;
+  uint64_t* bempty = bfull + kMaxBStages;
+  uint64_t* bres = bempty + kMaxBStages;
+  uint64_t* tfull = bres + 1;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
+  float* s_dotw = s_bias + 256;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < p.Co; i += kThreads) {
+    s_bias[i] = p.bias ? p.bias[i] : 0.f;
+    s_dotw[i] = p.dot_w ? p.dot_w[i] : 0.f;
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.tmA[0]);
+    if (p.nsrc > 1) ptx::prefetch_tmap(&p.tmA[1]);
+    ptx::prefetch_tmap(&p.tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kMaxAStages; ++s) { ptx::mbar_init(&afull[s], 1); ptx::mbar_init(&aempty[s], 1); }
+    for (int s = 0; s < kMaxBStages; ++s) { ptx::mbar_init(&bfull[s], 1); ptx::mbar_init(&bempty[s], 1); }
+    ptx::mbar_init(bres, 1);
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 4); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<kTmemCols>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ A producer: one halo tile per (tile, group) ------------------------------
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile);
+        for (int g = 0; g < p.ngroups; ++g, ++it) {
+          const int s = it % AS;
+          const uint32_t ph = (it / AS) & 1;
+          mbar_wait(&aempty[s], ph ^ 1);
+          const Tc2Group G = p.groups[g];
+          const int src = G.src;
+          const int hx = p.hx[src];
+          ptx::mbar_expect_tx(&afull[s], (uint32_t)(hx * p.rows_loaded[src] * ROWB));
+          uint8_t* dst = smem + (size_t)s * p.a_stage_bytes;
+          const int sr = p.split_rows[src];
+          for (int row0 = 0; row0 < p.rows_loaded[src]; row0 += sr) {
+            ptx::tma_load_5d(dst + (size_t)row0 * hx * ROWB, &p.tmA[src], &afull[s], G.c0, tc.x_first + p.org[src][0],
+                             tc.y_first + p.org[src][1] + row0 * p.L, tc.z + p.org[src][2] + G.dz, tc.n);
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------ B producer: weights, resident or streamed per tap ------------------------------
+    if (lane == 0) {
+      if (p.b_resident) {
+        ptx::mbar_expect_tx(bres, (uint32_t)(p.nkb * p.b_block_bytes));
+        for (int kb = 0; kb < p.nkb; ++kb)
+          ptx::tma_load_2d(smem + (size_t)AS * p.a_stage_bytes + (size_t)kb * p.b_block_bytes, &p.tmB, bres, 0,
+                           kb * p.Co);
+      } else {
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+          for (int g = 0; g < p.ngroups; ++g) {
+            const Tc2Group G = p.groups[g];
+            for (int t = 0; t < G.ntaps; ++t, ++it) {
+              const int s = it % BS;
+              const uint32_t ph = (it / BS) & 1;
+              mbar_wait(&bempty[s], ph ^ 1);
+              ptx::mbar_expect_tx(&bfull[s], (uint32_t)p.b_block_bytes);
+              ptx::tma_load_2d(smem + (size_t)AS * p.a_stage_bytes + (size_t)s * p.b_block_bytes, &p.tmB, &bfull[s], 0,
+                               (int)p.taps[G.tap_begin + t].kb * p.Co);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_f16(128, p.Co);
+      if (p.b_resident) {
+        mbar_wait(bres, 0);
+        ptx::tc_fence_after();
+      }
+      uint32_t ait = 0, bit = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t st = (p.acc_stages == 2) ? (tcount & 1) : 0;
+        const uint32_t aph = (p.acc_stages == 2) ? ((tcount >> 1) & 1) : (tcount & 1);
+        mbar_wait(&tempty[st], aph ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d0 = tmem_base + (st * 2) * p.CS;
+        const uint32_t d1 = d0 + p.CS;
+        uint32_t first = 1;
+        for (int g = 0; g < p.ngroups; ++g, ++ait) {
+          const int s = ait % AS;
+          const uint32_t ph = (ait / AS) & 1;
+          mbar_wait(&afull[s], ph);
+          ptx::tc_fence_after();
+          const Tc2Group G = p.groups[g];
+          const uint32_t hxb = (uint32_t)p.hx[G.src] * ROWB;          // bytes between consecutive tile rows (y)
+          const uint32_t a_tile = a_base + (uint32_t)s * p.a_stage_bytes;
+          for (int t = 0; t < G.ntaps; ++t) {
+            const Tc2Tap T = p.taps[G.tap_begin + t];
+            uint32_t b_addr;
+            int bs = 0;
+            if (p.b_resident) {
+              b_addr = b_base + (uint32_t)T.kb * p.b_block_bytes;
+            } else {
+              bs = bit % BS;
+              const uint32_t bph = (bit / BS) & 1;
+              mbar_wait(&bfull[bs], bph);
+              ptx::tc_fence_after();
+              b_addr = b_base + (uint32_t)bs * p.b_block_bytes;
+              ++bit;
+            }
+            const uint32_t a0 = a_tile + (uint32_t)T.row_off * ROWB;
+            const uint32_t a1 = a0 + 16u * hxb;
+#pragma unroll
+            for (int k = 0; k < KC / 16; ++k) {
+              const uint64_t db = ptx::umma_desc(b_addr + k * 32, 8 * ROWB, LAYOUT);
+              ptx::umma_f16(d0, ptx::umma_desc(a0 + k * 32, hxb, LAYOUT), db, idesc, (first && k == 0) ? 0u : 1u);
+              ptx::umma_f16(d1, ptx::umma_desc(a1 + k * 32, hxb, LAYOUT), db, idesc, (first && k == 0) ? 0u : 1u);
+            }
+            first = 0;
+            if (!p.b_resident) ptx::umma_commit(&bempty[bs]);
+          }
+          ptx::umma_commit(&aempty[s]);
+        }
+        ptx::umma_commit(&tfull[st]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------ epilogue ------------------------------
+    const int ew = warp - 4;
+    const int m = ew * 32 + lane;
+    const int li = m & 7, lj = m >> 3;   // lattice point (li, lj) of accumulator 0; accumulator 1 is 16 rows lower
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
+      const TileCoord tc = decode_tile(p, tile);
+      const uint32_t st = (p.acc_stages == 2) ? (tcount & 1) : 0;
+      const uint32_t aph = (p.acc_stages == 2) ? ((tcount >> 1) & 1) : (tcount & 1);
+      mbar_wait(&tfull[st], aph);
+      ptx::tc_fence_after();
+      for (int a = 0; a < 2; ++a) {
+        const int gx = tc.x_first + li * p.L;
+        const int gy = tc.y_first + (lj + 16 * a) * p.L;
+        const bool valid = (gx < p.Wo) && (gy < p.Ho);
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (st * 2 + a) * p.CS;
+        const long long opix = (((long long)tc.n * p.Do + tc.z) * p.Ho + gy) * p.Wo + gx;
+        __half* orow = p.out ? p.out + opix * p.out_ld + p.out_coff : nullptr;
+        const __half* rrow = nullptr;
+        if (p.res) {
+          const long long rpix =
+              (((long long)tc.n * p.res_D + (tc.z + p.res_org[2])) * p.res_H + (gy + p.res_org[1])) * p.res_W +
+              (gx + p.res_org[0]);
+          rrow = p.res + rpix * p.res_ld;
+        }
+        float dot = 0.f;
+        for (int c = 0; c < p.Co; c += 32) {
+          uint32_t r[32];
+          if (p.Co - c >= 32) {
+            ptx::tmem_ld32(taddr + c, r);
+          } else {
+            uint32_t r16[16];
+            ptx::tmem_ld16(taddr + c, r16);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { r[j] = r16[j]; r[16 + j] = 0; }
+          }
+          ptx::tmem_ld_wait();
+          const int nc = min(32, p.Co - c);
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_bias[min(c + j, 255)];
+          if (rrow && valid) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (q * 8 < nc) {
+                const uint4 u = *reinterpret_cast<const uint4*>(rrow + c + q * 8);
+                const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __half22float2(h[e]);
+                  const int j = q * 8 + e * 2;
+                  const float s0 = p.res_scale ? p.res_scale[c + j] : 1.f;
+                  const float s1 = p.res_scale ? p.res_scale[c + j + 1] : 1.f;
+                  v[j] += s0 * f.x;
+                  v[j + 1] += s1 * f.y;
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.neg_slope;
+          if (p.dot_out) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nc) dot = fmaf(v[j], s_dotw[c + j], dot);
+          }
+          if (orow && valid) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (q * 8 < nc) {
+                uint4 u;
+                __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[q * 8 + e * 2], v[q * 8 + e * 2 + 1]);
+                *reinterpret_cast<uint4*>(orow + c + q * 8) = u;
+              }
+            }
+          }
+        }
+        if (p.dot_out && valid) p.dot_out[opix] = dot + p.dot_b;
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty[st]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+int g_num_sms2 = 0;
+
+}  // namespace
+
+// returns 0 ok, <0 "not eligible" (caller falls back to the per-tap kernel), >0 error
+static int launch_v2(const TpzTcConvArgs* a, cudaStream_t stream, bool dry) {
+  const int L = a->lattice;
+  if (L < 1 || L > 8) return -1;
+  const int rowb = a->KC * 2;
+  Tc2Params p;
+  memset(&p, 0, sizeof(p));
+  p.L = L;
+  int a_stage = 0;
+  for (int s = 0; s < a->nsrc; ++s) {
+    const TpzTcSrc& src = a->src[s];
+    if (src.kw < 1 || src.kh < 1) return -1;
+    const int hx = T2W + src.kw - 1, hy = T2H + src.kh - 1;
+    if ((hx - 1) * L + 1 > 256) return -1;
+    const int ext = (hy - 1) * L + 1;
+    const int nsplit = (ext + 255) / 256;
+    const int sr = (hy + nsplit - 1) / nsplit;
+    if ((sr - 1) * L + 1 > 256) return -1;
+    p.hx[s] = hx; p.split_rows[s] = sr; p.rows_loaded[s] = sr * nsplit;
+    const int bytes = (hx * sr * nsplit * rowb + 1023) / 1024 * 1024;
+    if (bytes > a_stage) a_stage = bytes;
+  }
+  // group the k-blocks by (source, chunk, z-tap); all in-plane taps of a group read one halo tile
+  int ng = 0, nt = 0;
+  bool used[TPZ_TC_MAX_KB];
+  memset(used, 0, sizeof(used));
+  for (int i = 0; i < a->nkb; ++i) {
+    if (used[i]) continue;
+    if (ng >= kMaxGroups) return -1;
+    Tc2Group& G = p.groups[ng];
+    G.src = (int16_t)a->kb[i].src; G.c0 = a->kb[i].c0; G.dz = a->kb[i].dz; G.tap_begin = nt; G.ntaps = 0;
+    for (int j = i; j < a->nkb; ++j) {
+      const TcKBlock& k = a->kb[j];
+      if (used[j] || k.src != G.src || k.c0 != G.c0 || k.dz != G.dz) continue;
+      if (k.dx % L || k.dy % L) return -1;
+      const int sx = k.dx / L, ry = k.dy / L;
+      if (sx < 0 || sx >= a->src[k.src].kw || ry < 0 || ry >= a->src[k.src].kh) return -1;
+      p.taps[nt].kb = (uint16_t)j;
+      p.taps[nt].row_off = (uint16_t)(ry * p.hx[k.src] + sx);
+      used[j] = true; ++nt; ++G.ntaps;
+    }
+    ++ng;
+  }
+  p.ngroups = ng; p.nkb = a->nkb;
+  p.b_block_bytes = a->Co * rowb;
+  const int tail = 4096;
+  const int budget = 227 * 1024 - 1024 - tail;
+  const int resident_bytes = a->nkb * p.b_block_bytes;
+  p.a_stages = 2;
+  if (p.a_stages * a_stage + 2 * p.b_block_bytes > budget) return -1;
+  if (resident_bytes <= 112 * 1024 && p.a_stages * a_stage + resident_bytes <= budget && resident_bytes < (1 << 20)) {
+    p.b_resident = 1; p.b_stages = 0;
+    int as = (budget - resident_bytes) / a_stage;
+    p.a_stages = as > kMaxAStages ? kMaxAStages : as;
+  } else {
+    p.b_resident = 0;
+    int as = 2;
+    if (3 * a_stage + 4 * p.b_block_bytes <= budget) as = 3;
+    p.a_stages = as;
+    int bs = (budget - as * a_stage) / p.b_block_bytes;
+    p.b_stages = bs > kMaxBStages ? kMaxBStages : bs;
+    if (p.b_stages < 2) return -1;
+  }
+  p.a_stage_bytes = a_stage;
+  int cs = 32;
+  while (cs < a->Co) cs <<= 1;
+  p.CS = cs;
+  p.acc_stages = (4 * cs <= kTmemCols) ? 2 : 1;
+  if (dry) return 0;
+
+  for (int s = 0; s < a->nsrc; ++s) {
+    const TpzTcSrc& src = a->src[s];
+    TPZ_CHECK(src.C % a->KC == 0, "tpz_tc_conv: source %d channels %d not a multiple of KC=%d", s, src.C, a->KC);
+    TPZ_CHECK(src.ld % 8 == 0, "tpz_tc_conv: source %d channel stride %d must be a multiple of 8", s, src.ld);
+    uint64_t dims[5] = {(uint64_t)src.C, (uint64_t)src.W, (uint64_t)src.H, (uint64_t)src.D, (uint64_t)src.N};
+    uint64_t strides[4] = {(uint64_t)src.ld * 2, (uint64_t)src.ld * 2 * src.W, (uint64_t)src.ld * 2 * src.W * src.H,
+                           (uint64_t)src.ld * 2 * src.W * src.H * src.D};
+    uint32_t box[5] = {(uint32_t)a->KC, (uint32_t)((p.hx[s] - 1) * L + 1), (uint32_t)((p.split_rows[s] - 1) * L + 1), 1, 1};
+    uint32_t es[5] = {1, (uint32_t)L, (uint32_t)L, 1, 1};
+    int rc = tpz_encode_tmap(&p.tmA[s], src.ptr, 5, dims, strides, box, es, rowb);
+    if (rc) return rc;
+    p.org[s][0] = src.org[0]; p.org[s][1] = src.org[1]; p.org[s][2] = src.org[2];
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)a->KC, (uint64_t)a->nkb * a->Co};
+    uint64_t strides[1] = {(uint64_t)rowb};
+    uint32_t box[2] = {(uint32_t)a->KC, (uint32_t)a->Co};
+    uint32_t es[2] = {1, 1};
+    int rc = tpz_encode_tmap(&p.tmB, a->weights, 2, dims, strides, box, es, rowb);
+    if (rc) return rc;
+  }
+  p.nsrc = a->nsrc;
+  p.N = a->N; p.Do = a->Do; p.Ho = a->Ho; p.Wo = a->Wo; p.Co = a->Co;
+  const int qW = tpz_div_up(a->Wo, L), qH = tpz_div_up(a->Ho, L);
+  p.tiles_x = tpz_div_up(qW, T2W);
+  p.tiles_y = tpz_div_up(qH, T2H);
+  const long long ntl = (long long)L * L * p.tiles_x * p.tiles_y * a->Do * a->N;
+  TPZ_CHECK(ntl > 0 && ntl < (1ll << 31), "tpz_tc_conv: bad tile count %lld", ntl);
+  p.num_tiles = (int)ntl;
+  p.bias = a->bias; p.neg_slope = a->neg_slope;
+  p.res = reinterpret_cast<const __half*>(a->res); p.res_scale = a->res_scale; p.res_ld = a->res_ld;
+  p.res_D = a->res_D; p.res_H = a->res_H; p.res_W = a->res_W;
+  p.res_org[0] = a->res_org[0]; p.res_org[1] = a->res_org[1]; p.res_org[2] = a->res_org[2];
+  p.out = reinterpret_cast<__half*>(a->out); p.out_ld = a->out_ld; p.out_coff = a->out_coff;
+  p.dot_w = a->dot_w; p.dot_b = a->dot_b; p.dot_out = a->dot_out;
+
+  if (g_num_sms2 == 0) {
+    int dev = 0;
+    TPZ_CUDA(cudaGetDevice(&dev));
+    TPZ_CUDA(cudaDeviceGetAttribute(&g_num_sms2, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int b_region = p.b_resident ? resident_bytes : p.b_stages * p.b_block_bytes;
+  int smem = p.a_stages * a_stage + b_region + tail + 1024;
+  if (smem < 120 * 1024) smem = 120 * 1024;  // 1 CTA / SM (every CTA owns all 512 TMEM columns)
+  const int grid = p.num_tiles < g_num_sms2 ? p.num_tiles : g_num_sms2;
+  if (a->KC == 64) {
+    TPZ_CUDA(cudaFuncSetAttribute(tc_conv2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    tc_conv2_kernel<64><<<grid, kThreads, smem, stream>>>(p);
+  } else {
+    TPZ_CUDA(cudaFuncSetAttribute(tc_conv2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    tc_conv2_kernel<32><<<grid, kThreads, smem, stream>>>(p);
+  }
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int check_common(const TpzTcConvArgs* a) {
+  TPZ_CHECK(a != nullptr, "tpz_tc_conv: null args");
+  TPZ_CHECK(a->KC == 64 || a->KC == 32, "tpz_tc_conv: KC must be 32 or 64 (got %d)", a->KC);
+  TPZ_CHECK(a->Co >= 16 && a->Co <= 256 && a->Co % 16 == 0, "tpz_tc_conv: Co=%d must be a multiple of 16 in [16,256]", a->Co);
+  TPZ_CHECK(a->nsrc >= 1 && a->nsrc <= 2, "tpz_tc_conv: nsrc=%d", a->nsrc);
+  TPZ_CHECK(a->nkb >= 1 && a->nkb <= TPZ_TC_MAX_KB, "tpz_tc_conv: nkb=%d exceeds %d", a->nkb, TPZ_TC_MAX_KB);
+  TPZ_CHECK(a->out != nullptr || a->dot_out != nullptr, "tpz_tc_conv: no output");
+  TPZ_CHECK(a->out == nullptr || (a->out_ld % 8 == 0 && a->out_coff % 8 == 0), "tpz_tc_conv: output channel stride/offset must be multiples of 8");
+  TPZ_CHECK(a->res == nullptr || a->res_ld % 8 == 0, "tpz_tc_conv: residual channel stride must be a multiple of 8");
+  for (int i = 0; i < a->nkb; ++i)
+    TPZ_CHECK(a->kb[i].src >= 0 && a->kb[i].src < a->nsrc, "tpz_tc_conv: k-block %d bad source", i);
+  return 0;
+}
+
+extern "C" int tpz_tc_conv_v2(const TpzTcConvArgs* a, void* stream) {
+  int rc = check_common(a);
+  if (rc) return rc;
+  rc = launch_v2(a, reinterpret_cast<cudaStream_t>(stream), false);
+  if (rc < 0) return tpz_fail(3, "tpz_tc_conv_v2: configuration not eligible for the halo-resident kernel");
+  return rc;
+}
+
+extern "C" int tpz_tc_conv(const TpzTcConvArgs* a, void* stream) {
+  int rc = check_common(a);
+  if (rc) return rc;
+  static const bool force_v1 = getenv("TPZ_TC_FORCE_V1") != nullptr;
+  if (!force_v1 && launch_v2(a, reinterpret_cast<cudaStream_t>(stream), true) == 0)
+    return launch_v2(a, reinterpret_cast<cudaStream_t>(stream), false);
+  return tpz_tc_conv_v1(a, stream);
+}

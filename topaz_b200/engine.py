@@ -191,7 +191,7 @@ def _run_dense(plan, x: torch.Tensor, want_features: bool):
         res_org = (st['edge'], st['edge'], 0) if st.get('res') else (0, 0, 0)
         if st['dot'] and not want_features:
             out = torch.empty((N, D, Ho, Wo), dtype=torch.float32, device=x.device)
-            ops.tc_conv(p, srcs, (N, D, Ho, Wo), out=None, res=res, res_org=res_org, dot_out=out)
+            ops.tc_conv(p, srcs, (N, D, Ho, Wo), out=None, res=res, res_org=res_org, dot_out=out, tag='dominant')
             cur = None
         else:
             nxt = torch.empty((N, D, Ho, Wo, p.Co), dtype=torch.float16, device=x.device)

@@ -46,6 +46,8 @@ class TcConvPlan:
     kblocks: List[Tuple[int, int, int, int, int]]   # (dx, dy, dz, c0, src)
     orgs: List[Tuple[int, int, int]]
     c_stores: List[int]
+    tapgrids: List[Tuple[int, int]]   # (kw, kh) per source
+    lattice: int                      # in-plane dilation shared by all multi-tap sources
     weights: torch.Tensor        # [nkb, Co, KC] fp16 (device)
     bias: torch.Tensor           # [Co] fp32 (device)
     neg_slope: float
@@ -105,8 +107,11 @@ def pack_tc_conv(parts: Sequence[ConvPart], bias: Optional[torch.Tensor], co_sto
         rs = torch.ones(co_store, dtype=torch.float32)
         rs[:co_real] = res_scale.detach().to(torch.float32).cpu()
         rs = rs.to(device)
+    grids = [(int(p.w.shape[-1]), int(p.w.shape[-2])) for p in parts]
+    dils = {p.dil for p, g in zip(parts, grids) if g != (1, 1)}
+    lattice = dils.pop() if len(dils) == 1 else (1 if not dils else 0)
     return TcConvPlan(KC=KC, Co=co_store, kblocks=kbs, orgs=[tuple(p.org) for p in parts],
-                      c_stores=[p.c_store for p in parts], weights=wt, bias=b.to(device),
+                      c_stores=[p.c_store for p in parts], tapgrids=grids, lattice=lattice, weights=wt, bias=b.to(device),
                       neg_slope=float(neg_slope), dot_w=dw, dot_b=float(dot_b), res_scale=rs)
 
 
@@ -123,6 +128,7 @@ def fill_tc_args(plan: TcConvPlan, srcs: Sequence[torch.Tensor], out_shape: Tupl
         s.C = plan.c_stores[i]; s.ld = ld
         for j in range(3):
             s.org[j] = plan.orgs[i][j]
+        s.kw, s.kh = plan.tapgrids[i]
     a.weights = plan.weights.data_ptr()
     a.KC = plan.KC
     a.nkb = len(plan.kblocks)
@@ -132,6 +138,7 @@ def fill_tc_args(plan: TcConvPlan, srcs: Sequence[torch.Tensor], out_shape: Tupl
     a.N, a.Do, a.Ho, a.Wo = out_shape
     a.Co = plan.Co
     a.TW, a.TH = plan.TW, plan.TH
+    a.lattice = plan.lattice
     a.bias = plan.bias.data_ptr()
     a.neg_slope = plan.neg_slope
     if res is not None:
@@ -148,9 +155,28 @@ def fill_tc_args(plan: TcConvPlan, srcs: Sequence[torch.Tensor], out_shape: Tupl
     return a
 
 
-def tc_conv(plan: TcConvPlan, srcs, out_shape, out=None, res=None, res_org=(0, 0, 0), dot_out=None, out_coff=0):
+TC_VARIANT = 'auto'      # 'auto' (halo-resident kernel when eligible), 'v1' (per-tap loads), 'v2' (must be eligible)
+LAUNCH_COUNT = 0          # kernels launched through this module (bench.py reports it as gpu_launches)
+EVENT_HOOK = None         # optional callable(tag) -> (start_event, end_event) recorder used by bench.py
+
+
+def tc_conv(plan: TcConvPlan, srcs, out_shape, out=None, res=None, res_org=(0, 0, 0), dot_out=None, out_coff=0,
+            tag=None):
+    global LAUNCH_COUNT
     a = fill_tc_args(plan, srcs, out_shape, out, res, res_org, dot_out, out_coff)
-    check(_lib.lib().tpz_tc_conv(C.byref(a), _stream()))
+    fn = {'auto': _lib.lib().tpz_tc_conv, 'v1': _lib.lib().tpz_tc_conv_v1, 'v2': _lib.lib().tpz_tc_conv_v2}[TC_VARIANT]
+    hook = EVENT_HOOK(tag) if (EVENT_HOOK is not None and tag is not None) else None
+    if hook is not None:
+        hook[0].record(torch.cuda.current_stream())
+    check(fn(C.byref(a), _stream()))
+    if hook is not None:
+        hook[1].record(torch.cuda.current_stream())
+    LAUNCH_COUNT += 1
+
+
+def _count(n):
+    global LAUNCH_COUNT
+    LAUNCH_COUNT += n
 
 
 # ------------------------------------------------------------------------------------------------
@@ -164,7 +190,7 @@ def conv_first(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], d
     Do = D + 2 * pad - (kd - 1) * dil if kd > 1 else D
     Ho, Wo = H + 2 * pad - (kh - 1) * dil, W + 2 * pad - (kw - 1) * dil
     out = torch.empty((N, Do, Ho, Wo, out_ld), dtype=torch.float16, device=x.device)
-    check(_lib.lib().tpz_conv_first(_ptr(x), N, D, H, W, _ptr(w), _ptr(bias), Co, kd, kh, kw, dil, pad,
+    _count(1); check(_lib.lib().tpz_conv_first(_ptr(x), N, D, H, W, _ptr(w), _ptr(bias), Co, kd, kh, kw, dil, pad,
                                     float(neg_slope), 1, _ptr(out), out_ld, _stream()))
     return out
 
@@ -175,7 +201,7 @@ def conv_last(x: torch.Tensor, c_real: int, w: torch.Tensor, bias: float, kdhw, 
     N, D, H, W, ld = x.shape
     kd, kh, kw = kdhw
     out = torch.empty((N, D, H, W), dtype=torch.float32, device=x.device)
-    check(_lib.lib().tpz_conv_last(_ptr(x), N, D, H, W, w.shape[1], ld, _ptr(w), float(bias), kd, kh, kw, dil, pad,
+    _count(1); check(_lib.lib().tpz_conv_last(_ptr(x), N, D, H, W, w.shape[1], ld, _ptr(w), float(bias), kd, kh, kw, dil, pad,
                                    float(out_scale), float(out_shift), _ptr(stats), _ptr(out), _stream()))
     return out
 
@@ -189,7 +215,7 @@ def conv_generic(x0, c0, x1, c1, w, bias, stride, dil, pad, neg_slope, out_ld, r
         return (n + 2 * pad - (k - 1) * dil - 1) // stride + 1 if three else n
     Do = osz(D, kd, kd > 1); Ho = osz(H, kh, True); Wo = osz(W, kw, True)
     out = torch.zeros((N, Do, Ho, Wo, out_ld), dtype=torch.float16, device=x0.device)
-    check(_lib.lib().tpz_conv_generic(_ptr(x0), c0, ld0, _ptr(x1), c1, x1.shape[4] if x1 is not None else 0,
+    _count(1); check(_lib.lib().tpz_conv_generic(_ptr(x0), c0, ld0, _ptr(x1), c1, x1.shape[4] if x1 is not None else 0,
                                       N, D, H, W, _ptr(w), _ptr(bias), Co, kd, kh, kw, stride, dil, pad,
                                       float(neg_slope), _ptr(res), res.shape[4] if res is not None else 0, res_org,
                                       _ptr(out), out_ld, Do, Ho, Wo, _stream()))
@@ -200,7 +226,7 @@ def maxpool2(x: torch.Tensor, dims: int) -> torch.Tensor:
     N, D, H, W, ld = x.shape
     Do = D // 2 if dims == 3 else D
     out = torch.empty((N, Do, H // 2, W // 2, ld), dtype=torch.float16, device=x.device)
-    check(_lib.lib().tpz_maxpool2(_ptr(x), N, D, H, W, ld, ld, dims, _ptr(out), ld, _stream()))
+    _count(1); check(_lib.lib().tpz_maxpool2(_ptr(x), N, D, H, W, ld, ld, dims, _ptr(out), ld, _stream()))
     return out
 
 
@@ -208,7 +234,7 @@ def upsample_nearest(x: torch.Tensor, size: Tuple[int, int, int]) -> torch.Tenso
     N, D, H, W, ld = x.shape
     Do, Ho, Wo = size
     out = torch.empty((N, Do, Ho, Wo, ld), dtype=torch.float16, device=x.device)
-    check(_lib.lib().tpz_upsample_nearest(_ptr(x), N, D, H, W, ld, ld, Do, Ho, Wo, _ptr(out), ld, 0, _stream()))
+    _count(1); check(_lib.lib().tpz_upsample_nearest(_ptr(x), N, D, H, W, ld, ld, Do, Ho, Wo, _ptr(out), ld, 0, _stream()))
     return out
 
 
@@ -216,18 +242,25 @@ def meanstd(x: torch.Tensor, unbiased: bool) -> torch.Tensor:
     """Device float[2] = (mean, std) of a contiguous fp32 tensor; no host synchronisation."""
     stats = torch.empty(2, dtype=torch.float32, device=x.device)
     work = torch.empty(4, dtype=torch.float64, device=x.device)
-    check(_lib.lib().tpz_meanstd(_ptr(x), x.numel(), int(unbiased), _ptr(stats), _ptr(work), _stream()))
+    _count(5); check(_lib.lib().tpz_meanstd(_ptr(x), x.numel(), int(unbiased), _ptr(stats), _ptr(work), _stream()))
     return stats
 
 
 def affine(x: torch.Tensor, stats: torch.Tensor, inverse: bool = False, out: Optional[torch.Tensor] = None):
     y = torch.empty_like(x) if out is None else out
-    check(_lib.lib().tpz_affine(_ptr(x), x.numel(), _ptr(stats), int(inverse), _ptr(y), _stream()))
+    _count(1); check(_lib.lib().tpz_affine(_ptr(x), x.numel(), _ptr(stats), int(inverse), _ptr(y), _stream()))
     return y
 
 
-def lab_umma(A: torch.Tensor, B: torch.Tensor, shift: int, sbo_rows: int, base_off_mode: int) -> torch.Tensor:
+def lab_umma(A: torch.Tensor, B: torch.Tensor, shift: int, sbo_rows: int, base_off_mode: int, kc: int = 64) -> torch.Tensor:
     D = torch.zeros((128, B.shape[0]), dtype=torch.float32, device=A.device)
-    check(_lib.lib().tpz_lab_umma(_ptr(A), A.shape[0], _ptr(B), B.shape[0], shift, sbo_rows, base_off_mode,
+    check(_lib.lib().tpz_lab_umma(_ptr(A), A.shape[0], _ptr(B), B.shape[0], shift, sbo_rows, base_off_mode, kc,
                                   _ptr(D), _stream()))
     return D
+
+
+def lab_tma_stride(A: torch.Tensor, start: int, stride: int, nrows: int) -> torch.Tensor:
+    """Raw shared-memory image (fp16 [nrows, 64], still 128B-swizzled) of a strided TMA box load."""
+    out = torch.zeros((nrows, 64), dtype=torch.float16, device=A.device)
+    check(_lib.lib().tpz_lab_tma_stride(_ptr(A), A.shape[0], start, stride, nrows, _ptr(out), _stream()))
+    return out
