@@ -104,6 +104,30 @@ int tpz_upsample_nearest(const tpz_half* x, int N, int D, int H, int W, int C, i
 int tpz_meanstd(const float* x, long long n, int unbiased, float* stats, double* work4, void* stream);
 int tpz_affine(const float* x, long long n, const float* stats, int inverse, float* y, void* stream);
 
+/* ---- training step of the strided (unfilled) classifier: reference topaz/methods.py:98-165 ----
+ * fp32 NHWC activations, OIHW fp32 weights (the reference's parameter layout; gradients are written in the same
+ * layout so they alias torch .grad storage).  Input coordinate of a tap = o*stride + tap*dil + org.
+ *  tpz_conv_fwd_f32  : y = relu?(conv(x,w) + bias + res[(o*res_stride+res_org)])      (replaces cuDNN fprop)
+ *  tpz_conv_dgrad_f32: dx (=|+=) conv^T(dy,w), optionally masked by relu_mask > 0       (replaces cuDNN bwd-data)
+ *  tpz_conv_wgrad_f32: dw += x (*) dy, db += sum dy   (atomic accumulation; zero first) (replaces cuDNN bwd-filter)
+ *  tpz_ge_binomial_loss_grad: fused GE-binomial loss, metrics and closed-form d/dscore (methods.py:103-151);
+ *      scores/labels = the whole (global) minibatch, dscores written for the local shard [lo,hi)
+ *  tpz_adam_step: fused flat-buffer Adam (torch.optim.Adam defaults) + L2 term + gradient zeroing (methods.py:153-160) */
+int tpz_conv_fwd_f32(const float* x, int N, int H, int W, int Ci, const float* w, const float* bias, int Co, int kh,
+                     int kw, int stride, int dil, int org, const float* res, int res_H, int res_W, int res_org,
+                     int res_stride, int relu, float* y, int Ho, int Wo, void* stream);
+int tpz_conv_dgrad_f32(const float* dy, int N, int Ho, int Wo, int Co, const float* w, int Ci, int kh, int kw, int stride,
+                       int dil, int org, const float* relu_mask, int accumulate, float* dx, int H, int W, void* stream);
+int tpz_conv_wgrad_f32(const float* x, int N, int H, int W, int Ci, const float* dy, int Ho, int Wo, int Co, int kh,
+                       int kw, int stride, int dil, int org, float* dw, float* db, void* stream);
+int tpz_relu_bwd_f32(float* dy, const float* y, long long n, void* stream);
+int tpz_crop_add_f32(float* dx, int N, int H, int W, int C, const float* g, int Ho, int Wo, int org, int stride,
+                     void* stream);
+int tpz_ge_binomial_loss_grad(const float* scores, const double* labels, int B, double pi, double slack, int lo, int hi,
+                              float* dscores, float* out5, void* stream);
+int tpz_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                  float beta2, float eps, int step, float l2, float grad_scale, void* stream);
+
 /* ---- hardware probe used by tests/bring-up (UMMA descriptor row-offset behaviour), not on the product path ---- */
 int tpz_lab_umma(const tpz_half* A, int rowsA, const tpz_half* B, int N, int shift, int sbo_rows, int base_off_mode,
                  int kc, float* D, void* stream);

@@ -109,3 +109,104 @@ def patched():
     finally:
         for n, f in saved.items():
             setattr(ops, n, f)
+
+
+# ------------------------------------------------------------------------------------------------
+# training kernels (topaz_b200.train_engine wrappers) simulated with torch CPU ops
+# ------------------------------------------------------------------------------------------------
+def _nchw(t):
+    return t.permute(0, 3, 1, 2)
+
+
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def _shift_in(x, org, Ho, Wo, k, dil, stride):
+    """input window so that tap 0 of output pixel 0 sits at `org` (org >= 0 in the training nets)."""
+    need_h = (Ho - 1) * stride + (k - 1) * dil + 1
+    need_w = (Wo - 1) * stride + (k - 1) * dil + 1
+    return x[:, org:org + need_h, org:org + need_w]
+
+
+def t_conv_fwd(x, w, b, stride, dil, org, Ho, Wo, relu, res=None, res_org=0, res_stride=1):
+    k = w.shape[-1]
+    xin = _shift_in(x, org, Ho, Wo, k, dil, stride)
+    y = F.conv2d(_nchw(xin), w.detach(), b.detach() if b is not None else None, stride=stride, dilation=dil)
+    y = _nhwc(y)
+    if res is not None:
+        y = y + res[:, res_org:res_org + (Ho - 1) * res_stride + 1:res_stride, res_org:res_org + (Wo - 1) * res_stride + 1:res_stride]
+    return torch.relu(y) if relu else y
+
+
+def t_conv_dgrad(dy, w, stride, dil, org, H, W, mask=None, accumulate=False, out=None):
+    N, Ho, Wo, Co = dy.shape
+    k = w.shape[-1]
+    need_h = (Ho - 1) * stride + (k - 1) * dil + 1
+    need_w = (Wo - 1) * stride + (k - 1) * dil + 1
+    gi = torch.nn.grad.conv2d_input((N, w.shape[1], need_h, need_w), w.detach(), _nchw(dy).contiguous(), stride=stride, dilation=dil)
+    dx = torch.zeros((N, H, W, w.shape[1]))
+    dx[:, org:org + need_h, org:org + need_w] = _nhwc(gi)
+    if accumulate:
+        dx = dx + out
+    if mask is not None:
+        dx = torch.where(mask > 0, dx, torch.zeros_like(dx))
+    if out is not None:
+        out.copy_(dx); return out
+    return dx
+
+
+def t_conv_wgrad(x, dy, w_grad, b_grad, stride, dil, org):
+    N, Ho, Wo, Co = dy.shape
+    k = w_grad.shape[-1]
+    xin = _shift_in(x, org, Ho, Wo, k, dil, stride)
+    gw = torch.nn.grad.conv2d_weight(_nchw(xin).contiguous(), tuple(w_grad.shape), _nchw(dy).contiguous(), stride=stride, dilation=dil)
+    w_grad.add_(gw)
+    if b_grad is not None:
+        b_grad.add_(dy.sum((0, 1, 2)))
+
+
+def t_relu_bwd(dy, y):
+    dy.mul_((y > 0).float())
+
+
+def t_crop_add(dx, g, org, stride):
+    Ho, Wo = g.shape[1], g.shape[2]
+    dx[:, org:org + (Ho - 1) * stride + 1:stride, org:org + (Wo - 1) * stride + 1:stride] += g
+
+
+def t_ge_loss_grad(scores, labels, pi, slack, lo, hi, dscore, out5):
+    from oracle import topaz_oracle as O
+    s = scores.detach().clone().requires_grad_(True)
+    cls, ge, loss = O.ge_binomial_loss(s, labels, pi, slack)
+    loss.backward()
+    dscore.copy_(s.grad[lo:hi].float())
+    prec, tpr, fpr = O.ge_binomial_metrics(scores, labels)
+    out5.copy_(torch.tensor([cls.item(), ge.item(), prec, tpr, fpr]))
+
+
+def t_adam_step(fp, lr, b1, b2, eps, l2):
+    fp.step += 1
+    g = fp.flat_g + l2 * fp.flat_p
+    fp.flat_m.mul_(b1).add_(g, alpha=1 - b1)
+    fp.flat_v.mul_(b2).addcmul_(g, g, value=1 - b2)
+    bc1, bc2 = 1 - b1 ** fp.step, 1 - b2 ** fp.step
+    fp.flat_p.sub_((lr / bc1) * fp.flat_m / (fp.flat_v.sqrt() / math.sqrt(bc2) + eps))
+    fp.flat_g.zero_()
+
+
+@contextlib.contextmanager
+def patched_training():
+    from topaz_b200 import train_engine as T
+    names = {'_conv_fwd': t_conv_fwd, '_conv_dgrad': t_conv_dgrad, '_conv_wgrad': t_conv_wgrad, '_relu_bwd': t_relu_bwd,
+             '_crop_add': t_crop_add, 'ge_loss_grad': t_ge_loss_grad, 'adam_step': t_adam_step,
+             'read_back': lambda d, h: d.tolist()}
+    saved = {n: getattr(T, n) for n in names}
+    try:
+        for n, f in names.items():
+            setattr(T, n, f)
+        with patched():
+            yield
+    finally:
+        for n, f in saved.items():
+            setattr(T, n, f)

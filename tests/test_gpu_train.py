@@ -1,0 +1,109 @@
+"""-m gpu parity of the training path: fp32 fwd/dgrad/wgrad kernels vs torch CPU, the fused GE-binomial loss
+vs the oracle (autograd), and three full GE_binomial.step calls vs the reference golden (loss tuple, the
+gradient of step 1, the parameters after step 3).  fp32 kernels: tolerance 1e-3 per the north star, observed
+~1e-5."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from common import gold, weights_of, rel_err
+from oracle import topaz_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize('N,H,Ci,Co,k,stride,dil,org', [
+    (5, 71, 1, 32, 7, 2, 1, 0), (4, 33, 32, 32, 3, 1, 1, 0), (3, 31, 32, 64, 3, 2, 2, 0), (3, 27, 32, 64, 1, 2, 1, 3),
+    (2, 9, 64, 128, 5, 1, 1, 0), (7, 1, 128, 1, 1, 1, 1, 0),
+])
+def test_conv_f32_kernels(N, H, Ci, Co, k, stride, dil, org):
+    from topaz_b200 import train_engine as T
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(N, Ci, H, H, generator=g)
+    w = torch.randn(Co, Ci, k, k, generator=g) * 0.1
+    b = torch.randn(Co, generator=g) * 0.1
+    xin = x[:, :, org:, org:]
+    ref = F.conv2d(xin, w, b, stride=stride, dilation=dil)
+    Ho = ref.shape[2]
+    xin = xin[:, :, :(Ho - 1) * stride + (k - 1) * dil + 1, :(Ho - 1) * stride + (k - 1) * dil + 1]
+    xd, wd, bd = _nhwc(x).cuda(), w.cuda(), b.cuda()
+    y = T._conv_fwd(xd, wd, bd, stride, dil, org, Ho, Ho, relu=False).cpu()
+    assert max(rel_err(y, _nhwc(ref))) < 1e-4
+    dy = torch.randn(N, Co, Ho, Ho, generator=g)
+    gi = torch.nn.grad.conv2d_input(tuple(xin.shape), w, dy, stride=stride, dilation=dil)
+    gref = torch.zeros_like(x); gref[:, :, org:org + gi.shape[2], org:org + gi.shape[3]] = gi
+    dx = T._conv_dgrad(_nhwc(dy).cuda(), wd, stride, dil, org, H, H).cpu()
+    assert max(rel_err(dx, _nhwc(gref))) < 1e-4
+    gw = torch.nn.grad.conv2d_weight(xin.contiguous(), tuple(w.shape), dy, stride=stride, dilation=dil)
+    dw = torch.zeros_like(w).cuda(); db = torch.zeros_like(b).cuda()
+    T._conv_wgrad(xd, _nhwc(dy).cuda(), dw, db, stride, dil, org)
+    assert max(rel_err(dw.cpu(), gw)) < 1e-4 and max(rel_err(db.cpu(), dy.sum((0, 2, 3)))) < 1e-4
+
+
+def test_ge_loss_kernel_matches_oracle_autograd():
+    from topaz_b200 import train_engine as T
+    g = torch.Generator().manual_seed(3)
+    for B, npos, pi in [(256, 16, 0.035), (64, 4, 0.035), (40, 1, 0.2)]:
+        s = (2.0 * torch.randn(B, generator=g) - 2.0)
+        Y = torch.tensor([1.0] * npos + [0.0] * (B - npos), dtype=torch.float64)
+        sr = s.clone().requires_grad_(True)
+        cls, ge, loss = O.ge_binomial_loss(sr, Y, pi, 1.0)
+        loss.backward()
+        prec, tpr, fpr = O.ge_binomial_metrics(s, Y)
+        ds = torch.empty(B, device='cuda'); out5 = torch.empty(5, device='cuda')
+        T.ge_loss_grad(s.cuda(), Y.cuda(), pi, 1.0, 0, B, ds, out5)
+        np.testing.assert_allclose(out5.cpu().numpy(), [cls.item(), ge.item(), prec, tpr, fpr], rtol=2e-5, atol=1e-6)
+        assert max(rel_err(ds.cpu(), sr.grad.float())) < 1e-4
+        lo, hi = B // 4, B // 2
+        ds2 = torch.empty(hi - lo, device='cuda')
+        T.ge_loss_grad(s.cuda(), Y.cuda(), pi, 1.0, lo, hi, ds2, out5)
+        assert torch.equal(ds2.cpu(), ds.cpu()[lo:hi])
+
+
+def test_three_ge_binomial_steps_match_reference_golden():
+    from topaz_b200.methods import GE_binomial
+    from topaz_b200 import train_engine as T
+    from topaz_b200.model.factory import get_feature_extractor
+    from topaz_b200.model.classifier import LinearClassifier
+    g = gold('ge_binomial_u32'); sd = weights_of(gold('resnet8_u32_pretrained'))
+    m = LinearClassifier(get_feature_extractor('resnet8', units=32, bn=False))
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}); m.cuda(); m.train()
+    optim = torch.optim.Adam(m.parameters(), lr=2e-4)
+    tr = GE_binomial(m, optim, nn.BCEWithLogitsLoss(), float(g['pi']), l2=0.0, slack=1.0)
+    B = int(g['B']); Y = torch.from_numpy(g['Y']).cuda()
+    # unfilled forward of crops vs the reference golden
+    gc = gold('resnet8_u32_pretrained')
+    m.eval()
+    with torch.no_grad():
+        yc = m(torch.from_numpy(gc['crops']).cuda()).cpu().numpy()
+    assert yc.shape == gc['y_crops'].shape and max(rel_err(yc, gc['y_crops'])) < 1e-4
+    m.train()
+    outs = []
+    for step in range(3):
+        X = torch.from_numpy(np.random.default_rng(4000 + step).standard_normal((B, 71, 71)).astype(np.float32)).cuda()
+        if step == 0:     # gradient of step 1
+            fp = T.flat_params(m)
+            score = m(X).view(-1)
+            ds = torch.empty(B, device='cuda'); o5 = torch.empty(5, device='cuda')
+            T.ge_loss_grad(score.contiguous(), Y, tr.pi, tr.slack, 0, B, ds, o5)
+            T.backward(m, ds)
+            for k, p in m.named_parameters():
+                assert max(rel_err(p.grad.cpu().numpy(), g['g1.' + k])) < 1e-3, k
+            fp.flat_g.zero_()
+        outs.append(tr.step(X, Y))
+    np.testing.assert_allclose(np.array(outs), g['outs'], rtol=1e-3, atol=1e-6)
+    for k, p in m.named_parameters():
+        assert max(rel_err(p.detach().cpu().numpy(), g['p3.' + k])) < 1e-3, k
+    # after training, the dense (filled) evaluation forward uses the UPDATED weights (plan cache invalidation)
+    m.eval(); m.fill()
+    x = gc['x']
+    with torch.no_grad():
+        y = m(torch.from_numpy(x).cuda()).cpu().numpy()
+    ref = O.classifier_forward({k: p.detach().cpu().numpy() for k, p in m.state_dict().items()}, x, 'resnet8', 32, filled=True).numpy()
+    assert max(rel_err(y, ref)) < 1e-3

@@ -107,3 +107,44 @@ def test_unet_sim_pretrained_and_seeded():
         y = m(torch.from_numpy(g['x'])).numpy()
     mx, l2 = rel_err(y, g['y'])
     assert mx < 2e-3 and l2 < 2e-3, (mx, l2)
+
+
+def test_ge_binomial_step_wiring_sim():
+    """GE_binomial.step through the train engine (tape, backward, flat params, Adam, optim.state) with
+    simulated kernels reproduces the reference's 3-step golden."""
+    import torch.nn as nn
+    from topaz_b200.methods import GE_binomial
+    g = gold('ge_binomial_u32'); sd = weights_of(gold('resnet8_u32_pretrained'))
+    m = _load(_classifier('resnet8', 32, 1, False), sd); m.train()
+    optim = torch.optim.Adam(m.parameters(), lr=2e-4)
+    tr = GE_binomial(m, optim, nn.BCEWithLogitsLoss(), float(g['pi']), l2=0.0, slack=1.0)
+    assert tr.header == ['loss', 'ge_penalty', 'precision', 'adjusted_precision', 'tpr', 'fpr']
+    B = int(g['B'])
+    Y = torch.from_numpy(g['Y'])
+    outs = []
+    with sim_backend.patched_training():
+        for step in range(3):
+            X = torch.from_numpy(np.random.default_rng(4000 + step).standard_normal((B, 71, 71)).astype(np.float32))
+            if step == 0:
+                from topaz_b200 import train_engine as T
+                fp = T.flat_params(m)
+                score = m(X).view(-1)
+                dscore = torch.empty(B); out5 = torch.empty(5)
+                T.ge_loss_grad(score, Y, tr.pi, tr.slack, 0, B, dscore, out5)
+                T.backward(m, dscore)
+                for k, p in m.named_parameters():
+                    mx, l2 = rel_err(p.grad.numpy(), g['g1.' + k])
+                    assert mx < 5e-4 and l2 < 5e-4, (k, mx, l2)
+                fp.flat_g.zero_()
+            outs.append(tr.step(X, Y))
+    np.testing.assert_allclose(np.array(outs), g['outs'], rtol=5e-4, atol=1e-6)
+    for k, p in m.named_parameters():
+        mx, l2 = rel_err(p.detach().numpy(), g['p3.' + k])
+        assert mx < 1e-4 and l2 < 1e-4, (k, mx, l2)
+    st = optim.state[next(iter(m.parameters()))]
+    assert float(st['step']) == 3.0 and st['exp_avg'].abs().sum() > 0
+    # cached dense plans are invalidated by the in-place parameter update
+    m.eval(); m.fill()
+    with sim_backend.patched(), torch.no_grad():
+        y = m(torch.from_numpy(gold('resnet8_u32_pretrained')['x']))
+    assert torch.isfinite(y).all()

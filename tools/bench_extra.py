@@ -1,0 +1,108 @@
+#!/usr/bin/env python
+"""Secondary workloads of BASELINE.json (configs 3-5) on one GPU or sharded over ranks (torchrun):
+  denoise   : UDenoiseNet `unet` via Denoise.denoise(x, patch_size=1024, padding=500) on 4096x4096 images
+  train     : GE_binomial.step, resnet8_u32, 256 crops of 71x71 (batch sharded over ranks + NCCL all-reduce)
+  denoise3d : UDenoiseNet3D via Denoise3D.denoise(patch 96, padding 48) on an S^3 tomogram (patches sharded)
+One JSON line per workload on rank 0.  Weights: pretrained 2-D unet / resnet8_u32 from the golden fixtures;
+the 3-D model uses seeded random weights (the 11.7 MB pretrained file is not shipped)."""
+import argparse, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
+import numpy as np
+import torch
+import torch.nn as nn
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--workloads', default='denoise,train,denoise3d')
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--tomo', type=int, default=288)
+    args = ap.parse_args()
+    rank, world, local = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    from common import gold, weights_of, seeded_state
+    from common_shapes import unet_shapes
+    from topaz_b200 import ops
+    from topaz_b200.parallel import shard_range
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxms(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for wl in args.workloads.split(','):
+        if wl == 'denoise':
+            from topaz_b200.denoising.models import UDenoiseNet
+            from topaz_b200.denoise import Denoise
+            m = UDenoiseNet(base_width=11, top_width=5)
+            m.load_state_dict({k: torch.from_numpy(v) for k, v in weights_of(gold('unet_pretrained')).items()})
+            dn = Denoise(m)
+            imgs = [(10 + 3 * np.random.default_rng(3000 + rank * 100 + i).standard_normal((4096, 4096))).astype(np.float32) for i in range(2)]
+            dn.denoise(imgs[0], patch_size=1024, padding=500)
+            sync(); l0 = ops.LAUNCH_COUNT; t0 = time.perf_counter()
+            for i in range(args.steps):
+                y = dn.denoise(imgs[i % 2], patch_size=1024, padding=500)
+            torch.cuda.synchronize(); ms = maxms((time.perf_counter() - t0) * 1e3)
+            if rank == 0:
+                print(json.dumps(dict(workload='UDenoiseNet unet Denoise.denoise(4096x4096, patch 1024, padding 500), host numpy in/out',
+                                      n_gpus=world, ms_per_image=ms / args.steps, mpx_s=world * args.steps * 16.777216 / (ms / 1e3),
+                                      tflops=world * args.steps * 29.458 / (ms / 1e3), launches_per_image=(ops.LAUNCH_COUNT - l0) / args.steps,
+                                      finite=bool(np.isfinite(y).all()))))
+        elif wl == 'train':
+            from topaz_b200.methods import GE_binomial
+            from topaz_b200.model.factory import get_feature_extractor
+            from topaz_b200.model.classifier import LinearClassifier
+            m = LinearClassifier(get_feature_extractor('resnet8', units=32, bn=False))
+            m.load_state_dict({k: torch.from_numpy(v) for k, v in weights_of(gold('resnet8_u32_pretrained')).items()})
+            m.cuda(); m.train()
+            tr = GE_binomial(m, torch.optim.Adam(m.parameters(), lr=2e-4), nn.BCEWithLogitsLoss(), 0.035)
+            B = 256; b = B // world
+            Y = torch.tensor([1.0] * 16 + [0.0] * 240, dtype=torch.float64)
+            perm = torch.randperm(B, generator=torch.Generator().manual_seed(0))       # spread positives over shards
+            Xs = [torch.from_numpy(np.random.default_rng(4000 + s).standard_normal((B, 71, 71)).astype(np.float32))[perm][rank * b:(rank + 1) * b].cuda() for s in range(4)]
+            Yl = Y[perm][rank * b:(rank + 1) * b].cuda()
+            for s in range(5):
+                out = tr.step(Xs[s % 4], Yl)
+            sync(); l0 = ops.LAUNCH_COUNT; t0 = time.perf_counter()
+            n = 50
+            for s in range(n):
+                out = tr.step(Xs[s % 4], Yl)
+            torch.cuda.synchronize(); ms = maxms((time.perf_counter() - t0) * 1e3)
+            if rank == 0:
+                print(json.dumps(dict(workload='GE_binomial.step resnet8_u32, global minibatch 256 crops 71x71 (incl. per-step host readback)',
+                                      n_gpus=world, ms_per_step=ms / n, crops_s=n * B / (ms / 1e3), launches_per_step=(ops.LAUNCH_COUNT - l0) / n,
+                                      last_out=out)))
+        elif wl == 'denoise3d':
+            from topaz_b200.denoising.models import UDenoiseNet3D
+            from topaz_b200.denoise import Denoise3D
+            m = UDenoiseNet3D(nf=48, base_width=7, top_width=3)
+            m.load_state_dict({k: torch.from_numpy(v) for k, v in seeded_state(unet_shapes(48, 7, 3, 3), 202).items()})
+            d3 = Denoise3D(m)
+            S = args.tomo
+            tomo = np.random.default_rng(5000).standard_normal((S, S, S)).astype(np.float32)
+            npatch = int(np.ceil(S / 96)) ** 3
+            lo, hi = shard_range(npatch, rank, world)
+            d3.denoise(tomo[:96, :96, :96].copy(), verbose=False)       # warm-up: one 192^3 patch
+            sync(); t0 = time.perf_counter()
+            y = d3.denoise(tomo, patch_size=96, padding=48, verbose=False, patch_range=(lo, hi))
+            torch.cuda.synchronize(); ms = maxms((time.perf_counter() - t0) * 1e3)
+            if rank == 0:
+                print(json.dumps(dict(workload=f'UDenoiseNet3D Denoise3D.denoise({S}^3, patch 96, padding 48), {npatch} patches of 192^3, host numpy in/out',
+                                      n_gpus=world, ms_total=ms, ms_per_patch=ms / max(1, hi - lo), mvox_s=S ** 3 / 1e6 / (ms / 1e3),
+                                      tflops=npatch * 4.784 / (ms / 1e3), finite=bool(np.isfinite(y).all()))))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -36,7 +36,7 @@ class TpzTcConvArgs(C.Structure):
 
 _lib = None
 
-_I, _F, _P, _LL = C.c_int, C.c_float, C.c_void_p, C.c_longlong
+_I, _F, _P, _LL, _D = C.c_int, C.c_float, C.c_void_p, C.c_longlong, C.c_double
 _PROTOS = {
     'tpz_last_error': (C.c_char_p, []),
     'tpz_device_info': (_I, [C.POINTER(_I)] * 3),
@@ -52,6 +52,13 @@ _PROTOS = {
     'tpz_meanstd': (_I, [_P, _LL, _I, _P, _P, _P]),
     'tpz_affine': (_I, [_P, _LL, _P, _I, _P, _P]),
     'tpz_f32_to_f16': (_I, [_P, _LL, _P, _P]),
+    'tpz_conv_fwd_f32': (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P, _I, _I, _P]),
+    'tpz_conv_dgrad_f32': (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P]),
+    'tpz_conv_wgrad_f32': (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    'tpz_relu_bwd_f32': (_I, [_P, _P, _LL, _P]),
+    'tpz_crop_add_f32': (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P]),
+    'tpz_ge_binomial_loss_grad': (_I, [_P, _P, _I, _D, _D, _I, _I, _P, _P, _P]),
+    'tpz_adam_step': (_I, [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _I, _F, _F, _P]),
     'tpz_lab_umma': (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _P]),
     'tpz_lab_tma_stride': (_I, [_P, _I, _I, _I, _I, _P, _P]),
 }

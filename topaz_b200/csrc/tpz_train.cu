@@ -1,0 +1,370 @@
+// Training path of the strided (unfilled) classifier: fp32 forward / dgrad / wgrad convolutions on NHWC fp32
+// activations with the reference's OIHW fp32 weights (gradients land directly in .grad layout), the fused
+// GE-binomial loss + closed-form score gradient, and a fused flat-buffer Adam step.
+// Replaces, for reference topaz/methods.py:98-165 (GE_binomial.step): the cuDNN fwd/bwd-data/bwd-filter
+// calls under loss.backward() (:146), ~25 tiny ATen kernels + the CPU scipy binom.logpmf + .item() syncs of
+// the loss (:103-136), and torch.optim.Adam.step()/zero_grad() (:159-160).
+#include "tpz_common.cuh"
+#include "../../include/topaz_b200.h"
+
+namespace {
+
+struct ConvGeom {
+  int N, H, W, Ci;      // input  (x / dx)
+  int Ho, Wo, Co;       // output (y / dy)
+  int kh, kw, stride, dil, org;   // input coord = o*stride + tap*dil + org
+};
+
+constexpr int TM = 64, TN = 64, TK = 16;
+
+// MODE 0: forward   M = output pixels, N = Co, K = (tap, ci)
+// MODE 1: dgrad     M = input pixels,  N = Ci, K = (tap, co)
+// MODE 2: wgrad     M = Co,            N = (tap, ci), K = output pixels (split over blockIdx.z, atomic accumulate)
+template <int MODE>
+__global__ void __launch_bounds__(256) conv_f32_kernel(ConvGeom g, const float* __restrict__ A0 /*x | dy | dy*/,
+                                                       const float* __restrict__ Wt /*w | w | x*/,
+                                                       const float* __restrict__ bias, const float* __restrict__ res,
+                                                       int res_H, int res_W, int res_org, int res_stride,
+                                                       const float* __restrict__ mask, float* __restrict__ out,
+                                                       int relu, int accumulate, int k_per_split) {
+  __shared__ float As[TK][TM + 4];
+  __shared__ float Bs[TK][TN + 4];
+  const int taps = g.kh * g.kw;
+  long long Mtot, Ntot, Ktot;
+  if (MODE == 0) { Mtot = (long long)g.N * g.Ho * g.Wo; Ntot = g.Co; Ktot = (long long)taps * g.Ci; }
+  else if (MODE == 1) { Mtot = (long long)g.N * g.H * g.W; Ntot = g.Ci; Ktot = (long long)taps * g.Co; }
+  else { Mtot = g.Co; Ntot = (long long)taps * g.Ci; Ktot = (long long)g.N * g.Ho * g.Wo; }
+  const long long m0 = (long long)blockIdx.x * TM;
+  const long long n0 = (long long)blockIdx.y * TN;
+  long long kbeg = 0, kend = Ktot;
+  if (MODE == 2) { kbeg = (long long)blockIdx.z * k_per_split; kend = min(Ktot, kbeg + k_per_split); }
+
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (long long k0 = kbeg; k0 < kend; k0 += TK) {
+    // ---- stage A (TM x TK) and B (TK x TN): 4 elements each per thread ----
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + e * 256;          // 0..1023
+      {
+        const int kk = idx & (TK - 1), mm = idx >> 4;       // consecutive threads -> consecutive k (channel-contiguous)
+        const long long m = m0 + mm, k = k0 + kk;
+        float v = 0.f;
+        if (m < Mtot && k < kend) {
+          if (MODE == 0) {
+            const int ci = k % g.Ci, tap = k / g.Ci;
+            const int r = tap / g.kw, t = tap - r * g.kw;
+            const int ox = m % g.Wo; const long long q = m / g.Wo; const int oy = q % g.Ho; const int n = q / g.Ho;
+            const int iy = oy * g.stride + r * g.dil + g.org, ix = ox * g.stride + t * g.dil + g.org;
+            if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W) v = A0[(((long long)n * g.H + iy) * g.W + ix) * g.Ci + ci];
+          } else if (MODE == 1) {
+            const int co = k % g.Co, tap = k / g.Co;
+            const int r = tap / g.kw, t = tap - r * g.kw;
+            const int ix = m % g.W; const long long q = m / g.W; const int iy = q % g.H; const int n = q / g.H;
+            const int ny = iy - g.org - r * g.dil, nx = ix - g.org - t * g.dil;
+            if (ny >= 0 && nx >= 0 && ny % g.stride == 0 && nx % g.stride == 0) {
+              const int oy = ny / g.stride, ox = nx / g.stride;
+              if (oy < g.Ho && ox < g.Wo) v = A0[(((long long)n * g.Ho + oy) * g.Wo + ox) * g.Co + co];
+            }
+          } else {
+            v = A0[k * g.Co + m];     // dy[p][co]
+          }
+        }
+        As[kk][mm] = v;
+      }
+      {
+        float v = 0.f;
+        if (MODE == 2) {
+          const int nn = idx & (TN - 1), kk = idx >> 6;     // consecutive threads -> consecutive (tap,ci)
+          const long long n = n0 + nn, k = k0 + kk;
+          if (n < Ntot && k < kend) {
+            const int ci = n % g.Ci, tap = n / g.Ci;
+            const int r = tap / g.kw, t = tap - r * g.kw;
+            const int ox = k % g.Wo; const long long q = k / g.Wo; const int oy = q % g.Ho; const int b = q / g.Ho;
+            const int iy = oy * g.stride + r * g.dil + g.org, ix = ox * g.stride + t * g.dil + g.org;
+            if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W) v = Wt[(((long long)b * g.H + iy) * g.W + ix) * g.Ci + ci];
+          }
+          Bs[kk][nn] = v;
+        } else {
+          const int kk = idx & (TK - 1), nn = idx >> 4;
+          const long long n = n0 + nn, k = k0 + kk;
+          if (n < Ntot && k < kend) {
+            if (MODE == 0) {
+              const int ci = k % g.Ci, tap = k / g.Ci;
+              v = Wt[((long long)n * g.Ci + ci) * taps + tap];              // w[co=n][ci][tap]
+            } else {
+              const int co = k % g.Co, tap = k / g.Co;
+              v = Wt[((long long)co * g.Ci + n) * taps + tap];              // w[co][ci=n][tap]
+            }
+          }
+          Bs[kk][nn] = v;
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < TK; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue ----
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long m = m0 + ty * 4 + i;
+    if (m >= Mtot) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long n = n0 + tx * 4 + j;
+      if (n >= Ntot) continue;
+      float v = acc[i][j];
+      if (MODE == 0) {
+        if (bias) v += bias[n];
+        if (res) {
+          const int ox = m % g.Wo; const long long q = m / g.Wo; const int oy = q % g.Ho; const int b = q / g.Ho;
+          v += res[(((long long)b * res_H + (oy * res_stride + res_org)) * res_W + (ox * res_stride + res_org)) * g.Co + n];
+        }
+        if (relu) v = fmaxf(v, 0.f);
+        out[m * g.Co + n] = v;
+      } else if (MODE == 1) {
+        const long long o = m * g.Ci + n;
+        if (accumulate) v += out[o];
+        if (mask) v = mask[o] > 0.f ? v : 0.f;
+        out[o] = v;
+      } else {
+        const int ci = n % g.Ci, tap = n / g.Ci;
+        atomicAdd(&out[((long long)m * g.Ci + ci) * taps + tap], v);       // dw[co=m][ci][tap]
+      }
+    }
+  }
+}
+
+__global__ void relu_bwd_kernel(float* __restrict__ dy, const float* __restrict__ y, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dy[i] = y[i] > 0.f ? dy[i] : 0.f;
+}
+
+// dx[n, o*s+org, o*s+org, c] += g[n, o, o, c]   (identity / strided-identity skip connection backward)
+__global__ void crop_add_kernel(float* __restrict__ dx, int H, int W, const float* __restrict__ g, int N, int Ho, int Wo,
+                                int C, int org, int stride) {
+  const long long total = (long long)N * Ho * Wo * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = i % C; long long q = i / C;
+    const int ox = q % Wo; q /= Wo;
+    const int oy = q % Ho; const int n = q / Ho;
+    dx[(((long long)n * H + (oy * stride + org)) * W + (ox * stride + org)) * C + c] += g[i];
+  }
+}
+
+// db[c] += sum_p dy[p][c]
+__global__ void bias_grad_kernel(const float* __restrict__ dy, long long P, int C, float* __restrict__ db) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int slice = threadIdx.x >> 5;            // 8 slices
+  float s = 0.f;
+  if (c < C)
+    for (long long p = (long long)blockIdx.y * 8 + slice; p < P; p += (long long)gridDim.y * 8) s += dy[p * C + c];
+  __shared__ float sh[8][33];
+  sh[slice][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (slice == 0 && c < C) {
+    for (int k = 1; k < 8; ++k) s += sh[k][threadIdx.x & 31];
+    atomicAdd(&db[c], s);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// GE-binomial loss (methods.py:103-151), one block.  scores: all B_total logits of the (global) minibatch,
+// labels (fp64, as the reference's DataLoader collates them).  Writes dscore for [lo, hi) (the local shard)
+// and out[5] = {classifier_loss, ge_penalty, precision, tpr, fpr}.
+// closed form: dL/ds_i = slack*p_i(1-p_i)[G_mu + (1-2p_i)G_v]  (unlabeled),
+//                                               (sigmoid(s_i) - 1)/|P|                   (positives)
+// -------------------------------------------------------------------------------------------------
+__device__ double block_sum(double v, double* sh) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(~0u, v, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = 0.0;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) r += sh[i];
+  __syncthreads();
+  return r;
+}
+__device__ double block_max(double v, double* sh) {
+  for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(~0u, v, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = -1e300;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) r = fmax(r, sh[i]);
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(256) ge_binomial_kernel(const float* __restrict__ score, const double* __restrict__ label,
+                                                          int B, double pi, double slack, int lo, int hi,
+                                                          float* __restrict__ dscore, float* __restrict__ out5) {
+  __shared__ double sh[8];
+  double s_p_pos = 0, s_p_all = 0, s_p_unl = 0, n_pos = 0, n_unl = 0, mu = 0, var = 0, bce = 0;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const double s = score[i];
+    const double p = (double)(1.0f / (1.0f + expf(-(float)s)));     // torch.sigmoid in fp32
+    s_p_all += p;
+    if (label[i] == 1.0) {
+      n_pos += 1; s_p_pos += p;
+      bce += fmax(s, 0.0) - s + log1p(exp(-fabs(s)));    // BCEWithLogits, target 1 (fp64 like the reference)
+    } else if (label[i] == 0.0) {
+      n_unl += 1; s_p_unl += p; mu += p; var += p * (1.0 - p);
+    }
+  }
+  s_p_pos = block_sum(s_p_pos, sh); s_p_all = block_sum(s_p_all, sh); s_p_unl = block_sum(s_p_unl, sh);
+  n_pos = block_sum(n_pos, sh); n_unl = block_sum(n_unl, sh);
+  mu = (double)(float)block_sum(mu, sh); var = (double)(float)block_sum(var, sh); bce = block_sum(bce, sh);
+  const int N = (int)n_unl;
+  const double denom = var + 1e-10;
+  // q_k = softmax_k(-0.5 (mu-k)^2 / denom);  c_k = -logBinom(k; N, pi)
+  const double lgN = lgamma(N + 1.0), lp = log(pi), l1p = log1p(-pi);
+  double lmax = -1e300;
+  for (int k = threadIdx.x; k <= N; k += blockDim.x) lmax = fmax(lmax, -0.5 * (mu - k) * (mu - k) / denom);
+  lmax = block_max(lmax, sh);
+  double Z = 0, Sc = 0, Sc1 = 0, Sc2 = 0, S1 = 0, S2 = 0;
+  for (int k = threadIdx.x; k <= N; k += blockDim.x) {
+    const double e = exp(-0.5 * (mu - k) * (mu - k) / denom - lmax);
+    const double c = -(double)(float)(lgN - lgamma(k + 1.0) - lgamma(N - k + 1.0) + k * lp + (N - k) * l1p);
+    const double a1 = -(mu - k) / denom;                       // d logit_k / d mu
+    const double a2 = 0.5 * (mu - k) * (mu - k) / (denom * denom);   // d logit_k / d var
+    Z += e; Sc += e * c; Sc1 += e * c * a1; Sc2 += e * c * a2; S1 += e * a1; S2 += e * a2;
+  }
+  Z = block_sum(Z, sh); Sc = block_sum(Sc, sh); Sc1 = block_sum(Sc1, sh); Sc2 = block_sum(Sc2, sh);
+  S1 = block_sum(S1, sh); S2 = block_sum(S2, sh);
+  const double ge = Sc / Z;                                       // -sum_k logBinom_k q_k
+  const double Gmu = Sc1 / Z - ge * (S1 / Z);                     // sum_k q_k (c_k - ge) a1_k
+  const double Gv = Sc2 / Z - ge * (S2 / Z);
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const double s = score[i];
+    const double p = 1.0 / (1.0 + exp(-s));
+    double gsc = 0.0;
+    if (label[i] == 1.0) gsc = (p - 1.0) / n_pos;
+    else if (label[i] == 0.0) gsc = slack * p * (1.0 - p) * (Gmu + (1.0 - 2.0 * p) * Gv);
+    dscore[i - lo] = (float)gsc;
+  }
+  if (threadIdx.x == 0) {
+    out5[0] = (float)(bce / n_pos);
+    out5[1] = (float)ge;
+    out5[2] = (float)(s_p_pos / s_p_all);
+    out5[3] = (float)(s_p_pos / n_pos);
+    out5[4] = (float)(s_p_unl / n_unl);
+  }
+}
+
+// fused Adam on flat buffers (torch.optim.Adam defaults: no weight decay, no amsgrad) + gradient zeroing;
+// optional L2 term l2*w added to the gradient (methods.py:153-157: d/dw of 0.5*l2*sum w^2)
+__global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long long n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float l2,
+                            float gscale) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale + l2 * p[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] -= (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
+    g[i] = 0.f;
+  }
+}
+
+}  // namespace
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+static ConvGeom geom(int N, int H, int W, int Ci, int Ho, int Wo, int Co, int kh, int kw, int stride, int dil, int org) {
+  ConvGeom g; g.N = N; g.H = H; g.W = W; g.Ci = Ci; g.Ho = Ho; g.Wo = Wo; g.Co = Co; g.kh = kh; g.kw = kw;
+  g.stride = stride; g.dil = dil; g.org = org; return g;
+}
+
+extern "C" int tpz_conv_fwd_f32(const float* x, int N, int H, int W, int Ci, const float* w, const float* bias, int Co,
+                                int kh, int kw, int stride, int dil, int org, const float* res, int res_H, int res_W,
+                                int res_org, int res_stride, int relu, float* y, int Ho, int Wo, void* stream) {
+  const ConvGeom g = geom(N, H, W, Ci, Ho, Wo, Co, kh, kw, stride, dil, org);
+  dim3 grid(tpz_div_up((long long)N * Ho * Wo, TM), tpz_div_up(Co, TN), 1);
+  conv_f32_kernel<0><<<grid, 256, 0, ST(stream)>>>(g, x, w, bias, res, res_H, res_W, res_org, res_stride, nullptr, y,
+                                                   relu, 0, 0);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tpz_conv_dgrad_f32(const float* dy, int N, int Ho, int Wo, int Co, const float* w, int Ci, int kh, int kw,
+                                  int stride, int dil, int org, const float* relu_mask, int accumulate, float* dx, int H,
+                                  int W, void* stream) {
+  const ConvGeom g = geom(N, H, W, Ci, Ho, Wo, Co, kh, kw, stride, dil, org);
+  dim3 grid(tpz_div_up((long long)N * H * W, TM), tpz_div_up(Ci, TN), 1);
+  conv_f32_kernel<1><<<grid, 256, 0, ST(stream)>>>(g, dy, w, nullptr, nullptr, 0, 0, 0, 1, relu_mask, dx, 0, accumulate, 0);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tpz_conv_wgrad_f32(const float* x, int N, int H, int W, int Ci, const float* dy, int Ho, int Wo, int Co,
+                                  int kh, int kw, int stride, int dil, int org, float* dw, float* db, void* stream) {
+  const ConvGeom g = geom(N, H, W, Ci, Ho, Wo, Co, kh, kw, stride, dil, org);
+  const long long P = (long long)N * Ho * Wo;
+  const int mt = tpz_div_up(Co, TM), nt = tpz_div_up((long long)kh * kw * Ci, TN);
+  int splits = (148 * 4) / (mt * nt);
+  if (splits < 1) splits = 1;
+  long long kps = (P + splits - 1) / splits;
+  kps = (kps + TK - 1) / TK * TK;
+  splits = (int)((P + kps - 1) / kps);
+  dim3 grid(mt, nt, splits);
+  conv_f32_kernel<2><<<grid, 256, 0, ST(stream)>>>(g, dy, x, nullptr, nullptr, 0, 0, 0, 1, nullptr, dw, 0, 1, (int)kps);
+  if (db) {
+    dim3 bg(tpz_div_up(Co, 32), (unsigned)(P < 4096 ? 1 : 64));
+    bias_grad_kernel<<<bg, 256, 0, ST(stream)>>>(dy, P, Co, db);
+  }
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tpz_relu_bwd_f32(float* dy, const float* y, long long n, void* stream) {
+  int grid = tpz_div_up(n, 256 * 4); if (grid > 148 * 8) grid = 148 * 8;
+  relu_bwd_kernel<<<grid, 256, 0, ST(stream)>>>(dy, y, n);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tpz_crop_add_f32(float* dx, int N, int H, int W, int C, const float* g, int Ho, int Wo, int org, int stride,
+                                void* stream) {
+  const long long total = (long long)N * Ho * Wo * C;
+  int grid = tpz_div_up(total, 256 * 4); if (grid > 148 * 8) grid = 148 * 8;
+  crop_add_kernel<<<grid, 256, 0, ST(stream)>>>(dx, H, W, g, N, Ho, Wo, C, org, stride);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tpz_ge_binomial_loss_grad(const float* scores, const double* labels, int B, double pi, double slack,
+                                         int lo, int hi, float* dscores, float* out5, void* stream) {
+  TPZ_CHECK(B > 0 && lo >= 0 && hi <= B && lo <= hi, "tpz_ge_binomial_loss_grad: bad shard [%d,%d) of %d", lo, hi, B);
+  TPZ_CHECK(pi > 0.0 && pi < 1.0, "tpz_ge_binomial_loss_grad: pi=%g must be in (0,1)", pi);
+  ge_binomial_kernel<<<1, 256, 0, ST(stream)>>>(scores, labels, B, pi, slack, lo, hi, dscores, out5);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tpz_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                             float beta1, float beta2, float eps, int step, float l2, float grad_scale, void* stream) {
+  TPZ_CHECK(step >= 1, "tpz_adam_step: step must be >= 1");
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2 = sqrtf(1.f - powf(beta2, (float)step));
+  int grid = tpz_div_up(n, 256 * 4); if (grid > 148 * 8) grid = 148 * 8;
+  adam_kernel<<<grid, 256, 0, ST(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, bc2, l2,
+                                            grad_scale);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}

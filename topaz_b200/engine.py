@@ -48,7 +48,7 @@ def _bn_affine(bn: Optional[nn.Module], co: int):
 def _state_key(module: nn.Module, extra=()):
     ks = [(p.data_ptr(), p._version) for p in module.parameters()]
     ks += [(b.data_ptr(), b._version) for b in module.buffers()]
-    return (tuple(ks), module.training) + tuple(extra)
+    return (tuple(ks), module.training, module.__dict__.get('_tpz_epoch', 0)) + tuple(extra)
 
 
 def _cached(module: nn.Module, name: str, key, build):
