@@ -77,6 +77,10 @@ int tpz_tc_conv_v2(const TpzTcConvArgs* host_args, void* stream);/* halo-residen
 int tpz_conv_first(const float* x, int N, int D, int H, int W, const float* w, const float* bias, int Co,
                    int kd, int kh, int kw, int dil, int pad, float neg_slope, int pool, tpz_half* out,
                    int out_ld, void* stream);
+/* tpz_im2col_first: im2col of a single-channel 2-D image (k x k taps -> channels, zero padded to ld) so that
+ *   Cin = 1 convs (first BasicConv 7x7, U-Net enc1 11x11, the raw-image slice of U-Net dec1.0) run as a
+ *   1-tap tensor-core GEMM through tpz_tc_conv.  out: fp16 [N][1][Ho][Wo][ld].                       */
+int tpz_im2col_first(const float* x, int N, int H, int W, int k, int pad, tpz_half* out, int ld, void* stream);
 /* tpz_conv_last: Cout = 1 conv from fp16 NDHWC to dense fp32 (classifier 1x1, classifier.py:65; U-Net
  *   dec1.4, denoising/models.py:127,505).  out = (sum + bias) * out_scale + out_shift, then, if
  *   affine_stats (device float[2] = mean,std) is given, out = out*std + mean (denoise.py:295 de-normalise).               */

@@ -56,6 +56,17 @@ def conv_first(x, w, bias, dil, pad, neg_slope, out_ld):
     return out
 
 
+def im2col_first(x, k, pad, ld):
+    N, H, W = x.shape
+    xp = F.pad(x, (pad, pad, pad, pad))
+    Ho, Wo = H + 2 * pad - (k - 1), W + 2 * pad - (k - 1)
+    out = torch.zeros((N, 1, Ho, Wo, ld), dtype=torch.float16)
+    for r in range(k):
+        for s in range(k):
+            out[:, 0, :, :, r * k + s] = xp[:, r:r + Ho, s:s + Wo].half()
+    return out
+
+
 def conv_last(x, c_real, w, bias, kdhw, dil, pad, stats=None, out_scale=1.0, out_shift=0.0):
     N, D, H, W, ld = x.shape
     kd, kh, kw = kdhw
@@ -98,7 +109,7 @@ def affine(x, stats, inverse=False, out=None):
 
 @contextlib.contextmanager
 def patched():
-    names = ['tc_conv', 'conv_first', 'conv_last', 'maxpool2', 'upsample_nearest', 'meanstd', 'affine']
+    names = ['tc_conv', 'conv_first', 'im2col_first', 'conv_last', 'maxpool2', 'upsample_nearest', 'meanstd', 'affine']
     saved = {n: getattr(ops, n) for n in names}
     saved['require_cuda'] = ops.require_cuda
     try:

@@ -44,6 +44,7 @@ _PROTOS = {
     'tpz_tc_conv_v1': (_I, [C.POINTER(TpzTcConvArgs), _P]),
     'tpz_tc_conv_v2': (_I, [C.POINTER(TpzTcConvArgs), _P]),
     'tpz_conv_first': (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _I, _P]),
+    'tpz_im2col_first': (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P]),
     'tpz_conv_last': (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _F, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P]),
     'tpz_conv_generic': (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F,
                               _P, _I, _I, _P, _I, _I, _I, _I, _P]),

@@ -102,6 +102,49 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
 }
 
 // -------------------------------------------------------------------------------------------------
+// im2col of a single-channel image for the tensor-core path of Cin = 1 convs: out[n,y,x,t] = x[n, y-pad+r, x-pad+s]
+// for tap t = r*k+s (zero outside the image), channels [k*k, ld) = 0.  HBM-bound: reads 4 B, writes 2*ld B per pixel.
+// Block = 32x8 output pixels; the (8+k-1) x (32+k-1) input patch is staged in shared memory.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) im2col_first_kernel(const float* __restrict__ x, int N, int H, int W, int k, int pad,
+                                                           __half* __restrict__ out, int ld, int Ho, int Wo) {
+  extern __shared__ float sm_i2c[];
+  const int tw = 32 + k - 1, th = 8 + k - 1;
+  const int n = blockIdx.z, x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+  for (int i = threadIdx.x; i < tw * th; i += 256) {
+    const int yy = i / tw, xx = i - yy * tw;
+    const int gy = y0 - pad + yy, gx = x0 - pad + xx;
+    sm_i2c[i] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? x[((size_t)n * H + gy) * W + gx] : 0.f;
+  }
+  __syncthreads();
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int gx = x0 + lx, gy = y0 + ly;
+  if (gx >= Wo || gy >= Ho) return;
+  __half* o = out + (((size_t)n * Ho + gy) * Wo + gx) * ld;
+  const int taps = k * k;
+  for (int c = 0; c < ld; c += 8) {
+    uint4 u;
+    __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float v[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int t = c + 2 * e + q;
+        float val = 0.f;
+        if (t < taps) {
+          const int r = t / k, s2 = t - r * k;
+          val = sm_i2c[(ly + r) * tw + lx + s2];
+        }
+        v[q] = val;
+      }
+      h[e] = __floats2half2_rn(v[0], v[1]);
+    }
+    *reinterpret_cast<uint4*>(o + c) = u;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
 // Cout = 1 tail conv: one thread per output pixel, 8-channel (16 B) vector loads.
 // -------------------------------------------------------------------------------------------------
 __global__ void conv_last_kernel(const __half* __restrict__ x, int N, int D, int H, int W, int C, int ld,
@@ -356,6 +399,17 @@ extern "C" int tpz_conv_first(const float* x, int N, int D, int H, int W, const 
   dim3 grid(tpz_div_up(Wo, FT_W), tpz_div_up(Ho, FT_H), N * Do);
   conv_first_kernel<<<grid, 256, smem, ST(stream)>>>(x, N, D, H, W, w, bias, Co, kd, kh, kw, dil, pad, neg_slope,
                                                      HP(out), out_ld, Do, Ho, Wo, CoPad);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tpz_im2col_first(const float* x, int N, int H, int W, int k, int pad, tpz_half* out, int ld, void* stream) {
+  TPZ_CHECK(k >= 1 && k * k <= ld && ld % 8 == 0, "tpz_im2col_first: k=%d taps do not fit ld=%d", k, ld);
+  const int Ho = H + 2 * pad - (k - 1), Wo = W + 2 * pad - (k - 1);
+  TPZ_CHECK(Ho > 0 && Wo > 0, "tpz_im2col_first: empty output");
+  const size_t smem = (size_t)(32 + k - 1) * (8 + k - 1) * sizeof(float);
+  dim3 grid(tpz_div_up(Wo, 32), tpz_div_up(Ho, 8), N);
+  im2col_first_kernel<<<grid, 256, smem, ST(stream)>>>(x, N, H, W, k, pad, HP(out), ld, Ho, Wo);
   TPZ_CUDA(cudaGetLastError());
   return 0;
 }

@@ -42,7 +42,7 @@ struct Tc2Params {
   int N, Do, Ho, Wo, Co, CS;
   int tiles_x, tiles_y, num_tiles;
   int ngroups, nkb;
-  int a_stages, b_stages, b_resident, acc_stages;
+  int a_stages, b_stages, b_resident, acc_stages, ntile;
   int a_stage_bytes, b_block_bytes;
   const float* bias;
   float neg_slope;
@@ -89,7 +89,7 @@ __device__ __forceinline__ TileCoord decode_tile(const Tc2Params& p, int tile) {
   t.n = plane / p.Do;
   t.z = plane - t.n * p.Do;
   t.x_first = txq * T2W * p.L + (ph % p.L);
-  t.y_first = tyq * T2H * p.L + (ph / p.L);
+  t.y_first = tyq * (16 * p.ntile) * p.L + (ph / p.L);
   return t;
 }
 
@@ -206,8 +206,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv2_kernel(const __grid_cons
         const uint32_t aph = (p.acc_stages == 2) ? ((tcount >> 1) & 1) : (tcount & 1);
         mbar_wait(&tempty[st], aph ^ 1);
         ptx::tc_fence_after();
-        const uint32_t d0 = tmem_base + (st * 2) * p.CS;
+        const uint32_t d0 = tmem_base + (st * p.ntile) * p.CS;
         const uint32_t d1 = d0 + p.CS;
+        const bool two = p.ntile == 2;
         uint32_t first = 1;
         for (int g = 0; g < p.ngroups; ++g, ++ait) {
           const int s = ait % AS;
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv2_kernel(const __grid_cons
             for (int k = 0; k < KC / 16; ++k) {
               const uint64_t db = ptx::umma_desc(b_addr + k * 32, 8 * ROWB, LAYOUT);
               ptx::umma_f16(d0, ptx::umma_desc(a0 + k * 32, hxb, LAYOUT), db, idesc, (first && k == 0) ? 0u : 1u);
-              ptx::umma_f16(d1, ptx::umma_desc(a1 + k * 32, hxb, LAYOUT), db, idesc, (first && k == 0) ? 0u : 1u);
+              if (two) ptx::umma_f16(d1, ptx::umma_desc(a1 + k * 32, hxb, LAYOUT), db, idesc, (first && k == 0) ? 0u : 1u);
             }
             first = 0;
             if (!p.b_resident) ptx::umma_commit(&bempty[bs]);
@@ -259,11 +260,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv2_kernel(const __grid_cons
       const uint32_t aph = (p.acc_stages == 2) ? ((tcount >> 1) & 1) : (tcount & 1);
       mbar_wait(&tfull[st], aph);
       ptx::tc_fence_after();
-      for (int a = 0; a < 2; ++a) {
+      for (int a = 0; a < p.ntile; ++a) {
         const int gx = tc.x_first + li * p.L;
         const int gy = tc.y_first + (lj + 16 * a) * p.L;
         const bool valid = (gx < p.Wo) && (gy < p.Ho);
-        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (st * 2 + a) * p.CS;
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (st * p.ntile + a) * p.CS;
         const long long opix = (((long long)tc.n * p.Do + tc.z) * p.Ho + gy) * p.Wo + gx;
         __half* orow = p.out ? p.out + opix * p.out_ld + p.out_coff : nullptr;
         const __half* rrow = nullptr;
@@ -352,11 +353,17 @@ static int launch_v2(const TpzTcConvArgs* a, cudaStream_t stream, bool dry) {
   Tc2Params p;
   memset(&p, 0, sizeof(p));
   p.L = L;
+  int cs = 32;
+  while (cs < a->Co) cs <<= 1;
+  p.CS = cs;
+  p.ntile = (4 * cs <= kTmemCols) ? 2 : 1;      // Co = 256: one M=128 tile per CTA so the accumulator can be double-buffered
+  p.acc_stages = 2;
+  const int th = 16 * p.ntile;
   int a_stage = 0;
   for (int s = 0; s < a->nsrc; ++s) {
     const TpzTcSrc& src = a->src[s];
     if (src.kw < 1 || src.kh < 1) return -1;
-    const int hx = T2W + src.kw - 1, hy = T2H + src.kh - 1;
+    const int hx = T2W + src.kw - 1, hy = th + src.kh - 1;
     if ((hx - 1) * L + 1 > 256) return -1;
     const int ext = (hy - 1) * L + 1;
     const int nsplit = (ext + 255) / 256;
@@ -408,10 +415,6 @@ static int launch_v2(const TpzTcConvArgs* a, cudaStream_t stream, bool dry) {
     if (p.b_stages < 2) return -1;
   }
   p.a_stage_bytes = a_stage;
-  int cs = 32;
-  while (cs < a->Co) cs <<= 1;
-  p.CS = cs;
-  p.acc_stages = (4 * cs <= kTmemCols) ? 2 : 1;
   if (dry) return 0;
 
   for (int s = 0; s < a->nsrc; ++s) {
@@ -439,7 +442,7 @@ static int launch_v2(const TpzTcConvArgs* a, cudaStream_t stream, bool dry) {
   p.N = a->N; p.Do = a->Do; p.Ho = a->Ho; p.Wo = a->Wo; p.Co = a->Co;
   const int qW = tpz_div_up(a->Wo, L), qH = tpz_div_up(a->Ho, L);
   p.tiles_x = tpz_div_up(qW, T2W);
-  p.tiles_y = tpz_div_up(qH, T2H);
+  p.tiles_y = tpz_div_up(qH, th);
   const long long ntl = (long long)L * L * p.tiles_x * p.tiles_y * a->Do * a->N;
   TPZ_CHECK(ntl > 0 && ntl < (1ll << 31), "tpz_tc_conv: bad tile count %lld", ntl);
   p.num_tiles = (int)ntl;

@@ -14,8 +14,16 @@ from typing import List, Optional
 import torch
 import torch.nn as nn
 
+import os
+
 from . import ops
 from .ops import ConvPart
+
+# Engine knobs (environment, so the reference CLI signatures stay unchanged):
+#   TPZ_FIRST=simt        Cin=1 first convs on the fp32 SIMT kernel instead of im2col + tensor-core GEMM
+#   TPZ_RESIDUAL=epilogue identity skip added in the epilogue (global loads) instead of an identity k-block in the MMA
+FIRST_ON_TC = os.environ.get('TPZ_FIRST', 'tc') != 'simt'
+RESIDUAL_IN_MMA = os.environ.get('TPZ_RESIDUAL', 'mma') != 'epilogue'
 
 
 def _rup(c: int, m: int = 32) -> int:
@@ -124,8 +132,16 @@ def _build_dense_plan(features, classifier: Optional[nn.Module], device):
     if a is not None:
         w = w * a.view(-1, 1, 1, 1); b = b * a + sh
     c_real = w.shape[0]
-    steps.append(dict(op='first', w=w[:, 0][:, None].contiguous().to(device), b=b.to(device), dil=first['dil'],
-                      pad=features.width // 2, slope=first['slope'], out_ld=_rup(c_real)))
+    k0 = w.shape[-1]
+    if FIRST_ON_TC and first['dil'] == 1 and k0 * k0 <= 128:
+        # Cin = 1: im2col (taps -> channels) then a 1-tap tensor-core GEMM (K = k*k padded to 32)
+        ld = _rup(k0 * k0)
+        p1 = ops.pack_tc_conv([ConvPart(w.reshape(c_real, k0 * k0, 1, 1), ld, 1)], b, _rup(c_real), first['slope'], device)
+        steps.append(dict(op='im2col', k=k0, pad=features.width // 2, ld=ld))
+        steps.append(dict(op='tc', plan=p1, shrink=0, src='cur', dot=False, save_in=False))
+    else:
+        steps.append(dict(op='first', w=w[:, 0][:, None].contiguous().to(device), b=b.to(device), dil=first['dil'],
+                          pad=features.width // 2, slope=first['slope'], out_ld=_rup(c_real)))
     c_store = _rup(c_real)
     nblk = len(blocks)
     for bi, blk in enumerate(blocks[1:], 1):
@@ -163,6 +179,14 @@ def _build_dense_plan(features, classifier: Optional[nn.Module], device):
                 parts.append(ConvPart(blk['proj'], c_store, 1, (edge, edge, 0)))
                 p1 = ops.pack_tc_conv(parts, b1, _rup(co), blk['slope1'], device, out_scale=a1)
                 steps.append(dict(op='tc', plan=p1, shrink=2 * blk['d1'], src='cur+saved', dot=False, save_in=False))
+            elif RESIDUAL_IN_MMA:
+                # identity skip as one extra k-block per channel chunk: A = cropped block input, B = I (exact: x*1.0
+                # accumulated in fp32), so the epilogue issues no global loads
+                eye = torch.eye(co, dtype=torch.float32).reshape(co, co, 1, 1)
+                p1 = ops.pack_tc_conv(parts, b1, _rup(co), blk['slope1'], device, out_scale=a1)
+                pe = ops.pack_tc_conv([ConvPart(w1, _rup(ch), blk['d1']), ConvPart(eye, c_store, 1, (edge, edge, 0))], b1,
+                                      _rup(co), blk['slope1'], device, out_scale=a1)
+                steps.append(dict(op='tc', plan=pe, shrink=2 * blk['d1'], src='cur+saved', dot=False, save_in=False))
             else:
                 p1 = ops.pack_tc_conv(parts, b1, _rup(co), blk['slope1'], device, out_scale=a1, res_scale=a1)
                 steps.append(dict(op='tc', plan=p1, shrink=2 * blk['d1'], src='cur', res=True, edge=edge, dot=False,
@@ -180,6 +204,9 @@ def _run_dense(plan, x: torch.Tensor, want_features: bool):
     for st in plan['steps']:
         if st['op'] == 'first':
             cur = ops.conv_first(x.view(B, 1, H, W), st['w'], st['b'], st['dil'], st['pad'], st['slope'], st['out_ld'])
+            continue
+        if st['op'] == 'im2col':
+            cur = ops.im2col_first(x, st['k'], st['pad'], st['ld'])
             continue
         p = st['plan']
         N, D, Hc, Wc, _ = cur.shape
@@ -257,6 +284,12 @@ def _build_unet_plan(model, device):
 
     plan = dict(dims=dims, nf=nf, nenc=len(enc))
     c1 = enc[0][0]
+    k1 = c1.weight.shape[-1]
+    plan['first_tc'] = None
+    if dims == 2 and FIRST_ON_TC and k1 * k1 <= 128:
+        ld = _rup(k1 * k1)
+        plan['first_tc'] = dict(k=k1, ld=ld, plan=ops.pack_tc_conv(
+            [ConvPart(c1.weight.detach().reshape(nf, k1 * k1, 1, 1), ld, 1)], c1.bias, _rup(nf), slope, device))
     plan['first'] = dict(w=c1.weight.detach().float().reshape((nf,) + ((1,) if dims == 2 else ()) + tuple(c1.weight.shape[2:])).contiguous().to(device),
                          b=c1.bias.detach().float().to(device), pad=c1.weight.shape[-1] // 2, out_ld=_rup(nf),
                          pool=len(enc[0]) > 2)
@@ -316,7 +349,14 @@ def unet_forward(model, x: torch.Tensor, denorm_stats: Optional[torch.Tensor] = 
     if dims == 2:
         xi = xi[:, None]                                  # [N, 1, H, W]
     f = plan['first']
-    h = ops.conv_first(xi, f['w'], f['b'], 1, f['pad'], 0.1, f['out_ld'])
+    if plan['first_tc'] is not None:
+        ft = plan['first_tc']
+        col = ops.im2col_first(xi[:, 0], ft['k'], ft['k'] // 2, ft['ld'])
+        N0, _, H0, W0, _ = col.shape
+        h = torch.empty((N0, 1, H0, W0, ft['plan'].Co), dtype=torch.float16, device=x.device)
+        ops.tc_conv(ft['plan'], [col], (N0, 1, H0, W0), out=h)
+    else:
+        h = ops.conv_first(xi, f['w'], f['b'], 1, f['pad'], 0.1, f['out_ld'])
     skips = []
     if f['pool']:
         h = ops.maxpool2(h, dims)
@@ -344,7 +384,10 @@ def unet_forward(model, x: torch.Tensor, denorm_stats: Optional[torch.Tensor] = 
         else:
             N, D, H, W = xi.shape
             up = ops.upsample_nearest(h, (D, H, W))
-            raw = ops.conv_first(xi, d['onehot'], None, 1, d['k'] // 2, 1.0, d['ntap_store'])
+            if dims == 2:
+                raw = ops.im2col_first(xi[:, 0], d['k'], d['k'] // 2, d['ntap_store'])
+            else:
+                raw = ops.conv_first(xi, d['onehot'], None, 1, d['k'] // 2, 1.0, d['ntap_store'])
             o = torch.empty((N, D, H, W, d['a'].Co), dtype=torch.float16, device=x.device)
             ops.tc_conv(d['a'], [up, raw], (N, D, H, W), out=o)
             o2 = torch.empty((N, D, H, W, d['b'].Co), dtype=torch.float16, device=x.device)

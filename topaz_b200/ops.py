@@ -195,6 +195,15 @@ def conv_first(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], d
     return out
 
 
+def im2col_first(x: torch.Tensor, k: int, pad: int, ld: int) -> torch.Tensor:
+    """x: fp32 [N, H, W].  Returns fp16 [N, 1, Ho, Wo, ld] with channel t = tap (r*k+s), zero beyond k*k."""
+    N, H, W = x.shape
+    Ho, Wo = H + 2 * pad - (k - 1), W + 2 * pad - (k - 1)
+    out = torch.empty((N, 1, Ho, Wo, ld), dtype=torch.float16, device=x.device)
+    _count(1); check(_lib.lib().tpz_im2col_first(_ptr(x), N, H, W, k, pad, _ptr(out), ld, _stream()))
+    return out
+
+
 def conv_last(x: torch.Tensor, c_real: int, w: torch.Tensor, bias: float, kdhw, dil: int, pad: int,
               stats: Optional[torch.Tensor] = None, out_scale: float = 1.0, out_shift: float = 0.0) -> torch.Tensor:
     """x: fp16 [N,D,H,W,ld]; w: fp32 [taps, C] (device) with C = c_real rounded up to 8. Returns fp32 [N,D,H,W]."""
