@@ -117,12 +117,13 @@ __global__ void __launch_bounds__(256) im2col_first_kernel(const float* __restri
     sm_i2c[i] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? x[((size_t)n * H + gy) * W + gx] : 0.f;
   }
   __syncthreads();
-  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
-  const int gx = x0 + lx, gy = y0 + ly;
-  if (gx >= Wo || gy >= Ho) return;
-  __half* o = out + (((size_t)n * Ho + gy) * Wo + gx) * ld;
-  const int taps = k * k;
-  for (int c = 0; c < ld; c += 8) {
+  // consecutive threads write consecutive 16-byte chunks of a pixel's channel vector -> 512 B contiguous per warp store
+  const int taps = k * k, nch = ld >> 3;
+  for (int idx = threadIdx.x; idx < 256 * nch; idx += 256) {
+    const int pix = idx / nch, c = (idx - pix * nch) * 8;
+    const int lx = pix & 31, ly = pix >> 5;
+    const int gx = x0 + lx, gy = y0 + ly;
+    if (gx >= Wo || gy >= Ho) continue;
     uint4 u;
     __half2* h = reinterpret_cast<__half2*>(&u);
 #pragma unroll
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(256) im2col_first_kernel(const float* __restri
       }
       h[e] = __floats2half2_rn(v[0], v[1]);
     }
-    *reinterpret_cast<uint4*>(o + c) = u;
+    *reinterpret_cast<uint4*>(out + (((size_t)n * Ho + gy) * Wo + gx) * ld + c) = u;
   }
 }
 

@@ -134,3 +134,57 @@ extern "C" int tpz_lab_tma_stride(const tpz_half* A, int rowsA, int start, int s
   TPZ_CUDA(cudaGetLastError());
   return 0;
 }
+
+// ---- probe 3: MMA issue rate vs A-operand alignment.  One CTA issues `iters` x (K=64) MMA groups back to back
+// on fixed smem operands (A start row = shift, 8-row-group stride = sbo_rows) and reports SM cycles per MMA. ----
+namespace {
+__global__ void __launch_bounds__(128, 1) lab_rate_kernel(int N, int shift, int sbo_rows, int iters, int two_acc,
+                                                          long long* cycles) {
+  extern __shared__ uint8_t smem_raw3[];
+  const uint32_t raw = ptx::smem_u32(smem_raw3);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw3 + (base - raw);
+  const int a_bytes = 512 * 128, b_bytes = N * 128;
+  uint64_t* done = reinterpret_cast<uint64_t*>(smem + a_bytes + b_bytes);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(done + 1);
+  for (int i = threadIdx.x; i < (a_bytes + b_bytes) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { ptx::mbar_init(done, 1); ptx::fence_barrier_init(); }
+  ptx::fence_proxy_async();
+  if (threadIdx.x < 32) ptx::tmem_alloc<512>(slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *slot;
+  if (threadIdx.x == 0) {
+    const uint32_t a_addr = base + shift * 128, b_addr = base + a_bytes;
+    const uint32_t idesc = ptx::umma_idesc_f16(128, N);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t db = ptx::umma_desc(b_addr + k * 32, 1024, 2, 0);
+        ptx::umma_f16(tmem, ptx::umma_desc(a_addr + k * 32, sbo_rows * 128, 2, 0), db, idesc, 1);
+        if (two_acc)
+          ptx::umma_f16(tmem + 256, ptx::umma_desc(a_addr + 16 * sbo_rows * 128 + k * 32, sbo_rows * 128, 2, 0), db, idesc, 1);
+      }
+    }
+    ptx::umma_commit(done);
+    while (!lab_try(done, 0)) {}
+    const long long t1 = clock64();
+    cycles[0] = t1 - t0;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) ptx::tmem_dealloc<512>(tmem);
+}
+}  // namespace
+
+extern "C" int tpz_lab_umma_rate(int N, int shift, int sbo_rows, int iters, int two_acc, long long* cycles, void* stream) {
+  TPZ_CHECK(N % 16 == 0 && N >= 16 && N <= 256, "tpz_lab_umma_rate: bad N");
+  TPZ_CHECK(shift + 31 * sbo_rows + 8 <= 512, "tpz_lab_umma_rate: tile out of range");
+  const int smem = 512 * 128 + N * 128 + 2048;
+  TPZ_CUDA(cudaFuncSetAttribute(lab_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  lab_rate_kernel<<<1, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(N, shift, sbo_rows, iters, two_acc, cycles);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -356,8 +356,12 @@ static int launch_v2(const TpzTcConvArgs* a, cudaStream_t stream, bool dry) {
   int cs = 32;
   while (cs < a->Co) cs <<= 1;
   p.CS = cs;
-  p.ntile = (4 * cs <= kTmemCols) ? 2 : 1;      // Co = 256: one M=128 tile per CTA so the accumulator can be double-buffered
-  p.acc_stages = 2;
+  // Co = 256: two M=128 tiles fill all 512 TMEM columns (single-buffered accumulators, B shared by both tiles);
+  // TPZ_CO256_NTILE=1 selects one tile per CTA with double-buffered accumulators instead (measured slower on B200:
+  // twice the weight traffic per pixel starves the B ring).
+  static const int co256_ntile = getenv("TPZ_CO256_NTILE") ? atoi(getenv("TPZ_CO256_NTILE")) : 2;
+  p.ntile = (4 * cs <= kTmemCols) ? 2 : (co256_ntile == 1 ? 1 : 2);
+  p.acc_stages = (2 * p.ntile * cs <= kTmemCols) ? 2 : 1;
   const int th = 16 * p.ntile;
   int a_stage = 0;
   for (int s = 0; s < a->nsrc; ++s) {

@@ -273,3 +273,12 @@ def lab_tma_stride(A: torch.Tensor, start: int, stride: int, nrows: int) -> torc
     out = torch.zeros((nrows, 64), dtype=torch.float16, device=A.device)
     check(_lib.lib().tpz_lab_tma_stride(_ptr(A), A.shape[0], start, stride, nrows, _ptr(out), _stream()))
     return out
+
+
+def lab_umma_rate(N: int, shift: int, sbo_rows: int, iters: int = 2000, two_acc: bool = False) -> float:
+    """SM cycles per (M=128, N, K=16) fp16 MMA for an A operand starting at row `shift` with 8-row groups
+    `sbo_rows` rows apart (hardware probe, see csrc/tpz_lab.cu)."""
+    cyc = torch.zeros(1, dtype=torch.int64, device='cuda')
+    check(_lib.lib().tpz_lab_umma_rate(N, shift, sbo_rows, iters, int(two_acc), _ptr(cyc), _stream()))
+    torch.cuda.synchronize()
+    return float(cyc.item()) / (iters * 4 * (2 if two_acc else 1))
