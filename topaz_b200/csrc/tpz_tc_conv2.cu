@@ -146,107 +146,116 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv2_kernel(const __grid_cons
 
   if (warp == 0) {
     // ------------------------------ A producer: one halo tile per (tile, group) ------------------------------
-    if (lane == 0) {
-      uint32_t it = 0;
+    // warp-uniform loop; the TMA instructions are issued by one elected lane (keeps operands in uniform registers)
+    {
+      uint32_t s = 0, ph = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile);
-        for (int g = 0; g < p.ngroups; ++g, ++it) {
-          const int s = it % AS;
-          const uint32_t ph = (it / AS) & 1;
+        for (int g = 0; g < p.ngroups; ++g) {
           mbar_wait(&aempty[s], ph ^ 1);
           const Tc2Group G = p.groups[g];
           const int src = G.src;
           const int hx = p.hx[src];
-          ptx::mbar_expect_tx(&afull[s], (uint32_t)(hx * p.rows_loaded[src] * ROWB));
-          uint8_t* dst = smem + (size_t)s * p.a_stage_bytes;
           const int sr = p.split_rows[src];
-          for (int row0 = 0; row0 < p.rows_loaded[src]; row0 += sr) {
-            ptx::tma_load_5d(dst + (size_t)row0 * hx * ROWB, &p.tmA[src], &afull[s], G.c0, tc.x_first + p.org[src][0],
-                             tc.y_first + p.org[src][1] + row0 * p.L, tc.z + p.org[src][2] + G.dz, tc.n);
+          uint8_t* dst = smem + (size_t)s * p.a_stage_bytes;
+          if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(&afull[s], (uint32_t)(hx * p.rows_loaded[src] * ROWB));
+            for (int row0 = 0; row0 < p.rows_loaded[src]; row0 += sr) {
+              ptx::tma_load_5d(dst + (size_t)row0 * hx * ROWB, &p.tmA[src], &afull[s], G.c0, tc.x_first + p.org[src][0],
+                               tc.y_first + p.org[src][1] + row0 * p.L, tc.z + p.org[src][2] + G.dz, tc.n);
+            }
           }
+          __syncwarp();
+          if (++s == (uint32_t)AS) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 3) {
     // ------------------------------ B producer: weights, resident or streamed per tap ------------------------------
-    if (lane == 0) {
-      if (p.b_resident) {
+    if (p.b_resident) {
+      if (ptx::elect_one()) {
         ptx::mbar_expect_tx(bres, (uint32_t)(p.nkb * p.b_block_bytes));
         for (int kb = 0; kb < p.nkb; ++kb)
           ptx::tma_load_2d(smem + (size_t)AS * p.a_stage_bytes + (size_t)kb * p.b_block_bytes, &p.tmB, bres, 0,
                            kb * p.Co);
-      } else {
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-          for (int g = 0; g < p.ngroups; ++g) {
-            const Tc2Group G = p.groups[g];
-            for (int t = 0; t < G.ntaps; ++t, ++it) {
-              const int s = it % BS;
-              const uint32_t ph = (it / BS) & 1;
-              mbar_wait(&bempty[s], ph ^ 1);
+      }
+    } else {
+      uint32_t s = 0, ph = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int g = 0; g < p.ngroups; ++g) {
+          const Tc2Group G = p.groups[g];
+          for (int t = 0; t < G.ntaps; ++t) {
+            mbar_wait(&bempty[s], ph ^ 1);
+            const int kb = (int)p.taps[G.tap_begin + t].kb;
+            if (ptx::elect_one()) {
               ptx::mbar_expect_tx(&bfull[s], (uint32_t)p.b_block_bytes);
               ptx::tma_load_2d(smem + (size_t)AS * p.a_stage_bytes + (size_t)s * p.b_block_bytes, &p.tmB, &bfull[s], 0,
-                               (int)p.taps[G.tap_begin + t].kb * p.Co);
+                               kb * p.Co);
             }
+            __syncwarp();
+            if (++s == (uint32_t)BS) { s = 0; ph ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0) {
-      const uint32_t idesc = ptx::umma_idesc_f16(128, p.Co);
-      if (p.b_resident) {
-        mbar_wait(bres, 0);
+    // The whole warp walks the (warp-uniform) loops so addresses/descriptors live in uniform registers; lane 0
+    // issues the tcgen05 instructions.  Measured on B200 (tools/layer_bench.py): back-to-back MMAs into ONE
+    // accumulator are latency-chained (N=64: 93 cycles each), alternating two accumulators reaches 48 (N=64) /
+    // 64 (N=128) / 128 (N=256) cycles, so the issue loop must stay well below ~40 instructions per MMA pair.
+    const uint32_t idesc = ptx::umma_idesc_f16(128, p.Co);
+    const uint32_t b_hi = ptx::umma_desc_hi(8 * ROWB, LAYOUT);
+    if (p.b_resident) {
+      mbar_wait(bres, 0);
+      ptx::tc_fence_after();
+    }
+    const bool two = p.ntile == 2;
+    const bool resident = p.b_resident != 0;
+    uint32_t as = 0, aph = 0, bs = 0, bph = 0, st = 0, tph = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[st], tph ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d0 = tmem_base + (st * p.ntile) * p.CS;
+      const uint32_t d1 = d0 + p.CS;
+      uint32_t accf = 0;   // first MMA of the tile overwrites the accumulators
+      for (int g = 0; g < p.ngroups; ++g) {
+        mbar_wait(&afull[as], aph);
         ptx::tc_fence_after();
-      }
-      uint32_t ait = 0, bit = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
-        const uint32_t st = (p.acc_stages == 2) ? (tcount & 1) : 0;
-        const uint32_t aph = (p.acc_stages == 2) ? ((tcount >> 1) & 1) : (tcount & 1);
-        mbar_wait(&tempty[st], aph ^ 1);
-        ptx::tc_fence_after();
-        const uint32_t d0 = tmem_base + (st * p.ntile) * p.CS;
-        const uint32_t d1 = d0 + p.CS;
-        const bool two = p.ntile == 2;
-        uint32_t first = 1;
-        for (int g = 0; g < p.ngroups; ++g, ++ait) {
-          const int s = ait % AS;
-          const uint32_t ph = (ait / AS) & 1;
-          mbar_wait(&afull[s], ph);
-          ptx::tc_fence_after();
-          const Tc2Group G = p.groups[g];
-          const uint32_t hxb = (uint32_t)p.hx[G.src] * ROWB;          // bytes between consecutive tile rows (y)
-          const uint32_t a_tile = a_base + (uint32_t)s * p.a_stage_bytes;
-          for (int t = 0; t < G.ntaps; ++t) {
-            const Tc2Tap T = p.taps[G.tap_begin + t];
-            uint32_t b_addr;
-            int bs = 0;
-            if (p.b_resident) {
-              b_addr = b_base + (uint32_t)T.kb * p.b_block_bytes;
-            } else {
-              bs = bit % BS;
-              const uint32_t bph = (bit / BS) & 1;
-              mbar_wait(&bfull[bs], bph);
-              ptx::tc_fence_after();
-              b_addr = b_base + (uint32_t)bs * p.b_block_bytes;
-              ++bit;
-            }
-            const uint32_t a0 = a_tile + (uint32_t)T.row_off * ROWB;
-            const uint32_t a1 = a0 + 16u * hxb;
+        const Tc2Group G = p.groups[g];
+        const uint32_t hxb = (uint32_t)p.hx[G.src] * ROWB;          // bytes between consecutive tile rows (y)
+        const uint32_t a_hi = ptx::umma_desc_hi(hxb, LAYOUT);
+        const uint32_t a_tile_lo = (a_base + as * (uint32_t)p.a_stage_bytes) >> 4;
+        const uint32_t a1_off_lo = (16u * hxb) >> 4;
+        for (int t = 0; t < G.ntaps; ++t) {
+          const Tc2Tap T = p.taps[G.tap_begin + t];
+          uint32_t b_lo;
+          if (resident) {
+            b_lo = (b_base + (uint32_t)T.kb * p.b_block_bytes) >> 4;
+          } else {
+            mbar_wait(&bfull[bs], bph);
+            ptx::tc_fence_after();
+            b_lo = (b_base + bs * (uint32_t)p.b_block_bytes) >> 4;
+          }
+          const uint32_t a0_lo = a_tile_lo + (((uint32_t)T.row_off * ROWB) >> 4);
+          if (ptx::elect_one()) {
 #pragma unroll
             for (int k = 0; k < KC / 16; ++k) {
-              const uint64_t db = ptx::umma_desc(b_addr + k * 32, 8 * ROWB, LAYOUT);
-              ptx::umma_f16(d0, ptx::umma_desc(a0 + k * 32, hxb, LAYOUT), db, idesc, (first && k == 0) ? 0u : 1u);
-              if (two) ptx::umma_f16(d1, ptx::umma_desc(a1 + k * 32, hxb, LAYOUT), db, idesc, (first && k == 0) ? 0u : 1u);
+              ptx::umma_f16_lohi(d0, a0_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, (k == 0) ? accf : 1u);
+              if (two) ptx::umma_f16_lohi(d1, a0_lo + a1_off_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, (k == 0) ? accf : 1u);
             }
-            first = 0;
-            if (!p.b_resident) ptx::umma_commit(&bempty[bs]);
+            if (!resident) ptx::umma_commit(&bempty[bs]);
           }
-          ptx::umma_commit(&aempty[s]);
+          accf = 1;
+          if (!resident) {
+            if (++bs == (uint32_t)BS) { bs = 0; bph ^= 1; }
+          }
         }
-        ptx::umma_commit(&tfull[st]);
+        if (ptx::elect_one()) ptx::umma_commit(&aempty[as]);
+        if (++as == (uint32_t)AS) { as = 0; aph ^= 1; }
       }
+      if (ptx::elect_one()) ptx::umma_commit(&tfull[st]);
+      if (p.acc_stages == 2) { st ^= 1; if (st == 0) tph ^= 1; } else { tph ^= 1; }
     }
   } else if (warp >= 4) {
     // ------------------------------ epilogue ------------------------------
