@@ -110,7 +110,10 @@ __global__ void __launch_bounds__(256) im2col_first_kernel(const float* __restri
                                                            __half* __restrict__ out, int ld, int Ho, int Wo) {
   extern __shared__ float sm_i2c[];
   const int tw = 32 + k - 1, th = 8 + k - 1;
+  int* s_off = reinterpret_cast<int*>(sm_i2c + tw * th);      // tap -> offset inside the patch (or -1 for zero padding)
   const int n = blockIdx.z, x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+  const int taps = k * k;
+  for (int t = threadIdx.x; t < ld; t += 256) s_off[t] = (t < taps) ? (t / k) * tw + (t % k) : -1;
   for (int i = threadIdx.x; i < tw * th; i += 256) {
     const int yy = i / tw, xx = i - yy * tw;
     const int gy = y0 - pad + yy, gx = x0 - pad + xx;
@@ -118,28 +121,20 @@ __global__ void __launch_bounds__(256) im2col_first_kernel(const float* __restri
   }
   __syncthreads();
   // consecutive threads write consecutive 16-byte chunks of a pixel's channel vector -> 512 B contiguous per warp store
-  const int taps = k * k, nch = ld >> 3;
+  const int nch = ld >> 3;                    // 16-byte chunks per pixel (power of two for ld = 32/64/128)
+  const int sh = 31 - __clz(nch);
   for (int idx = threadIdx.x; idx < 256 * nch; idx += 256) {
-    const int pix = idx / nch, c = (idx - pix * nch) * 8;
+    const int pix = idx >> sh, c = (idx & (nch - 1)) * 8;
     const int lx = pix & 31, ly = pix >> 5;
     const int gx = x0 + lx, gy = y0 + ly;
     if (gx >= Wo || gy >= Ho) continue;
+    const float* bp = sm_i2c + ly * tw + lx;
     uint4 u;
     __half2* h = reinterpret_cast<__half2*>(&u);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      float v[2];
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int t = c + 2 * e + q;
-        float val = 0.f;
-        if (t < taps) {
-          const int r = t / k, s2 = t - r * k;
-          val = sm_i2c[(ly + r) * tw + lx + s2];
-        }
-        v[q] = val;
-      }
-      h[e] = __floats2half2_rn(v[0], v[1]);
+      const int o0 = s_off[c + 2 * e], o1 = s_off[c + 2 * e + 1];
+      h[e] = __floats2half2_rn(o0 >= 0 ? bp[o0] : 0.f, o1 >= 0 ? bp[o1] : 0.f);
     }
     *reinterpret_cast<uint4*>(out + (((size_t)n * Ho + gy) * Wo + gx) * ld + c) = u;
   }
@@ -408,7 +403,8 @@ extern "C" int tpz_im2col_first(const float* x, int N, int H, int W, int k, int 
   TPZ_CHECK(k >= 1 && k * k <= ld && ld % 8 == 0, "tpz_im2col_first: k=%d taps do not fit ld=%d", k, ld);
   const int Ho = H + 2 * pad - (k - 1), Wo = W + 2 * pad - (k - 1);
   TPZ_CHECK(Ho > 0 && Wo > 0, "tpz_im2col_first: empty output");
-  const size_t smem = (size_t)(32 + k - 1) * (8 + k - 1) * sizeof(float);
+  TPZ_CHECK((ld & (ld - 1)) == 0, "tpz_im2col_first: ld=%d must be a power of two", ld);
+  const size_t smem = (size_t)(32 + k - 1) * (8 + k - 1) * sizeof(float) + (size_t)ld * sizeof(int);
   dim3 grid(tpz_div_up(Wo, 32), tpz_div_up(Ho, 8), N);
   im2col_first_kernel<<<grid, 256, smem, ST(stream)>>>(x, N, H, W, k, pad, HP(out), ld, Ho, Wo);
   TPZ_CUDA(cudaGetLastError());

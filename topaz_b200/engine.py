@@ -30,6 +30,14 @@ def _rup(c: int, m: int = 32) -> int:
     return (c + m - 1) // m * m
 
 
+def _tap_ld(taps: int) -> int:
+    """channel count of an im2col tensor: next power of two >= 32 (the im2col kernel indexes chunks with shifts)."""
+    ld = 32
+    while ld < taps:
+        ld *= 2
+    return ld
+
+
 def _slope_of(act) -> float:
     if isinstance(act, nn.ReLU):
         return 0.0
@@ -135,7 +143,7 @@ def _build_dense_plan(features, classifier: Optional[nn.Module], device):
     k0 = w.shape[-1]
     if FIRST_ON_TC and first['dil'] == 1 and k0 * k0 <= 128:
         # Cin = 1: im2col (taps -> channels) then a 1-tap tensor-core GEMM (K = k*k padded to 32)
-        ld = _rup(k0 * k0)
+        ld = _tap_ld(k0 * k0)
         p1 = ops.pack_tc_conv([ConvPart(w.reshape(c_real, k0 * k0, 1, 1), ld, 1)], b, _rup(c_real), first['slope'], device)
         steps.append(dict(op='im2col', k=k0, pad=features.width // 2, ld=ld))
         steps.append(dict(op='tc', plan=p1, shrink=0, src='cur', dot=False, save_in=False))
@@ -287,7 +295,7 @@ def _build_unet_plan(model, device):
     k1 = c1.weight.shape[-1]
     plan['first_tc'] = None
     if dims == 2 and FIRST_ON_TC and k1 * k1 <= 128:
-        ld = _rup(k1 * k1)
+        ld = _tap_ld(k1 * k1)
         plan['first_tc'] = dict(k=k1, ld=ld, plan=ops.pack_tc_conv(
             [ConvPart(c1.weight.detach().reshape(nf, k1 * k1, 1, 1), ld, 1)], c1.bias, _rup(nf), slope, device))
     plan['first'] = dict(w=c1.weight.detach().float().reshape((nf,) + ((1,) if dims == 2 else ()) + tuple(c1.weight.shape[2:])).contiguous().to(device),
@@ -318,7 +326,7 @@ def _build_unet_plan(model, device):
             # dec1: [upsampled (up_c ch), raw image (1 ch)] -> conv,lrelu,conv,lrelu,conv
             ntap = k ** dims
             wraw = ca.weight[:, up_c].reshape(ca.weight.shape[0], ntap)         # [Co, taps]
-            raw_part = ConvPart(wraw.reshape(wraw.shape[0], ntap, 1, 1, 1), _rup(ntap), 1, (0, 0, 0))
+            raw_part = ConvPart(wraw.reshape(wraw.shape[0], ntap, 1, 1, 1), _tap_ld(ntap), 1, (0, 0, 0))
             parts = [ConvPart(ca.weight[:, :up_c], _rup(up_c), 1, same_org(k)), raw_part]
             pa = ops.pack_tc_conv(parts, ca.bias, _rup(ca.weight.shape[0]), slope, device)
             onehot = torch.eye(ntap, dtype=torch.float32).reshape((ntap,) + ((1,) if dims == 2 else ()) + (k,) * dims)
@@ -329,7 +337,7 @@ def _build_unet_plan(model, device):
             cin = cc.weight.shape[1]
             wl = torch.zeros((kl ** dims, _rup(cin)), dtype=torch.float32)
             wl[:, :cin] = cc.weight.detach().float().cpu()[0].reshape(cin, -1).t()
-            plan['dec'][1] = dict(a=pa, b=pb, onehot=onehot.contiguous().to(device), k=k, ntap_store=_rup(ntap),
+            plan['dec'][1] = dict(a=pa, b=pb, onehot=onehot.contiguous().to(device), k=k, ntap_store=_tap_ld(ntap),
                                   last_w=wl.contiguous().to(device), last_b=float(cc.bias.detach()[0]),
                                   last_k=(kl if dims == 3 else 1, kl, kl), last_pad=kl // 2, last_c=cin)
     return plan
