@@ -124,6 +124,19 @@ int tpz_conv_dgrad_f32(const float* dy, int N, int Ho, int Wo, int Co, const flo
                        int dil, int org, const float* relu_mask, int accumulate, float* dx, int H, int W, void* stream);
 int tpz_conv_wgrad_f32(const float* x, int N, int H, int W, int Ci, const float* dy, int Ho, int Wo, int Co, int kh,
                        int kw, int stride, int dil, int org, float* dw, float* db, void* stream);
+/* Tensor-core (mma.sync, error-compensated 3xTF32) variants for channel counts that are multiples of 16/32.
+ * Weights come from tpz_train_repack: OIHW -> [tap][ci][co] (forward) and [tap][co][ci] (dgrad); `descs` is a device
+ * array of {int64 src, dst_fwd, dst_dg; int32 Co, Ci, taps, pad} (element offsets into flat_params / packed). */
+int tpz_train_repack(const float* flat_params, const void* descs, int ndesc, long long max_elems, float* packed, void* stream);
+int tpz_conv_fwd_mma(const float* x, int N, int H, int W, int Ci, const float* w_fwd_packed, const float* bias, int Co,
+                     int kh, int kw, int stride, int dil, int org, const float* res, int res_H, int res_W, int res_org,
+                     int res_stride, int relu, float* y, int Ho, int Wo, void* stream);
+int tpz_conv_dgrad_mma(const float* dy, int N, int Ho, int Wo, int Co, const float* w_dg_packed, int Ci, int kh, int kw,
+                       int stride, int dil, int org, const float* relu_mask, int accumulate, float* dx, int H, int W,
+                       void* stream);
+int tpz_conv_wgrad_mma(const float* x, int N, int H, int W, int Ci, const float* dy, int Ho, int Wo, int Co, int kh, int kw,
+                       int stride, int dil, int org, float* dw, void* stream);
+int tpz_bias_grad_f32(const float* dy, long long P, int C, float* db, void* stream);   /* db[c] += sum_p dy[p][c] */
 int tpz_relu_bwd_f32(float* dy, const float* y, long long n, void* stream);
 int tpz_crop_add_f32(float* dx, int N, int H, int W, int C, const float* g, int Ho, int Wo, int org, int stride,
                      void* stream);

@@ -211,7 +211,7 @@ def patched_training():
     from topaz_b200 import train_engine as T
     names = {'_conv_fwd': t_conv_fwd, '_conv_dgrad': t_conv_dgrad, '_conv_wgrad': t_conv_wgrad, '_relu_bwd': t_relu_bwd,
              '_crop_add': t_crop_add, 'ge_loss_grad': t_ge_loss_grad, 'adam_step': t_adam_step,
-             'read_back': lambda d, h: d.tolist()}
+             'read_back': lambda d, h: d.tolist(), '_repack': lambda fp: None}
     saved = {n: getattr(T, n) for n in names}
     try:
         for n, f in names.items():

@@ -107,3 +107,41 @@ def test_three_ge_binomial_steps_match_reference_golden():
         y = m(torch.from_numpy(x).cuda()).cpu().numpy()
     ref = O.classifier_forward({k: p.detach().cpu().numpy() for k, p in m.state_dict().items()}, x, 'resnet8', 32, filled=True).numpy()
     assert max(rel_err(y, ref)) < 1e-3
+
+
+@pytest.mark.parametrize('N,H,Ci,Co,k,stride,dil,org', [
+    (4, 33, 32, 32, 3, 1, 1, 0), (3, 31, 32, 64, 3, 2, 2, 0), (3, 27, 32, 64, 1, 2, 1, 3), (2, 11, 64, 64, 3, 1, 2, 0),
+    (2, 9, 64, 128, 5, 1, 1, 0), (300, 5, 64, 64, 3, 1, 1, 0),
+])
+def test_conv_mma_kernels_match_fp32(N, H, Ci, Co, k, stride, dil, org):
+    """3xTF32 tensor-core fwd / dgrad / wgrad vs torch CPU fp32 (fp32-level accuracy expected)."""
+    import ctypes as C
+    from topaz_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(N, Ci, H, H, generator=g)
+    w = torch.randn(Co, Ci, k, k, generator=g) * 0.1
+    b = torch.randn(Co, generator=g) * 0.1
+    xin = x[:, :, org:, org:]
+    ref = F.conv2d(xin, w, b, stride=stride, dilation=dil)
+    Ho = ref.shape[2]
+    ext = (Ho - 1) * stride + (k - 1) * dil + 1
+    xin = xin[:, :, :ext, :ext]
+    P = lambda t: C.c_void_p(t.data_ptr())
+    xd, bd = _nhwc(x).cuda(), b.cuda()
+    wf = w.permute(2, 3, 1, 0).contiguous().cuda()      # [tap][ci][co]
+    wg = w.permute(2, 3, 0, 1).contiguous().cuda()      # [tap][co][ci]
+    y = torch.empty(N, Ho, Ho, Co, device='cuda')
+    _lib.check(L.tpz_conv_fwd_mma(P(xd), N, H, H, Ci, P(wf), P(bd), Co, k, k, stride, dil, org, None, 0, 0, 0, 1, 0, P(y), Ho, Ho, None))
+    assert max(rel_err(y.cpu(), _nhwc(ref))) < 2e-5
+    dy = torch.randn(N, Co, Ho, Ho, generator=g)
+    dyd = _nhwc(dy).cuda()
+    gi = torch.nn.grad.conv2d_input(tuple(xin.shape), w, dy, stride=stride, dilation=dil)
+    gref = torch.zeros_like(x); gref[:, :, org:org + ext, org:org + ext] = gi
+    dx = torch.empty(N, H, H, Ci, device='cuda')
+    _lib.check(L.tpz_conv_dgrad_mma(P(dyd), N, Ho, Ho, Co, P(wg), Ci, k, k, stride, dil, org, None, 0, P(dx), H, H, None))
+    assert max(rel_err(dx.cpu(), _nhwc(gref))) < 2e-5
+    gw = torch.nn.grad.conv2d_weight(xin.contiguous(), tuple(w.shape), dy, stride=stride, dilation=dil)
+    dw = torch.zeros_like(w).cuda()
+    _lib.check(L.tpz_conv_wgrad_mma(P(xd), N, H, H, Ci, P(dyd), Ho, Ho, Co, k, k, stride, dil, org, P(dw), None))
+    assert max(rel_err(dw.cpu(), gw)) < 2e-5

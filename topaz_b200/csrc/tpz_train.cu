@@ -332,6 +332,13 @@ extern "C" int tpz_conv_wgrad_f32(const float* x, int N, int H, int W, int Ci, c
   return 0;
 }
 
+extern "C" int tpz_bias_grad_f32(const float* dy, long long P, int C, float* db, void* stream) {
+  dim3 bg(tpz_div_up(C, 32), (unsigned)(P < 4096 ? 1 : 64));
+  bias_grad_kernel<<<bg, 256, 0, ST(stream)>>>(dy, P, C, db);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int tpz_relu_bwd_f32(float* dy, const float* y, long long n, void* stream) {
   int grid = tpz_div_up(n, 256 * 4); if (grid > 148 * 8) grid = 148 * 8;
   relu_bwd_kernel<<<grid, 256, 0, ST(stream)>>>(dy, y, n);

@@ -1,0 +1,407 @@
+// Tensor-core (mma.sync TF32, error-compensated "3xTF32") versions of the training convolutions for channel
+// counts that are multiples of 16/32: forward and data-gradient as one gather-GEMM kernel, weight-gradient as a
+// split-K GEMM.  fp32 in / fp32 out; the 3-term split (a = a_hi + a_lo, a*b ~ a_hi*b_hi + a_hi*b_lo + a_lo*b_hi)
+// keeps fp32-level accuracy so gradients match the fp32 CPU reference to ~1e-6.
+// The training step is latency-bound: these kernels matter for instruction count, not peak FLOPs;
+// the legacy mma.sync path is used on purpose (tiny, ragged tiles; tcgen05 needs 128-row fp16 tiles).
+// Same reference call sites as tpz_train.cu (topaz/methods.py:103,146).
+#include "tpz_common.cuh"
+#include "../../include/topaz_b200.h"
+
+#ifndef TPZ_3XTF32
+#define TPZ_3XTF32 1
+#endif
+
+namespace {
+
+struct MGeom {
+  int N, H, W, Ci;   // conv input  (x / dx)
+  int Ho, Wo, Co;    // conv output (y / dy)
+  int kh, kw, stride, dil, org;
+};
+
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// c += a*b with a,b fp32 fragments (compensated)
+__device__ __forceinline__ void mma_f32x3(float (&c)[4], const float (&a)[4], const float (&b)[2]) {
+  uint32_t ah[4], bh[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) ah[i] = to_tf32(a[i]);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) bh[i] = to_tf32(b[i]);
+#if TPZ_3XTF32
+  uint32_t al[4], bl[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) al[i] = to_tf32(a[i] - __uint_as_float(ah[i]));
+#pragma unroll
+  for (int i = 0; i < 2; ++i) bl[i] = to_tf32(b[i] - __uint_as_float(bh[i]));
+  mma_tf32(c, al, bh);
+  mma_tf32(c, ah, bl);
+#endif
+  mma_tf32(c, ah, bh);
+}
+
+// -------------------------------------------------------------------------------------------------
+// weight repack: OIHW [Co][Ci][taps] -> fwd layout [tap][ci][co] and dgrad layout [tap][co][ci]
+// -------------------------------------------------------------------------------------------------
+struct RepackDesc { long long src, dst_fwd, dst_dg; int Co, Ci, taps, pad; };
+
+__global__ void repack_kernel(const float* __restrict__ flat, const RepackDesc* __restrict__ descs, float* __restrict__ packed) {
+  const RepackDesc d = descs[blockIdx.y];
+  const long long n = (long long)d.Co * d.Ci * d.taps;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int tap = i % d.taps;
+    const long long q = i / d.taps;
+    const int ci = q % d.Ci, co = q / d.Ci;
+    const float v = flat[d.src + i];
+    packed[d.dst_fwd + ((long long)tap * d.Ci + ci) * d.Co + co] = v;
+    packed[d.dst_dg + ((long long)tap * d.Co + co) * d.Ci + ci] = v;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// forward / dgrad gather-GEMM.  M = pixels of the OUTPUT tensor of this op (fwd: y pixels, dgrad: x pixels),
+// K = (tap, source channel), N = output channels.  A(m,(tap,c)) = SRC[srcpix(m,tap)][c], B = packed weights.
+// -------------------------------------------------------------------------------------------------
+constexpr int GBM = 128, GBK = 16, GAS = 20;   // A smem row stride (floats): conflict-free fragment reads
+
+template <int BN, int MODE>   // MODE 0 fwd, 1 dgrad
+__global__ void __launch_bounds__(256) conv_mma_kernel(MGeom g, const float* __restrict__ src, const float* __restrict__ wpk,
+                                                       const float* __restrict__ bias, const float* __restrict__ res,
+                                                       int res_H, int res_W, int res_org, int res_stride,
+                                                       const float* __restrict__ mask, float* __restrict__ out, int relu,
+                                                       int accumulate) {
+  constexpr int BS = BN + 8;
+  constexpr int WN = BN / 32;            // warps along N (1 or 2)
+  constexpr int WM = 8 / WN;             // warps along M (8 or 4)
+  constexpr int MT = GBM / WM / 16;      // m16 tiles per warp (1 or 2)
+  __shared__ __align__(16) float As[2][GBM][GAS];
+  __shared__ __align__(16) float Bs[2][GBK][BS];
+
+  const int taps = g.kh * g.kw;
+  const int Cs = MODE == 0 ? g.Ci : g.Co;      // source channels (K per tap)
+  const int Nn = MODE == 0 ? g.Co : g.Ci;      // output channels
+  const int MH = MODE == 0 ? g.Ho : g.H, MW = MODE == 0 ? g.Wo : g.W;
+  const int SH = MODE == 0 ? g.H : g.Ho, SW = MODE == 0 ? g.W : g.Wo;
+  const long long Mtot = (long long)g.N * MH * MW;
+  const long long m0 = (long long)blockIdx.x * GBM;
+  const int n0 = blockIdx.y * BN;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gq = lane >> 2, tq = lane & 3;
+  const int wm = warp / WN, wn = warp % WN;
+
+  // staging roles: A: 2 rows per thread (r, r+64), one float4 (quad) each; B: GBK*BN/4 float4 over 256 threads
+  const int a_row = tid >> 2, a_quad = tid & 3;
+  int an[2], ay[2], ax[2];
+  bool arow_ok[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const long long m = m0 + a_row + h * 64;
+    arow_ok[h] = m < Mtot;
+    const long long mm = arow_ok[h] ? m : 0;
+    ax[h] = mm % MW;
+    const long long q = mm / MW;
+    ay[h] = q % MH;
+    an[h] = q / MH;
+  }
+  const int cchunks = Cs / GBK;
+  const int nk = taps * cchunks;
+
+  float acc[MT][4][4];
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+
+  float4 ra[2], rb[(GBK * BN / 4 + 255) / 256];
+  auto load_chunk = [&](int kc) {
+    const int tap = kc / cchunks, c0 = (kc - tap * cchunks) * GBK;
+    const int r = tap / g.kw, t = tap - r * g.kw;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (arow_ok[h]) {
+        int sy, sx;
+        bool ok;
+        if (MODE == 0) {
+          sy = ay[h] * g.stride + r * g.dil + g.org;
+          sx = ax[h] * g.stride + t * g.dil + g.org;
+          ok = sy >= 0 && sy < SH && sx >= 0 && sx < SW;
+        } else {
+          const int ny = ay[h] - g.org - r * g.dil, nx = ax[h] - g.org - t * g.dil;
+          ok = ny >= 0 && nx >= 0 && (ny % g.stride) == 0 && (nx % g.stride) == 0;
+          sy = ny / g.stride; sx = nx / g.stride;
+          ok = ok && sy < SH && sx < SW;
+        }
+        if (ok) v = *reinterpret_cast<const float4*>(src + (((long long)an[h] * SH + sy) * SW + sx) * Cs + c0 + a_quad * 4);
+      }
+      ra[h] = v;
+    }
+#pragma unroll
+    for (int e = 0; e < (GBK * BN / 4 + 255) / 256; ++e) {
+      const int idx = tid + e * 256;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < GBK * BN / 4) {
+        const int kk = idx / (BN / 4), nq = idx - kk * (BN / 4);
+        const int n = n0 + nq * 4;
+        if (n < Nn) v = *reinterpret_cast<const float4*>(wpk + ((long long)tap * Cs + c0 + kk) * Nn + n);
+      }
+      rb[e] = v;
+    }
+  };
+  auto store_chunk = [&](int buf) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) *reinterpret_cast<float4*>(&As[buf][a_row + h * 64][a_quad * 4]) = ra[h];
+#pragma unroll
+    for (int e = 0; e < (GBK * BN / 4 + 255) / 256; ++e) {
+      const int idx = tid + e * 256;
+      if (idx < GBK * BN / 4) {
+        const int kk = idx / (BN / 4), nq = idx - kk * (BN / 4);
+        *reinterpret_cast<float4*>(&Bs[buf][kk][nq * 4]) = rb[e];
+      }
+    }
+  };
+
+  load_chunk(0);
+  store_chunk(0);
+  __syncthreads();
+  for (int kc = 0; kc < nk; ++kc) {
+    const int buf = kc & 1;
+    if (kc + 1 < nk) load_chunk(kc + 1);
+#pragma unroll
+    for (int k8 = 0; k8 < GBK; k8 += 8) {
+      float bf[4][2];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        bf[j][0] = Bs[buf][k8 + tq][wn * 32 + j * 8 + gq];
+        bf[j][1] = Bs[buf][k8 + tq + 4][wn * 32 + j * 8 + gq];
+      }
+#pragma unroll
+      for (int i = 0; i < MT; ++i) {
+        const int rb0 = wm * (GBM / WM) + i * 16;
+        float af[4];
+        af[0] = As[buf][rb0 + gq][k8 + tq];
+        af[1] = As[buf][rb0 + gq + 8][k8 + tq];
+        af[2] = As[buf][rb0 + gq][k8 + tq + 4];
+        af[3] = As[buf][rb0 + gq + 8][k8 + tq + 4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mma_f32x3(acc[i][j], af, bf[j]);
+      }
+    }
+    if (kc + 1 < nk) store_chunk(buf ^ 1);
+    __syncthreads();
+  }
+
+  // epilogue: c0:(g,2t) c1:(g,2t+1) c2:(g+8,2t) c3:(g+8,2t+1)
+#pragma unroll
+  for (int i = 0; i < MT; ++i) {
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const long long m = m0 + wm * (GBM / WM) + i * 16 + gq + hh * 8;
+      if (m >= Mtot) continue;
+      long long rbase = 0;
+      if (MODE == 0 && res) {
+        const int ox = m % g.Wo; const long long q = m / g.Wo; const int oy = q % g.Ho; const int b = q / g.Ho;
+        rbase = (((long long)b * res_H + (oy * res_stride + res_org)) * res_W + (ox * res_stride + res_org)) * g.Co;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + wn * 32 + j * 8 + tq * 2;
+        if (n >= Nn) continue;
+        float v0 = acc[i][j][hh * 2], v1 = acc[i][j][hh * 2 + 1];
+        const long long o = m * Nn + n;
+        if (MODE == 0) {
+          if (bias) { v0 += bias[n]; v1 += bias[n + 1]; }
+          if (res) { v0 += res[rbase + n]; v1 += res[rbase + n + 1]; }
+          if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+        } else {
+          if (accumulate) { v0 += out[o]; v1 += out[o + 1]; }
+          if (mask) { v0 = mask[o] > 0.f ? v0 : 0.f; v1 = mask[o + 1] > 0.f ? v1 : 0.f; }
+        }
+        *reinterpret_cast<float2*>(out + o) = make_float2(v0, v1);
+      }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// wgrad: dw[co][ci][tap] += sum_p dy[p][co] * x[p'(p,tap)][ci].  CTA = (64 co x 64 ci) tile of one tap over a
+// K-split of the output pixels; fp32 atomics accumulate the splits (dw is zeroed by the Adam kernel).
+// -------------------------------------------------------------------------------------------------
+constexpr int WBM = 64, WBN = 64, WBK = 16, WS = 72;
+
+__global__ void __launch_bounds__(256) wgrad_mma_kernel(MGeom g, const float* __restrict__ x, const float* __restrict__ dy,
+                                                        float* __restrict__ dw, int k_per_split) {
+  __shared__ __align__(16) float As[2][WBK][WS];   // [pixel][co]
+  __shared__ __align__(16) float Bs[2][WBK][WS];   // [pixel][ci]
+  const int taps = g.kh * g.kw;
+  const int tap = blockIdx.z % taps, split = blockIdx.z / taps;
+  const int r = tap / g.kw, t = tap - r * g.kw;
+  const int co0 = blockIdx.x * WBM, ci0 = blockIdx.y * WBN;
+  const long long P = (long long)g.N * g.Ho * g.Wo;
+  const long long pbeg = (long long)split * k_per_split;
+  const long long pend = min(P, pbeg + k_per_split);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gq = lane >> 2, tq = lane & 3;
+  const int wm = warp >> 2, wn = warp & 3;       // 2 x 4 warps, warp tile 32 (co) x 16 (ci)
+  // staging: 16 pixels x 64 channels = 256 float4: thread -> (pixel = tid/16, quad = tid%16)
+  const int s_p = tid >> 4, s_q = tid & 15;
+
+  float acc[2][2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+
+  float4 ra, rb;
+  auto load_chunk = [&](long long p0) {
+    const long long p = p0 + s_p;
+    ra = make_float4(0.f, 0.f, 0.f, 0.f); rb = ra;
+    if (p < pend) {
+      if (co0 + s_q * 4 < g.Co) ra = *reinterpret_cast<const float4*>(dy + p * g.Co + co0 + s_q * 4);
+      const int ox = p % g.Wo; const long long q = p / g.Wo; const int oy = q % g.Ho; const int n = q / g.Ho;
+      const int iy = oy * g.stride + r * g.dil + g.org, ix = ox * g.stride + t * g.dil + g.org;
+      if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W && ci0 + s_q * 4 < g.Ci)
+        rb = *reinterpret_cast<const float4*>(x + (((long long)n * g.H + iy) * g.W + ix) * g.Ci + ci0 + s_q * 4);
+    }
+  };
+  auto store_chunk = [&](int buf) {
+    *reinterpret_cast<float4*>(&As[buf][s_p][s_q * 4]) = ra;
+    *reinterpret_cast<float4*>(&Bs[buf][s_p][s_q * 4]) = rb;
+  };
+  if (pbeg < pend) {
+    load_chunk(pbeg);
+    store_chunk(0);
+  }
+  __syncthreads();
+  int it = 0;
+  for (long long p0 = pbeg; p0 < pend; p0 += WBK, ++it) {
+    const int buf = it & 1;
+    const bool more = p0 + WBK < pend;
+    if (more) load_chunk(p0 + WBK);
+#pragma unroll
+    for (int k8 = 0; k8 < WBK; k8 += 8) {
+      float bf[2][2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        bf[j][0] = Bs[buf][k8 + tq][wn * 16 + j * 8 + gq];
+        bf[j][1] = Bs[buf][k8 + tq + 4][wn * 16 + j * 8 + gq];
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int mb = wm * 32 + i * 16;
+        float af[4];
+        af[0] = As[buf][k8 + tq][mb + gq];
+        af[1] = As[buf][k8 + tq][mb + gq + 8];
+        af[2] = As[buf][k8 + tq + 4][mb + gq];
+        af[3] = As[buf][k8 + tq + 4][mb + gq + 8];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) mma_f32x3(acc[i][j], af, bf[j]);
+      }
+    }
+    if (more) store_chunk(buf ^ 1);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int co = co0 + wm * 32 + i * 16 + gq + hh * 8;
+      if (co >= g.Co) continue;
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int ci = ci0 + wn * 16 + j * 8 + tq * 2 + e;
+          if (ci < g.Ci) atomicAdd(&dw[((long long)co * g.Ci + ci) * taps + tap], acc[i][j][hh * 2 + e]);
+        }
+    }
+}
+
+}  // namespace
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+static MGeom mgeom(int N, int H, int W, int Ci, int Ho, int Wo, int Co, int kh, int kw, int stride, int dil, int org) {
+  MGeom g; g.N = N; g.H = H; g.W = W; g.Ci = Ci; g.Ho = Ho; g.Wo = Wo; g.Co = Co; g.kh = kh; g.kw = kw;
+  g.stride = stride; g.dil = dil; g.org = org; return g;
+}
+
+// descs: device array of {src, dst_fwd, dst_dg (element offsets), Co, Ci, taps, pad}; one launch repacks all layers
+extern "C" int tpz_train_repack(const float* flat_params, const void* descs, int ndesc, long long max_elems, float* packed,
+                                void* stream) {
+  if (ndesc == 0) return 0;
+  dim3 grid(tpz_div_up(max_elems, 256 * 4), ndesc);
+  repack_kernel<<<grid, 256, 0, ST(stream)>>>(flat_params, reinterpret_cast<const RepackDesc*>(descs), packed);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tpz_conv_fwd_mma(const float* x, int N, int H, int W, int Ci, const float* w_fwd_packed, const float* bias,
+                                int Co, int kh, int kw, int stride, int dil, int org, const float* res, int res_H, int res_W,
+                                int res_org, int res_stride, int relu, float* y, int Ho, int Wo, void* stream) {
+  TPZ_CHECK(Ci % 16 == 0 && Co % 32 == 0, "tpz_conv_fwd_mma: needs Ci%%16==0 and Co%%32==0 (Ci=%d Co=%d)", Ci, Co);
+  const MGeom g = mgeom(N, H, W, Ci, Ho, Wo, Co, kh, kw, stride, dil, org);
+  const long long M = (long long)N * Ho * Wo;
+  if (Co % 64 == 0) {
+    dim3 grid(tpz_div_up(M, GBM), Co / 64);
+    conv_mma_kernel<64, 0><<<grid, 256, 0, ST(stream)>>>(g, x, w_fwd_packed, bias, res, res_H, res_W, res_org, res_stride,
+                                                         nullptr, y, relu, 0);
+  } else {
+    dim3 grid(tpz_div_up(M, GBM), Co / 32);
+    conv_mma_kernel<32, 0><<<grid, 256, 0, ST(stream)>>>(g, x, w_fwd_packed, bias, res, res_H, res_W, res_org, res_stride,
+                                                         nullptr, y, relu, 0);
+  }
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tpz_conv_dgrad_mma(const float* dy, int N, int Ho, int Wo, int Co, const float* w_dg_packed, int Ci, int kh,
+                                  int kw, int stride, int dil, int org, const float* relu_mask, int accumulate, float* dx,
+                                  int H, int W, void* stream) {
+  TPZ_CHECK(Co % 16 == 0 && Ci % 32 == 0, "tpz_conv_dgrad_mma: needs Co%%16==0 and Ci%%32==0 (Ci=%d Co=%d)", Ci, Co);
+  const MGeom g = mgeom(N, H, W, Ci, Ho, Wo, Co, kh, kw, stride, dil, org);
+  const long long M = (long long)N * H * W;
+  if (Ci % 64 == 0) {
+    dim3 grid(tpz_div_up(M, GBM), Ci / 64);
+    conv_mma_kernel<64, 1><<<grid, 256, 0, ST(stream)>>>(g, dy, w_dg_packed, nullptr, nullptr, 0, 0, 0, 1, relu_mask, dx, 0,
+                                                         accumulate);
+  } else {
+    dim3 grid(tpz_div_up(M, GBM), Ci / 32);
+    conv_mma_kernel<32, 1><<<grid, 256, 0, ST(stream)>>>(g, dy, w_dg_packed, nullptr, nullptr, 0, 0, 0, 1, relu_mask, dx, 0,
+                                                         accumulate);
+  }
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tpz_conv_wgrad_mma(const float* x, int N, int H, int W, int Ci, const float* dy, int Ho, int Wo, int Co,
+                                  int kh, int kw, int stride, int dil, int org, float* dw, void* stream) {
+  TPZ_CHECK(Ci % 4 == 0 && Co % 4 == 0, "tpz_conv_wgrad_mma: needs Ci%%4==0 and Co%%4==0 (Ci=%d Co=%d)", Ci, Co);
+  const MGeom g = mgeom(N, H, W, Ci, Ho, Wo, Co, kh, kw, stride, dil, org);
+  const long long P = (long long)N * Ho * Wo;
+  const int taps = kh * kw;
+  const int mt = tpz_div_up(Co, WBM), nt = tpz_div_up(Ci, WBN);
+  int splits = (148 * 6) / (mt * nt * taps);
+  if (splits < 1) splits = 1;
+  long long kps = (P + splits - 1) / splits;
+  kps = (kps + WBK - 1) / WBK * WBK;
+  if (kps < 256) kps = 256;
+  splits = (int)((P + kps - 1) / kps);
+  dim3 grid(mt, nt, taps * splits);
+  wgrad_mma_kernel<<<grid, 256, 0, ST(stream)>>>(g, x, dy, dw, (int)kps);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -14,6 +14,8 @@ from typing import List, Optional
 import torch
 import torch.nn as nn
 
+import os
+
 from . import _lib, ops
 from ._lib import check
 from .engine import _feature_blocks, is_filled
@@ -50,6 +52,33 @@ class FlatParams:
         self.n = n
         self.step = 0
         self.ptrs = tuple(p.data_ptr() for p in self.params)
+        # packed copies of the conv weights for the tensor-core training kernels (refreshed after every update)
+        self.packed_off = {}
+        descs, poff, mx = [], 0, 0
+        for p, off in zip(self.params, self.offsets):
+            if p.dim() == 4 and p.shape[1] % 16 == 0 and p.shape[0] % 16 == 0:
+                co, ci, kh, kw = p.shape
+                k = p.numel()
+                self.packed_off[id(p)] = (poff, poff + k)
+                descs.append((off, poff, poff + k, co, ci, kh * kw))
+                poff += 2 * k
+                mx = max(mx, k)
+        self.packed = torch.empty(max(poff, 1), dtype=torch.float32, device=dev)
+        self.ndesc, self.max_elems = len(descs), mx
+        import numpy as _np
+        rec = _np.zeros(len(descs), dtype=[('src', '<i8'), ('fwd', '<i8'), ('dg', '<i8'), ('co', '<i4'), ('ci', '<i4'),
+                                           ('taps', '<i4'), ('pad', '<i4')])
+        for i, d in enumerate(descs):
+            rec[i] = (d[0], d[1], d[2], d[3], d[4], d[5], 0)
+        self.descs = torch.from_numpy(rec.view(_np.uint8).copy()).to(dev) if descs else None
+        self.packed_step = -1
+
+    def packed_ptrs(self, w):
+        """(forward-layout, dgrad-layout) views of the packed copy of conv weight `w`, or None."""
+        o = self.packed_off.get(id(w))
+        if o is None:
+            return None
+        return self.packed[o[0]:], self.packed[o[1]:]
 
     def valid_for(self, model) -> bool:
         ps = [p for p in model.parameters()]
@@ -70,11 +99,36 @@ def flat_params(model) -> FlatParams:
     return fp
 
 
+_CUR = {'fp': None}      # FlatParams of the model whose step is running (packed weights for the mma kernels)
+USE_MMA = os.environ.get('TPZ_TRAIN_SIMT') is None
+
+
+def _repack(fp):
+    """Refresh the packed weight copies after a parameter update (one launch for all layers)."""
+    if fp.ndesc and fp.packed_step != fp.step:
+        ops._count(1)
+        check(_lib.lib().tpz_train_repack(_p(fp.flat_p), _p(fp.descs), fp.ndesc, fp.max_elems, _p(fp.packed), _s()))
+        fp.packed_step = fp.step
+
+
+def _packed(w):
+    fp = _CUR['fp']
+    if not USE_MMA or fp is None:
+        return None
+    return fp.packed_ptrs(w)
+
+
 def _conv_fwd(x, w, b, stride, dil, org, Ho, Wo, relu, res=None, res_org=0, res_stride=1):
     N, H, W, Ci = x.shape
     Co, _, kh, kw = w.shape
     y = torch.empty((N, Ho, Wo, Co), dtype=torch.float32, device=x.device)
     ops._count(1)
+    pk = _packed(w)
+    if pk is not None and Ci % 16 == 0 and Co % 32 == 0:
+        check(_lib.lib().tpz_conv_fwd_mma(_p(x), N, H, W, Ci, _p(pk[0]), _p(b), Co, kh, kw, stride, dil, org, _p(res),
+                                          res.shape[1] if res is not None else 0, res.shape[2] if res is not None else 0,
+                                          res_org, res_stride, int(relu), _p(y), Ho, Wo, _s()))
+        return y
     check(_lib.lib().tpz_conv_fwd_f32(_p(x), N, H, W, Ci, _p(w), _p(b), Co, kh, kw, stride, dil, org, _p(res),
                                       res.shape[1] if res is not None else 0, res.shape[2] if res is not None else 0,
                                       res_org, res_stride, int(relu), _p(y), Ho, Wo, _s()))
@@ -86,6 +140,11 @@ def _conv_dgrad(dy, w, stride, dil, org, H, W, mask=None, accumulate=False, out=
     _, Ci, kh, kw = w.shape
     dx = out if out is not None else torch.empty((N, H, W, Ci), dtype=torch.float32, device=dy.device)
     ops._count(1)
+    pk = _packed(w)
+    if pk is not None and Co % 16 == 0 and Ci % 32 == 0:
+        check(_lib.lib().tpz_conv_dgrad_mma(_p(dy), N, Ho, Wo, Co, _p(pk[1]), Ci, kh, kw, stride, dil, org, _p(mask),
+                                            int(accumulate), _p(dx), H, W, _s()))
+        return dx
     check(_lib.lib().tpz_conv_dgrad_f32(_p(dy), N, Ho, Wo, Co, _p(w), Ci, kh, kw, stride, dil, org, _p(mask),
                                         int(accumulate), _p(dx), H, W, _s()))
     return dx
@@ -96,6 +155,11 @@ def _conv_wgrad(x, dy, w_grad, b_grad, stride, dil, org):
     _, Ho, Wo, Co = dy.shape
     kh, kw = w_grad.shape[2], w_grad.shape[3]
     ops._count(2 if b_grad is not None else 1)
+    if USE_MMA and Ci % 16 == 0 and Co % 16 == 0:
+        check(_lib.lib().tpz_conv_wgrad_mma(_p(x), N, H, W, Ci, _p(dy), Ho, Wo, Co, kh, kw, stride, dil, org, _p(w_grad), _s()))
+        if b_grad is not None:      # bias gradient: the fp32 kernel with a zero-tap weight pass is not needed; reuse its reducer
+            check(_lib.lib().tpz_bias_grad_f32(_p(dy), N * Ho * Wo, Co, _p(b_grad), _s()))
+        return
     check(_lib.lib().tpz_conv_wgrad_f32(_p(x), N, H, W, Ci, _p(dy), Ho, Wo, Co, kh, kw, stride, dil, org, _p(w_grad),
                                         _p(b_grad), _s()))
 
@@ -180,8 +244,11 @@ def classifier_forward(model, x: torch.Tensor) -> torch.Tensor:
         raise RuntimeError('train_engine.classifier_forward called on a filled model')
     xi = _prep_input(x)
     save = torch.is_grad_enabled() and model.training
+    fp = None
     if save:
-        flat_params(model)              # make sure params / grads live in the flat buffers before taping pointers
+        fp = flat_params(model)         # make sure params / grads live in the flat buffers before taping pointers
+        _repack(fp)
+    _CUR['fp'] = fp
     with torch.no_grad():
         sc, tape = _forward(model.features, model.classifier, xi, save)
     model.__dict__['_tpz_tape'] = tape if save else None
@@ -203,6 +270,7 @@ def backward(model, dscore: torch.Tensor):
         raise RuntimeError('topaz_b200: backward() without a taped forward (call model(X) in train() mode first)')
     fp = flat_params(model)
     fp.ensure_grads()
+    _CUR['fp'] = fp
     g = None
     with torch.no_grad():
         for rec in reversed(tape):
