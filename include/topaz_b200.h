@@ -136,6 +136,11 @@ int tpz_conv_dgrad_mma(const float* dy, int N, int Ho, int Wo, int Co, const flo
                        void* stream);
 int tpz_conv_wgrad_mma(const float* x, int N, int H, int W, int Ci, const float* dy, int Ho, int Wo, int Co, int kh, int kw,
                        int stride, int dil, int org, float* dw, void* stream);
+/* Cin = 1 first layer of the training net (resnet.py:294, 7x7 stride 2), valid conv, org = 0 */
+int tpz_first_fwd_f32(const float* x, int N, int H, int W, const float* w, const float* bias, int Co, int k, int stride,
+                      int relu, float* y, int Ho, int Wo, void* stream);
+int tpz_first_wgrad_f32(const float* x, int N, int H, int W, const float* dy, int Ho, int Wo, int Co, int k, int stride,
+                        float* dw, void* stream);
 int tpz_bias_grad_f32(const float* dy, long long P, int C, float* db, void* stream);   /* db[c] += sum_p dy[p][c] */
 int tpz_relu_bwd_f32(float* dy, const float* y, long long n, void* stream);
 int tpz_crop_add_f32(float* dx, int N, int H, int W, int C, const float* g, int Ho, int Wo, int org, int stride,

@@ -133,15 +133,15 @@ def test_conv_mma_kernels_match_fp32(N, H, Ci, Co, k, stride, dil, org):
     wg = w.permute(2, 3, 0, 1).contiguous().cuda()      # [tap][co][ci]
     y = torch.empty(N, Ho, Ho, Co, device='cuda')
     _lib.check(L.tpz_conv_fwd_mma(P(xd), N, H, H, Ci, P(wf), P(bd), Co, k, k, stride, dil, org, None, 0, 0, 0, 1, 0, P(y), Ho, Ho, None))
-    assert max(rel_err(y.cpu(), _nhwc(ref))) < 2e-5
+    assert max(rel_err(y.cpu(), _nhwc(ref))) < 5e-5
     dy = torch.randn(N, Co, Ho, Ho, generator=g)
     dyd = _nhwc(dy).cuda()
     gi = torch.nn.grad.conv2d_input(tuple(xin.shape), w, dy, stride=stride, dilation=dil)
     gref = torch.zeros_like(x); gref[:, :, org:org + ext, org:org + ext] = gi
     dx = torch.empty(N, H, H, Ci, device='cuda')
     _lib.check(L.tpz_conv_dgrad_mma(P(dyd), N, Ho, Ho, Co, P(wg), Ci, k, k, stride, dil, org, None, 0, P(dx), H, H, None))
-    assert max(rel_err(dx.cpu(), _nhwc(gref))) < 2e-5
+    assert max(rel_err(dx.cpu(), _nhwc(gref))) < 5e-5
     gw = torch.nn.grad.conv2d_weight(xin.contiguous(), tuple(w.shape), dy, stride=stride, dilation=dil)
     dw = torch.zeros_like(w).cuda()
     _lib.check(L.tpz_conv_wgrad_mma(P(xd), N, H, H, Ci, P(dyd), Ho, Ho, Co, k, k, stride, dil, org, P(dw), None))
-    assert max(rel_err(dw.cpu(), gw)) < 2e-5
+    assert max(rel_err(dw.cpu(), gw)) < 5e-5

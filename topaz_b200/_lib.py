@@ -60,6 +60,8 @@ _PROTOS = {
     'tpz_conv_fwd_mma': (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P, _I, _I, _P]),
     'tpz_conv_dgrad_mma': (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P]),
     'tpz_conv_wgrad_mma': (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    'tpz_first_fwd_f32': (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P, _I, _I, _P]),
+    'tpz_first_wgrad_f32': (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P]),
     'tpz_bias_grad_f32': (_I, [_P, _LL, _I, _P, _P]),
     'tpz_relu_bwd_f32': (_I, [_P, _P, _LL, _P]),
     'tpz_crop_add_f32': (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P]),

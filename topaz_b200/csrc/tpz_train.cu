@@ -169,19 +169,105 @@ __global__ void crop_add_kernel(float* __restrict__ dx, int H, int W, const floa
   }
 }
 
-// db[c] += sum_p dy[p][c]
+// db[c] += sum_p dy[p][c].  Block = 32 channels x 8 row-slices; 4 independent loads in flight per thread.
 __global__ void bias_grad_kernel(const float* __restrict__ dy, long long P, int C, float* __restrict__ db) {
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int slice = threadIdx.x >> 5;            // 8 slices
-  float s = 0.f;
-  if (c < C)
-    for (long long p = (long long)blockIdx.y * 8 + slice; p < P; p += (long long)gridDim.y * 8) s += dy[p * C + c];
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (c < C) {
+    const long long step = (long long)gridDim.y * 8;
+    long long p = (long long)blockIdx.y * 8 + slice;
+    for (; p + 3 * step < P; p += 4 * step) {
+      s0 += dy[p * C + c]; s1 += dy[(p + step) * C + c]; s2 += dy[(p + 2 * step) * C + c]; s3 += dy[(p + 3 * step) * C + c];
+    }
+    for (; p < P; p += step) s0 += dy[p * C + c];
+  }
+  float s = (s0 + s1) + (s2 + s3);
   __shared__ float sh[8][33];
   sh[slice][threadIdx.x & 31] = s;
   __syncthreads();
   if (slice == 0 && c < C) {
     for (int k = 1; k < 8; ++k) s += sh[k][threadIdx.x & 31];
     atomicAdd(&db[c], s);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Cin = 1 first layer of the training net (7x7 stride 2): dedicated forward and weight-gradient kernels
+// (the generic implicit-GEMM tiles are wasteful for K = 49, Ci = 1).
+// -------------------------------------------------------------------------------------------------
+template <int CO>
+__global__ void __launch_bounds__(128) first_fwd_kernel(const float* __restrict__ x, int N, int H, int W,
+                                                        const float* __restrict__ w, const float* __restrict__ bias, int k,
+                                                        int stride, int relu, float* __restrict__ y, int Ho, int Wo) {
+  extern __shared__ float s_wf[];                 // [taps][CO]
+  const int taps = k * k;
+  for (int i = threadIdx.x; i < taps * CO; i += blockDim.x) {
+    const int t = i / CO, c = i - t * CO;
+    s_wf[i] = w[c * taps + t];
+  }
+  __syncthreads();
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long M = (long long)N * Ho * Wo;
+  if (m >= M) return;
+  const int ox = m % Wo; const long long q = m / Wo; const int oy = q % Ho; const int n = q / Ho;
+  const float* xb = x + ((long long)n * H + oy * stride) * W + ox * stride;
+  float acc[CO];
+#pragma unroll
+  for (int c = 0; c < CO; ++c) acc[c] = bias ? bias[c] : 0.f;
+  for (int r = 0; r < k; ++r)
+    for (int t = 0; t < k; ++t) {
+      const float v = xb[r * W + t];
+      const float4* wr = reinterpret_cast<const float4*>(s_wf + (r * k + t) * CO);
+#pragma unroll
+      for (int c4 = 0; c4 < CO / 4; ++c4) {
+        const float4 wv = wr[c4];
+        acc[c4 * 4 + 0] = fmaf(v, wv.x, acc[c4 * 4 + 0]);
+        acc[c4 * 4 + 1] = fmaf(v, wv.y, acc[c4 * 4 + 1]);
+        acc[c4 * 4 + 2] = fmaf(v, wv.z, acc[c4 * 4 + 2]);
+        acc[c4 * 4 + 3] = fmaf(v, wv.w, acc[c4 * 4 + 3]);
+      }
+    }
+  float4* o = reinterpret_cast<float4*>(y + m * CO);
+#pragma unroll
+  for (int c4 = 0; c4 < CO / 4; ++c4) {
+    float4 v = make_float4(acc[c4 * 4], acc[c4 * 4 + 1], acc[c4 * 4 + 2], acc[c4 * 4 + 3]);
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    o[c4] = v;
+  }
+}
+
+// dw[co][tap] += sum_p dy[p][co] * x[p*stride + tap]; thread = (co, tap group), block = a contiguous pixel range
+template <int CO>
+__global__ void __launch_bounds__(256) first_wgrad_kernel(const float* __restrict__ x, int N, int H, int W,
+                                                          const float* __restrict__ dy, int Ho, int Wo, int k, int stride,
+                                                          float* __restrict__ dw, int px_per_block) {
+  constexpr int TG = 256 / CO;                    // tap groups
+  constexpr int MAXT = 16;                        // taps per thread (k*k <= TG*MAXT)
+  const int co = threadIdx.x % CO, tg = threadIdx.x / CO;
+  const int taps = k * k;
+  float acc[MAXT];
+  int toff[MAXT];
+#pragma unroll
+  for (int j = 0; j < MAXT; ++j) {
+    acc[j] = 0.f;
+    const int t = tg + j * TG;
+    toff[j] = (t < taps) ? (t / k) * W + (t % k) : -1;
+  }
+  const long long M = (long long)N * Ho * Wo;
+  const long long p0 = (long long)blockIdx.x * px_per_block, p1 = min(M, p0 + px_per_block);
+  for (long long p = p0; p < p1; ++p) {
+    const float v = dy[p * CO + co];
+    const int ox = p % Wo; const long long q = p / Wo; const int oy = q % Ho; const int n = q / Ho;
+    const float* xb = x + ((long long)n * H + oy * stride) * W + ox * stride;
+#pragma unroll
+    for (int j = 0; j < MAXT; ++j)
+      if (toff[j] >= 0) acc[j] = fmaf(v, __ldg(xb + toff[j]), acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < MAXT; ++j) {
+    const int t = tg + j * TG;
+    if (t < taps) atomicAdd(&dw[co * taps + t], acc[j]);
   }
 }
 
@@ -325,15 +411,40 @@ extern "C" int tpz_conv_wgrad_f32(const float* x, int N, int H, int W, int Ci, c
   dim3 grid(mt, nt, splits);
   conv_f32_kernel<2><<<grid, 256, 0, ST(stream)>>>(g, dy, x, nullptr, nullptr, 0, 0, 0, 1, nullptr, dw, 0, 1, (int)kps);
   if (db) {
-    dim3 bg(tpz_div_up(Co, 32), (unsigned)(P < 4096 ? 1 : 64));
+    dim3 bg(tpz_div_up(Co, 32), (unsigned)(P < 4096 ? 1 : (P < 65536 ? 64 : 296)));
     bias_grad_kernel<<<bg, 256, 0, ST(stream)>>>(dy, P, Co, db);
   }
   TPZ_CUDA(cudaGetLastError());
   return 0;
 }
 
+extern "C" int tpz_first_fwd_f32(const float* x, int N, int H, int W, const float* w, const float* bias, int Co, int k,
+                                 int stride, int relu, float* y, int Ho, int Wo, void* stream) {
+  TPZ_CHECK(Co == 32 || Co == 64, "tpz_first_fwd_f32: Co must be 32 or 64 (got %d)", Co);
+  const long long M = (long long)N * Ho * Wo;
+  const size_t smem = (size_t)k * k * Co * sizeof(float);
+  if (Co == 32) first_fwd_kernel<32><<<tpz_div_up(M, 128), 128, smem, ST(stream)>>>(x, N, H, W, w, bias, k, stride, relu, y, Ho, Wo);
+  else first_fwd_kernel<64><<<tpz_div_up(M, 128), 128, smem, ST(stream)>>>(x, N, H, W, w, bias, k, stride, relu, y, Ho, Wo);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tpz_first_wgrad_f32(const float* x, int N, int H, int W, const float* dy, int Ho, int Wo, int Co, int k,
+                                   int stride, float* dw, void* stream) {
+  TPZ_CHECK(Co == 32 || Co == 64, "tpz_first_wgrad_f32: Co must be 32 or 64 (got %d)", Co);
+  TPZ_CHECK(k * k <= (256 / Co) * 16, "tpz_first_wgrad_f32: kernel %dx%d too large", k, k);
+  const long long M = (long long)N * Ho * Wo;
+  int ppb = (int)((M + 148 * 8 - 1) / (148 * 8));
+  if (ppb < 64) ppb = 64;
+  const int grid = tpz_div_up(M, ppb);
+  if (Co == 32) first_wgrad_kernel<32><<<grid, 256, 0, ST(stream)>>>(x, N, H, W, dy, Ho, Wo, k, stride, dw, ppb);
+  else first_wgrad_kernel<64><<<grid, 256, 0, ST(stream)>>>(x, N, H, W, dy, Ho, Wo, k, stride, dw, ppb);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int tpz_bias_grad_f32(const float* dy, long long P, int C, float* db, void* stream) {
-  dim3 bg(tpz_div_up(C, 32), (unsigned)(P < 4096 ? 1 : 64));
+  dim3 bg(tpz_div_up(C, 32), (unsigned)(P < 4096 ? 1 : (P < 65536 ? 64 : 296)));
   bias_grad_kernel<<<bg, 256, 0, ST(stream)>>>(dy, P, C, db);
   TPZ_CUDA(cudaGetLastError());
   return 0;

@@ -49,6 +49,15 @@ __device__ __forceinline__ void mma_f32x3(float (&c)[4], const float (&a)[4], co
   mma_tf32(c, ah, bh);
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int bytes = valid ? 16 : 0;      // src-size 0 => the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // -------------------------------------------------------------------------------------------------
 // weight repack: OIHW [Co][Ci][taps] -> fwd layout [tap][ci][co] and dgrad layout [tap][co][ci]
 // -------------------------------------------------------------------------------------------------
@@ -83,8 +92,9 @@ __global__ void __launch_bounds__(256) conv_mma_kernel(MGeom g, const float* __r
   constexpr int WN = BN / 32;            // warps along N (1 or 2)
   constexpr int WM = 8 / WN;             // warps along M (8 or 4)
   constexpr int MT = GBM / WM / 16;      // m16 tiles per warp (1 or 2)
-  __shared__ __align__(16) float As[2][GBM][GAS];
-  __shared__ __align__(16) float Bs[2][GBK][BS];
+  constexpr int STG = 3;                 // cp.async stages: the step is latency-bound, keep 2 chunks in flight
+  __shared__ __align__(16) float As[STG][GBM][GAS];
+  __shared__ __align__(16) float Bs[STG][GBK][BS];
 
   const int taps = g.kh * g.kw;
   const int Cs = MODE == 0 ? g.Ci : g.Co;      // source channels (K per tap)
@@ -123,16 +133,14 @@ __global__ void __launch_bounds__(256) conv_mma_kernel(MGeom g, const float* __r
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
 
-  float4 ra[2], rb[(GBK * BN / 4 + 255) / 256];
-  auto load_chunk = [&](int kc) {
+  auto issue_chunk = [&](int kc, int buf) {
     const int tap = kc / cchunks, c0 = (kc - tap * cchunks) * GBK;
     const int r = tap / g.kw, t = tap - r * g.kw;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (arow_ok[h]) {
-        int sy, sx;
-        bool ok;
+      bool ok = arow_ok[h];
+      int sy = 0, sx = 0;
+      if (ok) {
         if (MODE == 0) {
           sy = ay[h] * g.stride + r * g.dil + g.org;
           sx = ax[h] * g.stride + t * g.dil + g.org;
@@ -143,41 +151,34 @@ __global__ void __launch_bounds__(256) conv_mma_kernel(MGeom g, const float* __r
           sy = ny / g.stride; sx = nx / g.stride;
           ok = ok && sy < SH && sx < SW;
         }
-        if (ok) v = *reinterpret_cast<const float4*>(src + (((long long)an[h] * SH + sy) * SW + sx) * Cs + c0 + a_quad * 4);
       }
-      ra[h] = v;
+      const float* gp = ok ? src + (((long long)an[h] * SH + sy) * SW + sx) * Cs + c0 + a_quad * 4 : src;
+      cp_async16(&As[buf][a_row + h * 64][a_quad * 4], gp, ok);
     }
-#pragma unroll
-    for (int e = 0; e < (GBK * BN / 4 + 255) / 256; ++e) {
-      const int idx = tid + e * 256;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (idx < GBK * BN / 4) {
-        const int kk = idx / (BN / 4), nq = idx - kk * (BN / 4);
-        const int n = n0 + nq * 4;
-        if (n < Nn) v = *reinterpret_cast<const float4*>(wpk + ((long long)tap * Cs + c0 + kk) * Nn + n);
-      }
-      rb[e] = v;
-    }
-  };
-  auto store_chunk = [&](int buf) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) *reinterpret_cast<float4*>(&As[buf][a_row + h * 64][a_quad * 4]) = ra[h];
 #pragma unroll
     for (int e = 0; e < (GBK * BN / 4 + 255) / 256; ++e) {
       const int idx = tid + e * 256;
       if (idx < GBK * BN / 4) {
         const int kk = idx / (BN / 4), nq = idx - kk * (BN / 4);
-        *reinterpret_cast<float4*>(&Bs[buf][kk][nq * 4]) = rb[e];
+        const int n = n0 + nq * 4;
+        const bool ok = n < Nn;
+        const float* gp = ok ? wpk + ((long long)tap * Cs + c0 + kk) * Nn + n : wpk;
+        cp_async16(&Bs[buf][kk][nq * 4], gp, ok);
       }
     }
   };
 
-  load_chunk(0);
-  store_chunk(0);
-  __syncthreads();
+#pragma unroll
+  for (int s2 = 0; s2 < STG - 1; ++s2) {
+    if (s2 < nk) issue_chunk(s2, s2);
+    cp_async_commit();
+  }
   for (int kc = 0; kc < nk; ++kc) {
-    const int buf = kc & 1;
-    if (kc + 1 < nk) load_chunk(kc + 1);
+    const int buf = kc % STG;
+    cp_async_wait<STG - 2>();
+    __syncthreads();
+    if (kc + STG - 1 < nk) issue_chunk(kc + STG - 1, (kc + STG - 1) % STG);
+    cp_async_commit();
 #pragma unroll
     for (int k8 = 0; k8 < GBK; k8 += 8) {
       float bf[4][2];
@@ -198,8 +199,6 @@ __global__ void __launch_bounds__(256) conv_mma_kernel(MGeom g, const float* __r
         for (int j = 0; j < 4; ++j) mma_f32x3(acc[i][j], af, bf[j]);
       }
     }
-    if (kc + 1 < nk) store_chunk(buf ^ 1);
-    __syncthreads();
   }
 
   // epilogue: c0:(g,2t) c1:(g,2t+1) c2:(g+8,2t) c3:(g+8,2t+1)
@@ -238,93 +237,105 @@ __global__ void __launch_bounds__(256) conv_mma_kernel(MGeom g, const float* __r
 // wgrad: dw[co][ci][tap] += sum_p dy[p][co] * x[p'(p,tap)][ci].  CTA = (64 co x 64 ci) tile of one tap over a
 // K-split of the output pixels; fp32 atomics accumulate the splits (dw is zeroed by the Adam kernel).
 // -------------------------------------------------------------------------------------------------
-constexpr int WBM = 64, WBN = 64, WBK = 16, WS = 72;
+constexpr int WBK = 16;
 
+template <int BT>    // square (BT co) x (BT ci) tile, BT = 64 or 32
 __global__ void __launch_bounds__(256) wgrad_mma_kernel(MGeom g, const float* __restrict__ x, const float* __restrict__ dy,
                                                         float* __restrict__ dw, int k_per_split) {
-  __shared__ __align__(16) float As[2][WBK][WS];   // [pixel][co]
-  __shared__ __align__(16) float Bs[2][WBK][WS];   // [pixel][ci]
+  constexpr int STG = 4;
+  constexpr int WSS = BT + 8;
+  constexpr int WTM = BT / 2, WTN = BT / 4;        // warp tile (2 x 4 warps)
+  constexpr int MI = WTM / 16, NJ = WTN / 8;
+  __shared__ __align__(16) float As[STG][WBK][WSS];   // [pixel][co]
+  __shared__ __align__(16) float Bs[STG][WBK][WSS];   // [pixel][ci]
   const int taps = g.kh * g.kw;
   const int tap = blockIdx.z % taps, split = blockIdx.z / taps;
   const int r = tap / g.kw, t = tap - r * g.kw;
-  const int co0 = blockIdx.x * WBM, ci0 = blockIdx.y * WBN;
+  const int co0 = blockIdx.x * BT, ci0 = blockIdx.y * BT;
   const long long P = (long long)g.N * g.Ho * g.Wo;
   const long long pbeg = (long long)split * k_per_split;
   const long long pend = min(P, pbeg + k_per_split);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int gq = lane >> 2, tq = lane & 3;
-  const int wm = warp >> 2, wn = warp & 3;       // 2 x 4 warps, warp tile 32 (co) x 16 (ci)
-  // staging: 16 pixels x 64 channels = 256 float4: thread -> (pixel = tid/16, quad = tid%16)
-  const int s_p = tid >> 4, s_q = tid & 15;
+  const int wm = warp >> 2, wn = warp & 3;
+  // staging: 16 pixels x BT channels per operand.  BT=64: every thread copies one float4 of A and one of B;
+  // BT=32: threads 0-127 copy A, threads 128-255 copy B.
+  constexpr int QP = BT / 4;                        // float4 per pixel row
+  const int role = (BT == 64) ? 2 : (tid >> 7);     // 0: A only, 1: B only, 2: both
+  const int sidx = (BT == 64) ? tid : (tid & 127);
+  const int s_p = sidx / QP, s_q = sidx % QP;
 
-  float acc[2][2][4];
+  float acc[MI][NJ][4];
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < MI; ++i)
 #pragma unroll
-    for (int j = 0; j < 2; ++j)
+    for (int j = 0; j < NJ; ++j)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
 
-  float4 ra, rb;
-  auto load_chunk = [&](long long p0) {
+  auto issue_chunk = [&](long long p0, int buf) {
     const long long p = p0 + s_p;
-    ra = make_float4(0.f, 0.f, 0.f, 0.f); rb = ra;
-    if (p < pend) {
-      if (co0 + s_q * 4 < g.Co) ra = *reinterpret_cast<const float4*>(dy + p * g.Co + co0 + s_q * 4);
-      const int ox = p % g.Wo; const long long q = p / g.Wo; const int oy = q % g.Ho; const int n = q / g.Ho;
-      const int iy = oy * g.stride + r * g.dil + g.org, ix = ox * g.stride + t * g.dil + g.org;
-      if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W && ci0 + s_q * 4 < g.Ci)
-        rb = *reinterpret_cast<const float4*>(x + (((long long)n * g.H + iy) * g.W + ix) * g.Ci + ci0 + s_q * 4);
+    const bool pv = p < pend;
+    if (role != 1) {
+      const bool ok = pv && (co0 + s_q * 4 < g.Co);
+      cp_async16(&As[buf][s_p][s_q * 4], ok ? dy + p * g.Co + co0 + s_q * 4 : dy, ok);
+    }
+    if (role != 0) {
+      bool ok = pv && (ci0 + s_q * 4 < g.Ci);
+      const float* gp = x;
+      if (ok) {
+        const int ox = p % g.Wo; const long long q = p / g.Wo; const int oy = q % g.Ho; const int n = q / g.Ho;
+        const int iy = oy * g.stride + r * g.dil + g.org, ix = ox * g.stride + t * g.dil + g.org;
+        ok = iy >= 0 && iy < g.H && ix >= 0 && ix < g.W;
+        if (ok) gp = x + (((long long)n * g.H + iy) * g.W + ix) * g.Ci + ci0 + s_q * 4;
+      }
+      cp_async16(&Bs[buf][s_p][s_q * 4], gp, ok);
     }
   };
-  auto store_chunk = [&](int buf) {
-    *reinterpret_cast<float4*>(&As[buf][s_p][s_q * 4]) = ra;
-    *reinterpret_cast<float4*>(&Bs[buf][s_p][s_q * 4]) = rb;
-  };
-  if (pbeg < pend) {
-    load_chunk(pbeg);
-    store_chunk(0);
+  const int nchunks = (int)((pend - pbeg + WBK - 1) / WBK);
+#pragma unroll
+  for (int s2 = 0; s2 < STG - 1; ++s2) {
+    if (s2 < nchunks) issue_chunk(pbeg + (long long)s2 * WBK, s2);
+    cp_async_commit();
   }
-  __syncthreads();
-  int it = 0;
-  for (long long p0 = pbeg; p0 < pend; p0 += WBK, ++it) {
-    const int buf = it & 1;
-    const bool more = p0 + WBK < pend;
-    if (more) load_chunk(p0 + WBK);
+  for (int it = 0; it < nchunks; ++it) {
+    const int buf = it % STG;
+    cp_async_wait<STG - 2>();
+    __syncthreads();
+    if (it + STG - 1 < nchunks) issue_chunk(pbeg + (long long)(it + STG - 1) * WBK, (it + STG - 1) % STG);
+    cp_async_commit();
 #pragma unroll
     for (int k8 = 0; k8 < WBK; k8 += 8) {
-      float bf[2][2];
+      float bf[NJ][2];
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        bf[j][0] = Bs[buf][k8 + tq][wn * 16 + j * 8 + gq];
-        bf[j][1] = Bs[buf][k8 + tq + 4][wn * 16 + j * 8 + gq];
+      for (int j = 0; j < NJ; ++j) {
+        bf[j][0] = Bs[buf][k8 + tq][wn * WTN + j * 8 + gq];
+        bf[j][1] = Bs[buf][k8 + tq + 4][wn * WTN + j * 8 + gq];
       }
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int mb = wm * 32 + i * 16;
+      for (int i = 0; i < MI; ++i) {
+        const int mb = wm * WTM + i * 16;
         float af[4];
         af[0] = As[buf][k8 + tq][mb + gq];
         af[1] = As[buf][k8 + tq][mb + gq + 8];
         af[2] = As[buf][k8 + tq + 4][mb + gq];
         af[3] = As[buf][k8 + tq + 4][mb + gq + 8];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) mma_f32x3(acc[i][j], af, bf[j]);
+        for (int j = 0; j < NJ; ++j) mma_f32x3(acc[i][j], af, bf[j]);
       }
     }
-    if (more) store_chunk(buf ^ 1);
-    __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < MI; ++i)
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
-      const int co = co0 + wm * 32 + i * 16 + gq + hh * 8;
+      const int co = co0 + wm * WTM + i * 16 + gq + hh * 8;
       if (co >= g.Co) continue;
 #pragma unroll
-      for (int j = 0; j < 2; ++j)
+      for (int j = 0; j < NJ; ++j)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const int ci = ci0 + wn * 16 + j * 8 + tq * 2 + e;
+          const int ci = ci0 + wn * WTN + j * 8 + tq * 2 + e;
           if (ci < g.Ci) atomicAdd(&dw[((long long)co * g.Ci + ci) * taps + tap], acc[i][j][hh * 2 + e]);
         }
     }
@@ -393,15 +404,17 @@ extern "C" int tpz_conv_wgrad_mma(const float* x, int N, int H, int W, int Ci, c
   const MGeom g = mgeom(N, H, W, Ci, Ho, Wo, Co, kh, kw, stride, dil, org);
   const long long P = (long long)N * Ho * Wo;
   const int taps = kh * kw;
-  const int mt = tpz_div_up(Co, WBM), nt = tpz_div_up(Ci, WBN);
-  int splits = (148 * 6) / (mt * nt * taps);
+  const int BT = (Co <= 32 && Ci <= 32) ? 32 : 64;
+  const int mt = tpz_div_up(Co, BT), nt = tpz_div_up(Ci, BT);
+  int splits = (148 * 8) / (mt * nt * taps);
   if (splits < 1) splits = 1;
   long long kps = (P + splits - 1) / splits;
   kps = (kps + WBK - 1) / WBK * WBK;
-  if (kps < 256) kps = 256;
+  if (kps < 512) kps = 512;
   splits = (int)((P + kps - 1) / kps);
   dim3 grid(mt, nt, taps * splits);
-  wgrad_mma_kernel<<<grid, 256, 0, ST(stream)>>>(g, x, dy, dw, (int)kps);
+  if (BT == 32) wgrad_mma_kernel<32><<<grid, 256, 0, ST(stream)>>>(g, x, dy, dw, (int)kps);
+  else wgrad_mma_kernel<64><<<grid, 256, 0, ST(stream)>>>(g, x, dy, dw, (int)kps);
   TPZ_CUDA(cudaGetLastError());
   return 0;
 }

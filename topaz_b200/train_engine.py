@@ -123,6 +123,9 @@ def _conv_fwd(x, w, b, stride, dil, org, Ho, Wo, relu, res=None, res_org=0, res_
     Co, _, kh, kw = w.shape
     y = torch.empty((N, Ho, Wo, Co), dtype=torch.float32, device=x.device)
     ops._count(1)
+    if USE_MMA and Ci == 1 and Co in (32, 64) and org == 0 and dil == 1 and res is None and kh == kw:
+        check(_lib.lib().tpz_first_fwd_f32(_p(x), N, H, W, _p(w), _p(b), Co, kh, stride, int(relu), _p(y), Ho, Wo, _s()))
+        return y
     pk = _packed(w)
     if pk is not None and Ci % 16 == 0 and Co % 32 == 0:
         check(_lib.lib().tpz_conv_fwd_mma(_p(x), N, H, W, Ci, _p(pk[0]), _p(b), Co, kh, kw, stride, dil, org, _p(res),
@@ -155,6 +158,11 @@ def _conv_wgrad(x, dy, w_grad, b_grad, stride, dil, org):
     _, Ho, Wo, Co = dy.shape
     kh, kw = w_grad.shape[2], w_grad.shape[3]
     ops._count(2 if b_grad is not None else 1)
+    if USE_MMA and Ci == 1 and Co in (32, 64) and org == 0 and dil == 1 and kh == kw and kh * kw <= (256 // Co) * 16:
+        check(_lib.lib().tpz_first_wgrad_f32(_p(x), N, H, W, _p(dy), Ho, Wo, Co, kh, stride, _p(w_grad), _s()))
+        if b_grad is not None:
+            check(_lib.lib().tpz_bias_grad_f32(_p(dy), N * Ho * Wo, Co, _p(b_grad), _s()))
+        return
     if USE_MMA and Ci % 16 == 0 and Co % 16 == 0:
         check(_lib.lib().tpz_conv_wgrad_mma(_p(x), N, H, W, Ci, _p(dy), Ho, Wo, Co, kh, kw, stride, dil, org, _p(w_grad), _s()))
         if b_grad is not None:      # bias gradient: the fp32 kernel with a zero-tap weight pass is not needed; reuse its reducer
