@@ -62,6 +62,7 @@ typedef struct {
   const float* dot_w;      /* optional fused 1x1 "classifier": dot_out = sum_c act(.)*dot_w[c] + dot_b */
   float dot_b;
   float* dot_out;          /* [N][Do][Ho][Wo] fp32 or NULL */
+  const float* dot_affine; /* optional device float[2] = (shift, scale): dot_out = dot_out*scale + shift (de-normalise) */
 } TpzTcConvArgs;
 
 int tpz_tc_conv(const TpzTcConvArgs* host_args, void* stream);   /* dispatches: halo-resident kernel when

@@ -25,7 +25,7 @@ def _gather(src, org, d, out_shape, c0, kc):
     return out
 
 
-def tc_conv(plan, srcs, out_shape, out=None, res=None, res_org=(0, 0, 0), dot_out=None, out_coff=0, tag=None):
+def tc_conv(plan, srcs, out_shape, out=None, res=None, res_org=(0, 0, 0), dot_out=None, out_coff=0, tag=None, dot_affine=None):
     N, Do, Ho, Wo = out_shape
     acc = torch.zeros((N, Do, Ho, Wo, plan.Co), dtype=torch.float32)
     for kb, (dx, dy, dz, c0, si) in enumerate(plan.kblocks):
@@ -37,7 +37,10 @@ def tc_conv(plan, srcs, out_shape, out=None, res=None, res_org=(0, 0, 0), dot_ou
         v = v + (r * plan.res_scale if plan.res_scale is not None else r)
     v = torch.where(v > 0, v, v * plan.neg_slope)
     if dot_out is not None:
-        dot_out.copy_((v * plan.dot_w).sum(-1) + plan.dot_b)
+        dv = (v * plan.dot_w).sum(-1) + plan.dot_b
+        if dot_affine is not None:
+            dv = dv * dot_affine[1] + dot_affine[0]
+        dot_out.copy_(dv)
     if out is not None:
         out[..., out_coff:out_coff + plan.Co] = v.half()
 

@@ -30,7 +30,7 @@ class TpzTcConvArgs(C.Structure):
         ('res', C.c_void_p), ('res_scale', C.c_void_p),
         ('res_ld', C.c_int), ('res_D', C.c_int), ('res_H', C.c_int), ('res_W', C.c_int), ('res_org', C.c_int * 3),
         ('out', C.c_void_p), ('out_ld', C.c_int), ('out_coff', C.c_int),
-        ('dot_w', C.c_void_p), ('dot_b', C.c_float), ('dot_out', C.c_void_p),
+        ('dot_w', C.c_void_p), ('dot_b', C.c_float), ('dot_out', C.c_void_p), ('dot_affine', C.c_void_p),
     ]
 
 

@@ -231,7 +231,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
           }
         }
       }
-      if (p.dot_out && valid) p.dot_out[opix] = dot + p.dot_b;
+      if (p.dot_out && valid) {
+          float dv = dot + p.dot_b;
+          if (p.dot_affine) dv = dv * p.dot_affine[1] + p.dot_affine[0];
+          p.dot_out[opix] = dv;
+        }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
@@ -308,7 +312,7 @@ extern "C" int tpz_tc_conv_v1(const TpzTcConvArgs* a, void* stream_) {
   p.res_org[0] = a->res_org[0]; p.res_org[1] = a->res_org[1]; p.res_org[2] = a->res_org[2];
   TPZ_CHECK(a->res == nullptr || a->res_ld % 8 == 0, "tpz_tc_conv: residual channel stride must be a multiple of 8");
   p.out = reinterpret_cast<__half*>(a->out); p.out_ld = a->out_ld; p.out_coff = a->out_coff;
-  p.dot_w = a->dot_w; p.dot_b = a->dot_b; p.dot_out = a->dot_out;
+  p.dot_w = a->dot_w; p.dot_b = a->dot_b; p.dot_out = a->dot_out; p.dot_affine = a->dot_affine;
 
   const int rowb = a->KC * 2;
   const int stage_bytes = 128 * rowb + a->Co * rowb;

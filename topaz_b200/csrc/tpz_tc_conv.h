@@ -22,5 +22,6 @@ struct TcConvParams {
   const float* dot_w;
   float dot_b;
   float* dot_out;
+  const float* dot_affine;
   TcKBlock kb[TPZ_TC_MAX_KB];
 };

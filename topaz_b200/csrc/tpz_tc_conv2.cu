@@ -54,6 +54,7 @@ struct Tc2Params {
   const float* dot_w;
   float dot_b;
   float* dot_out;
+  const float* dot_affine;
   Tc2Group groups[kMaxGroups];
   Tc2Tap taps[TPZ_TC_MAX_KB];
 };
@@ -337,7 +338,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv2_kernel(const __grid_cons
             }
           }
         }
-        if (p.dot_out && valid) p.dot_out[opix] = dot + p.dot_b;
+        if (p.dot_out && valid) {
+          float dv = dot + p.dot_b;
+          if (p.dot_affine) dv = dv * p.dot_affine[1] + p.dot_affine[0];
+          p.dot_out[opix] = dv;
+        }
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -464,7 +469,7 @@ static int launch_v2(const TpzTcConvArgs* a, cudaStream_t stream, bool dry) {
   p.res_D = a->res_D; p.res_H = a->res_H; p.res_W = a->res_W;
   p.res_org[0] = a->res_org[0]; p.res_org[1] = a->res_org[1]; p.res_org[2] = a->res_org[2];
   p.out = reinterpret_cast<__half*>(a->out); p.out_ld = a->out_ld; p.out_coff = a->out_coff;
-  p.dot_w = a->dot_w; p.dot_b = a->dot_b; p.dot_out = a->dot_out;
+  p.dot_w = a->dot_w; p.dot_b = a->dot_b; p.dot_out = a->dot_out; p.dot_affine = a->dot_affine;
 
   if (g_num_sms2 == 0) {
     int dev = 0;

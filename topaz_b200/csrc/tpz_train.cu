@@ -256,13 +256,20 @@ __global__ void __launch_bounds__(256) first_wgrad_kernel(const float* __restric
   }
   const long long M = (long long)N * Ho * Wo;
   const long long p0 = (long long)blockIdx.x * px_per_block, p1 = min(M, p0 + px_per_block);
+  if (p0 >= p1) return;
+  int ox = p0 % Wo; long long q = p0 / Wo; int oy = q % Ho; int n = q / Ho;      // advanced incrementally below
+  const float* xb = x + ((long long)n * H + oy * stride) * W + ox * stride;
   for (long long p = p0; p < p1; ++p) {
     const float v = dy[p * CO + co];
-    const int ox = p % Wo; const long long q = p / Wo; const int oy = q % Ho; const int n = q / Ho;
-    const float* xb = x + ((long long)n * H + oy * stride) * W + ox * stride;
 #pragma unroll
     for (int j = 0; j < MAXT; ++j)
       if (toff[j] >= 0) acc[j] = fmaf(v, __ldg(xb + toff[j]), acc[j]);
+    xb += stride;
+    if (++ox == Wo) {
+      ox = 0;
+      if (++oy == Ho) { oy = 0; ++n; }
+      xb = x + ((long long)n * H + oy * stride) * W;
+    }
   }
 #pragma unroll
   for (int j = 0; j < MAXT; ++j) {

@@ -49,6 +49,28 @@ __device__ __forceinline__ void mma_f32x3(float (&c)[4], const float (&a)[4], co
   mma_tf32(c, ah, bh);
 }
 
+// split an fp32 fragment into TF32 hi (+ lo) parts once; reused by every MMA that consumes the fragment
+template <int N>
+__device__ __forceinline__ void split_tf32(const float (&v)[N], uint32_t (&hi)[N], uint32_t (&lo)[N]) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    hi[i] = to_tf32(v[i]);
+#if TPZ_3XTF32
+    lo[i] = to_tf32(v[i] - __uint_as_float(hi[i]));
+#else
+    lo[i] = 0;
+#endif
+  }
+}
+__device__ __forceinline__ void mma_split(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                          const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
+#if TPZ_3XTF32
+  mma_tf32(c, al, bh);
+  mma_tf32(c, ah, bl);
+#endif
+  mma_tf32(c, ah, bh);
+}
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   const int bytes = valid ? 16 : 0;      // src-size 0 => the 16 destination bytes are zero-filled
@@ -133,70 +155,82 @@ __global__ void __launch_bounds__(256) conv_mma_kernel(MGeom g, const float* __r
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
 
-  auto issue_chunk = [&](int kc, int buf) {
-    const int tap = kc / cchunks, c0 = (kc - tap * cchunks) * GBK;
-    const int r = tap / g.kw, t = tap - r * g.kw;
+  // issue-side running state: chunks are issued in order, so (tap row, tap col, channel chunk) advance incrementally
+  // and the per-row gather offsets are recomputed only when the tap changes (no divisions in the steady state)
+  int i_r = 0, i_t = 0, i_c0 = 0;
+  long long a_off[2] = {0, 0};
+  bool a_ok[2] = {false, false};
+  auto tap_setup = [&]() {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       bool ok = arow_ok[h];
       int sy = 0, sx = 0;
       if (ok) {
         if (MODE == 0) {
-          sy = ay[h] * g.stride + r * g.dil + g.org;
-          sx = ax[h] * g.stride + t * g.dil + g.org;
+          sy = ay[h] * g.stride + i_r * g.dil + g.org;
+          sx = ax[h] * g.stride + i_t * g.dil + g.org;
           ok = sy >= 0 && sy < SH && sx >= 0 && sx < SW;
         } else {
-          const int ny = ay[h] - g.org - r * g.dil, nx = ax[h] - g.org - t * g.dil;
-          ok = ny >= 0 && nx >= 0 && (ny % g.stride) == 0 && (nx % g.stride) == 0;
-          sy = ny / g.stride; sx = nx / g.stride;
+          const int ny = ay[h] - g.org - i_r * g.dil, nx = ax[h] - g.org - i_t * g.dil;
+          ok = ny >= 0 && nx >= 0;
+          if (g.stride == 1) { sy = ny; sx = nx; }
+          else { ok = ok && (ny % g.stride) == 0 && (nx % g.stride) == 0; sy = ny / g.stride; sx = nx / g.stride; }
           ok = ok && sy < SH && sx < SW;
         }
       }
-      const float* gp = ok ? src + (((long long)an[h] * SH + sy) * SW + sx) * Cs + c0 + a_quad * 4 : src;
-      cp_async16(&As[buf][a_row + h * 64][a_quad * 4], gp, ok);
+      a_ok[h] = ok;
+      a_off[h] = ok ? (((long long)an[h] * SH + sy) * SW + sx) * Cs + a_quad * 4 : 0;
     }
+  };
+  tap_setup();
+  const int b_kk = tid / (BN / 4), b_nq = tid - b_kk * (BN / 4);     // B staging role (threads < GBK*BN/4)
+  const bool b_role = tid < GBK * BN / 4;
+  const bool b_ok = b_role && (n0 + b_nq * 4 < Nn);
+  auto issue_chunk = [&](int buf) {
 #pragma unroll
-    for (int e = 0; e < (GBK * BN / 4 + 255) / 256; ++e) {
-      const int idx = tid + e * 256;
-      if (idx < GBK * BN / 4) {
-        const int kk = idx / (BN / 4), nq = idx - kk * (BN / 4);
-        const int n = n0 + nq * 4;
-        const bool ok = n < Nn;
-        const float* gp = ok ? wpk + ((long long)tap * Cs + c0 + kk) * Nn + n : wpk;
-        cp_async16(&Bs[buf][kk][nq * 4], gp, ok);
-      }
+    for (int h = 0; h < 2; ++h)
+      cp_async16(&As[buf][a_row + h * 64][a_quad * 4], src + a_off[h] + i_c0, a_ok[h]);
+    if (b_role) {
+      const int tap = i_r * g.kw + i_t;
+      const float* gp = b_ok ? wpk + ((long long)tap * Cs + i_c0 + b_kk) * Nn + n0 + b_nq * 4 : wpk;
+      cp_async16(&Bs[buf][b_kk][b_nq * 4], gp, b_ok);
+    }
+    i_c0 += GBK;
+    if (i_c0 == Cs) {
+      i_c0 = 0;
+      if (++i_t == g.kw) { i_t = 0; ++i_r; }
+      tap_setup();
     }
   };
 
 #pragma unroll
   for (int s2 = 0; s2 < STG - 1; ++s2) {
-    if (s2 < nk) issue_chunk(s2, s2);
+    if (s2 < nk) issue_chunk(s2);
     cp_async_commit();
   }
   for (int kc = 0; kc < nk; ++kc) {
     const int buf = kc % STG;
     cp_async_wait<STG - 2>();
     __syncthreads();
-    if (kc + STG - 1 < nk) issue_chunk(kc + STG - 1, (kc + STG - 1) % STG);
+    if (kc + STG - 1 < nk) issue_chunk((kc + STG - 1) % STG);
     cp_async_commit();
 #pragma unroll
     for (int k8 = 0; k8 < GBK; k8 += 8) {
-      float bf[4][2];
+      uint32_t bh[4][2], bl[4][2];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        bf[j][0] = Bs[buf][k8 + tq][wn * 32 + j * 8 + gq];
-        bf[j][1] = Bs[buf][k8 + tq + 4][wn * 32 + j * 8 + gq];
+        const float bf[2] = {Bs[buf][k8 + tq][wn * 32 + j * 8 + gq], Bs[buf][k8 + tq + 4][wn * 32 + j * 8 + gq]};
+        split_tf32(bf, bh[j], bl[j]);
       }
 #pragma unroll
       for (int i = 0; i < MT; ++i) {
         const int rb0 = wm * (GBM / WM) + i * 16;
-        float af[4];
-        af[0] = As[buf][rb0 + gq][k8 + tq];
-        af[1] = As[buf][rb0 + gq + 8][k8 + tq];
-        af[2] = As[buf][rb0 + gq][k8 + tq + 4];
-        af[3] = As[buf][rb0 + gq + 8][k8 + tq + 4];
+        const float af[4] = {As[buf][rb0 + gq][k8 + tq], As[buf][rb0 + gq + 8][k8 + tq], As[buf][rb0 + gq][k8 + tq + 4],
+                             As[buf][rb0 + gq + 8][k8 + tq + 4]};
+        uint32_t ah[4], al[4];
+        split_tf32(af, ah, al);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) mma_f32x3(acc[i][j], af, bf[j]);
+        for (int j = 0; j < 4; ++j) mma_split(acc[i][j], ah, al, bh[j], bl[j]);
       }
     }
   }
@@ -273,55 +307,58 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(MGeom g, const float* __
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
 
-  auto issue_chunk = [&](long long p0, int buf) {
-    const long long p = p0 + s_p;
-    const bool pv = p < pend;
+  // running (n, oy, ox) of this thread's staging pixel; advanced by WBK pixels per issued chunk (no divisions)
+  long long ip = pbeg + s_p;
+  int i_ox, i_oy, i_n;
+  {
+    const long long pp = ip < P ? ip : 0;
+    i_ox = pp % g.Wo; const long long q = pp / g.Wo; i_oy = q % g.Ho; i_n = q / g.Ho;
+  }
+  auto issue_chunk = [&](int buf) {
+    const bool pv = ip < pend;
     if (role != 1) {
       const bool ok = pv && (co0 + s_q * 4 < g.Co);
-      cp_async16(&As[buf][s_p][s_q * 4], ok ? dy + p * g.Co + co0 + s_q * 4 : dy, ok);
+      cp_async16(&As[buf][s_p][s_q * 4], ok ? dy + ip * g.Co + co0 + s_q * 4 : dy, ok);
     }
     if (role != 0) {
-      bool ok = pv && (ci0 + s_q * 4 < g.Ci);
-      const float* gp = x;
-      if (ok) {
-        const int ox = p % g.Wo; const long long q = p / g.Wo; const int oy = q % g.Ho; const int n = q / g.Ho;
-        const int iy = oy * g.stride + r * g.dil + g.org, ix = ox * g.stride + t * g.dil + g.org;
-        ok = iy >= 0 && iy < g.H && ix >= 0 && ix < g.W;
-        if (ok) gp = x + (((long long)n * g.H + iy) * g.W + ix) * g.Ci + ci0 + s_q * 4;
-      }
+      const int iy = i_oy * g.stride + r * g.dil + g.org, ix = i_ox * g.stride + t * g.dil + g.org;
+      const bool ok = pv && (ci0 + s_q * 4 < g.Ci) && iy >= 0 && iy < g.H && ix >= 0 && ix < g.W;
+      const float* gp = ok ? x + (((long long)i_n * g.H + iy) * g.W + ix) * g.Ci + ci0 + s_q * 4 : x;
       cp_async16(&Bs[buf][s_p][s_q * 4], gp, ok);
     }
+    ip += WBK;
+    i_ox += WBK;
+    while (i_ox >= g.Wo) { i_ox -= g.Wo; if (++i_oy == g.Ho) { i_oy = 0; ++i_n; } }
   };
   const int nchunks = (int)((pend - pbeg + WBK - 1) / WBK);
 #pragma unroll
   for (int s2 = 0; s2 < STG - 1; ++s2) {
-    if (s2 < nchunks) issue_chunk(pbeg + (long long)s2 * WBK, s2);
+    if (s2 < nchunks) issue_chunk(s2);
     cp_async_commit();
   }
   for (int it = 0; it < nchunks; ++it) {
     const int buf = it % STG;
     cp_async_wait<STG - 2>();
     __syncthreads();
-    if (it + STG - 1 < nchunks) issue_chunk(pbeg + (long long)(it + STG - 1) * WBK, (it + STG - 1) % STG);
+    if (it + STG - 1 < nchunks) issue_chunk((it + STG - 1) % STG);
     cp_async_commit();
 #pragma unroll
     for (int k8 = 0; k8 < WBK; k8 += 8) {
-      float bf[NJ][2];
+      uint32_t bh[NJ][2], bl[NJ][2];
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
-        bf[j][0] = Bs[buf][k8 + tq][wn * WTN + j * 8 + gq];
-        bf[j][1] = Bs[buf][k8 + tq + 4][wn * WTN + j * 8 + gq];
+        const float bf[2] = {Bs[buf][k8 + tq][wn * WTN + j * 8 + gq], Bs[buf][k8 + tq + 4][wn * WTN + j * 8 + gq]};
+        split_tf32(bf, bh[j], bl[j]);
       }
 #pragma unroll
       for (int i = 0; i < MI; ++i) {
         const int mb = wm * WTM + i * 16;
-        float af[4];
-        af[0] = As[buf][k8 + tq][mb + gq];
-        af[1] = As[buf][k8 + tq][mb + gq + 8];
-        af[2] = As[buf][k8 + tq + 4][mb + gq];
-        af[3] = As[buf][k8 + tq + 4][mb + gq + 8];
+        const float af[4] = {As[buf][k8 + tq][mb + gq], As[buf][k8 + tq][mb + gq + 8], As[buf][k8 + tq + 4][mb + gq],
+                             As[buf][k8 + tq + 4][mb + gq + 8]};
+        uint32_t ah[4], al[4];
+        split_tf32(af, ah, al);
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) mma_f32x3(acc[i][j], af, bf[j]);
+        for (int j = 0; j < NJ; ++j) mma_split(acc[i][j], ah, al, bh[j], bl[j]);
       }
     }
   }

@@ -24,6 +24,7 @@ from .ops import ConvPart
 #   TPZ_RESIDUAL=epilogue identity skip added in the epilogue (global loads) instead of an identity k-block in the MMA
 FIRST_ON_TC = os.environ.get('TPZ_FIRST', 'tc') != 'simt'
 RESIDUAL_IN_MMA = os.environ.get('TPZ_RESIDUAL', 'mma') != 'epilogue'
+LAST_ON_TC = os.environ.get('TPZ_LAST', 'tc') != 'simt'      # Cout=1 U-Net tail on the tensor-core kernel
 
 
 def _rup(c: int, m: int = 32) -> int:
@@ -337,7 +338,12 @@ def _build_unet_plan(model, device):
             cin = cc.weight.shape[1]
             wl = torch.zeros((kl ** dims, _rup(cin)), dtype=torch.float32)
             wl[:, :cin] = cc.weight.detach().float().cpu()[0].reshape(cin, -1).t()
-            plan['dec'][1] = dict(a=pa, b=pb, onehot=onehot.contiguous().to(device), k=k, ntap_store=_tap_ld(ntap),
+            # dec1.4 (Cout = 1) on the tensor-core kernel: 16 output columns (1 real), the fused "dot" epilogue picks
+            # column 0, adds the bias and de-normalises -> dense fp32 image; no 16-channel tensor is written
+            onehot0 = torch.zeros(1, 1, 1, 1); onehot0[0, 0, 0, 0] = 1.0
+            pl = ops.pack_tc_conv([ConvPart(cc.weight, _rup(cin), 1, same_org(kl))], None, 16, 1.0, device,
+                                  dot_w=onehot0, dot_b=float(cc.bias.detach()[0]))
+            plan['dec'][1] = dict(last_tc=pl, a=pa, b=pb, onehot=onehot.contiguous().to(device), k=k, ntap_store=_tap_ld(ntap),
                                   last_w=wl.contiguous().to(device), last_b=float(cc.bias.detach()[0]),
                                   last_k=(kl if dims == 3 else 1, kl, kl), last_pad=kl // 2, last_c=cin)
     return plan
@@ -400,8 +406,12 @@ def unet_forward(model, x: torch.Tensor, denorm_stats: Optional[torch.Tensor] = 
             ops.tc_conv(d['a'], [up, raw], (N, D, H, W), out=o)
             o2 = torch.empty((N, D, H, W, d['b'].Co), dtype=torch.float16, device=x.device)
             ops.tc_conv(d['b'], [o], (N, D, H, W), out=o2)
-            y = ops.conv_last(o2, d['last_c'], d['last_w'], d['last_b'], d['last_k'], 1, d['last_pad'],
-                              stats=denorm_stats)
+            if LAST_ON_TC:
+                y = torch.empty((N, D, H, W), dtype=torch.float32, device=x.device)
+                ops.tc_conv(d['last_tc'], [o2], (N, D, H, W), out=None, dot_out=y, dot_affine=denorm_stats)
+            else:
+                y = ops.conv_last(o2, d['last_c'], d['last_w'], d['last_b'], d['last_k'], 1, d['last_pad'],
+                                  stats=denorm_stats)
     if dims == 2:
         return y.view(y.shape[0], 1, y.shape[2], y.shape[3])
     return y.view(y.shape[0], 1, y.shape[1], y.shape[2], y.shape[3])

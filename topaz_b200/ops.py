@@ -118,7 +118,7 @@ def pack_tc_conv(parts: Sequence[ConvPart], bias: Optional[torch.Tensor], co_sto
 def fill_tc_args(plan: TcConvPlan, srcs: Sequence[torch.Tensor], out_shape: Tuple[int, int, int, int],
                  out: Optional[torch.Tensor], res: Optional[torch.Tensor] = None,
                  res_org: Tuple[int, int, int] = (0, 0, 0), dot_out: Optional[torch.Tensor] = None,
-                 out_coff: int = 0) -> TpzTcConvArgs:
+                 out_coff: int = 0, dot_affine: Optional[torch.Tensor] = None) -> TpzTcConvArgs:
     a = TpzTcConvArgs()
     a.nsrc = len(srcs)
     for i, t in enumerate(srcs):
@@ -152,6 +152,8 @@ def fill_tc_args(plan: TcConvPlan, srcs: Sequence[torch.Tensor], out_shape: Tupl
         a.out = out.data_ptr(); a.out_ld = out.shape[4]; a.out_coff = out_coff
     if dot_out is not None:
         a.dot_w = plan.dot_w.data_ptr(); a.dot_b = plan.dot_b; a.dot_out = dot_out.data_ptr()
+        if dot_affine is not None:
+            a.dot_affine = dot_affine.data_ptr()
     return a
 
 
@@ -161,9 +163,9 @@ EVENT_HOOK = None         # optional callable(tag) -> (start_event, end_event) r
 
 
 def tc_conv(plan: TcConvPlan, srcs, out_shape, out=None, res=None, res_org=(0, 0, 0), dot_out=None, out_coff=0,
-            tag=None):
+            tag=None, dot_affine=None):
     global LAUNCH_COUNT
-    a = fill_tc_args(plan, srcs, out_shape, out, res, res_org, dot_out, out_coff)
+    a = fill_tc_args(plan, srcs, out_shape, out, res, res_org, dot_out, out_coff, dot_affine)
     fn = {'auto': _lib.lib().tpz_tc_conv, 'v1': _lib.lib().tpz_tc_conv_v1, 'v2': _lib.lib().tpz_tc_conv_v2}[TC_VARIANT]
     hook = EVENT_HOOK(tag) if (EVENT_HOOK is not None and tag is not None) else None
     if hook is not None:
