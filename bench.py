@@ -23,6 +23,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
+# NCCL prints its version banner on STDOUT when NCCL_DEBUG=VERSION/INFO is set in the environment; the driver
+# expects exactly one JSON line there.
+if os.environ.get('TPZ_KEEP_NCCL_DEBUG') is None:
+    os.environ['NCCL_DEBUG'] = 'WARN'
+
 import numpy as np
 import torch
 
@@ -30,6 +35,14 @@ METRIC = 'megapixels/s scored (ResNet8-u64 dense forward, 4096x4096 micrographs)
 UNIT = 'Mpx/s'
 # algorithmic FLOPs (2*MAC) of the reference network per OUTPUT pixel at 4096^2 (SURVEY 8d / BASELINE.md section 2)
 FLOP_PER_PX_4096 = 2636177.0
+
+
+def load_traffic():
+    """DRAM bytes (read+write) per launch of the dominant kernel from the committed ncu --set full capture."""
+    path = os.path.join(ROOT, 'profiles', 'dominant_kernel_ncu.json')
+    if os.path.exists(path):
+        return json.load(open(path)).get('dram_bytes_per_launch')
+    return None
 
 
 def load_peaks():
@@ -245,7 +258,7 @@ def main():
             'clocks': sampler.summary(),
             'roofline': {'bound': 'tensor', 'kernel': 'tc_conv (5x5 dil4 128->256 + fused classifier dot)',
                          'achieved': achieved, 'peak': peaks['tflops'], 'unit': 'TFLOP/s',
-                         'frac': (achieved / peaks['tflops']) if achieved else None, 'traffic': None,
+                         'frac': (achieved / peaks['tflops']) if achieved else None, 'traffic': load_traffic() if S == 4096 else None,
                          'peak_source': peaks['src'], 'ms_per_launch': dom_avg_ms, 'launches_timed': len(dom_ms),
                          'step_tflops': (FLOP_PER_PX_4096 * S * S / 1e12) / (ms_max / args.steps / 1e3) if S == 4096 else None},
         }

@@ -6,6 +6,7 @@
 One JSON line per workload on rank 0.  Weights: pretrained 2-D unet / resnet8_u32 from the golden fixtures;
 the 3-D model uses seeded random weights (the 11.7 MB pretrained file is not shipped)."""
 import argparse, json, os, sys, time
+os.environ.setdefault('TPZ_X', '1'); os.environ['NCCL_DEBUG'] = 'WARN'
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np

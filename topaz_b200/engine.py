@@ -295,10 +295,16 @@ def _build_unet_plan(model, device):
     c1 = enc[0][0]
     k1 = c1.weight.shape[-1]
     plan['first_tc'] = None
-    if dims == 2 and FIRST_ON_TC and k1 * k1 <= 128:
+    if FIRST_ON_TC and k1 * k1 <= 128:
+        # Cin = 1: in-plane im2col (k*k taps -> channels) + tensor-core GEMM; in 3-D the k z-taps stay taps of the GEMM
         ld = _tap_ld(k1 * k1)
-        plan['first_tc'] = dict(k=k1, ld=ld, plan=ops.pack_tc_conv(
-            [ConvPart(c1.weight.detach().reshape(nf, k1 * k1, 1, 1), ld, 1)], c1.bias, _rup(nf), slope, device))
+        if dims == 2:
+            w1 = c1.weight.detach().reshape(nf, k1 * k1, 1, 1)
+            org = (0, 0, 0)
+        else:
+            w1 = c1.weight.detach().reshape(nf, k1, k1 * k1).permute(0, 2, 1).reshape(nf, k1 * k1, k1, 1, 1)
+            org = (0, 0, -(k1 // 2))
+        plan['first_tc'] = dict(k=k1, ld=ld, plan=ops.pack_tc_conv([ConvPart(w1, ld, 1, org)], c1.bias, _rup(nf), slope, device))
     plan['first'] = dict(w=c1.weight.detach().float().reshape((nf,) + ((1,) if dims == 2 else ()) + tuple(c1.weight.shape[2:])).contiguous().to(device),
                          b=c1.bias.detach().float().to(device), pad=c1.weight.shape[-1] // 2, out_ld=_rup(nf),
                          pool=len(enc[0]) > 2)
@@ -365,10 +371,10 @@ def unet_forward(model, x: torch.Tensor, denorm_stats: Optional[torch.Tensor] = 
     f = plan['first']
     if plan['first_tc'] is not None:
         ft = plan['first_tc']
-        col = ops.im2col_first(xi[:, 0], ft['k'], ft['k'] // 2, ft['ld'])
-        N0, _, H0, W0, _ = col.shape
-        h = torch.empty((N0, 1, H0, W0, ft['plan'].Co), dtype=torch.float16, device=x.device)
-        ops.tc_conv(ft['plan'], [col], (N0, 1, H0, W0), out=h)
+        N0, D0, H0, W0 = xi.shape
+        col = ops.im2col_first(xi.reshape(N0 * D0, H0, W0), ft['k'], ft['k'] // 2, ft['ld']).view(N0, D0, H0, W0, ft['ld'])
+        h = torch.empty((N0, D0, H0, W0, ft['plan'].Co), dtype=torch.float16, device=x.device)
+        ops.tc_conv(ft['plan'], [col], (N0, D0, H0, W0), out=h)
     else:
         h = ops.conv_first(xi, f['w'], f['b'], 1, f['pad'], 0.1, f['out_ld'])
     skips = []
