@@ -39,7 +39,11 @@ typedef struct {
   const tpz_half* ptr; /* [N][D][H][W][ld] fp16 */
   int N, D, H, W, C, ld;
   int org[3];          /* (x,y,z) offset added to the output coordinate: -padding or +crop */
-  int kw, kh;          /* in-plane tap grid of this source (taps at multiples of `lattice`)  */
+  int kw, kh;          /* in-plane tap grid of this source (taps at multiples of its lattice spacing)  */
+  int lat;             /* lattice spacing of THIS source in its own pixels (0 = same as the output `lattice`).  With
+                          lat != lattice the source has a different resolution than the output: lat = 1 under an output
+                          lattice of 2 reads a half-resolution tensor, i.e. a fused nearest-neighbour 2x up-sampling      */
+  int no_phase;        /* 1: the output phase offset is NOT added to this source's coordinates (half-resolution source) */
 } TpzTcSrc;
 
 typedef struct {
@@ -52,6 +56,7 @@ typedef struct {
   int N, Do, Ho, Wo, Co;   /* output geometry */
   int TW, TH;              /* pixel tile of the per-tap kernel, TW*TH == 128, TW % 8 == 0 */
   int lattice;             /* in-plane dilation shared by all taps (halo-resident kernel); 0 = per-tap kernel only */
+  int phase_sel;           /* 0: all lattice*lattice output phases; k>0: only phase k-1 (py*lattice+px) is computed    */
   const float* bias;       /* [Co] or NULL */
   float neg_slope;         /* activation: v>0 ? v : v*neg_slope (0 = ReLU, 1 = linear, 0.1 = LeakyReLU) */
   const tpz_half* res;     /* optional residual, added before the activation */

@@ -38,7 +38,8 @@ struct Tc2Params {
   int nsrc;
   int org[2][3];
   int hx[2], rows_loaded[2], split_rows[2];
-  int L;
+  int slat[2], sphase[2];   // per-source lattice spacing / whether the output phase shifts the source
+  int L, phase_fixed;
   int N, Do, Ho, Wo, Co, CS;
   int tiles_x, tiles_y, num_tiles;
   int ngroups, nkb;
@@ -76,12 +77,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 struct TileCoord {
-  int n, z, x_first, y_first;
+  int n, z, qx, qy, phx, phy;   // lattice index of the tile origin and the phase; output pixel = (q + i) * L + ph
 };
 __device__ __forceinline__ TileCoord decode_tile(const Tc2Params& p, int tile) {
   const int LL = p.L * p.L;
-  const int ph = tile % LL;
-  int rest = tile / LL;
+  int ph, rest;
+  if (p.phase_fixed >= 0) { ph = p.phase_fixed; rest = tile; }
+  else { ph = tile % LL; rest = tile / LL; }
   const int txq = rest % p.tiles_x;
   rest /= p.tiles_x;
   const int tyq = rest % p.tiles_y;
@@ -89,8 +91,10 @@ __device__ __forceinline__ TileCoord decode_tile(const Tc2Params& p, int tile) {
   TileCoord t;
   t.n = plane / p.Do;
   t.z = plane - t.n * p.Do;
-  t.x_first = txq * T2W * p.L + (ph % p.L);
-  t.y_first = tyq * (16 * p.ntile) * p.L + (ph / p.L);
+  t.qx = txq * T2W;
+  t.qy = tyq * (16 * p.ntile);
+  t.phx = ph % p.L;
+  t.phy = ph / p.L;
   return t;
 }
 
@@ -162,8 +166,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv2_kernel(const __grid_cons
           if (ptx::elect_one()) {
             ptx::mbar_expect_tx(&afull[s], (uint32_t)(hx * p.rows_loaded[src] * ROWB));
             for (int row0 = 0; row0 < p.rows_loaded[src]; row0 += sr) {
-              ptx::tma_load_5d(dst + (size_t)row0 * hx * ROWB, &p.tmA[src], &afull[s], G.c0, tc.x_first + p.org[src][0],
-                               tc.y_first + p.org[src][1] + row0 * p.L, tc.z + p.org[src][2] + G.dz, tc.n);
+              ptx::tma_load_5d(dst + (size_t)row0 * hx * ROWB, &p.tmA[src], &afull[s], G.c0,
+                               tc.qx * p.slat[src] + p.sphase[src] * tc.phx + p.org[src][0],
+                               (tc.qy + row0) * p.slat[src] + p.sphase[src] * tc.phy + p.org[src][1],
+                               tc.z + p.org[src][2] + G.dz, tc.n);
             }
           }
           __syncwarp();
@@ -271,8 +277,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv2_kernel(const __grid_cons
       mbar_wait(&tfull[st], aph);
       ptx::tc_fence_after();
       for (int a = 0; a < p.ntile; ++a) {
-        const int gx = tc.x_first + li * p.L;
-        const int gy = tc.y_first + (lj + 16 * a) * p.L;
+        const int gx = (tc.qx + li) * p.L + tc.phx;
+        const int gy = (tc.qy + lj + 16 * a) * p.L + tc.phy;
         const bool valid = (gx < p.Wo) && (gy < p.Ho);
         const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (st * p.ntile + a) * p.CS;
         const long long opix = (((long long)tc.n * p.Do + tc.z) * p.Ho + gy) * p.Wo + gx;
@@ -381,12 +387,15 @@ static int launch_v2(const TpzTcConvArgs* a, cudaStream_t stream, bool dry) {
   for (int s = 0; s < a->nsrc; ++s) {
     const TpzTcSrc& src = a->src[s];
     if (src.kw < 1 || src.kh < 1) return -1;
+    const int sl = src.lat > 0 ? src.lat : L;
+    if (sl > 8) return -1;
+    p.slat[s] = sl; p.sphase[s] = src.no_phase ? 0 : 1;
     const int hx = T2W + src.kw - 1, hy = th + src.kh - 1;
-    if ((hx - 1) * L + 1 > 256) return -1;
-    const int ext = (hy - 1) * L + 1;
+    if ((hx - 1) * sl + 1 > 256) return -1;
+    const int ext = (hy - 1) * sl + 1;
     const int nsplit = (ext + 255) / 256;
     const int sr = (hy + nsplit - 1) / nsplit;
-    if ((sr - 1) * L + 1 > 256) return -1;
+    if ((sr - 1) * sl + 1 > 256) return -1;
     p.hx[s] = hx; p.split_rows[s] = sr; p.rows_loaded[s] = sr * nsplit;
     const int bytes = (hx * sr * nsplit * rowb + 1023) / 1024 * 1024;
     if (bytes > a_stage) a_stage = bytes;
@@ -403,8 +412,9 @@ static int launch_v2(const TpzTcConvArgs* a, cudaStream_t stream, bool dry) {
     for (int j = i; j < a->nkb; ++j) {
       const TcKBlock& k = a->kb[j];
       if (used[j] || k.src != G.src || k.c0 != G.c0 || k.dz != G.dz) continue;
-      if (k.dx % L || k.dy % L) return -1;
-      const int sx = k.dx / L, ry = k.dy / L;
+      const int sl = p.slat[k.src];
+      if (k.dx % sl || k.dy % sl) return -1;
+      const int sx = k.dx / sl, ry = k.dy / sl;
       if (sx < 0 || sx >= a->src[k.src].kw || ry < 0 || ry >= a->src[k.src].kh) return -1;
       p.taps[nt].kb = (uint16_t)j;
       p.taps[nt].row_off = (uint16_t)(ry * p.hx[k.src] + sx);
@@ -442,8 +452,9 @@ static int launch_v2(const TpzTcConvArgs* a, cudaStream_t stream, bool dry) {
     uint64_t dims[5] = {(uint64_t)src.C, (uint64_t)src.W, (uint64_t)src.H, (uint64_t)src.D, (uint64_t)src.N};
     uint64_t strides[4] = {(uint64_t)src.ld * 2, (uint64_t)src.ld * 2 * src.W, (uint64_t)src.ld * 2 * src.W * src.H,
                            (uint64_t)src.ld * 2 * src.W * src.H * src.D};
-    uint32_t box[5] = {(uint32_t)a->KC, (uint32_t)((p.hx[s] - 1) * L + 1), (uint32_t)((p.split_rows[s] - 1) * L + 1), 1, 1};
-    uint32_t es[5] = {1, (uint32_t)L, (uint32_t)L, 1, 1};
+    const uint32_t sl = (uint32_t)p.slat[s];
+    uint32_t box[5] = {(uint32_t)a->KC, (uint32_t)((p.hx[s] - 1) * sl + 1), (uint32_t)((p.split_rows[s] - 1) * sl + 1), 1, 1};
+    uint32_t es[5] = {1, sl, sl, 1, 1};
     int rc = tpz_encode_tmap(&p.tmA[s], src.ptr, 5, dims, strides, box, es, rowb);
     if (rc) return rc;
     p.org[s][0] = src.org[0]; p.org[s][1] = src.org[1]; p.org[s][2] = src.org[2];
@@ -461,7 +472,9 @@ static int launch_v2(const TpzTcConvArgs* a, cudaStream_t stream, bool dry) {
   const int qW = tpz_div_up(a->Wo, L), qH = tpz_div_up(a->Ho, L);
   p.tiles_x = tpz_div_up(qW, T2W);
   p.tiles_y = tpz_div_up(qH, th);
-  const long long ntl = (long long)L * L * p.tiles_x * p.tiles_y * a->Do * a->N;
+  p.phase_fixed = a->phase_sel > 0 ? a->phase_sel - 1 : -1;
+  TPZ_CHECK(a->phase_sel >= 0 && a->phase_sel <= L * L, "tpz_tc_conv: phase_sel=%d out of range for lattice %d", a->phase_sel, L);
+  const long long ntl = (long long)(p.phase_fixed >= 0 ? 1 : L * L) * p.tiles_x * p.tiles_y * a->Do * a->N;
   TPZ_CHECK(ntl > 0 && ntl < (1ll << 31), "tpz_tc_conv: bad tile count %lld", ntl);
   p.num_tiles = (int)ntl;
   p.bias = a->bias; p.neg_slope = a->neg_slope;

@@ -24,6 +24,7 @@ from .ops import ConvPart
 #   TPZ_RESIDUAL=epilogue identity skip added in the epilogue (global loads) instead of an identity k-block in the MMA
 FIRST_ON_TC = os.environ.get('TPZ_FIRST', 'tc') != 'simt'
 RESIDUAL_IN_MMA = os.environ.get('TPZ_RESIDUAL', 'mma') != 'epilogue'
+UP2_FUSED = os.environ.get('TPZ_UP2', 'fused') != 'off'       # fused 2x up-sampling in U-Net dec1.0 (poly-phase)
 LAST_ON_TC = os.environ.get('TPZ_LAST', 'tc') != 'simt'      # Cout=1 U-Net tail on the tensor-core kernel
 
 
@@ -344,12 +345,33 @@ def _build_unet_plan(model, device):
             cin = cc.weight.shape[1]
             wl = torch.zeros((kl ** dims, _rup(cin)), dtype=torch.float32)
             wl[:, :cin] = cc.weight.detach().float().cpu()[0].reshape(cin, -1).t()
+            # fused nearest-2x up-sampling (2-D, exact factor 2): output phase (py,px) of the conv over the up-sampled
+            # tensor equals a conv over the HALF-resolution tensor with the taps that alias onto the same source pixel
+            # summed (5x5 -> 3x3 per phase: 2.8x fewer MACs on the dominant layer, and no up-sampled tensor in HBM).
+            up2 = None
+            if dims == 2 and UP2_FUSED:
+                pad = k // 2
+                wu = ca.weight.detach().float().cpu()[:, :up_c]                       # [Co, up_c, k, k]
+                up2 = []
+                for py in range(2):
+                    for px in range(2):
+                        offy = [(py + r - pad) // 2 for r in range(k)]
+                        offx = [(px + r - pad) // 2 for r in range(k)]
+                        ay0, ax0 = min(offy), min(offx)
+                        wm = torch.zeros((wu.shape[0], up_c, max(offy) - ay0 + 1, max(offx) - ax0 + 1))
+                        for r in range(k):
+                            for t in range(k):
+                                wm[:, :, offy[r] - ay0, offx[t] - ax0] += wu[:, :, r, t]
+                        parts2 = [ConvPart(wm, _rup(up_c), 1, (ax0, ay0, 0), lat=1, phase=False),
+                                  ConvPart(wraw.reshape(wraw.shape[0], ntap, 1, 1, 1), _tap_ld(ntap), 1, (0, 0, 0), lat=2)]
+                        up2.append(ops.pack_tc_conv(parts2, ca.bias, _rup(ca.weight.shape[0]), slope, device, lattice=2,
+                                                    phase_sel=py * 2 + px + 1))
             # dec1.4 (Cout = 1) on the tensor-core kernel: 16 output columns (1 real), the fused "dot" epilogue picks
             # column 0, adds the bias and de-normalises -> dense fp32 image; no 16-channel tensor is written
             onehot0 = torch.zeros(1, 1, 1, 1); onehot0[0, 0, 0, 0] = 1.0
             pl = ops.pack_tc_conv([ConvPart(cc.weight, _rup(cin), 1, same_org(kl))], None, 16, 1.0, device,
                                   dot_w=onehot0, dot_b=float(cc.bias.detach()[0]))
-            plan['dec'][1] = dict(last_tc=pl, a=pa, b=pb, onehot=onehot.contiguous().to(device), k=k, ntap_store=_tap_ld(ntap),
+            plan['dec'][1] = dict(last_tc=pl, up2=up2, a=pa, b=pb, onehot=onehot.contiguous().to(device), k=k, ntap_store=_tap_ld(ntap),
                                   last_w=wl.contiguous().to(device), last_b=float(cc.bias.detach()[0]),
                                   last_k=(kl if dims == 3 else 1, kl, kl), last_pad=kl // 2, last_c=cin)
     return plan
@@ -403,13 +425,17 @@ def unet_forward(model, x: torch.Tensor, denorm_stats: Optional[torch.Tensor] = 
             h = o2
         else:
             N, D, H, W = xi.shape
-            up = ops.upsample_nearest(h, (D, H, W))
             if dims == 2:
                 raw = ops.im2col_first(xi[:, 0], d['k'], d['k'] // 2, d['ntap_store'])
             else:
                 raw = ops.conv_first(xi, d['onehot'], None, 1, d['k'] // 2, 1.0, d['ntap_store'])
             o = torch.empty((N, D, H, W, d['a'].Co), dtype=torch.float16, device=x.device)
-            ops.tc_conv(d['a'], [up, raw], (N, D, H, W), out=o)
+            if d.get('up2') is not None and H == 2 * h.shape[2] and W == 2 * h.shape[3]:
+                for pl2 in d['up2']:                      # one launch per output phase, reading the half-res tensor
+                    ops.tc_conv(pl2, [h, raw], (N, D, H, W), out=o)
+            else:
+                up = ops.upsample_nearest(h, (D, H, W))
+                ops.tc_conv(d['a'], [up, raw], (N, D, H, W), out=o)
             o2 = torch.empty((N, D, H, W, d['b'].Co), dtype=torch.float16, device=x.device)
             ops.tc_conv(d['b'], [o], (N, D, H, W), out=o2)
             if LAST_ON_TC:

@@ -37,6 +37,8 @@ class ConvPart:
     c_store: int                 # stored channels of the source tensor (>= Ci_real, multiple of KC)
     dil: int = 1
     org: Tuple[int, int, int] = (0, 0, 0)   # (x, y, z) offset of tap 0 relative to the output pixel
+    lat: int = 0                 # lattice spacing of this source in its own pixels (0 = the plan's output lattice)
+    phase: bool = True           # False: the output phase does not shift this source (half-resolution source)
 
 
 @dataclass
@@ -47,10 +49,13 @@ class TcConvPlan:
     orgs: List[Tuple[int, int, int]]
     c_stores: List[int]
     tapgrids: List[Tuple[int, int]]   # (kw, kh) per source
-    lattice: int                      # in-plane dilation shared by all multi-tap sources
+    lattice: int                      # output lattice spacing (in-plane dilation shared by all multi-tap sources)
     weights: torch.Tensor        # [nkb, Co, KC] fp16 (device)
     bias: torch.Tensor           # [Co] fp32 (device)
     neg_slope: float
+    lats: List[int] = field(default_factory=list)        # per-source lattice spacing (0 = lattice)
+    phases: List[bool] = field(default_factory=list)     # per-source: output phase shifts the source
+    phase_sel: int = 0                # 0 = all output phases, k = only phase k-1
     dot_w: Optional[torch.Tensor] = None
     dot_b: float = 0.0
     res_scale: Optional[torch.Tensor] = None
@@ -60,7 +65,7 @@ class TcConvPlan:
 
 def pack_tc_conv(parts: Sequence[ConvPart], bias: Optional[torch.Tensor], co_store: int, neg_slope: float,
                  device, KC: Optional[int] = None, dot_w=None, dot_b: float = 0.0, res_scale=None,
-                 out_scale: Optional[torch.Tensor] = None) -> TcConvPlan:
+                 out_scale: Optional[torch.Tensor] = None, lattice: Optional[int] = None, phase_sel: int = 0) -> TcConvPlan:
     """Repack OIHW fp32 weights into the kernel's [k-block][Co][KC] fp16 layout.
 
     k-blocks are ordered (source, tap, chunk); all-zero blocks (channel padding) are dropped.
@@ -108,10 +113,13 @@ def pack_tc_conv(parts: Sequence[ConvPart], bias: Optional[torch.Tensor], co_sto
         rs[:co_real] = res_scale.detach().to(torch.float32).cpu()
         rs = rs.to(device)
     grids = [(int(p.w.shape[-1]), int(p.w.shape[-2])) for p in parts]
-    dils = {p.dil for p, g in zip(parts, grids) if g != (1, 1)}
-    lattice = dils.pop() if len(dils) == 1 else (1 if not dils else 0)
+    if lattice is None:
+        dils = {p.dil for p, g in zip(parts, grids) if g != (1, 1)}
+        lattice = dils.pop() if len(dils) == 1 else (1 if not dils else 0)
     return TcConvPlan(KC=KC, Co=co_store, kblocks=kbs, orgs=[tuple(p.org) for p in parts],
-                      c_stores=[p.c_store for p in parts], tapgrids=grids, lattice=lattice, weights=wt, bias=b.to(device),
+                      c_stores=[p.c_store for p in parts], tapgrids=grids, lattice=lattice,
+                      lats=[p.lat for p in parts], phases=[p.phase for p in parts], phase_sel=phase_sel,
+                      weights=wt, bias=b.to(device),
                       neg_slope=float(neg_slope), dot_w=dw, dot_b=float(dot_b), res_scale=rs)
 
 
@@ -129,6 +137,8 @@ def fill_tc_args(plan: TcConvPlan, srcs: Sequence[torch.Tensor], out_shape: Tupl
         for j in range(3):
             s.org[j] = plan.orgs[i][j]
         s.kw, s.kh = plan.tapgrids[i]
+        s.lat = plan.lats[i] if plan.lats else 0
+        s.no_phase = 0 if (not plan.phases or plan.phases[i]) else 1
     a.weights = plan.weights.data_ptr()
     a.KC = plan.KC
     a.nkb = len(plan.kblocks)
@@ -139,6 +149,7 @@ def fill_tc_args(plan: TcConvPlan, srcs: Sequence[torch.Tensor], out_shape: Tupl
     a.Co = plan.Co
     a.TW, a.TH = plan.TW, plan.TH
     a.lattice = plan.lattice
+    a.phase_sel = plan.phase_sel
     a.bias = plan.bias.data_ptr()
     a.neg_slope = plan.neg_slope
     if res is not None:
