@@ -191,3 +191,47 @@ def test_unet_seeded_2d_and_3d():
 def test_smoke_entry():
     import __graft_entry__ as ge
     ge.smoke()
+
+
+@pytest.mark.parametrize('shape', [(1, 1, 5, 7), (3, 1, 33, 9), (1, 1, 1, 64), (2, 1, 130, 257)])
+def test_dense_classifier_ragged_and_tiny_images(shape):
+    """Edge geometry: images smaller than one 8x32 lattice tile / the receptive field, 1-pixel strips, batches > 1."""
+    g = gold('resnet8_u32_pretrained'); sd = weights_of(g)
+    m = _load(_classifier('resnet8', 32), sd).cuda(); m.eval(); m.fill()
+    x = np.random.default_rng(7).standard_normal(shape).astype(np.float32)
+    with torch.no_grad():
+        y = m(torch.from_numpy(x).cuda()).cpu().numpy()
+    ref = O.classifier_forward(sd, x, 'resnet8', 32, filled=True).numpy()
+    assert y.shape == ref.shape == shape
+    _check(y, ref, TOL)
+
+
+@pytest.mark.parametrize('shape', [(1, 1, 32, 32), (2, 1, 40, 72), (1, 1, 33, 47), (1, 1, 250, 130)])
+def test_unet_edge_sizes(shape):
+    """Smallest legal U-Net inputs (5 poolings), odd sizes (non-2x up-sampling -> gather path) and even sizes (fused path)."""
+    from topaz_b200.denoising.models import UDenoiseNet
+    g = gold('unet_pretrained'); sd = weights_of(g)
+    m = _load(UDenoiseNet(base_width=11, top_width=5), sd).cuda(); m.eval()
+    x = np.random.default_rng(11).standard_normal(shape).astype(np.float32)
+    with torch.no_grad():
+        y = m(torch.from_numpy(x).cuda()).cpu().numpy()
+    ref = O.unet_forward(sd, x).numpy()
+    _check(y, ref, 2e-3)
+
+
+def test_variants_agree_v1_v2():
+    """The per-tap kernel (v1) and the halo-resident kernel (v2) compute the same layer outputs (fp32 accumulation order
+    differs only inside the tensor core)."""
+    from topaz_b200 import ops
+    g = gold('resnet8_u64_pretrained'); sd = weights_of(g)
+    m = _load(_classifier('resnet8', 64), sd).cuda(); m.eval(); m.fill()
+    x = torch.from_numpy(np.random.default_rng(3).standard_normal((1, 1, 160, 200)).astype(np.float32)).cuda()
+    outs = {}
+    try:
+        for v in ('v2', 'v1'):
+            ops.TC_VARIANT = v
+            with torch.no_grad():
+                outs[v] = m(x).cpu().numpy()
+    finally:
+        ops.TC_VARIANT = 'auto'
+    _check(outs['v1'], outs['v2'], 1e-4)

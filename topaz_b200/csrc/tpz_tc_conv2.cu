@@ -26,7 +26,7 @@ constexpr int kMaxAStages = 4, kMaxBStages = 8;
 
 struct Tc2Group {
   int16_t src, c0, dz, ntaps;
-  int32_t tap_begin;
+  int16_t tap_begin, gox, goy, pad;   // (gox, goy): residue class of the group's taps modulo the source lattice
 };
 struct Tc2Tap {
   uint16_t kb, row_off;
@@ -167,8 +167,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv2_kernel(const __grid_cons
             ptx::mbar_expect_tx(&afull[s], (uint32_t)(hx * p.rows_loaded[src] * ROWB));
             for (int row0 = 0; row0 < p.rows_loaded[src]; row0 += sr) {
               ptx::tma_load_5d(dst + (size_t)row0 * hx * ROWB, &p.tmA[src], &afull[s], G.c0,
-                               tc.qx * p.slat[src] + p.sphase[src] * tc.phx + p.org[src][0],
-                               (tc.qy + row0) * p.slat[src] + p.sphase[src] * tc.phy + p.org[src][1],
+                               tc.qx * p.slat[src] + p.sphase[src] * tc.phx + p.org[src][0] + G.gox,
+                               (tc.qy + row0) * p.slat[src] + p.sphase[src] * tc.phy + p.org[src][1] + G.goy,
                                tc.z + p.org[src][2] + G.dz, tc.n);
             }
           }
@@ -384,13 +384,24 @@ static int launch_v2(const TpzTcConvArgs* a, cudaStream_t stream, bool dry) {
   p.acc_stages = (2 * p.ntile * cs <= kTmemCols) ? 2 : 1;
   const int th = 16 * p.ntile;
   int a_stage = 0;
+  // lattice tap grid per source, derived from the k-block table: tap (dx,dy) = residue class (dx mod sl, dy mod sl)
+  // + lattice index (dx div sl, dy div sl); offsets must be >= 0 (the source origin absorbs negative taps)
+  int kwq[2] = {1, 1}, khq[2] = {1, 1};
   for (int s = 0; s < a->nsrc; ++s) {
-    const TpzTcSrc& src = a->src[s];
-    if (src.kw < 1 || src.kh < 1) return -1;
-    const int sl = src.lat > 0 ? src.lat : L;
+    const int sl = a->src[s].lat > 0 ? a->src[s].lat : L;
     if (sl > 8) return -1;
-    p.slat[s] = sl; p.sphase[s] = src.no_phase ? 0 : 1;
-    const int hx = T2W + src.kw - 1, hy = th + src.kh - 1;
+    p.slat[s] = sl; p.sphase[s] = a->src[s].no_phase ? 0 : 1;
+  }
+  for (int i = 0; i < a->nkb; ++i) {
+    const TcKBlock& k = a->kb[i];
+    if (k.dx < 0 || k.dy < 0) return -1;
+    const int sl = p.slat[k.src];
+    if (k.dx / sl + 1 > kwq[k.src]) kwq[k.src] = k.dx / sl + 1;
+    if (k.dy / sl + 1 > khq[k.src]) khq[k.src] = k.dy / sl + 1;
+  }
+  for (int s = 0; s < a->nsrc; ++s) {
+    const int sl = p.slat[s];
+    const int hx = T2W + kwq[s] - 1, hy = th + khq[s] - 1;
     if ((hx - 1) * sl + 1 > 256) return -1;
     const int ext = (hy - 1) * sl + 1;
     const int nsplit = (ext + 255) / 256;
@@ -400,7 +411,7 @@ static int launch_v2(const TpzTcConvArgs* a, cudaStream_t stream, bool dry) {
     const int bytes = (hx * sr * nsplit * rowb + 1023) / 1024 * 1024;
     if (bytes > a_stage) a_stage = bytes;
   }
-  // group the k-blocks by (source, chunk, z-tap); all in-plane taps of a group read one halo tile
+  // group the k-blocks by (source, chunk, z-tap, residue class); all taps of a group read one halo tile
   int ng = 0, nt = 0;
   bool used[TPZ_TC_MAX_KB];
   memset(used, 0, sizeof(used));
@@ -408,16 +419,14 @@ static int launch_v2(const TpzTcConvArgs* a, cudaStream_t stream, bool dry) {
     if (used[i]) continue;
     if (ng >= kMaxGroups) return -1;
     Tc2Group& G = p.groups[ng];
-    G.src = (int16_t)a->kb[i].src; G.c0 = a->kb[i].c0; G.dz = a->kb[i].dz; G.tap_begin = nt; G.ntaps = 0;
+    const int sl0 = p.slat[a->kb[i].src];
+    G.src = (int16_t)a->kb[i].src; G.c0 = a->kb[i].c0; G.dz = a->kb[i].dz; G.tap_begin = (int16_t)nt; G.ntaps = 0;
+    G.gox = (int16_t)(a->kb[i].dx % sl0); G.goy = (int16_t)(a->kb[i].dy % sl0); G.pad = 0;
     for (int j = i; j < a->nkb; ++j) {
       const TcKBlock& k = a->kb[j];
-      if (used[j] || k.src != G.src || k.c0 != G.c0 || k.dz != G.dz) continue;
-      const int sl = p.slat[k.src];
-      if (k.dx % sl || k.dy % sl) return -1;
-      const int sx = k.dx / sl, ry = k.dy / sl;
-      if (sx < 0 || sx >= a->src[k.src].kw || ry < 0 || ry >= a->src[k.src].kh) return -1;
+      if (used[j] || k.src != G.src || k.c0 != G.c0 || k.dz != G.dz || k.dx % sl0 != G.gox || k.dy % sl0 != G.goy) continue;
       p.taps[nt].kb = (uint16_t)j;
-      p.taps[nt].row_off = (uint16_t)(ry * p.hx[k.src] + sx);
+      p.taps[nt].row_off = (uint16_t)((k.dy / sl0) * p.hx[k.src] + (k.dx / sl0));
       used[j] = true; ++nt; ++G.ntaps;
     }
     ++ng;

@@ -280,6 +280,27 @@ def _conv_of(seq, idx):
     return c
 
 
+def _up2_phase_plans(w_up, up_c, k, second_part, bias, co_store, slope, device):
+    """Plans for conv(cat[nearest_up2(h), other]) computed per output phase (py, px) directly from the half-resolution
+    tensor h: taps of the k x k kernel that alias onto the same half-res pixel are summed (5x5 -> 3x3, 3x3 -> 2x2 per
+    phase).  ``second_part(py, px)`` returns the ConvPart of the full-resolution source for that phase."""
+    pad = k // 2
+    wu = w_up.detach().float().cpu()
+    plans = []
+    for py in range(2):
+        for px in range(2):
+            offy = [(py + r - pad) // 2 for r in range(k)]
+            offx = [(px + r - pad) // 2 for r in range(k)]
+            ay0, ax0 = min(offy), min(offx)
+            wm = torch.zeros((wu.shape[0], up_c, max(offy) - ay0 + 1, max(offx) - ax0 + 1))
+            for r in range(k):
+                for t in range(k):
+                    wm[:, :, offy[r] - ay0, offx[t] - ax0] += wu[:, :, r, t]
+            parts = [ConvPart(wm, _rup(up_c), 1, (ax0, ay0, 0), lat=1, phase=False), second_part(py, px)]
+            plans.append(ops.pack_tc_conv(parts, bias, co_store, slope, device, lattice=2, phase_sel=py * 2 + px + 1))
+    return plans
+
+
 def _build_unet_plan(model, device):
     enc = [getattr(model, f'enc{i}') for i in range(1, 10) if hasattr(model, f'enc{i}')]
     ndec = len(enc) - 1
@@ -328,7 +349,13 @@ def _build_unet_plan(model, device):
             pa = ops.pack_tc_conv(parts, ca.bias, _rup(ca.weight.shape[0]), slope, device)
             pb = ops.pack_tc_conv([ConvPart(cb.weight, _rup(ca.weight.shape[0]), 1, same_org(cb.weight.shape[-1]))],
                                   cb.bias, _rup(cb.weight.shape[0]), slope, device)
-            plan['dec'][l] = dict(a=pa, b=pb)
+            up2 = None
+            if dims == 2 and UP2_FUSED:
+                w_skip, pad_k = ca.weight[:, up_c:], k // 2
+                up2 = _up2_phase_plans(ca.weight[:, :up_c], up_c, k,
+                                       lambda py, px: ConvPart(w_skip, _rup(skip_c), 1, (px - pad_k, py - pad_k, 0), lat=2, phase=False),
+                                       ca.bias, _rup(ca.weight.shape[0]), slope, device)
+            plan['dec'][l] = dict(a=pa, b=pb, up2=up2)
             up_c = cb.weight.shape[0]
         else:
             # dec1: [upsampled (up_c ch), raw image (1 ch)] -> conv,lrelu,conv,lrelu,conv
@@ -350,22 +377,10 @@ def _build_unet_plan(model, device):
             # summed (5x5 -> 3x3 per phase: 2.8x fewer MACs on the dominant layer, and no up-sampled tensor in HBM).
             up2 = None
             if dims == 2 and UP2_FUSED:
-                pad = k // 2
-                wu = ca.weight.detach().float().cpu()[:, :up_c]                       # [Co, up_c, k, k]
-                up2 = []
-                for py in range(2):
-                    for px in range(2):
-                        offy = [(py + r - pad) // 2 for r in range(k)]
-                        offx = [(px + r - pad) // 2 for r in range(k)]
-                        ay0, ax0 = min(offy), min(offx)
-                        wm = torch.zeros((wu.shape[0], up_c, max(offy) - ay0 + 1, max(offx) - ax0 + 1))
-                        for r in range(k):
-                            for t in range(k):
-                                wm[:, :, offy[r] - ay0, offx[t] - ax0] += wu[:, :, r, t]
-                        parts2 = [ConvPart(wm, _rup(up_c), 1, (ax0, ay0, 0), lat=1, phase=False),
-                                  ConvPart(wraw.reshape(wraw.shape[0], ntap, 1, 1, 1), _tap_ld(ntap), 1, (0, 0, 0), lat=2)]
-                        up2.append(ops.pack_tc_conv(parts2, ca.bias, _rup(ca.weight.shape[0]), slope, device, lattice=2,
-                                                    phase_sel=py * 2 + px + 1))
+                up2 = _up2_phase_plans(ca.weight[:, :up_c], up_c, k,
+                                       lambda py, px: ConvPart(wraw.reshape(wraw.shape[0], ntap, 1, 1, 1), _tap_ld(ntap), 1,
+                                                               (0, 0, 0), lat=2),
+                                       ca.bias, _rup(ca.weight.shape[0]), slope, device)
             # dec1.4 (Cout = 1) on the tensor-core kernel: 16 output columns (1 real), the fused "dot" epilogue picks
             # column 0, adds the bias and de-normalises -> dense fp32 image; no 16-channel tensor is written
             onehot0 = torch.zeros(1, 1, 1, 1); onehot0[0, 0, 0, 0] = 1.0
@@ -417,9 +432,13 @@ def unet_forward(model, x: torch.Tensor, denorm_stats: Optional[torch.Tensor] = 
         if l > 1:
             skip = skips[l - 2]
             N, D, H, W, _ = skip.shape
-            up = ops.upsample_nearest(h, (D, H, W))
             o = torch.empty((N, D, H, W, d['a'].Co), dtype=torch.float16, device=x.device)
-            ops.tc_conv(d['a'], [up, skip], (N, D, H, W), out=o)
+            if d.get('up2') is not None and H == 2 * h.shape[2] and W == 2 * h.shape[3]:
+                for pl2 in d['up2']:                      # fused nearest-2x up-sampling, one launch per output phase
+                    ops.tc_conv(pl2, [h, skip], (N, D, H, W), out=o)
+            else:
+                up = ops.upsample_nearest(h, (D, H, W))
+                ops.tc_conv(d['a'], [up, skip], (N, D, H, W), out=o)
             o2 = torch.empty((N, D, H, W, d['b'].Co), dtype=torch.float16, device=x.device)
             ops.tc_conv(d['b'], [o], (N, D, H, W), out=o2)
             h = o2
