@@ -123,17 +123,17 @@ def pack_tc_conv(parts: Sequence[ConvPart], bias: Optional[torch.Tensor], co_sto
                       neg_slope=float(neg_slope), dot_w=dw, dot_b=float(dot_b), res_scale=rs)
 
 
-def fill_tc_args(plan: TcConvPlan, srcs: Sequence[torch.Tensor], out_shape: Tuple[int, int, int, int],
-                 out: Optional[torch.Tensor], res: Optional[torch.Tensor] = None,
-                 res_org: Tuple[int, int, int] = (0, 0, 0), dot_out: Optional[torch.Tensor] = None,
-                 out_coff: int = 0, dot_affine: Optional[torch.Tensor] = None) -> TpzTcConvArgs:
+def _static_tc_args(plan: TcConvPlan) -> TpzTcConvArgs:
+    """The launch-invariant part of the argument block (k-block table, weights, epilogue constants); built once per
+    plan and cached on it - filling the 256-entry table in Python on every launch cost more than the launch itself."""
+    a = plan.__dict__.get('_args')
+    if a is not None:
+        return a
     a = TpzTcConvArgs()
-    a.nsrc = len(srcs)
-    for i, t in enumerate(srcs):
-        N, D, H, W, ld = t.shape
+    a.nsrc = len(plan.c_stores)
+    for i in range(a.nsrc):
         s = a.src[i]
-        s.ptr = t.data_ptr(); s.N, s.D, s.H, s.W = N, D, H, W
-        s.C = plan.c_stores[i]; s.ld = ld
+        s.C = plan.c_stores[i]
         for j in range(3):
             s.org[j] = plan.orgs[i][j]
         s.kw, s.kh = plan.tapgrids[i]
@@ -145,26 +145,45 @@ def fill_tc_args(plan: TcConvPlan, srcs: Sequence[torch.Tensor], out_shape: Tupl
     for i, (dx, dy, dz, c0, si) in enumerate(plan.kblocks):
         k = a.kb[i]
         k.dx, k.dy, k.dz, k.c0, k.src = dx, dy, dz, c0, si
-    a.N, a.Do, a.Ho, a.Wo = out_shape
     a.Co = plan.Co
     a.TW, a.TH = plan.TW, plan.TH
     a.lattice = plan.lattice
     a.phase_sel = plan.phase_sel
     a.bias = plan.bias.data_ptr()
     a.neg_slope = plan.neg_slope
+    plan.__dict__['_args'] = a
+    return a
+
+
+def fill_tc_args(plan: TcConvPlan, srcs: Sequence[torch.Tensor], out_shape: Tuple[int, int, int, int],
+                 out: Optional[torch.Tensor], res: Optional[torch.Tensor] = None,
+                 res_org: Tuple[int, int, int] = (0, 0, 0), dot_out: Optional[torch.Tensor] = None,
+                 out_coff: int = 0, dot_affine: Optional[torch.Tensor] = None) -> TpzTcConvArgs:
+    a = _static_tc_args(plan)
+    assert len(srcs) == a.nsrc
+    for i, t in enumerate(srcs):
+        N, D, H, W, ld = t.shape
+        s = a.src[i]
+        s.ptr = t.data_ptr(); s.N, s.D, s.H, s.W = N, D, H, W
+        s.ld = ld
+    a.N, a.Do, a.Ho, a.Wo = out_shape
     if res is not None:
         a.res = res.data_ptr(); a.res_ld = res.shape[4]
         a.res_D, a.res_H, a.res_W = res.shape[1], res.shape[2], res.shape[3]
         for j in range(3):
             a.res_org[j] = res_org[j]
-        if plan.res_scale is not None:
-            a.res_scale = plan.res_scale.data_ptr()
+        a.res_scale = plan.res_scale.data_ptr() if plan.res_scale is not None else None
+    else:
+        a.res = None; a.res_scale = None
     if out is not None:
         a.out = out.data_ptr(); a.out_ld = out.shape[4]; a.out_coff = out_coff
+    else:
+        a.out = None
     if dot_out is not None:
         a.dot_w = plan.dot_w.data_ptr(); a.dot_b = plan.dot_b; a.dot_out = dot_out.data_ptr()
-        if dot_affine is not None:
-            a.dot_affine = dot_affine.data_ptr()
+        a.dot_affine = dot_affine.data_ptr() if dot_affine is not None else None
+    else:
+        a.dot_w = None; a.dot_out = None; a.dot_affine = None
     return a
 
 
