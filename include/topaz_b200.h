@@ -162,6 +162,10 @@ int tpz_lab_umma(const tpz_half* A, int rowsA, const tpz_half* B, int N, int shi
 int tpz_lab_umma_rate(int N, int shift, int sbo_rows, int iters, int two_acc, long long* cycles, void* stream);
 int tpz_lab_tma_stride(const tpz_half* A, int rowsA, int start, int stride, int nrows, tpz_half* out, void* stream);
 
+/* ---- fixed filters: dense 1->1 same-padded fp32 convolution (GaussianDenoise.apply, topaz/filters.py:62-79) ---- */
+int tpz_filter_f32(const float* x, int N, int D, int H, int W, const float* f, int kd, int kh, int kw, float bias, float* y,
+                   void* stream);
+
 /* ---- layout helpers ---- */
 int tpz_f32_to_f16(const float* x, long long n, tpz_half* y, void* stream);
 

@@ -235,3 +235,31 @@ def test_variants_agree_v1_v2():
     finally:
         ops.TC_VARIANT = 'auto'
     _check(outs['v1'], outs['v2'], 1e-4)
+
+
+def test_filters_and_affine_normalize_dropins():
+    """GaussianDenoise.apply (filters.py:62-79) and stats.normalize(method='affine') (stats.py:36-46) vs reference goldens."""
+    from topaz_b200.filters import GaussianDenoise
+    from topaz_b200.stats import normalize
+    g = gold('filters')
+    _check(GaussianDenoise(1.5).apply(g['img'].copy()), g['gauss'], 1e-5)
+    n, meta = normalize(g['img'].copy(), method='affine')
+    _check(n, g['norm'], 1e-5)
+    assert abs(meta['mu'] - float(g['mu'])) < 1e-4 and abs(meta['std'] - float(g['std'])) < 1e-4 and n.dtype == np.float32
+    vol = np.random.default_rng(5).standard_normal((12, 20, 16)).astype(np.float32)
+    _check(GaussianDenoise(0.8, dims=3).apply(vol), O.gaussian_denoise(vol, 0.8), 1e-5)
+
+
+def test_denoise_image_pipeline():
+    """denoise_image (denoise.py:382-416): numpy normalise -> patched denoise -> restore scale, vs the oracle composition."""
+    from topaz_b200.denoising.models import UDenoiseNet
+    from topaz_b200.denoise import Denoise, denoise_image
+    g = gold('unet_pretrained'); sd = weights_of(g)
+    dn = Denoise(_load(UDenoiseNet(base_width=11, top_width=5), sd))
+    mic = g['img']
+    mu, std = mic.mean(), mic.std()
+    ref = std * O.denoise(sd, (mic - mu) / std, patch_size=64, padding=24) + mu
+    _check(denoise_image(mic.copy(), [dn], patch_size=64, padding=24), ref, TOL)
+    refn = O.denoise(sd, (mic - mu) / std, patch_size=64, padding=24)
+    refn = (refn - refn.mean()) / refn.std()
+    _check(denoise_image(mic.copy(), [dn, dn], patch_size=64, padding=24, normalize=True), refn, 2e-3)

@@ -367,6 +367,38 @@ __global__ void affine_kernel(const float* __restrict__ x, long long n, const fl
     y[i] = inverse ? x[i] * sd + mu : (x[i] - mu) / sd;
 }
 
+// dense 1->1 "same" convolution with a small fp32 filter (GaussianDenoise, topaz/filters.py:62-79): one thread per
+// output voxel, filter in shared memory, zero padding.  Memory/L1-bound; optional pre/post filter of the denoise path.
+__global__ void filter_f32_kernel(const float* __restrict__ x, int N, int D, int H, int W, const float* __restrict__ f,
+                                  int kd, int kh, int kw, float bias, float* __restrict__ y) {
+  extern __shared__ float s_f[];
+  const int taps = kd * kh * kw;
+  for (int i = threadIdx.x; i < taps; i += blockDim.x) s_f[i] = f[i];
+  __syncthreads();
+  const size_t total = (size_t)N * D * H * W;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int gx = idx % W; size_t r = idx / W;
+  const int gy = r % H; r /= H;
+  const int gz = r % D; const int n = r / D;
+  float acc = bias;
+  for (int q = 0; q < kd; ++q) {
+    const int iz = gz + q - kd / 2;
+    if (iz < 0 || iz >= D) continue;
+    for (int a = 0; a < kh; ++a) {
+      const int iy = gy + a - kh / 2;
+      if (iy < 0 || iy >= H) continue;
+      const float* row = x + (((size_t)n * D + iz) * H + iy) * W;
+      const float* fr = s_f + (q * kh + a) * kw;
+      for (int b = 0; b < kw; ++b) {
+        const int ix = gx + b - kw / 2;
+        if (ix >= 0 && ix < W) acc = fmaf(row[ix], fr[b], acc);
+      }
+    }
+  }
+  y[idx] = acc;
+}
+
 __global__ void f32_to_f16_kernel(const float* __restrict__ x, long long n, __half* __restrict__ y) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = __float2half_rn(x[i]);
@@ -474,6 +506,18 @@ extern "C" int tpz_affine(const float* x, long long n, const float* stats, int i
   int grid = tpz_div_up(n, 256 * 4);
   if (grid > 148 * 16) grid = 148 * 16;
   affine_kernel<<<grid, 256, 0, ST(stream)>>>(x, n, stats, inverse, y);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tpz_filter_f32(const float* x, int N, int D, int H, int W, const float* f, int kd, int kh, int kw, float bias,
+                              float* y, void* stream) {
+  TPZ_CHECK(kd % 2 == 1 && kh % 2 == 1 && kw % 2 == 1, "tpz_filter_f32: filter sizes must be odd");
+  const size_t smem = (size_t)kd * kh * kw * sizeof(float);
+  TPZ_CHECK(smem <= 200 * 1024, "tpz_filter_f32: filter too large");
+  TPZ_CUDA(cudaFuncSetAttribute(filter_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t total = (size_t)N * D * H * W;
+  filter_f32_kernel<<<tpz_div_up(total, 256), 256, smem, ST(stream)>>>(x, N, D, H, W, f, kd, kh, kw, bias, y);
   TPZ_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,32 +1,23 @@
-"""Drop-in mirror of topaz/model/classifier.py:14-66 (LinearClassifier = features + 1x1 conv to one logit)."""
-from __future__ import division, print_function
-
-import torch
+"""Drop-in for ``topaz.model.classifier.LinearClassifier`` (reference classifier.py:14-66): a feature extractor followed
+by a 1x1 convolution to one logit per position.  ``self.classifier`` only stores the (weight, bias) under the reference's
+state_dict keys; in the dense forward the 1x1 conv is fused into the epilogue of the last feature convolution."""
 import torch.nn as nn
 
 
 class LinearClassifier(nn.Module):
-    '''A simple convolutional layer without non-linear activation.'''
-
     def __init__(self, features, dims=2, patch_size: int = None, padding: int = None, batch_size: int = 1):
         super().__init__()
+        head = nn.Conv3d if dims == 3 else nn.Conv2d
         self.features = features
         self.dims = dims
-        conv = nn.Conv3d if dims == 3 else nn.Conv2d
-        self.classifier = conv(features.latent_dim, 1, 1)   # parameter container
-        self.patch_size = patch_size
-        self.padding = padding
-        self.batch_size = batch_size
+        self.classifier = head(features.latent_dim, 1, 1)
+        self.patch_size, self.padding, self.batch_size = patch_size, padding, batch_size
 
-    @property
-    def width(self):
-        return self.features.width
-
-    @property
-    def latent_dim(self):
-        return self.features.latent_dim
+    width = property(lambda self: self.features.width)
+    latent_dim = property(lambda self: self.features.latent_dim)
 
     def fill(self, stride=1):
+        """Switch to dense evaluation; returns the cumulative stride of the extractor (4 for ResNet8, 8 for conv63)."""
         return self.features.fill(stride=stride)
 
     def unfill(self):

@@ -1,75 +1,73 @@
-"""Drop-in mirror of topaz/model/features/basic.py:12-111 (conv31/63/127 stacks: conv -> BN -> PReLU,
-stride 2 per layer, fill() turns stride into dilation).  Children are parameter containers; forward runs
-the sm_100a kernels via topaz_b200.engine."""
-from __future__ import print_function, division
-from typing import List
+"""conv31 / conv63 / conv127 feature extractors: drop-in for ``topaz.model.features.basic.BasicConv`` (reference
+basic.py:12-111).  A stack of valid convolutions (first kernels stride 2, last stride 1), each followed by optional
+BatchNorm and an activation (PReLU with one slope by default).  ``fill()`` turns the strides into dilations so the
+patch classifier can be evaluated densely; ``unfill()`` restores the training geometry.
 
-import torch
+The torch.nn children only carry parameters / buffers under the reference's state_dict keys (``features.<i>.*``);
+arithmetic runs in the sm_100a kernels through ``topaz_b200.engine``.
+"""
+from typing import List, Sequence
+
 import torch.nn as nn
 
 from topaz_b200.model.utils import insize_from_outsize
 
+_CONV = {2: nn.Conv2d, 3: nn.Conv3d}
+_NORM = {2: nn.BatchNorm2d, 3: nn.BatchNorm3d}
+
 
 class BasicConv(nn.Module):
-    def __init__(self, layers: List[int], units: int, unit_scaling: int = 1, dropout: float = 0,
-                 bn: bool = True, pooling=None, activation=nn.PReLU, dims: int = 2):
+    def __init__(self, layers: List[int], units: int, unit_scaling: int = 1, dropout: float = 0, bn: bool = True,
+                 pooling=None, activation=nn.PReLU, dims: int = 2):
         super().__init__()
-        if dims not in (2, 3):
+        if dims not in _CONV:
             raise ValueError(f'Unsupported number of dimensions: {dims}. Try dims=2 or dims=3.')
         if pooling is not None:
             raise NotImplementedError('topaz_b200: pooled conv31/63/127 extractors are outside the B200 hot path')
-        conv = nn.Conv2d if dims == 2 else nn.Conv3d
-        batch_norm = nn.BatchNorm2d if dims == 2 else nn.BatchNorm3d
-        use_bias = (not bn)
-        stride = 2
-        sizes = layers
-        layers, strides = [], []
-        nin = 1
-        for size in sizes[:-1]:
-            layers += [conv(nin, units, size, stride=stride, bias=use_bias)]
-            strides += [stride]
+        kernel_sizes: Sequence[int] = list(layers)
+        mods, per_module_stride = [], []
+        width_in, width_out = 1, units
+        for pos, ksize in enumerate(kernel_sizes):
+            final = pos == len(kernel_sizes) - 1
+            step = 1 if final else 2
+            block = [(_CONV[dims](width_in, width_out, ksize, stride=step, bias=not bn), step)]
             if bn:
-                layers += [batch_norm(units)]
-                strides += [1]
-            layers += [activation()]
-            strides += [1]
+                block.append((_NORM[dims](width_out), 1))
+            block.append((activation(), 1))
             if dropout > 0:
-                layers += [nn.Dropout(p=dropout)]
-            nin = units
-            units *= unit_scaling
-        layers += [conv(nin, units, sizes[-1], bias=use_bias)]
-        strides += [1]
-        if bn:
-            layers += [batch_norm(units)]
-            strides += [1]
-        layers += [activation()]
-        if dropout > 0:
-            layers += [nn.Dropout(p=dropout)]
-        strides += [1]
-        self.strides = strides
-        self.width = insize_from_outsize(layers, 1)
+                block.append((nn.Dropout(p=dropout), None))      # dropout carries no entry in the stride table
+            for mod, st in block:
+                mods.append(mod)
+                if st is not None:
+                    per_module_stride.append(st)
+            width_in = width_out
+            if not final:
+                width_out *= unit_scaling
+        self.strides = per_module_stride
+        self.width = insize_from_outsize(mods, 1)
         self.filled = False
-        self.features = nn.Sequential(*layers)
-        self.latent_dim = units
+        self.features = nn.Sequential(*mods)
+        self.latent_dim = width_in
         self.dims = dims
 
-    def fill(self, stride: int = 1):
-        for mod, mod_stride in zip(self.features.children(), self.strides):
+    def _retarget(self, dense: bool, start: int = 1) -> int:
+        """Walk the stack with its stride table: dense=True -> stride 1 / dilation = cumulative stride."""
+        cumulative = start
+        live = [m for m in self.features.children() if not isinstance(m, nn.Dropout)]   # dropout has no stride entry
+        for mod, st in zip(live, self.strides):
             if hasattr(mod, 'dilation'):
-                mod.dilation = tuple(stride for _ in range(self.dims))
+                mod.dilation = (cumulative if dense else 1,) * self.dims
             if hasattr(mod, 'stride'):
-                mod.stride = tuple(1 for _ in range(self.dims))
-            stride *= mod_stride
-        self.filled = True
-        return stride
+                mod.stride = (1 if dense else st,) * self.dims
+            cumulative *= st
+        self.filled = dense
+        return cumulative
 
-    def unfill(self):
-        for mod, mod_stride in zip(self.features.children(), self.strides):
-            if hasattr(mod, 'dilation'):
-                mod.dilation = tuple(1 for _ in range(self.dims))
-            if hasattr(mod, 'stride'):
-                mod.stride = tuple(mod_stride for _ in range(self.dims))
-        self.filled = False
+    def fill(self, stride: int = 1) -> int:
+        return self._retarget(True, stride)
+
+    def unfill(self) -> None:
+        self._retarget(False)
 
     def forward(self, x):
         from topaz_b200 import engine

@@ -31,84 +31,93 @@ class MaxPool(nn.Module):
         raise NotImplementedError('topaz_b200: pooling="max" feature extractors are outside the B200 hot path')
 
 
+def _nd(value, dims):
+    return (value,) * dims
+
+
+_CONVS = {2: nn.Conv2d, 3: nn.Conv3d}
+_NORMS = {2: nn.BatchNorm2d, 3: nn.BatchNorm3d}
+
+
+def _check_dims(dims):
+    if dims not in _CONVS:
+        raise ValueError(f'Unsupported number of dimensions: {dims}. Try dims=2 or dims=3.')
+
+
 class BasicConv(nn.Module):
+    """conv (+BN) + activation block of the ResNets (reference resnet.py:50-105).  Attributes mirror the reference:
+    kernel_size, stride (training stride), dilation (current), og_dilation, padding, dims; children conv / bn / act."""
+
     def __init__(self, nin, nout, kernel_size, dilation=1, stride=1, bn=False, activation=nn.ReLU, dims=2):
         super().__init__()
-        if dims not in (2, 3):
-            raise ValueError(f'Unsupported number of dimensions: {dims}. Try dims=2 or dims=3.')
-        conv = nn.Conv2d if dims == 2 else nn.Conv3d
-        batch_norm = nn.BatchNorm2d if dims == 2 else nn.BatchNorm3d
-        self.conv = conv(nin, nout, kernel_size, dilation=dilation, stride=stride, bias=(not bn))
+        _check_dims(dims)
+        self.conv = _CONVS[dims](nin, nout, kernel_size, dilation=dilation, stride=stride, bias=not bn)
         if bn:
-            self.bn = batch_norm(nout)
+            self.bn = _NORMS[dims](nout)
         self.act = activation(inplace=True)
-        self.kernel_size = kernel_size
-        self.stride = stride
-        self.dilation = dilation
-        self.og_dilation = dilation
+        self.kernel_size, self.stride, self.dims = kernel_size, stride, dims
+        self.dilation = self.og_dilation = dilation
         self.padding = 0
-        self.dims = dims
 
     def set_padding(self, pad):
-        p = self.dilation * (self.kernel_size // 2) if pad else 0
-        self.conv.padding = tuple(p for _ in range(self.dims))
-        self.padding = p
+        self.padding = self.dilation * (self.kernel_size // 2) if pad else 0
+        self.conv.padding = _nd(self.padding, self.dims)
 
     def fill(self, stride):
-        self.conv.dilation = tuple(self.og_dilation * stride for _ in range(self.dims))
-        self.conv.stride = tuple(1 for _ in range(self.dims))
-        self.conv.padding = tuple(pad * stride for pad in self.conv.padding)
-        self.dilation *= stride
-        return self.stride
-
-    def unfill(self):
-        stride = self.dilation // self.og_dilation
-        self.conv.dilation = tuple(self.og_dilation for _ in range(self.dims))
-        self.conv.stride = tuple(self.stride for _ in range(self.dims))
-        self.conv.padding = tuple(pad // stride for pad in self.conv.padding)
-        self.dilation = self.og_dilation
-
-
-class ResidA(nn.Module):
-    def __init__(self, nin, nhidden, nout, dilation=1, stride=1, activation=nn.ReLU, bn=False, dims=2):
-        super().__init__()
-        if dims not in (2, 3):
-            raise ValueError(f'Unsupported number of dimensions: {dims}. Try dims=2 or dims=3.')
-        self.dims = dims
-        conv = nn.Conv2d if dims == 2 else nn.Conv3d
-        batch_norm = nn.BatchNorm2d if dims == 2 else nn.BatchNorm3d
-        self.bn = bn
-        bias = (not bn)
-        if nin != nout:
-            self.proj = conv(nin, nout, 1, stride=stride, bias=False)
-        self.conv0 = conv(nin, nhidden, 3, bias=bias)
-        if self.bn:
-            self.bn0 = batch_norm(nhidden)
-        self.act0 = activation(inplace=True)
-        self.conv1 = conv(nhidden, nout, 3, dilation=dilation, stride=stride, bias=bias)
-        if self.bn:
-            self.bn1 = batch_norm(nout)
-        self.act1 = activation(inplace=True)
-        self.kernel_size = 2 * dilation + 3
-        self.stride = stride
-        self.dilation = 1
-        self.padding = 0
-
-    def fill(self, stride):
-        self.conv0.dilation = tuple(stride for _ in range(self.dims))
-        self.conv1.dilation = tuple(dil * stride for dil in self.conv1.dilation)
-        self.conv1.stride = tuple(1 for _ in range(self.dims))
-        if hasattr(self, 'proj'):
-            self.proj.stride = tuple(1 for _ in range(self.dims))
+        """Dense mode: this conv runs at stride 1 with its dilation multiplied by the cumulative stride so far."""
+        c = self.conv
+        c.dilation, c.stride = _nd(self.og_dilation * stride, self.dims), _nd(1, self.dims)
+        c.padding = tuple(p * stride for p in c.padding)
         self.dilation = self.dilation * stride
         return self.stride
 
     def unfill(self):
-        self.conv0.dilation = tuple(1 for _ in range(self.dims))
-        self.conv1.dilation = tuple(dil // self.dilation for dil in self.conv1.dilation)
-        self.conv1.stride = tuple(self.stride for _ in range(self.dims))
-        if hasattr(self, 'proj'):
-            self.proj.stride = tuple(self.stride for _ in range(self.dims))
+        c = self.conv
+        factor = self.dilation // self.og_dilation
+        c.dilation, c.stride = _nd(self.og_dilation, self.dims), _nd(self.stride, self.dims)
+        c.padding = tuple(p // factor for p in c.padding)
+        self.dilation = self.og_dilation
+
+
+class ResidA(nn.Module):
+    """Residual block (reference resnet.py:108-204): conv0 3x3 -> act -> conv1 3x3 (dilated, optionally strided);
+    the block input, centre-cropped by conv0.dilation + conv1.dilation, is added (through a bias-free 1x1 ``proj``
+    when the channel count changes) before the optional BN and the final activation."""
+
+    def __init__(self, nin, nhidden, nout, dilation=1, stride=1, activation=nn.ReLU, bn=False, dims=2):
+        super().__init__()
+        _check_dims(dims)
+        conv, norm = _CONVS[dims], _NORMS[dims]
+        self.dims, self.bn = dims, bn
+        if nin != nout:
+            self.proj = conv(nin, nout, 1, stride=stride, bias=False)
+        self.conv0 = conv(nin, nhidden, 3, bias=not bn)
+        if bn:
+            self.bn0 = norm(nhidden)
+        self.act0 = activation(inplace=True)
+        self.conv1 = conv(nhidden, nout, 3, dilation=dilation, stride=stride, bias=not bn)
+        if bn:
+            self.bn1 = norm(nout)
+        self.act1 = activation(inplace=True)
+        self.kernel_size = 3 + 2 * dilation       # receptive field of the block at stride 1
+        self.stride, self.dilation, self.padding = stride, 1, 0
+
+    def _skip_convs(self):
+        return [self.proj] if hasattr(self, 'proj') else []
+
+    def fill(self, stride):
+        self.conv0.dilation = _nd(stride, self.dims)
+        self.conv1.dilation = tuple(d * stride for d in self.conv1.dilation)
+        for c in [self.conv1] + self._skip_convs():
+            c.stride = _nd(1, self.dims)
+        self.dilation *= stride
+        return self.stride
+
+    def unfill(self):
+        self.conv0.dilation = _nd(1, self.dims)
+        self.conv1.dilation = tuple(d // self.dilation for d in self.conv1.dilation)
+        for c in [self.conv1] + self._skip_convs():
+            c.stride = _nd(self.stride, self.dims)
         self.dilation = 1
 
 

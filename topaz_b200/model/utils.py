@@ -46,67 +46,57 @@ def load_pretrained_state(kind: str, name: str):
     return torch.load(pretrained_path(kind, name), map_location='cpu', weights_only=False)
 
 
+def _patch_origins(shape, step, is_3d):
+    """Origins of the patches in the reference's iteration order: y outer, x middle, z inner (utils.py:146-166, 180-191)."""
+    import itertools
+    y, x = shape[-2:]
+    ranges = [range(0, y, step), range(0, x, step)]
+    if is_3d:
+        ranges.append(range(0, shape[-3], step))
+    return itertools.product(*ranges)
+
+
 def get_patches(X, patch_size, patch_padding=0, is_3d=False):
-    """utils.py:133-168 (including the all-zero-patch skip)."""
-    y, x = X.shape[-2:]
-    z = X.shape[-3] if is_3d else None
-    pad = (patch_padding, patch_padding) * (3 if is_3d else 2)
-    X = torch.nn.functional.pad(X, pad)
-    y_pad, x_pad = X.shape[-2:]
-    z_pad = X.shape[-3] if is_3d else None
-    step_size = patch_size - 2 * patch_padding
-    patches = []
-    for i in range(0, y, step_size):
-        for j in range(0, x, step_size):
-            i_end = min(i + patch_size, y_pad)
-            j_end = min(j + patch_size, x_pad)
-            if is_3d:
-                for k in range(0, z, step_size):
-                    k_end = min(k + patch_size, z_pad)
-                    patch = X[..., k:k_end, i:i_end, j:j_end]
-                    if patch.abs().sum() == 0:
-                        continue
-                    patches.append(patch)
-            else:
-                patch = X[..., i:i_end, j:j_end]
-                if patch.abs().sum() == 0:
-                    continue
-                patches.append(patch)
-    return patches
+    """Split a padded image/volume into overlapping patches (reference utils.py:133-168): the input is zero-padded by
+    ``patch_padding`` on every side, patches of ``patch_size`` start every ``patch_size - 2*patch_padding`` pixels and are
+    clipped at the padded border; all-zero patches are dropped (as the reference does)."""
+    ndim_sp = 3 if is_3d else 2
+    Xp = torch.nn.functional.pad(X, (patch_padding, patch_padding) * ndim_sp)
+    step = patch_size - 2 * patch_padding
+    out = []
+    for org in _patch_origins(X.shape, step, is_3d):
+        i, j = org[0], org[1]
+        window = (slice(i, min(i + patch_size, Xp.shape[-2])), slice(j, min(j + patch_size, Xp.shape[-1])))
+        if is_3d:
+            k = org[2]
+            window = (slice(k, min(k + patch_size, Xp.shape[-3])),) + window
+        patch = Xp[(Ellipsis,) + window]
+        if patch.abs().sum() == 0:
+            continue
+        out.append(patch)
+    return out
 
 
 def reconstruct_from_patches(patches, original_shape, patch_size, patch_padding=0, is_3d=False):
-    """utils.py:172-193 (float64 result)."""
-    y, x = original_shape[-2:]
-    z = original_shape[-3] if is_3d else None
-    step_size = patch_size - patch_padding * 2
-    reassembled = np.zeros(original_shape)
-    patch_idx = 0
-    for i in range(0, y, step_size):
-        for j in range(0, x, step_size):
-            if is_3d:
-                for k in range(0, z, step_size):
-                    patch = patches[patch_idx]
-                    reassembled[..., k:k + patch.shape[-3], i:i + patch.shape[-2], j:j + patch.shape[-1]] = patch
-                    patch_idx += 1
-            else:
-                patch = patches[patch_idx]
-                reassembled[..., i:i + patch.shape[-2], j:j + patch.shape[-1]] = patch
-                patch_idx += 1
-    return reassembled
+    """Paste the halo-cropped patch scores back (reference utils.py:172-193); the result is float64 like the reference."""
+    step = patch_size - 2 * patch_padding
+    canvas = np.zeros(original_shape)
+    for patch, org in zip(patches, _patch_origins(original_shape, step, is_3d)):
+        i, j = org[0], org[1]
+        window = (slice(i, i + patch.shape[-2]), slice(j, j + patch.shape[-1]))
+        if is_3d:
+            window = (slice(org[2], org[2] + patch.shape[-3]),) + window
+        canvas[(Ellipsis,) + window] = patch
+    return canvas
 
 
 def predict_in_patches(model, X, patch_size, is_3d=False, use_cuda=False):
-    '''utils.py:110-130: predict on an image in patches (halo = receptive field // 2) and reassemble.'''
-    patch_padding = model.width // 2
-    patches = get_patches(X, patch_size, patch_padding=patch_padding, is_3d=is_3d)
+    """Score an image patch-wise with a halo of half the receptive field and stitch (reference utils.py:110-130)."""
+    halo = model.width // 2
+    crop = (Ellipsis,) + ((slice(halo, -halo),) * 3 if is_3d else (slice(halo, -halo),) * 2)
     scores = []
-    for patch in patches:
-        with torch.no_grad():
-            patch = patch.cuda() if use_cuda else patch
-            score = model(patch).data[0, 0].cpu().numpy()
-            score = score[..., patch_padding:-patch_padding, patch_padding:-patch_padding]
-            if is_3d:
-                score = score[..., patch_padding:-patch_padding, :, :]
-        scores.append(score)
-    return reconstruct_from_patches(scores, X.shape, patch_size, patch_padding=patch_padding, is_3d=is_3d)
+    with torch.no_grad():
+        for patch in get_patches(X, patch_size, patch_padding=halo, is_3d=is_3d):
+            dev = patch.cuda() if use_cuda else patch
+            scores.append(model(dev).data[0, 0].cpu().numpy()[crop])
+    return reconstruct_from_patches(scores, X.shape, patch_size, patch_padding=halo, is_3d=is_3d)

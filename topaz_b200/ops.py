@@ -293,6 +293,15 @@ def affine(x: torch.Tensor, stats: torch.Tensor, inverse: bool = False, out: Opt
     return y
 
 
+def filter_f32(x: torch.Tensor, f: torch.Tensor, bias: float = 0.0) -> torch.Tensor:
+    """Same-padded 1->1 fp32 convolution of x [N,D,H,W] with filter f [kd,kh,kw] (both on device)."""
+    N, D, H, W = x.shape
+    kd, kh, kw = f.shape
+    y = torch.empty_like(x)
+    _count(1); check(_lib.lib().tpz_filter_f32(_ptr(x), N, D, H, W, _ptr(f), kd, kh, kw, float(bias), _ptr(y), _stream()))
+    return y
+
+
 def lab_umma(A: torch.Tensor, B: torch.Tensor, shift: int, sbo_rows: int, base_off_mode: int, kc: int = 64) -> torch.Tensor:
     D = torch.zeros((128, B.shape[0]), dtype=torch.float32, device=A.device)
     check(_lib.lib().tpz_lab_umma(_ptr(A), A.shape[0], _ptr(B), B.shape[0], shift, sbo_rows, base_off_mode, kc,
