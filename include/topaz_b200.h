@@ -44,6 +44,7 @@ typedef struct {
                           lat != lattice the source has a different resolution than the output: lat = 1 under an output
                           lattice of 2 reads a half-resolution tensor, i.e. a fused nearest-neighbour 2x up-sampling      */
   int no_phase;        /* 1: the output phase offset is NOT added to this source's coordinates (half-resolution source) */
+  int lat_z;           /* lattice spacing of this source along z (0 = lattice_z); z taps are separate plane loads          */
 } TpzTcSrc;
 
 typedef struct {
@@ -57,6 +58,8 @@ typedef struct {
   int TW, TH;              /* pixel tile of the per-tap kernel, TW*TH == 128, TW % 8 == 0 */
   int lattice;             /* in-plane dilation shared by all taps (halo-resident kernel); 0 = per-tap kernel only */
   int phase_sel;           /* 0: all lattice*lattice output phases; k>0: only phase k-1 (py*lattice+px) is computed    */
+  int lattice_z, phase_z;  /* output z lattice (0/1 = every plane) and the z phase computed by this launch: output plane
+                              index = zq*lattice_z + phase_z, source plane = zq*lat_z + org_z + dz (+phase_z unless no_phase) */
   const float* bias;       /* [Co] or NULL */
   float neg_slope;         /* activation: v>0 ? v : v*neg_slope (0 = ReLU, 1 = linear, 0.1 = LeakyReLU) */
   const tpz_half* res;     /* optional residual, added before the activation */

@@ -25,13 +25,13 @@ def _gather(src, org, d, out_shape, c0, kc):
     return out
 
 
-def _gather_lattice(src, org, d, qshape, c0, kc, lat, ph):
+def _gather_lattice(src, org, d, qshape, c0, kc, lat, ph, latz=1, phz=0):
     """A operand of one k-block on an output lattice: lattice point (qy,qx) reads source pixel q*lat + ph + org + d."""
     N, Do, QH, QW = qshape
     _, D, H, W, _ = src.shape
     ys = torch.arange(QH) * lat + ph[1] + org[1] + d[1]
     xs = torch.arange(QW) * lat + ph[0] + org[0] + d[0]
-    zs = torch.arange(Do) + org[2] + d[2]
+    zs = torch.arange(Do) * latz + phz + org[2] + d[2]
     out = torch.zeros((N, Do, QH, QW, kc), dtype=torch.float32)
     vz, vy, vx = (zs >= 0) & (zs < D), (ys >= 0) & (ys < H), (xs >= 0) & (xs < W)
     if vz.any() and vy.any() and vx.any():
@@ -43,7 +43,7 @@ def _gather_lattice(src, org, d, qshape, c0, kc, lat, ph):
 
 def tc_conv(plan, srcs, out_shape, out=None, res=None, res_org=(0, 0, 0), dot_out=None, out_coff=0, tag=None, dot_affine=None):
     N, Do, Ho, Wo = out_shape
-    mixed = plan.phase_sel != 0 or any(l not in (0, plan.lattice) for l in (plan.lats or [])) or any(not p for p in (plan.phases or []))
+    mixed = plan.lattice_z > 1 or plan.phase_sel != 0 or any(l not in (0, plan.lattice) for l in (plan.lats or [])) or any(not p for p in (plan.phases or []))
     if not mixed:
         return _tc_conv_dense(plan, srcs, out_shape, out, res, res_org, dot_out, out_coff, dot_affine)
     L = plan.lattice
@@ -52,16 +52,19 @@ def tc_conv(plan, srcs, out_shape, out=None, res=None, res_org=(0, 0, 0), dot_ou
     for ph in phases:
         phy, phx = ph // L, ph % L
         QH, QW = (Ho - phy + L - 1) // L, (Wo - phx + L - 1) // L
-        acc = torch.zeros((N, Do, QH, QW, plan.Co), dtype=torch.float32)
+        Lz, pz = plan.lattice_z, plan.phase_z
+        QD = (Do - pz + Lz - 1) // Lz
+        acc = torch.zeros((N, QD, QH, QW, plan.Co), dtype=torch.float32)
         for kb, (dx, dy, dz, c0, si) in enumerate(plan.kblocks):
             lat = plan.lats[si] or L
             p_on = plan.phases[si]
-            A = _gather_lattice(srcs[si], plan.orgs[si], (dx, dy, dz), (N, Do, QH, QW), c0, plan.KC, lat,
-                                (phx if p_on else 0, phy if p_on else 0))
+            latz = (plan.lat_zs[si] if plan.lat_zs else 0) or Lz
+            A = _gather_lattice(srcs[si], plan.orgs[si], (dx, dy, dz), (N, QD, QH, QW), c0, plan.KC, lat,
+                                (phx if p_on else 0, phy if p_on else 0), latz, pz if p_on else 0)
             acc += A @ plan.weights[kb].float().t()
         v = acc + plan.bias
         v = torch.where(v > 0, v, v * plan.neg_slope)
-        out[:, :, phy::L, phx::L, out_coff:out_coff + plan.Co] = v.half()
+        out[:, pz::Lz, phy::L, phx::L, out_coff:out_coff + plan.Co] = v.half()
 
 
 def _tc_conv_dense(plan, srcs, out_shape, out, res, res_org, dot_out, out_coff, dot_affine):

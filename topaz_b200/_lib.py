@@ -17,7 +17,7 @@ class TcKBlock(C.Structure):
 
 class TpzTcSrc(C.Structure):
     _fields_ = [('ptr', C.c_void_p), ('N', C.c_int), ('D', C.c_int), ('H', C.c_int), ('W', C.c_int),
-                ('C', C.c_int), ('ld', C.c_int), ('org', C.c_int * 3), ('kw', C.c_int), ('kh', C.c_int), ('lat', C.c_int), ('no_phase', C.c_int)]
+                ('C', C.c_int), ('ld', C.c_int), ('org', C.c_int * 3), ('kw', C.c_int), ('kh', C.c_int), ('lat', C.c_int), ('no_phase', C.c_int), ('lat_z', C.c_int)]
 
 
 class TpzTcConvArgs(C.Structure):
@@ -25,7 +25,7 @@ class TpzTcConvArgs(C.Structure):
         ('nsrc', C.c_int), ('src', TpzTcSrc * 2), ('weights', C.c_void_p), ('KC', C.c_int), ('nkb', C.c_int),
         ('kb', TcKBlock * TPZ_TC_MAX_KB),
         ('N', C.c_int), ('Do', C.c_int), ('Ho', C.c_int), ('Wo', C.c_int), ('Co', C.c_int),
-        ('TW', C.c_int), ('TH', C.c_int), ('lattice', C.c_int), ('phase_sel', C.c_int),
+        ('TW', C.c_int), ('TH', C.c_int), ('lattice', C.c_int), ('phase_sel', C.c_int), ('lattice_z', C.c_int), ('phase_z', C.c_int),
         ('bias', C.c_void_p), ('neg_slope', C.c_float),
         ('res', C.c_void_p), ('res_scale', C.c_void_p),
         ('res_ld', C.c_int), ('res_D', C.c_int), ('res_H', C.c_int), ('res_W', C.c_int), ('res_org', C.c_int * 3),

@@ -270,7 +270,7 @@ extern "C" int tpz_tc_conv_v1(const TpzTcConvArgs* a, void* stream_) {
     TPZ_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
 
-  TPZ_CHECK(a->phase_sel == 0, "tpz_tc_conv_v1: phase selection needs the halo-resident kernel");
+  TPZ_CHECK(a->phase_sel == 0 && a->lattice_z <= 1, "tpz_tc_conv_v1: phase selection needs the halo-resident kernel");
   for (int s = 0; s < a->nsrc; ++s)
     TPZ_CHECK((a->src[s].lat == 0 || a->src[s].lat == a->lattice || a->lattice == 0) && !a->src[s].no_phase,
               "tpz_tc_conv_v1: mixed-resolution sources need the halo-resident kernel");

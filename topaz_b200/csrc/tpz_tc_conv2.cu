@@ -39,6 +39,7 @@ struct Tc2Params {
   int org[2][3];
   int hx[2], rows_loaded[2], split_rows[2];
   int slat[2], sphase[2];   // per-source lattice spacing / whether the output phase shifts the source
+  int slatz[2], Lz, phz, Dq; // z lattice: output plane = zq*Lz + phz (zq < Dq), source plane = zq*slatz + org_z + dz
   int L, phase_fixed;
   int N, Do, Ho, Wo, Co, CS;
   int tiles_x, tiles_y, num_tiles;
@@ -89,8 +90,8 @@ __device__ __forceinline__ TileCoord decode_tile(const Tc2Params& p, int tile) {
   const int tyq = rest % p.tiles_y;
   const int plane = rest / p.tiles_y;
   TileCoord t;
-  t.n = plane / p.Do;
-  t.z = plane - t.n * p.Do;
+  t.n = plane / p.Dq;
+  t.z = plane - t.n * p.Dq;      // z lattice index
   t.qx = txq * T2W;
   t.qy = tyq * (16 * p.ntile);
   t.phx = ph % p.L;
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv2_kernel(const __grid_cons
               ptx::tma_load_5d(dst + (size_t)row0 * hx * ROWB, &p.tmA[src], &afull[s], G.c0,
                                tc.qx * p.slat[src] + p.sphase[src] * tc.phx + p.org[src][0] + G.gox,
                                (tc.qy + row0) * p.slat[src] + p.sphase[src] * tc.phy + p.org[src][1] + G.goy,
-                               tc.z + p.org[src][2] + G.dz, tc.n);
+                               tc.z * p.slatz[src] + p.sphase[src] * p.phz + p.org[src][2] + G.dz, tc.n);
             }
           }
           __syncwarp();
@@ -281,12 +282,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv2_kernel(const __grid_cons
         const int gy = (tc.qy + lj + 16 * a) * p.L + tc.phy;
         const bool valid = (gx < p.Wo) && (gy < p.Ho);
         const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (st * p.ntile + a) * p.CS;
-        const long long opix = (((long long)tc.n * p.Do + tc.z) * p.Ho + gy) * p.Wo + gx;
+        const int gz = tc.z * p.Lz + p.phz;
+        const long long opix = (((long long)tc.n * p.Do + gz) * p.Ho + gy) * p.Wo + gx;
         __half* orow = p.out ? p.out + opix * p.out_ld + p.out_coff : nullptr;
         const __half* rrow = nullptr;
         if (p.res) {
           const long long rpix =
-              (((long long)tc.n * p.res_D + (tc.z + p.res_org[2])) * p.res_H + (gy + p.res_org[1])) * p.res_W +
+              (((long long)tc.n * p.res_D + (gz + p.res_org[2])) * p.res_H + (gy + p.res_org[1])) * p.res_W +
               (gx + p.res_org[0]);
           rrow = p.res + rpix * p.res_ld;
         }
@@ -483,7 +485,13 @@ static int launch_v2(const TpzTcConvArgs* a, cudaStream_t stream, bool dry) {
   p.tiles_y = tpz_div_up(qH, th);
   p.phase_fixed = a->phase_sel > 0 ? a->phase_sel - 1 : -1;
   TPZ_CHECK(a->phase_sel >= 0 && a->phase_sel <= L * L, "tpz_tc_conv: phase_sel=%d out of range for lattice %d", a->phase_sel, L);
-  const long long ntl = (long long)(p.phase_fixed >= 0 ? 1 : L * L) * p.tiles_x * p.tiles_y * a->Do * a->N;
+  p.Lz = a->lattice_z > 1 ? a->lattice_z : 1;
+  p.phz = a->phase_z;
+  TPZ_CHECK(p.phz >= 0 && p.phz < p.Lz, "tpz_tc_conv: phase_z=%d out of range for lattice_z=%d", p.phz, p.Lz);
+  p.Dq = (a->Do - p.phz + p.Lz - 1) / p.Lz;
+  for (int s = 0; s < a->nsrc; ++s) p.slatz[s] = a->src[s].lat_z > 0 ? a->src[s].lat_z : p.Lz;
+  if (p.Dq <= 0) return 0;
+  const long long ntl = (long long)(p.phase_fixed >= 0 ? 1 : L * L) * p.tiles_x * p.tiles_y * p.Dq * a->N;
   TPZ_CHECK(ntl > 0 && ntl < (1ll << 31), "tpz_tc_conv: bad tile count %lld", ntl);
   p.num_tiles = (int)ntl;
   p.bias = a->bias; p.neg_slope = a->neg_slope;

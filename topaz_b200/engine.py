@@ -280,24 +280,31 @@ def _conv_of(seq, idx):
     return c
 
 
-def _up2_phase_plans(w_up, up_c, k, second_part, bias, co_store, slope, device):
-    """Plans for conv(cat[nearest_up2(h), other]) computed per output phase (py, px) directly from the half-resolution
-    tensor h: taps of the k x k kernel that alias onto the same half-res pixel are summed (5x5 -> 3x3, 3x3 -> 2x2 per
-    phase).  ``second_part(py, px)`` returns the ConvPart of the full-resolution source for that phase."""
+def _up2_phase_plans(w_up, up_c, k, second_part, bias, co_store, slope, device, dims=2):
+    """Plans for conv(cat[nearest_up2(h), other]) computed per output phase directly from the half-resolution tensor
+    h: taps of the k^dims kernel that alias onto the same half-res voxel are summed (5x5 -> 3x3, 3x3(x3) -> 2x2(x2) per
+    phase).  ``second_part(phase)`` returns the ConvPart of the full-resolution source for phase = (px, py, pz)."""
     pad = k // 2
     wu = w_up.detach().float().cpu()
+    if wu.dim() == 4:
+        wu = wu[:, :, None]
+    kz = wu.shape[2]
     plans = []
-    for py in range(2):
-        for px in range(2):
+    for pz in range(2 if dims == 3 else 1):
+        offz = [(pz + r - pad) // 2 for r in range(kz)] if dims == 3 else [0]
+        for py in range(2):
             offy = [(py + r - pad) // 2 for r in range(k)]
-            offx = [(px + r - pad) // 2 for r in range(k)]
-            ay0, ax0 = min(offy), min(offx)
-            wm = torch.zeros((wu.shape[0], up_c, max(offy) - ay0 + 1, max(offx) - ax0 + 1))
-            for r in range(k):
-                for t in range(k):
-                    wm[:, :, offy[r] - ay0, offx[t] - ax0] += wu[:, :, r, t]
-            parts = [ConvPart(wm, _rup(up_c), 1, (ax0, ay0, 0), lat=1, phase=False), second_part(py, px)]
-            plans.append(ops.pack_tc_conv(parts, bias, co_store, slope, device, lattice=2, phase_sel=py * 2 + px + 1))
+            for px in range(2):
+                offx = [(px + r - pad) // 2 for r in range(k)]
+                az0, ay0, ax0 = min(offz), min(offy), min(offx)
+                wm = torch.zeros((wu.shape[0], up_c, max(offz) - az0 + 1, max(offy) - ay0 + 1, max(offx) - ax0 + 1))
+                for q in range(kz):
+                    for r in range(k):
+                        for t in range(k):
+                            wm[:, :, offz[q] - az0, offy[r] - ay0, offx[t] - ax0] += wu[:, :, q, r, t]
+                parts = [ConvPart(wm, _rup(up_c), 1, (ax0, ay0, az0), lat=1, lat_z=1, phase=False), second_part((px, py, pz))]
+                plans.append(ops.pack_tc_conv(parts, bias, co_store, slope, device, lattice=2, phase_sel=py * 2 + px + 1,
+                                              lattice_z=2 if dims == 3 else 1, phase_z=pz))
     return plans
 
 
@@ -350,11 +357,13 @@ def _build_unet_plan(model, device):
             pb = ops.pack_tc_conv([ConvPart(cb.weight, _rup(ca.weight.shape[0]), 1, same_org(cb.weight.shape[-1]))],
                                   cb.bias, _rup(cb.weight.shape[0]), slope, device)
             up2 = None
-            if dims == 2 and UP2_FUSED:
+            if UP2_FUSED:
                 w_skip, pad_k = ca.weight[:, up_c:], k // 2
                 up2 = _up2_phase_plans(ca.weight[:, :up_c], up_c, k,
-                                       lambda py, px: ConvPart(w_skip, _rup(skip_c), 1, (px - pad_k, py - pad_k, 0), lat=2, phase=False),
-                                       ca.bias, _rup(ca.weight.shape[0]), slope, device)
+                                       lambda ph: ConvPart(w_skip, _rup(skip_c), 1,
+                                                           (ph[0] - pad_k, ph[1] - pad_k, ph[2] - pad_k if dims == 3 else 0),
+                                                           lat=2, lat_z=2 if dims == 3 else 0, phase=False),
+                                       ca.bias, _rup(ca.weight.shape[0]), slope, device, dims)
             plan['dec'][l] = dict(a=pa, b=pb, up2=up2)
             up_c = cb.weight.shape[0]
         else:
@@ -376,11 +385,12 @@ def _build_unet_plan(model, device):
             # tensor equals a conv over the HALF-resolution tensor with the taps that alias onto the same source pixel
             # summed (5x5 -> 3x3 per phase: 2.8x fewer MACs on the dominant layer, and no up-sampled tensor in HBM).
             up2 = None
-            if dims == 2 and UP2_FUSED:
+            if UP2_FUSED:
                 up2 = _up2_phase_plans(ca.weight[:, :up_c], up_c, k,
-                                       lambda py, px: ConvPart(wraw.reshape(wraw.shape[0], ntap, 1, 1, 1), _tap_ld(ntap), 1,
-                                                               (0, 0, 0), lat=2),
-                                       ca.bias, _rup(ca.weight.shape[0]), slope, device)
+                                       lambda ph: ConvPart(wraw.reshape(wraw.shape[0], ntap, 1, 1, 1), _tap_ld(ntap), 1,
+                                                           (ph[0], ph[1], ph[2] if dims == 3 else 0), lat=2,
+                                                           lat_z=2 if dims == 3 else 0, phase=False),
+                                       ca.bias, _rup(ca.weight.shape[0]), slope, device, dims)
             # dec1.4 (Cout = 1) on the tensor-core kernel: 16 output columns (1 real), the fused "dot" epilogue picks
             # column 0, adds the bias and de-normalises -> dense fp32 image; no 16-channel tensor is written
             onehot0 = torch.zeros(1, 1, 1, 1); onehot0[0, 0, 0, 0] = 1.0
@@ -433,7 +443,7 @@ def unet_forward(model, x: torch.Tensor, denorm_stats: Optional[torch.Tensor] = 
             skip = skips[l - 2]
             N, D, H, W, _ = skip.shape
             o = torch.empty((N, D, H, W, d['a'].Co), dtype=torch.float16, device=x.device)
-            if d.get('up2') is not None and H == 2 * h.shape[2] and W == 2 * h.shape[3]:
+            if d.get('up2') is not None and H == 2 * h.shape[2] and W == 2 * h.shape[3] and (dims == 2 or D == 2 * h.shape[1]):
                 for pl2 in d['up2']:                      # fused nearest-2x up-sampling, one launch per output phase
                     ops.tc_conv(pl2, [h, skip], (N, D, H, W), out=o)
             else:
@@ -449,7 +459,7 @@ def unet_forward(model, x: torch.Tensor, denorm_stats: Optional[torch.Tensor] = 
             else:
                 raw = ops.conv_first(xi, d['onehot'], None, 1, d['k'] // 2, 1.0, d['ntap_store'])
             o = torch.empty((N, D, H, W, d['a'].Co), dtype=torch.float16, device=x.device)
-            if d.get('up2') is not None and H == 2 * h.shape[2] and W == 2 * h.shape[3]:
+            if d.get('up2') is not None and H == 2 * h.shape[2] and W == 2 * h.shape[3] and (dims == 2 or D == 2 * h.shape[1]):
                 for pl2 in d['up2']:                      # one launch per output phase, reading the half-res tensor
                     ops.tc_conv(pl2, [h, raw], (N, D, H, W), out=o)
             else:

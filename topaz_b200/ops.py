@@ -38,6 +38,7 @@ class ConvPart:
     dil: int = 1
     org: Tuple[int, int, int] = (0, 0, 0)   # (x, y, z) offset of tap 0 relative to the output pixel
     lat: int = 0                 # lattice spacing of this source in its own pixels (0 = the plan's output lattice)
+    lat_z: int = 0               # same along z (0 = the plan's lattice_z)
     phase: bool = True           # False: the output phase does not shift this source (half-resolution source)
 
 
@@ -56,6 +57,9 @@ class TcConvPlan:
     lats: List[int] = field(default_factory=list)        # per-source lattice spacing (0 = lattice)
     phases: List[bool] = field(default_factory=list)     # per-source: output phase shifts the source
     phase_sel: int = 0                # 0 = all output phases, k = only phase k-1
+    lat_zs: List[int] = field(default_factory=list)
+    lattice_z: int = 1                # output z lattice and the z phase this plan computes
+    phase_z: int = 0
     dot_w: Optional[torch.Tensor] = None
     dot_b: float = 0.0
     res_scale: Optional[torch.Tensor] = None
@@ -65,7 +69,8 @@ class TcConvPlan:
 
 def pack_tc_conv(parts: Sequence[ConvPart], bias: Optional[torch.Tensor], co_store: int, neg_slope: float,
                  device, KC: Optional[int] = None, dot_w=None, dot_b: float = 0.0, res_scale=None,
-                 out_scale: Optional[torch.Tensor] = None, lattice: Optional[int] = None, phase_sel: int = 0) -> TcConvPlan:
+                 out_scale: Optional[torch.Tensor] = None, lattice: Optional[int] = None, phase_sel: int = 0,
+                 lattice_z: int = 1, phase_z: int = 0) -> TcConvPlan:
     """Repack OIHW fp32 weights into the kernel's [k-block][Co][KC] fp16 layout.
 
     k-blocks are ordered (source, tap, chunk); all-zero blocks (channel padding) are dropped.
@@ -119,6 +124,7 @@ def pack_tc_conv(parts: Sequence[ConvPart], bias: Optional[torch.Tensor], co_sto
     return TcConvPlan(KC=KC, Co=co_store, kblocks=kbs, orgs=[tuple(p.org) for p in parts],
                       c_stores=[p.c_store for p in parts], tapgrids=grids, lattice=lattice,
                       lats=[p.lat for p in parts], phases=[p.phase for p in parts], phase_sel=phase_sel,
+                      lat_zs=[p.lat_z for p in parts], lattice_z=lattice_z, phase_z=phase_z,
                       weights=wt, bias=b.to(device),
                       neg_slope=float(neg_slope), dot_w=dw, dot_b=float(dot_b), res_scale=rs)
 
@@ -139,6 +145,7 @@ def _static_tc_args(plan: TcConvPlan) -> TpzTcConvArgs:
         s.kw, s.kh = plan.tapgrids[i]
         s.lat = plan.lats[i] if plan.lats else 0
         s.no_phase = 0 if (not plan.phases or plan.phases[i]) else 1
+        s.lat_z = plan.lat_zs[i] if plan.lat_zs else 0
     a.weights = plan.weights.data_ptr()
     a.KC = plan.KC
     a.nkb = len(plan.kblocks)
@@ -149,6 +156,7 @@ def _static_tc_args(plan: TcConvPlan) -> TpzTcConvArgs:
     a.TW, a.TH = plan.TW, plan.TH
     a.lattice = plan.lattice
     a.phase_sel = plan.phase_sel
+    a.lattice_z, a.phase_z = plan.lattice_z, plan.phase_z
     a.bias = plan.bias.data_ptr()
     a.neg_slope = plan.neg_slope
     plan.__dict__['_args'] = a
