@@ -155,12 +155,14 @@ def denoise_image(mic: np.ndarray, models: List[Denoise], lowpass=1, cutoff=0, g
                   deconvolve=False, deconv_patch=1, patch_size=-1, padding=0, normalize=False, use_cuda=True) -> np.ndarray:
     ''' reference denoise.py:382-416 with the optional lowpass / gaussian / deconvolve pre-filters
     outside the hot path (off in every BASELINE config).'''
-    if lowpass > 1 or gaus is not None or inv_gaus is not None or deconvolve:
-        raise NotImplementedError('topaz_b200: lowpass/gaussian/deconvolve pre-filters are outside the B200 hot path')
+    if lowpass > 1 or inv_gaus is not None or deconvolve:
+        raise NotImplementedError('topaz_b200: lowpass / inverse-Gaussian / deconvolve pre-filters are outside the B200 hot path')
     mu, std = mic.mean(), mic.std()
     x = (mic - mu) / std
     if cutoff > 0:
         x[(x < -cutoff) | (x > cutoff)] = 0
+    if gaus is not None:            # topaz_b200.filters.GaussianDenoise (reference denoise.py:397-398)
+        x = gaus.apply(x)
     mic = sum([model.denoise(x, patch_size=patch_size, padding=padding) for model in models]) / len(models)
     if normalize:
         mic = (mic - mic.mean()) / mic.std()
