@@ -165,6 +165,12 @@ int tpz_lab_umma(const tpz_half* A, int rowsA, const tpz_half* B, int N, int shi
 int tpz_lab_umma_rate(int N, int shift, int sbo_rows, int iters, int two_acc, long long* cycles, void* stream);
 int tpz_lab_tma_stride(const tpz_half* A, int rowsA, int start, int stride, int nrows, tpz_half* out, void* stream);
 
+/* ---- greedy non-maximum suppression, picks bit-identical to topaz/algorithms.py:25-63 ----
+ * scores: device fp32 [H][W]; state (uint8[H*W]), list (int32[max_picks]), counters (int32[2]) are device scratch.
+ * On return list[0..*host_num_picks) holds the flat indices of the picks (unordered; the caller orders them by score).  */
+int tpz_nms2d(const float* scores, int H, int W, int r, float threshold, unsigned char* state, int* list, int* counters,
+              int max_picks, int* host_num_picks, void* stream);
+
 /* ---- fixed filters: dense 1->1 same-padded fp32 convolution (GaussianDenoise.apply, topaz/filters.py:62-79) ---- */
 int tpz_filter_f32(const float* x, int N, int D, int H, int W, const float* f, int kd, int kh, int kw, float bias, float* y,
                    void* stream);

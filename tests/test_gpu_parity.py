@@ -263,3 +263,23 @@ def test_denoise_image_pipeline():
     refn = O.denoise(sd, (mic - mu) / std, patch_size=64, padding=24)
     refn = (refn - refn.mean()) / refn.std()
     _check(denoise_image(mic.copy(), [dn, dn], patch_size=64, padding=24, normalize=True), refn, 2e-3)
+
+
+@pytest.mark.parametrize('H,W,r,thr', [(20, 24, 3, -np.inf), (25, 25, 2, -np.inf), (40, 6, 3, -np.inf), (6, 40, 3, -np.inf),
+                                       (33, 35, 8, -2.0), (300, 420, 9, -1.0), (8, 8, 1, 0.5)])
+def test_gpu_nms_bit_exact(H, W, r, thr):
+    """GPU greedy NMS vs the oracle restatement of topaz.algorithms.non_maximum_suppression (pinned to the reference
+    by tests/test_oracle_golden.py): identical scores and (x, y) coordinates, incl. the right-border clip quirk."""
+    from topaz_b200.algorithms import non_maximum_suppression
+    x = np.random.default_rng(H * 1000 + W).standard_normal((H, W)).astype(np.float32)
+    s_ref, c_ref = O.nms(x, r, thr)
+    s, c = non_maximum_suppression(x, r, thr)
+    assert s.dtype == np.float32 and c.dtype == np.int32
+    assert np.array_equal(c, c_ref) and np.array_equal(s, s_ref)
+
+
+def test_gpu_nms_on_reference_score_map():
+    from topaz_b200.algorithms import non_maximum_suppression
+    g = gold('resnet8_u32_pretrained')
+    s, c = non_maximum_suppression(g['y_full'][0, 0], 6, -6.0)
+    assert np.array_equal(c, g['nms_coords']) and np.array_equal(s, g['nms_scores'])
