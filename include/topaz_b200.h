@@ -156,6 +156,10 @@ int tpz_crop_add_f32(float* dx, int N, int H, int W, int C, const float* g, int 
                      void* stream);
 int tpz_ge_binomial_loss_grad(const float* scores, const double* labels, int B, double pi, double slack, int lo, int hi,
                               float* dscores, float* out5, void* stream);
+/* PN / GE_KL / PU objectives (topaz/methods.py:25-74, 168-255, 258-322): mode 0/1/2; out6 = {loss, ge_penalty, precision,
+ * tpr, fpr, aux}; aux_in = running expectation (GE_KL) or beta (PU); pi <= 0 selects the unweighted PN loss.            */
+int tpz_pu_objective_loss_grad(const float* scores, const double* labels, int B, int mode, double pi, double slack,
+                               double momentum, double aux_in, int lo, int hi, float* dscores, float* out6, void* stream);
 int tpz_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
                   float beta2, float eps, int step, float l2, float grad_scale, void* stream);
 

@@ -367,6 +367,38 @@ def ge_binomial_loss(score: torch.Tensor, Y: torch.Tensor, pi: float, slack: flo
     return cls, ge, cls + slack * ge
 
 
+def pu_objective_loss(mode: str, score: torch.Tensor, Y: torch.Tensor, pi, slack: float = 1.0, momentum: float = 1.0,
+                      running: float = None, beta: float = 0.0):
+    """Loss parts of PN.step (methods.py:42-53), GE_KL.step (:189-214, entropy_penalty=0) and PU.step (:282-298).
+    Returns (reported_loss, ge_penalty or None, backprop_loss, new_running_expectation or None)."""
+    bce = lambda s, t: F.binary_cross_entropy_with_logits(s.double(), t.double())
+    pos, neg = (Y == 1), (Y == 0)
+    if mode == 'PN':
+        if pi is not None:
+            loss = bce(score[pos], Y[pos]) * pi + bce(score[neg], Y[neg]) * (1 - pi)
+        else:
+            loss = bce(score, Y)
+        return loss, None, loss, None
+    if mode == 'GE_KL':
+        cls = bce(score[pos], Y[pos])
+        p_hat = torch.sigmoid(score[neg]).mean()
+        new_run = None
+        if momentum < 1:
+            p_hat = momentum * p_hat + (1 - momentum) * running
+            new_run = p_hat.item()
+        entropy = pi * np.log(pi) + (1 - pi) * np.log1p(-pi)
+        ge = (-torch.log(p_hat) * pi - torch.log1p(-p_hat) * (1 - pi) + entropy) * slack / momentum
+        return cls, ge, cls + ge, new_run
+    if mode == 'PU':
+        loss_pp = bce(score[pos], Y[pos]); loss_pn = bce(score[pos], 0 * Y[pos]); loss_un = bce(score[neg], Y[neg])
+        loss_u = loss_un - loss_pn * pi
+        if loss_u.item() < -beta:
+            return loss_pp * pi + (-beta), None, -loss_u, None
+        loss = loss_pp * pi + loss_u
+        return loss, None, loss, None
+    raise ValueError(mode)
+
+
 def ge_binomial_metrics(score: torch.Tensor, Y: torch.Tensor):
     """precision / tpr / fpr (methods.py:148-151)."""
     p = torch.sigmoid(score.detach())

@@ -241,6 +241,18 @@ def t_ge_loss_grad(scores, labels, pi, slack, lo, hi, dscore, out5):
     out5.copy_(torch.tensor([cls.item(), ge.item(), prec, tpr, fpr]))
 
 
+def t_pu_objective(scores, labels, mode, pi, slack, momentum, aux_in, lo, hi, dscore, out6):
+    from oracle import topaz_oracle as O
+    s = scores.detach().clone().requires_grad_(True)
+    name = ['PN', 'GE_KL', 'PU'][mode]
+    rep, ge, back, new_run = O.pu_objective_loss(name, s, labels, (pi if pi > 0 else None) if mode == 0 else pi, slack, momentum,
+                                                 aux_in, aux_in)
+    back.backward()
+    dscore.copy_(s.grad[lo:hi].float())
+    prec, tpr, fpr = O.ge_binomial_metrics(scores, labels)
+    out6.copy_(torch.tensor([rep.item(), ge.item() if ge is not None else 0.0, prec, tpr, fpr, new_run if new_run is not None else 0.0]))
+
+
 def t_adam_step(fp, lr, b1, b2, eps, l2):
     fp.step += 1
     g = fp.flat_g + l2 * fp.flat_p
@@ -255,7 +267,7 @@ def t_adam_step(fp, lr, b1, b2, eps, l2):
 def patched_training():
     from topaz_b200 import train_engine as T
     names = {'_conv_fwd': t_conv_fwd, '_conv_dgrad': t_conv_dgrad, '_conv_wgrad': t_conv_wgrad, '_relu_bwd': t_relu_bwd,
-             '_crop_add': t_crop_add, 'ge_loss_grad': t_ge_loss_grad, 'adam_step': t_adam_step,
+             '_crop_add': t_crop_add, 'ge_loss_grad': t_ge_loss_grad, 'pu_objective_loss_grad': t_pu_objective, 'adam_step': t_adam_step,
              'read_back': lambda d, h: d.tolist(), '_repack': lambda fp: None}
     saved = {n: getattr(T, n) for n in names}
     try:

@@ -145,3 +145,42 @@ def test_conv_mma_kernels_match_fp32(N, H, Ci, Co, k, stride, dil, org):
     dw = torch.zeros_like(w).cuda()
     _lib.check(L.tpz_conv_wgrad_mma(P(xd), N, H, H, Ci, P(dyd), Ho, Ho, Co, k, k, stride, dil, org, P(dw), None))
     assert max(rel_err(dw.cpu(), gw)) < 5e-5
+
+
+@pytest.mark.parametrize('tag', ['PN', 'PNpi', 'GE_KL', 'PU', 'PUclip'])
+def test_other_objectives_match_reference_golden(tag):
+    """PN / GE_KL / PU on the GPU: loss tuples of 2 steps and updated parameters vs the reference goldens; the fused loss
+    kernel's d/dscore vs the oracle's autograd."""
+    from topaz_b200 import methods as M, train_engine as T
+    from topaz_b200.model.factory import get_feature_extractor
+    from topaz_b200.model.classifier import LinearClassifier
+    g = gold('objectives_u32'); sd = weights_of(gold('resnet8_u32_pretrained'))
+    m = LinearClassifier(get_feature_extractor('resnet8', units=32, bn=False))
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}); m.cuda(); m.train()
+    opt = torch.optim.Adam(m.parameters(), lr=2e-4); crit = nn.BCEWithLogitsLoss()
+    cfg = {'PN': (0, -1.0, 1.0, 1.0, 0.0), 'PNpi': (0, 0.1, 1.0, 1.0, 0.0), 'GE_KL': (1, 0.035, 1.0, 0.9, 0.035),
+           'PU': (2, 0.035, 1.0, 1.0, 0.0), 'PUclip': (2, 0.6, 1.0, 1.0, 0.0)}[tag]
+    # kernel vs oracle autograd on random logits
+    gen = torch.Generator().manual_seed(5)
+    s = 2.0 * torch.randn(64, generator=gen) - 1.0
+    Yt = torch.tensor([1.0] * 6 + [0.0] * 58, dtype=torch.float64)
+    sr = s.clone().requires_grad_(True)
+    name = ['PN', 'GE_KL', 'PU'][cfg[0]]
+    rep, ge, back, _ = O.pu_objective_loss(name, sr, Yt, (cfg[1] if cfg[1] > 0 else None) if cfg[0] == 0 else cfg[1], cfg[2], cfg[3], cfg[4], cfg[4])
+    back.backward()
+    ds = torch.empty(64, device='cuda'); o6 = torch.empty(6, device='cuda')
+    T.pu_objective_loss_grad(s.cuda(), Yt.cuda(), *cfg, 0, 64, ds, o6)
+    assert max(rel_err(ds.cpu(), sr.grad.float())) < 1e-4
+    assert abs(o6[0].item() - rep.item()) < 1e-5 * max(1, abs(rep.item()))
+    tr = {'PN': lambda: M.PN(m, opt, crit, pi=None), 'PNpi': lambda: M.PN(m, opt, crit, pi=0.1),
+          'GE_KL': lambda: M.GE_KL(m, opt, crit, 0.035, slack=1.0, momentum=0.9),
+          'PU': lambda: M.PU(m, opt, crit, 0.035, beta=0.0), 'PUclip': lambda: M.PU(m, opt, crit, 0.6, beta=0.0)}[tag]()
+    B = int(g['B']); Y = torch.from_numpy(g['Y']).cuda()
+    outs = []
+    for step in range(2):
+        X = torch.from_numpy(np.random.default_rng(4000 + step).standard_normal((B, 71, 71)).astype(np.float32)).cuda()
+        outs.append(tr.step(X, Y))
+    np.testing.assert_allclose(np.array(outs), g[tag + '.outs'], rtol=1e-3, atol=1e-6)
+    sdn = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+    for k in ['classifier.weight', 'features.features.0.conv.weight', 'features.features.2.proj.weight']:
+        assert max(rel_err(sdn[k], g[tag + '.p.' + k])) < 1e-3, k

@@ -148,3 +148,30 @@ def test_ge_binomial_step_wiring_sim():
     with sim_backend.patched(), torch.no_grad():
         y = m(torch.from_numpy(gold('resnet8_u32_pretrained')['x']))
     assert torch.isfinite(y).all()
+
+
+@pytest.mark.parametrize('tag', ['PN', 'PNpi', 'GE_KL', 'PU', 'PUclip'])
+def test_other_objectives_wiring_sim(tag):
+    """PN / GE_KL / PU drop-ins (reference methods.py:25-74,168-322) through the shared step skeleton with simulated
+    kernels vs the reference's 2-step goldens."""
+    import torch.nn as nn
+    from topaz_b200 import methods as M
+    g = gold('objectives_u32'); sd = weights_of(gold('resnet8_u32_pretrained'))
+    m = _load(_classifier('resnet8', 32, 1, False), sd); m.train()
+    opt = torch.optim.Adam(m.parameters(), lr=2e-4); crit = nn.BCEWithLogitsLoss()
+    tr = {'PN': lambda: M.PN(m, opt, crit, pi=None), 'PNpi': lambda: M.PN(m, opt, crit, pi=0.1),
+          'GE_KL': lambda: M.GE_KL(m, opt, crit, 0.035, slack=1.0, momentum=0.9),
+          'PU': lambda: M.PU(m, opt, crit, 0.035, beta=0.0), 'PUclip': lambda: M.PU(m, opt, crit, 0.6, beta=0.0)}[tag]()
+    B = int(g['B']); Y = torch.from_numpy(g['Y'])
+    outs = []
+    with sim_backend.patched_training():
+        for step in range(2):
+            X = torch.from_numpy(np.random.default_rng(4000 + step).standard_normal((B, 71, 71)).astype(np.float32))
+            outs.append(tr.step(X, Y))
+    np.testing.assert_allclose(np.array(outs), g[tag + '.outs'], rtol=5e-4, atol=1e-6)
+    sdn = {k: v.detach().numpy() for k, v in m.state_dict().items()}
+    for k in ['classifier.weight', 'features.features.0.conv.weight', 'features.features.2.proj.weight', 'features.features.4.conv.bias']:
+        mx, l2 = rel_err(sdn[k], g[tag + '.p.' + k])
+        assert mx < 1e-4, (k, mx)
+    norms = np.array([float(np.linalg.norm(v.astype(np.float64))) for v in sdn.values()])
+    np.testing.assert_allclose(norms, g[tag + '.norms'], rtol=1e-5)

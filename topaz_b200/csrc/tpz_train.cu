@@ -360,6 +360,80 @@ __global__ void __launch_bounds__(256) ge_binomial_kernel(const float* __restric
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// The other PU-learning objectives of topaz/methods.py on the same skeleton (loss value(s), metrics, d/dscore):
+//   mode 0  PN     (methods.py:25-74)   pi <= 0: mean BCE over all;  pi > 0: pi*BCE_pos + (1-pi)*BCE_neg
+//   mode 1  GE_KL  (methods.py:168-255) BCE on positives + slack/momentum * KL(pi || p_hat), p_hat = momentum*mean_unl
+//                  sigmoid + (1-momentum)*running;   aux_in = running expectation, out[5] = new running expectation
+//   mode 2  PU     (methods.py:258-322) non-negative PU risk with clipping at -beta (aux_in = beta)
+// out6 = {loss (classifier loss for GE_KL), ge_penalty (GE_KL) or 0, precision, tpr, fpr, aux_out}
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pu_objective_kernel(const float* __restrict__ score, const double* __restrict__ label,
+                                                           int B, int mode, double pi, double slack, double momentum,
+                                                           double aux_in, int lo, int hi, float* __restrict__ dscore,
+                                                           float* __restrict__ out6) {
+  __shared__ double sh[8];
+  double s_p_pos = 0, s_p_all = 0, s_p_unl = 0, n_pos = 0, n_unl = 0, bce_pos1 = 0, bce_pos0 = 0, bce_unl0 = 0, bce_all = 0;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const double s = score[i];
+    const double p = (double)(1.0f / (1.0f + expf(-(float)s)));
+    const double sp = fmax(s, 0.0) + log1p(exp(-fabs(s)));      // softplus(s) = BCE(s, target 0)
+    s_p_all += p;
+    if (label[i] == 1.0) { n_pos += 1; s_p_pos += p; bce_pos1 += sp - s; bce_pos0 += sp; bce_all += sp - s; }
+    else if (label[i] == 0.0) { n_unl += 1; s_p_unl += p; bce_unl0 += sp; bce_all += sp; }
+    else { bce_all += sp - s * label[i]; }
+  }
+  s_p_pos = block_sum(s_p_pos, sh); s_p_all = block_sum(s_p_all, sh); s_p_unl = block_sum(s_p_unl, sh);
+  n_pos = block_sum(n_pos, sh); n_unl = block_sum(n_unl, sh);
+  bce_pos1 = block_sum(bce_pos1, sh); bce_pos0 = block_sum(bce_pos0, sh); bce_unl0 = block_sum(bce_unl0, sh);
+  bce_all = block_sum(bce_all, sh);
+  double loss = 0, ge = 0, aux = 0;
+  double w_pos_a = 0, w_pos_b = 0, w_unl = 0;      // dscore = w_pos_a*(p-1) + w_pos_b*p  (positives),  w_unl*p (Y==0)
+  double kl_coef = 0;                              // GE_KL: extra term kl_coef * p(1-p) on Y==0
+  if (mode == 0) {
+    if (pi > 0) {
+      loss = pi * bce_pos1 / n_pos + (1 - pi) * bce_unl0 / n_unl;
+      w_pos_a = pi / n_pos; w_unl = (1 - pi) / n_unl;
+    } else {
+      loss = bce_all / B;
+      w_pos_a = 1.0 / B; w_unl = 1.0 / B;
+    }
+  } else if (mode == 1) {
+    loss = bce_pos1 / n_pos;
+    w_pos_a = 1.0 / n_pos;
+    double p_hat = s_p_unl / n_unl;
+    if (momentum < 1) p_hat = momentum * p_hat + (1 - momentum) * aux_in;
+    aux = p_hat;
+    const double entropy = pi * log(pi) + (1 - pi) * log1p(-pi);
+    ge = (-log(p_hat) * pi - log1p(-p_hat) * (1 - pi) + entropy) * slack / momentum;
+    kl_coef = (slack / momentum) * (-pi / p_hat + (1 - pi) / (1 - p_hat)) * momentum / n_unl;
+  } else {
+    const double loss_pp = bce_pos1 / n_pos, loss_pn = bce_pos0 / n_pos, loss_un = bce_unl0 / n_unl;
+    const double loss_u = loss_un - loss_pn * pi;
+    if (loss_u < -aux_in) {                  // clipped: step along -loss_u, report pi*loss_pp - beta
+      loss = loss_pp * pi - aux_in;
+      w_pos_b = pi / n_pos; w_unl = -1.0 / n_unl;
+    } else {
+      loss = loss_pp * pi + loss_u;
+      w_pos_a = pi / n_pos; w_pos_b = -pi / n_pos; w_unl = 1.0 / n_unl;
+    }
+  }
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const double s = score[i];
+    const double p = 1.0 / (1.0 + exp(-s));
+    double g = 0.0;
+    if (label[i] == 1.0) g = w_pos_a * (p - 1.0) + w_pos_b * p;
+    else if (label[i] == 0.0) g = w_unl * p + kl_coef * p * (1.0 - p);
+    else if (mode == 0 && pi <= 0) g = (p - label[i]) / B;
+    dscore[i - lo] = (float)g;
+  }
+  if (threadIdx.x == 0) {
+    out6[0] = (float)loss; out6[1] = (float)ge;
+    out6[2] = (float)(s_p_pos / s_p_all); out6[3] = (float)(s_p_pos / n_pos); out6[4] = (float)(s_p_unl / n_unl);
+    out6[5] = (float)aux;
+  }
+}
+
 // fused Adam on flat buffers (torch.optim.Adam defaults: no weight decay, no amsgrad) + gradient zeroing;
 // optional L2 term l2*w added to the gradient (methods.py:153-157: d/dw of 0.5*l2*sum w^2)
 __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
@@ -478,6 +552,16 @@ extern "C" int tpz_ge_binomial_loss_grad(const float* scores, const double* labe
   TPZ_CHECK(B > 0 && lo >= 0 && hi <= B && lo <= hi, "tpz_ge_binomial_loss_grad: bad shard [%d,%d) of %d", lo, hi, B);
   TPZ_CHECK(pi > 0.0 && pi < 1.0, "tpz_ge_binomial_loss_grad: pi=%g must be in (0,1)", pi);
   ge_binomial_kernel<<<1, 256, 0, ST(stream)>>>(scores, labels, B, pi, slack, lo, hi, dscores, out5);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tpz_pu_objective_loss_grad(const float* scores, const double* labels, int B, int mode, double pi, double slack,
+                                          double momentum, double aux_in, int lo, int hi, float* dscores, float* out6,
+                                          void* stream) {
+  TPZ_CHECK(B > 0 && lo >= 0 && hi <= B && lo <= hi, "tpz_pu_objective_loss_grad: bad shard [%d,%d) of %d", lo, hi, B);
+  TPZ_CHECK(mode >= 0 && mode <= 2, "tpz_pu_objective_loss_grad: mode %d", mode);
+  pu_objective_kernel<<<1, 256, 0, ST(stream)>>>(scores, labels, B, mode, pi, slack, momentum, aux_in, lo, hi, dscores, out6);
   TPZ_CUDA(cudaGetLastError());
   return 0;
 }

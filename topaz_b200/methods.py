@@ -22,6 +22,115 @@ def _dist():
     return None
 
 
+class _Objective:
+    """Shared step skeleton: taped strided forward, fused loss kernel, backward, (DP) gradient all-reduce, fused Adam."""
+    n_out = 5
+
+    def _setup(self, model, optim, criteria):
+        if not isinstance(criteria, nn.BCEWithLogitsLoss):
+            raise NotImplementedError('topaz_b200: objectives expect criteria = nn.BCEWithLogitsLoss() (training.py:377)')
+        if not isinstance(optim, torch.optim.Adam):
+            raise NotImplementedError('topaz_b200: objectives expect torch.optim.Adam (training.py:355-356)')
+        self.model, self.optim, self.criteria = model, optim, criteria
+        self._out = None
+        self._host = None
+
+    _hyper = None          # bound below (shared with GE_binomial)
+
+    def _loss(self, gs, gy, lo, hi, dscore, out):
+        raise NotImplementedError
+
+    def _run(self, X, Y):
+        ops.require_cuda(X, 'training minibatch')
+        model = self.model
+        if not model.training:
+            model.train()
+        fp = train_engine.flat_params(model)
+        score = model(X).view(-1)
+        Yd = Y.to(device=score.device, dtype=torch.float64).view(-1)
+        b = score.numel()
+        dist = _dist()
+        if dist is not None:
+            world, rank = dist.get_world_size(), dist.get_rank()
+            gs = torch.empty(world * b, dtype=torch.float32, device=score.device)
+            gy = torch.empty(world * b, dtype=torch.float64, device=score.device)
+            dist.all_gather_into_tensor(gs, score.contiguous())
+            dist.all_gather_into_tensor(gy, Yd.contiguous())
+            lo, hi = rank * b, (rank + 1) * b
+        else:
+            gs, gy, lo, hi = score.contiguous(), Yd.contiguous(), 0, b
+        if self._out is None or self._out.device != score.device:
+            self._out = torch.empty(6, dtype=torch.float32, device=score.device)
+            self._host = torch.empty(6, dtype=torch.float32)
+            if score.is_cuda:
+                self._host = self._host.pin_memory()
+        dscore = torch.empty(b, dtype=torch.float32, device=score.device)
+        self._loss(gs, gy, lo, hi, dscore, self._out)
+        train_engine.backward(model, dscore)
+        if dist is not None:
+            dist.all_reduce(fp.flat_g, op=dist.ReduceOp.SUM)
+        lr, b1, b2, eps = GE_binomial._hyper(self)
+        train_engine.adam_step(fp, lr, b1, b2, eps, self.l2)
+        model.__dict__['_tpz_epoch'] = model.features.__dict__['_tpz_epoch'] = fp.step
+        GE_binomial._sync_optim_state(self, fp)
+        return [float(v) for v in train_engine.read_back(self._out, self._host)]
+
+
+class PN(_Objective):
+    """reference methods.py:25-74 (autoencoder = 0)."""
+    def __init__(self, model, optim, criteria, pi=None, l2=0, autoencoder=0):
+        if autoencoder > 0:
+            raise NotImplementedError('topaz_b200: autoencoder is outside the B200 hot path')
+        self._setup(model, optim, criteria)
+        self.pi, self.l2, self.autoencoder = pi, l2, autoencoder
+        self.header = ['loss', 'precision', 'adjusted_precision', 'tpr', 'fpr']
+
+    def _loss(self, gs, gy, lo, hi, dscore, out):
+        train_engine.pu_objective_loss_grad(gs, gy, 0, self.pi if self.pi is not None else -1.0, 1.0, 1.0, 0.0, lo, hi, dscore, out)
+
+    def step(self, X, Y):
+        o = self._run(X, Y)
+        return (o[0], o[2], o[3], o[4])
+
+
+class GE_KL(_Objective):
+    """reference methods.py:168-255 (entropy_penalty = 0)."""
+    def __init__(self, model, optim, criteria, pi, l2=0, slack=1.0, momentum=1.0, entropy_penalty=0):
+        if entropy_penalty > 0:
+            raise NotImplementedError('topaz_b200: entropy_penalty is outside the B200 hot path')
+        self._setup(model, optim, criteria)
+        self.pi, self.l2, self.slack, self.momentum = pi, l2, slack, momentum
+        self.running_expectation = pi
+        self.entropy_penalty = entropy_penalty
+        self.header = ['loss', 'ge_penalty', 'precision', 'adjusted_precision', 'tpr', 'fpr']
+
+    def _loss(self, gs, gy, lo, hi, dscore, out):
+        train_engine.pu_objective_loss_grad(gs, gy, 1, self.pi, self.slack, self.momentum, self.running_expectation, lo, hi, dscore, out)
+
+    def step(self, X, Y):
+        o = self._run(X, Y)
+        if self.momentum < 1:
+            self.running_expectation = o[5]
+        return o[0], o[1], o[2], o[3], o[4]
+
+
+class PU(_Objective):
+    """reference methods.py:258-322 (non-negative PU risk; autoencoder = 0)."""
+    def __init__(self, model, optim, criteria, pi, l2=0, beta=0.0, autoencoder=0):
+        if autoencoder > 0:
+            raise NotImplementedError('topaz_b200: autoencoder is outside the B200 hot path')
+        self._setup(model, optim, criteria)
+        self.pi, self.l2, self.beta, self.autoencoder = pi, l2, beta, autoencoder
+        self.header = ['loss', 'precision', 'adjusted_precision', 'tpr', 'fpr']
+
+    def _loss(self, gs, gy, lo, hi, dscore, out):
+        train_engine.pu_objective_loss_grad(gs, gy, 2, self.pi, 1.0, 1.0, self.beta, lo, hi, dscore, out)
+
+    def step(self, X, Y):
+        o = self._run(X, Y)
+        return (o[0], o[2], o[3], o[4])
+
+
 class GE_binomial:
     def __init__(self, model, optim, criteria, pi, l2=0, slack=1.0, entropy_penalty=0, autoencoder=0, posterior_L1=0):
         if entropy_penalty > 0 or autoencoder > 0 or posterior_L1 > 0:

@@ -320,6 +320,13 @@ def ge_loss_grad(scores, labels, pi, slack, lo, hi, dscore, out5):
                                                _p(dscore), _p(out5), _s()))
 
 
+def pu_objective_loss_grad(scores, labels, mode, pi, slack, momentum, aux_in, lo, hi, dscore, out6):
+    """PN (mode 0) / GE_KL (1) / PU (2) loss, metrics and d(loss)/d(score) (reference methods.py:25-74,168-322)."""
+    ops._count(1)
+    check(_lib.lib().tpz_pu_objective_loss_grad(_p(scores), _p(labels), scores.numel(), int(mode), float(pi), float(slack),
+                                                float(momentum), float(aux_in), lo, hi, _p(dscore), _p(out6), _s()))
+
+
 def adam_step(fp: FlatParams, lr, b1, b2, eps, l2):
     """Fused Adam on the flat buffers + L2 term + gradient zeroing (reference methods.py:153-160)."""
     fp.step += 1
