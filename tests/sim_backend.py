@@ -140,6 +140,12 @@ def upsample_nearest(x, size):
     return x[:, idx(D, Do)][:, :, idx(H, Ho)][:, :, :, idx(W, Wo)].contiguous()
 
 
+def filter_f32(x, f, bias=0.0):
+    kd, kh, kw = f.shape
+    y = F.conv3d(x[:, None], f[None, None], None, padding=(kd // 2, kh // 2, kw // 2))[:, 0]
+    return y + bias
+
+
 def meanstd(x, unbiased):
     xd = x.double()
     return torch.stack([xd.mean(), xd.std(unbiased=unbiased)]).float()
@@ -154,7 +160,7 @@ def affine(x, stats, inverse=False, out=None):
 
 @contextlib.contextmanager
 def patched():
-    names = ['tc_conv', 'conv_first', 'im2col_first', 'conv_last', 'maxpool2', 'upsample_nearest', 'meanstd', 'affine']
+    names = ['tc_conv', 'conv_first', 'im2col_first', 'filter_f32', 'conv_last', 'maxpool2', 'upsample_nearest', 'meanstd', 'affine']
     saved = {n: getattr(ops, n) for n in names}
     saved['require_cuda'] = ops.require_cuda
     try:

@@ -283,3 +283,19 @@ def test_gpu_nms_on_reference_score_map():
     g = gold('resnet8_u32_pretrained')
     s, c = non_maximum_suppression(g['y_full'][0, 0], 6, -6.0)
     assert np.array_equal(c, g['nms_coords']) and np.array_equal(s, g['nms_scores'])
+
+
+def test_fcnn_and_affine_denoisers():
+    from topaz_b200.denoising.models import DenoiseNet2, AffineDenoise
+    from topaz_b200.denoise import Denoise
+    g = gold('fcnn_affine_seeded')
+    mf = _load(DenoiseNet2(64, width=11), seeded_state({k: tuple(v.shape) for k, v in DenoiseNet2(64, width=11).state_dict().items()}, 301)).cuda()
+    ma = _load(AffineDenoise(max_size=31), seeded_state({k: tuple(v.shape) for k, v in AffineDenoise(31).state_dict().items()}, 302)).cuda()
+    x = torch.from_numpy(g['x']).cuda()
+    with torch.no_grad():
+        _check(mf(x).cpu().numpy(), g['y_fcnn'], TOL_SEEDED)
+        _check(ma(x).cpu().numpy(), g['y_affine'], 1e-5)
+    img = (10 + 3 * g['x'][0, 0]).astype(np.float32)
+    for m, key in ((mf, 'y_fcnn'), (ma, 'y_affine')):
+        out = Denoise(m)._denoise(img.copy())
+        assert out.shape == img.shape and np.isfinite(out).all()

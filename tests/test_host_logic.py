@@ -175,3 +175,18 @@ def test_other_objectives_wiring_sim(tag):
         assert mx < 1e-4, (k, mx)
     norms = np.array([float(np.linalg.norm(v.astype(np.float64))) for v in sdn.values()])
     np.testing.assert_allclose(norms, g[tag + '.norms'], rtol=1e-5)
+
+
+def test_fcnn_and_affine_denoisers_sim():
+    from topaz_b200.denoising.models import DenoiseNet2, AffineDenoise
+    g = gold('fcnn_affine_seeded')
+    mf = DenoiseNet2(64, width=11)
+    assert list(mf.state_dict().keys()) == [str(k) for k in g['keys_fcnn']]
+    _load(mf, seeded_state({k: tuple(v.shape) for k, v in mf.state_dict().items()}, 301)); mf.eval()
+    ma = AffineDenoise(max_size=31)
+    assert list(ma.state_dict().keys()) == [str(k) for k in g['keys_affine']]
+    _load(ma, seeded_state({k: tuple(v.shape) for k, v in ma.state_dict().items()}, 302)); ma.eval()
+    with sim_backend.patched(), torch.no_grad():
+        yf = mf(torch.from_numpy(g['x'])).numpy(); ya = ma(torch.from_numpy(g['x'])).numpy()
+    mx, l2 = rel_err(yf, g['y_fcnn']); assert mx < TOL_SEEDED and l2 < TOL_SEEDED, (mx, l2)
+    mx, l2 = rel_err(ya, g['y_affine']); assert mx < 1e-5, (mx, l2)

@@ -48,7 +48,13 @@ class Denoise():
             xn = xn[None, None]
         elif xn.dim() == self.dims + 1:
             xn = xn.unsqueeze(1)
-        pred = engine.unet_forward(self.model, xn, denorm_stats=stats)   # pred*std+mu fused (denoise.py:295)
+        from topaz_b200.denoising.models import DenoiseNet2, AffineDenoise
+        if isinstance(self.model, DenoiseNet2):
+            pred = engine.fcnn_forward(self.model, xn, denorm_stats=stats)
+        elif isinstance(self.model, AffineDenoise):
+            pred = engine.affine_forward(self.model, xn, denorm_stats=stats)
+        else:
+            pred = engine.unet_forward(self.model, xn, denorm_stats=stats)   # pred*std+mu fused (denoise.py:295)
         return pred.squeeze()
 
     @torch.no_grad()

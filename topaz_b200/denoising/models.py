@@ -11,11 +11,6 @@ from torch import nn
 from topaz_b200.model.utils import load_pretrained_state
 
 
-def _stage(conv, cin, cout, k, pool, n_extra=0):
-    mods = [conv(cin, cout, k, padding=k // 2), nn.LeakyReLU(0.1)]
-    return mods
-
-
 class _UNetBase(nn.Module):
     _dims = 2
 
@@ -69,10 +64,40 @@ class UDenoiseNet3D(_UNetBase):
         self._build(nf, base_width, top_width, depth=6)
 
 
+class DenoiseNet2(nn.Module):
+    """`fcnn` denoiser (reference denoising/models.py:52-66): three same-padded width x width convs, LeakyReLU(0.1)."""
+    def __init__(self, base_filters, width=11):
+        super().__init__()
+        self.base_filters = base_filters
+        nf = base_filters
+        self.net = nn.Sequential(nn.Conv2d(1, nf, width, padding=width // 2), nn.LeakyReLU(0.1),
+                                 nn.Conv2d(nf, nf, width, padding=width // 2), nn.LeakyReLU(0.1),
+                                 nn.Conv2d(nf, 1, width, padding=width // 2))
+
+    def forward(self, x):
+        from topaz_b200 import engine
+        return engine.fcnn_forward(self, x)
+
+
+class AffineDenoise(nn.Module):
+    """`affine` denoiser (reference filters.py:40-48): one learned max_size x max_size filter."""
+    def __init__(self, max_size=31):
+        super().__init__()
+        self.filter = nn.Conv2d(1, 1, max_size, padding=max_size // 2)
+        self.filter.weight.data.zero_()
+        self.filter.bias.data.zero_()
+
+    def forward(self, x):
+        from topaz_b200 import engine
+        return engine.affine_forward(self, x)
+
+
 model_name_dict = {
     # 2D models
     'unet': 'unet_L2_v0.2.2.sav',
     'unet-small': 'unet_small_L1_v0.2.2.sav',
+    'fcnn': 'fcnn_L1_v0.2.2.sav',
+    'affine': 'affine_L1_v0.2.2.sav',
     'unet-v0.2.1': 'unet_L2_v0.2.1.sav',
     # 3D models
     'unet-3d': 'unet-3d-10a-v0.2.4.sav',
@@ -84,20 +109,20 @@ _ARCH = {
     'unet_L2_v0.2.1.sav': lambda: UDenoiseNet(base_width=7, top_width=3),
     'unet_L2_v0.2.2.sav': lambda: UDenoiseNet(base_width=11, top_width=5),
     'unet_small_L1_v0.2.2.sav': lambda: UDenoiseNetSmall(width=11, top_width=5),
+    'fcnn_L1_v0.2.2.sav': lambda: DenoiseNet2(64, width=11),
+    'affine_L1_v0.2.2.sav': lambda: AffineDenoise(max_size=31),
     'unet-3d-10a-v0.2.4.sav': lambda: UDenoiseNet3D(base_width=7),
     'unet-3d-20a-v0.2.4.sav': lambda: UDenoiseNet3D(base_width=7),
 }
 
 
 def load_model(name, base_kernel_width=11):
-    '''reference denoising/models.py:581-625 (fcnn / affine pretrained models are outside the B200 hot path).'''
+    '''reference denoising/models.py:581-625.'''
     pretrained = name in model_name_dict
     if pretrained:
         name = model_name_dict[name]
     if name in _ARCH:
         model = _ARCH[name]()
-    elif name in ('fcnn', 'affine', 'fcnn_L1_v0.2.2.sav', 'affine_L1_v0.2.2.sav'):
-        raise NotImplementedError(f'topaz_b200: denoiser {name!r} is outside the B200 hot path (U-Net models only)')
     else:
         model = torch.load(name, weights_only=False)
     if pretrained:

@@ -476,3 +476,46 @@ def unet_forward(model, x: torch.Tensor, denorm_stats: Optional[torch.Tensor] = 
     if dims == 2:
         return y.view(y.shape[0], 1, y.shape[2], y.shape[3])
     return y.view(y.shape[0], 1, y.shape[1], y.shape[2], y.shape[3])
+
+
+# ------------------------------------------------------------------------------------------------
+# fcnn (DenoiseNet2) and affine denoisers (same kernels, small deltas)
+# ------------------------------------------------------------------------------------------------
+def _build_fcnn_plan(model, device):
+    c0, c1, c2 = model.net[0], model.net[2], model.net[4]
+    k = c0.weight.shape[-1]
+    nf = c0.weight.shape[0]
+    pad = (-(k // 2), -(k // 2), 0)
+    ld = _tap_ld(k * k)
+    p0 = ops.pack_tc_conv([ConvPart(c0.weight.detach().reshape(nf, k * k, 1, 1), ld, 1)], c0.bias, _rup(nf), 0.1, device)
+    p1 = ops.pack_tc_conv([ConvPart(c1.weight, _rup(nf), 1, pad)], c1.bias, _rup(c1.weight.shape[0]), 0.1, device)
+    one = torch.zeros(1, 1, 1, 1); one[0, 0, 0, 0] = 1.0
+    p2 = ops.pack_tc_conv([ConvPart(c2.weight, _rup(c1.weight.shape[0]), 1, pad)], None, 16, 1.0, device, dot_w=one,
+                          dot_b=float(c2.bias.detach()[0]))
+    return dict(k=k, ld=ld, p0=p0, p1=p1, p2=p2)
+
+
+def fcnn_forward(model, x: torch.Tensor, denorm_stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """DenoiseNet2.forward (reference denoising/models.py:52-66); x: fp32 [N,1,H,W] on the device."""
+    ops.require_cuda(x, 'denoiser input')
+    plan = _cached(model, 'fcnn', _state_key(model, ('fcnn', str(x.device))), lambda: _build_fcnn_plan(model, x.device))
+    xi = x[:, 0].contiguous().float()
+    N, H, W = xi.shape
+    col = ops.im2col_first(xi, plan['k'], plan['k'] // 2, plan['ld'])
+    h0 = torch.empty((N, 1, H, W, plan['p0'].Co), dtype=torch.float16, device=x.device)
+    ops.tc_conv(plan['p0'], [col], (N, 1, H, W), out=h0)
+    h1 = torch.empty((N, 1, H, W, plan['p1'].Co), dtype=torch.float16, device=x.device)
+    ops.tc_conv(plan['p1'], [h0], (N, 1, H, W), out=h1)
+    y = torch.empty((N, 1, H, W), dtype=torch.float32, device=x.device)
+    ops.tc_conv(plan['p2'], [h1], (N, 1, H, W), out=None, dot_out=y, dot_affine=denorm_stats)
+    return y
+
+
+def affine_forward(model, x: torch.Tensor, denorm_stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """AffineDenoise.forward (reference filters.py:40-48): one same-padded 1->1 filter."""
+    ops.require_cuda(x, 'denoiser input')
+    w = model.filter.weight.detach().to(x.device, torch.float32)[0, 0][None].contiguous()
+    y = ops.filter_f32(x[:, 0].contiguous().float()[:, None], w, float(model.filter.bias.detach()[0]))
+    if denorm_stats is not None:
+        y = ops.affine(y, denorm_stats, inverse=True)
+    return y
