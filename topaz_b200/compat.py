@@ -1,0 +1,47 @@
+"""Make an unmodified Topaz use the B200 modules: ``install()`` aliases the reference's L2 module paths
+(`topaz.model.factory`, `topaz.model.classifier`, `topaz.model.features.{resnet,basic}`, `topaz.denoising.models`,
+`topaz.methods`) to their topaz_b200 drop-ins in ``sys.modules`` and patches `topaz.algorithms.non_maximum_suppression`.  Call it
+BEFORE importing `topaz.extract` / `topaz.training` / `topaz.denoise`; the reference's own L3-L5 code (CLI, pipelines)
+then runs unchanged on the sm_100a kernels.  Whole-module pickles saved by the reference (`torch.save(model)`,
+training.py:601) resolve to the drop-in classes through the same aliases."""
+import importlib
+import sys
+
+_ALIASES = {
+    'topaz.model.factory': 'topaz_b200.model.factory',
+    'topaz.model.classifier': 'topaz_b200.model.classifier',
+    'topaz.model.features.resnet': 'topaz_b200.model.features.resnet',
+    'topaz.model.features.basic': 'topaz_b200.model.features.basic',
+    'topaz.denoising.models': 'topaz_b200.denoising.models',
+    'topaz.methods': 'topaz_b200.methods',
+}
+# functions patched INTO reference modules that also hold out-of-scope helpers (match_coordinates, 3-D NMS, ...)
+_FUNCTION_PATCHES = {('topaz.algorithms', 'non_maximum_suppression'): ('topaz_b200.algorithms', 'non_maximum_suppression')}
+
+
+def install(names=None):
+    """Alias the listed reference module paths (default: all) to the topaz_b200 implementations."""
+    for ref, ours in _ALIASES.items():
+        if names is not None and ref not in names:
+            continue
+        mod = importlib.import_module(ours)
+        sys.modules[ref] = mod
+        parent, _, leaf = ref.rpartition('.')
+        if parent in sys.modules:                 # keep `import topaz.model.factory as f` style attribute access working
+            setattr(sys.modules[parent], leaf, mod)
+    for (ref_mod, fn), (our_mod, our_fn) in _FUNCTION_PATCHES.items():
+        if names is not None and ref_mod not in names:
+            continue
+        try:
+            target = importlib.import_module(ref_mod)
+        except ImportError:
+            continue
+        if not hasattr(target, '_tpz_orig_' + fn):
+            setattr(target, '_tpz_orig_' + fn, getattr(target, fn))
+        setattr(target, fn, getattr(importlib.import_module(our_mod), our_fn))
+    return sorted(_ALIASES if names is None else names)
+
+
+def uninstall():
+    for ref in _ALIASES:
+        sys.modules.pop(ref, None)

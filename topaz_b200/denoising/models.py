@@ -134,3 +134,8 @@ def load_model(name, base_kernel_width=11):
         model.load_state_dict(state)
     model.eval()
     return model
+
+
+def train_model(*args, **kwargs):
+    """Noise2noise denoiser training (reference denoising/models.py:636-758) is outside the B200 hot path."""
+    raise NotImplementedError('topaz_b200: denoiser training is outside the B200 hot path; train with the reference and load the .sav')

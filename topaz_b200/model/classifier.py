@@ -26,3 +26,8 @@ class LinearClassifier(nn.Module):
     def forward(self, x):
         from topaz_b200 import engine
         return engine.classifier_forward(self, x)
+
+
+def classify_patches(classifier, tomo_stack, patch_size=48, padding=36, batch_size=1, volume_num=1, total_volumes=1, verbose=True):
+    """3-D evaluation tiling of the reference (classifier.py:69-103); 3-D classifiers are outside the B200 hot path."""
+    raise NotImplementedError('topaz_b200: 3-D classifier tiling (classify_patches) is outside the B200 hot path')

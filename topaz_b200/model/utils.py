@@ -42,6 +42,13 @@ def pretrained_path(kind: str, name: str) -> str:
     raise RuntimeError(f'Could not locate pretrained weights {kind}/{name}; set TOPAZ_PRETRAINED_DIR')
 
 
+def load_state_dict_from_pkg(pkg: str, path: str, map_location='cpu'):
+    """Signature-compatible with topaz.model.utils.load_state_dict_from_pkg (reference utils.py:12-36): ``path`` is
+    'pretrained/<kind>/<file>' (possibly with a leading '../')."""
+    parts = path.replace('\\', '/').split('/')
+    return load_pretrained_state(parts[-2], parts[-1])
+
+
 def load_pretrained_state(kind: str, name: str):
     return torch.load(pretrained_path(kind, name), map_location='cpu', weights_only=False)
 
