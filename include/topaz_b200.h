@@ -169,6 +169,20 @@ int tpz_lab_umma(const tpz_half* A, int rowsA, const tpz_half* B, int N, int shi
 int tpz_lab_umma_rate(int N, int shift, int sbo_rows, int iters, int two_acc, long long* cycles, void* stream);
 int tpz_lab_tma_stride(const tpz_half* A, int rowsA, int start, int stride, int nrows, tpz_half* out, void* stream);
 
+/* ---- training-crop sampler + augmentation on the GPU ----
+ * Replaces MultipleImageSetDataset.__getitem__ / MemoryMappedImage.get_crop (topaz/utils/data/memory_mapped_data.py:45-100,
+ * 195-233).  `pixels`: all micrographs concatenated (fp32); imgs[i] = {element offset, H, W}; set_begin[nsets+1] partitions
+ * the image list into sets, set_cdf = cumulative set probabilities; positives = int32 [P][3] (image, y, x) of every labelled
+ * pixel; pos_mask = uint8 per pixel (same offsets) for the 'pn' rejection of labelled pixels.  Writes X [B][crop][crop] fp32
+ * and Y [B] fp64; params_scratch >= 32*B bytes.  Reproducible from (seed, batch_index).                                   */
+typedef struct { long long offset; int H, W; } TpzSamplerImage;
+int tpz_sample_crops(int B, unsigned long long seed, unsigned long long batch_index, const TpzSamplerImage* imgs,
+                     const float* pixels, const int* set_begin, const float* set_cdf, int nsets, const int* positives,
+                     int num_positives, const unsigned char* pos_mask, float positive_balance, int split_pn, int rotate,
+                     int flip, int crop, int big_crop, void* params_scratch, float* X, double* Y, void* stream);
+int tpz_make_crops(int B, int crop, int big_crop, const TpzSamplerImage* imgs, const float* pixels, const void* params,
+                   float* X, void* stream);
+
 /* ---- greedy non-maximum suppression, picks bit-identical to topaz/algorithms.py:25-63 ----
  * scores: device fp32 [H][W]; state (uint8[H*W]), list (int32[max_picks]), counters (int32[2]) are device scratch.
  * On return list[0..*host_num_picks) holds the flat indices of the picks (unordered; the caller orders them by score).  */

@@ -94,6 +94,36 @@ def main():
                 print(json.dumps(dict(workload='GE_binomial.step resnet8_u32, global minibatch 256 crops 71x71 (incl. per-step host readback)',
                                       n_gpus=world, ms_per_step=ms / n, crops_s=n * B / (ms / 1e3), launches_per_step=(ops.LAUNCH_COUNT - l0) / n,
                                       last_out=out)))
+        elif wl == 'train_e2e':
+            # GE-binomial training fed by the GPU crop sampler (the reference's host loader: 0.28-0.35 s per minibatch)
+            from topaz_b200.methods import GE_binomial
+            from topaz_b200.sampler import GpuCropSampler
+            from topaz_b200.model.factory import get_feature_extractor
+            from topaz_b200.model.classifier import LinearClassifier
+            m = LinearClassifier(get_feature_extractor('resnet8', units=32, bn=False))
+            m.load_state_dict({k: torch.from_numpy(v) for k, v in weights_of(gold('resnet8_u32_pretrained')).items()})
+            m.cuda(); m.train()
+            tr = GE_binomial(m, torch.optim.Adam(m.parameters(), lr=2e-4), nn.BCEWithLogitsLoss(), 0.035)
+            g = np.random.default_rng(7 + rank)
+            mics = [g.standard_normal((1024, 1024)).astype(np.float32) for _ in range(16)]
+            pos = []
+            for k in range(16):
+                for (py, px) in g.integers(40, 984, size=(60, 2)):
+                    for dy in range(-3, 4):
+                        for dx in range(-3, 4):
+                            if dy * dy + dx * dx <= 9:
+                                pos.append((k, py + dy, px + dx))
+            smp = GpuCropSampler([mics], np.array(pos, dtype=np.int32), 71, positive_balance=0.0625, seed=rank)
+            b = 256 // world
+            for _ in range(5):
+                tr.step(*smp.sample(b))
+            sync(); t0 = time.perf_counter(); n = 50
+            for _ in range(n):
+                out = tr.step(*smp.sample(b))
+            torch.cuda.synchronize(); ms = maxms((time.perf_counter() - t0) * 1e3)
+            if rank == 0:
+                print(json.dumps(dict(workload='GPU crop sampler (rotate+flip, 16 micrographs 1024^2) + GE_binomial.step, 256 crops/minibatch',
+                                      n_gpus=world, ms_per_step=ms / n, crops_s=n * 256 / (ms / 1e3), last_out=out)))
         elif wl == 'denoise3d':
             from topaz_b200.denoising.models import UDenoiseNet3D
             from topaz_b200.denoise import Denoise3D
