@@ -136,6 +136,10 @@ int tpz_conv_wgrad_f32(const float* x, int N, int H, int W, int Ci, const float*
 /* Tensor-core (mma.sync, error-compensated 3xTF32) variants for channel counts that are multiples of 16/32.
  * Weights come from tpz_train_repack: OIHW -> [tap][ci][co] (forward) and [tap][co][ci] (dgrad); `descs` is a device
  * array of {int64 src, dst_fwd, dst_dg; int32 Co, Ci, taps, pad} (element offsets into flat_params / packed). */
+/* Precision of the mma training convs: 0 (default) = error-compensated 3xTF32, fp32-level accuracy (the reference's CPU
+ * results); 1 = single-pass TF32, the precision of the reference's own GPU path (torch.backends.cudnn.allow_tf32 defaults
+ * to True).  Also selectable with the environment variable TPZ_TRAIN_TF32=1.  Returns the previous mode. */
+int tpz_train_set_tf32(int single_pass);
 int tpz_train_repack(const float* flat_params, const void* descs, int ndesc, long long max_elems, float* packed, void* stream);
 int tpz_conv_fwd_mma(const float* x, int N, int H, int W, int Ci, const float* w_fwd_packed, const float* bias, int Co,
                      int kh, int kw, int stride, int dil, int org, const float* res, int res_H, int res_W, int res_org,
@@ -188,6 +192,11 @@ int tpz_make_crops(int B, int crop, int big_crop, const TpzSamplerImage* imgs, c
  * On return list[0..*host_num_picks) holds the flat indices of the picks (unordered; the caller orders them by score).  */
 int tpz_nms2d(const float* scores, int H, int W, int r, float threshold, unsigned char* state, int* list, int* counters,
               int max_picks, int* host_num_picks, void* stream);
+/* 3-D variant (topaz/algorithms.py:66-103): the reference suppresses FLAT indices i + delta (delta = dz*H*W + dy*W + dx
+ * over the ball of radius scale*r) with no bounds handling, so neighbours wrap across rows/slices; `deltas` (device
+ * int32[num_deltas], symmetric set) is built by the caller exactly as the reference builds coord_deltas. */
+int tpz_nms_flat(const float* scores, long long n, const int* deltas, int num_deltas, float threshold, unsigned char* state,
+                 int* list, int* counters, int max_picks, int* host_num_picks, void* stream);
 
 /* ---- fixed filters: dense 1->1 same-padded fp32 convolution (GaussianDenoise.apply, topaz/filters.py:62-79) ---- */
 int tpz_filter_f32(const float* x, int N, int D, int H, int W, const float* f, int kd, int kh, int kw, float bias, float* y,

@@ -491,3 +491,29 @@ def nms(x: np.ndarray, r: int, threshold: float = -np.inf):
             xc = np.clip(xx + jj, 0, x.shape[1])
             S[yc * W + xc] = True
     return np.asarray(scores, dtype=np.float32), np.asarray(coords, dtype=np.int32).reshape(-1, 2)
+
+
+def nms3d(x: np.ndarray, r, scale: float = 1.0, threshold: float = -np.inf):
+    """algorithms.non_maximum_suppression_3d (algorithms.py:66-103): flat-index deltas over the ball of radius scale*r, no
+    bounds handling (the reference's set of suppressed flat indices may hold out-of-range values; they never match)."""
+    r = scale * r
+    width = int(np.ceil(r))
+    ax = np.arange(-width, width + 1)
+    ii, jj, kk = np.meshgrid(ax, ax, ax)
+    mask = (ii ** 2 + jj ** 2 + kk ** 2) <= r * r
+    deltas = ii[mask] * (x.shape[1] * x.shape[2]) + jj[mask] * x.shape[2] + kk[mask]
+    A = x.ravel()
+    n = len(A)
+    I = np.argsort(A, axis=None)[::-1]
+    S = np.zeros(n, dtype=bool)
+    scores, coords = [], []
+    for i in I:
+        if A[i] <= threshold:
+            break
+        if not S[i]:
+            zz, yy, xx = np.unravel_index(i, x.shape)
+            scores.append(A[i])
+            coords.append((xx, yy, zz))
+            t = i + deltas
+            S[t[(t >= 0) & (t < n)]] = True
+    return np.asarray(scores, dtype=np.float32), np.asarray(coords, dtype=np.int32).reshape(-1, 3)

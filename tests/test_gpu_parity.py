@@ -299,3 +299,17 @@ def test_fcnn_and_affine_denoisers():
     for m, key in ((mf, 'y_fcnn'), (ma, 'y_affine')):
         out = Denoise(m)._denoise(img.copy())
         assert out.shape == img.shape and np.isfinite(out).all()
+
+
+def test_gpu_nms3d_bit_exact():
+    """3-D greedy NMS (algorithms.py:66-103) vs the reference goldens and, on a larger volume, the oracle."""
+    from topaz_b200.algorithms import non_maximum_suppression_3d
+    g = gold('nms3d')
+    for tag in 'abcd':
+        s, c = non_maximum_suppression_3d(g[f'{tag}.x'], float(g[f'{tag}.r']), scale=float(g[f'{tag}.scale']), threshold=float(g[f'{tag}.thr']))
+        assert s.dtype == np.float32 and c.dtype == np.int32 and c.shape[1] == 3
+        assert np.array_equal(c, g[f'{tag}.coords']) and np.array_equal(s, g[f'{tag}.scores']), tag
+    x = np.random.default_rng(9).standard_normal((64, 80, 96)).astype(np.float32)
+    s_ref, c_ref = O.nms3d(x, 5, 1.0, 1.0)
+    s, c = non_maximum_suppression_3d(x, 5, threshold=1.0)
+    assert len(s) > 300 and np.array_equal(c, c_ref) and np.array_equal(s, s_ref)

@@ -184,3 +184,30 @@ def test_other_objectives_match_reference_golden(tag):
     sdn = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
     for k in ['classifier.weight', 'features.features.0.conv.weight', 'features.features.2.proj.weight']:
         assert max(rel_err(sdn[k], g[tag + '.p.' + k])) < 1e-3, k
+
+
+def test_single_pass_tf32_mode_gradients():
+    """Optional single-pass TF32 training mode (precision of the reference's own cuDNN path): gradients of one step
+    stay within 1e-2 of the fp32 reference golden (documented tolerance for TF32), and the mode switch is restored."""
+    from topaz_b200 import train_engine as T
+    from topaz_b200.model.factory import get_feature_extractor
+    from topaz_b200.model.classifier import LinearClassifier
+    g = gold('ge_binomial_u32'); sd = weights_of(gold('resnet8_u32_pretrained'))
+    m = LinearClassifier(get_feature_extractor('resnet8', units=32, bn=False))
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}); m.cuda(); m.train()
+    B = int(g['B']); Y = torch.from_numpy(g['Y']).cuda()
+    X = torch.from_numpy(np.random.default_rng(4000).standard_normal((B, 71, 71)).astype(np.float32)).cuda()
+    prev = T.set_tf32(True)
+    try:
+        T.flat_params(m)
+        score = m(X).view(-1)
+        ds = torch.empty(B, device='cuda'); o5 = torch.empty(5, device='cuda')
+        T.ge_loss_grad(score.contiguous(), Y, float(g['pi']), 1.0, 0, B, ds, o5)
+        T.backward(m, ds)
+        worst = 0.0
+        for k, p in m.named_parameters():
+            worst = max(worst, max(rel_err(p.grad.cpu().numpy(), g['g1.' + k])))
+        print('single-pass TF32 worst gradient rel err', worst)
+        assert worst < 1e-2
+    finally:
+        assert T.set_tf32(prev) is True

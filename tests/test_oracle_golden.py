@@ -104,3 +104,10 @@ def test_log_binom_matches_scipy():
     for N, pi in [(240, 0.035), (60, 0.2), (1, 0.5)]:
         ref = scipy_stats.binom.logpmf(np.arange(N + 1), N, pi).astype(np.float32)
         np.testing.assert_allclose(O.log_binom_pmf(N, pi), ref, rtol=2e-6, atol=1e-5)
+
+
+def test_nms3d_bit_exact_vs_reference_golden():
+    g = gold('nms3d')
+    for tag in 'abcd':
+        s, c = O.nms3d(g[f'{tag}.x'], float(g[f'{tag}.r']), float(g[f'{tag}.scale']), float(g[f'{tag}.thr']))
+        assert len(s) > 0 and np.array_equal(c, g[f'{tag}.coords']) and np.array_equal(s, g[f'{tag}.scores']), tag

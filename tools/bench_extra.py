@@ -70,7 +70,9 @@ def main():
                                       n_gpus=world, ms_per_image=ms / args.steps, mpx_s=world * args.steps * 16.777216 / (ms / 1e3),
                                       tflops=world * args.steps * 29.458 / (ms / 1e3), launches_per_image=(ops.LAUNCH_COUNT - l0) / args.steps,
                                       finite=bool(np.isfinite(y).all()))))
-        elif wl == 'train':
+        elif wl in ('train', 'train_tf32'):
+            from topaz_b200 import train_engine as _T
+            _T.set_tf32(wl == 'train_tf32')
             from topaz_b200.methods import GE_binomial
             from topaz_b200.model.factory import get_feature_extractor
             from topaz_b200.model.classifier import LinearClassifier
@@ -91,9 +93,10 @@ def main():
                 out = tr.step(Xs[s % 4], Yl)
             torch.cuda.synchronize(); ms = maxms((time.perf_counter() - t0) * 1e3)
             if rank == 0:
-                print(json.dumps(dict(workload='GE_binomial.step resnet8_u32, global minibatch 256 crops 71x71 (incl. per-step host readback)',
+                print(json.dumps(dict(workload='GE_binomial.step resnet8_u32, global minibatch 256 crops 71x71 (incl. per-step host readback)' + (', single-pass TF32 mode' if wl == 'train_tf32' else ', 3xTF32'),
                                       n_gpus=world, ms_per_step=ms / n, crops_s=n * B / (ms / 1e3), launches_per_step=(ops.LAUNCH_COUNT - l0) / n,
                                       last_out=out)))
+            _T.set_tf32(False)
         elif wl == 'train_e2e':
             # GE-binomial training fed by the GPU crop sampler (the reference's host loader: 0.28-0.35 s per minibatch)
             from topaz_b200.methods import GE_binomial

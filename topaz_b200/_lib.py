@@ -54,12 +54,14 @@ _PROTOS = {
     'tpz_affine': (_I, [_P, _LL, _P, _I, _P, _P]),
     'tpz_sample_crops': (_I, [_I, C.c_ulonglong, C.c_ulonglong, _P, _P, _P, _P, _I, _P, _I, _P, _F, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     'tpz_make_crops': (_I, [_I, _I, _I, _P, _P, _P, _P, _P]),
+    'tpz_nms_flat': (_I, [_P, _LL, _P, _I, _F, _P, _P, _P, _I, C.POINTER(_I), _P]),
     'tpz_nms2d': (_I, [_P, _I, _I, _I, _F, _P, _P, _P, _I, C.POINTER(_I), _P]),
     'tpz_filter_f32': (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _F, _P, _P]),
     'tpz_f32_to_f16': (_I, [_P, _LL, _P, _P]),
     'tpz_conv_fwd_f32': (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P, _I, _I, _P]),
     'tpz_conv_dgrad_f32': (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P]),
     'tpz_conv_wgrad_f32': (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    'tpz_train_set_tf32': (_I, [_I]),
     'tpz_train_repack': (_I, [_P, _P, _I, _LL, _P, _P]),
     'tpz_conv_fwd_mma': (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P, _I, _I, _P]),
     'tpz_conv_dgrad_mma': (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P]),

@@ -1,6 +1,6 @@
 """Make an unmodified Topaz use the B200 modules: ``install()`` aliases the reference's L2 module paths
 (`topaz.model.factory`, `topaz.model.classifier`, `topaz.model.features.{resnet,basic}`, `topaz.denoising.models`,
-`topaz.methods`) to their topaz_b200 drop-ins in ``sys.modules`` and patches `topaz.algorithms.non_maximum_suppression`.  Call it
+`topaz.methods`) to their topaz_b200 drop-ins in ``sys.modules`` and patches `topaz.algorithms.non_maximum_suppression(_3d)`.  Call it
 BEFORE importing `topaz.extract` / `topaz.training` / `topaz.denoise`; the reference's own L3-L5 code (CLI, pipelines)
 then runs unchanged on the sm_100a kernels.  Whole-module pickles saved by the reference (`torch.save(model)`,
 training.py:601) resolve to the drop-in classes through the same aliases."""
@@ -15,8 +15,9 @@ _ALIASES = {
     'topaz.denoising.models': 'topaz_b200.denoising.models',
     'topaz.methods': 'topaz_b200.methods',
 }
-# functions patched INTO reference modules that also hold out-of-scope helpers (match_coordinates, 3-D NMS, ...)
-_FUNCTION_PATCHES = {('topaz.algorithms', 'non_maximum_suppression'): ('topaz_b200.algorithms', 'non_maximum_suppression')}
+# functions patched INTO reference modules that also hold out-of-scope helpers (match_coordinates, ...)
+_FUNCTION_PATCHES = {('topaz.algorithms', 'non_maximum_suppression'): ('topaz_b200.algorithms', 'non_maximum_suppression'),
+                     ('topaz.algorithms', 'non_maximum_suppression_3d'): ('topaz_b200.algorithms', 'non_maximum_suppression_3d')}
 
 
 def install(names=None):

@@ -86,7 +86,66 @@ __global__ void nms_suppress_kernel(const float* __restrict__ A, const int* __re
     if (idx < (long long)H * W && state[idx] == UND && ranks_higher(A, p, (int)idx)) state[idx] = SUP;
   }
 }
+
+// ---- flat-delta variant: the reference's 3-D NMS (algorithms.py:66-103) suppresses FLAT indices i + delta with no bounds
+// handling (neighbours wrap across rows / slices).  The delta set is symmetric, so "p suppresses q" == (q - p) in deltas.
+__global__ void nms_flat_pick_kernel(const float* __restrict__ A, const unsigned char* __restrict__ state, long long n,
+                                     const int* __restrict__ deltas, int nd, int* __restrict__ list,
+                                     int* __restrict__ counters, int max_picks) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n || state[q] != UND) return;
+  const float aq = A[q];
+  bool blocked = false;
+  for (int t = 0; t < nd; ++t) {
+    const long long p = q + deltas[t];
+    if (p < 0 || p >= n || p == q) continue;
+    if (state[p] != UND) continue;
+    const float ap = A[p];
+    if (ap > aq || (ap == aq && p > q)) { blocked = true; break; }
+  }
+  if (blocked) { atomicAdd(&counters[1], 1); return; }
+  const int slot = atomicAdd(&counters[0], 1);
+  if (slot < max_picks) list[slot] = (int)q;
+}
+__global__ void nms_flat_suppress_kernel(const float* __restrict__ A, const int* __restrict__ list, int begin, long long n,
+                                         const int* __restrict__ deltas, int nd, unsigned char* __restrict__ state) {
+  const int p = list[begin + blockIdx.x];
+  for (int t = threadIdx.x; t < nd; t += blockDim.x) {
+    const long long idx = (long long)p + deltas[t];
+    if (idx >= 0 && idx < n && state[idx] == UND && ranks_higher(A, p, (int)idx)) state[idx] = SUP;
+  }
+}
 }  // namespace
+
+extern "C" int tpz_nms_flat(const float* scores, long long n, const int* deltas, int num_deltas, float threshold,
+                            unsigned char* state, int* list, int* counters, int max_picks, int* host_num_picks,
+                            void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  TPZ_CHECK(n > 0 && n < (1ll << 31) && num_deltas > 0, "tpz_nms_flat: bad sizes n=%lld deltas=%d", n, num_deltas);
+  TPZ_CUDA(cudaMemsetAsync(counters, 0, 2 * sizeof(int), stream));
+  const int blocks = (int)((n + 255) / 256);
+  nms_init_kernel<<<blocks, 256, 0, stream>>>(scores, (int)n, threshold, state);
+  int picked = 0;
+  for (int round = 0; round < 100000; ++round) {
+    TPZ_CUDA(cudaMemsetAsync(counters + 1, 0, sizeof(int), stream));
+    nms_flat_pick_kernel<<<blocks, 256, 0, stream>>>(scores, state, n, deltas, num_deltas, list, counters, max_picks);
+    int h[2];
+    TPZ_CUDA(cudaMemcpyAsync(h, counters, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    TPZ_CUDA(cudaStreamSynchronize(stream));
+    TPZ_CHECK(h[0] <= max_picks, "tpz_nms_flat: more than max_picks=%d picks", max_picks);
+    const int fresh = h[0] - picked;
+    if (fresh > 0) {
+      nms_commit_kernel<<<tpz_div_up(fresh, 256), 256, 0, stream>>>(list, picked, h[0], state);
+      nms_flat_suppress_kernel<<<fresh, 128, 0, stream>>>(scores, list, picked, n, deltas, num_deltas, state);
+    }
+    picked = h[0];
+    if (h[1] == 0) break;
+    TPZ_CHECK(fresh > 0, "tpz_nms_flat: no progress (NaN scores?)");
+  }
+  TPZ_CUDA(cudaGetLastError());
+  *host_num_picks = picked;
+  return 0;
+}
 
 // scores: device fp32 [H][W]; state: device uint8 [H*W] scratch; list: device int32 [max_picks] (flat indices of the
 // picks, unordered); counters: device int32[2] scratch.  *host_num_picks receives the pick count.  Synchronises the

@@ -8,9 +8,9 @@
 #include "tpz_common.cuh"
 #include "../../include/topaz_b200.h"
 
-#ifndef TPZ_3XTF32
-#define TPZ_3XTF32 1
-#endif
+#include <stdlib.h>
+// X3 = true: error-compensated 3xTF32 (fp32-level accuracy, default).  X3 = false (env TPZ_TRAIN_TF32=1): single-pass TF32,
+// the precision of the reference's own cuDNN path (torch.backends.cudnn.allow_tf32 = True), ~1.3x faster step.
 
 namespace {
 
@@ -30,44 +30,22 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
-// c += a*b with a,b fp32 fragments (compensated)
-__device__ __forceinline__ void mma_f32x3(float (&c)[4], const float (&a)[4], const float (&b)[2]) {
-  uint32_t ah[4], bh[2];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) ah[i] = to_tf32(a[i]);
-#pragma unroll
-  for (int i = 0; i < 2; ++i) bh[i] = to_tf32(b[i]);
-#if TPZ_3XTF32
-  uint32_t al[4], bl[2];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) al[i] = to_tf32(a[i] - __uint_as_float(ah[i]));
-#pragma unroll
-  for (int i = 0; i < 2; ++i) bl[i] = to_tf32(b[i] - __uint_as_float(bh[i]));
-  mma_tf32(c, al, bh);
-  mma_tf32(c, ah, bl);
-#endif
-  mma_tf32(c, ah, bh);
-}
-
 // split an fp32 fragment into TF32 hi (+ lo) parts once; reused by every MMA that consumes the fragment
-template <int N>
+template <bool X3, int N>
 __device__ __forceinline__ void split_tf32(const float (&v)[N], uint32_t (&hi)[N], uint32_t (&lo)[N]) {
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     hi[i] = to_tf32(v[i]);
-#if TPZ_3XTF32
-    lo[i] = to_tf32(v[i] - __uint_as_float(hi[i]));
-#else
-    lo[i] = 0;
-#endif
+    lo[i] = X3 ? to_tf32(v[i] - __uint_as_float(hi[i])) : 0u;
   }
 }
+template <bool X3>
 __device__ __forceinline__ void mma_split(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
                                           const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
-#if TPZ_3XTF32
-  mma_tf32(c, al, bh);
-  mma_tf32(c, ah, bl);
-#endif
+  if (X3) {
+    mma_tf32(c, al, bh);
+    mma_tf32(c, ah, bl);
+  }
   mma_tf32(c, ah, bh);
 }
 
@@ -104,7 +82,7 @@ __global__ void repack_kernel(const float* __restrict__ flat, const RepackDesc* 
 // -------------------------------------------------------------------------------------------------
 constexpr int GBM = 128, GBK = 16, GAS = 20;   // A smem row stride (floats): conflict-free fragment reads
 
-template <int BN, int MODE>   // MODE 0 fwd, 1 dgrad
+template <int BN, int MODE, bool X3>   // MODE 0 fwd, 1 dgrad
 __global__ void __launch_bounds__(256) conv_mma_kernel(MGeom g, const float* __restrict__ src, const float* __restrict__ wpk,
                                                        const float* __restrict__ bias, const float* __restrict__ res,
                                                        int res_H, int res_W, int res_org, int res_stride,
@@ -220,7 +198,7 @@ __global__ void __launch_bounds__(256) conv_mma_kernel(MGeom g, const float* __r
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float bf[2] = {Bs[buf][k8 + tq][wn * 32 + j * 8 + gq], Bs[buf][k8 + tq + 4][wn * 32 + j * 8 + gq]};
-        split_tf32(bf, bh[j], bl[j]);
+        split_tf32<X3>(bf, bh[j], bl[j]);
       }
 #pragma unroll
       for (int i = 0; i < MT; ++i) {
@@ -228,9 +206,9 @@ __global__ void __launch_bounds__(256) conv_mma_kernel(MGeom g, const float* __r
         const float af[4] = {As[buf][rb0 + gq][k8 + tq], As[buf][rb0 + gq + 8][k8 + tq], As[buf][rb0 + gq][k8 + tq + 4],
                              As[buf][rb0 + gq + 8][k8 + tq + 4]};
         uint32_t ah[4], al[4];
-        split_tf32(af, ah, al);
+        split_tf32<X3>(af, ah, al);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) mma_split(acc[i][j], ah, al, bh[j], bl[j]);
+        for (int j = 0; j < 4; ++j) mma_split<X3>(acc[i][j], ah, al, bh[j], bl[j]);
       }
     }
   }
@@ -273,7 +251,7 @@ __global__ void __launch_bounds__(256) conv_mma_kernel(MGeom g, const float* __r
 // -------------------------------------------------------------------------------------------------
 constexpr int WBK = 16;
 
-template <int BT>    // square (BT co) x (BT ci) tile, BT = 64 or 32
+template <int BT, bool X3>    // square (BT co) x (BT ci) tile, BT = 64 or 32
 __global__ void __launch_bounds__(256) wgrad_mma_kernel(MGeom g, const float* __restrict__ x, const float* __restrict__ dy,
                                                         float* __restrict__ dw, int k_per_split) {
   constexpr int STG = 4;
@@ -348,7 +326,7 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(MGeom g, const float* __
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         const float bf[2] = {Bs[buf][k8 + tq][wn * WTN + j * 8 + gq], Bs[buf][k8 + tq + 4][wn * WTN + j * 8 + gq]};
-        split_tf32(bf, bh[j], bl[j]);
+        split_tf32<X3>(bf, bh[j], bl[j]);
       }
 #pragma unroll
       for (int i = 0; i < MI; ++i) {
@@ -356,9 +334,9 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(MGeom g, const float* __
         const float af[4] = {As[buf][k8 + tq][mb + gq], As[buf][k8 + tq][mb + gq + 8], As[buf][k8 + tq + 4][mb + gq],
                              As[buf][k8 + tq + 4][mb + gq + 8]};
         uint32_t ah[4], al[4];
-        split_tf32(af, ah, al);
+        split_tf32<X3>(af, ah, al);
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) mma_split(acc[i][j], ah, al, bh[j], bl[j]);
+        for (int j = 0; j < NJ; ++j) mma_split<X3>(acc[i][j], ah, al, bh[j], bl[j]);
       }
     }
   }
@@ -381,6 +359,20 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(MGeom g, const float* __
 }  // namespace
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+static int g_tf32_mode = -1;   // -1: read the environment on first use
+static bool use_x3() {
+  if (g_tf32_mode < 0) {
+    const char* e = getenv("TPZ_TRAIN_TF32");
+    g_tf32_mode = (e && e[0] == '1') ? 1 : 0;
+  }
+  return g_tf32_mode == 0;
+}
+extern "C" int tpz_train_set_tf32(int single_pass) {
+  int prev = use_x3() ? 0 : 1;
+  g_tf32_mode = single_pass ? 1 : 0;
+  return prev;
+}
 
 static MGeom mgeom(int N, int H, int W, int Ci, int Ho, int Wo, int Co, int kh, int kw, int stride, int dil, int org) {
   MGeom g; g.N = N; g.H = H; g.W = W; g.Ci = Ci; g.Ho = Ho; g.Wo = Wo; g.Co = Co; g.kh = kh; g.kw = kw;
@@ -405,12 +397,12 @@ extern "C" int tpz_conv_fwd_mma(const float* x, int N, int H, int W, int Ci, con
   const long long M = (long long)N * Ho * Wo;
   if (Co % 64 == 0) {
     dim3 grid(tpz_div_up(M, GBM), Co / 64);
-    conv_mma_kernel<64, 0><<<grid, 256, 0, ST(stream)>>>(g, x, w_fwd_packed, bias, res, res_H, res_W, res_org, res_stride,
-                                                         nullptr, y, relu, 0);
+    if (use_x3()) conv_mma_kernel<64, 0, true><<<grid, 256, 0, ST(stream)>>>(g, x, w_fwd_packed, bias, res, res_H, res_W, res_org, res_stride, nullptr, y, relu, 0);
+    else conv_mma_kernel<64, 0, false><<<grid, 256, 0, ST(stream)>>>(g, x, w_fwd_packed, bias, res, res_H, res_W, res_org, res_stride, nullptr, y, relu, 0);
   } else {
     dim3 grid(tpz_div_up(M, GBM), Co / 32);
-    conv_mma_kernel<32, 0><<<grid, 256, 0, ST(stream)>>>(g, x, w_fwd_packed, bias, res, res_H, res_W, res_org, res_stride,
-                                                         nullptr, y, relu, 0);
+    if (use_x3()) conv_mma_kernel<32, 0, true><<<grid, 256, 0, ST(stream)>>>(g, x, w_fwd_packed, bias, res, res_H, res_W, res_org, res_stride, nullptr, y, relu, 0);
+    else conv_mma_kernel<32, 0, false><<<grid, 256, 0, ST(stream)>>>(g, x, w_fwd_packed, bias, res, res_H, res_W, res_org, res_stride, nullptr, y, relu, 0);
   }
   TPZ_CUDA(cudaGetLastError());
   return 0;
@@ -424,12 +416,12 @@ extern "C" int tpz_conv_dgrad_mma(const float* dy, int N, int Ho, int Wo, int Co
   const long long M = (long long)N * H * W;
   if (Ci % 64 == 0) {
     dim3 grid(tpz_div_up(M, GBM), Ci / 64);
-    conv_mma_kernel<64, 1><<<grid, 256, 0, ST(stream)>>>(g, dy, w_dg_packed, nullptr, nullptr, 0, 0, 0, 1, relu_mask, dx, 0,
-                                                         accumulate);
+    if (use_x3()) conv_mma_kernel<64, 1, true><<<grid, 256, 0, ST(stream)>>>(g, dy, w_dg_packed, nullptr, nullptr, 0, 0, 0, 1, relu_mask, dx, 0, accumulate);
+    else conv_mma_kernel<64, 1, false><<<grid, 256, 0, ST(stream)>>>(g, dy, w_dg_packed, nullptr, nullptr, 0, 0, 0, 1, relu_mask, dx, 0, accumulate);
   } else {
     dim3 grid(tpz_div_up(M, GBM), Ci / 32);
-    conv_mma_kernel<32, 1><<<grid, 256, 0, ST(stream)>>>(g, dy, w_dg_packed, nullptr, nullptr, 0, 0, 0, 1, relu_mask, dx, 0,
-                                                         accumulate);
+    if (use_x3()) conv_mma_kernel<32, 1, true><<<grid, 256, 0, ST(stream)>>>(g, dy, w_dg_packed, nullptr, nullptr, 0, 0, 0, 1, relu_mask, dx, 0, accumulate);
+    else conv_mma_kernel<32, 1, false><<<grid, 256, 0, ST(stream)>>>(g, dy, w_dg_packed, nullptr, nullptr, 0, 0, 0, 1, relu_mask, dx, 0, accumulate);
   }
   TPZ_CUDA(cudaGetLastError());
   return 0;
@@ -450,8 +442,13 @@ extern "C" int tpz_conv_wgrad_mma(const float* x, int N, int H, int W, int Ci, c
   if (kps < 512) kps = 512;
   splits = (int)((P + kps - 1) / kps);
   dim3 grid(mt, nt, taps * splits);
-  if (BT == 32) wgrad_mma_kernel<32><<<grid, 256, 0, ST(stream)>>>(g, x, dy, dw, (int)kps);
-  else wgrad_mma_kernel<64><<<grid, 256, 0, ST(stream)>>>(g, x, dy, dw, (int)kps);
+  if (BT == 32) {
+    if (use_x3()) wgrad_mma_kernel<32, true><<<grid, 256, 0, ST(stream)>>>(g, x, dy, dw, (int)kps);
+    else wgrad_mma_kernel<32, false><<<grid, 256, 0, ST(stream)>>>(g, x, dy, dw, (int)kps);
+  } else {
+    if (use_x3()) wgrad_mma_kernel<64, true><<<grid, 256, 0, ST(stream)>>>(g, x, dy, dw, (int)kps);
+    else wgrad_mma_kernel<64, false><<<grid, 256, 0, ST(stream)>>>(g, x, dy, dw, (int)kps);
+  }
   TPZ_CUDA(cudaGetLastError());
   return 0;
 }

@@ -335,6 +335,12 @@ def adam_step(fp: FlatParams, lr, b1, b2, eps, l2):
                                    fp.step, float(l2), 1.0, _s()))
 
 
+def set_tf32(single_pass: bool) -> bool:
+    """Select the training-conv precision: False (default) = 3xTF32 (fp32-level), True = single-pass TF32 (what the
+    reference's cuDNN path computes with allow_tf32=True).  Returns the previous setting."""
+    return bool(_lib.lib().tpz_train_set_tf32(1 if single_pass else 0))
+
+
 def read_back(dev_vec: torch.Tensor, host_vec: torch.Tensor):
     """Single host synchronisation of a training step: copy the 5 loss/metric floats to pinned memory."""
     host_vec.copy_(dev_vec, non_blocking=True)
