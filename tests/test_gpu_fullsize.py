@@ -26,8 +26,8 @@ def test_resnet8_u64_4096_windows_vs_oracle_and_translation_equivariance():
     from topaz_b200.extract import score_arrays
     g = gold('resnet8_u64_pretrained'); sd = weights_of(g)
     m = _classifier(64)
-    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}); m.cuda(); m.eval(); m.fill()
-    S = 4096
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})      # score_arrays fills the model itself, like
+    S = 4096                                                                   # extract.score_images (extract.py:231-232)
     x = np.random.default_rng(1000).standard_normal((S, S)).astype(np.float32)
     (y,) = list(score_arrays(m, [x]))
     assert y.shape == (S, S) and y.dtype == np.float32 and np.isfinite(y).all()
@@ -46,6 +46,7 @@ def test_resnet8_u64_4096_windows_vs_oracle_and_translation_equivariance():
     # translation equivariance: scoring the image shifted by (37, 101) gives the shifted scores away from the borders
     # (different tile decomposition, same arithmetic per output pixel)
     di, dj = 37, 101
+    m.unfill()
     (y2,) = list(score_arrays(m, [np.ascontiguousarray(x[di:, dj:])]))
     a = y[di + halo:S - halo, dj + halo:S - halo]
     b = y2[halo:S - di - halo, halo:S - dj - halo]
