@@ -24,22 +24,51 @@ def score_images(model: Union[torch.nn.Module, str], paths: Union[List[str], Ite
         model.eval()
         model.fill()
         model.cuda()
-        for path in paths:
-            image = load_image(path, make_image=False, return_header=False)
-            is_3d = len(image.shape) == 3
-            image = torch.from_numpy(np.ascontiguousarray(image)).float()
-            image = image.unsqueeze(0).unsqueeze(0)
-            if patch_size:
+        if patch_size:
+            for path, image in _prefetch(paths):
+                is_3d = len(image.shape) == 3
+                image = torch.from_numpy(np.ascontiguousarray(image)).float()
+                image = image.unsqueeze(0).unsqueeze(0)
                 patch_overlap = model.width // 2
                 scores = predict_in_patches(model, image, patch_size + 2 * patch_overlap, is_3d=is_3d, use_cuda=True)
-                scores = scores[0, 0]
-            else:
-                with torch.no_grad():
-                    scores = model(image.cuda(non_blocking=True)).data[0, 0].cpu().numpy()
-            yield path, scores
+                yield path, scores[0, 0]
+        else:
+            # file reads (background thread), pinned H2D / D2H (side streams) and the network overlap across images
+            names = []
+
+            def images():
+                for path, image in _prefetch(paths):
+                    names.append(path)
+                    yield image
+            for i, scores in enumerate(_score_stream(model, images())):
+                yield names[i], scores
     else:
         for path in paths:
             yield path, load_image(path, make_image=False, return_header=False)
+
+
+def _prefetch(paths, depth: int = 2):
+    """Read micrographs one ahead of the consumer on a background thread (file I/O and numpy decoding release the GIL)."""
+    import queue
+    import threading
+    q = queue.Queue(maxsize=depth)
+    end = object()
+
+    def reader():
+        try:
+            for path in paths:
+                q.put((path, load_image(path, make_image=False, return_header=False)))
+            q.put(end)
+        except BaseException as e:           # surface I/O errors in the consumer
+            q.put(e)
+    threading.Thread(target=reader, daemon=True).start()
+    while True:
+        item = q.get()
+        if item is end:
+            return
+        if isinstance(item, BaseException):
+            raise item
+        yield item
 
 
 def score_arrays(model: torch.nn.Module, images: Iterable[np.ndarray], device: int = 0, pinned: bool = True):
@@ -47,6 +76,10 @@ def score_arrays(model: torch.nn.Module, images: Iterable[np.ndarray], device: i
     side streams so copies of image i+1 / i-1 overlap the network of image i."""
     torch.cuda.set_device(device)
     model.eval(); model.fill(); model.cuda()
+    return _score_stream(model, images, pinned)
+
+
+def _score_stream(model: torch.nn.Module, images: Iterable[np.ndarray], pinned: bool = True):
     copy_in, copy_out = torch.cuda.Stream(), torch.cuda.Stream()
     main = torch.cuda.current_stream()
     pending = None
