@@ -517,3 +517,86 @@ def nms3d(x: np.ndarray, r, scale: float = 1.0, threshold: float = -np.inf):
             t = i + deltas
             S[t[(t >= 0) & (t < n)]] = True
     return np.asarray(scores, dtype=np.float32), np.asarray(coords, dtype=np.int32).reshape(-1, 3)
+
+
+# --------------------------------------------------------------------------------------
+# Preprocessing: Fourier-crop downsample, GMM normalisation
+# --------------------------------------------------------------------------------------
+
+def downsample(x: np.ndarray, factor=1, shape=None) -> np.ndarray:
+    """utils/image.py:38-61: rfft2, keep rows [0:m//2] + [-m//2:] and columns [0:n//2+1], rescale, irfft2."""
+    if shape is None:
+        shape = (int(x.shape[-2] / factor), int(x.shape[-1] / factor))
+    m, n = shape
+    F = np.fft.rfft2(x)
+    F = np.concatenate([F[..., 0:m // 2, 0:n // 2 + 1], F[..., -m // 2:, 0:n // 2 + 1]], axis=0)
+    F = F * ((n * m) / (x.shape[-2] * x.shape[-1]))
+    return np.fft.irfft2(F, s=shape).astype(x.dtype)
+
+
+def _beta_logpdf(p, a, b):
+    import math
+    xlogy = lambda c, v: 0.0 if c == 0 else c * math.log(v)
+    return xlogy(a - 1, p) + xlogy(b - 1, 1 - p) + math.lgamma(a + b) - math.lgamma(a) - math.lgamma(b)
+
+
+def gmm_fit(x: torch.Tensor, pi, split, alpha, beta, scale=1, tol=1e-3, num_iters=100):
+    """stats.py:122-214 with share_var=True, in float32 tensors like the reference."""
+    mu = torch.mean(x)
+    pi = torch.as_tensor(pi)
+    p0 = (x <= split).float()
+    p1 = 1 - p0
+
+    def m_step(p0, p1):
+        s0, s1 = torch.sum(p0), torch.sum(p1)
+        mu0 = torch.sum(x * p0) / s0 if s0 > 0 else mu
+        mu1 = torch.sum(x * p1) / s1 if s1 > 0 else mu
+        var = torch.mean(p0 * (x - mu0) ** 2 + p1 * (x - mu1) ** 2)
+        return mu0, mu1, var
+
+    def e_step(mu0, mu1, var, pi):
+        l0 = -(x - mu0) ** 2 / 2 / var - 0.5 * torch.log(2 * np.pi * var) + torch.log1p(-pi)
+        l1 = -(x - mu1) ** 2 / 2 / var - 0.5 * torch.log(2 * np.pi * var) + torch.log(pi)
+        ma = torch.max(l0, l1)
+        Z = ma + torch.log(torch.exp(l0 - ma) + torch.exp(l1 - ma))
+        return l0, l1, Z, scale * torch.sum(Z) + _beta_logpdf(float(pi), alpha, beta)
+
+    mu0, mu1, var = m_step(p0, p1)
+    l0, l1, Z, logp = e_step(mu0, mu1, var, pi)
+    logp_cur = logp
+    for _ in range(1, num_iters + 1):
+        p0, p1 = torch.exp(l0 - Z), torch.exp(l1 - Z)
+        s = torch.sum(p1)
+        a, b = alpha + s, beta + p1.numel() - s
+        pi = (a - 1) / (a + b - 2)
+        mu0, mu1, var = m_step(p0, p1)
+        l0, l1, Z, logp = e_step(mu0, mu1, var, pi)
+        if logp - logp_cur <= tol:
+            break
+        logp_cur = logp
+    return logp, mu0, var, mu1, var, pi
+
+
+def norm_fit(x: np.ndarray, alpha=900, beta=1, scale=1, num_iters=100):
+    """stats.py:86-119."""
+    pis = np.array([0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 0.95, 0.98, 1])
+    splits = np.quantile(x, 1 - pis)
+    logps, mus, stds = np.zeros(len(pis)), np.zeros(len(pis)), np.zeros(len(pis))
+    xt = torch.from_numpy(np.ascontiguousarray(x))
+    for i in range(len(pis)):
+        if pis[i] == 1:
+            mu, var = xt.mean(), xt.var()
+            quirk = float(alpha) if beta == 1 else (0.0 if beta > 1 else np.inf)          # beta.PDF (not logpdf) at 1, stats.py:106
+            logp = scale * torch.sum(-(xt - mu) ** 2 / 2 / var - 0.5 * torch.log(2 * np.pi * var)) + quirk
+            pi = torch.as_tensor(1.0)
+        else:
+            logp, _, _, mu, var, pi = gmm_fit(xt, pis[i], splits[i], alpha, beta, scale, 1e-3, num_iters)
+        pis[i], logps[i], mus[i], stds[i] = pi.item(), logp.item(), mu.item(), np.sqrt(var.item())
+    i = int(np.argmax(logps))
+    return mus[i], stds[i], pis[i], logps[i], mus, stds, pis, logps
+
+
+def gmm_normalize(x: np.ndarray, alpha=900, beta=1, num_iters=100):
+    """stats.normalize(method='gmm', sample=1) (stats.py:49-83) -> (normalised float32 image, mu, std, pi)."""
+    mu, std, pi, *_ = norm_fit(x, alpha, beta, 1, num_iters)
+    return ((x - mu) / std).astype(np.float32), mu, std, pi

@@ -158,9 +158,51 @@ def affine(x, stats, inverse=False, out=None):
     return y
 
 
+def gemm_f32(A, B, C):
+    C.copy_((A.double() @ B.double()).float())
+    return C
+
+
+def gmm_sums(x, mode, params8, work7=None):
+    """tpz_gmm_sums in float64 numpy."""
+    import numpy as np
+    shift, split, mu0, mu1, var0, var1, lp0, lp1 = [float(v) for v in params8]
+    xf = x.numpy().ravel()
+    xc = xf.astype(np.float64) - shift
+    if mode == 0:
+        p0 = (xf <= np.float32(split)).astype(np.float64); p1 = 1.0 - p0; Z = np.zeros_like(xc)
+    else:
+        l0 = -(xc - mu0) ** 2 / 2 / var0 - 0.5 * np.log(2 * np.pi * var0) + lp0
+        l1 = -(xc - mu1) ** 2 / 2 / var1 - 0.5 * np.log(2 * np.pi * var1) + lp1
+        ma = np.maximum(l0, l1)
+        Z = ma + np.log(np.exp(l0 - ma) + np.exp(l1 - ma))
+        p0, p1 = np.exp(l0 - Z), np.exp(l1 - Z)
+    return np.array([Z.sum(), p0.sum(), p1.sum(), (p0 * xc).sum(), (p1 * xc).sum(), (p0 * xc * xc).sum(), (p1 * xc * xc).sum()])
+
+
+def select_hist(x, level, prefixes=()):
+    import numpy as np
+    b = x.numpy().ravel().view(np.uint32).astype(np.uint64)
+    key = np.where(b & 0x80000000, (~b) & 0xFFFFFFFF, b | 0x80000000).astype(np.uint64)
+    if level == 0:
+        return np.bincount((key >> 20).astype(np.int64), minlength=4096).astype(np.int64)
+    rows = []
+    for p in prefixes:
+        if level == 1:
+            sel = key[(key >> 20) == p]; rows.append(np.bincount(((sel >> 8) & 0xFFF).astype(np.int64), minlength=4096))
+        else:
+            sel = key[(key >> 8) == p]; rows.append(np.bincount((sel & 0xFF).astype(np.int64), minlength=256))
+    return np.stack(rows).astype(np.int64)
+
+
+def to_device(t):
+    return t
+
+
 @contextlib.contextmanager
 def patched():
-    names = ['tc_conv', 'conv_first', 'im2col_first', 'filter_f32', 'conv_last', 'maxpool2', 'upsample_nearest', 'meanstd', 'affine']
+    names = ['tc_conv', 'conv_first', 'im2col_first', 'filter_f32', 'conv_last', 'maxpool2', 'upsample_nearest', 'meanstd', 'affine',
+             'gemm_f32', 'gmm_sums', 'select_hist', 'to_device']
     saved = {n: getattr(ops, n) for n in names}
     saved['require_cuda'] = ops.require_cuda
     try:

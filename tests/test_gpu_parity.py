@@ -313,3 +313,38 @@ def test_gpu_nms3d_bit_exact():
     s_ref, c_ref = O.nms3d(x, 5, 1.0, 1.0)
     s, c = non_maximum_suppression_3d(x, 5, threshold=1.0)
     assert len(s) > 300 and np.array_equal(c, c_ref) and np.array_equal(s, s_ref)
+
+
+def test_downsample_and_gmm_normalize_gpu():
+    """Fourier-crop downsample (utils/image.py:38-61) and GMM normalisation (stats.py:36-214) on the
+    GPU vs the reference goldens and, at larger sizes, the oracle."""
+    from topaz_b200 import preprocess, stats
+    g = gold('preprocess')
+    x = g['x']
+    for tag, kw in [('f2', dict(factor=2)), ('f4', dict(factor=4)), ('f3', dict(factor=3)), ('s', dict(shape=(37, 50))),
+                    ('f1p7', dict(factor=1.7))]:
+        y = preprocess.downsample(x, **kw)
+        ref = g['ds.' + tag]
+        assert y.shape == ref.shape and y.dtype == np.float32
+        assert np.abs(y - ref).max() < 1e-4 * np.abs(ref).max(), tag
+    big = (100 + 5 * np.random.default_rng(8).standard_normal((1900, 2100))).astype(np.float32)
+    for kw in (dict(factor=4), dict(factor=8), dict(shape=(333, 512))):
+        y, ref = preprocess.downsample(big, **kw), O.downsample(big, **kw)
+        assert y.shape == ref.shape and np.abs(y - ref).max() < 1e-4 * np.abs(ref).max()
+    qs = [0.0, 0.02, 0.05, 0.1, 0.5, 0.77, 0.9, 1.0]
+    np.testing.assert_allclose(stats.quantiles(torch.from_numpy(big).cuda().view(-1), qs), np.quantile(big.astype(np.float64), qs), rtol=1e-7)
+    for tag in 'abc':
+        img = g[f'n.{tag}.x']
+        y, md = stats.normalize(img, alpha=float(g[f'n.{tag}.alpha']), beta=float(g[f'n.{tag}.beta']),
+                                num_iters=int(g[f'n.{tag}.iters']), method='gmm')
+        assert abs(md['mu'] - g[f'n.{tag}.mu']) < 1e-4 * abs(md['mu']) and abs(md['std'] - g[f'n.{tag}.std']) < 1e-3 * md['std'], tag
+        assert abs(md['pi'] - g[f'n.{tag}.pi']) < 1e-3
+        np.testing.assert_allclose(md['logps'], g[f'n.{tag}.logps'], rtol=2e-5)
+        assert y.dtype == np.float32 and np.abs(y - g[f'n.{tag}.y']).max() < 1e-3
+    # a 480x512 micrograph-like image with a real two-component structure (Beta(2,2) prior so the mixture wins)
+    gg = np.random.default_rng(77)
+    img = (50 + 3 * gg.standard_normal((480, 512)) + 9 * (gg.random((480, 512)) < 0.2)).astype(np.float32)
+    y, md = stats.normalize(img, alpha=2, beta=2, num_iters=60, method='gmm')
+    yr, mu, std, pi = O.gmm_normalize(img, 2, 2, 60)
+    assert abs(md['mu'] - mu) < 1e-3 * abs(mu) and abs(md['std'] - std) < 1e-3 * std and abs(md['pi'] - pi) < 1e-3
+    assert np.abs(y - yr).max() < 1e-3 * np.abs(yr).max()

@@ -190,3 +190,31 @@ def test_fcnn_and_affine_denoisers_sim():
         yf = mf(torch.from_numpy(g['x'])).numpy(); ya = ma(torch.from_numpy(g['x'])).numpy()
     mx, l2 = rel_err(yf, g['y_fcnn']); assert mx < TOL_SEEDED and l2 < TOL_SEEDED, (mx, l2)
     mx, l2 = rel_err(ya, g['y_affine']); assert mx < 1e-5, (mx, l2)
+
+
+def test_preprocess_downsample_and_gmm_normalize_host_logic():
+    """Operator construction of the Fourier-crop downsample, radix-select quantiles and the EM driver of the GMM
+    normalisation, with the kernels replaced by the CPU simulation, against the reference goldens."""
+    from topaz_b200 import preprocess, stats
+    g = gold('preprocess')
+    x = g['x']
+    with sim_backend.patched():
+        for tag, kw in [('f2', dict(factor=2)), ('f4', dict(factor=4)), ('f3', dict(factor=3)), ('s', dict(shape=(37, 50))),
+                        ('f1p7', dict(factor=1.7))]:
+            y = preprocess.downsample(x, **kw)
+            ref = g['ds.' + tag]
+            assert y.shape == ref.shape and y.dtype == np.float32
+            assert np.abs(y - ref).max() < 1e-4 * np.abs(ref).max(), tag
+        xt = torch.from_numpy(x)
+        qs = [0.0, 0.02, 0.05, 0.1, 0.5, 0.77, 0.9, 1.0]
+        np.testing.assert_allclose(stats.quantiles(xt.view(-1), qs), np.quantile(x.astype(np.float64), qs), rtol=1e-7)
+        for tag in 'abc':
+            img = g[f'n.{tag}.x']
+            y, md = stats.normalize(img, alpha=float(g[f'n.{tag}.alpha']), beta=float(g[f'n.{tag}.beta']),
+                                    num_iters=int(g[f'n.{tag}.iters']), method='gmm')
+            assert abs(md['mu'] - g[f'n.{tag}.mu']) < 1e-4 * abs(md['mu']) and abs(md['std'] - g[f'n.{tag}.std']) < 1e-3 * md['std'], tag
+            assert abs(md['pi'] - g[f'n.{tag}.pi']) < 1e-3
+            np.testing.assert_allclose(md['logps'], g[f'n.{tag}.logps'], rtol=2e-5)
+            assert y.dtype == np.float32 and np.abs(y - g[f'n.{tag}.y']).max() < 1e-3
+            ya, mda = stats.normalize(img, method='affine')
+            assert abs(mda['mu'] - img.astype(np.float64).mean()) < 1e-4 and mda['pi'] == 1

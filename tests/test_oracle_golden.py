@@ -111,3 +111,17 @@ def test_nms3d_bit_exact_vs_reference_golden():
     for tag in 'abcd':
         s, c = O.nms3d(g[f'{tag}.x'], float(g[f'{tag}.r']), float(g[f'{tag}.scale']), float(g[f'{tag}.thr']))
         assert len(s) > 0 and np.array_equal(c, g[f'{tag}.coords']) and np.array_equal(s, g[f'{tag}.scores']), tag
+
+
+def test_downsample_and_gmm_normalize_vs_reference_golden():
+    g = gold('preprocess')
+    x = g['x']
+    for tag, kw in [('f2', dict(factor=2)), ('f4', dict(factor=4)), ('f3', dict(factor=3)), ('s', dict(shape=(37, 50))),
+                    ('f1p7', dict(factor=1.7))]:
+        y = O.downsample(x, **kw)
+        assert y.shape == g['ds.' + tag].shape and np.abs(y - g['ds.' + tag]).max() < 1e-4 * np.abs(g['ds.' + tag]).max()
+    for tag in 'abc':
+        y, mu, std, pi = O.gmm_normalize(g[f'n.{tag}.x'], float(g[f'n.{tag}.alpha']), float(g[f'n.{tag}.beta']), int(g[f'n.{tag}.iters']))
+        assert abs(mu - g[f'n.{tag}.mu']) < 1e-5 * abs(mu) and abs(std - g[f'n.{tag}.std']) < 1e-4 * std, tag
+        assert abs(pi - g[f'n.{tag}.pi']) < 1e-4
+        assert np.abs(y - g[f'n.{tag}.y']).max() < 1e-3

@@ -145,6 +145,56 @@ def main():
                 print(json.dumps(dict(workload=f'UDenoiseNet3D Denoise3D.denoise({S}^3, patch 96, padding 48), {npatch} patches of 192^3, host numpy in/out',
                                       n_gpus=world, ms_total=ms, ms_per_patch=ms / max(1, hi - lo), mvox_s=S ** 3 / 1e6 / (ms / 1e3),
                                       tflops=npatch * 4.784 / (ms / 1e3), finite=bool(np.isfinite(y).all()))))
+        elif wl == 'preprocess':
+            # `topaz preprocess -s 8`: Fourier-crop downsample + GMM normalisation of a K3-sized micrograph; then NMS timing
+            from topaz_b200 import preprocess, stats
+            from topaz_b200.algorithms import non_maximum_suppression
+            sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+            from oracle import topaz_oracle as O
+            gq = np.random.default_rng(6000 + rank)
+            big = (100 + 5 * gq.standard_normal((7676, 7420)) + 10 * (gq.random((7676, 7420)) < 0.15)).astype(np.float32)
+            xd = torch.from_numpy(big).cuda()
+            preprocess.downsample_device(xd, 8); torch.cuda.synchronize()      # builds + caches the operators
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                sm = preprocess.downsample_device(xd, 8)
+            e1.record(); torch.cuda.synchronize(); ds_ms = e0.elapsed_time(e1) / 5
+            t0 = time.perf_counter(); small_h = preprocess.downsample(big, 8); ds_host_ms = (time.perf_counter() - t0) * 1e3
+            t0 = time.perf_counter(); ref = O.downsample(big, 8); cpu_ds_ms = (time.perf_counter() - t0) * 1e3
+            err = float(np.abs(small_h - ref).max() / np.abs(ref).max())
+            stats.normalize_device(sm, method='gmm'); torch.cuda.synchronize()
+            t0 = time.perf_counter(); yn, md = stats.normalize_device(sm, method='gmm'); torch.cuda.synchronize()
+            gmm_ms = (time.perf_counter() - t0) * 1e3
+            t0 = time.perf_counter(); yr, mu, std, pi = O.gmm_normalize(sm.cpu().numpy()); cpu_gmm_ms = (time.perf_counter() - t0) * 1e3
+            full = torch.from_numpy(big[:4096, :4096].copy()).cuda()
+            stats.normalize_device(full, method='gmm', alpha=2, beta=2); torch.cuda.synchronize()
+            t0 = time.perf_counter(); _, md2 = stats.normalize_device(full, method='gmm', alpha=2, beta=2); torch.cuda.synchronize()
+            gmm_full_ms = (time.perf_counter() - t0) * 1e3
+            if rank == 0:
+                print(json.dumps(dict(workload='preprocess: downsample(7676x7420, 8) -> 959x927, then stats.normalize(method=gmm)',
+                                      downsample_device_ms=ds_ms, downsample_host_in_out_ms=ds_host_ms, cpu_oracle_downsample_ms=cpu_ds_ms,
+                                      downsample_max_rel_err=err, gmm_normalize_ms=gmm_ms, cpu_oracle_gmm_ms=cpu_gmm_ms,
+                                      mu=[md['mu'], mu], std=[md['std'], std], gmm_normalize_4096sq_ms=gmm_full_ms, pi_4096=md2['pi'])))
+        elif wl == 'nms':
+            from topaz_b200.algorithms import non_maximum_suppression, non_maximum_suppression_3d
+            sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+            from oracle import topaz_oracle as O
+            gq = np.random.default_rng(7000)
+            sc = gq.standard_normal((4096, 4096)).astype(np.float32)
+            sd = torch.from_numpy(sc).cuda()
+            res = {}
+            for r, thr in [(8, 1.5), (8, -6.0), (14, 0.0)]:
+                non_maximum_suppression(sd, r, thr); torch.cuda.synchronize()
+                t0 = time.perf_counter(); s, c = non_maximum_suppression(sd, r, thr); res[f'2d_r{r}_thr{thr}_ms'] = (time.perf_counter() - t0) * 1e3
+                res[f'2d_r{r}_thr{thr}_picks'] = len(s)
+            t0 = time.perf_counter(); s_ref, c_ref = O.nms(sc, 8, 1.5); res['cpu_oracle_2d_r8_thr1.5_ms'] = (time.perf_counter() - t0) * 1e3
+            vol = torch.from_numpy(gq.standard_normal((128, 512, 512)).astype(np.float32)).cuda()
+            non_maximum_suppression_3d(vol, 6, threshold=1.5); torch.cuda.synchronize()
+            t0 = time.perf_counter(); s3, c3 = non_maximum_suppression_3d(vol, 6, threshold=1.5); res['3d_128x512x512_r6_thr1.5_ms'] = (time.perf_counter() - t0) * 1e3
+            res['3d_picks'] = len(s3)
+            if rank == 0:
+                print(json.dumps(dict(workload='greedy NMS on 4096^2 score maps / a 128x512x512 volume (host-visible time incl. result read-back)', **res)))
     if world > 1:
         dist.destroy_process_group()
 

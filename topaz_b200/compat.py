@@ -17,7 +17,11 @@ _ALIASES = {
 }
 # functions patched INTO reference modules that also hold out-of-scope helpers (match_coordinates, ...)
 _FUNCTION_PATCHES = {('topaz.algorithms', 'non_maximum_suppression'): ('topaz_b200.algorithms', 'non_maximum_suppression'),
-                     ('topaz.algorithms', 'non_maximum_suppression_3d'): ('topaz_b200.algorithms', 'non_maximum_suppression_3d')}
+                     ('topaz.algorithms', 'non_maximum_suppression_3d'): ('topaz_b200.algorithms', 'non_maximum_suppression_3d'),
+                     ('topaz.utils.image', 'downsample'): ('topaz_b200.preprocess', 'downsample'),
+                     ('topaz.stats', 'normalize'): ('topaz_b200.stats', 'normalize'),
+                     ('topaz.stats', 'norm_fit'): ('topaz_b200.stats', 'norm_fit'),
+                     ('topaz.stats', 'gmm_fit'): ('topaz_b200.stats', 'gmm_fit')}
 
 
 def install(names=None):

@@ -408,6 +408,22 @@ extern "C" int tpz_conv_fwd_mma(const float* x, int N, int H, int W, int Ci, con
   return 0;
 }
 
+// Plain row-major fp32 product C[M][N] = A[M][K] * B[K][N] on the same gather-GEMM kernel (a 1x1 "convolution" over M
+// pixels), always error-compensated 3xTF32.  Used by the Fourier-crop downsample (utils/image.py:38-61).
+extern "C" int tpz_gemm_f32(const float* A, long long M, int K, const float* B, int N, float* Cout, void* stream) {
+  TPZ_CHECK(K % 16 == 0 && N % 32 == 0 && M > 0 && M < (1ll << 31), "tpz_gemm_f32: needs K%%16==0, N%%32==0 (M=%lld K=%d N=%d)", M, K, N);
+  const MGeom g = mgeom(1, 1, (int)M, K, 1, (int)M, N, 1, 1, 1, 1, 0);
+  if (N % 64 == 0) {
+    dim3 grid(tpz_div_up(M, GBM), N / 64);
+    conv_mma_kernel<64, 0, true><<<grid, 256, 0, ST(stream)>>>(g, A, B, nullptr, nullptr, 0, 0, 0, 1, nullptr, Cout, 0, 0);
+  } else {
+    dim3 grid(tpz_div_up(M, GBM), N / 32);
+    conv_mma_kernel<32, 0, true><<<grid, 256, 0, ST(stream)>>>(g, A, B, nullptr, nullptr, 0, 0, 0, 1, nullptr, Cout, 0, 0);
+  }
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int tpz_conv_dgrad_mma(const float* dy, int N, int Ho, int Wo, int Co, const float* w_dg_packed, int Ci, int kh,
                                   int kw, int stride, int dil, int org, const float* relu_mask, int accumulate, float* dx,
                                   int H, int W, void* stream) {

@@ -301,6 +301,43 @@ def affine(x: torch.Tensor, stats: torch.Tensor, inverse: bool = False, out: Opt
     return y
 
 
+def gemm_f32(A: torch.Tensor, B: torch.Tensor, C: torch.Tensor):
+    """C[M][N] = A[M][K] @ B[K][N], contiguous fp32 device tensors, 3xTF32 tensor-core product (K%16==0, N%32==0)."""
+    M, K = A.shape
+    K2, N = B.shape
+    assert K == K2 and tuple(C.shape) == (M, N) and A.is_contiguous() and B.is_contiguous() and C.is_contiguous()
+    _count(1); check(_lib.lib().tpz_gemm_f32(_ptr(A), M, K, _ptr(B), N, _ptr(C), _stream()))
+    return C
+
+
+def gmm_sums(x: torch.Tensor, mode: int, params8, work7: Optional[torch.Tensor] = None):
+    """One GMM pass over a flat fp32 device tensor -> numpy float64[7] (see include/topaz_b200.h: tpz_gmm_sums)."""
+    import numpy as np
+    p = np.ascontiguousarray(params8, dtype=np.float64)
+    buf = work7 if work7 is not None else torch.empty(7, dtype=torch.float64, device=x.device)
+    _count(1); check(_lib.lib().tpz_gmm_sums(_ptr(x), x.numel(), int(mode), p.ctypes.data, _ptr(buf), _stream()))
+    return buf.cpu().numpy()
+
+
+def select_hist(x: torch.Tensor, level: int, prefixes=()):
+    """Radix-select histogram pass (tpz_select_hist) -> numpy int64 [4096] (level 0) or [len(prefixes), 4096 | 256]."""
+    import numpy as np
+    n_pref = len(prefixes)
+    bins = 4096 if level < 2 else 256
+    rows = 1 if level == 0 else n_pref
+    hist = torch.empty(rows * bins, dtype=torch.int32, device=x.device)
+    pref = torch.tensor(list(prefixes), dtype=torch.int64).to(torch.int32).to(x.device) if n_pref else None
+    _count(1); check(_lib.lib().tpz_select_hist(_ptr(x), x.numel(), int(level), _ptr(pref) if n_pref else None, n_pref,
+                                                _ptr(hist), _stream()))
+    h = hist.cpu().numpy().astype(np.int64)
+    return h if level == 0 else h.reshape(rows, bins)
+
+
+def to_device(t: torch.Tensor) -> torch.Tensor:
+    """Host -> current CUDA device (separate hook so the CPU simulation of the kernels can keep tensors on the host)."""
+    return t if t.is_cuda else t.cuda()
+
+
 def filter_f32(x: torch.Tensor, f: torch.Tensor, bias: float = 0.0) -> torch.Tensor:
     """Same-padded 1->1 fp32 convolution of x [N,D,H,W] with filter f [kd,kh,kw] (both on device)."""
     N, D, H, W = x.shape

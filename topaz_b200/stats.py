@@ -1,17 +1,186 @@
-"""Drop-in mirror of topaz.stats.normalize(method='affine') (reference stats.py:36-46): (x - mean) / std (population
-std) as float32 + the metadata dict; statistics and the rescale run on the GPU (tpz_meanstd / tpz_affine).
-The GMM normalisation (stats.py:86-214) is outside the B200 hot path."""
+"""GPU drop-in for topaz.stats.normalize / norm_fit / gmm_fit (reference stats.py:36-214).
+
+method='affine' (stats.py:38-46): (x - mean) / std (population std) as float32 + metadata, statistics and rescale on the
+GPU (tpz_meanstd / tpz_affine).
+
+method='gmm' (stats.py:49-214): 12 initialisations of a shared-variance 2-component Gaussian mixture with a Beta(alpha,
+beta) prior on the mixing weight, EM until the log-posterior improves by <= 1e-3 or `num_iters`; the image is scaled by
+the brighter component of the best fit.  Every EM iteration is ONE fused pass over the pixels on the GPU (tpz_gmm_sums:
+responsibilities, log-likelihood and all sufficient statistics, fp64 accumulation); the M step (a handful of scalars)
+runs on the host in float64.  The quantile initialisation (np.quantile, stats.py:91) uses exact order statistics from
+a 3-pass radix select (tpz_select_hist).  The reference runs the same arithmetic in float32 tensors, so its stopping
+iteration can differ by rounding noise; results agree to ~1e-4 relative (tests)."""
+import math
+
 import numpy as np
 import torch
 
 from topaz_b200 import ops
 
+_PIS = (0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 0.95, 0.98, 1)
+
+
+def _xlogy(c, v):
+    return 0.0 if c == 0 else (c * math.log(v) if v > 0 else -math.inf * c)
+
+
+def _beta_logpdf(p, a, b):
+    """log Beta(p; a, b) (scipy.stats.beta.logpdf, stats.py:167,203)."""
+    return _xlogy(a - 1, p) + _xlogy(b - 1, 1 - p) + math.lgamma(a + b) - math.lgamma(a) - math.lgamma(b)
+
+
+def _beta_pdf_at_one(a, b):
+    if b == 1:
+        return float(a)
+    return 0.0 if b > 1 else math.inf
+
+
+def _key_to_float(key: int) -> float:
+    bits = (key & 0x7FFFFFFF) if key & 0x80000000 else (~key & 0xFFFFFFFF)
+    return float(np.array([bits], dtype=np.uint32).view(np.float32)[0])
+
+
+def order_statistics(xd: torch.Tensor, ranks) -> np.ndarray:
+    """Exact k-th smallest values (0-based ranks) of a device fp32 tensor: three histogram passes over the data."""
+    ranks = [int(r) for r in ranks]
+    c0 = np.cumsum(ops.select_hist(xd, 0))
+    lvl1 = {}                                     # rank -> (top12 bin, residual rank)
+    for r in ranks:
+        b = int(np.searchsorted(c0, r, side='right'))
+        lvl1[r] = (b, r - (int(c0[b - 1]) if b else 0))
+    p1 = sorted({b for b, _ in lvl1.values()})
+    h1 = ops.select_hist(xd, 1, p1)
+    lvl2 = {}
+    for r, (b, rr) in lvl1.items():
+        c = np.cumsum(h1[p1.index(b)])
+        bb = int(np.searchsorted(c, rr, side='right'))
+        lvl2[r] = ((b << 12) | bb, rr - (int(c[bb - 1]) if bb else 0))
+    p2 = sorted({b for b, _ in lvl2.values()})
+    out = {}
+    for lo in range(0, len(p2), 64):
+        chunk = p2[lo:lo + 64]
+        h2 = ops.select_hist(xd, 2, chunk)
+        for r, (b, rr) in lvl2.items():
+            if b in chunk:
+                c = np.cumsum(h2[chunk.index(b)])
+                out[r] = _key_to_float((b << 8) | int(np.searchsorted(c, rr, side='right')))
+    return np.array([out[r] for r in ranks], dtype=np.float64)
+
+
+def quantiles(xd: torch.Tensor, qs) -> np.ndarray:
+    """np.quantile(x, qs) (default linear interpolation) from exact order statistics."""
+    n = xd.numel()
+    pos = np.asarray(qs, dtype=np.float64) * (n - 1)
+    lo = np.floor(pos).astype(np.int64)
+    hi = np.minimum(lo + 1, n - 1)
+    ranks = sorted(set(lo.tolist()) | set(hi.tolist()))
+    vals = dict(zip(ranks, order_statistics(xd, ranks)))
+    a = np.array([vals[int(i)] for i in lo]); b = np.array([vals[int(i)] for i in hi])
+    t = pos - lo
+    return np.where(t >= 0.5, b - (b - a) * (1 - t), a + (b - a) * t)
+
+
+class _Sums:
+    """Device pass + host M step bookkeeping for one image (shifted coordinates xc = x - shift)."""
+
+    def __init__(self, xd: torch.Tensor):
+        self.x = xd.contiguous().view(-1)
+        self.n = self.x.numel()
+        self.buf = torch.empty(7, dtype=torch.float64, device=xd.device)
+        self.params = (np.zeros(8, dtype=np.float64))
+        st = ops.meanstd(self.x, unbiased=True).cpu().numpy().astype(np.float64)
+        self.mean, self.var_unbiased = float(st[0]), float(st[1]) ** 2
+        self.shift = self.mean
+
+    def run(self, mode, split=0.0, mu0=0.0, mu1=0.0, var0=1.0, var1=1.0, pi=0.5):
+        p = self.params
+        p[:] = (self.shift, split, mu0 - self.shift, mu1 - self.shift, var0, var1,
+                math.log1p(-pi) if pi < 1 else -math.inf, math.log(pi) if pi > 0 else -math.inf)
+        return ops.gmm_sums(self.x, mode, p, self.buf)
+
+    def m_step(self, s):
+        """stats.py:138-153 / 176-192 from the sufficient statistics: means, shared variance."""
+        _, S0, S1, Sx0, Sx1, Sxx0, Sxx1 = s
+        mu0 = Sx0 / S0 if S0 > 0 else self.mean - self.shift
+        mu1 = Sx1 / S1 if S1 > 0 else self.mean - self.shift
+        var = ((Sxx0 - 2 * mu0 * Sx0 + mu0 * mu0 * S0) + (Sxx1 - 2 * mu1 * Sx1 + mu1 * mu1 * S1)) / self.n
+        return mu0 + self.shift, mu1 + self.shift, var
+
+
+def _gmm_fit(S: _Sums, pi, split, alpha, beta, scale, tol, num_iters):
+    mu0, mu1, var = S.m_step(S.run(0, split=split))
+    s = S.run(1, mu0=mu0, mu1=mu1, var0=var, var1=var, pi=pi)
+    logp_cur = np.float32(scale * s[0] + _beta_logpdf(pi, alpha, beta))
+    logp = logp_cur
+    for _ in range(1, num_iters + 1):
+        a = alpha + s[2]
+        b = beta + S.n - s[2]
+        pi = (a - 1) / (a + b - 2)
+        mu0, mu1, var = S.m_step(s)
+        s = S.run(1, mu0=mu0, mu1=mu1, var0=var, var1=var, pi=pi)
+        logp = np.float32(scale * s[0] + _beta_logpdf(pi, alpha, beta))      # the reference compares float32 tensors
+        if logp - logp_cur <= tol:
+            break
+        logp_cur = logp
+    return float(logp), mu0, var, mu1, var, pi
+
+
+def gmm_fit(x, pi=0.5, split=None, alpha=0.5, beta=0.5, scale=1, tol=1e-3, num_iters=100, share_var=True, verbose=False):
+    """stats.py:122-214 -> (logp, mu0, var0, mu1, var1, pi) as Python floats.  share_var=False is not on this path."""
+    if not share_var:
+        raise NotImplementedError('topaz_b200.stats.gmm_fit: share_var=False is not implemented')
+    xd = _to_device(x)
+    if split is None:
+        split = float(quantiles(xd.view(-1), [1 - pi])[0])
+    return _gmm_fit(_Sums(xd), float(pi), float(split), alpha, beta, scale, tol, num_iters)
+
+
+def norm_fit(x, alpha=900, beta=1, scale=1, num_iters=100, use_cuda=True, verbose=False):
+    """stats.py:86-119 -> (mu, std, pi, logp, mus, stds, pis, logps)."""
+    xd = _to_device(x)
+    S = _Sums(xd)
+    pis = np.array(_PIS, dtype=np.float64)
+    splits = quantiles(S.x, 1 - pis)
+    logps, mus, stds = np.zeros(len(pis)), np.zeros(len(pis)), np.zeros(len(pis))
+    for i in range(len(pis)):
+        if pis[i] == 1:                                                      # single component (stats.py:103-106)
+            mu, var = S.mean, S.var_unbiased
+            logp = float(np.float32(scale * (-(S.n - 1) / 2.0 - 0.5 * S.n * math.log(2 * math.pi * var)) + _beta_pdf_at_one(alpha, beta)))
+            pi = 1.0
+        else:
+            logp, _, _, mu, var, pi = _gmm_fit(S, float(pis[i]), float(splits[i]), alpha, beta, scale, 1e-3, num_iters)
+        pis[i], logps[i], mus[i], stds[i] = pi, logp, mu, math.sqrt(var)
+    i = int(np.argmax(logps))
+    return mus[i], stds[i], pis[i], logps[i], mus, stds, pis, logps
+
+
+def _to_device(x) -> torch.Tensor:
+    if isinstance(x, torch.Tensor):
+        return ops.to_device(x.float().contiguous())
+    return ops.to_device(torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)))
+
+
+def normalize_device(xd: torch.Tensor, alpha=900, beta=1, num_iters=100, sample=1, method='gmm'):
+    """Device fp32 image -> (device fp32 normalised image, metadata)."""
+    ops.require_cuda(xd, 'image')
+    xd = xd.contiguous().float()
+    if method == 'affine':
+        stats = ops.meanstd(xd, unbiased=False)
+        mu, std = (float(v) for v in stats.cpu())
+        return ops.affine(xd, stats), {'mu': mu, 'std': std, 'pi': 1}
+    x_sample, scale = xd, 1
+    if sample > 1:                                                           # stats.py:53-58 (host RNG, numpy global state)
+        n = int(np.round(xd.numel() / sample))
+        scale = xd.numel() / n
+        idx = np.random.choice(xd.numel(), size=n, replace=False)
+        x_sample = xd.view(-1)[torch.from_numpy(idx).to(xd.device)]
+    mu, std, pi, logp, mus, stds, pis, logps = norm_fit(x_sample, alpha=alpha, beta=beta, scale=scale, num_iters=num_iters)
+    stats = torch.tensor([mu, std], dtype=torch.float32, device=xd.device)
+    meta = {'mu': mu, 'std': std, 'pi': pi, 'logp': logp, 'mus': mus, 'stds': stds, 'pis': pis, 'logps': logps,
+            'alpha': alpha, 'beta': beta, 'sample': sample}
+    return ops.affine(xd, stats), meta
+
 
 def normalize(x, alpha=900, beta=1, num_iters=100, sample=1, method='gmm', use_cuda=True, verbose=False):
-    if method != 'affine':
-        raise NotImplementedError("topaz_b200.stats.normalize: only method='affine' is on the B200 hot path")
-    xd = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).cuda()
-    stats = ops.meanstd(xd, unbiased=False)
-    y = ops.affine(xd, stats)
-    mu, std = (float(v) for v in stats.cpu())
-    return y.cpu().numpy().astype(np.float32), {'mu': mu, 'std': std, 'pi': 1}
+    y, meta = normalize_device(_to_device(x), alpha, beta, num_iters, sample, method)
+    return y.cpu().numpy().astype(np.float32), meta
