@@ -191,16 +191,17 @@ int tpz_make_crops(int B, int crop, int big_crop, const TpzSamplerImage* imgs, c
  * tpz_gemm_f32: C[M][N] = A[M][K] * B[K][N], row-major fp32, 3xTF32 tensor-core product (K%16==0, N%32==0).  The
  *   Fourier-crop downsample (topaz/utils/image.py:38-61: rfft2 -> crop -> irfft2) is linear and separable; the host
  *   builds its real row / column operators once per shape and applies them with this product.
- * tpz_gmm_sums: one pass of the 2-component GMM normalisation (topaz/stats.py:122-214).  params8 (host doubles) =
- *   {shift, split, mu0-shift, mu1-shift, var0, var1, log(1-pi), log(pi)}; mode 0 = initial hard split at `split`
- *   (stats.py:136-139), mode 1 = E step.  sums7 (device double[7]) = {sum Z, sum p0, sum p1, sum p0*xc, sum p1*xc,
- *   sum p0*xc^2, sum p1*xc^2} with xc = x - shift.
+ * tpz_gmm_sums: one pass over the pixels of the 2-component GMM normalisation (topaz/stats.py:122-214) for up to 12
+ *   parameter sets at once (the reference's 12 initialisations, advanced in lockstep).  sets8 (host doubles,
+ *   [nsets][8]) = {mode, split, mu0-shift, mu1-shift, var0, var1, log(1-pi), log(pi)}; mode 0 = initial hard split at
+ *   `split` (stats.py:136-139), mode 1 = E step.  sums (device double[nsets][7]) = {sum Z, sum p0, sum p1, sum p0*xc,
+ *   sum p1*xc, sum p0*xc^2, sum p1*xc^2} with xc = x - shift.
  * tpz_select_hist: radix-select histograms over the order-preserving uint32 key of each float, for the exact order
  *   statistics behind np.quantile (stats.py:91): level 0 -> hist[4096] of key>>20; level 1 -> hist[s][4096] of
  *   (key>>8)&0xFFF for keys whose top 12 bits equal prefixes[s]; level 2 -> hist[s][256] of key&0xFF for keys whose
  *   top 24 bits equal prefixes[s] (prefixes: device uint32[nprefix <= 64]). */
 int tpz_gemm_f32(const float* A, long long M, int K, const float* B, int N, float* C, void* stream);
-int tpz_gmm_sums(const float* x, long long n, int mode, const double* params8, double* sums7, void* stream);
+int tpz_gmm_sums(const float* x, long long n, double shift, const double* sets8, int nsets, double* sums, void* stream);
 int tpz_select_hist(const float* x, long long n, int level, const unsigned* prefixes, int nprefix, unsigned* hist,
                     void* stream);
 

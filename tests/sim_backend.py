@@ -163,21 +163,23 @@ def gemm_f32(A, B, C):
     return C
 
 
-def gmm_sums(x, mode, params8, work7=None):
+def gmm_sums(x, shift, sets8, work=None):
     """tpz_gmm_sums in float64 numpy."""
     import numpy as np
-    shift, split, mu0, mu1, var0, var1, lp0, lp1 = [float(v) for v in params8]
     xf = x.numpy().ravel()
-    xc = xf.astype(np.float64) - shift
-    if mode == 0:
-        p0 = (xf <= np.float32(split)).astype(np.float64); p1 = 1.0 - p0; Z = np.zeros_like(xc)
-    else:
-        l0 = -(xc - mu0) ** 2 / 2 / var0 - 0.5 * np.log(2 * np.pi * var0) + lp0
-        l1 = -(xc - mu1) ** 2 / 2 / var1 - 0.5 * np.log(2 * np.pi * var1) + lp1
-        ma = np.maximum(l0, l1)
-        Z = ma + np.log(np.exp(l0 - ma) + np.exp(l1 - ma))
-        p0, p1 = np.exp(l0 - Z), np.exp(l1 - Z)
-    return np.array([Z.sum(), p0.sum(), p1.sum(), (p0 * xc).sum(), (p1 * xc).sum(), (p0 * xc * xc).sum(), (p1 * xc * xc).sum()])
+    xc = xf.astype(np.float64) - float(shift)
+    out = []
+    for mode, split, mu0, mu1, var0, var1, lp0, lp1 in np.asarray(sets8, dtype=np.float64).reshape(-1, 8):
+        if mode == 0:
+            p0 = (xf <= np.float32(split)).astype(np.float64); p1 = 1.0 - p0; Z = np.zeros_like(xc)
+        else:
+            l0 = -(xc - mu0) ** 2 / 2 / var0 - 0.5 * np.log(2 * np.pi * var0) + lp0
+            l1 = -(xc - mu1) ** 2 / 2 / var1 - 0.5 * np.log(2 * np.pi * var1) + lp1
+            ma = np.maximum(l0, l1)
+            Z = ma + np.log(np.exp(l0 - ma) + np.exp(l1 - ma))
+            p0, p1 = np.exp(l0 - Z), np.exp(l1 - Z)
+        out.append([Z.sum(), p0.sum(), p1.sum(), (p0 * xc).sum(), (p1 * xc).sum(), (p0 * xc * xc).sum(), (p1 * xc * xc).sum()])
+    return np.array(out)
 
 
 def select_hist(x, level, prefixes=()):

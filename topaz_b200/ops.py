@@ -310,13 +310,15 @@ def gemm_f32(A: torch.Tensor, B: torch.Tensor, C: torch.Tensor):
     return C
 
 
-def gmm_sums(x: torch.Tensor, mode: int, params8, work7: Optional[torch.Tensor] = None):
-    """One GMM pass over a flat fp32 device tensor -> numpy float64[7] (see include/topaz_b200.h: tpz_gmm_sums)."""
+def gmm_sums(x: torch.Tensor, shift: float, sets8, work: Optional[torch.Tensor] = None):
+    """One GMM pass over a flat fp32 device tensor for k <= 12 parameter sets -> numpy float64 [k, 7]
+    (see include/topaz_b200.h: tpz_gmm_sums)."""
     import numpy as np
-    p = np.ascontiguousarray(params8, dtype=np.float64)
-    buf = work7 if work7 is not None else torch.empty(7, dtype=torch.float64, device=x.device)
-    _count(1); check(_lib.lib().tpz_gmm_sums(_ptr(x), x.numel(), int(mode), p.ctypes.data, _ptr(buf), _stream()))
-    return buf.cpu().numpy()
+    p = np.ascontiguousarray(sets8, dtype=np.float64).reshape(-1, 8)
+    k = p.shape[0]
+    buf = work if work is not None else torch.empty(12 * 7, dtype=torch.float64, device=x.device)
+    _count(1); check(_lib.lib().tpz_gmm_sums(_ptr(x), x.numel(), float(shift), p.ctypes.data, k, _ptr(buf), _stream()))
+    return buf[:k * 7].cpu().numpy().reshape(k, 7)
 
 
 def select_hist(x: torch.Tensor, level: int, prefixes=()):

@@ -76,17 +76,24 @@ def downsample_device(xd: torch.Tensor, factor=1, shape=None) -> torch.Tensor:
         shape = (int(M / factor), int(N / factor))
     m, n = shape
     RT, CaT, CbT, Mp, Np, np_ = _operators(M, N, m, n, str(xd.device))
+    # The map preserves constants and is linear, so it is applied to the standardised image (x - mean)/std and undone
+    # afterwards: raw micrographs carry a mean far above their contrast, and the tensor cores' truncating fp32
+    # accumulation would otherwise add a systematic offset proportional to that mean.
+    xd = xd.contiguous().float()
+    stats = ops.meanstd(xd, unbiased=False)
+    stats = torch.stack([stats[0], stats[1].clamp_min(1e-30)])           # constant image: (x - mean)/tiny = 0
+    xn = ops.affine(xd, stats)
     if Np != N:
         xp = torch.zeros((M, Np), dtype=torch.float32, device=xd.device)
-        xp[:, :N] = xd
+        xp[:, :N] = xn
     else:
-        xp = xd.contiguous().float()
+        xp = xn
     T = torch.zeros((2 * Mp, np_), dtype=torch.float32, device=xd.device)        # [x Ca^T ; x Cb^T], K-padding rows stay 0
     ops.gemm_f32(xp, CaT, T[:M])
     ops.gemm_f32(xp, CbT, T[Mp:Mp + M])
     out = torch.empty((m, np_), dtype=torch.float32, device=xd.device)
     ops.gemm_f32(RT, T, out)
-    return out[:, :n].contiguous()
+    return ops.affine(out[:, :n].contiguous(), stats, inverse=True)
 
 
 def downsample(x, factor=1, shape=None):

@@ -5,8 +5,8 @@ GPU (tpz_meanstd / tpz_affine).
 
 method='gmm' (stats.py:49-214): 12 initialisations of a shared-variance 2-component Gaussian mixture with a Beta(alpha,
 beta) prior on the mixing weight, EM until the log-posterior improves by <= 1e-3 or `num_iters`; the image is scaled by
-the brighter component of the best fit.  Every EM iteration is ONE fused pass over the pixels on the GPU (tpz_gmm_sums:
-responsibilities, log-likelihood and all sufficient statistics, fp64 accumulation); the M step (a handful of scalars)
+the brighter component of the best fit.  The 11 mixture fits advance in lockstep: every EM iteration is ONE fused pass over the pixels for all of
+them (tpz_gmm_sums: responsibilities, log-likelihood and all sufficient statistics, fp64 accumulation); the M step (a handful of scalars)
 runs on the host in float64.  The quantile initialisation (np.quantile, stats.py:91) uses exact order statistics from
 a 3-pass radix select (tpz_select_hist).  The reference runs the same arithmetic in float32 tensors, so its stopping
 iteration can differ by rounding noise; results agree to ~1e-4 relative (tests)."""
@@ -80,75 +80,117 @@ def quantiles(xd: torch.Tensor, qs) -> np.ndarray:
     return np.where(t >= 0.5, b - (b - a) * (1 - t), a + (b - a) * t)
 
 
-class _Sums:
-    """Device pass + host M step bookkeeping for one image (shifted coordinates xc = x - shift)."""
+class _Image:
+    """Flat device pixels + the scalars every fit shares (shifted coordinates xc = x - shift keep the fp64 sums
+    well conditioned for raw micrographs whose mean is far above their contrast)."""
 
     def __init__(self, xd: torch.Tensor):
         self.x = xd.contiguous().view(-1)
         self.n = self.x.numel()
-        self.buf = torch.empty(7, dtype=torch.float64, device=xd.device)
-        self.params = (np.zeros(8, dtype=np.float64))
+        self.work = torch.empty(12 * 7, dtype=torch.float64, device=xd.device)
         st = ops.meanstd(self.x, unbiased=True).cpu().numpy().astype(np.float64)
         self.mean, self.var_unbiased = float(st[0]), float(st[1]) ** 2
         self.shift = self.mean
 
-    def run(self, mode, split=0.0, mu0=0.0, mu1=0.0, var0=1.0, var1=1.0, pi=0.5):
-        p = self.params
-        p[:] = (self.shift, split, mu0 - self.shift, mu1 - self.shift, var0, var1,
-                math.log1p(-pi) if pi < 1 else -math.inf, math.log(pi) if pi > 0 else -math.inf)
-        return ops.gmm_sums(self.x, mode, p, self.buf)
+    def sums(self, sets8):
+        return ops.gmm_sums(self.x, self.shift, sets8, self.work)
 
-    def m_step(self, s):
-        """stats.py:138-153 / 176-192 from the sufficient statistics: means, shared variance."""
+
+class _Fit:
+    """One EM run (stats.py:122-214, share_var=True): host-side state machine around the device sums."""
+
+    def __init__(self, img: _Image, pi, split, alpha, beta, scale, tol, num_iters):
+        self.img, self.pi, self.split = img, float(pi), float(split)
+        self.alpha, self.beta, self.scale, self.tol, self.num_iters = alpha, beta, scale, tol, num_iters
+        self.stage, self.it, self.done = 'init', 0, False
+        self.mu0 = self.mu1 = self.var = 0.0
+        self.logp = self.logp_cur = None
+
+    def request(self):
+        """Parameter row for tpz_gmm_sums: {mode, split, mu0-shift, mu1-shift, var0, var1, log(1-pi), log(pi)}."""
+        if self.stage == 'init':
+            return (0.0, self.split, 0.0, 0.0, 1.0, 1.0, 0.0, 0.0)
+        sh = self.img.shift
+        lp0 = math.log1p(-self.pi) if self.pi < 1 else -math.inf
+        lp1 = math.log(self.pi) if self.pi > 0 else -math.inf
+        return (1.0, 0.0, self.mu0 - sh, self.mu1 - sh, self.var, self.var, lp0, lp1)
+
+    def _m_step(self, s):
+        """stats.py:138-153 / 176-192 from the sufficient statistics: component means, shared variance."""
+        img = self.img
         _, S0, S1, Sx0, Sx1, Sxx0, Sxx1 = s
-        mu0 = Sx0 / S0 if S0 > 0 else self.mean - self.shift
-        mu1 = Sx1 / S1 if S1 > 0 else self.mean - self.shift
-        var = ((Sxx0 - 2 * mu0 * Sx0 + mu0 * mu0 * S0) + (Sxx1 - 2 * mu1 * Sx1 + mu1 * mu1 * S1)) / self.n
-        return mu0 + self.shift, mu1 + self.shift, var
+        mu0 = Sx0 / S0 if S0 > 0 else img.mean - img.shift
+        mu1 = Sx1 / S1 if S1 > 0 else img.mean - img.shift
+        self.var = ((Sxx0 - 2 * mu0 * Sx0 + mu0 * mu0 * S0) + (Sxx1 - 2 * mu1 * Sx1 + mu1 * mu1 * S1)) / img.n
+        self.mu0, self.mu1 = mu0 + img.shift, mu1 + img.shift
+
+    def consume(self, s):
+        if self.stage == 'init':                              # hard-split statistics -> first parameters
+            self._m_step(s)
+            self.stage = 'first'
+            return
+        # `s` was computed under the current parameters: their log-posterior, and the statistics for the next M step.
+        # The reference compares float32 tensors (stats.py:167,203,209), hence the rounding.
+        logp = np.float32(self.scale * s[0] + _beta_logpdf(self.pi, self.alpha, self.beta))
+        if self.stage == 'first':
+            self.logp = self.logp_cur = logp
+            self.stage = 'em'
+        else:
+            self.logp = logp
+            if logp - self.logp_cur <= self.tol or self.it >= self.num_iters:
+                self.done = True
+                return
+            self.logp_cur = logp
+        if self.num_iters < 1:
+            self.done = True
+            return
+        self.it += 1
+        a = self.alpha + s[2]
+        b = self.beta + self.img.n - s[2]
+        self.pi = (a - 1) / (a + b - 2)                       # MAP estimate under the Beta prior (stats.py:176-179)
+        self._m_step(s)
+
+    def result(self):
+        return float(self.logp), self.mu0, self.var, self.mu1, self.var, self.pi
 
 
-def _gmm_fit(S: _Sums, pi, split, alpha, beta, scale, tol, num_iters):
-    mu0, mu1, var = S.m_step(S.run(0, split=split))
-    s = S.run(1, mu0=mu0, mu1=mu1, var0=var, var1=var, pi=pi)
-    logp_cur = np.float32(scale * s[0] + _beta_logpdf(pi, alpha, beta))
-    logp = logp_cur
-    for _ in range(1, num_iters + 1):
-        a = alpha + s[2]
-        b = beta + S.n - s[2]
-        pi = (a - 1) / (a + b - 2)
-        mu0, mu1, var = S.m_step(s)
-        s = S.run(1, mu0=mu0, mu1=mu1, var0=var, var1=var, pi=pi)
-        logp = np.float32(scale * s[0] + _beta_logpdf(pi, alpha, beta))      # the reference compares float32 tensors
-        if logp - logp_cur <= tol:
-            break
-        logp_cur = logp
-    return float(logp), mu0, var, mu1, var, pi
+def _run_fits(img: _Image, fits):
+    """Advance all unfinished fits in lockstep: one device pass per EM iteration for the whole group."""
+    while True:
+        active = [f for f in fits if not f.done]
+        if not active:
+            return
+        sums = img.sums([f.request() for f in active])
+        for f, s in zip(active, sums):
+            f.consume(s)
 
 
 def gmm_fit(x, pi=0.5, split=None, alpha=0.5, beta=0.5, scale=1, tol=1e-3, num_iters=100, share_var=True, verbose=False):
     """stats.py:122-214 -> (logp, mu0, var0, mu1, var1, pi) as Python floats.  share_var=False is not on this path."""
     if not share_var:
         raise NotImplementedError('topaz_b200.stats.gmm_fit: share_var=False is not implemented')
-    xd = _to_device(x)
+    img = _Image(_to_device(x))
     if split is None:
-        split = float(quantiles(xd.view(-1), [1 - pi])[0])
-    return _gmm_fit(_Sums(xd), float(pi), float(split), alpha, beta, scale, tol, num_iters)
+        split = float(quantiles(img.x, [1 - pi])[0])
+    fit = _Fit(img, pi, split, alpha, beta, scale, tol, num_iters)
+    _run_fits(img, [fit])
+    return fit.result()
 
 
 def norm_fit(x, alpha=900, beta=1, scale=1, num_iters=100, use_cuda=True, verbose=False):
     """stats.py:86-119 -> (mu, std, pi, logp, mus, stds, pis, logps)."""
-    xd = _to_device(x)
-    S = _Sums(xd)
+    img = _Image(_to_device(x))
     pis = np.array(_PIS, dtype=np.float64)
-    splits = quantiles(S.x, 1 - pis)
+    splits = quantiles(img.x, 1 - pis)
+    fits = {i: _Fit(img, pis[i], splits[i], alpha, beta, scale, 1e-3, num_iters) for i in range(len(pis)) if pis[i] != 1}
+    _run_fits(img, list(fits.values()))
     logps, mus, stds = np.zeros(len(pis)), np.zeros(len(pis)), np.zeros(len(pis))
     for i in range(len(pis)):
-        if pis[i] == 1:                                                      # single component (stats.py:103-106)
-            mu, var = S.mean, S.var_unbiased
-            logp = float(np.float32(scale * (-(S.n - 1) / 2.0 - 0.5 * S.n * math.log(2 * math.pi * var)) + _beta_pdf_at_one(alpha, beta)))
-            pi = 1.0
-        else:
-            logp, _, _, mu, var, pi = _gmm_fit(S, float(pis[i]), float(splits[i]), alpha, beta, scale, 1e-3, num_iters)
+        if i in fits:
+            logp, _, _, mu, var, pi = fits[i].result()
+        else:                                                                # single component (stats.py:103-106)
+            mu, var, pi = img.mean, img.var_unbiased, 1.0
+            logp = float(np.float32(scale * (-(img.n - 1) / 2.0 - 0.5 * img.n * math.log(2 * math.pi * var)) + _beta_pdf_at_one(alpha, beta)))
         pis[i], logps[i], mus[i], stds[i] = pi, logp, mu, math.sqrt(var)
     i = int(np.argmax(logps))
     return mus[i], stds[i], pis[i], logps[i], mus, stds, pis, logps
