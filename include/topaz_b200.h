@@ -86,6 +86,13 @@ int tpz_tc_conv_v2(const TpzTcConvArgs* host_args, void* stream);/* halo-residen
 int tpz_conv_first(const float* x, int N, int D, int H, int W, const float* w, const float* bias, int Co,
                    int kd, int kh, int kw, int dil, int pad, float neg_slope, int pool, tpz_half* out,
                    int out_ld, void* stream);
+/* tpz_conv_first_tc: the same Cin = 1 convolution (2-D, dilation 1) as ONE tcgen05 kernel: each CTA builds the im2col
+ *   tile of 128 output pixels in shared memory (SWIZZLE_128B K-major, generic stores + fence.proxy.async) and multiplies
+ *   it with the smem-resident weights; HBM sees only the fp32 image in and the fp16 [N][Ho][Wo][Cp] map out.
+ *   w_packed: fp16 [ceil(k*k/64)][Cp][64] (tap t = r*k+s, zero padded); bias fp32 [Cp]; Cp in {32,64}; k in {3,5,7,11}. */
+int tpz_conv_first_tc(const float* x, int B, int H, int W, const tpz_half* w_packed, const float* bias, int Cp, int k,
+                      int pad, float neg_slope, tpz_half* out, void* stream);
+int tpz_conv_first_tc_supported(int k, int Cp);
 /* tpz_im2col_first: im2col of a single-channel 2-D image (k x k taps -> channels, zero padded to ld) so that
  *   Cin = 1 convs (first BasicConv 7x7, U-Net enc1 11x11, the raw-image slice of U-Net dec1.0) run as a
  *   1-tap tensor-core GEMM through tpz_tc_conv.  out: fp16 [N][1][Ho][Wo][ld].                       */

@@ -101,6 +101,15 @@ def conv_first(x, w, bias, dil, pad, neg_slope, out_ld):
     return out
 
 
+def conv_first_tc(x, w_packed, bias, k, pad, neg_slope):
+    """tpz_conv_first_tc: fp16 taps x fp16 weights, fp32 accumulate, bias + activation, fp16 NHWC out."""
+    kb, cp, _ = w_packed.shape
+    w = w_packed.float().permute(1, 0, 2).reshape(cp, kb * 64)[:, :k * k].reshape(cp, 1, k, k)
+    y = F.conv2d(x.half().float()[:, None], w, bias.float(), padding=pad)
+    y = torch.where(y > 0, y, y * neg_slope)
+    return y.permute(0, 2, 3, 1)[:, None].contiguous().half()
+
+
 def im2col_first(x, k, pad, ld):
     N, H, W = x.shape
     xp = F.pad(x, (pad, pad, pad, pad))
@@ -203,7 +212,7 @@ def to_device(t):
 
 @contextlib.contextmanager
 def patched():
-    names = ['tc_conv', 'conv_first', 'im2col_first', 'filter_f32', 'conv_last', 'maxpool2', 'upsample_nearest', 'meanstd', 'affine',
+    names = ['tc_conv', 'conv_first', 'conv_first_tc', 'im2col_first', 'filter_f32', 'conv_last', 'maxpool2', 'upsample_nearest', 'meanstd', 'affine',
              'gemm_f32', 'gmm_sums', 'select_hist', 'to_device']
     saved = {n: getattr(ops, n) for n in names}
     saved['require_cuda'] = ops.require_cuda

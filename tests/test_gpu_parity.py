@@ -348,3 +348,41 @@ def test_downsample_and_gmm_normalize_gpu():
     yr, mu, std, pi = O.gmm_normalize(img, 2, 2, 60)
     assert abs(md['mu'] - mu) < 1e-3 * abs(mu) and abs(md['std'] - std) < 1e-3 * std and abs(md['pi'] - pi) < 1e-3
     assert np.abs(y - yr).max() < 1e-3 * np.abs(yr).max()
+
+
+def test_pick_arrays_matches_score_then_nms():
+    """Device-resident score -> NMS pipeline equals score_arrays followed by the oracle NMS on the same score map."""
+    from topaz_b200.extract import pick_arrays, score_arrays, nms_iterator
+    g = gold('resnet8_u32_pretrained'); sd = weights_of(g)
+    m = _load(_classifier('resnet8', 32), sd)
+    imgs = [np.random.default_rng(50 + i).standard_normal((300 + 40 * i, 280)).astype(np.float32) for i in range(3)]
+    picks = list(pick_arrays(m, imgs, radius=6, threshold=-3.0))
+    m.unfill()
+    maps = list(score_arrays(m, imgs))
+    assert len(picks) == 3
+    for (s, c), y in zip(picks, maps):
+        s_ref, c_ref = O.nms(y, 6, -3.0)
+        assert len(s) > 20 and np.array_equal(c, c_ref) and np.array_equal(s, s_ref)
+    out = list(nms_iterator([('a', maps[0])], 6, -3.0))
+    assert out[0][0] == 'a' and np.array_equal(out[0][2], picks[0][1])
+
+
+@pytest.mark.parametrize('k,co,slope', [(7, 64, 0.0), (7, 32, 0.0), (11, 48, 0.1), (5, 20, 1.0), (3, 64, 0.25), (11, 32, 0.0)])
+def test_fused_first_layer_kernel_matches_fp32_conv(k, co, slope):
+    """tpz_conv_first_tc (im2col tile built in smem + tcgen05) vs a plain fp32 torch convolution of the same Cin=1
+    layer, on ragged sizes and batch > 1; tolerance = fp16 operand rounding (2^-11) over k*k taps."""
+    from topaz_b200 import ops
+    g = torch.Generator().manual_seed(k * 100 + co)
+    w = torch.randn(co, k, k, generator=g) / k
+    b = torch.randn(co, generator=g)
+    cp = (co + 31) // 32 * 32
+    wp, bp = ops.pack_first_tc(w, b, cp, 'cuda')
+    for (B, H, W, pad) in [(1, 64, 64, k // 2), (2, 37, 53, 35 if k == 7 else k // 2), (1, 5, 200, k // 2), (1, 300, 9, k // 2)]:
+        x = torch.randn(B, H, W, generator=g)
+        y = ops.conv_first_tc(x.cuda(), wp, bp, k, pad, slope).float().cpu()          # [B,1,Ho,Wo,cp]
+        ref = F.conv2d(x[:, None], w[:, None], b, padding=pad)
+        ref = torch.where(ref > 0, ref, ref * slope).permute(0, 2, 3, 1)
+        assert y.shape[:4] == (B, 1) + tuple(ref.shape[1:3])
+        assert torch.all(y[..., co:] == 0)                                             # padded channels stay zero
+        err = (y[:, 0, :, :, :co] - ref).abs().max() / ref.abs().max()
+        assert err < 2e-3, (B, H, W, float(err))

@@ -63,18 +63,22 @@ class Denoise():
         input = torch.from_numpy(input) if type(input) == np.ndarray else input
         return self._denoise_device(input).cpu().numpy()
 
+    def _patch_row(self, xd: torch.Tensor, y: torch.Tensor, i: int, patch_size: int, padding: int):
+        """All patches whose centres start at row i (reference denoise.py:305-322)."""
+        H, W = xd.shape[0], xd.shape[1]
+        si, ei = max(0, i - padding), min(H, i + patch_size + padding)
+        for j in range(0, W, patch_size):
+            sj, ej = max(0, j - padding), min(W, j + patch_size + padding)
+            yij = self._denoise_device(xd[si:ei, sj:ej])
+            oi, oj = i - si, j - sj
+            y[i:i + patch_size, j:j + patch_size] = yij[oi:oi + patch_size, oj:oj + patch_size]
+
     @torch.no_grad()
     def denoise_patches_device(self, xd: torch.Tensor, patch_size: int, padding: int = 128) -> torch.Tensor:
         """Patch loop of denoise_patches on a device-resident fp32 micrograph; returns the device result."""
         y = torch.zeros_like(xd)
-        H, W = xd.shape[0], xd.shape[1]
-        for i in range(0, H, patch_size):
-            for j in range(0, W, patch_size):
-                si, ei = max(0, i - padding), min(H, i + patch_size + padding)
-                sj, ej = max(0, j - padding), min(W, j + patch_size + padding)
-                yij = self._denoise_device(xd[si:ei, sj:ej])
-                oi, oj = i - si, j - sj
-                y[i:i + patch_size, j:j + patch_size] = yij[oi:oi + patch_size, oj:oj + patch_size]
+        for i in range(0, xd.shape[0], patch_size):
+            self._patch_row(xd, y, i, patch_size, padding)
         return y
 
     def _pinned(self, name: str, shape) -> torch.Tensor:
@@ -88,20 +92,47 @@ class Denoise():
 
     @torch.no_grad()
     def denoise_patches(self, x: Union[np.ndarray, torch.Tensor], patch_size: int, padding: int = 128) -> np.ndarray:
-        ''' Denoise 2D micrograph patches (reference denoise.py:299-324).  The micrograph is uploaded once through a
-        pinned staging buffer; patches are cropped, denoised and pasted on the device; one download at the end.'''
+        ''' Denoise 2D micrograph patches (reference denoise.py:299-324).  Patches are cropped, denoised and pasted on the
+        device.  For a host image the transfer is pipelined by patch row: the rows a patch row needs are staged through
+        pinned memory and uploaded on a copy stream while earlier rows compute, and each finished row is downloaded and
+        copied into the result while later rows compute.'''
         x = torch.from_numpy(x) if type(x) == np.ndarray else x
         if x.is_cuda:
-            xd = x.float()
-        else:
-            stage = self._pinned('in', x.shape)
-            stage.copy_(x)
-            xd = stage.to(self.device, non_blocking=True)
-        y = self.denoise_patches_device(xd, patch_size, padding)
-        out = self._pinned('out', y.shape)
-        out.copy_(y, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return out.numpy().copy()
+            y = self.denoise_patches_device(x.float(), patch_size, padding)
+            return y.cpu().numpy()
+        x = x.float()
+        H, W = x.shape
+        stage, out = self._pinned('in', x.shape), self._pinned('out', x.shape)
+        streams = self.__dict__.setdefault('_streams', None) or (torch.cuda.Stream(), torch.cuda.Stream())
+        self._streams = streams
+        copy_in, copy_out = streams
+        main = torch.cuda.current_stream()
+        xd = torch.empty((H, W), dtype=torch.float32, device=self.device)
+        y = torch.empty((H, W), dtype=torch.float32, device=self.device)
+        copy_in.wait_stream(main); copy_out.wait_stream(main)
+        result = np.empty((H, W), dtype=np.float32)
+        uploaded, done = 0, []
+        for i in range(0, H, patch_size):
+            need = min(H, i + patch_size + padding)
+            if need > uploaded:
+                stage[uploaded:need].copy_(x[uploaded:need])
+                with torch.cuda.stream(copy_in):
+                    xd[uploaded:need].copy_(stage[uploaded:need], non_blocking=True)
+                    ev = torch.cuda.Event(); ev.record(copy_in)
+                main.wait_event(ev)
+                uploaded = need
+            self._patch_row(xd, y, i, patch_size, padding)
+            ev = torch.cuda.Event(); ev.record(main)
+            hi = min(H, i + patch_size)
+            with torch.cuda.stream(copy_out):
+                copy_out.wait_event(ev)
+                out[i:hi].copy_(y[i:hi], non_blocking=True)
+                evo = torch.cuda.Event(); evo.record(copy_out)
+            done.append((i, hi, evo))
+        for i, hi, evo in done:
+            evo.synchronize()
+            result[i:hi] = out[i:hi].numpy()
+        return result
 
     @torch.no_grad()
     def denoise(self, x: Union[np.ndarray, torch.Tensor], patch_size=-1, padding=128):

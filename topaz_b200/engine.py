@@ -20,9 +20,11 @@ from . import ops
 from .ops import ConvPart
 
 # Engine knobs (environment, so the reference CLI signatures stay unchanged):
-#   TPZ_FIRST=simt        Cin=1 first convs on the fp32 SIMT kernel instead of im2col + tensor-core GEMM
+#   TPZ_FIRST=simt        Cin=1 first convs on the fp32 SIMT kernel instead of the tensor cores
+#   TPZ_FIRST=im2col      Cin=1 first convs as HBM im2col + 1-tap tensor-core GEMM (the pre-fusion path)
 #   TPZ_RESIDUAL=epilogue identity skip added in the epilogue (global loads) instead of an identity k-block in the MMA
 FIRST_ON_TC = os.environ.get('TPZ_FIRST', 'tc') != 'simt'
+FIRST_FUSED = os.environ.get('TPZ_FIRST', 'tc') == 'tc'      # im2col tile built in smem inside the GEMM kernel
 RESIDUAL_IN_MMA = os.environ.get('TPZ_RESIDUAL', 'mma') != 'epilogue'
 UP2_FUSED = os.environ.get('TPZ_UP2', 'fused') != 'off'       # fused 2x up-sampling in U-Net dec1.0 (poly-phase)
 LAST_ON_TC = os.environ.get('TPZ_LAST', 'tc') != 'simt'      # Cout=1 U-Net tail on the tensor-core kernel
@@ -143,7 +145,11 @@ def _build_dense_plan(features, classifier: Optional[nn.Module], device):
         w = w * a.view(-1, 1, 1, 1); b = b * a + sh
     c_real = w.shape[0]
     k0 = w.shape[-1]
-    if FIRST_ON_TC and first['dil'] == 1 and k0 * k0 <= 128:
+    if FIRST_FUSED and first['dil'] == 1 and ops.first_tc_supported(k0, _rup(c_real)):
+        # Cin = 1: one tcgen05 kernel that builds the im2col tile in shared memory (tpz_first_tc.cu)
+        wp, bp = ops.pack_first_tc(w[:, 0], b, _rup(c_real), device)
+        steps.append(dict(op='first_tc', w=wp, b=bp, k=k0, pad=features.width // 2, slope=first['slope']))
+    elif FIRST_ON_TC and first['dil'] == 1 and k0 * k0 <= 128:
         # Cin = 1: im2col (taps -> channels) then a 1-tap tensor-core GEMM (K = k*k padded to 32)
         ld = _tap_ld(k0 * k0)
         p1 = ops.pack_tc_conv([ConvPart(w.reshape(c_real, k0 * k0, 1, 1), ld, 1)], b, _rup(c_real), first['slope'], device)
@@ -214,6 +220,9 @@ def _run_dense(plan, x: torch.Tensor, want_features: bool):
     for st in plan['steps']:
         if st['op'] == 'first':
             cur = ops.conv_first(x.view(B, 1, H, W), st['w'], st['b'], st['dil'], st['pad'], st['slope'], st['out_ld'])
+            continue
+        if st['op'] == 'first_tc':
+            cur = ops.conv_first_tc(x, st['w'], st['b'], st['k'], st['pad'], st['slope'])
             continue
         if st['op'] == 'im2col':
             cur = ops.im2col_first(x, st['k'], st['pad'], st['ld'])
@@ -324,7 +333,11 @@ def _build_unet_plan(model, device):
     c1 = enc[0][0]
     k1 = c1.weight.shape[-1]
     plan['first_tc'] = None
-    if FIRST_ON_TC and k1 * k1 <= 128:
+    plan['first_fused'] = None
+    if FIRST_FUSED and dims == 2 and ops.first_tc_supported(k1, _rup(nf)):
+        wp, bp = ops.pack_first_tc(c1.weight.detach()[:, 0], c1.bias, _rup(nf), device)
+        plan['first_fused'] = dict(w=wp, b=bp, k=k1)
+    elif FIRST_ON_TC and k1 * k1 <= 128:
         # Cin = 1: in-plane im2col (k*k taps -> channels) + tensor-core GEMM; in 3-D the k z-taps stay taps of the GEMM
         ld = _tap_ld(k1 * k1)
         if dims == 2:
@@ -416,7 +429,10 @@ def unet_forward(model, x: torch.Tensor, denorm_stats: Optional[torch.Tensor] = 
     if dims == 2:
         xi = xi[:, None]                                  # [N, 1, H, W]
     f = plan['first']
-    if plan['first_tc'] is not None:
+    if plan['first_fused'] is not None:
+        ff = plan['first_fused']
+        h = ops.conv_first_tc(xi[:, 0].contiguous(), ff['w'], ff['b'], ff['k'], ff['k'] // 2, 0.1)
+    elif plan['first_tc'] is not None:
         ft = plan['first_tc']
         N0, D0, H0, W0 = xi.shape
         col = ops.im2col_first(xi.reshape(N0 * D0, H0, W0), ft['k'], ft['k'] // 2, ft['ld']).view(N0, D0, H0, W0, ft['ld'])

@@ -106,3 +106,55 @@ def _score_stream(model: torch.nn.Module, images: Iterable[np.ndarray], pinned: 
     if pending is not None:
         pending[1].synchronize()
         yield pending[0].numpy()
+
+
+def nms_iterator(paths_scores, radius: int, threshold: float, pool=None, dims: int = 2, patch_size: int = 0,
+                 patch_overlap: int = 0, verbose: bool = False):
+    """Drop-in for topaz.extract.nms_iterator (reference extract.py:91-103) on the GPU NMS: yields (name, scores, coords).
+    `pool` is accepted and ignored (the reference parallelises its Python loop over CPU processes; one GPU call replaces it).
+    The patched variant of the reference (`patch_size > 0`, extract.py:44-75) unpacks three values from the two that
+    non_maximum_suppression returns and cannot run; it is not reproduced."""
+    from topaz_b200.algorithms import non_maximum_suppression, non_maximum_suppression_3d
+    if patch_size:
+        raise NotImplementedError('topaz_b200.extract.nms_iterator: patched NMS is not supported (see docstring)')
+    nms = non_maximum_suppression if dims == 2 else non_maximum_suppression_3d
+    for name, score in paths_scores:
+        s, c = nms(score, radius, threshold=threshold)
+        yield name, s, c
+
+
+def pick_arrays(model: torch.nn.Module, images: Iterable[np.ndarray], radius: int, threshold: float = -6.0, device: int = 0):
+    """Score micrographs and run the greedy NMS without the score map leaving the GPU: yields (scores float32 [j],
+    coords int32 [j,2] as (x, y)) per image -- `topaz extract` (extract.py:224-256 followed by extract.py:91-103) minus
+    the 2 x 64 MB of PCIe traffic per 4096^2 micrograph and the reference's multi-second Python NMS loop."""
+    from topaz_b200.algorithms import non_maximum_suppression
+    torch.cuda.set_device(device)
+    model.eval(); model.fill(); model.cuda()
+    copy_in = torch.cuda.Stream()
+    main = torch.cuda.current_stream()
+    nxt = None
+    it = iter(images)
+
+    def stage(img):
+        h = torch.from_numpy(np.ascontiguousarray(img, dtype=np.float32))
+        if not h.is_pinned():
+            h = h.pin_memory()
+        with torch.cuda.stream(copy_in):
+            d = h.cuda(non_blocking=True)
+            ev = torch.cuda.Event(); ev.record(copy_in)
+        return d, ev, h
+    try:
+        nxt = stage(next(it))
+    except StopIteration:
+        return
+    while nxt is not None:
+        d, ev, keep = nxt
+        try:
+            nxt = stage(next(it))            # H2D of image i+1 overlaps the network + NMS of image i
+        except StopIteration:
+            nxt = None
+        main.wait_event(ev)
+        with torch.no_grad():
+            s = model(d[None, None])[0, 0]
+        d.record_stream(main)
+        yield non_maximum_suppression(s, radius, threshold)

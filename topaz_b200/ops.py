@@ -235,6 +235,34 @@ def conv_first(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], d
     return out
 
 
+def first_tc_supported(k: int, cp: int) -> bool:
+    return (k in (3, 5, 7, 11)) and (cp in (32, 64))
+
+
+def pack_first_tc(w: torch.Tensor, bias: Optional[torch.Tensor], cp: int, device):
+    """w: fp32 [Co, k, k] (BN already folded).  Returns (fp16 [KB][cp][64] k-block-major packed taps, fp32 bias [cp])."""
+    co, k, _ = w.shape
+    kb = (k * k + 63) // 64
+    wp = torch.zeros((cp, kb * 64), dtype=torch.float32)
+    wp[:co, :k * k] = w.detach().float().cpu().reshape(co, k * k)
+    wp = wp.reshape(cp, kb, 64).permute(1, 0, 2).contiguous().to(torch.float16)
+    bp = torch.zeros(cp, dtype=torch.float32)
+    if bias is not None:
+        bp[:co] = bias.detach().float().cpu()
+    return wp.to(device), bp.to(device)
+
+
+def conv_first_tc(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, k: int, pad: int, neg_slope: float) -> torch.Tensor:
+    """x: fp32 [N, H, W] on device.  Returns fp16 [N, 1, Ho, Wo, Cp]: conv k x k (zero padding `pad`) + bias + activation."""
+    N, H, W = x.shape
+    cp = w_packed.shape[1]
+    Ho, Wo = H + 2 * pad - (k - 1), W + 2 * pad - (k - 1)
+    out = torch.empty((N, 1, Ho, Wo, cp), dtype=torch.float16, device=x.device)
+    _count(1); check(_lib.lib().tpz_conv_first_tc(_ptr(x), N, H, W, _ptr(w_packed), _ptr(bias), cp, k, pad, float(neg_slope),
+                                                  _ptr(out), _stream()))
+    return out
+
+
 def im2col_first(x: torch.Tensor, k: int, pad: int, ld: int) -> torch.Tensor:
     """x: fp32 [N, H, W].  Returns fp16 [N, 1, Ho, Wo, ld] with channel t = tap (r*k+s), zero beyond k*k."""
     N, H, W = x.shape
