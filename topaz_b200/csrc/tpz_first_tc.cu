@@ -10,8 +10,9 @@
 //   2. thread p writes row p of A: its k*k taps as fp16, K padded to 64/128, in the canonical K-major SWIZZLE_128B
 //      layout (16-byte chunk c of row p lands at chunk c ^ (p & 7)), generic-proxy stores + fence.proxy.async,
 //   3. one elected thread issues Kp/16 tcgen05.mma (M=128, N=Cp) against the smem-resident weights, commit -> mbarrier,
-//   4. the epilogue of the PREVIOUS tile (other TMEM stage, other A buffer) runs while those MMAs execute:
-//      tcgen05.ld -> +bias -> activation -> fp16 -> 16-byte global stores (each pixel's Cp channels are contiguous).
+//   4. epilogue: tcgen05.ld -> +bias -> activation -> fp16 -> 16-byte global stores (a pixel's Cp channels are contiguous).
+// A CTA is strictly sequential per tile; up to 8 CTAs are resident per SM (64 TMEM columns, ~27 KB smem, <= 64
+// registers each) and overlap one another, and each CTA prefetches its next input window into registers.
 #include "tpz_common.cuh"
 #include "../../include/topaz_b200.h"
 
@@ -29,30 +30,37 @@ struct FirstArgs {
   int tiles_x, tiles_y;
 };
 
-template <int KW, int CP>
-__global__ void __launch_bounds__(128) first_tc_kernel(const FirstArgs a) {
-  constexpr int TAPS = KW * KW;
-  constexpr int KB = (TAPS + 63) / 64;               // 64-wide k-blocks (7x7 -> 1, 11x11 -> 2)
-  constexpr int PH = TH + KW - 1, PW = TW + KW - 1;  // input window
-  constexpr int PWP = PW | 1;                        // odd pitch: conflict-free column walks
+template <int KW>
+struct FirstGeom {
+  static constexpr int TAPS = KW * KW;
+  static constexpr int KB = (TAPS + 63) / 64;                 // 64-wide k-blocks (7x7 -> 1, 11x11 -> 2)
+  static constexpr int PH = TH + KW - 1, PW = TW + KW - 1;    // input window
+  // window pitch == 16 (mod 32): a warp reads two tile rows of 16 pixels, the second row must land on the other 16 banks
+  static constexpr int PWP = PW <= 16 ? 16 : (PW <= 48 ? 48 : 80);
+  static constexpr int NPRE = (PH * PW + 127) / 128;          // window elements prefetched per thread
+};
+
+template <int KW, int CP, int MINB>
+__global__ void __launch_bounds__(128, MINB) first_tc_kernel(const FirstArgs a) {
+  using G = FirstGeom<KW>;
+  constexpr int TAPS = G::TAPS, KB = G::KB, PH = G::PH, PW = G::PW, PWP = G::PWP, NPRE = G::NPRE;
   constexpr uint32_t A_BYTES = 128 * 128;            // one k-block of A: 128 rows x 128 B
   constexpr uint32_t B_BYTES = CP * 128;
   constexpr uint32_t IDESC = ptx::umma_idesc_f16(128, CP);
-  constexpr int TCOLS = 2 * CP < 32 ? 32 : 2 * CP;   // two accumulator stages
+  constexpr int TCOLS = CP < 32 ? 32 : CP;           // one accumulator; CTAs co-resident on the SM overlap each other
 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  unsigned char* sA = base;                                   // [2 stages][KB][128 x 128 B]
-  unsigned char* sB = base + 2 * KB * A_BYTES;                // [KB][CP x 128 B]
+  unsigned char* sA = base;                                   // [KB][128 x 128 B]
+  unsigned char* sB = base + KB * A_BYTES;                    // [KB][CP x 128 B]
   float* sImg = reinterpret_cast<float*>(sB + KB * B_BYTES);  // [PH][PWP]
   float* sBias = sImg + PH * PWP;                             // [CP]
-  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) {
-    ptx::mbar_init(&bar[0], 1);
-    ptx::mbar_init(&bar[1], 1);
+    ptx::mbar_init(&bar, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 0) ptx::tmem_alloc<TCOLS>(&tmem_base_s);
@@ -72,67 +80,51 @@ __global__ void __launch_bounds__(128) first_tc_kernel(const FirstArgs a) {
   const long long tiles_per_img = (long long)a.tiles_x * a.tiles_y;
   const long long ntiles = tiles_per_img * a.B;
   const uint32_t a_hi = ptx::umma_desc_hi(1024, 2), b_hi = a_hi;       // SBO = 8 rows x 128 B, SWIZZLE_128B
-  const uint32_t sA_u32 = ptx::smem_u32(sA), sB_u32 = ptx::smem_u32(sB);
+  const uint32_t a_lo0 = (ptx::smem_u32(sA) & 0x3FFFF) >> 4, b_lo0 = (ptx::smem_u32(sB) & 0x3FFFF) >> 4;
 
-  long long prev_tile = -1;
-  int it = 0;
-  uint32_t phases = 0;                               // bit s = parity of the next completion of bar[s]
-  auto epilogue = [&](long long tile, int stage) {
-    ptx::mbar_wait(&bar[stage], (phases >> stage) & 1u);
-    phases ^= 1u << stage;
-    ptx::tc_fence_after();
+  // input window of a tile -> registers (zero outside the image = the conv padding); issued one tile ahead so the
+  // global-load latency hides behind the previous tile's MMA + epilogue
+  float pre[NPRE];
+  auto load_window = [&](long long tile) {
     const int b = (int)(tile / tiles_per_img);
     const int tr = (int)(tile % tiles_per_img);
-    const int oy = (tr / a.tiles_x) * TH + py, ox = (tr % a.tiles_x) * TW + px;
-    const bool ok = oy < a.Ho && ox < a.Wo;
-    __half* dst = a.out + (((size_t)b * a.Ho + oy) * a.Wo + ox) * CP;
-    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + stage * CP;
-#pragma unroll
-    for (int c0 = 0; c0 < CP; c0 += 16) {
-      uint32_t r[16];
-      ptx::tmem_ld16(taddr + c0, r);
-      ptx::tmem_ld_wait();
-      uint32_t pk[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float v0 = __uint_as_float(r[2 * j]) + sBias[c0 + 2 * j];
-        float v1 = __uint_as_float(r[2 * j + 1]) + sBias[c0 + 2 * j + 1];
-        v0 = v0 > 0.f ? v0 : v0 * a.slope;
-        v1 = v1 > 0.f ? v1 : v1 * a.slope;
-        const __half2 h = __floats2half2_rn(v0, v1);
-        pk[j] = *reinterpret_cast<const uint32_t*>(&h);
-      }
-      if (ok) {
-        *reinterpret_cast<uint4*>(dst + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(dst + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      }
-    }
-    ptx::tc_fence_before();
-  };
-
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-    const int stage = it & 1;
-    const int b = (int)(tile / tiles_per_img);
-    const int tr = (int)(tile % tiles_per_img);
-    const int y0 = (tr / a.tiles_x) * TH - a.pad, x0 = (tr % a.tiles_x) * TW - a.pad;   // window origin in the image
-    // 1. input window (sImg was last read before the previous __syncthreads)
+    const int y0 = (tr / a.tiles_x) * TH - a.pad, x0 = (tr % a.tiles_x) * TW - a.pad;
     const float* img = a.x + (size_t)b * a.H * a.W;
-    for (int i = tid; i < PH * PW; i += 128) {
+#pragma unroll
+    for (int e = 0; e < NPRE; ++e) {
+      const int i = tid + e * 128;
       const int wy = i / PW, wx = i - wy * PW;
       const int iy = y0 + wy, ix = x0 + wx;
-      sImg[wy * PWP + wx] = (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) ? img[(size_t)iy * a.W + ix] : 0.f;
+      pre[e] = (i < PH * PW && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) ? __ldg(img + (size_t)iy * a.W + ix) : 0.f;
+    }
+  };
+
+  long long tile = blockIdx.x;
+  if (tile < ntiles) load_window(tile);
+  uint32_t phase = 0;
+  for (; tile < ntiles; tile += gridDim.x) {
+    // 1. window registers -> smem (sImg was last read before the second __syncthreads of the previous iteration)
+#pragma unroll
+    for (int e = 0; e < NPRE; ++e) {
+      const int i = tid + e * 128;
+      if (i < PH * PW) { const int wy = i / PW; sImg[wy * PWP + (i - wy * PW)] = pre[e]; }
     }
     __syncthreads();
-    // 2. this pixel's im2col row (A buffer `stage` was last read by the MMAs of tile it-2, whose completion the
-    //    epilogue of that tile waited for)
+    if (tile + gridDim.x < ntiles) load_window(tile + gridDim.x);
+    // 2. this pixel's im2col row (the A tile was last read by the previous tile's MMAs, whose completion every thread
+    //    waited for before its epilogue)
     {
-      unsigned char* rowp = sA + stage * (KB * A_BYTES) + tid * 128;
+      unsigned char* rowp = sA + tid * 128;
       const float* win = sImg + py * PWP + px;
       const int sw = tid & 7;
 #pragma unroll
       for (int kb = 0; kb < KB; ++kb) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
+          if (kb * 64 + c * 8 >= TAPS) {              // all-zero chunk (K padding)
+            *reinterpret_cast<uint4*>(rowp + kb * A_BYTES + ((c ^ sw) << 4)) = make_uint4(0, 0, 0, 0);
+            continue;
+          }
           uint32_t pk[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -153,42 +145,73 @@ __global__ void __launch_bounds__(128) first_tc_kernel(const FirstArgs a) {
     if (warp == 0) {
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
-        const uint32_t d = tmem_base + stage * CP;
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
-          const uint32_t a_lo = ((sA_u32 + stage * (KB * A_BYTES) + kb * A_BYTES) & 0x3FFFF) >> 4;
-          const uint32_t b_lo = ((sB_u32 + kb * B_BYTES) & 0x3FFFF) >> 4;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            ptx::umma_f16_lohi(d, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, IDESC, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            if (kb * 64 + k * 16 >= TAPS) continue;   // K=16 slice that is entirely padding
+            ptx::umma_f16_lohi(tmem_base, a_lo0 + kb * (A_BYTES >> 4) + 2 * k, a_hi, b_lo0 + kb * (B_BYTES >> 4) + 2 * k,
+                               b_hi, IDESC, (kb | k) ? 1u : 0u);
+          }
         }
-        ptx::umma_commit(&bar[stage]);
+        ptx::umma_commit(&bar);
       }
       __syncwarp();
     }
-    // 4. epilogue of the previous tile while the tensor core works
-    if (prev_tile >= 0) epilogue(prev_tile, stage ^ 1);
-    prev_tile = tile;
+    // 4. epilogue (other CTAs resident on this SM fill the tensor-core / memory pipes meanwhile)
+    ptx::mbar_wait(&bar, phase);
+    phase ^= 1u;
+    ptx::tc_fence_after();
+    {
+      const int b = (int)(tile / tiles_per_img);
+      const int tr = (int)(tile % tiles_per_img);
+      const int oy = (tr / a.tiles_x) * TH + py, ox = (tr % a.tiles_x) * TW + px;
+      const bool ok = oy < a.Ho && ox < a.Wo;
+      __half* dst = a.out + (((size_t)b * a.Ho + oy) * a.Wo + ox) * CP;
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+      for (int c0 = 0; c0 < CP; c0 += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld32(taddr + c0, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int ch = q * 8 + 2 * j;
+            float v0 = __uint_as_float(r[ch]) + sBias[c0 + ch];
+            float v1 = __uint_as_float(r[ch + 1]) + sBias[c0 + ch + 1];
+            v0 = v0 > 0.f ? v0 : v0 * a.slope;
+            v1 = v1 > 0.f ? v1 : v1 * a.slope;
+            const __half2 h = __floats2half2_rn(v0, v1);
+            pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          if (ok) *reinterpret_cast<uint4*>(dst + c0 + q * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+    }
+    ptx::tc_fence_before();
   }
-  if (prev_tile >= 0) epilogue(prev_tile, (it - 1) & 1);
   __syncthreads();
   if (warp == 0) ptx::tmem_dealloc<TCOLS>(tmem_base);
 }
 
 template <int KW, int CP>
 int launch_first(const FirstArgs& a, cudaStream_t stream) {
-  constexpr int TAPS = KW * KW, KB = (TAPS + 63) / 64, PH = TH + KW - 1, PW = (TW + KW - 1) | 1;
-  size_t smem = 1024 + 2 * KB * 128 * 128 + KB * CP * 128 + (PH * PW + CP) * sizeof(float);
-  // resident CTAs per SM are bounded by TMEM (512 columns / 2*CP per CTA, at most 4 wanted); ask for enough shared
-  // memory that the hardware cannot co-schedule more than that (an extra CTA would spin in tcgen05.alloc)
-  int per_sm = 512 / (2 * CP < 32 ? 32 : 2 * CP);
-  if (per_sm > 4) per_sm = 4;
+  using G = FirstGeom<KW>;
+  constexpr int MINB = G::KB == 1 ? 8 : 4;
+  size_t smem = 1024 + G::KB * 128 * 128 + G::KB * CP * 128 + (G::PH * G::PWP + CP) * sizeof(float);
+  // resident CTAs per SM: TMEM allows 512 / max(32, CP); registers / threads allow MINB.  Ask for enough shared memory that
+  // the hardware cannot co-schedule more than that (an extra CTA would spin in tcgen05.alloc until another one exits).
+  int per_sm = 512 / (CP < 32 ? 32 : CP);
+  if (per_sm > MINB) per_sm = MINB;
   while (per_sm > 1 && (size_t)per_sm * (smem + 1024) > 227 * 1024) --per_sm;
   const size_t floor_smem = (227 * 1024) / (per_sm + 1) + 1;
   if (smem < floor_smem) smem = floor_smem;
   static bool configured = false;
   if (!configured) {
-    TPZ_CUDA(cudaFuncSetAttribute(first_tc_kernel<KW, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TPZ_CUDA(cudaFuncSetAttribute(first_tc_kernel<KW, CP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   int dev = 0, sms = 148;
@@ -196,7 +219,7 @@ int launch_first(const FirstArgs& a, cudaStream_t stream) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long ntiles = (long long)a.tiles_x * a.tiles_y * a.B;
   const int grid = (int)(ntiles < (long long)sms * per_sm ? ntiles : (long long)sms * per_sm);
-  first_tc_kernel<KW, CP><<<grid, 128, smem, stream>>>(a);
+  first_tc_kernel<KW, CP, MINB><<<grid, 128, smem, stream>>>(a);
   TPZ_CUDA(cudaGetLastError());
   return 0;
 }
