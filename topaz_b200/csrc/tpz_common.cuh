@@ -154,6 +154,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+// One 32-byte (full L2 sector) global store per thread.  An epilogue thread owns one pixel and writes its channel vector
+// piecewise; with 16-byte pieces every warp-wide store touches 32 half-filled sectors, which doubles the L2 write
+// requests (measured: the HBM-bound Cin=1 layer ran at 1.2 ms instead of ~0.6 ms).  `p` must be 32-byte aligned.
+__device__ __forceinline__ void st_global_256(void* p, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, uint32_t r4,
+                                              uint32_t r5, uint32_t r6, uint32_t r7) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(r4),
+               "r"(r5), "r"(r6), "r"(r7)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor for a K-major operand tile whose rows are `row_bytes` (32/64/128) wide with

@@ -175,11 +175,11 @@ __global__ void __launch_bounds__(128, MINB) first_tc_kernel(const FirstArgs a) 
         ptx::tmem_ld32(taddr + c0, r);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint32_t pk[4];
+        for (int q = 0; q < 2; ++q) {                 // 16 channels = 32 B = one full sector per store
+          uint32_t pk[8];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int ch = q * 8 + 2 * j;
+          for (int j = 0; j < 8; ++j) {
+            const int ch = q * 16 + 2 * j;
             float v0 = __uint_as_float(r[ch]) + sBias[c0 + ch];
             float v1 = __uint_as_float(r[ch + 1]) + sBias[c0 + ch + 1];
             v0 = v0 > 0.f ? v0 : v0 * a.slope;
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(128, MINB) first_tc_kernel(const FirstArgs a) 
             const __half2 h = __floats2half2_rn(v0, v1);
             pk[j] = *reinterpret_cast<const uint32_t*>(&h);
           }
-          if (ok) *reinterpret_cast<uint4*>(dst + c0 + q * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          if (ok) ptx::st_global_256(dst + c0 + q * 16, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
         }
       }
     }

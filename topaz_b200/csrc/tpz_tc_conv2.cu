@@ -334,14 +334,23 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv2_kernel(const __grid_cons
               if (j < nc) dot = fmaf(v[j], s_dotw[c + j], dot);
           }
           if (orow && valid) {
+            // 32-byte stores (one full L2 sector each) when the channel slice is 32-byte aligned, else 16-byte pieces
+            const bool wide = ((reinterpret_cast<uintptr_t>(orow + c) & 31) == 0);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (q * 8 < nc) {
-                uint4 u;
-                __half2* h = reinterpret_cast<__half2*>(&u);
+            for (int q = 0; q < 2; ++q) {
+              if (q * 16 < nc) {
+                uint32_t u[8];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[q * 8 + e * 2], v[q * 8 + e * 2 + 1]);
-                *reinterpret_cast<uint4*>(orow + c + q * 8) = u;
+                for (int e = 0; e < 8; ++e) {
+                  const __half2 h = __floats2half2_rn(v[q * 16 + e * 2], v[q * 16 + e * 2 + 1]);
+                  u[e] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                if (wide && q * 16 + 8 < nc) {
+                  ptx::st_global_256(orow + c + q * 16, u[0], u[1], u[2], u[3], u[4], u[5], u[6], u[7]);
+                } else {
+                  *reinterpret_cast<uint4*>(orow + c + q * 16) = make_uint4(u[0], u[1], u[2], u[3]);
+                  if (q * 16 + 8 < nc) *reinterpret_cast<uint4*>(orow + c + q * 16 + 8) = make_uint4(u[4], u[5], u[6], u[7]);
+                }
               }
             }
           }
