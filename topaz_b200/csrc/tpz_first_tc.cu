@@ -158,16 +158,18 @@ __global__ void __launch_bounds__(128, MINB) first_tc_kernel(const FirstArgs a) 
       }
       __syncwarp();
     }
-    // 4. epilogue (other CTAs resident on this SM fill the tensor-core / memory pipes meanwhile)
+    // 4. epilogue (other CTAs resident on this SM fill the tensor-core / memory pipes meanwhile).  The finished MMAs no
+    //    longer need the A tile, so its first CP*256 bytes stage the fp16 output tile: each thread deposits its pixel's
+    //    channel vector (16-byte chunks, XOR-swizzled against bank conflicts), then the warp writes its 32 pixels back
+    //    with every store instruction covering whole 128-byte lines (CP*2/32 lanes per pixel, 32 bytes per lane).
     ptx::mbar_wait(&bar, phase);
     phase ^= 1u;
     ptx::tc_fence_after();
     {
-      const int b = (int)(tile / tiles_per_img);
-      const int tr = (int)(tile % tiles_per_img);
-      const int oy = (tr / a.tiles_x) * TH + py, ox = (tr % a.tiles_x) * TW + px;
-      const bool ok = oy < a.Ho && ox < a.Wo;
-      __half* dst = a.out + (((size_t)b * a.Ho + oy) * a.Wo + ox) * CP;
+      constexpr int ROWB = CP * 2;                    // bytes per pixel
+      constexpr int CH16 = ROWB / 16;                 // 16-byte chunks per pixel (4 or 8)
+      unsigned char* stg = sA + (size_t)tid * ROWB;
+      const int sw = tid & (CH16 - 1);
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
 #pragma unroll
       for (int c0 = 0; c0 < CP; c0 += 32) {
@@ -175,11 +177,11 @@ __global__ void __launch_bounds__(128, MINB) first_tc_kernel(const FirstArgs a) 
         ptx::tmem_ld32(taddr + c0, r);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {                 // 16 channels = 32 B = one full sector per store
-          uint32_t pk[8];
+        for (int q = 0; q < 4; ++q) {
+          uint32_t pk[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int ch = q * 16 + 2 * j;
+          for (int j = 0; j < 4; ++j) {
+            const int ch = q * 8 + 2 * j;
             float v0 = __uint_as_float(r[ch]) + sBias[c0 + ch];
             float v1 = __uint_as_float(r[ch + 1]) + sBias[c0 + ch + 1];
             v0 = v0 > 0.f ? v0 : v0 * a.slope;
@@ -187,8 +189,28 @@ __global__ void __launch_bounds__(128, MINB) first_tc_kernel(const FirstArgs a) 
             const __half2 h = __floats2half2_rn(v0, v1);
             pk[j] = *reinterpret_cast<const uint32_t*>(&h);
           }
-          if (ok) ptx::st_global_256(dst + c0 + q * 16, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+          *reinterpret_cast<uint4*>(stg + (((c0 / 8 + q) ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
+      }
+      __syncwarp();
+      constexpr int LPP = ROWB / 32;                  // lanes per pixel (2 or 4), 32 bytes each
+      constexpr int PPI = 32 / LPP;                   // pixels per store instruction
+      const int lane = tid & 31;
+      const int b = (int)(tile / tiles_per_img);
+      const int tr = (int)(tile % tiles_per_img);
+      const int ty0 = (tr / a.tiles_x) * TH, tx0 = (tr % a.tiles_x) * TW;
+#pragma unroll
+      for (int i = 0; i < 32 / PPI; ++i) {
+        const int pix = warp * 32 + i * PPI + lane / LPP;        // pixel (row of the tile) this lane helps to write
+        const int part = lane % LPP;                              // which 32-byte piece of its channel vector
+        const int oy = ty0 + pix / TW, ox = tx0 + pix % TW;
+        const unsigned char* src = sA + (size_t)pix * ROWB;
+        const int psw = pix & (CH16 - 1);
+        const uint4 lo = *reinterpret_cast<const uint4*>(src + (((2 * part) ^ psw) << 4));
+        const uint4 hi = *reinterpret_cast<const uint4*>(src + (((2 * part + 1) ^ psw) << 4));
+        if (oy < a.Ho && ox < a.Wo)
+          ptx::st_global_256(a.out + (((size_t)b * a.Ho + oy) * a.Wo + ox) * CP + part * 16, lo.x, lo.y, lo.z, lo.w, hi.x, hi.y,
+                             hi.z, hi.w);
       }
     }
     ptx::tc_fence_before();
