@@ -1,4 +1,6 @@
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "fused_first or resnet8_u64 or unet_pretrained" 2>&1 | tail -3 || exit 1
-TPZ_FIRST=tc timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 30 --csv --log-file gpurun_out/launches_stage.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
-grep -E "first_tc" gpurun_out/launches_stage.csv | tail -2 | cut -c1-300
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -3
+timeout 600 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; tail -c 2600 gpurun_out/bench_final.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches_final.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+timeout 600 python tools/bench_extra.py --workloads denoise,train,denoise3d --steps 4 2>&1 | tail -4 | cut -c1-330
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
