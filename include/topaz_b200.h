@@ -177,6 +177,8 @@ int tpz_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq
 /* ---- hardware probe used by tests/bring-up (UMMA descriptor row-offset behaviour), not on the product path ---- */
 int tpz_lab_umma(const tpz_half* A, int rowsA, const tpz_half* B, int N, int shift, int sbo_rows, int base_off_mode,
                  int kc, float* D, void* stream);
+/* CTA-pair probe: tcgen05.mma.cta_group::2 (M = 256 over two CTAs of a cluster), operands by generic stores or pair TMA. */
+int tpz_lab_umma_pair(const tpz_half* A, const tpz_half* B, int N, int use_tma, float* D, int* status, void* stream);
 int tpz_lab_umma_rate(int N, int shift, int sbo_rows, int iters, int two_acc, long long* cycles, void* stream);
 int tpz_lab_tma_stride(const tpz_half* A, int rowsA, int start, int stride, int nrows, tpz_half* out, void* stream);
 

@@ -56,6 +56,7 @@ _PROTOS = {
     'tpz_make_crops': (_I, [_I, _I, _I, _P, _P, _P, _P, _P]),
     'tpz_conv_first_tc': (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _I, _F, _P, _P]),
     'tpz_conv_first_tc_supported': (_I, [_I, _I]),
+    'tpz_lab_umma_pair': (_I, [_P, _P, _I, _I, _P, _P, _P]),
     'tpz_gemm_f32': (_I, [_P, _LL, _I, _P, _I, _P, _P]),
     'tpz_gmm_sums': (_I, [_P, _LL, C.c_double, _P, _I, _P, _P]),
     'tpz_select_hist': (_I, [_P, _LL, _I, _P, _I, _P, _P]),

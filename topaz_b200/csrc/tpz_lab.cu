@@ -188,3 +188,111 @@ extern "C" int tpz_lab_umma_rate(int N, int shift, int sbo_rows, int iters, int 
   TPZ_CUDA(cudaGetLastError());
   return 0;
 }
+
+
+// ---- probe 4: CTA-pair MMA (tcgen05.mma.cta_group::2, M = 256 across two CTAs of a cluster).  Each CTA holds rows
+// [128*rank, 128*rank+128) of A and rows [N/2*rank, N/2*rank+N/2) of B (K = 64, SWIZZLE_128B), filled either by generic
+// stores (use_tma = 0) or by pair TMA loads that credit the leader's barrier (use_tma = 1).  D: fp32 [256][N].
+// status[0] != 0 reports a timed-out wait (all waits are bounded so a wrong assumption cannot hang the GPU). ----
+namespace {
+__device__ __forceinline__ bool lab_wait(uint64_t* bar, uint32_t parity, int* status, int code) {
+  for (int spins = 0; spins < (1 << 24); ++spins)
+    if (lab_try(bar, parity)) return true;
+  if (status) atomicExch(status, code);
+  return false;
+}
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+lab_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __half* A,
+                const __half* B, int N, int use_tma, float* D, int* status) {
+  extern __shared__ uint8_t smem_raw4[];
+  const uint32_t raw = ptx::smem_u32(smem_raw4);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw4 + (base - raw);
+  uint8_t* sA = smem;                       // 128 rows x 128 B
+  uint8_t* sB = smem + 16384;               // N/2 rows x 128 B
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + 16384 + 16384);
+  uint64_t* bar_done = bar_full + 1;
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar_done + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int nb = N / 2;
+  if (tid == 0) {
+    ptx::mbar_init(bar_full, 1);
+    ptx::mbar_init(bar_done, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) ptx::tmem_alloc_pair<256>(slot);
+  if (!use_tma) {
+    for (int i = tid; i < 128 * 8; i += 128) {
+      const int r = i >> 3, c = i & 7;
+      *reinterpret_cast<uint4*>(sA + r * 128 + ((c ^ (r & 7)) << 4)) =
+          *reinterpret_cast<const uint4*>(A + ((size_t)(rank * 128 + r) * 64 + c * 8));
+    }
+    for (int i = tid; i < nb * 8; i += 128) {
+      const int r = i >> 3, c = i & 7;
+      *reinterpret_cast<uint4*>(sB + r * 128 + ((c ^ (r & 7)) << 4)) =
+          *reinterpret_cast<const uint4*>(B + ((size_t)(rank * nb + r) * 64 + c * 8));
+    }
+    ptx::fence_proxy_async();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *slot;
+  if (use_tma && tid == 0) {
+    if (rank == 0) ptx::mbar_expect_tx(bar_full, (uint32_t)(2 * (16384 + nb * 128)));
+    ptx::tma_load_2d_pair(sA, &tmA, bar_full, 0, (int)rank * 128);
+    ptx::tma_load_2d_pair(sB, &tmB, bar_full, 0, (int)rank * nb);
+  }
+  if (rank == 0 && warp == 0) {
+    bool ok = true;
+    if (use_tma) ok = lab_wait(bar_full, 0, status, 1);
+    ptx::tc_fence_after();
+    if (ptx::elect_one()) {
+      const uint32_t hi = ptx::umma_desc_hi(1024, 2);
+      const uint32_t a_lo = ((base) & 0x3FFFF) >> 4, b_lo = ((base + 16384) & 0x3FFFF) >> 4;
+      const uint32_t idesc = ptx::umma_idesc_f16_pair(N);
+      for (int k = 0; k < 4; ++k) ptx::umma_f16_pair(tmem, a_lo + 2 * k, hi, b_lo + 2 * k, hi, idesc, k != 0);
+      ptx::umma_commit_pair(bar_done);
+    }
+    __syncwarp();
+    (void)ok;
+  }
+  lab_wait(bar_done, 0, status, 2 + (int)rank);
+  ptx::tc_fence_after();
+  const int row = (int)rank * 128 + tid;
+  for (int c = 0; c < N; c += 16) {
+    uint32_t r[16];
+    ptx::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c, r);
+    ptx::tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) D[(size_t)row * N + c + j] = __uint_as_float(r[j]);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  if (warp == 0) ptx::tmem_dealloc_pair<256>(tmem);
+}
+}  // namespace
+
+// A: device fp16 [256][64], B: device fp16 [N][64] (N % 32 == 0, N <= 256), D: device fp32 [256][N], status: device int[1]
+extern "C" int tpz_lab_umma_pair(const tpz_half* A, const tpz_half* B, int N, int use_tma, float* D, int* status, void* stream) {
+  TPZ_CHECK(N % 32 == 0 && N >= 32 && N <= 256, "tpz_lab_umma_pair: bad N=%d", N);
+  CUtensorMap tmA, tmB;
+  uint64_t dA[2] = {64, 256}, sA[1] = {128};
+  uint32_t bA[2] = {64, 128}, es[2] = {1, 1};
+  int rc = tpz_encode_tmap(&tmA, A, 2, dA, sA, bA, es, 128);
+  if (rc) return rc;
+  uint64_t dB[2] = {64, (uint64_t)N};
+  uint32_t bB[2] = {64, (uint32_t)(N / 2)};
+  rc = tpz_encode_tmap(&tmB, B, 2, dB, sA, bB, es, 128);
+  if (rc) return rc;
+  const int smem = 16384 + 16384 + 1024 + 256;
+  TPZ_CUDA(cudaFuncSetAttribute(lab_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  TPZ_CUDA(cudaMemsetAsync(status, 0, sizeof(int), reinterpret_cast<cudaStream_t>(stream)));
+  lab_pair_kernel<<<2, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tmA, tmB, reinterpret_cast<const __half*>(A),
+                                                                            reinterpret_cast<const __half*>(B), N, use_tma, D,
+                                                                            status);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
