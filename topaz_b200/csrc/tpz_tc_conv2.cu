@@ -72,9 +72,10 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Bounded spin: a protocol error (wrong arrival count, lost TMA credit) traps after ~10 s instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try(bar, parity)) {
-  }
+  for (uint32_t spins = 0; !mbar_try(bar, parity); ++spins)
+    if (spins > (1u << 28)) __trap();
 }
 
 struct TileCoord {
@@ -99,10 +100,22 @@ __device__ __forceinline__ TileCoord decode_tile(const Tc2Params& p, int tile) {
   return t;
 }
 
-template <int KC>
+// PAIR = true: the kernel is launched in clusters of two CTAs (one TPC) that issue M = 256 MMAs together
+// (tcgen05 cta_group::2).  CTA `rank` works on tile 2T + rank of super-tile T with its own halo tiles and accumulators
+// and holds HALF of every weight block (rows rank*Co/2 ...), so the shared-memory operand traffic per MMA drops from
+// A + B to A + B/2 per SM -- the N <= 128 layers are bound by exactly that traffic.  The even CTA (leader) issues all
+// MMAs; TMA loads of both CTAs credit the leader's "full" barriers, tcgen05.commit multicasts the "empty" / "accumulator
+// full" arrivals to both CTAs, and both epilogues release an accumulator stage on the leader's barrier.
+template <int KC, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1) tc_conv2_kernel(const __grid_constant__ Tc2Params p) {
   constexpr int ROWB = KC * 2;
   constexpr uint32_t LAYOUT = (KC == 64) ? 2u : 4u;
+  const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int cta_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // first super-tile of this CTA (pair)
+  const int cta_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int nsuper = PAIR ? (p.num_tiles + 1) >> 1 : p.num_tiles;
+  const int last_tile = p.num_tiles - 1;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
@@ -141,12 +154,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv2_kernel(const __grid_cons
     for (int s = 0; s < kMaxAStages; ++s) { ptx::mbar_init(&afull[s], 1); ptx::mbar_init(&aempty[s], 1); }
     for (int s = 0; s < kMaxBStages; ++s) { ptx::mbar_init(&bfull[s], 1); ptx::mbar_init(&bempty[s], 1); }
     ptx::mbar_init(bres, 1);
-    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 4); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], PAIR ? 8 : 4); }
     ptx::fence_barrier_init();
   }
-  if (warp == 2) ptx::tmem_alloc<kTmemCols>(tmem_slot);
+  if (warp == 2) {
+    if (PAIR) ptx::tmem_alloc_pair<kTmemCols>(tmem_slot); else ptx::tmem_alloc<kTmemCols>(tmem_slot);
+  }
   ptx::tc_fence_before();
   __syncthreads();
+  if (PAIR) ptx::cluster_sync();        // the peer's barriers are initialised before any remote arrive / TMA credit
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -155,7 +171,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv2_kernel(const __grid_cons
     // warp-uniform loop; the TMA instructions are issued by one elected lane (keeps operands in uniform registers)
     {
       uint32_t s = 0, ph = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int T = cta_first; T < nsuper; T += cta_step) {
+        const int tile = PAIR ? min(2 * T + (int)rank, last_tile) : T;      // an odd tile count leaves the peer a repeat
         const TileCoord tc = decode_tile(p, tile);
         for (int g = 0; g < p.ngroups; ++g) {
           mbar_wait(&aempty[s], ph ^ 1);
@@ -165,12 +182,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv2_kernel(const __grid_cons
           const int sr = p.split_rows[src];
           uint8_t* dst = smem + (size_t)s * p.a_stage_bytes;
           if (ptx::elect_one()) {
-            ptx::mbar_expect_tx(&afull[s], (uint32_t)(hx * p.rows_loaded[src] * ROWB));
+            const uint32_t bytes = (uint32_t)(hx * p.rows_loaded[src] * ROWB);
+            if (!PAIR) ptx::mbar_expect_tx(&afull[s], bytes);
+            else if (leader) ptx::mbar_expect_tx(&afull[s], 2 * bytes);
             for (int row0 = 0; row0 < p.rows_loaded[src]; row0 += sr) {
-              ptx::tma_load_5d(dst + (size_t)row0 * hx * ROWB, &p.tmA[src], &afull[s], G.c0,
-                               tc.qx * p.slat[src] + p.sphase[src] * tc.phx + p.org[src][0] + G.gox,
-                               (tc.qy + row0) * p.slat[src] + p.sphase[src] * tc.phy + p.org[src][1] + G.goy,
-                               tc.z * p.slatz[src] + p.sphase[src] * p.phz + p.org[src][2] + G.dz, tc.n);
+              const int cx = tc.qx * p.slat[src] + p.sphase[src] * tc.phx + p.org[src][0] + G.gox;
+              const int cy = (tc.qy + row0) * p.slat[src] + p.sphase[src] * tc.phy + p.org[src][1] + G.goy;
+              const int cz = tc.z * p.slatz[src] + p.sphase[src] * p.phz + p.org[src][2] + G.dz;
+              if (PAIR) ptx::tma_load_5d_pair(dst + (size_t)row0 * hx * ROWB, &p.tmA[src], &afull[s], G.c0, cx, cy, cz, tc.n);
+              else ptx::tma_load_5d(dst + (size_t)row0 * hx * ROWB, &p.tmA[src], &afull[s], G.c0, cx, cy, cz, tc.n);
             }
           }
           __syncwarp();
@@ -182,23 +202,32 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv2_kernel(const __grid_cons
     // ------------------------------ B producer: weights, resident or streamed per tap ------------------------------
     if (p.b_resident) {
       if (ptx::elect_one()) {
-        ptx::mbar_expect_tx(bres, (uint32_t)(p.nkb * p.b_block_bytes));
-        for (int kb = 0; kb < p.nkb; ++kb)
-          ptx::tma_load_2d(smem + (size_t)AS * p.a_stage_bytes + (size_t)kb * p.b_block_bytes, &p.tmB, bres, 0,
-                           kb * p.Co);
+        const uint32_t bytes = (uint32_t)(p.nkb * p.b_block_bytes);
+        if (!PAIR) ptx::mbar_expect_tx(bres, bytes);
+        else if (leader) ptx::mbar_expect_tx(bres, 2 * bytes);
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          uint8_t* dst = smem + (size_t)AS * p.a_stage_bytes + (size_t)kb * p.b_block_bytes;
+          if (PAIR) ptx::tma_load_2d_pair(dst, &p.tmB, bres, 0, kb * p.Co + (int)rank * (p.Co >> 1));
+          else ptx::tma_load_2d(dst, &p.tmB, bres, 0, kb * p.Co);
+        }
       }
     } else {
       uint32_t s = 0, ph = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int T = cta_first; T < nsuper; T += cta_step) {
         for (int g = 0; g < p.ngroups; ++g) {
           const Tc2Group G = p.groups[g];
           for (int t = 0; t < G.ntaps; ++t) {
             mbar_wait(&bempty[s], ph ^ 1);
             const int kb = (int)p.taps[G.tap_begin + t].kb;
             if (ptx::elect_one()) {
-              ptx::mbar_expect_tx(&bfull[s], (uint32_t)p.b_block_bytes);
-              ptx::tma_load_2d(smem + (size_t)AS * p.a_stage_bytes + (size_t)s * p.b_block_bytes, &p.tmB, &bfull[s], 0,
-                               kb * p.Co);
+              uint8_t* dst = smem + (size_t)AS * p.a_stage_bytes + (size_t)s * p.b_block_bytes;
+              if (!PAIR) {
+                ptx::mbar_expect_tx(&bfull[s], (uint32_t)p.b_block_bytes);
+                ptx::tma_load_2d(dst, &p.tmB, &bfull[s], 0, kb * p.Co);
+              } else {
+                if (leader) ptx::mbar_expect_tx(&bfull[s], 2u * (uint32_t)p.b_block_bytes);
+                ptx::tma_load_2d_pair(dst, &p.tmB, &bfull[s], 0, kb * p.Co + (int)rank * (p.Co >> 1));
+              }
             }
             __syncwarp();
             if (++s == (uint32_t)BS) { s = 0; ph ^= 1; }
@@ -206,13 +235,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv2_kernel(const __grid_cons
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------ MMA issuer ------------------------------
+  } else if (warp == 1 && leader) {
+    // ------------------------------ MMA issuer (pair mode: the leader CTA only) ------------------------------
     // The whole warp walks the (warp-uniform) loops so addresses/descriptors live in uniform registers; lane 0
     // issues the tcgen05 instructions.  Measured on B200 (tools/layer_bench.py): back-to-back MMAs into ONE
     // accumulator are latency-chained (N=64: 93 cycles each), alternating two accumulators reaches 48 (N=64) /
     // 64 (N=128) / 128 (N=256) cycles, so the issue loop must stay well below ~40 instructions per MMA pair.
-    const uint32_t idesc = ptx::umma_idesc_f16(128, p.Co);
+    const uint32_t idesc = PAIR ? ptx::umma_idesc_f16_pair(p.Co) : ptx::umma_idesc_f16(128, p.Co);
     const uint32_t b_hi = ptx::umma_desc_hi(8 * ROWB, LAYOUT);
     if (p.b_resident) {
       mbar_wait(bres, 0);
@@ -221,7 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv2_kernel(const __grid_cons
     const bool two = p.ntile == 2;
     const bool resident = p.b_resident != 0;
     uint32_t as = 0, aph = 0, bs = 0, bph = 0, st = 0, tph = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int T = cta_first; T < nsuper; T += cta_step) {
       mbar_wait(&tempty[st], tph ^ 1);
       ptx::tc_fence_after();
       const uint32_t d0 = tmem_base + (st * p.ntile) * p.CS;
@@ -233,36 +262,41 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv2_kernel(const __grid_cons
         const Tc2Group G = p.groups[g];
         const uint32_t hxb = (uint32_t)p.hx[G.src] * ROWB;          // bytes between consecutive tile rows (y)
         const uint32_t a_hi = ptx::umma_desc_hi(hxb, LAYOUT);
-        const uint32_t a_tile_lo = (a_base + as * (uint32_t)p.a_stage_bytes) >> 4;
+        const uint32_t a_tile_lo = ((a_base + as * (uint32_t)p.a_stage_bytes) & 0x3FFFFu) >> 4;
         const uint32_t a1_off_lo = (16u * hxb) >> 4;
         for (int t = 0; t < G.ntaps; ++t) {
           const Tc2Tap T = p.taps[G.tap_begin + t];
           uint32_t b_lo;
           if (resident) {
-            b_lo = (b_base + (uint32_t)T.kb * p.b_block_bytes) >> 4;
+            b_lo = ((b_base + (uint32_t)T.kb * p.b_block_bytes) & 0x3FFFFu) >> 4;
           } else {
             mbar_wait(&bfull[bs], bph);
             ptx::tc_fence_after();
-            b_lo = (b_base + bs * (uint32_t)p.b_block_bytes) >> 4;
+            b_lo = ((b_base + bs * (uint32_t)p.b_block_bytes) & 0x3FFFFu) >> 4;
           }
           const uint32_t a0_lo = a_tile_lo + (((uint32_t)T.row_off * ROWB) >> 4);
           if (ptx::elect_one()) {
 #pragma unroll
             for (int k = 0; k < KC / 16; ++k) {
-              ptx::umma_f16_lohi(d0, a0_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, (k == 0) ? accf : 1u);
-              if (two) ptx::umma_f16_lohi(d1, a0_lo + a1_off_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, (k == 0) ? accf : 1u);
+              if (PAIR) {
+                ptx::umma_f16_pair(d0, a0_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, (k == 0) ? accf : 1u);
+                if (two) ptx::umma_f16_pair(d1, a0_lo + a1_off_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, (k == 0) ? accf : 1u);
+              } else {
+                ptx::umma_f16_lohi(d0, a0_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, (k == 0) ? accf : 1u);
+                if (two) ptx::umma_f16_lohi(d1, a0_lo + a1_off_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, (k == 0) ? accf : 1u);
+              }
             }
-            if (!resident) ptx::umma_commit(&bempty[bs]);
+            if (!resident) { if (PAIR) ptx::umma_commit_pair(&bempty[bs]); else ptx::umma_commit(&bempty[bs]); }
           }
           accf = 1;
           if (!resident) {
             if (++bs == (uint32_t)BS) { bs = 0; bph ^= 1; }
           }
         }
-        if (ptx::elect_one()) ptx::umma_commit(&aempty[as]);
+        if (ptx::elect_one()) { if (PAIR) ptx::umma_commit_pair(&aempty[as]); else ptx::umma_commit(&aempty[as]); }
         if (++as == (uint32_t)AS) { as = 0; aph ^= 1; }
       }
-      if (ptx::elect_one()) ptx::umma_commit(&tfull[st]);
+      if (ptx::elect_one()) { if (PAIR) ptx::umma_commit_pair(&tfull[st]); else ptx::umma_commit(&tfull[st]); }
       if (p.acc_stages == 2) { st ^= 1; if (st == 0) tph ^= 1; } else { tph ^= 1; }
     }
   } else if (warp >= 4) {
@@ -271,8 +305,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv2_kernel(const __grid_cons
     const int m = ew * 32 + lane;
     const int li = m & 7, lj = m >> 3;   // lattice point (li, lj) of accumulator 0; accumulator 1 is 16 rows lower
     uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
-      const TileCoord tc = decode_tile(p, tile);
+    for (int T = cta_first; T < nsuper; T += cta_step, ++tcount) {
+      const int tile_raw = PAIR ? 2 * T + (int)rank : T;
+      const bool tile_ok = tile_raw <= last_tile;                       // pair mode, odd tile count: nothing to write
+      const TileCoord tc = decode_tile(p, tile_ok ? tile_raw : last_tile);
       const uint32_t st = (p.acc_stages == 2) ? (tcount & 1) : 0;
       const uint32_t aph = (p.acc_stages == 2) ? ((tcount >> 1) & 1) : (tcount & 1);
       mbar_wait(&tfull[st], aph);
@@ -280,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv2_kernel(const __grid_cons
       for (int a = 0; a < p.ntile; ++a) {
         const int gx = (tc.qx + li) * p.L + tc.phx;
         const int gy = (tc.qy + lj + 16 * a) * p.L + tc.phy;
-        const bool valid = (gx < p.Wo) && (gy < p.Ho);
+        const bool valid = tile_ok && (gx < p.Wo) && (gy < p.Ho);
         const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (st * p.ntile + a) * p.CS;
         const int gz = tc.z * p.Lz + p.phz;
         const long long opix = (((long long)tc.n * p.Do + gz) * p.Ho + gy) * p.Wo + gx;
@@ -363,13 +399,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv2_kernel(const __grid_cons
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty[st]);
+      if (lane == 0) { if (PAIR) ptx::mbar_arrive_leader(&tempty[st]); else ptx::mbar_arrive(&tempty[st]); }
     }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 2) ptx::tmem_dealloc<kTmemCols>(tmem_base);
+  if (PAIR) ptx::cluster_sync();        // no CTA leaves while its peer may still signal its barriers / write its TMEM
+  if (warp == 2) {
+    if (PAIR) ptx::tmem_dealloc_pair<kTmemCols>(tmem_base); else ptx::tmem_dealloc<kTmemCols>(tmem_base);
+  }
 }
 
 int g_num_sms2 = 0;
@@ -443,7 +482,19 @@ static int launch_v2(const TpzTcConvArgs* a, cudaStream_t stream, bool dry) {
     ++ng;
   }
   p.ngroups = ng; p.nkb = a->nkb;
-  p.b_block_bytes = a->Co * rowb;
+  // CTA-pair mode (tcgen05 cta_group::2): each CTA of a cluster of two keeps half of every weight block.
+  // TPZ_TC_PAIR = 0 never, 1 whenever eligible, unset: the layers whose MMAs are shared-memory-operand bound (Co <= 128).
+  static const int pair_env = getenv("TPZ_TC_PAIR") ? atoi(getenv("TPZ_TC_PAIR")) : -1;
+  long long ntl_early;
+  {
+    const int lz = a->lattice_z > 1 ? a->lattice_z : 1;
+    const long long dq = (a->Do - a->phase_z + lz - 1) / lz;
+    ntl_early = (long long)(a->phase_sel > 0 ? 1 : L * L) * tpz_div_up(tpz_div_up(a->Wo, L), T2W) *
+                tpz_div_up(tpz_div_up(a->Ho, L), th) * (dq > 0 ? dq : 0) * a->N;
+  }
+  const bool pair_ok = a->Co % 32 == 0 && a->Co >= 64 && ntl_early >= 2;
+  const bool pair = pair_ok && (pair_env == 1 || (pair_env < 0 && a->Co <= 128));
+  p.b_block_bytes = (pair ? a->Co / 2 : a->Co) * rowb;
   const int tail = 4096;
   const int budget = 227 * 1024 - 1024 - tail;
   const int resident_bytes = a->nkb * p.b_block_bytes;
@@ -482,7 +533,7 @@ static int launch_v2(const TpzTcConvArgs* a, cudaStream_t stream, bool dry) {
   {
     uint64_t dims[2] = {(uint64_t)a->KC, (uint64_t)a->nkb * a->Co};
     uint64_t strides[1] = {(uint64_t)rowb};
-    uint32_t box[2] = {(uint32_t)a->KC, (uint32_t)a->Co};
+    uint32_t box[2] = {(uint32_t)a->KC, (uint32_t)(pair ? a->Co / 2 : a->Co)};
     uint32_t es[2] = {1, 1};
     int rc = tpz_encode_tmap(&p.tmB, a->weights, 2, dims, strides, box, es, rowb);
     if (rc) return rc;
@@ -518,13 +569,35 @@ static int launch_v2(const TpzTcConvArgs* a, cudaStream_t stream, bool dry) {
   const int b_region = p.b_resident ? resident_bytes : p.b_stages * p.b_block_bytes;
   int smem = p.a_stages * a_stage + b_region + tail + 1024;
   if (smem < 120 * 1024) smem = 120 * 1024;  // 1 CTA / SM (every CTA owns all 512 TMEM columns)
+  if (pair) {
+    // clusters of two CTAs; an odd tile count leaves the second CTA of the last pair a repeat tile it does not write
+    int grid = 2 * ((p.num_tiles + 1) / 2);
+    const int cap = g_num_sms2 & ~1;
+    if (grid > cap) grid = cap;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid, 1, 1); cfg.blockDim = dim3(kThreads, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    if (a->KC == 64) {
+      TPZ_CUDA(cudaFuncSetAttribute(tc_conv2_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      TPZ_CUDA(cudaLaunchKernelEx(&cfg, tc_conv2_kernel<64, true>, p));
+    } else {
+      TPZ_CUDA(cudaFuncSetAttribute(tc_conv2_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      TPZ_CUDA(cudaLaunchKernelEx(&cfg, tc_conv2_kernel<32, true>, p));
+    }
+    TPZ_CUDA(cudaGetLastError());
+    return 0;
+  }
   const int grid = p.num_tiles < g_num_sms2 ? p.num_tiles : g_num_sms2;
   if (a->KC == 64) {
-    TPZ_CUDA(cudaFuncSetAttribute(tc_conv2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    tc_conv2_kernel<64><<<grid, kThreads, smem, stream>>>(p);
+    TPZ_CUDA(cudaFuncSetAttribute(tc_conv2_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    tc_conv2_kernel<64, false><<<grid, kThreads, smem, stream>>>(p);
   } else {
-    TPZ_CUDA(cudaFuncSetAttribute(tc_conv2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    tc_conv2_kernel<32><<<grid, kThreads, smem, stream>>>(p);
+    TPZ_CUDA(cudaFuncSetAttribute(tc_conv2_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    tc_conv2_kernel<32, false><<<grid, kThreads, smem, stream>>>(p);
   }
   TPZ_CUDA(cudaGetLastError());
   return 0;
