@@ -241,6 +241,7 @@ def main():
     n_e2e = 0
     for out in score_arrays(model, (host[i % nimg].numpy() for i in range(args.steps)), device=local):
         n_e2e += 1
+        assert out.shape == (S, S), f'end-to-end leg produced {out.shape}, expected {(S, S)} (same network as the timed leg)'
     tcuda1.record()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - e0

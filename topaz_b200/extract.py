@@ -13,6 +13,17 @@ from topaz_b200.model.utils import predict_in_patches
 from topaz_b200.mrc import load_image
 
 
+def _ensure_filled(model):
+    """Dense mode for scoring (reference extract.py:231-232 calls fill() unconditionally on a freshly loaded model; a
+    second fill() would multiply the ResidA dilations again -- in the reference too -- so an already filled model is left
+    as it is)."""
+    from topaz_b200.engine import is_filled
+    model.eval()
+    if not is_filled(model.features):
+        model.fill()
+    return model
+
+
 def score_images(model: Union[torch.nn.Module, str], paths: Union[List[str], Iterable[str]], device: int = 0,
                  patch_size: int = 0, batch_size: int = 1) -> Iterator[Tuple[str, np.ndarray]]:
     if model is not None and model != 'none':
@@ -21,8 +32,7 @@ def score_images(model: Union[torch.nn.Module, str], paths: Union[List[str], Ite
         torch.cuda.set_device(device)
         if isinstance(model, str):
             model = load_model(model)
-        model.eval()
-        model.fill()
+        _ensure_filled(model)
         model.cuda()
         if patch_size:
             for path, image in _prefetch(paths):
@@ -75,7 +85,7 @@ def score_arrays(model: torch.nn.Module, images: Iterable[np.ndarray], device: i
     """Array-in / array-out variant used by bench.py's end-to-end leg: double-buffered pinned H2D / D2H on
     side streams so copies of image i+1 / i-1 overlap the network of image i."""
     torch.cuda.set_device(device)
-    model.eval(); model.fill(); model.cuda()
+    _ensure_filled(model); model.cuda()
     return _score_stream(model, images, pinned)
 
 
@@ -129,7 +139,7 @@ def pick_arrays(model: torch.nn.Module, images: Iterable[np.ndarray], radius: in
     the 2 x 64 MB of PCIe traffic per 4096^2 micrograph and the reference's multi-second Python NMS loop."""
     from topaz_b200.algorithms import non_maximum_suppression
     torch.cuda.set_device(device)
-    model.eval(); model.fill(); model.cuda()
+    _ensure_filled(model); model.cuda()
     copy_in = torch.cuda.Stream()
     main = torch.cuda.current_stream()
     nxt = None
