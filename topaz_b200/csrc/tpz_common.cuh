@@ -225,6 +225,11 @@ __device__ __forceinline__ void st_global_256(void* p, uint32_t r0, uint32_t r1,
                "r"(r5), "r"(r6), "r"(r7)
                : "memory");
 }
+__device__ __forceinline__ void ld_global_256(const void* p, uint32_t (&r)[8]) {     // 32-byte aligned, read-only path
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor for a K-major operand tile whose rows are `row_bytes` (32/64/128) wide with

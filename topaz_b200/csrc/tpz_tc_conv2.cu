@@ -345,15 +345,25 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv2_kernel(const __grid_cons
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_bias[min(c + j, 255)];
           if (rrow && valid) {
+            const bool wide_r = ((reinterpret_cast<uintptr_t>(rrow + c) & 31) == 0);     // full-sector 32-byte loads
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (q * 8 < nc) {
-                const uint4 u = *reinterpret_cast<const uint4*>(rrow + c + q * 8);
-                const __half2* h = reinterpret_cast<const __half2*>(&u);
+            for (int q = 0; q < 2; ++q) {
+              if (q * 16 < nc) {
+                uint32_t u[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                if (wide_r && q * 16 + 8 < nc) {
+                  ptx::ld_global_256(rrow + c + q * 16, u);
+                } else {
+                  const uint4 lo = *reinterpret_cast<const uint4*>(rrow + c + q * 16);
+                  u[0] = lo.x; u[1] = lo.y; u[2] = lo.z; u[3] = lo.w;
+                  if (q * 16 + 8 < nc) {
+                    const uint4 hi = *reinterpret_cast<const uint4*>(rrow + c + q * 16 + 8);
+                    u[4] = hi.x; u[5] = hi.y; u[6] = hi.z; u[7] = hi.w;
+                  }
+                }
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = __half22float2(h[e]);
-                  const int j = q * 8 + e * 2;
+                for (int e = 0; e < 8; ++e) {
+                  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[e]));
+                  const int j = q * 16 + e * 2;
                   const float s0 = p.res_scale ? p.res_scale[c + j] : 1.f;
                   const float s1 = p.res_scale ? p.res_scale[c + j + 1] : 1.f;
                   v[j] += s0 * f.x;
