@@ -55,32 +55,66 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples SM clocks / throttle reasons during the timed region.  Uses NVML in-process (initialised before the timed
+    region): spawning `nvidia-smi` every 200 ms re-initialises NVML each time, which takes a driver-wide lock and stalls
+    the host-side CUDA calls of the end-to-end leg by tens of ms.  Falls back to nvidia-smi if pynvml is unavailable."""
+    NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.stop_flag, self.rows = index, False, []
+        self.index, self.stop_flag, self.rows = index, False, []      # rows: (sm_mhz, sm_max_mhz, [active reason flags])
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber devices: address the GPU by the UUID torch reports
+            uuid = str(torch.cuda.get_device_properties(index).uuid)
+            uuid = uuid if uuid.startswith('GPU-') else 'GPU-' + uuid
+            try:
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if isinstance(uuid, str) else uuid)
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
-    def run(self):
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        flags = [bool(r & n.nvmlClocksThrottleReasonHwSlowdown), bool(r & n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                 bool(r & n.nvmlClocksThrottleReasonSwThermalSlowdown), bool(r & n.nvmlClocksThrottleReasonSwPowerCap)]
+        self.rows.append((int(sm), int(mx), flags))
+
+    def _sample_smi(self):
         q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={q}', '--format=csv,noheader,nounits'],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if out:
+            c = [v.strip() for v in out.split(',')]
+            if c[0].isdigit():
+                self.rows.append((int(c[0]), int(c[1]) if c[1].isdigit() else None, [v.lower().startswith('active') for v in c[2:6]]))
+
+    def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={q}', '--format=csv,noheader,nounits'],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(',')])
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05 if self.nvml is not None else 0.2)
 
     def summary(self):
         if not self.rows:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=['unavailable'])
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith('active') for r in self.rows)]
-        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                    reasons=reasons, samples=len(self.rows))
+        sm = sorted(r[0] for r in self.rows)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(r[2][i] for r in self.rows)]
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=self.rows[0][1], reasons=reasons, samples=len(self.rows),
+                    source='nvml' if self.nvml is not None else 'nvidia-smi')
 
 
 def pretrained_u64_state():
