@@ -23,10 +23,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
-# NCCL prints its version banner on STDOUT when NCCL_DEBUG=VERSION/INFO is set in the environment; the driver
-# expects exactly one JSON line there.
-if os.environ.get('TPZ_KEEP_NCCL_DEBUG') is None:
-    os.environ['NCCL_DEBUG'] = 'WARN'
+# The driver expects exactly ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner on
+# fd 1 at NCCL_DEBUG=VERSION and above), so fd 1 is pointed at stderr for the whole run and the JSON line is written to
+# the saved original descriptor at the end (emit()).
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+sys.stdout = os.fdopen(os.dup(2), 'w', buffering=1)
+
+
+def emit(obj):
+    os.write(_REAL_STDOUT, (json.dumps(obj) + '\n').encode())
 
 import numpy as np
 import torch
@@ -175,14 +181,14 @@ def run_reference(args, rank):
     dt = time.perf_counter() - t0
     v = steps * size * size / 1e6 / dt
     sample = f'{steps} x one {size}x{size} micrograph (bounded sample of the 4096x4096 workload), torch CPU fp32, {threads} threads (fastest of the tried thread counts; host has {os.cpu_count()} logical CPUs)'
-    print(json.dumps({
+    emit({
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * dt / steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': 'resnet8_u64 dense scoring, CPU reference path', 'sample': sample},
         'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
         'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-    }))
+    })
 
 
 def main():
@@ -318,7 +324,7 @@ def main():
             v, dt, thr = cpu_oracle_mpxs()
             line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': thr, 'kind': 'port',
                                     'sample': f'one 512x512 micrograph x3 (bounded sample), oracle torch CPU fp32, {dt:.2f} s each, {thr} threads = fastest of the tried counts on {os.cpu_count()} logical CPUs'}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
