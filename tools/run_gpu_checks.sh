@@ -1,8 +1,7 @@
 mkdir -p gpurun_out
-TPZ_RESIDUAL=epilogue timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "resnet or seeded or ragged" 2>&1 | tail -3
-for rs in mma epilogue mma epilogue; do
-  TPZ_RESIDUAL=$rs timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline 2>/dev/null > gpurun_out/bench_res_$rs.json
-  python - <<PY
-import json; d=json.load(open("gpurun_out/bench_res_$rs.json")); print("residual=$rs", "value", round(d["value"],1), "ms", round(d["ms_per_step"],2), "e2e", round(d["e2e"]["value"],1), "dom ms", round(d["roofline"]["ms_per_launch"],2), d["clocks"])
-PY
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py -m gpu -q -k "unet or denoise or pool_upsample_last or fcnn" 2>&1 | tail -4
+for m in auto tc; do
+  echo "TPZ_LAST=$m"; TPZ_LAST=$m timeout 600 python tools/bench_extra.py --workloads denoise --steps 4 2>&1 | tail -2 | cut -c1-220
 done
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_unet2d.csv python tools/unet_patch.py 2048 > /dev/null 2>&1
+grep -E "conv_last_tiled" gpurun_out/launches_unet2d.csv | tail -1 | cut -c1-260

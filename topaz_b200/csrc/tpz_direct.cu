@@ -187,6 +187,111 @@ __global__ void conv_last_kernel(const __half* __restrict__ x, int N, int D, int
 }
 
 // -------------------------------------------------------------------------------------------------
+// Cout = 1 tail conv, 2-D, tiled: the U-Net's dec1.4 (32 -> 1, 5x5) has 1600 FLOP/px -- far too little for the tensor
+// core path, whose issue loop and 4 KB-per-MMA A-operand reads made it cost as much as a 64-channel layer (0.58 ms per
+// 2048^2 patch, 15 % of the network).  Here a block stages a (TY+K-1) x (TX+K-1) x C fp16 window in shared memory (pixel
+// stride C*2+16 bytes: conflict-free 16-byte loads across a warp), each thread owns 4 vertically adjacent outputs of one
+// column and walks the (s, channel-chunk) pairs with the 5 x 8 weights of that pair held in registers, so every staged
+// value is loaded once per s and used by up to 4 outputs.  fp32 accumulation, fused bias + de-normalisation.
+// -------------------------------------------------------------------------------------------------
+template <int C, int K>
+__global__ void __launch_bounds__(128) conv_last_tiled_kernel(const __half* __restrict__ x, int N, int H, int W, int ld,
+                                                              const float* __restrict__ w /*[K*K][C]*/, float bias,
+                                                              float oscale, float oshift, const float* __restrict__ stats,
+                                                              float* __restrict__ out, int tiles_x, int tiles_y) {
+  constexpr int TX = 32, TY = 16, PX = TX + K - 1, PY = TY + K - 1;
+  constexpr int PSTRIDE = C * 2 + 16;          // bytes per staged pixel
+  constexpr int CH = C / 8;                    // 16-byte chunks per pixel
+  extern __shared__ __align__(16) unsigned char smem_last[];
+  unsigned char* tile = smem_last;                                            // [PY][PX][PSTRIDE]
+  float* sw = reinterpret_cast<float*>(smem_last + PY * PX * PSTRIDE);        // [K*K][C]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < K * K * C; i += 128) sw[i] = w[i];
+  const int tx = tid & 31, tg = tid >> 5;      // column inside the tile, group of 4 rows
+  const long long ntiles = (long long)tiles_x * tiles_y * N;
+  for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int n = (int)(t / ((long long)tiles_x * tiles_y));
+    const int tr = (int)(t % ((long long)tiles_x * tiles_y));
+    const int x0 = (tr % tiles_x) * TX, y0 = (tr / tiles_x) * TY;
+    __syncthreads();                            // previous tile fully consumed (also orders the weight staging)
+    for (int i = tid; i < PY * PX * CH; i += 128) {
+      const int c = i % CH, p = i / CH;
+      const int wx = p % PX, wy = p / PX;
+      const int ix = x0 + wx - K / 2, iy = y0 + wy - K / 2;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (ix >= 0 && ix < W && iy >= 0 && iy < H) v = *reinterpret_cast<const uint4*>(x + (((size_t)n * H + iy) * W + ix) * ld + c * 8);
+      *reinterpret_cast<uint4*>(tile + (size_t)(wy * PX + wx) * PSTRIDE + c * 16) = v;
+    }
+    __syncthreads();
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int s = 0; s < K; ++s) {
+#pragma unroll 1
+      for (int c = 0; c < CH; ++c) {
+        float wr[K][8];                         // weights of taps (r, s), channels 8c..8c+7
+#pragma unroll
+        for (int r = 0; r < K; ++r) {
+          const float4 a = *reinterpret_cast<const float4*>(sw + (r * K + s) * C + c * 8);
+          const float4 b = *reinterpret_cast<const float4*>(sw + (r * K + s) * C + c * 8 + 4);
+          wr[r][0] = a.x; wr[r][1] = a.y; wr[r][2] = a.z; wr[r][3] = a.w;
+          wr[r][4] = b.x; wr[r][5] = b.y; wr[r][6] = b.z; wr[r][7] = b.w;
+        }
+        const unsigned char* col = tile + (size_t)((tg * 4) * PX + tx + s) * PSTRIDE + c * 16;
+#pragma unroll
+        for (int row = 0; row < 4 + K - 1; ++row) {
+          const uint4 u = *reinterpret_cast<const uint4*>(col + (size_t)row * PX * PSTRIDE);
+          const __half2* h = reinterpret_cast<const __half2*>(&u);
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { const float2 q = __half22float2(h[e]); f[2 * e] = q.x; f[2 * e + 1] = q.y; }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int r = row - j;              // output j (row tg*4 + j) sees this input row through tap row r
+            if (r >= 0 && r < K) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) acc[j] = fmaf(f[e], wr[r][e], acc[j]);
+            }
+          }
+        }
+      }
+    }
+    const int ox = x0 + tx;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int oy = y0 + tg * 4 + j;
+      if (ox < W && oy < H) {
+        float v = (acc[j] + bias) * oscale + oshift;
+        if (stats) v = v * stats[1] + stats[0];
+        out[((size_t)n * H + oy) * W + ox] = v;
+      }
+    }
+  }
+}
+
+template <int C, int K>
+static int launch_conv_last_tiled(const __half* x, int N, int H, int W, int ld, const float* w, float bias, float oscale,
+                                  float oshift, const float* stats, float* out, cudaStream_t stream) {
+  constexpr int TX = 32, TY = 16;
+  const int smem = (TY + K - 1) * (TX + K - 1) * (C * 2 + 16) + K * K * C * (int)sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    TPZ_CUDA(cudaFuncSetAttribute(conv_last_tiled_kernel<C, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int tiles_x = tpz_div_up(W, TX), tiles_y = tpz_div_up(H, TY);
+  const long long ntiles = (long long)tiles_x * tiles_y * N;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int per_sm = (220 * 1024) / (smem + 1024) > 8 ? 8 : (220 * 1024) / (smem + 1024);
+  const long long cap = (long long)sms * (per_sm < 1 ? 1 : per_sm);
+  conv_last_tiled_kernel<C, K><<<(int)(ntiles < cap ? ntiles : cap), 128, smem, stream>>>(x, N, H, W, ld, w, bias, oscale,
+                                                                                       oshift, stats, out, tiles_x, tiles_y);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
 // Generic conv (validation / uncovered shapes): one thread per (output pixel, 8 output channels).
 // -------------------------------------------------------------------------------------------------
 __global__ void conv_generic_kernel(const __half* __restrict__ x0, int C0, int ld0, const __half* __restrict__ x1,
@@ -447,6 +552,11 @@ extern "C" int tpz_conv_last(const tpz_half* x, int N, int D, int H, int W, int 
                              int kd, int kh, int kw, int dil, int pad, float out_scale, float out_shift,
                              const float* affine_stats, float* out, void* stream) {
   TPZ_CHECK(C % 8 == 0 && ld % 8 == 0, "tpz_conv_last: C=%d / ld=%d must be multiples of 8", C, ld);
+  if (kd == 1 && dil == 1 && kh == kw && pad == kh / 2 && C == 32 && (kh == 5 || kh == 3)) {     // tiled 2-D kernel
+    const __half* xh = HCP(x);
+    if (kh == 5) return launch_conv_last_tiled<32, 5>(xh, N * D, H, W, ld, w, bias, out_scale, out_shift, affine_stats, out, ST(stream));
+    return launch_conv_last_tiled<32, 3>(xh, N * D, H, W, ld, w, bias, out_scale, out_shift, affine_stats, out, ST(stream));
+  }
   const size_t total = (size_t)N * D * H * W;
   conv_last_kernel<<<tpz_div_up(total, 128), 128, 0, ST(stream)>>>(HCP(x), N, D, H, W, C, ld, w, bias, kd, kh, kw,
                                                                    dil, pad, out_scale, out_shift, affine_stats, out);

@@ -27,7 +27,10 @@ FIRST_ON_TC = os.environ.get('TPZ_FIRST', 'tc') != 'simt'
 FIRST_FUSED = os.environ.get('TPZ_FIRST', 'tc') == 'tc'      # im2col tile built in smem inside the GEMM kernel
 RESIDUAL_IN_MMA = os.environ.get('TPZ_RESIDUAL', 'mma') != 'epilogue'
 UP2_FUSED = os.environ.get('TPZ_UP2', 'fused') != 'off'       # fused 2x up-sampling in U-Net dec1.0 (poly-phase)
-LAST_ON_TC = os.environ.get('TPZ_LAST', 'tc') != 'simt'      # Cout=1 U-Net tail on the tensor-core kernel
+# Cout=1 U-Net tail: 'tc' = 16-column tensor-core GEMM with a fused dot epilogue, 'simt' = fp32 CUDA-core kernel;
+# default: the tiled CUDA-core kernel where it exists (2-D, 32 channels, 3x3 / 5x5: 1600 FLOP/px is too little for the
+# tensor-core path), the GEMM elsewhere (3-D)
+LAST_MODE = os.environ.get('TPZ_LAST', 'auto')
 
 
 def _rup(c: int, m: int = 32) -> int:
@@ -483,7 +486,9 @@ def unet_forward(model, x: torch.Tensor, denorm_stats: Optional[torch.Tensor] = 
                 ops.tc_conv(d['a'], [up, raw], (N, D, H, W), out=o)
             o2 = torch.empty((N, D, H, W, d['b'].Co), dtype=torch.float16, device=x.device)
             ops.tc_conv(d['b'], [o], (N, D, H, W), out=o2)
-            if LAST_ON_TC:
+            last_simt = LAST_MODE == 'simt' or (LAST_MODE == 'auto' and dims == 2 and d['last_w'].shape[1] == 32
+                                                and d['last_k'][1] in (3, 5))
+            if not last_simt:
                 y = torch.empty((N, D, H, W), dtype=torch.float32, device=x.device)
                 ops.tc_conv(d['last_tc'], [o2], (N, D, H, W), out=None, dot_out=y, dot_affine=denorm_stats)
             else:
