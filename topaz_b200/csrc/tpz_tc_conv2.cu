@@ -503,7 +503,7 @@ static int launch_v2(const TpzTcConvArgs* a, cudaStream_t stream, bool dry) {
     ntl_early = (long long)(a->phase_sel > 0 ? 1 : L * L) * tpz_div_up(tpz_div_up(a->Wo, L), T2W) *
                 tpz_div_up(tpz_div_up(a->Ho, L), th) * (dq > 0 ? dq : 0) * a->N;
   }
-  const bool pair_ok = a->Co % 32 == 0 && a->Co >= 64 && ntl_early >= 2;
+  const bool pair_ok = a->Co % 32 == 0 && a->Co >= 32 && ntl_early >= 2;
   const bool pair = pair_ok && pair_env != 0;
   p.b_block_bytes = (pair ? a->Co / 2 : a->Co) * rowb;
   const int tail = 4096;
