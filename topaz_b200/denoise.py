@@ -70,7 +70,7 @@ class Denoise():
         of 4 shapes and ~90 kernel launches each; issued one by one from Python the host becomes the bottleneck (1422
         launches, ~45 ms) although the GPU needs 39 ms.  Graphs are keyed by (shape, parameter versions) and hold their
         own static input / activations / output; TPZ_DENOISE_GRAPH=0 disables them."""
-        if os.environ.get('TPZ_DENOISE_GRAPH', '1') == '0' or self.dims != 2:
+        if os.environ.get('TPZ_DENOISE_GRAPH', '1') == '0':
             return self._denoise_device(crop)
         graphs = self.__dict__.setdefault('_graphs', {})
         key = (tuple(crop.shape), str(crop.device), engine._state_key(self.model))
@@ -220,7 +220,7 @@ class Denoise3D(Denoise):
             sic, sjc, skc = padding - i + si, padding - j + sj, padding - k + sk
             x[sic:sic + ei - si, sjc:sjc + ej - sj, skc:skc + ek - sk] = td[si:ei, sj:ej, sk:ek]
             xb = (x[None] - mu32) / std32                     # batch of 1 (DataLoader(batch_size=1))
-            y = self._denoise_device(xb) * std32 + mu32
+            y = self._denoise_crop(xb) * std32 + mu32        # graph replay: all 192^3 crops share one shape
             dz, dy, dx = out_d[i:i + patch_size, j:j + patch_size, k:k + patch_size].shape
             out_d[i:i + patch_size, j:j + patch_size, k:k + patch_size] = \
                 y[padding:padding + dz, padding:padding + dy, padding:padding + dx]
