@@ -220,7 +220,7 @@ class Denoise3D(Denoise):
             sic, sjc, skc = padding - i + si, padding - j + sj, padding - k + sk
             x[sic:sic + ei - si, sjc:sjc + ej - sj, skc:skc + ek - sk] = td[si:ei, sj:ej, sk:ek]
             xb = (x[None] - mu32) / std32                     # batch of 1 (DataLoader(batch_size=1))
-            y = self._denoise_crop(xb) * std32 + mu32        # graph replay: all 192^3 crops share one shape
+            y = self._denoise_device(xb) * std32 + mu32       # GPU-bound (12 ms per crop): graph replay measured slower here
             dz, dy, dx = out_d[i:i + patch_size, j:j + patch_size, k:k + patch_size].shape
             out_d[i:i + patch_size, j:j + patch_size, k:k + patch_size] = \
                 y[padding:padding + dz, padding:padding + dy, padding:padding + dx]
