@@ -426,7 +426,7 @@ int g_num_sms2 = 0;
 }  // namespace
 
 // returns 0 ok, <0 "not eligible" (caller falls back to the per-tap kernel), >0 error
-static int launch_v2(const TpzTcConvArgs* a, cudaStream_t stream, bool dry) {
+static int launch_v2(const TpzTcConvArgs* a, cudaStream_t stream, bool dry, bool allow_pair = true) {
   const int L = a->lattice;
   if (L < 1 || L > 8) return -1;
   const int rowb = a->KC * 2;
@@ -504,7 +504,7 @@ static int launch_v2(const TpzTcConvArgs* a, cudaStream_t stream, bool dry) {
                 tpz_div_up(tpz_div_up(a->Ho, L), th) * (dq > 0 ? dq : 0) * a->N;
   }
   const bool pair_ok = a->Co % 32 == 0 && a->Co >= 32 && ntl_early >= 2;
-  const bool pair = pair_ok && pair_env != 0;
+  const bool pair = allow_pair && pair_ok && pair_env != 0;
   p.b_block_bytes = (pair ? a->Co / 2 : a->Co) * rowb;
   const int tail = 4096;
   const int budget = 227 * 1024 - 1024 - tail;
@@ -592,12 +592,17 @@ static int launch_v2(const TpzTcConvArgs* a, cudaStream_t stream, bool dry) {
     attr.id = cudaLaunchAttributeClusterDimension;
     attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr; cfg.numAttrs = 1;
+    cudaError_t le;
     if (a->KC == 64) {
       TPZ_CUDA(cudaFuncSetAttribute(tc_conv2_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      TPZ_CUDA(cudaLaunchKernelEx(&cfg, tc_conv2_kernel<64, true>, p));
+      le = cudaLaunchKernelEx(&cfg, tc_conv2_kernel<64, true>, p);
     } else {
       TPZ_CUDA(cudaFuncSetAttribute(tc_conv2_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      TPZ_CUDA(cudaLaunchKernelEx(&cfg, tc_conv2_kernel<32, true>, p));
+      le = cudaLaunchKernelEx(&cfg, tc_conv2_kernel<32, true>, p);
+    }
+    if (le != cudaSuccess) {          // clusters of two not schedulable here (e.g. a partitioned GPU): single-CTA plan
+      (void)cudaGetLastError();
+      return launch_v2(a, stream, dry, false);
     }
     TPZ_CUDA(cudaGetLastError());
     return 0;
