@@ -207,7 +207,7 @@ def test_dense_classifier_ragged_and_tiny_images(shape):
 
 
 @pytest.mark.parametrize('shape', [(1, 1, 32, 32), (2, 1, 40, 72), (1, 1, 33, 47), (1, 1, 250, 130),
-                                   (1, 1, 96, 24)])      # 3 x 3 = 9 tiles: odd count -> the CTA pair's repeat-tile path
+                                   (1, 1, 96, 40)])      # 5 x 3 = 15 tiles: odd count -> the CTA pair's repeat-tile path
 def test_unet_edge_sizes(shape):
     """Smallest legal U-Net inputs (5 poolings), odd sizes (non-2x up-sampling -> gather path) and even sizes (fused path)."""
     from topaz_b200.denoising.models import UDenoiseNet
