@@ -89,9 +89,11 @@ int tpz_conv_first(const float* x, int N, int D, int H, int W, const float* w, c
 /* tpz_conv_first_tc: the same Cin = 1 convolution (2-D, dilation 1) as ONE tcgen05 kernel: each CTA builds the im2col
  *   tile of 128 output pixels in shared memory (SWIZZLE_128B K-major, generic stores + fence.proxy.async) and multiplies
  *   it with the smem-resident weights; HBM sees only the fp32 image in and the fp16 [N][Ho][Wo][Cp] map out.
- *   w_packed: fp16 [ceil(k*k/64)][Cp][64] (tap t = r*k+s, zero padded); bias fp32 [Cp]; Cp in {32,64}; k in {3,5,7,11}. */
+ *   w_packed: fp16 [ceil(k*k/64)][Cp][64] (tap t = r*k+s, zero padded); bias fp32 [Cp]; Cp in {32,64}; k in {3,5,7,11}.
+ *   pool = 1 fuses the MaxPool2d(2) that follows the U-Net's enc1 conv (denoising/models.py:80): out is then
+ *   [N][Ho/2][Wo/2][Cp] and the full-resolution map is never written. */
 int tpz_conv_first_tc(const float* x, int B, int H, int W, const tpz_half* w_packed, const float* bias, int Cp, int k,
-                      int pad, float neg_slope, tpz_half* out, void* stream);
+                      int pad, float neg_slope, int pool, tpz_half* out, void* stream);
 int tpz_conv_first_tc_supported(int k, int Cp);
 /* tpz_im2col_first: im2col of a single-channel 2-D image (k x k taps -> channels, zero padded to ld) so that
  *   Cin = 1 convs (first BasicConv 7x7, U-Net enc1 11x11, the raw-image slice of U-Net dec1.0) run as a

@@ -101,12 +101,14 @@ def conv_first(x, w, bias, dil, pad, neg_slope, out_ld):
     return out
 
 
-def conv_first_tc(x, w_packed, bias, k, pad, neg_slope):
+def conv_first_tc(x, w_packed, bias, k, pad, neg_slope, pool=False):
     """tpz_conv_first_tc: fp16 taps x fp16 weights, fp32 accumulate, bias + activation, fp16 NHWC out."""
     kb, cp, _ = w_packed.shape
     w = w_packed.float().permute(1, 0, 2).reshape(cp, kb * 64)[:, :k * k].reshape(cp, 1, k, k)
     y = F.conv2d(x.half().float()[:, None], w, bias.float(), padding=pad)
-    y = torch.where(y > 0, y, y * neg_slope)
+    y = torch.where(y > 0, y, y * neg_slope).half().float()
+    if pool:
+        y = F.max_pool2d(y, 2)
     return y.permute(0, 2, 3, 1)[:, None].contiguous().half()
 
 

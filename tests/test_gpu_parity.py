@@ -387,3 +387,18 @@ def test_fused_first_layer_kernel_matches_fp32_conv(k, co, slope):
         assert torch.all(y[..., co:] == 0)                                             # padded channels stay zero
         err = (y[:, 0, :, :, :co] - ref).abs().max() / ref.abs().max()
         assert err < 2e-3, (B, H, W, float(err))
+
+
+@pytest.mark.parametrize('H,W', [(64, 64), (37, 53), (130, 18), (9, 200)])
+def test_fused_first_layer_with_pool_matches_unfused(H, W):
+    """tpz_conv_first_tc(pool=1) == maxpool2(tpz_conv_first_tc(pool=0)) bit for bit (odd sizes: floor, like MaxPool2d)."""
+    from topaz_b200 import ops
+    g = torch.Generator().manual_seed(H * 7 + W)
+    w = torch.randn(48, 11, 11, generator=g) / 11
+    b = torch.randn(48, generator=g)
+    wp, bp = ops.pack_first_tc(w, b, 64, 'cuda')
+    x = torch.randn(2, H, W, generator=g).cuda()
+    full = ops.conv_first_tc(x, wp, bp, 11, 5, 0.1)
+    ref = ops.maxpool2(full, 2)
+    got = ops.conv_first_tc(x, wp, bp, 11, 5, 0.1, pool=True)
+    assert got.shape == ref.shape and torch.equal(got, ref)

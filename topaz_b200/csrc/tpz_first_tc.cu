@@ -28,6 +28,7 @@ struct FirstArgs {
   int Ho, Wo, pad;
   float slope;
   int tiles_x, tiles_y;
+  int pool;               // 1: fused 2x2 max-pool (floor), out is [B][Ho/2][Wo/2][Cp]
 };
 
 template <int KW>
@@ -199,18 +200,51 @@ __global__ void __launch_bounds__(128, MINB) first_tc_kernel(const FirstArgs a) 
       const int b = (int)(tile / tiles_per_img);
       const int tr = (int)(tile % tiles_per_img);
       const int ty0 = (tr / a.tiles_x) * TH, tx0 = (tr % a.tiles_x) * TW;
+      if (!a.pool) {
 #pragma unroll
-      for (int i = 0; i < 32 / PPI; ++i) {
-        const int pix = warp * 32 + i * PPI + lane / LPP;        // pixel (row of the tile) this lane helps to write
-        const int part = lane % LPP;                              // which 32-byte piece of its channel vector
-        const int oy = ty0 + pix / TW, ox = tx0 + pix % TW;
-        const unsigned char* src = sA + (size_t)pix * ROWB;
-        const int psw = pix & (CH16 - 1);
-        const uint4 lo = *reinterpret_cast<const uint4*>(src + (((2 * part) ^ psw) << 4));
-        const uint4 hi = *reinterpret_cast<const uint4*>(src + (((2 * part + 1) ^ psw) << 4));
-        if (oy < a.Ho && ox < a.Wo)
-          ptx::st_global_256(a.out + (((size_t)b * a.Ho + oy) * a.Wo + ox) * CP + part * 16, lo.x, lo.y, lo.z, lo.w, hi.x, hi.y,
-                             hi.z, hi.w);
+        for (int i = 0; i < 32 / PPI; ++i) {
+          const int pix = warp * 32 + i * PPI + lane / LPP;        // pixel (row of the tile) this lane helps to write
+          const int part = lane % LPP;                              // which 32-byte piece of its channel vector
+          const int oy = ty0 + pix / TW, ox = tx0 + pix % TW;
+          const unsigned char* src = sA + (size_t)pix * ROWB;
+          const int psw = pix & (CH16 - 1);
+          const uint4 lo = *reinterpret_cast<const uint4*>(src + (((2 * part) ^ psw) << 4));
+          const uint4 hi = *reinterpret_cast<const uint4*>(src + (((2 * part + 1) ^ psw) << 4));
+          if (oy < a.Ho && ox < a.Wo)
+            ptx::st_global_256(a.out + (((size_t)b * a.Ho + oy) * a.Wo + ox) * CP + part * 16, lo.x, lo.y, lo.z, lo.w, hi.x,
+                               hi.y, hi.z, hi.w);
+        }
+      } else {
+        // fused MaxPool2d(2) (denoising/models.py:80: enc1 = conv, LeakyReLU, MaxPool): a warp owns tile rows 2w, 2w+1, i.e.
+        // one row of 8 pooled pixels; lane -> (pooled pixel, 32-byte piece), max over the 2x2 staged vectors
+        const int Hp = a.Ho >> 1, Wp = a.Wo >> 1;
+#pragma unroll
+        for (int i = 0; i < (8 * LPP + 31) / 32; ++i) {
+          const int item = i * 32 + lane;
+          if (item < 8 * LPP) {
+            const int pxp = item / LPP, part = item % LPP;         // pooled column inside the tile, 32-byte piece
+            const int oyp = (ty0 >> 1) + warp, oxp = (tx0 >> 1) + pxp;
+            uint4 mlo = make_uint4(0, 0, 0, 0), mhi = mlo;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int pix = (2 * warp + (q >> 1)) * TW + 2 * pxp + (q & 1);
+              const unsigned char* src = sA + (size_t)pix * ROWB;
+              const int psw = pix & (CH16 - 1);
+              const uint4 lo = *reinterpret_cast<const uint4*>(src + (((2 * part) ^ psw) << 4));
+              const uint4 hi = *reinterpret_cast<const uint4*>(src + (((2 * part + 1) ^ psw) << 4));
+              if (q == 0) { mlo = lo; mhi = hi; }
+              else {
+                __half2* a2 = reinterpret_cast<__half2*>(&mlo); const __half2* b2 = reinterpret_cast<const __half2*>(&lo);
+                __half2* c2 = reinterpret_cast<__half2*>(&mhi); const __half2* d2 = reinterpret_cast<const __half2*>(&hi);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { a2[e] = __hmax2(a2[e], b2[e]); c2[e] = __hmax2(c2[e], d2[e]); }
+              }
+            }
+            if (oyp < Hp && oxp < Wp)
+              ptx::st_global_256(a.out + (((size_t)b * Hp + oyp) * Wp + oxp) * CP + part * 16, mlo.x, mlo.y, mlo.z, mlo.w,
+                                 mhi.x, mhi.y, mhi.z, mhi.w);
+          }
+        }
       }
     }
     ptx::tc_fence_before();
@@ -249,12 +283,12 @@ int launch_first(const FirstArgs& a, cudaStream_t stream) {
 }  // namespace
 
 extern "C" int tpz_conv_first_tc(const float* x, int B, int H, int W, const tpz_half* w_packed, const float* bias, int Cp,
-                                 int k, int pad, float neg_slope, tpz_half* out, void* stream_) {
+                                 int k, int pad, float neg_slope, int pool, tpz_half* out, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   FirstArgs a;
   a.x = x; a.B = B; a.H = H; a.W = W;
   a.w = reinterpret_cast<const __half*>(w_packed); a.bias = bias; a.out = reinterpret_cast<__half*>(out);
-  a.Ho = H + 2 * pad - (k - 1); a.Wo = W + 2 * pad - (k - 1); a.pad = pad; a.slope = neg_slope;
+  a.Ho = H + 2 * pad - (k - 1); a.Wo = W + 2 * pad - (k - 1); a.pad = pad; a.slope = neg_slope; a.pool = pool ? 1 : 0;
   TPZ_CHECK(a.Ho > 0 && a.Wo > 0 && B > 0, "tpz_conv_first_tc: empty output (H=%d W=%d k=%d pad=%d)", H, W, k, pad);
   a.tiles_x = tpz_div_up(a.Wo, TW); a.tiles_y = tpz_div_up(a.Ho, TH);
 #define TPZ_FIRST_CASE(KW_, CP_) if (k == KW_ && Cp == CP_) return launch_first<KW_, CP_>(a, stream);

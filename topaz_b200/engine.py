@@ -432,9 +432,11 @@ def unet_forward(model, x: torch.Tensor, denorm_stats: Optional[torch.Tensor] = 
     if dims == 2:
         xi = xi[:, None]                                  # [N, 1, H, W]
     f = plan['first']
+    fused_pool = False
     if plan['first_fused'] is not None:
         ff = plan['first_fused']
-        h = ops.conv_first_tc(xi[:, 0].contiguous(), ff['w'], ff['b'], ff['k'], ff['k'] // 2, 0.1)
+        h = ops.conv_first_tc(xi[:, 0].contiguous(), ff['w'], ff['b'], ff['k'], ff['k'] // 2, 0.1, pool=bool(f['pool']))
+        fused_pool = bool(f['pool'])
     elif plan['first_tc'] is not None:
         ft = plan['first_tc']
         N0, D0, H0, W0 = xi.shape
@@ -444,7 +446,7 @@ def unet_forward(model, x: torch.Tensor, denorm_stats: Optional[torch.Tensor] = 
     else:
         h = ops.conv_first(xi, f['w'], f['b'], 1, f['pad'], 0.1, f['out_ld'])
     skips = []
-    if f['pool']:
+    if f['pool'] and not fused_pool:
         h = ops.maxpool2(h, dims)
     skips.append(h)
     for e in plan['enc']:

@@ -252,14 +252,19 @@ def pack_first_tc(w: torch.Tensor, bias: Optional[torch.Tensor], cp: int, device
     return wp.to(device), bp.to(device)
 
 
-def conv_first_tc(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, k: int, pad: int, neg_slope: float) -> torch.Tensor:
-    """x: fp32 [N, H, W] on device.  Returns fp16 [N, 1, Ho, Wo, Cp]: conv k x k (zero padding `pad`) + bias + activation."""
+def conv_first_tc(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, k: int, pad: int, neg_slope: float,
+                  pool: bool = False) -> torch.Tensor:
+    """x: fp32 [N, H, W] on device.  Returns fp16 [N, 1, Ho, Wo, Cp]: conv k x k (zero padding `pad`) + bias + activation;
+    with ``pool`` the 2x2 max-pool that follows is fused and the result is [N, 1, Ho//2, Wo//2, Cp]."""
     N, H, W = x.shape
     cp = w_packed.shape[1]
     Ho, Wo = H + 2 * pad - (k - 1), W + 2 * pad - (k - 1)
-    out = torch.empty((N, 1, Ho, Wo, cp), dtype=torch.float16, device=x.device)
+    oshape = (N, 1, Ho // 2, Wo // 2, cp) if pool else (N, 1, Ho, Wo, cp)
+    out = torch.empty(oshape, dtype=torch.float16, device=x.device)
+    if out.numel() == 0:
+        return out
     _count(1); check(_lib.lib().tpz_conv_first_tc(_ptr(x), N, H, W, _ptr(w_packed), _ptr(bias), cp, k, pad, float(neg_slope),
-                                                  _ptr(out), _stream()))
+                                                  int(pool), _ptr(out), _stream()))
     return out
 
 
