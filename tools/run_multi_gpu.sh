@@ -3,16 +3,9 @@
 N=${1:-2}
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517"
-nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
 timeout 300 $TR tools/dp_check.py 2>&1 | grep dp_check
-for rep in 1 2; do
-timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline 2>gpurun_out/bench_n1.err > gpurun_out/bench_n1.json; python - <<PY
-import json; d=json.load(open("gpurun_out/bench_n1.json")); print("bench N=1", round(d["value"],1), "Mpx/s  ms/step", round(d["ms_per_step"],2), "e2e", round(d["e2e"]["value"],1), d["clocks"])
-PY
-done
-timeout 600 $TR bench.py --gpus $N --steps 8 --warmup 3 --no-cpu-baseline 2>gpurun_out/bench_n$N.err > gpurun_out/bench_n$N.json; python - <<PY
+timeout 600 $TR bench.py --gpus $N --steps 8 --warmup 3 --no-cpu-baseline 2>gpurun_out/bench_n$N.err > gpurun_out/bench_n$N.json
+echo "stdout lines: $(wc -l < gpurun_out/bench_n$N.json)"; python - <<PY
 import json; d=json.load(open("gpurun_out/bench_n$N.json")); print("bench N=$N", round(d["value"],1), "Mpx/s  ms/step", round(d["ms_per_step"],2), "e2e", round(d["e2e"]["value"],1), d["clocks"])
 PY
-timeout 300 $TR bench.py --impl reference --gpus $N --steps 2 --warmup 1 2>/dev/null | cut -c1-200
-timeout 600 $TR tools/bench_extra.py --workloads train,denoise --steps 4 2>gpurun_out/extra_n$N.err | tee gpurun_out/bench_extra_n$N.jsonl | cut -c1-280
-tail -2 gpurun_out/extra_n$N.err
+timeout 300 $TR bench.py --impl reference --gpus $N --steps 2 --warmup 1 2>/dev/null > gpurun_out/bench_ref_n$N.json; echo "reference stdout lines: $(wc -l < gpurun_out/bench_ref_n$N.json)"; cut -c1-120 gpurun_out/bench_ref_n$N.json
