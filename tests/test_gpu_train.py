@@ -213,3 +213,29 @@ def test_single_pass_tf32_mode_gradients():
         assert worst < 5e-2
     finally:
         assert T.set_tf32(prev) is True
+
+
+def test_u64_training_step_gradients_match_oracle_autograd():
+    """cfg4 also names resnet8_u64 (64/128/256 channels -> the BN=64 tensor-core training kernels): forward logits and the
+    gradient of one GE-binomial step vs autograd through the oracle, pretrained u64 weights, 48 crops."""
+    from topaz_b200 import train_engine as T
+    from topaz_b200.model.factory import get_feature_extractor
+    from topaz_b200.model.classifier import LinearClassifier
+    sd = weights_of(gold('resnet8_u64_pretrained'))
+    m = LinearClassifier(get_feature_extractor('resnet8', units=64, bn=False))
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}); m.cuda(); m.train()
+    B, pi = 48, 0.05
+    X = torch.from_numpy(np.random.default_rng(77).standard_normal((B, 71, 71)).astype(np.float32))
+    Y = torch.tensor([1.0] * 5 + [0.0] * (B - 5), dtype=torch.float64)
+    params = {k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in sd.items()}
+    score_ref = O.classifier_forward_grad(params, X[:, None], 'resnet8', 64).view(-1)
+    _, _, loss = O.ge_binomial_loss(score_ref, Y, pi, 1.0)
+    loss.backward()
+    T.flat_params(m)
+    score = m(X.cuda()).view(-1)
+    assert max(rel_err(score.detach().cpu().numpy(), score_ref.detach().numpy())) < 1e-4
+    ds = torch.empty(B, device='cuda'); o5 = torch.empty(5, device='cuda')
+    T.ge_loss_grad(score.contiguous(), Y.cuda(), pi, 1.0, 0, B, ds, o5)
+    T.backward(m, ds)
+    for k, p in m.named_parameters():
+        assert max(rel_err(p.grad.cpu().numpy(), params[k].grad.numpy())) < 1e-3, k
