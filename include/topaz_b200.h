@@ -99,6 +99,9 @@ int tpz_conv_first_tc_supported(int k, int Cp);
  *   Cin = 1 convs (first BasicConv 7x7, U-Net enc1 11x11, the raw-image slice of U-Net dec1.0) run as a
  *   1-tap tensor-core GEMM through tpz_tc_conv.  out: fp16 [N][1][Ho][Wo][ld].                       */
 int tpz_im2col_first(const float* x, int N, int H, int W, int k, int pad, tpz_half* out, int ld, void* stream);
+/* tpz_im2col3d_first: the 3-D analogue ('same' padding, pad = k/2): out fp16 [N][D][H][W][ld], channel t = (dz*k+dy)*k+dx;
+ *   the raw-volume slice of UDenoiseNet3D dec1.0 (denoising/models.py:555) as a second tensor-core source. */
+int tpz_im2col3d_first(const float* x, int N, int D, int H, int W, int k, int pad, tpz_half* out, int ld, void* stream);
 /* tpz_conv_last: Cout = 1 conv from fp16 NDHWC to dense fp32 (classifier 1x1, classifier.py:65; U-Net
  *   dec1.4, denoising/models.py:127,505).  out = (sum + bias) * out_scale + out_shift, then, if
  *   affine_stats (device float[2] = mean,std) is given, out = out*std + mean (denoise.py:295 de-normalise).               */

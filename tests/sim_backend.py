@@ -112,6 +112,20 @@ def conv_first_tc(x, w_packed, bias, k, pad, neg_slope, pool=False):
     return y.permute(0, 2, 3, 1)[:, None].contiguous().half()
 
 
+def im2col3d_first(x, k, ld):
+    N, D, H, W = x.shape
+    p = k // 2
+    xp = F.pad(x, (p, p, p, p, p, p))
+    out = torch.zeros((N, D, H, W, ld), dtype=torch.float16)
+    t = 0
+    for dz in range(k):
+        for dy in range(k):
+            for dx in range(k):
+                out[..., t] = xp[:, dz:dz + D, dy:dy + H, dx:dx + W].half()
+                t += 1
+    return out
+
+
 def im2col_first(x, k, pad, ld):
     N, H, W = x.shape
     xp = F.pad(x, (pad, pad, pad, pad))
@@ -214,7 +228,7 @@ def to_device(t):
 
 @contextlib.contextmanager
 def patched():
-    names = ['tc_conv', 'conv_first', 'conv_first_tc', 'im2col_first', 'filter_f32', 'conv_last', 'maxpool2', 'upsample_nearest', 'meanstd', 'affine',
+    names = ['tc_conv', 'conv_first', 'conv_first_tc', 'im2col_first', 'im2col3d_first', 'filter_f32', 'conv_last', 'maxpool2', 'upsample_nearest', 'meanstd', 'affine',
              'gemm_f32', 'gmm_sums', 'select_hist', 'to_device']
     saved = {n: getattr(ops, n) for n in names}
     saved['require_cuda'] = ops.require_cuda

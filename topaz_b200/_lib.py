@@ -54,6 +54,7 @@ _PROTOS = {
     'tpz_affine': (_I, [_P, _LL, _P, _I, _P, _P]),
     'tpz_sample_crops': (_I, [_I, C.c_ulonglong, C.c_ulonglong, _P, _P, _P, _P, _I, _P, _I, _P, _F, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     'tpz_make_crops': (_I, [_I, _I, _I, _P, _P, _P, _P, _P]),
+    'tpz_im2col3d_first': (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _I, _P]),
     'tpz_conv_first_tc': (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _I, _F, _I, _P, _P]),
     'tpz_conv_first_tc_supported': (_I, [_I, _I]),
     'tpz_lab_umma_pair': (_I, [_P, _P, _I, _I, _P, _P, _P]),

@@ -478,7 +478,8 @@ def unet_forward(model, x: torch.Tensor, denorm_stats: Optional[torch.Tensor] = 
             if dims == 2:
                 raw = ops.im2col_first(xi[:, 0], d['k'], d['k'] // 2, d['ntap_store'])
             else:
-                raw = ops.conv_first(xi, d['onehot'], None, 1, d['k'] // 2, 1.0, d['ntap_store'])
+                raw = ops.im2col3d_first(xi, d['k'], d['ntap_store']) if d['ntap_store'] % 16 == 0 else \
+                    ops.conv_first(xi, d['onehot'], None, 1, d['k'] // 2, 1.0, d['ntap_store'])
             o = torch.empty((N, D, H, W, d['a'].Co), dtype=torch.float16, device=x.device)
             if d.get('up2') is not None and H == 2 * h.shape[2] and W == 2 * h.shape[3] and (dims == 2 or D == 2 * h.shape[1]):
                 for pl2 in d['up2']:                      # one launch per output phase, reading the half-res tensor

@@ -235,6 +235,14 @@ def conv_first(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], d
     return out
 
 
+def im2col3d_first(x: torch.Tensor, k: int, ld: int) -> torch.Tensor:
+    """x: fp32 [N, D, H, W].  Returns fp16 [N, D, H, W, ld] with channel t = tap (dz*k+dy)*k+dx ('same' padding), zero beyond k^3."""
+    N, D, H, W = x.shape
+    out = torch.empty((N, D, H, W, ld), dtype=torch.float16, device=x.device)
+    _count(1); check(_lib.lib().tpz_im2col3d_first(_ptr(x), N, D, H, W, k, k // 2, _ptr(out), ld, _stream()))
+    return out
+
+
 def first_tc_supported(k: int, cp: int) -> bool:
     return (k in (3, 5, 7, 11)) and (cp in (32, 64))
 
