@@ -147,8 +147,10 @@ __global__ void __launch_bounds__(256) im2col_first_kernel(const float* __restri
 // convolution that cost 0.55 ms per 192^3 patch.  One thread per (voxel, 16-channel piece): 32-byte stores, the
 // neighbourhood reads hit L1/L2.
 // -------------------------------------------------------------------------------------------------
-__global__ void im2col3d_first_kernel(const float* __restrict__ x, int N, int D, int H, int W, int k, int pad,
+template <int KT>   // KT > 0: compile-time kernel size (tap offsets become constants); KT = 0: runtime k
+__global__ void im2col3d_first_kernel(const float* __restrict__ x, int N, int D, int H, int W, int k_rt, int pad,
                                       __half* __restrict__ out, int ld) {
+  const int k = KT > 0 ? KT : k_rt;
   const int pieces = ld >> 4;
   const size_t total = (size_t)N * D * H * W * pieces;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -596,7 +598,8 @@ extern "C" int tpz_im2col3d_first(const float* x, int N, int D, int H, int W, in
   TPZ_CHECK(k >= 1 && k * k * k <= ld && ld % 16 == 0 && pad == k / 2, "tpz_im2col3d_first: k=%d pad=%d ld=%d", k, pad, ld);
   const size_t total = (size_t)N * D * H * W * (ld / 16);
   if (total == 0) return 0;
-  im2col3d_first_kernel<<<tpz_div_up(total, 256), 256, 0, ST(stream)>>>(x, N, D, H, W, k, pad, HP(out), ld);
+  if (k == 3) im2col3d_first_kernel<3><<<tpz_div_up(total, 256), 256, 0, ST(stream)>>>(x, N, D, H, W, k, pad, HP(out), ld);
+  else im2col3d_first_kernel<0><<<tpz_div_up(total, 256), 256, 0, ST(stream)>>>(x, N, D, H, W, k, pad, HP(out), ld);
   TPZ_CUDA(cudaGetLastError());
   return 0;
 }
