@@ -112,6 +112,7 @@ def test_three_ge_binomial_steps_match_reference_golden():
 @pytest.mark.parametrize('N,H,Ci,Co,k,stride,dil,org', [
     (4, 33, 32, 32, 3, 1, 1, 0), (3, 31, 32, 64, 3, 2, 2, 0), (3, 27, 32, 64, 1, 2, 1, 3), (2, 11, 64, 64, 3, 1, 2, 0),
     (2, 9, 64, 128, 5, 1, 1, 0), (300, 5, 64, 64, 3, 1, 1, 0),
+    (48, 27, 64, 128, 1, 2, 1, 3), (48, 25, 64, 128, 3, 2, 2, 0), (48, 9, 128, 256, 5, 1, 1, 0), (48, 11, 128, 128, 3, 1, 2, 0),   # resnet8_u64 layers
 ])
 def test_conv_mma_kernels_match_fp32(N, H, Ci, Co, k, stride, dil, org):
     """3xTF32 tensor-core fwd / dgrad / wgrad vs torch CPU fp32 (fp32-level accuracy expected)."""
