@@ -240,3 +240,34 @@ def test_u64_training_step_gradients_match_oracle_autograd():
     T.backward(m, ds)
     for k, p in m.named_parameters():
         assert max(rel_err(p.grad.cpu().numpy(), params[k].grad.numpy())) < 1e-3, k
+
+
+@pytest.mark.parametrize('N,Ci,Co', [(48, 64, 128), (256, 32, 64), (5, 64, 128)])
+def test_proj_wgrad_dgrad_engine_geometry(N, Ci, Co):
+    """The 1x1 stride-2 projection of ResidA2 as the engine calls it: input 27^2, crop offset 3, output 11^2 (the main
+    path's size, one less than the full extent would give); non-negative (post-ReLU) activations like the real ones."""
+    import ctypes as C
+    from topaz_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(5)
+    H, Ho, org, stride = 27, 11, 3, 2
+    x = torch.relu(torch.randn(N, Ci, H, H, generator=g)) * 3.0
+    w = torch.randn(Co, Ci, 1, 1, generator=g) * 0.1
+    dy = torch.randn(N, Co, Ho, Ho, generator=g) * 0.01
+    xin = x[:, :, org:org + 2 * Ho - 1, org:org + 2 * Ho - 1].contiguous()
+    gw = torch.nn.grad.conv2d_weight(xin.double(), tuple(w.shape), dy.double(), stride=stride).float()
+    gi = torch.nn.grad.conv2d_input(tuple(xin.shape), w.double(), dy.double(), stride=stride).float()
+    P = lambda t: C.c_void_p(t.data_ptr())
+    xd, dyd = _nhwc(x).cuda(), _nhwc(dy).cuda()
+    dw = torch.zeros_like(w).cuda()
+    _lib.check(L.tpz_conv_wgrad_mma(P(xd), N, H, H, Ci, P(dyd), Ho, Ho, Co, 1, 1, stride, 1, org, P(dw), None))
+    e = rel_err(dw.cpu(), gw)
+    print('proj wgrad rel err', e)
+    assert max(e) < 5e-5
+    wg = w.permute(2, 3, 0, 1).contiguous().cuda()
+    dx = torch.zeros(N, H, H, Ci, device='cuda')
+    _lib.check(L.tpz_conv_dgrad_mma(P(dyd), N, Ho, Ho, Co, P(wg), Ci, 1, 1, stride, 1, org, None, 1, P(dx), H, H, None))
+    gref = torch.zeros_like(x); gref[:, :, org:org + 2 * Ho - 1, org:org + 2 * Ho - 1] = gi
+    e = rel_err(dx.cpu(), _nhwc(gref))
+    print('proj dgrad rel err', e)
+    assert max(e) < 5e-5
