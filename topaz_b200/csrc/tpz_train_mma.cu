@@ -125,13 +125,17 @@ __global__ void __launch_bounds__(256) conv_mma_kernel(MGeom g, const float* __r
   const int cchunks = Cs / GBK;
   const int nk = taps * cchunks;
 
-  float acc[MT][4][4];
+  // The tensor core's fp32 accumulate truncates (measured: a chain of ~430 mma ops drifts by 2e-5 relative, biased), which
+  // is enough to flip ReLU masks of near-zero activations against the fp32 reference.  In the compensated mode the MMA
+  // chain is therefore cut every FLUSH k-chunks and the partial sums are added with round-to-nearest FADDs.
+  constexpr int FLUSH = 4;
+  float acc[MT][4][4], tot[MT][4][4];
 #pragma unroll
   for (int i = 0; i < MT; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+      for (int e = 0; e < 4; ++e) { acc[i][j][e] = 0.f; tot[i][j][e] = 0.f; }
 
   // issue-side running state: chunks are issued in order, so (tap row, tap col, channel chunk) advance incrementally
   // and the per-row gather offsets are recomputed only when the tap changes (no divisions in the steady state)
@@ -211,7 +215,21 @@ __global__ void __launch_bounds__(256) conv_mma_kernel(MGeom g, const float* __r
         for (int j = 0; j < 4; ++j) mma_split<X3>(acc[i][j], ah, al, bh[j], bl[j]);
       }
     }
+    if (X3 && (kc % FLUSH) == FLUSH - 1) {
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { tot[i][j][e] += acc[i][j][e]; acc[i][j][e] = 0.f; }
+    }
   }
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[i][j][e] += tot[i][j][e];
 
   // epilogue: c0:(g,2t) c1:(g,2t+1) c2:(g+8,2t) c3:(g+8,2t+1)
 #pragma unroll
@@ -277,13 +295,14 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(MGeom g, const float* __
   const int sidx = (BT == 64) ? tid : (tid & 127);
   const int s_p = sidx / QP, s_q = sidx % QP;
 
-  float acc[MI][NJ][4];
+  constexpr int FLUSH = 4;          // see conv_mma_kernel: cut the truncating MMA accumulation chain every 4 chunks
+  float acc[MI][NJ][4], tot[MI][NJ][4];
 #pragma unroll
   for (int i = 0; i < MI; ++i)
 #pragma unroll
     for (int j = 0; j < NJ; ++j)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+      for (int e = 0; e < 4; ++e) { acc[i][j][e] = 0.f; tot[i][j][e] = 0.f; }
 
   // running (n, oy, ox) of this thread's staging pixel; advanced by WBK pixels per issued chunk (no divisions)
   long long ip = pbeg + s_p;
@@ -339,7 +358,21 @@ __global__ void __launch_bounds__(256) wgrad_mma_kernel(MGeom g, const float* __
         for (int j = 0; j < NJ; ++j) mma_split<X3>(acc[i][j], ah, al, bh[j], bl[j]);
       }
     }
+    if (X3 && (it % FLUSH) == FLUSH - 1) {
+#pragma unroll
+      for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { tot[i][j][e] += acc[i][j][e]; acc[i][j][e] = 0.f; }
+    }
   }
+#pragma unroll
+  for (int i = 0; i < MI; ++i)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[i][j][e] += tot[i][j][e];
 #pragma unroll
   for (int i = 0; i < MI; ++i)
 #pragma unroll
