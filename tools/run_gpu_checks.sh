@@ -5,5 +5,4 @@ python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tai
 timeout 600 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; python - <<PY
 import json; d=json.load(open("gpurun_out/bench_final.json")); print("bench", round(d["value"],1), "ms", round(d["ms_per_step"],2), "e2e", round(d["e2e"]["value"],1), "frac", round(d["roofline"]["frac"],3), d["clocks"], "cpu", round(d["cpu_baseline"]["value"],3), d["cpu_baseline"]["cores"])
 PY
-timeout 300 python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | cut -c1-160
-timeout 900 python tools/bench_extra.py --workloads denoise,train,train_tf32,denoise3d --steps 6 2>/dev/null | tee gpurun_out/bench_extra_final.jsonl | cut -c1-200
+timeout 900 python tools/bench_extra.py --workloads denoise,train,denoise3d --steps 6 2>/dev/null | tee gpurun_out/bench_extra_final.jsonl | cut -c1-200
