@@ -170,6 +170,25 @@ int tpz_bias_grad_f32(const float* dy, long long P, int C, float* db, void* stre
 int tpz_relu_bwd_f32(float* dy, const float* y, long long n, void* stream);
 int tpz_crop_add_f32(float* dx, int N, int H, int W, int C, const float* g, int Ho, int Wo, int org, int stride,
                      void* stream);
+/* Training-mode BatchNorm of the strided classifier (nn.BatchNorm2d inside BasicConv / ResidA when bn=True, the default of
+ * `topaz train`: topaz/commands/train.py:91, topaz/model/features/resnet.py:68-70,101-104,134-141,185-204).  NHWC fp32 [P][C].
+ *  tpz_bn_stats_f32     : sums[c] += sum_p x[p][c], sums[C+c] += sum_p x[p][c]^2   (fp64; caller zeroes; all-reduced by the
+ *                         host across ranks so that multi-GPU training normalises with the statistics of the GLOBAL minibatch)
+ *  tpz_bn_fwd_f32       : sums != NULL (training): mean = sums[c]/count, var = sums[C+c]/count - mean^2 (biased),
+ *                         y = relu?((x-mean)*rsqrt(var+eps)*gamma+beta), save = {mean[C], invstd[C]}, and when running_mean
+ *                         != NULL: running = (1-momentum)*running + momentum*{mean, var*count/(count-1)};
+ *                         sums == NULL (eval): mean / invstd are READ from save
+ *  tpz_bn_bwd_reduce_f32: sums[c] += sum_p g[p][c], sums[C+c] += sum_p g[p][c]*xhat[p][c]   (xhat = (x-mean)*invstd)
+ *  tpz_bn_bwd_f32       : dx = gamma*invstd*(g - sums[c]/count - xhat*sums[C+c]/count) (dx may alias g);
+ *                         dbeta[c] += local_sums[c], dgamma[c] += local_sums[C+c] (this rank's share; gradients are summed
+ *                         over ranks later by the flat-gradient all-reduce)                                                */
+int tpz_bn_stats_f32(const float* x, long long P, int C, double* sums, void* stream);
+int tpz_bn_fwd_f32(const float* x, long long P, int C, const double* sums, long long count, const float* gamma,
+                   const float* beta, float eps, float momentum, float* running_mean, float* running_var, int relu,
+                   float* y, float* save, void* stream);
+int tpz_bn_bwd_reduce_f32(const float* g, const float* x, long long P, int C, const float* save, double* sums, void* stream);
+int tpz_bn_bwd_f32(const float* g, const float* x, long long P, int C, const float* save, const double* sums, long long count,
+                   const float* gamma, const double* local_sums, float* dgamma, float* dbeta, float* dx, void* stream);
 int tpz_ge_binomial_loss_grad(const float* scores, const double* labels, int B, double pi, double slack, int lo, int hi,
                               float* dscores, float* out5, void* stream);
 /* PN / GE_KL / PU objectives (topaz/methods.py:25-74, 168-255, 258-322): mode 0/1/2; out6 = {loss, ge_penalty, precision,

@@ -91,8 +91,35 @@ def _bn_eval(x, sd, prefix, eps=1e-5):
     return (x - m.view(shape)) / torch.sqrt(v.view(shape) + eps) * g.view(shape) + b.view(shape)
 
 
+def _bn_train(x, sd, prefix, eps=1e-5, momentum=0.1, running=None):
+    """nn.BatchNorm2d in training mode (resnet.py:68-70,134-141): biased batch variance for the normalisation,
+    running_mean/var <- (1-momentum)*running + momentum*(batch mean, UNBIASED batch variance).  `running` (a dict)
+    receives the updated buffers."""
+    g, b = _t(sd[prefix + '.weight']), _t(sd[prefix + '.bias'])
+    dims = [0] + list(range(2, x.dim()))
+    shape = (1, -1) + (1,) * (x.dim() - 2)
+    mean = x.mean(dims)
+    var = x.var(dims, unbiased=False)
+    if running is not None:
+        n = x.numel() // x.shape[1]
+        with torch.no_grad():
+            running[prefix + '.running_mean'] = (1 - momentum) * _t(sd[prefix + '.running_mean']).detach() + momentum * mean.detach()
+            running[prefix + '.running_var'] = (1 - momentum) * _t(sd[prefix + '.running_var']).detach() + \
+                momentum * var.detach() * (n / (n - 1.0))
+    return (x - mean.view(shape)) / torch.sqrt(var.view(shape) + eps) * g.view(shape) + b.view(shape)
+
+
+def _act(y, relu_masks):
+    """ReLU; with `relu_masks` (an iterator of 0/1 tensors in layer order) the mask is imposed instead of derived from
+    y, so that a gradient check is not at the mercy of activations within rounding noise of zero."""
+    if relu_masks is None:
+        return F.relu(y)
+    return y * next(relu_masks).to(y.dtype)
+
+
 def resnet_features(sd: Dict, x: torch.Tensor, kind: str, units: int, filled: bool,
-                    bn: bool = False, prefix: str = 'features.features.') -> torch.Tensor:
+                    bn: bool = False, prefix: str = 'features.features.', bn_train: bool = False,
+                    running: Optional[Dict] = None, relu_masks=None) -> torch.Tensor:
     """ResNet.forward (resnet.py:243-251) with fill() semantics (resnet.py:87-92,153-164,227-232).
 
     filled=True: input padded by width//2 once, every stride -> 1, dilations multiplied by the
@@ -118,8 +145,8 @@ def resnet_features(sd: Dict, x: torch.Tensor, kind: str, units: int, filled: bo
             else:
                 y = _conv(x, w, b, stride=blk['stride'], dilation=blk['dil'])
             if bn:
-                y = _bn_eval(y, sd, pre + 'bn')
-            x = F.relu(y)
+                y = _bn_train(y, sd, pre + 'bn', running=running) if bn_train else _bn_eval(y, sd, pre + 'bn')
+            x = _act(y, relu_masks)
         else:
             w0 = _t(sd[pre + 'conv0.weight'])
             b0 = _t(sd[pre + 'conv0.bias']) if (pre + 'conv0.bias') in sd else None
@@ -131,8 +158,8 @@ def resnet_features(sd: Dict, x: torch.Tensor, kind: str, units: int, filled: bo
                 d0, d1, s = 1, blk['dil'], blk['stride']
             h = _conv(x, w0, b0, dilation=d0)
             if bn:
-                h = _bn_eval(h, sd, pre + 'bn0')
-            h = F.relu(h)
+                h = _bn_train(h, sd, pre + 'bn0', running=running) if bn_train else _bn_eval(h, sd, pre + 'bn0')
+            h = _act(h, relu_masks)
             y = _conv(h, w1, b1, stride=s, dilation=d1)
             edge = d0 + d1
             xs = x[:, :, edge:-edge, edge:-edge]
@@ -142,8 +169,8 @@ def resnet_features(sd: Dict, x: torch.Tensor, kind: str, units: int, filled: bo
                 xs = xs[..., ::s, ::s]
             y = y + xs
             if bn:
-                y = _bn_eval(y, sd, pre + 'bn1')
-            x = F.relu(y)
+                y = _bn_train(y, sd, pre + 'bn1', running=running) if bn_train else _bn_eval(y, sd, pre + 'bn1')
+            x = _act(y, relu_masks)
             if filled:
                 cum *= blk['stride']
     return x
@@ -415,16 +442,25 @@ def adam_update(p, g, m, v, step, lr=2e-4, b1=0.9, b2=0.999, eps=1e-8):
 
 
 def ge_binomial_steps(sd: Dict, Xs: Sequence[np.ndarray], Ys: Sequence[np.ndarray], arch: str, units: int,
-                      pi: float, slack: float = 1.0, l2: float = 0.0, lr: float = 2e-4):
-    """Run len(Xs) GE_binomial.step calls (methods.py:98-165) with Adam, BN-free model, on CPU.
-    Returns (list of 5-tuples, list of per-step grads dict, final params dict)."""
-    params = {k: _t(v).clone().requires_grad_(True) for k, v in sd.items()}
+                      pi: float, slack: float = 1.0, l2: float = 0.0, lr: float = 2e-4, bn: bool = False):
+    """Run len(Xs) GE_binomial.step calls (methods.py:98-165) with Adam on CPU; bn=True: a BatchNorm model in train()
+    mode (minibatch statistics, running-buffer updates).
+    Returns (list of 5-tuples, list of per-step grads dict, final state dict)."""
+    def is_buf(k):
+        return k.endswith(('running_mean', 'running_var', 'num_batches_tracked'))
+    params = {k: _t(v).clone().requires_grad_(True) for k, v in sd.items() if not is_buf(k)}
+    bufs = {k: torch.as_tensor(np.asarray(v)).clone() for k, v in sd.items() if is_buf(k)}
     m = {k: torch.zeros_like(v) for k, v in params.items()}
     v2 = {k: torch.zeros_like(v) for k, v in params.items()}
     outs, grads = [], []
     for t, (X, Y) in enumerate(zip(Xs, Ys), 1):
         Yt = torch.from_numpy(np.asarray(Y, dtype=np.float64))
-        score = classifier_forward_grad(params, torch.from_numpy(X), arch, units).view(-1)
+        running = {}
+        score = classifier_forward_grad({**params, **bufs}, torch.from_numpy(X), arch, units, bn=bn, running=running).view(-1)
+        bufs.update(running)
+        for k in bufs:
+            if k.endswith('num_batches_tracked'):
+                bufs[k] = bufs[k] + 1
         cls, ge, loss = ge_binomial_loss(score, Yt, pi, slack)
         for p_ in params.values():
             p_.grad = None
@@ -440,13 +476,18 @@ def ge_binomial_steps(sd: Dict, Xs: Sequence[np.ndarray], Ys: Sequence[np.ndarra
                 newp, m[k], v2[k] = adam_update(params[k].detach(), g[k], m[k], v2[k], t, lr)
                 params[k].copy_(newp)
         outs.append((cls.item(), ge.item(), prec, tpr, fpr))
-    return outs, grads, {k: p_.detach().numpy() for k, p_ in params.items()}
+    final = {k: p_.detach().numpy() for k, p_ in params.items()}
+    final.update({k: b.numpy() for k, b in bufs.items()})
+    return outs, grads, final
 
 
-def classifier_forward_grad(params: Dict, x: torch.Tensor, arch: str, units: int) -> torch.Tensor:
-    """Same as classifier_forward(filled=False) but keeps the autograd graph (params are leaf tensors)."""
+def classifier_forward_grad(params: Dict, x: torch.Tensor, arch: str, units: int, bn: bool = False,
+                            running: Optional[Dict] = None, relu_masks=None) -> torch.Tensor:
+    """Same as classifier_forward(filled=False) but keeps the autograd graph (params are leaf tensors).  bn=True: the
+    model is in train() mode, i.e. BatchNorm uses minibatch statistics (`running` receives the updated buffers)."""
     assert arch in ('resnet8', 'resnet16')
-    z = resnet_features(params, x.float(), arch, units, filled=False, bn=False)
+    z = resnet_features(params, x.float(), arch, units, filled=False, bn=bn, bn_train=bn, running=running,
+                        relu_masks=iter(relu_masks) if relu_masks is not None else None)
     return _conv(z, params['classifier.weight'], params['classifier.bias'])
 
 

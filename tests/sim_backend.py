@@ -306,6 +306,46 @@ def t_crop_add(dx, g, org, stride):
     dx[:, org:org + (Ho - 1) * stride + 1:stride, org:org + (Wo - 1) * stride + 1:stride] += g
 
 
+def t_bn_stats(x, sums):
+    C = x.shape[-1]
+    xd = x.double().reshape(-1, C)
+    sums[:C] += xd.sum(0)
+    sums[C:] += (xd * xd).sum(0)
+
+
+def t_bn_fwd(x, sums, count, gamma, beta, eps, momentum, running_mean, running_var, relu, save):
+    C = x.shape[-1]
+    if sums is not None:
+        mean = sums[:C] / count
+        var = (sums[C:] / count - mean * mean).clamp_min(0)
+        invstd = 1.0 / torch.sqrt(var + eps)
+        save[:C] = mean.float()
+        save[C:] = invstd.float()
+        if running_mean is not None:
+            running_mean.mul_(1 - momentum).add_(momentum * mean.float())
+            running_var.mul_(1 - momentum).add_(momentum * (var * (count / (count - 1.0))).float())
+    y = (x - save[:C]) * (save[C:] * gamma.detach()) + beta.detach()
+    return torch.relu(y) if relu else y
+
+
+def t_bn_bwd_reduce(g, x, save, sums):
+    C = x.shape[-1]
+    xhat = ((x - save[:C]) * save[C:]).double().reshape(-1, C)
+    gd = g.double().reshape(-1, C)
+    sums[:C] += gd.sum(0)
+    sums[C:] += (gd * xhat).sum(0)
+
+
+def t_bn_bwd(g, x, save, sums, count, gamma, local_sums, dgamma, dbeta):
+    C = x.shape[-1]
+    xhat = (x - save[:C]) * save[C:]
+    a, b = (sums[:C] / count).float(), (sums[C:] / count).float()
+    dx = (save[C:] * gamma.detach()) * (g - a - xhat * b)
+    dbeta.add_(local_sums[:C].float())
+    dgamma.add_(local_sums[C:].float())
+    g.copy_(dx)
+
+
 def t_ge_loss_grad(scores, labels, pi, slack, lo, hi, dscore, out5):
     from oracle import topaz_oracle as O
     s = scores.detach().clone().requires_grad_(True)
@@ -342,7 +382,8 @@ def t_adam_step(fp, lr, b1, b2, eps, l2):
 def patched_training():
     from topaz_b200 import train_engine as T
     names = {'_conv_fwd': t_conv_fwd, '_conv_dgrad': t_conv_dgrad, '_conv_wgrad': t_conv_wgrad, '_relu_bwd': t_relu_bwd,
-             '_crop_add': t_crop_add, 'ge_loss_grad': t_ge_loss_grad, 'pu_objective_loss_grad': t_pu_objective, 'adam_step': t_adam_step,
+             '_crop_add': t_crop_add, '_bn_stats': t_bn_stats, '_bn_fwd': t_bn_fwd, '_bn_bwd_reduce': t_bn_bwd_reduce,
+             '_bn_bwd': t_bn_bwd, 'ge_loss_grad': t_ge_loss_grad, 'pu_objective_loss_grad': t_pu_objective, 'adam_step': t_adam_step,
              'read_back': lambda d, h: d.tolist(), '_repack': lambda fp: None}
     saved = {n: getattr(T, n) for n in names}
     try:

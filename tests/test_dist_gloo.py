@@ -17,7 +17,7 @@ def _free_port():
     s = socket.socket(); s.bind(('127.0.0.1', 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, bn=False):
     import torch.distributed as dist
     import torch.nn as nn
     os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
@@ -27,8 +27,13 @@ def _worker(rank, world, port, q):
     from topaz_b200.methods import GE_binomial
     from topaz_b200.model.factory import get_feature_extractor
     from topaz_b200.model.classifier import LinearClassifier
-    g = gold('ge_binomial_u32'); sd = weights_of(gold('resnet8_u32_pretrained'))
-    m = LinearClassifier(get_feature_extractor('resnet8', units=32, bn=False))
+    if bn:
+        from common import seeded_state
+        from common_shapes import classifier_shapes
+        g = gold('ge_binomial_u32_bn'); sd = seeded_state(classifier_shapes('resnet8', 32, 1, True), int(g['seed']))
+    else:
+        g = gold('ge_binomial_u32'); sd = weights_of(gold('resnet8_u32_pretrained'))
+    m = LinearClassifier(get_feature_extractor('resnet8', units=32, bn=bn))
     m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}); m.train()
     optim = torch.optim.Adam(m.parameters(), lr=2e-4)
     tr = GE_binomial(m, optim, nn.BCEWithLogitsLoss(), float(g['pi']))
@@ -36,10 +41,10 @@ def _worker(rank, world, port, q):
     Y = torch.from_numpy(g['Y'])
     outs = []
     with sim_backend.patched_training():
-        for step in range(2):
+        for step in range(1 if bn else 2):
             X = torch.from_numpy(np.random.default_rng(4000 + step).standard_normal((B, 71, 71)).astype(np.float32))
             outs.append(tr.step(X[rank * b:(rank + 1) * b], Y[rank * b:(rank + 1) * b]))
-    q.put((rank, outs, {k: p.detach().numpy().copy() for k, p in m.named_parameters()}))
+    q.put((rank, outs, {k: p.detach().numpy().copy() for k, p in m.state_dict().items()}))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -64,6 +69,43 @@ def test_data_parallel_ge_binomial_matches_single_process():
     # replicas stay bit-identical after the all-reduced update
     for k in res[0][2]:
         assert np.array_equal(res[0][2][k], res[1][2][k]), k
+
+
+def test_data_parallel_batchnorm_uses_global_minibatch_statistics():
+    """BatchNorm model, two ranks x 32 crops: the fp64 per-channel sums are all-reduced in the forward (statistics) and in
+    the backward (sum g, sum g*xhat), so one step equals the single-process step on the 64-crop minibatch: loss tuple and
+    running buffers (forward quantities) tightly, parameters within the Adam sign-flip bound (see test_host_logic)."""
+    from oracle import topaz_oracle as O
+    from common import seeded_state
+    from common_shapes import classifier_shapes
+    g = gold('ge_binomial_u32_bn')
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, True)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=900) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    res.sort(key=lambda r: r[0])
+    np.testing.assert_allclose(np.array(res[0][1]), g['outs'][:1], rtol=1e-3, atol=1e-6)
+    for k in res[0][2]:
+        assert np.array_equal(res[0][2][k], res[1][2][k]), k          # replicas (buffers included) stay bit-identical
+    # the golden stores the state after 3 steps; the single-process state after ONE step comes from the oracle (pinned to
+    # that golden in tests/test_oracle_golden.py)
+    sd = seeded_state(classifier_shapes('resnet8', 32, 1, True), int(g['seed']))
+    X = np.random.default_rng(4000).standard_normal((int(g['B']), 71, 71)).astype(np.float32)
+    _, _, final = O.ge_binomial_steps(sd, [X], [g['Y']], 'resnet8', 32, float(g['pi']), bn=True)
+    for k, v in res[0][2].items():
+        if k.endswith('num_batches_tracked'):
+            assert int(v) == 1
+        elif 'running' in k:
+            assert max(rel_err(v, final[k])) < 1e-5, k
+        else:
+            mx, l2 = rel_err(v, final[k])
+            assert mx < 5e-3 and l2 < 5e-4, (k, mx, l2)
 
 
 def test_sharding_helpers():

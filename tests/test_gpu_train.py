@@ -272,3 +272,145 @@ def test_proj_wgrad_dgrad_engine_geometry(N, Ci, Co):
     e = rel_err(dx.cpu(), _nhwc(gref))
     print('proj dgrad rel err', e)
     assert max(e) < 5e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# training-mode BatchNorm (the default `topaz train` model has --bn on: reference commands/train.py:91)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('N,H,C', [(64, 33, 32), (16, 11, 64), (256, 1, 128), (3, 5, 6), (2, 7, 48)])
+def test_batchnorm_kernels_match_torch_fp64(N, H, C):
+    """tpz_bn_stats / tpz_bn_fwd / tpz_bn_bwd_reduce / tpz_bn_bwd vs torch.nn.functional.batch_norm + autograd in fp64
+    (training mode: batch statistics, running-buffer update; eval mode: running statistics).  C = 6 takes the scalar
+    (C % 4 != 0) path, the others the float4 path; P from 25 to 69 696 rows covers all three reduction grids."""
+    from topaz_b200 import train_engine as T
+    rng = np.random.default_rng(N * 1000 + C)
+    x = torch.from_numpy((1.5 + 2.0 * rng.standard_normal((N, H, H, C))).astype(np.float32)).cuda()       # NHWC, mean != 0
+    g = torch.from_numpy(rng.standard_normal((N, H, H, C)).astype(np.float32)).cuda()
+    gamma = torch.from_numpy(rng.uniform(0.5, 1.5, C).astype(np.float32)).cuda()
+    beta = torch.from_numpy((0.3 * rng.standard_normal(C)).astype(np.float32)).cuda()
+    rm0 = torch.from_numpy((0.1 * rng.standard_normal(C)).astype(np.float32)).cuda()
+    rv0 = torch.from_numpy(rng.uniform(0.5, 1.5, C).astype(np.float32)).cuda()
+    eps, mom = 1e-5, 0.1
+    P = N * H * H
+    # kernels: statistics + forward
+    sums = torch.zeros(2 * C, dtype=torch.float64, device='cuda')
+    T._bn_stats(x, sums)
+    xd = x.double().reshape(-1, C)
+    assert max(rel_err(sums[:C].cpu(), xd.sum(0).cpu())) < 1e-12 and max(rel_err(sums[C:].cpu(), (xd * xd).sum(0).cpu())) < 1e-12
+    save = torch.empty(2 * C, device='cuda')
+    rm1, rv1 = rm0.clone(), rv0.clone()
+    y = T._bn_fwd(x, sums, P, gamma, beta, eps, mom, rm1, rv1, True, save)
+    # fp64 reference (NCHW); the ReLU mask of the kernel output is imposed so that outputs within fp32 rounding of zero
+    # cannot flip a mask between the two (their forward values are ~1e-7 either way)
+    xr = x.double().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    gr, br = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    rm, rv = rm0.double().clone(), rv0.double().clone()
+    yr = F.batch_norm(xr, rm, rv, gr, br, True, mom, eps) * (y > 0).permute(0, 3, 1, 2).double()
+    yr.backward(g.double().permute(0, 3, 1, 2))
+    assert max(rel_err(y.permute(0, 3, 1, 2).cpu(), yr.detach().cpu())) < 2e-6
+    assert max(rel_err(rm1.cpu(), rm.cpu())) < 1e-6 and max(rel_err(rv1.cpu(), rv.cpu())) < 1e-6
+    mean = xd.mean(0); invstd = 1.0 / torch.sqrt(xd.var(0, unbiased=False) + eps)
+    assert max(rel_err(save[:C].cpu(), mean.cpu())) < 1e-6 and max(rel_err(save[C:].cpu(), invstd.cpu())) < 1e-6
+    # backward: g masked by the ReLU of y, as _conv_dgrad(mask=...) / _relu_bwd deliver it
+    gm = (g * (y > 0)).contiguous()
+    local = torch.zeros(2 * C, dtype=torch.float64, device='cuda')
+    T._bn_bwd_reduce(gm, x, save, local)
+    dgamma = torch.zeros(C, device='cuda'); dbeta = torch.zeros(C, device='cuda')
+    T._bn_bwd(gm, x, save, local, P, gamma, local, dgamma, dbeta)
+    assert max(rel_err(dgamma.cpu(), gr.grad.cpu())) < 1e-5, rel_err(dgamma.cpu(), gr.grad.cpu())
+    assert max(rel_err(dbeta.cpu(), br.grad.cpu())) < 1e-5
+    assert max(rel_err(gm.permute(0, 3, 1, 2).cpu(), xr.grad.cpu())) < 1e-5, rel_err(gm.permute(0, 3, 1, 2).cpu(), xr.grad.cpu())
+    # eval mode: statistics read from `save` (running buffers), no ReLU
+    save_e = torch.cat([rm0, torch.rsqrt(rv0 + eps)])
+    ye = T._bn_fwd(x, None, 0, gamma, beta, eps, 0.0, None, None, False, save_e)
+    yer = F.batch_norm(x.double().permute(0, 3, 1, 2), rm0.double(), rv0.double(), gamma.double(), beta.double(), False, mom, eps)
+    assert max(rel_err(ye.permute(0, 3, 1, 2).cpu(), yer.cpu())) < 2e-6
+
+
+def _bn_case():
+    from common import seeded_state
+    from common_shapes import classifier_shapes
+    from topaz_b200.model.factory import get_feature_extractor
+    from topaz_b200.model.classifier import LinearClassifier
+    g = gold('ge_binomial_u32_bn')
+    sd = seeded_state(classifier_shapes('resnet8', 32, 1, True), int(g['seed']))
+    m = LinearClassifier(get_feature_extractor('resnet8', units=32, bn=True))
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    return g, sd, m
+
+
+def test_batchnorm_training_gradients_match_oracle_with_imposed_masks():
+    """One GE-binomial step of ResNet8(units=32, bn=True) in train() mode: logits, loss tuple and EVERY gradient vs autograd
+    through the oracle.  He-random weights leave a handful of the 8 M BatchNorm outputs within rounding noise of zero, and a
+    single flipped ReLU mask moves the early-layer gradients by ~3e-3 (tests/test_host_logic.py), so the oracle is run with
+    the ReLU masks of the GPU forward imposed (O._act); the flipped activations themselves are ~1e-7, invisible in the
+    forward.  With the masks aligned the north-star tolerance (1e-3) applies to every tensor."""
+    from topaz_b200 import train_engine as T
+    g, sd, m = _bn_case()
+    m.cuda(); m.train()
+    B, pi = int(g['B']), float(g['pi'])
+    X = torch.from_numpy(np.random.default_rng(4000).standard_normal((B, 71, 71)).astype(np.float32))
+    Y = torch.from_numpy(g['Y'])
+    T.flat_params(m)
+    score = m(X.cuda()).view(-1)
+    tape = m.__dict__['_tpz_tape']
+    masks = []
+    for rec in tape:
+        if rec['kind'] == 'conv':
+            masks.append((rec['y'] > 0).permute(0, 3, 1, 2).cpu())
+        elif rec['kind'] == 'resid':
+            masks.append((rec['h'] > 0).permute(0, 3, 1, 2).cpu())
+            masks.append((rec['y'] > 0).permute(0, 3, 1, 2).cpu())
+    assert len(masks) == 8
+    params = {k: torch.from_numpy(v).clone().requires_grad_('running' not in k and v.dtype == np.float32) for k, v in sd.items()}
+    running = {}
+    score_ref = O.classifier_forward_grad(params, X, 'resnet8', 32, bn=True, running=running, relu_masks=masks).view(-1)
+    assert max(rel_err(score.detach().cpu().numpy(), score_ref.detach().numpy())) < 1e-4
+    cls, ge, loss = O.ge_binomial_loss(score_ref, Y, pi, 1.0)
+    loss.backward()
+    ds = torch.empty(B, device='cuda'); o5 = torch.empty(5, device='cuda')
+    T.ge_loss_grad(score.contiguous(), Y.cuda(), pi, 1.0, 0, B, ds, o5)
+    np.testing.assert_allclose(o5.cpu().numpy()[:2], [cls.item(), ge.item()], rtol=1e-4)
+    T.backward(m, ds)
+    errs = {k: max(rel_err(p.grad.cpu().numpy(), params[k].grad.numpy())) for k, p in m.named_parameters()}
+    print({k: f'{v:.1e}' for k, v in errs.items()})
+    assert max(errs.values()) < 1e-3, errs
+    # running statistics after this one forward (momentum 0.1, unbiased variance) and the batch counter
+    sdm = m.state_dict()
+    for k, v in running.items():
+        assert max(rel_err(sdm[k].cpu().numpy(), v.numpy())) < 1e-5, k
+    assert all(int(v) == 1 for k, v in sdm.items() if k.endswith('num_batches_tracked'))
+
+
+def test_three_ge_binomial_batchnorm_steps_match_reference_golden():
+    """Three full GE_binomial.step calls on the BatchNorm model vs the REAL reference's golden: loss tuples, BatchNorm
+    running buffers (forward-only quantities: tight), parameters (Adam moves an element by ~lr per step whatever |g| is,
+    so elements whose tiny gradient changed sign through a mask flip end up to 2*lr*3 apart: max loose, rel-L2 tight);
+    then the eval-mode strided forward (running statistics) and the filled dense forward with the folded BatchNorm."""
+    from topaz_b200.methods import GE_binomial
+    g, sd, m = _bn_case()
+    m.cuda(); m.train()
+    optim = torch.optim.Adam(m.parameters(), lr=2e-4)
+    tr = GE_binomial(m, optim, nn.BCEWithLogitsLoss(), float(g['pi']), l2=0.0, slack=1.0)
+    B = int(g['B']); Y = torch.from_numpy(g['Y']).cuda()
+    outs = []
+    for step in range(3):
+        X = torch.from_numpy(np.random.default_rng(4000 + step).standard_normal((B, 71, 71)).astype(np.float32)).cuda()
+        outs.append(tr.step(X, Y))
+    np.testing.assert_allclose(np.array(outs), g['outs'], rtol=2e-3, atol=1e-6)
+    for k, v in m.state_dict().items():
+        if k.endswith('num_batches_tracked'):
+            assert int(v) == 3
+        elif 'running' in k:
+            assert max(rel_err(v.cpu().numpy(), g['p3.' + k])) < 1e-3, k
+        else:
+            mx, l2 = rel_err(v.detach().cpu().numpy(), g['p3.' + k])
+            assert mx < 5e-3 and l2 < 1e-3, (k, mx, l2)
+    m.eval()
+    with torch.no_grad():
+        yc = m(torch.from_numpy(np.random.default_rng(4100).standard_normal((8, 71, 71)).astype(np.float32)).cuda()).cpu().numpy()
+    assert yc.shape == g['y_crops'].shape and max(rel_err(yc, g['y_crops'])) < 2e-3
+    m.fill()
+    with torch.no_grad():
+        yd = m(torch.from_numpy(g['x_dense']).cuda()).cpu().numpy()
+    assert yd.shape == g['y_dense'].shape and max(rel_err(yd, g['y_dense'])) < 5e-3

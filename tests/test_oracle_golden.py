@@ -92,6 +92,49 @@ def test_ge_binomial_three_steps():
         _close(final[k], g['p3.' + k], 1e-5)
 
 
+def test_ge_binomial_batchnorm_steps_match_reference():
+    """Training-mode BatchNorm in the oracle (batch statistics, running buffers) vs the reference's 3 GE_binomial steps of
+    ResNet8(units=32, bn=True) -- the default model of `topaz train` (commands/train.py:89-91).  Both run the same fp32
+    torch CPU operators, so no ReLU mask flips separate them; the imposed-mask variant used by the GPU gradient test
+    must give the same gradient when fed the oracle's own masks."""
+    import torch
+    from common_shapes import classifier_shapes
+    g = gold('ge_binomial_u32_bn')
+    sd = seeded_state(classifier_shapes('resnet8', 32, 1, True), int(g['seed']))
+    B = int(g['B'])
+    Xs = [np.random.default_rng(4000 + s).standard_normal((B, 71, 71)).astype(np.float32) for s in range(3)]
+    outs, grads, final = O.ge_binomial_steps(sd, Xs, [g['Y']] * 3, 'resnet8', 32, float(g['pi']), bn=True)
+    np.testing.assert_allclose(np.array(outs), g['outs'], rtol=2e-4, atol=1e-6)
+    for k in grads[0]:
+        _close(grads[0][k], g['g1.' + k], 5e-4)
+    for k in final:
+        if k.endswith('num_batches_tracked'):
+            assert int(final[k]) == 3
+        else:
+            _close(final[k], g['p3.' + k], 2e-4)
+    # imposed masks == derived masks -> identical gradient
+    params = {k: torch.from_numpy(v).clone().requires_grad_(v.dtype == np.float32 and 'running' not in k) for k, v in sd.items()}
+    masks = []
+    with torch.no_grad():
+        x = torch.from_numpy(Xs[0]).unsqueeze(1)
+        spec = O.resnet_spec('resnet8', 32)
+        # derive the masks by running the oracle with a recording activation
+        rec = []
+        orig = O._act
+        O._act = lambda y, rm: (rec.append((y > 0)), orig(y, None))[1]
+        try:
+            O.classifier_forward_grad(params, torch.from_numpy(Xs[0]), 'resnet8', 32, bn=True)
+        finally:
+            O._act = orig
+        masks = rec
+    assert len(masks) == 8        # conv, 3 x (act0, act1), conv
+    score = O.classifier_forward_grad(params, torch.from_numpy(Xs[0]), 'resnet8', 32, bn=True, relu_masks=masks).view(-1)
+    _, _, loss = O.ge_binomial_loss(score, torch.from_numpy(g['Y']), float(g['pi']), 1.0)
+    loss.backward()
+    for k in grads[0]:
+        _close(params[k].grad.numpy(), grads[0][k], 1e-6)
+
+
 def test_filters():
     g = gold('filters')
     _close(O.gaussian_denoise(g['img'], 1.5), g['gauss'])

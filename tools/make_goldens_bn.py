@@ -1,0 +1,59 @@
+#!/usr/bin/env python
+"""Golden vectors for the BatchNorm training path (`topaz train` default: --bn on), produced by the REAL reference
+imported read-only from /root/reference (h5py stub).  Build container only:
+    PYTHONDONTWRITEBYTECODE=1 python tools/make_goldens_bn.py
+Writes tests/golden/ge_binomial_u32_bn.npz: 3 GE_binomial steps of ResNet8(units=32, bn=True) from seeded weights
+(tests/common.seeded_state, seed 401), gradients of step 1, every parameter / buffer after step 3, the unfilled
+eval-mode scores of a crop batch and the filled dense scores of a small image after training."""
+import os, sys
+sys.dont_write_bytecode = True
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, '/root/reference')
+sys.path.insert(0, os.path.join(ROOT, 'tools', 'stubs'))
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+import numpy as np
+import torch
+import torch.nn as nn
+
+torch.set_num_threads(os.cpu_count())
+from common import seeded_state, GOLD  # noqa: E402
+from topaz.model.classifier import LinearClassifier
+from topaz.model.features.resnet import ResNet8
+from topaz.methods import GE_binomial
+
+rng = np.random.default_rng
+SEED = 401
+m = LinearClassifier(ResNet8(units=32, bn=True))
+sd = seeded_state({k: tuple(v.shape) for k, v in m.state_dict().items()}, SEED)
+m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+m.train()
+optim = torch.optim.Adam(m.parameters(), lr=2e-4)
+tr = GE_binomial(m, optim, nn.BCEWithLogitsLoss(), 0.035, l2=0.0, slack=1.0)
+B = 64
+Y = np.array([1.0] * 4 + [0.0] * (B - 4))
+outs, grads1 = [], None
+for step in range(3):
+    X = rng(4000 + step).standard_normal((B, 71, 71)).astype(np.float32)
+    orig = optim.step
+    if step == 0:
+        def grab(*a, **k):
+            global grads1
+            grads1 = {n: p.grad.detach().clone().numpy() for n, p in m.named_parameters()}
+            return orig(*a, **k)
+        optim.step = grab
+    outs.append(tr.step(torch.from_numpy(X), torch.from_numpy(Y)))
+    optim.step = orig
+final = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+m.eval()
+Xe = rng(4100).standard_normal((8, 71, 71)).astype(np.float32)
+with torch.no_grad():
+    y_crops = m(torch.from_numpy(Xe)).numpy()
+    m.fill()
+    xd = rng(4101).standard_normal((1, 96, 80)).astype(np.float32)
+    y_dense = m(torch.from_numpy(xd)).numpy()
+    m.unfill()
+path = os.path.join(GOLD, 'ge_binomial_u32_bn.npz')
+np.savez_compressed(path, seed=np.int64(SEED), B=np.int64(B), Y=Y, pi=np.float64(0.035), outs=np.array(outs, dtype=np.float64),
+                    y_crops=y_crops, x_dense=xd, y_dense=y_dense,
+                    **{'g1.' + k: v for k, v in grads1.items()}, **{'p3.' + k: v for k, v in final.items()})
+print('wrote', path, f'{os.path.getsize(path) / 1e6:.2f} MB', 'outs', outs)

@@ -183,15 +183,112 @@ def _crop_add(dx, g, org, stride):
     check(_lib.lib().tpz_crop_add_f32(_p(dx), N, H, W, Cc, _p(g), g.shape[1], g.shape[2], org, stride, _s()))
 
 
+class _BnWorkspace:
+    """fp64 per-channel sum slots of one training step (forward and backward statistics of every BatchNorm layer),
+    zeroed by ONE fill launch; slices are handed out in call order."""
+
+    def __init__(self, n_doubles: int, device):
+        ops._count(1)
+        self.buf = torch.zeros(max(n_doubles, 1), dtype=torch.float64, device=device)
+        self.used = 0
+
+    def take(self, n: int) -> torch.Tensor:
+        if self.used + n > self.buf.numel():          # e.g. a second forward on the same tape: fall back to a fresh slot
+            ops._count(1)
+            return torch.zeros(n, dtype=torch.float64, device=self.buf.device)
+        out = self.buf[self.used:self.used + n]
+        self.used += n
+        return out
+
+
+def _dp():
+    """torch.distributed when this process is one rank of a data-parallel job (see methods._run), else None."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist
+    return None
+
+
+def _bn_stats(x, sums):
+    ops._count(1)
+    check(_lib.lib().tpz_bn_stats_f32(_p(x), x.numel() // x.shape[-1], x.shape[-1], _p(sums), _s()))
+
+
+def _bn_fwd(x, sums, count, gamma, beta, eps, momentum, running_mean, running_var, relu, save):
+    y = torch.empty_like(x)
+    ops._count(1)
+    check(_lib.lib().tpz_bn_fwd_f32(_p(x), x.numel() // x.shape[-1], x.shape[-1], _p(sums), int(count), _p(gamma), _p(beta),
+                                    float(eps), float(momentum), _p(running_mean), _p(running_var), int(relu), _p(y),
+                                    _p(save), _s()))
+    return y
+
+
+def _bn_bwd_reduce(g, x, save, sums):
+    ops._count(1)
+    check(_lib.lib().tpz_bn_bwd_reduce_f32(_p(g), _p(x), x.numel() // x.shape[-1], x.shape[-1], _p(save), _p(sums), _s()))
+
+
+def _bn_bwd(g, x, save, sums, count, gamma, local_sums, dgamma, dbeta):
+    """in place: g <- d(loss)/d(bn input)"""
+    ops._count(1)
+    check(_lib.lib().tpz_bn_bwd_f32(_p(g), _p(x), x.numel() // x.shape[-1], x.shape[-1], _p(save), _p(sums), int(count),
+                                    _p(gamma), _p(local_sums), _p(dgamma), _p(dbeta), _p(g), _s()))
+
+
+def _bn_forward(c, bn, relu, ws):
+    """nn.BatchNorm2d.forward (+ReLU) on the NHWC conv output `c` (reference resnet.py:101-104,186-187,201-203).
+    Training mode: statistics of the minibatch -- of the GLOBAL minibatch under data parallelism (the raw fp64 sums are
+    all-reduced) -- and the running-statistics update; eval mode: the running statistics.  Returns (y, save, count)."""
+    C_ = c.shape[-1]
+    save = torch.empty(2 * C_, dtype=torch.float32, device=c.device)
+    if bn.training or bn.running_mean is None:
+        P = c.numel() // C_
+        sums = ws.take(2 * C_)
+        _bn_stats(c, sums)
+        dist = _dp()
+        count = P
+        if dist is not None:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+            count = P * dist.get_world_size()
+        if count <= 1:
+            raise ValueError('Expected more than 1 value per channel when training, got input size ' + str(list(c.shape)))
+        track = bn.track_running_stats and bn.running_mean is not None
+        if track and bn.momentum is None:
+            raise NotImplementedError('topaz_b200: BatchNorm momentum=None (cumulative average) is not supported')
+        y = _bn_fwd(c, sums, count, bn.weight, bn.bias, bn.eps, bn.momentum if track else 0.0,
+                    bn.running_mean if track else None, bn.running_var if track else None, relu, save)
+        if track and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        return y, save, count
+    save[:C_] = bn.running_mean
+    save[C_:] = torch.rsqrt(bn.running_var.float() + bn.eps)
+    y = _bn_fwd(c, None, 0, bn.weight, bn.bias, bn.eps, 0.0, None, None, relu, save)
+    return y, save, 0
+
+
+def _bn_backward(g, c, save, count, bn, ws):
+    """Gradient through training-mode BatchNorm: in place g <- d/d(c); accumulates bn.weight.grad / bn.bias.grad."""
+    if count == 0:
+        raise RuntimeError('topaz_b200: backward through an eval-mode BatchNorm layer')
+    C_ = c.shape[-1]
+    local = ws.take(2 * C_)
+    _bn_bwd_reduce(g, c, save, local)
+    sums = local
+    dist = _dp()
+    if dist is not None:
+        sums = local.clone()
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    _bn_bwd(g, c, save, sums, count, bn.weight, local, bn.weight.grad if bn.weight is not None else None,
+            bn.bias.grad if bn.bias is not None else None)
+    return g
+
+
 def _osz(n, k, dil, stride):
     return (n - (k - 1) * dil - 1) // stride + 1
 
 
 def _check_trainable(blocks):
     for b in blocks:
-        if b.get('bn') is not None or b.get('bn0') is not None or b.get('bn1') is not None:
-            raise NotImplementedError('topaz_b200: BatchNorm classifiers are not supported by the B200 training path '
-                                      '(the default `topaz train` models are BN-free pretrained ResNets)')
         for k in ('slope', 'slope0', 'slope1'):
             if k in b and b[k] != 0.0:
                 raise NotImplementedError('topaz_b200: only ReLU classifiers are supported by the B200 training path')
@@ -203,31 +300,51 @@ def _forward(model_features, classifier, x: torch.Tensor, save: bool):
     _check_trainable(blocks)
     tape = []
     cur = x
+    n_bn = sum(2 * 2 * bn.num_features for blk in blocks for bn in (blk.get('bn'), blk.get('bn0'), blk.get('bn1'))
+               if bn is not None)
+    ws = _BnWorkspace(n_bn, x.device) if n_bn else None
     for blk in blocks:
         N, H, W, _ = cur.shape
         if blk['kind'] == 'conv':
-            w, b = blk['w'], blk['b']
+            w, b, bn = blk['w'], blk['b'], blk.get('bn')
             k = w.shape[-1]
             Ho, Wo = _osz(H, k, blk['dil'], blk['stride']), _osz(W, k, blk['dil'], blk['stride'])
-            y = _conv_fwd(cur, w, b, blk['stride'], blk['dil'], 0, Ho, Wo, relu=True)
-            tape.append(dict(kind='conv', x=cur, y=y, w=w, b=b, stride=blk['stride'], dil=blk['dil']))
+            y = _conv_fwd(cur, w, b, blk['stride'], blk['dil'], 0, Ho, Wo, relu=bn is None)
+            rec = dict(kind='conv', x=cur, y=y, w=w, b=b, stride=blk['stride'], dil=blk['dil'])
+            if bn is not None:
+                z, sv, cnt = _bn_forward(y, bn, True, ws)
+                rec.update(bn=bn, c=y, save=sv, count=cnt, y=z)
+                y = z
+            tape.append(rec)
             cur = y
         else:
             w0, b0, w1, b1 = blk['w0'], blk['b0'], blk['w1'], blk['b1']
+            bn0, bn1 = blk.get('bn0'), blk.get('bn1')
             d0, d1, s = blk['d0'], blk['d1'], blk['stride']
             H1, W1 = _osz(H, 3, d0, 1), _osz(W, 3, d0, 1)
-            h = _conv_fwd(cur, w0, b0, 1, d0, 0, H1, W1, relu=True)
+            h = _conv_fwd(cur, w0, b0, 1, d0, 0, H1, W1, relu=bn0 is None)
+            rec = dict(kind='resid', x=cur, w0=w0, b0=b0, w1=w1, b1=b1, proj=blk['proj'], d0=d0, d1=d1, stride=s)
+            if bn0 is not None:
+                hc = h
+                h, sv, cnt = _bn_forward(hc, bn0, True, ws)
+                rec.update(bn0=bn0, c0=hc, save0=sv, count0=cnt)
             Ho, Wo = _osz(H1, 3, d1, s), _osz(W1, 3, d1, s)
             edge = d0 + d1
             pr = None
             if blk['proj'] is not None:
                 pr = _conv_fwd(cur, blk['proj'], None, s, 1, edge, Ho, Wo, relu=False)
-                y = _conv_fwd(h, w1, b1, s, d1, 0, Ho, Wo, relu=True, res=pr, res_org=0, res_stride=1)
+                y = _conv_fwd(h, w1, b1, s, d1, 0, Ho, Wo, relu=bn1 is None, res=pr, res_org=0, res_stride=1)
             else:
-                y = _conv_fwd(h, w1, b1, s, d1, 0, Ho, Wo, relu=True, res=cur, res_org=edge, res_stride=s)
-            tape.append(dict(kind='resid', x=cur, h=h, y=y, w0=w0, b0=b0, w1=w1, b1=b1, proj=blk['proj'], d0=d0, d1=d1,
-                             stride=s, edge=edge))
+                y = _conv_fwd(h, w1, b1, s, d1, 0, Ho, Wo, relu=bn1 is None, res=cur, res_org=edge, res_stride=s)
+            if bn1 is not None:
+                yc = y
+                y, sv, cnt = _bn_forward(yc, bn1, True, ws)
+                rec.update(bn1=bn1, c1=yc, save1=sv, count1=cnt)
+            rec.update(h=h, y=y, edge=edge)
+            tape.append(rec)
             cur = y
+    if ws is not None and tape:
+        tape[0]['bn_ws'] = ws
     if classifier is None:
         return cur, tape
     N, H, W, _ = cur.shape
@@ -280,6 +397,7 @@ def backward(model, dscore: torch.Tensor):
     fp.ensure_grads()
     _CUR['fp'] = fp
     g = None
+    ws = tape[0].get('bn_ws')
     with torch.no_grad():
         for rec in reversed(tape):
             if rec['kind'] == 'cls':
@@ -290,6 +408,8 @@ def backward(model, dscore: torch.Tensor):
                 g = _conv_dgrad(g, rec['w'], 1, 1, 0, H, W, mask=x)          # masked by relu of the last feature conv
             elif rec['kind'] == 'conv':
                 x = rec['x']
+                if rec.get('bn') is not None:                                 # g: d/d(bn output) -> d/d(conv output)
+                    g = _bn_backward(g, rec['c'], rec['save'], rec['count'], rec['bn'], ws)
                 _conv_wgrad(x, g, rec['w'].grad, rec['b'].grad if rec['b'] is not None else None, rec['stride'], rec['dil'], 0)
                 if x.shape[3] == 1 and rec is tape[0]:
                     g = None                                                  # network input: no data gradient needed
@@ -298,8 +418,12 @@ def backward(model, dscore: torch.Tensor):
             else:
                 x, h = rec['x'], rec['h']
                 s, d0, d1, edge = rec['stride'], rec['d0'], rec['d1'], rec['edge']
+                if rec.get('bn1') is not None:                                # bn1 sits after the skip addition (resnet.py:200-203)
+                    g = _bn_backward(g, rec['c1'], rec['save1'], rec['count1'], rec['bn1'], ws)
                 _conv_wgrad(h, g, rec['w1'].grad, rec['b1'].grad if rec['b1'] is not None else None, s, d1, 0)
                 dh = _conv_dgrad(g, rec['w1'], s, d1, 0, h.shape[1], h.shape[2], mask=h)
+                if rec.get('bn0') is not None:
+                    dh = _bn_backward(dh, rec['c0'], rec['save0'], rec['count0'], rec['bn0'], ws)
                 _conv_wgrad(x, dh, rec['w0'].grad, rec['b0'].grad if rec['b0'] is not None else None, 1, d0, 0)
                 dx = _conv_dgrad(dh, rec['w0'], 1, d0, 0, x.shape[1], x.shape[2])
                 if rec['proj'] is not None:
