@@ -86,3 +86,88 @@ def test_reference_denoise_pipeline_runs_on_dropin_unet(aliased, monkeypatch):
         y = dn.denoise(g['img'].copy(), patch_size=64, padding=24)
     mx, l2 = rel_err(y, g['y_pat'])
     assert mx < 1e-3 and l2 < 1e-3, (mx, l2)
+
+
+def test_reference_fit_epochs_runs_on_dropin_modules(aliased, tmp_path):
+    """The reference's own training loop (training.py: make_training_step_method -> fit_epochs -> fit_epoch /
+    evaluate_model -> torch.save of the whole module) on the default `topaz train` model (ResNet8, 32 units, BatchNorm ON,
+    l2 > 0): once in a subprocess on the unmodified reference, once in-process on the drop-in modules (simulated kernels).
+    Same log lines (train: loss, GE penalty, precision, tpr, fpr; test: loss, ..., auprc), same final state, and the saved
+    .sav holds no engine caches and still loads / evaluates."""
+    import subprocess
+    import ref_fit_script
+    ref_dir, our_dir = tmp_path / 'ref', tmp_path / 'ours'
+    ref_dir.mkdir(); our_dir.mkdir()
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE='1', PYTHONPATH=os.pathsep.join([REF, os.path.join(ROOT, 'tools', 'stubs')]))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'ref_fit_script.py'), str(ref_dir)], env=env, cwd=str(tmp_path),
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.strip().splitlines()[-1] == 'topaz.model.classifier'
+    with sim_backend.patched_training():
+        owner = ref_fit_script.run(str(our_dir))
+    assert owner == 'topaz_b200.model.classifier'
+
+    def table(p):
+        rows = [l.rstrip('\n').split('\t') for l in open(p)]
+        return rows[0], rows[1:]
+    (h0, ref_rows), (h1, our_rows) = table(ref_dir / 'log.tsv'), table(our_dir / 'log.tsv')
+    assert h0 == h1 and len(ref_rows) == len(our_rows) == 6
+    for a, b in zip(ref_rows, our_rows):
+        assert a[:3] == b[:3]
+        for u, v in zip(a[3:], b[3:]):
+            if u == '-':
+                assert v == '-'
+            else:
+                # train lines: fp32-level; test lines: dense fp16-operand forward of He-random weights (TOL_SEEDED-like)
+                assert abs(float(u) - float(v)) <= (2e-3 if a[2] == 'train' else 1e-2) * max(abs(float(u)), 1e-3), (a, b)
+    fr, fo = np.load(ref_dir / 'final.npz'), np.load(our_dir / 'final.npz')
+    assert fr.files == fo.files
+    for k in fr.files:
+        if k.endswith('num_batches_tracked'):
+            assert int(fr[k]) == int(fo[k]) == 4
+            continue
+        mx, l2 = rel_err(fo[k], fr[k])
+        assert mx < 5e-3 and l2 < 1e-3, (k, mx, l2)
+    # the whole-module pickle written by training.py:600-601 carries parameters and buffers only
+    for ep in (1, 2):
+        saved = torch.load(str(our_dir / f'model_epoch{ep}.sav'), weights_only=False)
+        assert not [k for mod in saved.modules() for k in mod.__dict__ if k.startswith('_tpz_')]
+        assert abs(os.path.getsize(our_dir / f'model_epoch{ep}.sav') - os.path.getsize(ref_dir / f'model_epoch{ep}.sav')) < 65536
+    saved.eval(); saved.fill()
+    with sim_backend.patched(), torch.no_grad():
+        y = saved(torch.zeros(1, 1, 80, 80))
+    assert y.shape == (1, 1, 80, 80) and torch.isfinite(y).all()
+
+
+def test_adam_state_survives_a_device_round_trip():
+    """training.py:600-603 moves the classifier to the CPU for torch.save and back after every epoch: the parameters get
+    new storage, the flat buffers must be rebuilt around them WITHOUT resetting the Adam moments or the step count."""
+    import torch.nn as nn
+    from topaz_b200.methods import GE_binomial
+    from topaz_b200.model.factory import get_feature_extractor
+    from topaz_b200.model.classifier import LinearClassifier
+
+    def run(round_trip):
+        torch.manual_seed(0)
+        m = LinearClassifier(get_feature_extractor('resnet8', units=16, bn=True)); m.train()
+        opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+        tr = GE_binomial(m, opt, nn.BCEWithLogitsLoss(), 0.05)
+        Y = torch.tensor([1.0] * 2 + [0.0] * 6, dtype=torch.float64)
+        outs = []
+        with sim_backend.patched_training():
+            for step in range(4):
+                X = torch.from_numpy(np.random.default_rng(step).standard_normal((8, 71, 71)).astype(np.float32))
+                outs.append(tr.step(X, Y))
+                if round_trip and step == 1:
+                    for p in m.parameters():          # what nn.Module.cpu().cuda() does to every parameter
+                        p.data = p.data.clone()
+                        if p.grad is not None:
+                            p.grad.data = p.grad.data.clone()
+        st = opt.state[next(iter(m.parameters()))]
+        return np.array(outs), {k: v.detach().numpy().copy() for k, v in m.state_dict().items()}, float(st['step'])
+    o0, s0, n0 = run(False)
+    o1, s1, n1 = run(True)
+    assert n0 == n1 == 4.0
+    np.testing.assert_array_equal(o0, o1)
+    for k in s0:
+        np.testing.assert_array_equal(s0[k], s1[k], err_msg=k)

@@ -32,8 +32,12 @@ def install(names=None):
         mod = importlib.import_module(ours)
         sys.modules[ref] = mod
         parent, _, leaf = ref.rpartition('.')
-        if parent in sys.modules:                 # keep `import topaz.model.factory as f` style attribute access working
-            setattr(sys.modules[parent], leaf, mod)
+        try:                                      # `import topaz.model.classifier as C` (training.py:15) resolves the leaf as
+            pkg = importlib.import_module(parent)  # an ATTRIBUTE of the (real, empty) parent package: import it and bind
+        except ImportError:
+            pkg = sys.modules.get(parent)
+        if pkg is not None:
+            setattr(pkg, leaf, mod)
     for (ref_mod, fn), (our_mod, our_fn) in _FUNCTION_PATCHES.items():
         if names is not None and ref_mod not in names:
             continue

@@ -8,10 +8,10 @@ from collections import OrderedDict
 import torch
 from torch import nn
 
-from topaz_b200.model.utils import load_pretrained_state
+from topaz_b200.model.utils import EngineStateMixin, load_pretrained_state
 
 
-class _UNetBase(nn.Module):
+class _UNetBase(EngineStateMixin, nn.Module):
     _dims = 2
 
     def _build(self, nf, base_width, top_width, depth):
@@ -64,7 +64,7 @@ class UDenoiseNet3D(_UNetBase):
         self._build(nf, base_width, top_width, depth=6)
 
 
-class DenoiseNet2(nn.Module):
+class DenoiseNet2(EngineStateMixin, nn.Module):
     """`fcnn` denoiser (reference denoising/models.py:52-66): three same-padded width x width convs, LeakyReLU(0.1)."""
     def __init__(self, base_filters, width=11):
         super().__init__()
@@ -79,7 +79,7 @@ class DenoiseNet2(nn.Module):
         return engine.fcnn_forward(self, x)
 
 
-class AffineDenoise(nn.Module):
+class AffineDenoise(EngineStateMixin, nn.Module):
     """`affine` denoiser (reference filters.py:40-48): one learned max_size x max_size filter."""
     def __init__(self, max_size=31):
         super().__init__()

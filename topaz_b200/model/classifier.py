@@ -3,8 +3,10 @@ by a 1x1 convolution to one logit per position.  ``self.classifier`` only stores
 state_dict keys; in the dense forward the 1x1 conv is fused into the epilogue of the last feature convolution."""
 import torch.nn as nn
 
+from topaz_b200.model.utils import EngineStateMixin
 
-class LinearClassifier(nn.Module):
+
+class LinearClassifier(EngineStateMixin, nn.Module):
     def __init__(self, features, dims=2, patch_size: int = None, padding: int = None, batch_size: int = 1):
         super().__init__()
         head = nn.Conv3d if dims == 3 else nn.Conv2d

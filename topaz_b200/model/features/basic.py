@@ -10,13 +10,13 @@ from typing import List, Sequence
 
 import torch.nn as nn
 
-from topaz_b200.model.utils import insize_from_outsize
+from topaz_b200.model.utils import EngineStateMixin, insize_from_outsize
 
 _CONV = {2: nn.Conv2d, 3: nn.Conv3d}
 _NORM = {2: nn.BatchNorm2d, 3: nn.BatchNorm3d}
 
 
-class BasicConv(nn.Module):
+class BasicConv(EngineStateMixin, nn.Module):
     def __init__(self, layers: List[int], units: int, unit_scaling: int = 1, dropout: float = 0, bn: bool = True,
                  pooling=None, activation=nn.PReLU, dims: int = 2):
         super().__init__()

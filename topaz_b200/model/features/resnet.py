@@ -10,7 +10,7 @@ from __future__ import division, print_function
 import torch
 import torch.nn as nn
 
-from topaz_b200.model.utils import insize_from_outsize
+from topaz_b200.model.utils import EngineStateMixin, insize_from_outsize
 
 
 class MaxPool(nn.Module):
@@ -121,7 +121,7 @@ class ResidA(nn.Module):
         self.dilation = 1
 
 
-class ResNet(nn.Module):
+class ResNet(EngineStateMixin, nn.Module):
     '''ResNet utility functions. Must be subclassed to define network architecture.'''
     def __init__(self, dims=2, **kwargs):
         super().__init__()

@@ -107,3 +107,12 @@ def predict_in_patches(model, X, patch_size, is_3d=False, use_cuda=False):
             dev = patch.cuda() if use_cuda else patch
             scores.append(model(dev).data[0, 0].cpu().numpy()[crop])
     return reconstruct_from_patches(scores, X.shape, patch_size, patch_padding=halo, is_3d=is_3d)
+
+
+class EngineStateMixin:
+    """The engine keeps per-module caches (packed fp16 weights and launch plans, the flat training buffers, the activation
+    tape) in the instance ``__dict__`` under ``_tpz_*`` names.  They are rebuilt on demand and must not travel with pickles
+    -- the reference saves WHOLE modules (``torch.save(classifier, path)``, training.py:600-601) -- or deep copies."""
+
+    def __getstate__(self):
+        return {k: v for k, v in self.__dict__.items() if not k.startswith('_tpz_')}

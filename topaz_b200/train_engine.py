@@ -94,7 +94,16 @@ class FlatParams:
 def flat_params(model) -> FlatParams:
     fp = model.__dict__.get('_tpz_flat')
     if fp is None or not fp.valid_for(model):
+        old = fp
         fp = FlatParams(model)
+        # Same Parameter objects in new storage: the module went through .cpu()/.cuda() (the reference does that around
+        # torch.save after EVERY epoch, training.py:600-603).  torch.optim.Adam keeps its state across that (it is keyed
+        # by the Parameter objects), so the moments and the step count move over to the new flat buffers.
+        if old is not None and len(old.params) == len(fp.params) and all(a is b for a, b in zip(old.params, fp.params)) \
+                and old.n == fp.n:
+            fp.flat_m.copy_(old.flat_m)
+            fp.flat_v.copy_(old.flat_v)
+            fp.step = old.step
         model.__dict__['_tpz_flat'] = fp
     return fp
 
