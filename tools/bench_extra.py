@@ -70,14 +70,17 @@ def main():
                                       n_gpus=world, ms_per_image=ms / args.steps, mpx_s=world * args.steps * 16.777216 / (ms / 1e3),
                                       tflops=world * args.steps * 29.458 / (ms / 1e3), launches_per_image=(ops.LAUNCH_COUNT - l0) / args.steps,
                                       finite=bool(np.isfinite(y).all()))))
-        elif wl in ('train', 'train_tf32'):
+        elif wl in ('train', 'train_tf32', 'train_bn'):
             from topaz_b200 import train_engine as _T
             _T.set_tf32(wl == 'train_tf32')
             from topaz_b200.methods import GE_binomial
             from topaz_b200.model.factory import get_feature_extractor
             from topaz_b200.model.classifier import LinearClassifier
-            m = LinearClassifier(get_feature_extractor('resnet8', units=32, bn=False))
-            m.load_state_dict({k: torch.from_numpy(v) for k, v in weights_of(gold('resnet8_u32_pretrained')).items()})
+            m = LinearClassifier(get_feature_extractor('resnet8', units=32, bn=wl == 'train_bn'))
+            if wl == 'train_bn':      # the default `topaz train` model (BatchNorm on, no packaged weights): seeded He init
+                m.load_state_dict({k: torch.from_numpy(v) for k, v in seeded_state({k: tuple(v.shape) for k, v in m.state_dict().items()}, 401).items()})
+            else:
+                m.load_state_dict({k: torch.from_numpy(v) for k, v in weights_of(gold('resnet8_u32_pretrained')).items()})
             m.cuda(); m.train()
             tr = GE_binomial(m, torch.optim.Adam(m.parameters(), lr=2e-4), nn.BCEWithLogitsLoss(), 0.035)
             B = 256; b = B // world
@@ -93,7 +96,7 @@ def main():
                 out = tr.step(Xs[s % 4], Yl)
             torch.cuda.synchronize(); ms = maxms((time.perf_counter() - t0) * 1e3)
             if rank == 0:
-                print(json.dumps(dict(workload='GE_binomial.step resnet8_u32, global minibatch 256 crops 71x71 (incl. per-step host readback)' + (', single-pass TF32 mode' if wl == 'train_tf32' else ', 3xTF32'),
+                print(json.dumps(dict(workload='GE_binomial.step resnet8_u32, global minibatch 256 crops 71x71 (incl. per-step host readback)' + (', single-pass TF32 mode' if wl == 'train_tf32' else ', 3xTF32') + (', BatchNorm (training mode)' if wl == 'train_bn' else ''),
                                       n_gpus=world, ms_per_step=ms / n, crops_s=n * B / (ms / 1e3), launches_per_step=(ops.LAUNCH_COUNT - l0) / n,
                                       last_out=out)))
             _T.set_tf32(False)
