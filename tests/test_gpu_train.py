@@ -21,6 +21,8 @@ def _nhwc(t):
 @pytest.mark.parametrize('N,H,Ci,Co,k,stride,dil,org', [
     (5, 71, 1, 32, 7, 2, 1, 0), (4, 33, 32, 32, 3, 1, 1, 0), (3, 31, 32, 64, 3, 2, 2, 0), (3, 27, 32, 64, 1, 2, 1, 3),
     (2, 9, 64, 128, 5, 1, 1, 0), (7, 1, 128, 1, 1, 1, 1, 0),
+    # Cin = 1 first layer (row-strip wgrad kernel): 64 channels, k=5 stride 1, and an input one pixel larger than the taps reach
+    (3, 71, 1, 64, 7, 2, 1, 0), (2, 40, 1, 32, 5, 1, 1, 0), (2, 72, 1, 32, 7, 2, 1, 0),
 ])
 def test_conv_f32_kernels(N, H, Ci, Co, k, stride, dil, org):
     from topaz_b200 import train_engine as T

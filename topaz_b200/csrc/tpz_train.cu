@@ -4,6 +4,7 @@
 // Replaces, for reference topaz/methods.py:98-165 (GE_binomial.step): the cuDNN fwd/bwd-data/bwd-filter
 // calls under loss.backward() (:146), ~25 tiny ATen kernels + the CPU scipy binom.logpmf + .item() syncs of
 // the loss (:103-136), and torch.optim.Adam.step()/zero_grad() (:159-160).
+#include <stdlib.h>
 #include "tpz_common.cuh"
 #include "../../include/topaz_b200.h"
 
@@ -278,6 +279,71 @@ __global__ void __launch_bounds__(256) first_wgrad_kernel(const float* __restric
   }
 }
 
+// Row-strip version of the same reduction.  A block walks over (image, output row) strips: it stages the k input rows
+// of the strip and the strip's dy[Wo][CO] in shared memory (coalesced), then every thread accumulates a 4-channel x
+// MAXT-tap register block over the strip's pixels: per pixel one 16-byte dy load + MAXT broadcast x loads feed
+// 4*MAXT FMAs (the pixel-per-iteration kernel above issues one global load per FMA and waits on each).  Partial sums
+// stay in registers across all strips of the block; one atomicAdd per (block, weight) at the end.
+template <int CO>
+__global__ void __launch_bounds__(256) first_wgrad_strip_kernel(const float* __restrict__ x, int N, int H, int W,
+                                                                const float* __restrict__ dy, int Ho, int Wo, int k,
+                                                                int stride, float* __restrict__ dw, int xw) {
+  constexpr int CQ = CO / 4;                      // threads along the channel quads
+  constexpr int TG = 256 / CQ;                    // tap groups
+  constexpr int MAXT = 64 / TG;                   // taps per thread (k*k <= 64)
+  extern __shared__ __align__(16) float s_fw[];   // dy strip [Wo][CO] | x strip [k][xw]
+  float* s_dy = s_fw;
+  float* s_x = s_fw + Wo * CO;
+  const int cq = threadIdx.x % CQ, tg = threadIdx.x / CQ;
+  const int taps = k * k;
+  float acc[MAXT][4];
+  int xoff[MAXT];
+#pragma unroll
+  for (int j = 0; j < MAXT; ++j) {
+    acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    const int t = tg + j * TG;
+    xoff[j] = (t < taps) ? (t / k) * xw + (t % k) : 0;      // invalid taps read x[0] of the strip and are dropped at the end
+  }
+  const int rows = N * Ho;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / Ho, oy = row - n * Ho;
+    __syncthreads();                                // previous strip fully consumed
+    {
+      const float4* src = reinterpret_cast<const float4*>(dy + (long long)row * Wo * CO);
+      float4* dst = reinterpret_cast<float4*>(s_dy);
+      for (int i = threadIdx.x; i < Wo * CQ; i += 256) dst[i] = src[i];
+      const float* xr = x + ((long long)n * H + (long long)oy * stride) * W;
+      for (int i = threadIdx.x; i < k * xw; i += 256) {
+        const int r = i / xw, c = i - r * xw;
+        s_x[i] = xr[(long long)r * W + c];
+      }
+    }
+    __syncthreads();
+    const float4* d4 = reinterpret_cast<const float4*>(s_dy) + cq;
+#pragma unroll 3
+    for (int ox = 0; ox < Wo; ++ox) {
+      const float4 d = d4[ox * CQ];
+      const float* xp = s_x + ox * stride;
+#pragma unroll
+      for (int j = 0; j < MAXT; ++j) {
+        const float xv = xp[xoff[j]];
+        acc[j][0] = fmaf(d.x, xv, acc[j][0]);
+        acc[j][1] = fmaf(d.y, xv, acc[j][1]);
+        acc[j][2] = fmaf(d.z, xv, acc[j][2]);
+        acc[j][3] = fmaf(d.w, xv, acc[j][3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < MAXT; ++j) {
+    const int t = tg + j * TG;
+    if (t < taps) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) atomicAdd(&dw[(cq * 4 + e) * taps + t], acc[j][e]);
+    }
+  }
+}
+
 // -------------------------------------------------------------------------------------------------
 // GE-binomial loss (methods.py:103-151), one block.  scores: all B_total logits of the (global) minibatch,
 // labels (fp64, as the reference's DataLoader collates them).  Writes dscore for [lo, hi) (the local shard)
@@ -515,6 +581,20 @@ extern "C" int tpz_first_wgrad_f32(const float* x, int N, int H, int W, const fl
   TPZ_CHECK(Co == 32 || Co == 64, "tpz_first_wgrad_f32: Co must be 32 or 64 (got %d)", Co);
   TPZ_CHECK(k * k <= (256 / Co) * 16, "tpz_first_wgrad_f32: kernel %dx%d too large", k, k);
   const long long M = (long long)N * Ho * Wo;
+  {
+    // row-strip kernel (default); TPZ_FIRST_WGRAD=v1 selects the pixel-per-iteration kernel (A/B switch)
+    static const bool strip = []() { const char* e = getenv("TPZ_FIRST_WGRAD"); return !(e && strcmp(e, "v1") == 0); }();
+    const int xw = (Wo - 1) * stride + k;
+    const size_t smem = ((size_t)Wo * Co + (size_t)k * xw) * sizeof(float);
+    if (strip && k * k <= 64 && xw <= W && (Ho - 1) * stride + k <= H && smem <= 48 * 1024) {
+      const long long rows = (long long)N * Ho;
+      const int grid = (int)(rows < 148 * 6 ? rows : 148 * 6);
+      if (Co == 32) first_wgrad_strip_kernel<32><<<grid, 256, smem, ST(stream)>>>(x, N, H, W, dy, Ho, Wo, k, stride, dw, xw);
+      else first_wgrad_strip_kernel<64><<<grid, 256, smem, ST(stream)>>>(x, N, H, W, dy, Ho, Wo, k, stride, dw, xw);
+      TPZ_CUDA(cudaGetLastError());
+      return 0;
+    }
+  }
   int ppb = (int)((M + 148 * 8 - 1) / (148 * 8));
   if (ppb < 64) ppb = 64;
   const int grid = tpz_div_up(M, ppb);
