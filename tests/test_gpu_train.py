@@ -2,6 +2,8 @@
 vs the oracle (autograd), and three full GE_binomial.step calls vs the reference golden (loss tuple, the
 gradient of step 1, the parameters after step 3).  fp32 kernels: tolerance 1e-3 per the north star, observed
 ~1e-5."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -416,3 +418,45 @@ def test_three_ge_binomial_batchnorm_steps_match_reference_golden():
     with torch.no_grad():
         yd = m(torch.from_numpy(g['x_dense']).cuda()).cpu().numpy()
     assert yd.shape == g['y_dense'].shape and max(rel_err(yd, g['y_dense'])) < 5e-3
+
+
+def test_epoch_boundary_round_trip_keeps_the_optimizer_state(tmp_path):
+    """What the reference's fit_epochs does between epochs (training.py:576-603): eval() + fill() + a dense forward +
+    unfill(), then classifier.cpu(), torch.save(classifier), classifier.cuda(), then train() again.  The parameters change
+    storage twice; the flat training buffers are rebuilt around them and must keep the Adam moments and the step count, so
+    the interrupted run reproduces the uninterrupted one (up to the fp32 atomics' summation order)."""
+    from topaz_b200.methods import GE_binomial
+
+    def run(interrupt):
+        g, sd, m = _bn_case()
+        m.cuda(); m.train()
+        optim = torch.optim.Adam(m.parameters(), lr=2e-4)
+        tr = GE_binomial(m, optim, nn.BCEWithLogitsLoss(), float(g['pi']), l2=1e-5, slack=1.0)
+        B = 32; Y = torch.from_numpy(g['Y'][:B]).cuda()
+        outs = []
+        for step in range(4):
+            X = torch.from_numpy(np.random.default_rng(4000 + step).standard_normal((B, 71, 71)).astype(np.float32)).cuda()
+            outs.append(tr.step(X, Y))
+            if interrupt and step == 1:
+                m.eval(); m.fill()
+                with torch.no_grad():
+                    yd = m(torch.from_numpy(g['x_dense']).cuda())
+                assert torch.isfinite(yd).all()
+                m.unfill()
+                m.cpu()
+                path = str(tmp_path / 'model_epoch1.sav')
+                torch.save(m, path)
+                assert os.path.getsize(path) < 2 * 1024 * 1024          # parameters + buffers only (1.3 MB), no engine caches
+                m.cuda(); m.train()
+        st = optim.state[next(iter(m.parameters()))]
+        return np.array(outs), {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}, float(st['step'])
+    o0, s0, n0 = run(False)
+    o1, s1, n1 = run(True)
+    assert n0 == n1 == 4.0
+    np.testing.assert_allclose(o1, o0, rtol=1e-3, atol=1e-6)
+    for k in s0:
+        if 'num_batches' in k:
+            assert int(s0[k]) == int(s1[k]) == 4
+        else:
+            mx, l2 = rel_err(s1[k], s0[k])          # a lost Adam state would show as ~1e-2 (bias correction restarts)
+            assert mx < 5e-3 and l2 < 1e-3, (k, mx, l2)
