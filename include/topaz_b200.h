@@ -189,6 +189,12 @@ int tpz_bn_fwd_f32(const float* x, long long P, int C, const double* sums, long 
 int tpz_bn_bwd_reduce_f32(const float* g, const float* x, long long P, int C, const float* save, double* sums, void* stream);
 int tpz_bn_bwd_f32(const float* g, const float* x, long long P, int C, const float* save, const double* sums, long long count,
                    const float* gamma, const double* local_sums, float* dgamma, float* dbeta, float* dx, void* stream);
+/* PReLU (one learnable slope) / LeakyReLU of the conv31/63/127 extractors in training (topaz/model/features/basic.py:16,51,66):
+ *  tpz_act_fwd_f32: y = v > 0 ? v : a*v, a = *slope_dev (nn.PReLU().weight, device) when non-NULL else slope_const
+ *  tpz_act_bwd_f32: g <- g*(v > 0 ? 1 : a) in place; *dslope += sum over v <= 0 of g*v (NULL: no slope gradient)          */
+int tpz_act_fwd_f32(const float* v, long long n, const float* slope_dev, float slope_const, float* y, void* stream);
+int tpz_act_bwd_f32(float* g, const float* v, long long n, const float* slope_dev, float slope_const, float* dslope,
+                    void* stream);
 int tpz_ge_binomial_loss_grad(const float* scores, const double* labels, int B, double pi, double slack, int lo, int hi,
                               float* dscores, float* out5, void* stream);
 /* PN / GE_KL / PU objectives (topaz/methods.py:25-74, 168-255, 258-322): mode 0/1/2; out6 = {loss, ge_penalty, precision,

@@ -193,10 +193,19 @@ def basicconv_width(layers: Sequence[dict]) -> int:
     return out
 
 
+def _prelu(y, a, act_masks):
+    """PReLU with one slope; with `act_masks` (iterator of boolean "v > 0" tensors) the branch is imposed, see _act."""
+    if act_masks is None:
+        return F.prelu(y, a)
+    return torch.where(next(act_masks), y, a.reshape(()) * y)
+
+
 def basicconv_features(sd: Dict, x: torch.Tensor, sizes: Sequence[int], units: int, unit_scaling: int,
-                       filled: bool, bn: bool = True, prefix: str = 'features.features.') -> torch.Tensor:
+                       filled: bool, bn: bool = True, prefix: str = 'features.features.', bn_train: bool = False,
+                       running: Optional[Dict] = None, act_masks=None) -> torch.Tensor:
     """BasicConv.forward + fill (basic.py:81-111): conv -> (BN) -> PReLU(1 slope) per layer;
-    filled => stride 1, dilation = cumulative stride, one pad of width//2 at the input."""
+    filled => stride 1, dilation = cumulative stride, one pad of width//2 at the input.
+    bn_train: BatchNorm in training mode (minibatch statistics; `running` receives the updated buffers)."""
     layers = basicconv_layers(sizes, units, unit_scaling)
     if x.dim() < 4:
         x = x.unsqueeze(1)
@@ -214,10 +223,10 @@ def basicconv_features(sd: Dict, x: torch.Tensor, sizes: Sequence[int], units: i
             y = _conv(x, w, b, stride=l['stride'])
         idx += 1
         if bn:
-            y = _bn_eval(y, sd, f'{prefix}{idx}')
+            y = _bn_train(y, sd, f'{prefix}{idx}', running=running) if bn_train else _bn_eval(y, sd, f'{prefix}{idx}')
             idx += 1
         a = _t(sd[f'{prefix}{idx}.weight'])
-        x = F.prelu(y, a)
+        x = _prelu(y, a, act_masks)
         idx += 1
     return x
 
@@ -442,7 +451,8 @@ def adam_update(p, g, m, v, step, lr=2e-4, b1=0.9, b2=0.999, eps=1e-8):
 
 
 def ge_binomial_steps(sd: Dict, Xs: Sequence[np.ndarray], Ys: Sequence[np.ndarray], arch: str, units: int,
-                      pi: float, slack: float = 1.0, l2: float = 0.0, lr: float = 2e-4, bn: bool = False):
+                      pi: float, slack: float = 1.0, l2: float = 0.0, lr: float = 2e-4, bn: bool = False,
+                      unit_scaling: int = 1):
     """Run len(Xs) GE_binomial.step calls (methods.py:98-165) with Adam on CPU; bn=True: a BatchNorm model in train()
     mode (minibatch statistics, running-buffer updates).
     Returns (list of 5-tuples, list of per-step grads dict, final state dict)."""
@@ -456,7 +466,8 @@ def ge_binomial_steps(sd: Dict, Xs: Sequence[np.ndarray], Ys: Sequence[np.ndarra
     for t, (X, Y) in enumerate(zip(Xs, Ys), 1):
         Yt = torch.from_numpy(np.asarray(Y, dtype=np.float64))
         running = {}
-        score = classifier_forward_grad({**params, **bufs}, torch.from_numpy(X), arch, units, bn=bn, running=running).view(-1)
+        score = classifier_forward_grad({**params, **bufs}, torch.from_numpy(X), arch, units, bn=bn, running=running,
+                                        unit_scaling=unit_scaling).view(-1)
         bufs.update(running)
         for k in bufs:
             if k.endswith('num_batches_tracked'):
@@ -482,12 +493,16 @@ def ge_binomial_steps(sd: Dict, Xs: Sequence[np.ndarray], Ys: Sequence[np.ndarra
 
 
 def classifier_forward_grad(params: Dict, x: torch.Tensor, arch: str, units: int, bn: bool = False,
-                            running: Optional[Dict] = None, relu_masks=None) -> torch.Tensor:
+                            running: Optional[Dict] = None, relu_masks=None, unit_scaling: int = 1) -> torch.Tensor:
     """Same as classifier_forward(filled=False) but keeps the autograd graph (params are leaf tensors).  bn=True: the
     model is in train() mode, i.e. BatchNorm uses minibatch statistics (`running` receives the updated buffers)."""
-    assert arch in ('resnet8', 'resnet16')
-    z = resnet_features(params, x.float(), arch, units, filled=False, bn=bn, bn_train=bn, running=running,
-                        relu_masks=iter(relu_masks) if relu_masks is not None else None)
+    masks = iter(relu_masks) if relu_masks is not None else None
+    if arch in ('resnet8', 'resnet16'):
+        z = resnet_features(params, x.float(), arch, units, filled=False, bn=bn, bn_train=bn, running=running, relu_masks=masks)
+    else:
+        sizes = {'conv31': [7, 5, 5], 'conv63': [7, 5, 5, 5], 'conv127': [7, 5, 5, 5, 5]}[arch]
+        z = basicconv_features(params, x.float(), sizes, units, unit_scaling, filled=False, bn=bn, bn_train=bn,
+                               running=running, act_masks=masks)
     return _conv(z, params['classifier.weight'], params['classifier.bias'])
 
 

@@ -346,6 +346,22 @@ def t_bn_bwd(g, x, save, sums, count, gamma, local_sums, dgamma, dbeta):
     g.copy_(dx)
 
 
+def _slope(act):
+    return act.weight.detach().reshape(()) if isinstance(act, torch.nn.PReLU) else torch.tensor(float(act.negative_slope))
+
+
+def t_act_fwd(v, act):
+    return torch.where(v > 0, v, _slope(act) * v)
+
+
+def t_act_bwd(g, v, act):
+    neg = ~(v > 0)
+    if isinstance(act, torch.nn.PReLU):
+        act.weight.grad.add_((g[neg].double() * v[neg].double()).sum().float())
+    g.copy_(torch.where(neg, _slope(act) * g, g))
+    return g
+
+
 def t_ge_loss_grad(scores, labels, pi, slack, lo, hi, dscore, out5):
     from oracle import topaz_oracle as O
     s = scores.detach().clone().requires_grad_(True)
@@ -383,7 +399,7 @@ def patched_training():
     from topaz_b200 import train_engine as T
     names = {'_conv_fwd': t_conv_fwd, '_conv_dgrad': t_conv_dgrad, '_conv_wgrad': t_conv_wgrad, '_relu_bwd': t_relu_bwd,
              '_crop_add': t_crop_add, '_bn_stats': t_bn_stats, '_bn_fwd': t_bn_fwd, '_bn_bwd_reduce': t_bn_bwd_reduce,
-             '_bn_bwd': t_bn_bwd, 'ge_loss_grad': t_ge_loss_grad, 'pu_objective_loss_grad': t_pu_objective, 'adam_step': t_adam_step,
+             '_bn_bwd': t_bn_bwd, '_act_fwd': t_act_fwd, '_act_bwd': t_act_bwd, 'ge_loss_grad': t_ge_loss_grad, 'pu_objective_loss_grad': t_pu_objective, 'adam_step': t_adam_step,
              'read_back': lambda d, h: d.tolist(), '_repack': lambda fp: None}
     saved = {n: getattr(T, n) for n in names}
     try:

@@ -460,3 +460,85 @@ def test_epoch_boundary_round_trip_keeps_the_optimizer_state(tmp_path):
         else:
             mx, l2 = rel_err(s1[k], s0[k])          # a lost Adam state would show as ~1e-2 (bias correction restarts)
             assert mx < 5e-3 and l2 < 1e-3, (k, mx, l2)
+
+
+# ------------------------------------------------------------------------------------------------
+# PReLU / LeakyReLU extractors in training (`topaz train -m conv31|conv63|conv127`, reference basic.py:16-78)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('n,learnable', [(1000, True), (64 * 13 * 13 * 16, True), (5 * 7 * 7 * 33, False)])
+def test_activation_kernels_match_torch(n, learnable):
+    from topaz_b200 import train_engine as T
+    rng = np.random.default_rng(n)
+    v = torch.from_numpy(rng.standard_normal(n).astype(np.float32)).cuda()
+    v[::17] = 0.0                                                      # exact zeros take the "v <= 0" branch, as in torch
+    g = torch.from_numpy(rng.standard_normal(n).astype(np.float32)).cuda()
+    act = (nn.PReLU(init=0.2) if learnable else nn.LeakyReLU(0.1)).cuda()
+    if learnable:
+        act.weight.grad = torch.zeros_like(act.weight)
+    vr = v.double().clone().requires_grad_(True)
+    if learnable:
+        ar = act.weight.detach().double().clone().requires_grad_(True)
+        yr = F.prelu(vr, ar)
+    else:
+        yr = F.leaky_relu(vr, 0.1)
+    yr.backward(g.double())
+    y = T._act_fwd(v, act)
+    assert torch.equal(y.cpu(), torch.where(v > 0, v, (act.weight.detach() if learnable else torch.tensor(0.1, device='cuda')) * v).cpu())
+    gi = g.clone()
+    T._act_bwd(gi, v, act)
+    assert max(rel_err(gi.cpu(), vr.grad.cpu())) < 1e-6
+    if learnable:
+        assert max(rel_err(act.weight.grad.cpu(), ar.grad.cpu())) < 1e-5
+
+
+@pytest.mark.parametrize('tag,bn', [('ge_binomial_conv31_bn', True), ('ge_binomial_conv31_nobn', False)])
+def test_prelu_extractor_training_matches_oracle_and_reference_golden(tag, bn):
+    """conv31 (16 units x2; conv -> [BN] -> PReLU with a learnable slope): every gradient of one GE-binomial step vs autograd
+    through the oracle with the GPU forward's activation branches imposed (same reasoning as the ReLU masks of the BatchNorm
+    ResNet test), then two full steps vs the reference's golden."""
+    from common import seeded_state
+    from common_shapes import classifier_shapes
+    from topaz_b200 import train_engine as T
+    from topaz_b200.methods import GE_binomial
+    from topaz_b200.model.factory import get_feature_extractor
+    from topaz_b200.model.classifier import LinearClassifier
+    g = gold(tag)
+    sd = seeded_state(classifier_shapes('conv31', 16, 2, bn), int(g['seed']))
+
+    def model():
+        m = LinearClassifier(get_feature_extractor('conv31', units=16, bn=bn, unit_scaling=2))
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        return m.cuda().train()
+    B, W, pi = int(g['B']), int(g['width']), float(g['pi'])
+    Y = torch.from_numpy(g['Y'])
+    X0 = torch.from_numpy(np.random.default_rng(4200).standard_normal((B, W, W)).astype(np.float32))
+    m = model()
+    T.flat_params(m)
+    score = m(X0.cuda()).view(-1)
+    masks = [(rec['v'] > 0).permute(0, 3, 1, 2).cpu() for rec in m.__dict__['_tpz_tape'] if rec['kind'] == 'conv']
+    assert len(masks) == 3
+    params = {k: torch.from_numpy(v).clone().requires_grad_('running' not in k and v.dtype == np.float32) for k, v in sd.items()}
+    score_ref = O.classifier_forward_grad(params, X0, 'conv31', 16, bn=bn, relu_masks=masks, unit_scaling=2).view(-1)
+    assert max(rel_err(score.detach().cpu().numpy(), score_ref.detach().numpy())) < 1e-4
+    _, _, loss = O.ge_binomial_loss(score_ref, Y, pi, 1.0)
+    loss.backward()
+    ds = torch.empty(B, device='cuda'); o5 = torch.empty(5, device='cuda')
+    T.ge_loss_grad(score.contiguous(), Y.cuda(), pi, 1.0, 0, B, ds, o5)
+    T.backward(m, ds)
+    errs = {k: max(rel_err(p.grad.cpu().numpy(), params[k].grad.numpy())) for k, p in m.named_parameters()}
+    print({k: f'{v:.1e}' for k, v in errs.items()})
+    assert max(errs.values()) < 1e-3, errs
+    # two full steps vs the real reference
+    m = model()
+    tr = GE_binomial(m, torch.optim.Adam(m.parameters(), lr=2e-4), nn.BCEWithLogitsLoss(), pi)
+    outs = []
+    for step in range(2):
+        X = torch.from_numpy(np.random.default_rng(4200 + step).standard_normal((B, W, W)).astype(np.float32)).cuda()
+        outs.append(tr.step(X, Y.cuda()))
+    np.testing.assert_allclose(np.array(outs), g['outs'], rtol=2e-3, atol=1e-6)
+    for k, v in m.state_dict().items():
+        if k.endswith('num_batches_tracked'):
+            assert int(v) == 2
+        else:
+            mx, l2 = rel_err(v.detach().cpu().numpy(), g['p2.' + k])
+            assert mx < 5e-3 and l2 < 1e-3, (k, mx, l2)

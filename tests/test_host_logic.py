@@ -217,6 +217,46 @@ def test_ge_binomial_batchnorm_step_wiring_sim():
     assert mx < 3e-3 and l2 < 3e-3, (mx, l2)
 
 
+@pytest.mark.parametrize('tag,bn', [('ge_binomial_conv31_bn', True), ('ge_binomial_conv31_nobn', False)])
+def test_ge_binomial_prelu_extractor_wiring_sim(tag, bn):
+    """`topaz train -m conv31` (conv -> [BN] -> PReLU with a learnable slope, basic.py:16-78): two GE_binomial steps through
+    the train engine with simulated kernels vs the reference golden -- slope gradients included."""
+    import torch.nn as nn
+    from topaz_b200.methods import GE_binomial
+    from topaz_b200 import train_engine as T
+    g = gold(tag)
+    m = _classifier('conv31', 16, 2, bn)
+    assert list(m.state_dict().keys()) == [str(k) for k in g['keys']]
+    _load(m, seeded_state({k: tuple(v.shape) for k, v in m.state_dict().items()}, int(g['seed']))); m.train()
+    assert m.width == int(g['width'])
+    optim = torch.optim.Adam(m.parameters(), lr=2e-4)
+    tr = GE_binomial(m, optim, nn.BCEWithLogitsLoss(), float(g['pi']))
+    B = int(g['B']); Y = torch.from_numpy(g['Y'])
+    outs = []
+    with sim_backend.patched_training():
+        for step in range(2):
+            X = torch.from_numpy(np.random.default_rng(4200 + step).standard_normal((B, m.width, m.width)).astype(np.float32))
+            if step == 0:
+                bufs = {k: v.clone() for k, v in m.state_dict().items() if 'running' in k or 'num_batches' in k}
+                fp = T.flat_params(m)
+                score = m(X).view(-1)
+                dscore = torch.empty(B); out5 = torch.empty(5)
+                T.ge_loss_grad(score, Y, tr.pi, tr.slack, 0, B, dscore, out5)
+                T.backward(m, dscore)
+                errs = {k: rel_err(p.grad.numpy(), g['g1.' + k]) for k, p in m.named_parameters()}
+                assert max(e[1] for e in errs.values()) < BN_GRAD_TOL_EARLY, errs
+                fp.flat_g.zero_()
+                m.load_state_dict(bufs, strict=False)
+            outs.append(tr.step(X, Y))
+    np.testing.assert_allclose(np.array(outs), g['outs'], rtol=1e-3, atol=1e-6)
+    for k, v in m.state_dict().items():
+        if k.endswith('num_batches_tracked'):
+            assert int(v) == 2
+            continue
+        mx, l2 = rel_err(v.detach().numpy(), g['p2.' + k])
+        assert mx < 5e-3 and l2 < 5e-4, (k, mx, l2)
+
+
 @pytest.mark.parametrize('tag', ['PN', 'PNpi', 'GE_KL', 'PU', 'PUclip'])
 def test_other_objectives_wiring_sim(tag):
     """PN / GE_KL / PU drop-ins (reference methods.py:25-74,168-322) through the shared step skeleton with simulated

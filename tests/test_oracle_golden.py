@@ -135,6 +135,24 @@ def test_ge_binomial_batchnorm_steps_match_reference():
         _close(params[k].grad.numpy(), grads[0][k], 1e-6)
 
 
+@pytest.mark.parametrize('tag,bn', [('ge_binomial_conv31_bn', True), ('ge_binomial_conv31_nobn', False)])
+def test_ge_binomial_prelu_extractor_steps_match_reference(tag, bn):
+    """conv31 (conv -> [BN] -> PReLU, learnable slope) in training: the oracle's two GE_binomial steps vs the reference's."""
+    from common_shapes import classifier_shapes
+    g = gold(tag)
+    sd = seeded_state(classifier_shapes('conv31', 16, 2, bn), int(g['seed']))
+    assert list(sd.keys()) == [str(k) for k in g['keys']]
+    B, W = int(g['B']), int(g['width'])
+    Xs = [np.random.default_rng(4200 + s).standard_normal((B, W, W)).astype(np.float32) for s in range(2)]
+    outs, grads, final = O.ge_binomial_steps(sd, Xs, [g['Y']] * 2, 'conv31', 16, float(g['pi']), bn=bn, unit_scaling=2)
+    np.testing.assert_allclose(np.array(outs), g['outs'], rtol=2e-4, atol=1e-6)
+    for k in grads[0]:
+        _close(grads[0][k], g['g1.' + k], 5e-4)
+    for k in final:
+        if not k.endswith('num_batches_tracked'):
+            _close(final[k], g['p2.' + k], 2e-4)
+
+
 def test_filters():
     g = gold('filters')
     _close(O.gaussian_denoise(g['img'], 1.5), g['gauss'])

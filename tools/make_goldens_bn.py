@@ -57,3 +57,34 @@ np.savez_compressed(path, seed=np.int64(SEED), B=np.int64(B), Y=Y, pi=np.float64
                     y_crops=y_crops, x_dense=xd, y_dense=y_dense,
                     **{'g1.' + k: v for k, v in grads1.items()}, **{'p3.' + k: v for k, v in final.items()})
 print('wrote', path, f'{os.path.getsize(path) / 1e6:.2f} MB', 'outs', outs)
+
+# ---- PReLU extractors in training (`topaz train -m conv31|conv63|conv127`): conv31, 16 units x2, with and without BatchNorm ----
+from topaz.model.factory import get_feature_extractor
+for tag, bn in (('ge_binomial_conv31_bn', True), ('ge_binomial_conv31_nobn', False)):
+    seed = 402 if bn else 403
+    m = LinearClassifier(get_feature_extractor('conv31', units=16, dropout=0.0, bn=bn, unit_scaling=2, pooling=None, dims=2))
+    sd = seeded_state({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    m.train()
+    optim = torch.optim.Adam(m.parameters(), lr=2e-4)
+    tr = GE_binomial(m, optim, nn.BCEWithLogitsLoss(), 0.035, l2=0.0, slack=1.0)
+    B = 32
+    Y = np.array([1.0] * 3 + [0.0] * (B - 3))
+    outs, grads1 = [], None
+    for step in range(2):
+        X = rng(4200 + step).standard_normal((B, m.width, m.width)).astype(np.float32)
+        orig = optim.step
+        if step == 0:
+            def grab(*a, **k):
+                global grads1
+                grads1 = {n: p.grad.detach().clone().numpy() for n, p in m.named_parameters()}
+                return orig(*a, **k)
+            optim.step = grab
+        outs.append(tr.step(torch.from_numpy(X), torch.from_numpy(Y)))
+        optim.step = orig
+    final = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+    path = os.path.join(GOLD, tag + '.npz')
+    np.savez_compressed(path, seed=np.int64(seed), B=np.int64(B), width=np.int64(m.width), Y=Y, pi=np.float64(0.035),
+                        outs=np.array(outs, dtype=np.float64), keys=np.array(list(sd.keys())),
+                        **{'g1.' + k: v for k, v in grads1.items()}, **{'p2.' + k: v for k, v in final.items()})
+    print('wrote', path, f'{os.path.getsize(path) / 1e6:.2f} MB', 'width', m.width, 'outs', outs)

@@ -171,6 +171,44 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const float* g, const float
   }
 }
 
+// PReLU with one learnable slope / LeakyReLU (the activation of the conv31/63/127 extractors: reference
+// topaz/model/features/basic.py:16,51,66):  y = v > 0 ? v : a*v.   a = *slope_dev when given (nn.PReLU().weight), else
+// slope_const (nn.LeakyReLU).
+__global__ void __launch_bounds__(256) act_fwd_kernel(const float* __restrict__ v, long long n, const float* __restrict__ slope_dev,
+                                                      float slope_const, float* __restrict__ y) {
+  const float a = slope_dev != nullptr ? slope_dev[0] : slope_const;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float x = v[i];
+    y[i] = x > 0.f ? x : a * x;
+  }
+}
+
+// g <- g * (v > 0 ? 1 : a);  dslope += sum over v <= 0 of g*v (torch's PReLU backward; one atomicAdd per block)
+__global__ void __launch_bounds__(256) act_bwd_kernel(float* g, const float* __restrict__ v, long long n,
+                                                      const float* __restrict__ slope_dev, float slope_const,
+                                                      float* __restrict__ dslope) {
+  const float a = slope_dev != nullptr ? slope_dev[0] : slope_const;
+  double part = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float x = v[i], gi = g[i];
+    if (!(x > 0.f)) {
+      part += (double)gi * (double)x;
+      g[i] = a * gi;
+    }
+  }
+  if (dslope != nullptr) {          // uniform branch (kernel argument)
+    __shared__ double sh[8];
+    for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < 8; ++w) tot += sh[w];
+      atomicAdd(dslope, (float)tot);
+    }
+  }
+}
+
 inline dim3 reduce_grid(long long P, int C) {
   return dim3(tpz_div_up(C, 32), (unsigned)(P < 4096 ? 1 : (P < 65536 ? 64 : 296)));
 }
@@ -224,6 +262,21 @@ extern "C" int tpz_bn_bwd_f32(const float* g, const float* x, long long P, int C
   TPZ_CHECK((dgamma == nullptr && dbeta == nullptr) || local_sums != nullptr, "tpz_bn_bwd_f32: local_sums required");
   bn_bwd_kernel<<<elementwise_grid(P * C), 256, 5 * C * sizeof(float), ST(stream)>>>(
       g, x, P, C, save, sums, 1.0 / (double)count, gamma, local_sums, dgamma, dbeta, dx);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tpz_act_fwd_f32(const float* v, long long n, const float* slope_dev, float slope_const, float* y, void* stream) {
+  TPZ_CHECK(n > 0, "tpz_act_fwd_f32: empty tensor");
+  act_fwd_kernel<<<elementwise_grid(n), 256, 0, ST(stream)>>>(v, n, slope_dev, slope_const, y);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tpz_act_bwd_f32(float* g, const float* v, long long n, const float* slope_dev, float slope_const,
+                               float* dslope, void* stream) {
+  TPZ_CHECK(n > 0, "tpz_act_bwd_f32: empty tensor");
+  act_bwd_kernel<<<elementwise_grid(n), 256, 0, ST(stream)>>>(g, v, n, slope_dev, slope_const, dslope);
   TPZ_CUDA(cudaGetLastError());
   return 0;
 }

@@ -87,21 +87,24 @@ def _cached(module: nn.Module, name: str, key, build):
 # ------------------------------------------------------------------------------------------------
 # classifier (ResNet8/16, conv31/63/127) dense forward
 # ------------------------------------------------------------------------------------------------
-def _feature_blocks(features) -> List[dict]:
-    """Describe the feature extractor's layers in their CURRENT geometry (after fill()/unfill())."""
+def _feature_blocks(features, slopes: bool = True) -> List[dict]:
+    """Describe the feature extractor's layers in their CURRENT geometry (after fill()/unfill()).  slopes=False (training)
+    leaves the activation slopes unread -- a PReLU slope lives on the device and reading it would synchronise every step;
+    the activation modules themselves are returned under 'act' / 'act0' / 'act1'."""
+    _slope = _slope_of if slopes else (lambda act: None)
     from .model.features import resnet as R, basic as B
     blocks = []
     if isinstance(features, R.ResNet):
         for mod in features.features.children():
             if isinstance(mod, R.BasicConv):
                 blocks.append(dict(kind='conv', w=mod.conv.weight, b=mod.conv.bias, bn=getattr(mod, 'bn', None),
-                                   dil=mod.conv.dilation[0], stride=mod.conv.stride[0], slope=_slope_of(mod.act)))
+                                   dil=mod.conv.dilation[0], stride=mod.conv.stride[0], slope=_slope(mod.act), act=mod.act))
             elif isinstance(mod, R.ResidA):
                 blocks.append(dict(kind='resid', w0=mod.conv0.weight, b0=mod.conv0.bias, bn0=getattr(mod, 'bn0', None),
                                    w1=mod.conv1.weight, b1=mod.conv1.bias, bn1=getattr(mod, 'bn1', None),
                                    proj=mod.proj.weight if hasattr(mod, 'proj') else None,
                                    d0=mod.conv0.dilation[0], d1=mod.conv1.dilation[0], stride=mod.conv1.stride[0],
-                                   slope0=_slope_of(mod.act0), slope1=_slope_of(mod.act1)))
+                                   slope0=_slope(mod.act0), slope1=_slope(mod.act1), act0=mod.act0, act1=mod.act1))
             elif isinstance(mod, nn.Dropout):
                 if features.training and mod.p > 0:
                     raise NotImplementedError('topaz_b200: dropout in training mode is not supported')
@@ -120,7 +123,7 @@ def _feature_blocks(features) -> List[dict]:
                 bn = mods[i]; i += 1
             act = mods[i]; i += 1
             blocks.append(dict(kind='conv', w=conv.weight, b=conv.bias, bn=bn, dil=conv.dilation[0],
-                               stride=conv.stride[0], slope=_slope_of(act)))
+                               stride=conv.stride[0], slope=_slope(act), act=act))
     else:
         raise NotImplementedError(f'topaz_b200: unsupported feature extractor {type(features).__name__}')
     return blocks

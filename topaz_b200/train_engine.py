@@ -296,16 +296,51 @@ def _osz(n, k, dil, stride):
     return (n - (k - 1) * dil - 1) // stride + 1
 
 
+def _is_relu(act) -> bool:
+    return isinstance(act, nn.ReLU)
+
+
 def _check_trainable(blocks):
+    """ReLU everywhere (the ResNets), or -- in plain conv blocks (conv31/63/127, basic.py:16) -- PReLU with ONE learnable
+    slope / LeakyReLU."""
     for b in blocks:
-        for k in ('slope', 'slope0', 'slope1'):
-            if k in b and b[k] != 0.0:
-                raise NotImplementedError('topaz_b200: only ReLU classifiers are supported by the B200 training path')
+        if b['kind'] == 'conv':
+            act = b['act']
+            if isinstance(act, nn.PReLU) and act.weight.numel() != 1:
+                raise NotImplementedError('topaz_b200: per-channel PReLU is not supported')
+            if not isinstance(act, (nn.ReLU, nn.PReLU, nn.LeakyReLU)):
+                raise NotImplementedError(f'topaz_b200: activation {type(act).__name__} is not supported by the B200 training path')
+        elif not (_is_relu(b['act0']) and _is_relu(b['act1'])):
+            raise NotImplementedError('topaz_b200: residual blocks train with ReLU only on the B200 path')
+
+
+def _slope_args(act):
+    """(device pointer of the learnable slope | None, constant slope) for tpz_act_*"""
+    if isinstance(act, nn.PReLU):
+        return act.weight, 0.0
+    return None, float(act.negative_slope)
+
+
+def _act_fwd(v, act):
+    """y = PReLU / LeakyReLU(v) (new tensor; v is kept for the backward)."""
+    y = torch.empty_like(v)
+    sp, sc = _slope_args(act)
+    ops._count(1)
+    check(_lib.lib().tpz_act_fwd_f32(_p(v), v.numel(), _p(sp), sc, _p(y), _s()))
+    return y
+
+
+def _act_bwd(g, v, act):
+    """in place: g <- d/d(v); accumulates the slope gradient of a PReLU."""
+    sp, sc = _slope_args(act)
+    ops._count(1)
+    check(_lib.lib().tpz_act_bwd_f32(_p(g), _p(v), v.numel(), _p(sp), sc, _p(sp.grad) if sp is not None else None, _s()))
+    return g
 
 
 def _forward(model_features, classifier, x: torch.Tensor, save: bool):
     """x: [B,H,W,1] fp32.  Returns (score [B] or features NHWC, tape)."""
-    blocks = _feature_blocks(model_features)
+    blocks = _feature_blocks(model_features, slopes=False)
     _check_trainable(blocks)
     tape = []
     cur = x
@@ -318,11 +353,16 @@ def _forward(model_features, classifier, x: torch.Tensor, save: bool):
             w, b, bn = blk['w'], blk['b'], blk.get('bn')
             k = w.shape[-1]
             Ho, Wo = _osz(H, k, blk['dil'], blk['stride']), _osz(W, k, blk['dil'], blk['stride'])
-            y = _conv_fwd(cur, w, b, blk['stride'], blk['dil'], 0, Ho, Wo, relu=bn is None)
-            rec = dict(kind='conv', x=cur, y=y, w=w, b=b, stride=blk['stride'], dil=blk['dil'])
+            relu = _is_relu(blk['act'])
+            y = _conv_fwd(cur, w, b, blk['stride'], blk['dil'], 0, Ho, Wo, relu=relu and bn is None)
+            rec = dict(kind='conv', x=cur, y=y, w=w, b=b, stride=blk['stride'], dil=blk['dil'], relu=relu)
             if bn is not None:
-                z, sv, cnt = _bn_forward(y, bn, True, ws)
+                z, sv, cnt = _bn_forward(y, bn, relu, ws)
                 rec.update(bn=bn, c=y, save=sv, count=cnt, y=z)
+                y = z
+            if not relu:                              # PReLU / LeakyReLU: separate pass, pre-activation kept for the backward
+                z = _act_fwd(y, blk['act'])
+                rec.update(act=blk['act'], v=y, y=z)
                 y = z
             tape.append(rec)
             cur = y
@@ -408,22 +448,28 @@ def backward(model, dscore: torch.Tensor):
     g = None
     ws = tape[0].get('bn_ws')
     with torch.no_grad():
-        for rec in reversed(tape):
+        for idx in range(len(tape) - 1, -1, -1):
+            rec = tape[idx]
+            # the producer of this op's input applies ReLU: its mask (input > 0) is fused into the data-gradient kernel;
+            # a PReLU / LeakyReLU producer gets the unmasked gradient and runs its own activation backward
+            in_relu = idx > 0 and tape[idx - 1].get('relu', True)
             if rec['kind'] == 'cls':
                 x = rec['x']
                 N, H, W, _ = x.shape
                 g = dscore.contiguous().view(N, H, W, 1)
                 _conv_wgrad(x, g, rec['w'].grad, rec['b'].grad, 1, 1, 0)
-                g = _conv_dgrad(g, rec['w'], 1, 1, 0, H, W, mask=x)          # masked by relu of the last feature conv
+                g = _conv_dgrad(g, rec['w'], 1, 1, 0, H, W, mask=x if in_relu else None)
             elif rec['kind'] == 'conv':
                 x = rec['x']
+                if rec.get('act') is not None:                                # g: d/d(activation output) -> d/d(pre-activation)
+                    g = _act_bwd(g, rec['v'], rec['act'])
                 if rec.get('bn') is not None:                                 # g: d/d(bn output) -> d/d(conv output)
                     g = _bn_backward(g, rec['c'], rec['save'], rec['count'], rec['bn'], ws)
                 _conv_wgrad(x, g, rec['w'].grad, rec['b'].grad if rec['b'] is not None else None, rec['stride'], rec['dil'], 0)
                 if x.shape[3] == 1 and rec is tape[0]:
                     g = None                                                  # network input: no data gradient needed
                 else:
-                    g = _conv_dgrad(g, rec['w'], rec['stride'], rec['dil'], 0, x.shape[1], x.shape[2], mask=x)
+                    g = _conv_dgrad(g, rec['w'], rec['stride'], rec['dil'], 0, x.shape[1], x.shape[2], mask=x if in_relu else None)
             else:
                 x, h = rec['x'], rec['h']
                 s, d0, d1, edge = rec['stride'], rec['d0'], rec['d1'], rec['edge']
