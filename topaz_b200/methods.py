@@ -24,7 +24,7 @@ def _dist():
 
 class _Objective:
     """Shared step skeleton: taped strided forward, fused loss kernel, backward, (DP) gradient all-reduce, fused Adam."""
-    n_out = 5
+    n_out = 6          # floats written by the loss kernel (GE_binomial: 5)
 
     def _setup(self, model, optim, criteria):
         if not isinstance(criteria, nn.BCEWithLogitsLoss):
@@ -32,10 +32,25 @@ class _Objective:
         if not isinstance(optim, torch.optim.Adam):
             raise NotImplementedError('topaz_b200: objectives expect torch.optim.Adam (training.py:355-356)')
         self.model, self.optim, self.criteria = model, optim, criteria
-        self._out = None
-        self._host = None
+        self._out = None           # device floats written by the loss kernel
+        self._host = None          # their pinned host mirror (the step's single read-back)
 
-    _hyper = None          # bound below (shared with GE_binomial)
+    def _hyper(self):
+        g = self.optim.param_groups[0]
+        if g.get('weight_decay', 0) != 0 or g.get('amsgrad', False):
+            raise NotImplementedError('topaz_b200: Adam weight_decay / amsgrad are not supported')
+        return float(g['lr']), float(g['betas'][0]), float(g['betas'][1]), float(g['eps'])
+
+    def _sync_optim_state(self, fp):
+        """Keep optim.state inspectable/saveable: exp_avg / exp_avg_sq alias the flat moment buffers."""
+        st = self.optim.state
+        for p, off in zip(fp.params, fp.offsets):
+            s = st[p]
+            if 'exp_avg' not in s or s['exp_avg'].data_ptr() != fp.flat_m[off:].data_ptr():
+                k = p.numel()
+                s['exp_avg'] = fp.flat_m[off:off + k].view_as(p)
+                s['exp_avg_sq'] = fp.flat_v[off:off + k].view_as(p)
+            s['step'] = torch.tensor(float(fp.step))
 
     def _loss(self, gs, gy, lo, hi, dscore, out):
         raise NotImplementedError
@@ -60,8 +75,8 @@ class _Objective:
         else:
             gs, gy, lo, hi = score.contiguous(), Yd.contiguous(), 0, b
         if self._out is None or self._out.device != score.device:
-            self._out = torch.empty(6, dtype=torch.float32, device=score.device)
-            self._host = torch.empty(6, dtype=torch.float32)
+            self._out = torch.empty(self.n_out, dtype=torch.float32, device=score.device)
+            self._host = torch.empty(self.n_out, dtype=torch.float32)
             if score.is_cuda:
                 self._host = self._host.pin_memory()
         dscore = torch.empty(b, dtype=torch.float32, device=score.device)
@@ -69,10 +84,10 @@ class _Objective:
         train_engine.backward(model, dscore)
         if dist is not None:
             dist.all_reduce(fp.flat_g, op=dist.ReduceOp.SUM)
-        lr, b1, b2, eps = GE_binomial._hyper(self)
+        lr, b1, b2, eps = self._hyper()
         train_engine.adam_step(fp, lr, b1, b2, eps, self.l2)
         model.__dict__['_tpz_epoch'] = model.features.__dict__['_tpz_epoch'] = fp.step
-        GE_binomial._sync_optim_state(self, fp)
+        self._sync_optim_state(fp)
         return [float(v) for v in train_engine.read_back(self._out, self._host)]
 
 
@@ -131,17 +146,14 @@ class PU(_Objective):
         return (o[0], o[2], o[3], o[4])
 
 
-class GE_binomial:
+class GE_binomial(_Objective):
+    """reference methods.py:77-165 (entropy_penalty = autoencoder = posterior_L1 = 0)."""
+    n_out = 5
+
     def __init__(self, model, optim, criteria, pi, l2=0, slack=1.0, entropy_penalty=0, autoencoder=0, posterior_L1=0):
         if entropy_penalty > 0 or autoencoder > 0 or posterior_L1 > 0:
             raise NotImplementedError('topaz_b200: entropy_penalty / autoencoder / posterior_L1 are outside the B200 hot path')
-        if not isinstance(criteria, nn.BCEWithLogitsLoss):
-            raise NotImplementedError('topaz_b200: GE_binomial expects criteria = nn.BCEWithLogitsLoss() (training.py:377)')
-        if not isinstance(optim, torch.optim.Adam):
-            raise NotImplementedError('topaz_b200: GE_binomial expects torch.optim.Adam (training.py:355-356)')
-        self.model = model
-        self.optim = optim
-        self.criteria = criteria
+        self._setup(model, optim, criteria)
         self.slack = slack
         self.pi = pi
         self.entropy_penalty = entropy_penalty
@@ -149,58 +161,13 @@ class GE_binomial:
         self.autoencoder = autoencoder
         self.posterior_L1 = posterior_L1
         self.header = ['loss', 'ge_penalty', 'precision', 'adjusted_precision', 'tpr', 'fpr']
-        self._out = None
-        self._host = None
 
-    def _hyper(self):
-        g = self.optim.param_groups[0]
-        if g.get('weight_decay', 0) != 0 or g.get('amsgrad', False):
-            raise NotImplementedError('topaz_b200: Adam weight_decay / amsgrad are not supported')
-        return float(g['lr']), float(g['betas'][0]), float(g['betas'][1]), float(g['eps'])
+    def _loss(self, gs, gy, lo, hi, dscore, out):
+        train_engine.ge_loss_grad(gs, gy, self.pi, self.slack, lo, hi, dscore, out)
 
     def step(self, X, Y):
-        ops.require_cuda(X, 'training minibatch')
-        model = self.model
-        if not model.training:
-            model.train()
-        fp = train_engine.flat_params(model)
-        score = model(X).view(-1)                                   # taped strided forward (methods.py:103)
-        Yd = Y.to(device=score.device, dtype=torch.float64).view(-1)
-        b = score.numel()
-        dist = _dist()
-        if dist is not None:
-            world, rank = dist.get_world_size(), dist.get_rank()
-            gs = torch.empty(world * b, dtype=torch.float32, device=score.device)
-            gy = torch.empty(world * b, dtype=torch.float64, device=score.device)
-            dist.all_gather_into_tensor(gs, score.contiguous())
-            dist.all_gather_into_tensor(gy, Yd.contiguous())
-            lo, hi = rank * b, (rank + 1) * b
-        else:
-            gs, gy, lo, hi = score.contiguous(), Yd.contiguous(), 0, b
-        if self._out is None or self._out.device != score.device:
-            self._out = torch.empty(5, dtype=torch.float32, device=score.device)
-            self._host = torch.empty(5, dtype=torch.float32)
-            if score.is_cuda:
-                self._host = self._host.pin_memory()
-        dscore = torch.empty(b, dtype=torch.float32, device=score.device)
-        train_engine.ge_loss_grad(gs, gy, self.pi, self.slack, lo, hi, dscore, self._out)
-        train_engine.backward(model, dscore)                        # loss.backward() (methods.py:146)
-        if dist is not None:
-            dist.all_reduce(fp.flat_g, op=dist.ReduceOp.SUM)        # one flat-buffer all-reduce over NVLink
-        lr, b1, b2, eps = self._hyper()
-        train_engine.adam_step(fp, lr, b1, b2, eps, self.l2)        # optim.step(); optim.zero_grad() (:159-160)
-        model.__dict__['_tpz_epoch'] = model.features.__dict__['_tpz_epoch'] = fp.step   # invalidates cached dense plans
-        self._sync_optim_state(fp)
-        cls_loss, ge, precision, tpr, fpr = (float(v) for v in train_engine.read_back(self._out, self._host))
+        """One training step (methods.py:98-165): taped strided forward (:103), fused loss + closed-form score gradient
+        (:105-136), backward (:146), flat-gradient all-reduce under data parallelism, fused Adam + gradient zeroing
+        (:153-160).  Returns (classifier_loss, ge_penalty, precision, tpr, fpr) as Python floats."""
+        cls_loss, ge, precision, tpr, fpr = self._run(X, Y)[:5]
         return cls_loss, ge, precision, tpr, fpr
-
-    def _sync_optim_state(self, fp):
-        """Keep optim.state inspectable/saveable: exp_avg / exp_avg_sq alias the flat moment buffers."""
-        st = self.optim.state
-        for p, off in zip(fp.params, fp.offsets):
-            s = st[p]
-            if 'exp_avg' not in s or s['exp_avg'].data_ptr() != fp.flat_m[off:].data_ptr():
-                k = p.numel()
-                s['exp_avg'] = fp.flat_m[off:off + k].view_as(p)
-                s['exp_avg_sq'] = fp.flat_v[off:off + k].view_as(p)
-            s['step'] = torch.tensor(float(fp.step))
