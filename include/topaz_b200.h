@@ -195,6 +195,12 @@ int tpz_bn_bwd_f32(const float* g, const float* x, long long P, int C, const flo
 int tpz_act_fwd_f32(const float* v, long long n, const float* slope_dev, float slope_const, float* y, void* stream);
 int tpz_act_bwd_f32(float* g, const float* v, long long n, const float* slope_dev, float slope_const, float* dslope,
                     void* stream);
+/* nn.Dropout in training (topaz/model/features/resnet.py:296-303, basic.py:58-59,71-72; `topaz train --dropout`):
+ *  tpz_dropout_fwd_f32: mask[i] = Philox(seed, subsequence i/4, offset)[i%4] > p;  y = mask ? x/(1-p) : 0
+ *  tpz_dropout_bwd_f32: g <- mask ? g/(1-p) : 0                                                                            */
+int tpz_dropout_fwd_f32(const float* x, long long n, float p, unsigned long long seed, unsigned long long offset, float* y,
+                        unsigned char* mask, void* stream);
+int tpz_dropout_bwd_f32(float* g, const unsigned char* mask, long long n, float p, void* stream);
 int tpz_ge_binomial_loss_grad(const float* scores, const double* labels, int B, double pi, double slack, int lo, int hi,
                               float* dscores, float* out5, void* stream);
 /* PN / GE_KL / PU objectives (topaz/methods.py:25-74, 168-255, 258-322): mode 0/1/2; out6 = {loss, ge_penalty, precision,

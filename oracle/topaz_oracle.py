@@ -117,9 +117,20 @@ def _act(y, relu_masks):
     return y * next(relu_masks).to(y.dtype)
 
 
+def _dropout(x, p, dropout_masks):
+    """nn.Dropout(p) in training with the keep-mask imposed (an iterator of 0/1 tensors shaped like x): x * mask / (1-p).
+    torch's own mask stream cannot be reproduced outside torch, so the masks always come from the implementation under test;
+    the arithmetic is pinned against F.dropout in tests/test_oracle_golden.py."""
+    return x * (next(dropout_masks).to(x.dtype) / (1.0 - p))        # ATen: input * (bernoulli(1-p) / (1-p))
+
+
+RESNET_DROPOUT_AFTER = {'resnet8': (0, 2, 4), 'resnet16': (1, 5, 8)}     # spec indices followed by nn.Dropout (resnet.py:294-336)
+
+
 def resnet_features(sd: Dict, x: torch.Tensor, kind: str, units: int, filled: bool,
                     bn: bool = False, prefix: str = 'features.features.', bn_train: bool = False,
-                    running: Optional[Dict] = None, relu_masks=None) -> torch.Tensor:
+                    running: Optional[Dict] = None, relu_masks=None, dropout: float = 0.0,
+                    dropout_masks=None) -> torch.Tensor:
     """ResNet.forward (resnet.py:243-251) with fill() semantics (resnet.py:87-92,153-164,227-232).
 
     filled=True: input padded by width//2 once, every stride -> 1, dilations multiplied by the
@@ -134,8 +145,11 @@ def resnet_features(sd: Dict, x: torch.Tensor, kind: str, units: int, filled: bo
         p = resnet_width(spec) // 2
         x = F.pad(x, (p, p, p, p))
     cum = 1
+    drop_after = RESNET_DROPOUT_AFTER[kind] if dropout > 0 else ()
+    mod_idx = 0                      # index in the nn.Sequential: Dropout modules occupy slots too (state_dict keys shift)
     for i, blk in enumerate(spec):
-        pre = f'{prefix}{i}.'
+        pre = f'{prefix}{mod_idx}.'
+        mod_idx += 2 if i in drop_after else 1
         if blk['type'] == 'conv':
             w = _t(sd[pre + 'conv.weight'])
             b = _t(sd[pre + 'conv.bias']) if (pre + 'conv.bias') in sd else None
@@ -147,6 +161,8 @@ def resnet_features(sd: Dict, x: torch.Tensor, kind: str, units: int, filled: bo
             if bn:
                 y = _bn_train(y, sd, pre + 'bn', running=running) if bn_train else _bn_eval(y, sd, pre + 'bn')
             x = _act(y, relu_masks)
+            if i in drop_after and dropout_masks is not None:
+                x = _dropout(x, dropout, dropout_masks)
         else:
             w0 = _t(sd[pre + 'conv0.weight'])
             b0 = _t(sd[pre + 'conv0.bias']) if (pre + 'conv0.bias') in sd else None
@@ -171,6 +187,8 @@ def resnet_features(sd: Dict, x: torch.Tensor, kind: str, units: int, filled: bo
             if bn:
                 y = _bn_train(y, sd, pre + 'bn1', running=running) if bn_train else _bn_eval(y, sd, pre + 'bn1')
             x = _act(y, relu_masks)
+            if i in drop_after and dropout_masks is not None:
+                x = _dropout(x, dropout, dropout_masks)
             if filled:
                 cum *= blk['stride']
     return x
@@ -202,7 +220,8 @@ def _prelu(y, a, act_masks):
 
 def basicconv_features(sd: Dict, x: torch.Tensor, sizes: Sequence[int], units: int, unit_scaling: int,
                        filled: bool, bn: bool = True, prefix: str = 'features.features.', bn_train: bool = False,
-                       running: Optional[Dict] = None, act_masks=None) -> torch.Tensor:
+                       running: Optional[Dict] = None, act_masks=None, dropout: float = 0.0,
+                       dropout_masks=None) -> torch.Tensor:
     """BasicConv.forward + fill (basic.py:81-111): conv -> (BN) -> PReLU(1 slope) per layer;
     filled => stride 1, dilation = cumulative stride, one pad of width//2 at the input.
     bn_train: BatchNorm in training mode (minibatch statistics; `running` receives the updated buffers)."""
@@ -228,6 +247,10 @@ def basicconv_features(sd: Dict, x: torch.Tensor, sizes: Sequence[int], units: i
         a = _t(sd[f'{prefix}{idx}.weight'])
         x = _prelu(y, a, act_masks)
         idx += 1
+        if dropout > 0:              # nn.Dropout follows every activation (basic.py:58-59,71-72) and occupies a module slot
+            idx += 1
+            if dropout_masks is not None:
+                x = _dropout(x, dropout, dropout_masks)
     return x
 
 
@@ -493,16 +516,19 @@ def ge_binomial_steps(sd: Dict, Xs: Sequence[np.ndarray], Ys: Sequence[np.ndarra
 
 
 def classifier_forward_grad(params: Dict, x: torch.Tensor, arch: str, units: int, bn: bool = False,
-                            running: Optional[Dict] = None, relu_masks=None, unit_scaling: int = 1) -> torch.Tensor:
+                            running: Optional[Dict] = None, relu_masks=None, unit_scaling: int = 1,
+                            dropout: float = 0.0, dropout_masks=None) -> torch.Tensor:
     """Same as classifier_forward(filled=False) but keeps the autograd graph (params are leaf tensors).  bn=True: the
     model is in train() mode, i.e. BatchNorm uses minibatch statistics (`running` receives the updated buffers)."""
     masks = iter(relu_masks) if relu_masks is not None else None
+    dmasks = iter(dropout_masks) if dropout_masks is not None else None
     if arch in ('resnet8', 'resnet16'):
-        z = resnet_features(params, x.float(), arch, units, filled=False, bn=bn, bn_train=bn, running=running, relu_masks=masks)
+        z = resnet_features(params, x.float(), arch, units, filled=False, bn=bn, bn_train=bn, running=running, relu_masks=masks,
+                            dropout=dropout, dropout_masks=dmasks)
     else:
         sizes = {'conv31': [7, 5, 5], 'conv63': [7, 5, 5, 5], 'conv127': [7, 5, 5, 5, 5]}[arch]
         z = basicconv_features(params, x.float(), sizes, units, unit_scaling, filled=False, bn=bn, bn_train=bn,
-                               running=running, act_masks=masks)
+                               running=running, act_masks=masks, dropout=dropout, dropout_masks=dmasks)
     return _conv(z, params['classifier.weight'], params['classifier.bias'])
 
 

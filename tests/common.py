@@ -50,3 +50,14 @@ def rel_err(y, ref):
     y = np.asarray(y, dtype=np.float64); ref = np.asarray(ref, dtype=np.float64)
     d = np.abs(y - ref)
     return float(d.max() / max(np.abs(ref).max(), 1e-30)), float(np.linalg.norm(y - ref) / max(np.linalg.norm(ref), 1e-30))
+
+
+def dropout_masks_of(g):
+    """keep-masks of the reference's nn.Dropout layers stored bit-packed in a golden (NCHW, bool)."""
+    out = []
+    i = 0
+    while f'mask{i}' in g.files:
+        shp = tuple(int(v) for v in g[f'mask{i}.shape'])
+        out.append(np.unpackbits(g[f'mask{i}'])[:int(np.prod(shp))].reshape(shp).astype(bool))
+        i += 1
+    return out

@@ -362,6 +362,19 @@ def t_act_bwd(g, v, act):
     return g
 
 
+DROPOUT_REPLAY = []          # tests may queue keep-masks (NHWC, bool) recorded from the reference's nn.Dropout layers
+
+
+def t_dropout_fwd(x, p):
+    keep = DROPOUT_REPLAY.pop(0) if DROPOUT_REPLAY else (torch.rand_like(x) > p)
+    return x * (keep.to(x.dtype) / (1.0 - p)), keep.to(torch.uint8)
+
+
+def t_dropout_bwd(g, mask, p):
+    g.copy_(g * (mask.to(g.dtype) / (1.0 - p)))
+    return g
+
+
 def t_ge_loss_grad(scores, labels, pi, slack, lo, hi, dscore, out5):
     from oracle import topaz_oracle as O
     s = scores.detach().clone().requires_grad_(True)
@@ -399,7 +412,8 @@ def patched_training():
     from topaz_b200 import train_engine as T
     names = {'_conv_fwd': t_conv_fwd, '_conv_dgrad': t_conv_dgrad, '_conv_wgrad': t_conv_wgrad, '_relu_bwd': t_relu_bwd,
              '_crop_add': t_crop_add, '_bn_stats': t_bn_stats, '_bn_fwd': t_bn_fwd, '_bn_bwd_reduce': t_bn_bwd_reduce,
-             '_bn_bwd': t_bn_bwd, '_act_fwd': t_act_fwd, '_act_bwd': t_act_bwd, 'ge_loss_grad': t_ge_loss_grad, 'pu_objective_loss_grad': t_pu_objective, 'adam_step': t_adam_step,
+             '_bn_bwd': t_bn_bwd, '_act_fwd': t_act_fwd, '_act_bwd': t_act_bwd, '_dropout_fwd': t_dropout_fwd, '_dropout_bwd': t_dropout_bwd,
+             'ge_loss_grad': t_ge_loss_grad, 'pu_objective_loss_grad': t_pu_objective, 'adam_step': t_adam_step,
              'read_back': lambda d, h: d.tolist(), '_repack': lambda fp: None}
     saved = {n: getattr(T, n) for n in names}
     try:

@@ -542,3 +542,79 @@ def test_prelu_extractor_training_matches_oracle_and_reference_golden(tag, bn):
         else:
             mx, l2 = rel_err(v.detach().cpu().numpy(), g['p2.' + k])
             assert mx < 5e-3 and l2 < 1e-3, (k, mx, l2)
+
+
+# ------------------------------------------------------------------------------------------------
+# nn.Dropout in training (`topaz train --dropout p`, reference resnet.py:296-303)
+# ------------------------------------------------------------------------------------------------
+def test_dropout_kernels():
+    from topaz_b200 import train_engine as T
+    n, p = 1 << 20, 0.25
+    x = torch.randn(n + 3, device='cuda')                                  # n % 4 != 0: ragged last Philox group
+    torch.manual_seed(77)
+    T._DROPOUT['calls'] = 10
+    y, keep = T._dropout_fwd(x, p)
+    frac = keep.float().mean().item()
+    assert abs(frac - (1 - p)) < 4 * np.sqrt(p * (1 - p) / n), frac       # Bernoulli(1-p) within 4 sigma
+    assert torch.equal(y, x * (keep.float() / (1.0 - p)))                 # ATen's arithmetic: input * (mask / (1-p))
+    T._DROPOUT['calls'] = 10
+    y2, keep2 = T._dropout_fwd(x, p)
+    assert torch.equal(keep, keep2) and torch.equal(y, y2)                # same (seed, offset) -> same mask
+    y3, keep3 = T._dropout_fwd(x, p)                                      # next call: new stream position
+    agree = (keep3 == keep).float().mean().item()
+    assert abs(agree - (p * p + (1 - p) * (1 - p))) < 0.01                # independent of the previous mask
+    torch.manual_seed(78)
+    T._DROPOUT['calls'] = 10
+    assert not torch.equal(T._dropout_fwd(x, p)[1], keep)                 # another seed -> another mask
+    g = torch.randn(n + 3, device='cuda')
+    ref = g * (keep.float() / (1.0 - p))
+    T._dropout_bwd(g, keep, p)
+    assert torch.equal(g, ref)
+
+
+def test_dropout_training_gradients_match_oracle_with_imposed_masks():
+    """ResNet8 (16 units, BatchNorm, dropout 0.25) in train() mode: the GPU draws its own Philox keep-masks; with those masks
+    (and the ReLU masks, see the BatchNorm test) imposed on the oracle -- whose dropout handling is pinned to the real
+    reference in tests/test_oracle_golden.py -- logits, loss and every gradient agree."""
+    from common import seeded_state
+    from topaz_b200 import train_engine as T
+    from topaz_b200.model.factory import get_feature_extractor
+    from topaz_b200.model.classifier import LinearClassifier
+    g = gold('ge_binomial_u16_dropout')
+    p, B, pi = float(g['p']), int(g['B']), float(g['pi'])
+    m = LinearClassifier(get_feature_extractor('resnet8', units=16, bn=True, dropout=p))
+    sd = seeded_state({k: tuple(v.shape) for k, v in m.state_dict().items()}, int(g['seed']))
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    m.cuda(); m.train()
+    X = torch.from_numpy(np.random.default_rng(4300).standard_normal((B, 71, 71)).astype(np.float32))
+    Y = torch.from_numpy(g['Y'])
+    T.flat_params(m)
+    score = m(X.cuda()).view(-1)
+    relu_masks, drop_masks = [], []
+    for rec in m.__dict__['_tpz_tape']:
+        if rec['kind'] == 'conv':
+            relu_masks.append((rec['y'] > 0).permute(0, 3, 1, 2).cpu())
+        elif rec['kind'] == 'resid':
+            relu_masks.append((rec['h'] > 0).permute(0, 3, 1, 2).cpu())
+            relu_masks.append((rec['y'] > 0).permute(0, 3, 1, 2).cpu())
+        elif rec['kind'] == 'dropout':
+            drop_masks.append(rec['mask'].bool().permute(0, 3, 1, 2).cpu())
+    assert len(relu_masks) == 8 and len(drop_masks) == 3
+    assert all(abs(dm.float().mean().item() - (1 - p)) < 0.02 for dm in drop_masks[:2])
+    params = {k: torch.from_numpy(v).clone().requires_grad_('running' not in k and v.dtype == np.float32) for k, v in sd.items()}
+    score_ref = O.classifier_forward_grad(params, X, 'resnet8', 16, bn=True, relu_masks=relu_masks, dropout=p,
+                                          dropout_masks=drop_masks).view(-1)
+    assert max(rel_err(score.detach().cpu().numpy(), score_ref.detach().numpy())) < 1e-4
+    _, _, loss = O.ge_binomial_loss(score_ref, Y, pi, 1.0)
+    loss.backward()
+    ds = torch.empty(B, device='cuda'); o5 = torch.empty(5, device='cuda')
+    T.ge_loss_grad(score.contiguous(), Y.cuda(), pi, 1.0, 0, B, ds, o5)
+    T.backward(m, ds)
+    errs = {k: max(rel_err(p_.grad.cpu().numpy(), params[k].grad.numpy())) for k, p_ in m.named_parameters()}
+    print({k: f'{v:.1e}' for k, v in errs.items()})
+    assert max(errs.values()) < 1e-3, errs
+    # eval(): identity
+    m.eval()
+    with torch.no_grad():
+        a = m(X[:4].cuda()); b = m(X[:4].cuda())
+    assert torch.equal(a, b)

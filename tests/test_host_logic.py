@@ -257,6 +257,43 @@ def test_ge_binomial_prelu_extractor_wiring_sim(tag, bn):
         assert mx < 5e-3 and l2 < 5e-4, (k, mx, l2)
 
 
+def test_ge_binomial_dropout_wiring_sim():
+    """`topaz train --dropout 0.25` (ResNet8, 16 units, BatchNorm): the train engine with simulated kernels, fed the keep-masks
+    the reference's nn.Dropout layers drew, reproduces the reference's loss tuple and every gradient (dropout placement,
+    1/(1-p) scaling, and the fused "input > 0" masks that now also cover dropped elements)."""
+    import torch.nn as nn
+    from common import dropout_masks_of
+    from topaz_b200 import train_engine as T
+    g = gold('ge_binomial_u16_dropout')
+    p = float(g['p'])
+    from topaz_b200.model.factory import get_feature_extractor
+    from topaz_b200.model.classifier import LinearClassifier
+    m = LinearClassifier(get_feature_extractor('resnet8', units=16, bn=True, dropout=p))
+    assert list(m.state_dict().keys()) == [str(k) for k in g['keys']]
+    _load(m, seeded_state({k: tuple(v.shape) for k, v in m.state_dict().items()}, int(g['seed']))); m.train()
+    B = int(g['B']); Y = torch.from_numpy(g['Y'])
+    X = torch.from_numpy(np.random.default_rng(4300).standard_normal((B, 71, 71)).astype(np.float32))
+    sim_backend.DROPOUT_REPLAY[:] = [torch.from_numpy(mk).permute(0, 2, 3, 1).contiguous() for mk in dropout_masks_of(g)]
+    try:
+        with sim_backend.patched_training():
+            T.flat_params(m)
+            score = m(X).view(-1)
+            assert not sim_backend.DROPOUT_REPLAY            # all three masks consumed, in order
+            dscore = torch.empty(B); out5 = torch.empty(5)
+            T.ge_loss_grad(score, Y, float(g['pi']), 1.0, 0, B, dscore, out5)
+            T.backward(m, dscore)
+    finally:
+        sim_backend.DROPOUT_REPLAY[:] = []
+    np.testing.assert_allclose(out5.numpy(), g['out'], rtol=5e-4, atol=1e-6)
+    errs = {k: rel_err(p_.grad.numpy(), g['g1.' + k]) for k, p_ in m.named_parameters()}
+    assert max(e[1] for e in errs.values()) < BN_GRAD_TOL_EARLY, errs
+    # eval(): dropout is the identity and the dense path builds its plan
+    m.eval(); m.fill()
+    with sim_backend.patched(), torch.no_grad():
+        y = m(torch.zeros(1, 1, 80, 80))
+    assert y.shape == (1, 1, 80, 80)
+
+
 @pytest.mark.parametrize('tag', ['PN', 'PNpi', 'GE_KL', 'PU', 'PUclip'])
 def test_other_objectives_wiring_sim(tag):
     """PN / GE_KL / PU drop-ins (reference methods.py:25-74,168-322) through the shared step skeleton with simulated

@@ -153,6 +153,50 @@ def test_ge_binomial_prelu_extractor_steps_match_reference(tag, bn):
             _close(final[k], g['p2.' + k], 2e-4)
 
 
+def test_dropout_training_step_matches_reference_with_its_masks():
+    """`topaz train --dropout 0.25`: ResNet8 (16 units, BatchNorm) in train() mode.  With the keep-masks that the reference's
+    three nn.Dropout layers drew (recorded by hooks in tools/make_goldens_bn.py) imposed, the oracle reproduces the
+    reference's loss tuple and every gradient -- this pins where the Dropout layers sit (after blocks 0, 2, 4), how they shift
+    the state_dict keys, and the 1/(1-p) scaling.  The arithmetic itself is also checked against F.dropout."""
+    import torch
+    import torch.nn.functional as F
+    from common import dropout_masks_of
+    g = gold('ge_binomial_u16_dropout')
+    p = float(g['p'])
+    keys = [str(k) for k in g['keys']]
+    assert 'features.features.2.conv0.weight' in keys and 'features.features.1.conv0.weight' not in keys   # slot 1 = Dropout
+    shapes = {k: tuple(g['g1.' + k].shape) for k in keys if 'g1.' + k in g.files}
+    # buffers have no gradient entry: rebuild the full shape table from a BN ResNet8 with shifted indices
+    from common_shapes import classifier_shapes
+    base = classifier_shapes('resnet8', 16, 1, True)
+    remap = {0: 0, 1: 2, 2: 3, 3: 5, 4: 6}
+    full = {}
+    for k, shp in base.items():
+        if k.startswith('features.features.'):
+            parts = k.split('.')
+            parts[2] = str(remap[int(parts[2])])
+            k = '.'.join(parts)
+        full[k] = shp
+    assert list(full.keys()) == keys
+    sd = seeded_state(full, int(g['seed']))
+    B = int(g['B'])
+    X = np.random.default_rng(4300).standard_normal((B, 71, 71)).astype(np.float32)
+    params = {k: torch.from_numpy(v).clone().requires_grad_('running' not in k and v.dtype == np.float32) for k, v in sd.items()}
+    masks = [torch.from_numpy(m) for m in dropout_masks_of(g)]
+    score = O.classifier_forward_grad(params, torch.from_numpy(X), 'resnet8', 16, bn=True, dropout=p, dropout_masks=masks).view(-1)
+    Y = torch.from_numpy(g['Y'])
+    cls, ge, loss = O.ge_binomial_loss(score, Y, float(g['pi']), 1.0)
+    loss.backward()
+    prec, tpr, fpr = O.ge_binomial_metrics(score.detach(), Y)
+    np.testing.assert_allclose([cls.item(), ge.item(), prec, tpr, fpr], g['out'], rtol=2e-4, atol=1e-6)
+    for k in shapes:
+        _close(params[k].grad.numpy(), g['g1.' + k], 5e-4)
+    x = torch.randn(4, 3, 5, 5)
+    torch.manual_seed(3)
+    ref = F.dropout(x, p, training=True)
+    assert torch.equal(O._dropout(x, p, iter([ref != 0])), ref)
+
+
 def test_filters():
     g = gold('filters')
     _close(O.gaussian_denoise(g['img'], 1.5), g['gauss'])

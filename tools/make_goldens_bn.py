@@ -88,3 +88,38 @@ for tag, bn in (('ge_binomial_conv31_bn', True), ('ge_binomial_conv31_nobn', Fal
                         outs=np.array(outs, dtype=np.float64), keys=np.array(list(sd.keys())),
                         **{'g1.' + k: v for k, v in grads1.items()}, **{'p2.' + k: v for k, v in final.items()})
     print('wrote', path, f'{os.path.getsize(path) / 1e6:.2f} MB', 'width', m.width, 'outs', outs)
+
+# ---- nn.Dropout in training (`topaz train --dropout`): ResNet8, 16 units, BatchNorm, p = 0.25; one GE_binomial step with the
+# keep-masks of the three Dropout layers recorded by forward hooks (torch's mask stream cannot be reproduced outside torch,
+# so parity is "same masks -> same logits, loss and gradients") ----
+torch.manual_seed(1234)
+P_DROP = 0.25
+m = LinearClassifier(ResNet8(units=16, bn=True, dropout=P_DROP))
+sd = seeded_state({k: tuple(v.shape) for k, v in m.state_dict().items()}, 404)
+m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+m.train()
+masks = []
+for mod in m.modules():
+    if isinstance(mod, nn.Dropout):
+        mod.register_forward_hook(lambda mod, inp, out: masks.append(((out != 0) | (inp[0] == 0)).numpy().copy()))
+optim = torch.optim.Adam(m.parameters(), lr=2e-4)
+tr = GE_binomial(m, optim, nn.BCEWithLogitsLoss(), 0.035, l2=0.0, slack=1.0)
+B = 16
+Y = np.array([1.0] * 2 + [0.0] * (B - 2))
+X = rng(4300).standard_normal((B, 71, 71)).astype(np.float32)
+grads1 = None
+orig = optim.step
+def grab(*a, **k):
+    global grads1
+    grads1 = {n: p.grad.detach().clone().numpy() for n, p in m.named_parameters()}
+    return orig(*a, **k)
+optim.step = grab
+out = tr.step(torch.from_numpy(X), torch.from_numpy(Y))
+assert len(masks) == 3, len(masks)
+path = os.path.join(GOLD, 'ge_binomial_u16_dropout.npz')
+np.savez_compressed(path, seed=np.int64(404), B=np.int64(B), Y=Y, pi=np.float64(0.035), p=np.float64(P_DROP),
+                    out=np.array(out, dtype=np.float64), keys=np.array(list(sd.keys())),
+                    **{f'mask{i}': np.packbits(mk.reshape(-1)) for i, mk in enumerate(masks)},
+                    **{f'mask{i}.shape': np.array(mk.shape) for i, mk in enumerate(masks)},
+                    **{'g1.' + k: v for k, v in grads1.items()})
+print('wrote', path, f'{os.path.getsize(path) / 1e6:.2f} MB', 'out', out, [mk.mean() for mk in masks])

@@ -84,6 +84,8 @@ _PROTOS = {
     'tpz_bn_bwd_f32': (_I, [_P, _P, _LL, _I, _P, _P, _LL, _P, _P, _P, _P, _P, _P]),
     'tpz_act_fwd_f32': (_I, [_P, _LL, _P, _F, _P, _P]),
     'tpz_act_bwd_f32': (_I, [_P, _P, _LL, _P, _F, _P, _P]),
+    'tpz_dropout_fwd_f32': (_I, [_P, _LL, _F, C.c_ulonglong, C.c_ulonglong, _P, _P, _P]),
+    'tpz_dropout_bwd_f32': (_I, [_P, _P, _LL, _F, _P]),
     'tpz_ge_binomial_loss_grad': (_I, [_P, _P, _I, _D, _D, _I, _I, _P, _P, _P]),
     'tpz_pu_objective_loss_grad': (_I, [_P, _P, _I, _I, _D, _D, _D, _D, _I, _I, _P, _P, _P]),
     'tpz_adam_step': (_I, [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _I, _F, _F, _P]),

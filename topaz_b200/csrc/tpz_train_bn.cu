@@ -11,6 +11,7 @@
 // All four are HBM-bound single passes (4-8 B per element read, 4 B written).
 #include "tpz_common.cuh"
 #include "../../include/topaz_b200.h"
+#include <curand_kernel.h>
 
 namespace {
 
@@ -209,6 +210,37 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(float* g, const float* __r
   }
 }
 
+// nn.Dropout in training (reference resnet.py:296-303, basic.py:58-59,71-72): keep each element with probability 1-p and
+// scale the kept ones by 1/(1-p).  Philox counter RNG: element group q = i/4 draws from subsequence q at `offset`, so the
+// mask is a pure function of (seed, offset, i) -- reproducible under torch.manual_seed, independent of the launch shape.
+__global__ void __launch_bounds__(256) dropout_fwd_kernel(const float* __restrict__ x, long long n, float p, float scale,
+                                                          unsigned long long seed, unsigned long long offset,
+                                                          float* __restrict__ y, unsigned char* __restrict__ mask) {
+  const long long groups = (n + 3) >> 2;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < groups; q += (long long)gridDim.x * blockDim.x) {
+    curandStatePhilox4_32_10_t st;
+    curand_init(seed, (unsigned long long)q, offset, &st);
+    const float4 r4 = curand_uniform4(&st);          // uniform in (0, 1]
+    const float r[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const long long i = (q << 2) + e;
+      if (i < n) {
+        const bool keep = r[e] > p;
+        y[i] = keep ? x[i] * scale : 0.f;
+        mask[i] = keep ? 1 : 0;
+      }
+    }
+  }
+}
+
+// g <- g * mask * scale
+__global__ void __launch_bounds__(256) dropout_bwd_kernel(float* __restrict__ g, const unsigned char* __restrict__ mask,
+                                                          long long n, float scale) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    g[i] = mask[i] ? g[i] * scale : 0.f;
+}
+
 inline dim3 reduce_grid(long long P, int C) {
   return dim3(tpz_div_up(C, 32), (unsigned)(P < 4096 ? 1 : (P < 65536 ? 64 : 296)));
 }
@@ -277,6 +309,21 @@ extern "C" int tpz_act_bwd_f32(float* g, const float* v, long long n, const floa
                                float* dslope, void* stream) {
   TPZ_CHECK(n > 0, "tpz_act_bwd_f32: empty tensor");
   act_bwd_kernel<<<elementwise_grid(n), 256, 0, ST(stream)>>>(g, v, n, slope_dev, slope_const, dslope);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tpz_dropout_fwd_f32(const float* x, long long n, float p, unsigned long long seed, unsigned long long offset,
+                                   float* y, unsigned char* mask, void* stream) {
+  TPZ_CHECK(n > 0 && p >= 0.f && p < 1.f, "tpz_dropout_fwd_f32: bad arguments n=%lld p=%g", n, (double)p);
+  dropout_fwd_kernel<<<elementwise_grid(n), 256, 0, ST(stream)>>>(x, n, p, 1.f / (1.f - p), seed, offset, y, mask);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tpz_dropout_bwd_f32(float* g, const unsigned char* mask, long long n, float p, void* stream) {
+  TPZ_CHECK(n > 0 && p >= 0.f && p < 1.f, "tpz_dropout_bwd_f32: bad arguments n=%lld p=%g", n, (double)p);
+  dropout_bwd_kernel<<<elementwise_grid(n), 256, 0, ST(stream)>>>(g, mask, n, 1.f / (1.f - p));
   TPZ_CUDA(cudaGetLastError());
   return 0;
 }

@@ -87,10 +87,12 @@ def _cached(module: nn.Module, name: str, key, build):
 # ------------------------------------------------------------------------------------------------
 # classifier (ResNet8/16, conv31/63/127) dense forward
 # ------------------------------------------------------------------------------------------------
-def _feature_blocks(features, slopes: bool = True) -> List[dict]:
+def _feature_blocks(features, slopes: bool = True, dropout: bool = False) -> List[dict]:
     """Describe the feature extractor's layers in their CURRENT geometry (after fill()/unfill()).  slopes=False (training)
     leaves the activation slopes unread -- a PReLU slope lives on the device and reading it would synchronise every step;
-    the activation modules themselves are returned under 'act' / 'act0' / 'act1'."""
+    the activation modules themselves are returned under 'act' / 'act0' / 'act1'.  dropout=True (training engine) lists the
+    active nn.Dropout layers as {'kind': 'dropout', 'p': p} blocks; otherwise an active dropout layer is an error (the dense
+    path runs in eval() mode, where dropout is the identity)."""
     _slope = _slope_of if slopes else (lambda act: None)
     from .model.features import resnet as R, basic as B
     blocks = []
@@ -106,8 +108,10 @@ def _feature_blocks(features, slopes: bool = True) -> List[dict]:
                                    d0=mod.conv0.dilation[0], d1=mod.conv1.dilation[0], stride=mod.conv1.stride[0],
                                    slope0=_slope(mod.act0), slope1=_slope(mod.act1), act0=mod.act0, act1=mod.act1))
             elif isinstance(mod, nn.Dropout):
-                if features.training and mod.p > 0:
-                    raise NotImplementedError('topaz_b200: dropout in training mode is not supported')
+                if mod.training and mod.p > 0:
+                    if not dropout:
+                        raise NotImplementedError('topaz_b200: the dense forward expects eval() mode (active dropout layer)')
+                    blocks.append(dict(kind='dropout', p=float(mod.p)))
             else:
                 raise NotImplementedError(f'topaz_b200: unsupported ResNet child {type(mod).__name__}')
     elif isinstance(features, B.BasicConv):
@@ -116,6 +120,10 @@ def _feature_blocks(features, slopes: bool = True) -> List[dict]:
         while i < len(mods):
             conv = mods[i]; i += 1
             if isinstance(conv, nn.Dropout):
+                if conv.training and conv.p > 0:
+                    if not dropout:
+                        raise NotImplementedError('topaz_b200: the dense forward expects eval() mode (active dropout layer)')
+                    blocks.append(dict(kind='dropout', p=float(conv.p)))
                 continue
             assert isinstance(conv, (nn.Conv2d, nn.Conv3d)), type(conv)
             bn = None

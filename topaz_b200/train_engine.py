@@ -296,6 +296,27 @@ def _osz(n, k, dil, stride):
     return (n - (k - 1) * dil - 1) // stride + 1
 
 
+_DROPOUT = {'calls': 0}      # Philox offset: every dropout launch of the process draws from its own stream position
+
+
+def _dropout_fwd(x, p):
+    """nn.Dropout(p) in training: returns (y, keep-mask uint8).  Seeded by torch's default generator (torch.manual_seed)."""
+    y = torch.empty_like(x)
+    mask = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    _DROPOUT['calls'] += 1
+    ops._count(1)
+    check(_lib.lib().tpz_dropout_fwd_f32(_p(x), x.numel(), float(p), torch.initial_seed() & 0xFFFFFFFFFFFFFFFF,
+                                         _DROPOUT['calls'] * 4, _p(y), _p(mask), _s()))
+    return y, mask
+
+
+def _dropout_bwd(g, mask, p):
+    """in place: g <- g * mask / (1 - p)"""
+    ops._count(1)
+    check(_lib.lib().tpz_dropout_bwd_f32(_p(g), _p(mask), g.numel(), float(p), _s()))
+    return g
+
+
 def _is_relu(act) -> bool:
     return isinstance(act, nn.ReLU)
 
@@ -304,6 +325,8 @@ def _check_trainable(blocks):
     """ReLU everywhere (the ResNets), or -- in plain conv blocks (conv31/63/127, basic.py:16) -- PReLU with ONE learnable
     slope / LeakyReLU."""
     for b in blocks:
+        if b['kind'] == 'dropout':
+            continue
         if b['kind'] == 'conv':
             act = b['act']
             if isinstance(act, nn.PReLU) and act.weight.numel() != 1:
@@ -340,7 +363,7 @@ def _act_bwd(g, v, act):
 
 def _forward(model_features, classifier, x: torch.Tensor, save: bool):
     """x: [B,H,W,1] fp32.  Returns (score [B] or features NHWC, tape)."""
-    blocks = _feature_blocks(model_features, slopes=False)
+    blocks = _feature_blocks(model_features, slopes=False, dropout=True)
     _check_trainable(blocks)
     tape = []
     cur = x
@@ -349,7 +372,12 @@ def _forward(model_features, classifier, x: torch.Tensor, save: bool):
     ws = _BnWorkspace(n_bn, x.device) if n_bn else None
     for blk in blocks:
         N, H, W, _ = cur.shape
-        if blk['kind'] == 'conv':
+        if blk['kind'] == 'dropout':
+            y, keep = _dropout_fwd(cur, blk['p'])
+            # 'relu' is inherited: the consumer's fused mask (input > 0) then covers ReLU AND dropped elements at once
+            tape.append(dict(kind='dropout', p=blk['p'], mask=keep, relu=tape[-1].get('relu', True) if tape else True))
+            cur = y
+        elif blk['kind'] == 'conv':
             w, b, bn = blk['w'], blk['b'], blk.get('bn')
             k = w.shape[-1]
             Ho, Wo = _osz(H, k, blk['dil'], blk['stride']), _osz(W, k, blk['dil'], blk['stride'])
@@ -459,6 +487,8 @@ def backward(model, dscore: torch.Tensor):
                 g = dscore.contiguous().view(N, H, W, 1)
                 _conv_wgrad(x, g, rec['w'].grad, rec['b'].grad, 1, 1, 0)
                 g = _conv_dgrad(g, rec['w'], 1, 1, 0, H, W, mask=x if in_relu else None)
+            elif rec['kind'] == 'dropout':
+                g = _dropout_bwd(g, rec['mask'], rec['p'])
             elif rec['kind'] == 'conv':
                 x = rec['x']
                 if rec.get('act') is not None:                                # g: d/d(activation output) -> d/d(pre-activation)
