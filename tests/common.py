@@ -61,3 +61,18 @@ def dropout_masks_of(g):
         out.append(np.unpackbits(g[f'mask{i}'])[:int(np.prod(shp))].reshape(shp).astype(bool))
         i += 1
     return out
+
+
+def assert_params_after_adam(v, ref, steps, l2_tol, key='', lr=2e-4):
+    """Compare a parameter tensor after `steps` Adam updates with the reference's.
+
+    Adam moves every element by about lr per step whatever the size of its gradient, so an element whose tiny gradient
+    changed SIGN -- which one flipped ReLU mask among millions of activations is enough to cause (see test_host_logic) --
+    ends up to 2*lr*steps away.  The maximum deviation is therefore bounded ABSOLUTELY by that budget (with headroom for the
+    bias-corrected step exceeding lr), not relative to max|p| (for a BatchNorm bias of ~0.2 the same budget is 0.6 %); the
+    rel-L2 bound carries the actual parity claim: a wrong update rule, a lost optimizer state or a missed layer shifts ALL
+    elements and shows up at 1e-2."""
+    v = np.asarray(v, dtype=np.float64); ref = np.asarray(ref, dtype=np.float64)
+    worst = float(np.abs(v - ref).max())
+    l2 = float(np.linalg.norm(v - ref) / max(np.linalg.norm(ref), 1e-30))
+    assert worst <= 3.5 * lr * steps and l2 < l2_tol, (key, worst, l2)

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from common import ROOT, gold, rel_err
+from common import ROOT, gold, rel_err, assert_params_after_adam
 import sim_backend
 
 REF = '/root/reference'
@@ -126,8 +126,10 @@ def test_reference_fit_epochs_runs_on_dropin_modules(aliased, tmp_path):
         if k.endswith('num_batches_tracked'):
             assert int(fr[k]) == int(fo[k]) == 4
             continue
-        mx, l2 = rel_err(fo[k], fr[k])
-        assert mx < 5e-3 and l2 < 1e-3, (k, mx, l2)
+        if 'running' in k:
+            assert max(rel_err(fo[k], fr[k])) < 1e-3, k
+        else:
+            assert_params_after_adam(fo[k], fr[k], 4, 1e-3, k)
     # the whole-module pickle written by training.py:600-601 carries parameters and buffers only
     for ep in (1, 2):
         saved = torch.load(str(our_dir / f'model_epoch{ep}.sav'), weights_only=False)
