@@ -623,3 +623,42 @@ def test_dropout_training_gradients_match_oracle_with_imposed_masks():
     with torch.no_grad():
         a = m(X[:4].cuda()); b = m(X[:4].cuda())
     assert torch.equal(a, b)
+
+
+def test_resnet16_batchnorm_training_gradients_match_oracle():
+    """ResNet16 (the default of `topaz extract`; 32 units, BatchNorm) in train() mode: stride-1 7x7 first layer, nine blocks
+    with two strided residual blocks.  Logits and every gradient of a GE-binomial step vs autograd through the oracle with
+    the GPU forward's ReLU masks imposed."""
+    from common import seeded_state
+    from common_shapes import classifier_shapes
+    from topaz_b200 import train_engine as T
+    from topaz_b200.model.factory import get_feature_extractor
+    from topaz_b200.model.classifier import LinearClassifier
+    m = LinearClassifier(get_feature_extractor('resnet16', units=32, bn=True))
+    sd = seeded_state(classifier_shapes('resnet16', 32, 1, True), 405)
+    assert list(sd.keys()) == list(m.state_dict().keys())
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    m.cuda(); m.train()
+    B, W, pi = 6, m.width, 0.05
+    assert W == 91
+    X = torch.from_numpy(np.random.default_rng(4400).standard_normal((B, W, W)).astype(np.float32))
+    Y = torch.tensor([1.0] + [0.0] * (B - 1), dtype=torch.float64)
+    T.flat_params(m)
+    score = m(X.cuda()).view(-1)
+    masks = []
+    for rec in m.__dict__['_tpz_tape']:
+        if rec['kind'] == 'conv':
+            masks.append((rec['y'] > 0).permute(0, 3, 1, 2).cpu())
+        elif rec['kind'] == 'resid':
+            masks += [(rec['h'] > 0).permute(0, 3, 1, 2).cpu(), (rec['y'] > 0).permute(0, 3, 1, 2).cpu()]
+    assert len(masks) == 16
+    params = {k: torch.from_numpy(v).clone().requires_grad_('running' not in k and v.dtype == np.float32) for k, v in sd.items()}
+    score_ref = O.classifier_forward_grad(params, X, 'resnet16', 32, bn=True, relu_masks=masks).view(-1)
+    assert max(rel_err(score.detach().cpu().numpy(), score_ref.detach().numpy())) < 1e-4
+    _, _, loss = O.ge_binomial_loss(score_ref, Y, pi, 1.0)
+    loss.backward()
+    ds = torch.empty(B, device='cuda'); o5 = torch.empty(5, device='cuda')
+    T.ge_loss_grad(score.contiguous(), Y.cuda(), pi, 1.0, 0, B, ds, o5)
+    T.backward(m, ds)
+    errs = {k: max(rel_err(p_.grad.cpu().numpy(), params[k].grad.numpy())) for k, p_ in m.named_parameters()}
+    assert max(errs.values()) < 1e-3, errs

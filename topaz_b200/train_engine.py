@@ -304,9 +304,11 @@ def _dropout_fwd(x, p):
     y = torch.empty_like(x)
     mask = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
     _DROPOUT['calls'] += 1
+    dist = _dp()
+    rank = dist.get_rank() if dist is not None else 0          # data-parallel ranks draw independent masks for their shards
+    seed = (torch.initial_seed() + rank * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
     ops._count(1)
-    check(_lib.lib().tpz_dropout_fwd_f32(_p(x), x.numel(), float(p), torch.initial_seed() & 0xFFFFFFFFFFFFFFFF,
-                                         _DROPOUT['calls'] * 4, _p(y), _p(mask), _s()))
+    check(_lib.lib().tpz_dropout_fwd_f32(_p(x), x.numel(), float(p), seed, _DROPOUT['calls'] * 4, _p(y), _p(mask), _s()))
     return y, mask
 
 
