@@ -320,7 +320,7 @@ def main():
                          'peak_source': peaks['src'], 'ms_per_launch': dom_avg_ms, 'launches_timed': len(dom_ms),
                          'step_tflops': (FLOP_PER_PX_4096 * S * S / 1e12) / (ms_max / args.steps / 1e3) if S == 4096 else None},
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N=1 only (the reference arm covers N>1)
             v, dt, thr = cpu_oracle_mpxs()
             line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': thr, 'kind': 'port',
                                     'sample': f'one 512x512 micrograph x3 (bounded sample), oracle torch CPU fp32, {dt:.2f} s each, {thr} threads = fastest of the tried counts on {os.cpu_count()} logical CPUs'}
