@@ -9,7 +9,9 @@ Parity pin: the oracle is checked against golden vectors produced by the REAL
 reference (imported from /root/reference by ``tools/make_goldens.py``) in
 ``tests/test_oracle_golden.py``.  The reference's own test-suite pins no numeric
 result on this path, so those goldens + the packaged
-pretrained weights are the pin.
+pretrained weights are the pin.  Training-mode BatchNorm, the PReLU extractors and dropout are pinned the same way
+(``tools/make_goldens_bn.py``: 2-3 GE_binomial steps of the real reference; for dropout, with the keep-masks its
+nn.Dropout layers drew recorded by hooks, since torch's mask stream cannot be reproduced outside torch).
 
 Every function cites the reference file:line it restates.  Weights are passed
 as a plain ``dict[str, np.ndarray | torch.Tensor]`` keyed by the reference's
