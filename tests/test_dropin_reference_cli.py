@@ -173,3 +173,38 @@ def test_adam_state_survives_a_device_round_trip():
     np.testing.assert_array_equal(o0, o1)
     for k in s0:
         np.testing.assert_array_equal(s0[k], s1[k], err_msg=k)
+
+
+def test_reference_train_command_runs_on_dropin_modules(aliased, tmp_path, monkeypatch):
+    """`topaz train` end to end: the reference's command function (commands/train.py main: make_model -> train_model ->
+    its own data loaders, crop sampler and augmentation -> fit_epochs with a test split and --save-prefix) drives the drop-in
+    modules (simulated kernels) on a tiny data set with a pretended GPU, so that the reference takes its use_cuda=True paths.
+    The reference's samplers draw from unseeded generators (two runs of the reference itself see different minibatches), so
+    this test checks the run structurally; the numeric comparison of the same loop on fixed minibatches is
+    test_reference_fit_epochs_runs_on_dropin_modules.  With --minibatch-balance 0.0625 x 8 crops most minibatches hold no
+    positive: the classifier loss is then nan in the log -- in the reference too (mean over an empty selection) -- while
+    the GE term still trains, and the parameters must stay finite."""
+    import ref_train_cli_script
+    monkeypatch.setattr(torch.nn.Module, 'cuda', torch.nn.Module.cuda)             # restored after pretend_gpu() below
+    monkeypatch.setattr(torch.Tensor, 'cuda', torch.Tensor.cuda)
+    import topaz.cuda
+    monkeypatch.setattr(topaz.cuda, 'set_device', topaz.cuda.set_device)
+    ref_train_cli_script.pretend_gpu()
+    with sim_backend.patched_training():
+        log = ref_train_cli_script.run(str(tmp_path), 0)
+    rows = [l.rstrip('\n').split('\t') for l in open(log)]
+    assert rows[0] == ['epoch', 'iter', 'split', 'loss', 'ge_penalty', 'precision', 'adjusted_precision', 'tpr', 'fpr', 'auprc']
+    body = rows[1:]
+    assert [r[2] for r in body] == ['train', 'train', 'test', 'train', 'train', 'test']
+    for r in body:
+        if r[2] == 'train':
+            ge, prec, fpr = float(r[4]), float(r[5]), float(r[8])
+            assert np.isfinite(ge) and ge > 0 and 0.0 <= prec <= 1.0 and 0.0 < fpr < 1.0 and r[9] == '-', r
+        else:
+            assert np.isfinite(float(r[3])) and r[4] == '-' and 0.0 <= float(r[9]) <= 1.0, r
+    from topaz_b200.model.classifier import LinearClassifier as Ours
+    for ep in (1, 2):
+        saved = torch.load(str(tmp_path / f'model_epoch{ep}.sav'), weights_only=False)
+        assert type(saved) is Ours and not [k for mod in saved.modules() for k in mod.__dict__ if k.startswith('_tpz_')]
+        assert all(torch.isfinite(v).all() for v in saved.state_dict().values())
+    assert int(saved.state_dict()['features.features.0.bn.num_batches_tracked']) == 4
