@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from common import ROOT, gold, rel_err, assert_params_after_adam
+from common import ROOT, gold, weights_of, rel_err, assert_params_after_adam
 import sim_backend
 
 REF = '/root/reference'
@@ -208,3 +208,126 @@ def test_reference_train_command_runs_on_dropin_modules(aliased, tmp_path, monke
         assert type(saved) is Ours and not [k for mod in saved.modules() for k in mod.__dict__ if k.startswith('_tpz_')]
         assert all(torch.isfinite(v).all() for v in saved.state_dict().values())
     assert int(saved.state_dict()['features.features.0.bn.num_batches_tracked']) == 4
+
+
+def test_reference_extract_command_runs_on_dropin_modules(aliased, tmp_path, monkeypatch):
+    """`topaz extract` end to end: the reference's command function (commands/extract.py main -> extract_particles ->
+    score_images -> nms_iterator -> coordinate table) on the drop-in classifier (simulated conv kernels).  The build container
+    has no GPU for the NMS kernel, so the reference module's NMS name is bound to the oracle's (the GPU NMS itself is held
+    bit-exact to that oracle in tests/test_gpu_parity.py); what is checked here is that the reference pipeline scores through
+    the drop-in modules and writes the picks of THAT score map."""
+    import topaz.cuda
+    import topaz.extract as ref_extract
+    import topaz.commands.extract as extract_cmd
+    from oracle import topaz_oracle as O
+    from topaz_b200 import mrc
+    g = gold('resnet8_u32_pretrained')
+    p = str(tmp_path / 'mic.mrc'); mrc.write(p, g['x'][0, 0])
+    monkeypatch.setattr(topaz.cuda, 'set_device', lambda device, **kw: True)
+    monkeypatch.setattr(torch.nn.Module, 'cuda', lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.Tensor, 'cuda', lambda self, *a, **k: self)
+    monkeypatch.setattr(ref_extract, 'non_maximum_suppression', lambda x, r, threshold=-np.inf: O.nms(x, r, threshold))
+    out = str(tmp_path / 'picks.txt')
+    args = extract_cmd.add_arguments().parse_args([p, '-m', 'resnet8_u32', '-r', '8', '-t', '-6', '-o', out, '-d', '0'])
+    with sim_backend.patched():
+        extract_cmd.main(args)
+        scores = dict(ref_extract.score_images('resnet8_u32', [p], device=0))[p]
+    rows = [l.rstrip('\n').split('\t') for l in open(out)]
+    assert rows[0] == ['image_name', 'x_coord', 'y_coord', 'score']
+    sc, coords = O.nms(scores, 8, -6)
+    assert len(rows) - 1 == len(sc) > 0
+    for r, s, (x, y) in zip(rows[1:], sc, coords):
+        assert r[0] == 'mic' and int(r[1]) == x and int(r[2]) == y and abs(float(r[3]) - s) < 1e-5
+    # the best pick is also the best pick of the reference's own score map
+    ref_sc, ref_coords = O.nms(g['y_dense'][0, 0], 8, -6)
+    assert tuple(ref_coords[0]) == tuple(coords[0]) and abs(ref_sc[0] - sc[0]) < 1e-3 * np.abs(g['y_dense']).max()
+
+
+def test_reference_denoise_command_runs_on_dropin_modules(aliased, tmp_path, monkeypatch):
+    """`topaz denoise` end to end: the reference's command function (commands/denoise.py main -> Denoise('unet') ->
+    denoise_stream -> denoise_image -> Denoise.denoise in patches -> MRC written) with the drop-in UDenoiseNet behind the
+    reference's own Denoise class (simulated kernels, pretended GPU); the written micrograph equals the oracle's result of
+    the same pipeline (normalise, patched denoise with the packaged v0.2.2 weights, de-normalise)."""
+    import topaz.cuda
+    import topaz.commands.denoise as denoise_cmd
+    from oracle import topaz_oracle as O
+    from topaz_b200 import mrc
+    from topaz_b200.denoising.models import UDenoiseNet as Ours
+    g = gold('unet_pretrained')
+    img = g['img']
+    p = str(tmp_path / 'mic.mrc'); mrc.write(p, img)
+    monkeypatch.setattr(denoise_cmd, 'set_device', lambda device, **kw: True)
+    monkeypatch.setattr(topaz.cuda, 'set_device', lambda device, **kw: True)
+    monkeypatch.setattr(torch.nn.Module, 'cuda', lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.Tensor, 'cuda', lambda self, *a, **k: self)
+    outdir = str(tmp_path / 'out')
+    args = denoise_cmd.add_arguments().parse_args([p, '-o', outdir, '-s', '64', '-p', '24', '-d', '0'])
+    with sim_backend.patched():
+        denoised = denoise_cmd.main(args)
+    assert len(denoised) == 1 and denoised[0].shape == img.shape
+    written = mrc.parse(open(os.path.join(outdir, 'mic.mrc'), 'rb').read())[0]
+    written = written[0] if written.ndim == 3 else written
+    mu, std = img.mean(), img.std()
+    ref = std * O.denoise(weights_of(g), (img - mu) / std, 64, 24) + mu
+    for y in (denoised[0], written):
+        mx, l2 = rel_err(y, ref)
+        assert mx < 2e-3 and l2 < 2e-3, (mx, l2)
+
+
+def test_reference_denoise3d_command_runs_on_dropin_modules(aliased, tmp_path):
+    """`topaz denoise3d` end to end: the reference's command function (commands/denoise3d.py main -> Denoise3D('unet-3d') ->
+    denoise_tomogram_stream -> PatchDataset crops -> model -> MRC written) with the drop-in UDenoiseNet3D (packaged
+    unet-3d-10a weights, simulated kernels); the written tomogram equals the oracle's result of the same pipeline."""
+    import topaz.commands.denoise3d as denoise3d_cmd
+    import topaz.mrc as ref_mrc
+    from oracle import topaz_oracle as O
+    from topaz_b200.denoising.models import UDenoiseNet3D as Ours, load_model
+    tomo = gold('unet3d_seeded')['tomo']
+    p = str(tmp_path / 'tomo.mrc')
+    with open(p, 'wb') as f:
+        ref_mrc.write(f, tomo)
+    outdir = str(tmp_path / 'out'); os.makedirs(outdir)
+    args = denoise3d_cmd.add_arguments().parse_args([p, '-o', outdir, '-s', '16', '-p', '8', '-d', '-1'])
+    with sim_backend.patched():
+        denoise3d_cmd.main(args)
+    with open(os.path.join(outdir, 'tomo.mrc'), 'rb') as f:
+        written = ref_mrc.parse(f.read())[0]
+    m = load_model('unet-3d')
+    assert type(m) is Ours
+    ref = O.denoise3d({k: v.numpy() for k, v in m.state_dict().items()}, tomo, 16, 8)
+    mx, l2 = rel_err(written, ref)
+    assert written.shape == tomo.shape and mx < 2e-3 and l2 < 2e-3, (mx, l2)
+
+
+def test_reference_preprocess_command_runs_on_dropin_kernels(aliased, tmp_path, monkeypatch):
+    """`topaz preprocess -s 2` end to end: the reference's command function (commands/normalize.py main -> normalize_images ->
+    Normalize.__call__: load, downsample, GMM-normalise, write MRC + metadata) with compat's function patches
+    (`topaz.utils.image.downsample`, `topaz.stats.normalize` -> the Fourier-crop GEMMs and the one-pass-per-iteration EM of
+    tpz_preproc.cu, simulated here) vs the unmodified reference command run in a subprocess on the CPU."""
+    import json
+    import subprocess
+    import topaz.cuda
+    import topaz.stats
+    import topaz.commands.normalize as normalize_cmd
+    from topaz_b200 import mrc, preprocess
+    assert topaz.stats.downsample is preprocess.downsample          # the name `Normalize.__call__` resolves (stats.py:304)
+    x = gold('preprocess')['x']
+    p = str(tmp_path / 'mic.mrc'); mrc.write(p, x)
+    ref_dir, our_dir = str(tmp_path / 'ref'), str(tmp_path / 'ours')
+    common = [p, '-s', '2', '--sample', '1', '--metadata']
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE='1', PYTHONPATH=os.pathsep.join([REF, os.path.join(ROOT, 'tools', 'stubs')]))
+    r = subprocess.run([sys.executable, os.path.join(REF, 'topaz', 'commands', 'normalize.py')] + common + ['-o', ref_dir, '-d', '-1'],
+                       env=env, cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    monkeypatch.setattr(normalize_cmd, 'set_device', lambda device, **kw: True)
+    monkeypatch.setattr(torch.Tensor, 'cuda', lambda self, *a, **k: self)
+    with sim_backend.patched():
+        normalize_cmd.main(normalize_cmd.add_arguments().parse_args(common + ['-o', our_dir, '-d', '0']))
+    ours, ref = mrc.read(os.path.join(our_dir, 'mic.mrc'))[0], mrc.read(os.path.join(ref_dir, 'mic.mrc'))[0]
+    ours, ref = np.squeeze(ours), np.squeeze(ref)
+    assert ours.shape == ref.shape == (75, 66)
+    assert np.abs(ours - ref).max() < 2e-3, np.abs(ours - ref).max()          # normalised micrograph: unit variance
+    mo, mr = json.load(open(os.path.join(our_dir, 'mic.metadata.json'))), json.load(open(os.path.join(ref_dir, 'mic.metadata.json')))
+    assert set(mo) == set(mr)
+    for k in ('mu', 'std', 'pi', 'logp'):
+        assert abs(mo[k] - mr[k]) <= 2e-3 * max(1.0, abs(mr[k])), (k, mo[k], mr[k])

@@ -24,6 +24,13 @@ _FUNCTION_PATCHES = {('topaz.algorithms', 'non_maximum_suppression'): ('topaz_b2
                      ('topaz.stats', 'gmm_fit'): ('topaz_b200.stats', 'gmm_fit')}
 
 
+# names that reference modules bind with `from X import f` at import time: re-pointed when the consumer module is ALREADY
+# loaded (install() after `import topaz.stats` / `import topaz.extract` would otherwise leave them on the reference function)
+_REEXPORTS = {('topaz.stats', 'downsample'): ('topaz_b200.preprocess', 'downsample'),
+              ('topaz.extract', 'non_maximum_suppression'): ('topaz_b200.algorithms', 'non_maximum_suppression'),
+              ('topaz.extract', 'non_maximum_suppression_3d'): ('topaz_b200.algorithms', 'non_maximum_suppression_3d')}
+
+
 def install(names=None):
     """Alias the listed reference module paths (default: all) to the topaz_b200 implementations."""
     for ref, ours in _ALIASES.items():
@@ -48,6 +55,10 @@ def install(names=None):
         if not hasattr(target, '_tpz_orig_' + fn):
             setattr(target, '_tpz_orig_' + fn, getattr(target, fn))
         setattr(target, fn, getattr(importlib.import_module(our_mod), our_fn))
+    for (ref_mod, fn), (our_mod, our_fn) in _REEXPORTS.items():
+        target = sys.modules.get(ref_mod)
+        if target is not None and (names is None or ref_mod in names) and hasattr(target, fn):
+            setattr(target, fn, getattr(importlib.import_module(our_mod), our_fn))
     return sorted(_ALIASES if names is None else names)
 
 
