@@ -77,20 +77,25 @@ def unet(nf=48, base=11, top=5):
 
 
 class TrainNet(nn.Module):
-    def __init__(s, u=32):
+    """ResNet8 in its strided training geometry; bn=True: BatchNorm after every conv / residual sum (the model `topaz train
+    --no-pretrained` builds), convs without bias."""
+    def __init__(s, u=32, bn=False):
         super().__init__()
-        s.c7 = nn.Conv2d(1, u, 7, stride=2)
-        s.r1a, s.r1b = nn.Conv2d(u, u, 3), nn.Conv2d(u, u, 3, dilation=2)
-        s.r2a, s.r2b, s.r2p = nn.Conv2d(u, u, 3), nn.Conv2d(u, 2 * u, 3, dilation=2, stride=2), nn.Conv2d(u, 2 * u, 1, stride=2, bias=False)
-        s.r3a, s.r3b = nn.Conv2d(2 * u, 2 * u, 3), nn.Conv2d(2 * u, 2 * u, 3, dilation=2)
-        s.c5, s.cls = nn.Conv2d(2 * u, 4 * u, 5), nn.Conv2d(4 * u, 1, 1)
+        b = not bn
+        s.c7 = nn.Conv2d(1, u, 7, stride=2, bias=b)
+        s.r1a, s.r1b = nn.Conv2d(u, u, 3, bias=b), nn.Conv2d(u, u, 3, dilation=2, bias=b)
+        s.r2a, s.r2b, s.r2p = nn.Conv2d(u, u, 3, bias=b), nn.Conv2d(u, 2 * u, 3, dilation=2, stride=2, bias=b), nn.Conv2d(u, 2 * u, 1, stride=2, bias=False)
+        s.r3a, s.r3b = nn.Conv2d(2 * u, 2 * u, 3, bias=b), nn.Conv2d(2 * u, 2 * u, 3, dilation=2, bias=b)
+        s.c5, s.cls = nn.Conv2d(2 * u, 4 * u, 5, bias=b), nn.Conv2d(4 * u, 1, 1)
+        norm = (lambda c: nn.BatchNorm2d(c)) if bn else (lambda c: nn.Identity())
+        s.n7, s.n1a, s.n1b, s.n2a, s.n2b, s.n3a, s.n3b, s.n5 = (norm(c) for c in (u, u, u, u, 2 * u, 2 * u, 2 * u, 4 * u))
 
     def forward(s, x):
-        x = F.relu(s.c7(x.unsqueeze(1)))
-        x = F.relu(s.r1b(F.relu(s.r1a(x))) + x[:, :, 3:-3, 3:-3])
-        x = F.relu(s.r2b(F.relu(s.r2a(x))) + s.r2p(x[:, :, 3:-3, 3:-3]))
-        x = F.relu(s.r3b(F.relu(s.r3a(x))) + x[:, :, 3:-3, 3:-3])
-        return s.cls(F.relu(s.c5(x))).view(-1)
+        x = F.relu(s.n7(s.c7(x.unsqueeze(1))))
+        x = F.relu(s.n1b(s.r1b(F.relu(s.n1a(s.r1a(x)))) + x[:, :, 3:-3, 3:-3]))
+        x = F.relu(s.n2b(s.r2b(F.relu(s.n2a(s.r2a(x)))) + s.r2p(x[:, :, 3:-3, 3:-3])))
+        x = F.relu(s.n3b(s.r3b(F.relu(s.n3a(s.r3a(x)))) + x[:, :, 3:-3, 3:-3]))
+        return s.cls(F.relu(s.n5(s.c5(x)))).view(-1)
 
 
 def main():
@@ -120,18 +125,20 @@ def main():
                 out.append(dict(workload='UDenoiseNet 2048x2048', cudnn_benchmark=bench_flag, error=str(e)[:200]))
             torch.cuda.empty_cache()
     torch.backends.cudnn.benchmark = False
-    net = TrainNet(32).cuda()
-    opt = torch.optim.Adam(net.parameters(), lr=2e-4)
     X = torch.randn(256, 71, 71, device='cuda'); Y = torch.zeros(256, device='cuda'); Y[:16] = 1
+    for bn in (False, True):
+        net = TrainNet(32, bn=bn).cuda()
+        opt = torch.optim.Adam(net.parameters(), lr=2e-4)
 
-    def step():
-        s = net(X)
-        loss = F.binary_cross_entropy_with_logits(s[Y == 1], Y[Y == 1]) + torch.sigmoid(s[Y == 0]).sum() * 1e-3
-        loss.backward()
-        opt.step(); opt.zero_grad()
-        return loss.item()      # the reference syncs every step (methods.py:148-165)
-    ms = time_it(step, warm=5, reps=20)
-    out.append(dict(workload='GE-style train step, resnet8_u32, 256x71x71 (torch+cuDNN, simplified loss)', ms=ms, crops_s=256 / (ms / 1e3)))
+        def step():
+            s = net(X)
+            loss = F.binary_cross_entropy_with_logits(s[Y == 1], Y[Y == 1]) + torch.sigmoid(s[Y == 0]).sum() * 1e-3
+            loss.backward()
+            opt.step(); opt.zero_grad()
+            return loss.item()      # the reference syncs every step (methods.py:148-165)
+        ms = time_it(step, warm=5, reps=20)
+        out.append(dict(workload='GE-style train step, resnet8_u32' + (' + BatchNorm' if bn else '') + ', 256x71x71 (torch+cuDNN, simplified loss)',
+                        ms=ms, crops_s=256 / (ms / 1e3)))
     for o in out:
         o.update(info)
         print(json.dumps(o))
