@@ -331,3 +331,23 @@ def test_reference_preprocess_command_runs_on_dropin_kernels(aliased, tmp_path, 
     assert set(mo) == set(mr)
     for k in ('mu', 'std', 'pi', 'logp'):
         assert abs(mo[k] - mr[k]) <= 2e-3 * max(1.0, abs(mr[k])), (k, mo[k], mr[k])
+
+
+def test_reference_segment_command_runs_on_dropin_modules(aliased, tmp_path, monkeypatch):
+    """`topaz segment` end to end: the reference's command function (commands/segment.py main -> load_model -> eval/fill ->
+    the reference's own segment_images -> TIFF score map) on the drop-in classifier (simulated kernels)."""
+    import topaz.cuda
+    import topaz.commands.segment as segment_cmd
+    from PIL import Image
+    from topaz_b200 import mrc
+    g = gold('resnet8_u32_pretrained')
+    p = str(tmp_path / 'mic.mrc'); mrc.write(p, g['x'][0, 0])
+    monkeypatch.setattr(topaz.cuda, 'set_device', lambda device, **kw: True)
+    monkeypatch.setattr(torch.nn.Module, 'cuda', lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.Tensor, 'cuda', lambda self, *a, **k: self)
+    outdir = str(tmp_path / 'seg')
+    with sim_backend.patched():
+        segment_cmd.main(segment_cmd.add_arguments().parse_args([p, '-m', 'resnet8_u32', '-o', outdir, '-d', '0']))
+    y = np.array(Image.open(os.path.join(outdir, 'mic.tiff')))
+    mx, l2 = rel_err(y, g['y_dense'][0, 0])
+    assert y.dtype == np.float32 and mx < 1e-3 and l2 < 1e-3, (mx, l2)
