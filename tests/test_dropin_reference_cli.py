@@ -351,3 +351,17 @@ def test_reference_segment_command_runs_on_dropin_modules(aliased, tmp_path, mon
     y = np.array(Image.open(os.path.join(outdir, 'mic.tiff')))
     mx, l2 = rel_err(y, g['y_dense'][0, 0])
     assert y.dtype == np.float32 and mx < 1e-3 and l2 < 1e-3, (mx, l2)
+
+
+def test_python_m_topaz_b200_runs_the_reference_command_line(tmp_path):
+    """`python -m topaz_b200 train --describe --no-pretrained`: the reference's own dispatcher (topaz/main.py) with the
+    drop-in modules installed prints the default BatchNorm ResNet8 built from the drop-in classes."""
+    import subprocess
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE='1', PYTHONPATH=os.pathsep.join([ROOT, REF, os.path.join(ROOT, 'tools', 'stubs')]))
+    r = subprocess.run([sys.executable, '-m', 'topaz_b200', 'train', '--describe', '--no-pretrained'], env=env, cwd=str(tmp_path),
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.startswith('LinearClassifier(') and '(bn1): BatchNorm2d(64' in r.stdout and 'ResidA(' in r.stdout
+    r = subprocess.run([sys.executable, '-c', 'import topaz_b200.compat as c; c.install(); import topaz.model.classifier as m; '
+                        'print(m.LinearClassifier.__module__)'], env=env, cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
+    assert r.stdout.strip() == 'topaz_b200.model.classifier', (r.stdout, r.stderr[-500:])
