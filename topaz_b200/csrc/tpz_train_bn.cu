@@ -9,6 +9,10 @@
 //   tpz_bn_bwd_reduce_f32 sums[c] += sum_p g[p][c],  sums[C+c] += sum_p g[p][c]*xhat[p][c]
 //   tpz_bn_bwd_f32        dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat));  dgamma += sum g*xhat, dbeta += sum g
 // All four are HBM-bound single passes (4-8 B per element read, 4 B written).
+//
+// The other element-wise layers of the training nets live here too:
+//   tpz_act_fwd_f32 / tpz_act_bwd_f32          PReLU (one learnable slope) / LeakyReLU of conv31/63/127 (basic.py:16,51,66)
+//   tpz_dropout_fwd_f32 / tpz_dropout_bwd_f32  nn.Dropout in training (resnet.py:296-303): Philox keep-masks
 #include "tpz_common.cuh"
 #include "../../include/topaz_b200.h"
 #include <curand_kernel.h>
