@@ -9,8 +9,14 @@
 #include "../../include/topaz_b200.h"
 
 #include <stdlib.h>
-// X3 = true: error-compensated 3xTF32 (fp32-level accuracy, default).  X3 = false (env TPZ_TRAIN_TF32=1): single-pass TF32,
+// X3 = 1: error-compensated 3xTF32 (fp32-level accuracy, default).  X3 = 0 (env TPZ_TRAIN_TF32=1): single-pass TF32,
 // the precision of the reference's own cuDNN path (torch.backends.cudnn.allow_tf32 = True), ~1.3x faster step.
+// X3 = 2 (env TPZ_TRAIN_SPLIT=fast, opt-in candidate, NOT yet validated on hardware): 3xTF32 with a 3-instruction operand
+// split.  On sm_100a `cvt.rna.tf32.f32` is emulated (FSETP inf/nan guard + predicated integer add of half an ulp + LOP3
+// mask, `profiles/r01_sass_train_mma_s2.md`), so the default split costs 7 instructions per operand value and the hot loops
+// issue 4.4-6.8 instructions per HMMA.  The fast split rounds hi with the same add+mask but without the guard (inf stays inf;
+// NaN payloads are irrelevant here) and hands lo = x - hi to the MMA unrounded (the tensor core ignores the 13 low mantissa
+// bits of a .tf32 operand, i.e. truncates: an extra error of < 2^-21 |x| per product).
 
 namespace {
 
@@ -31,15 +37,20 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 // split an fp32 fragment into TF32 hi (+ lo) parts once; reused by every MMA that consumes the fragment
-template <bool X3, int N>
+template <int X3, int N>
 __device__ __forceinline__ void split_tf32(const float (&v)[N], uint32_t (&hi)[N], uint32_t (&lo)[N]) {
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    hi[i] = to_tf32(v[i]);
-    lo[i] = X3 ? to_tf32(v[i] - __uint_as_float(hi[i])) : 0u;
+    if (X3 == 2) {
+      hi[i] = (__float_as_uint(v[i]) + 0x1000u) & 0xffffe000u;          // round-half-away to 10 mantissa bits (finite inputs)
+      lo[i] = __float_as_uint(v[i] - __uint_as_float(hi[i]));           // exact in fp32; truncated by the tensor core
+    } else {
+      hi[i] = to_tf32(v[i]);
+      lo[i] = X3 ? to_tf32(v[i] - __uint_as_float(hi[i])) : 0u;
+    }
   }
 }
-template <bool X3>
+template <int X3>
 __device__ __forceinline__ void mma_split(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
                                           const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
   if (X3) {
@@ -82,7 +93,7 @@ __global__ void repack_kernel(const float* __restrict__ flat, const RepackDesc* 
 // -------------------------------------------------------------------------------------------------
 constexpr int GBM = 128, GBK = 16, GAS = 20;   // A smem row stride (floats): conflict-free fragment reads
 
-template <int BN, int MODE, bool X3>   // MODE 0 fwd, 1 dgrad
+template <int BN, int MODE, int X3>   // MODE 0 fwd, 1 dgrad; X3: see the top of the file
 __global__ void __launch_bounds__(256) conv_mma_kernel(MGeom g, const float* __restrict__ src, const float* __restrict__ wpk,
                                                        const float* __restrict__ bias, const float* __restrict__ res,
                                                        int res_H, int res_W, int res_org, int res_stride,
@@ -269,7 +280,7 @@ __global__ void __launch_bounds__(256) conv_mma_kernel(MGeom g, const float* __r
 // -------------------------------------------------------------------------------------------------
 constexpr int WBK = 16;
 
-template <int BT, bool X3>    // square (BT co) x (BT ci) tile, BT = 64 or 32
+template <int BT, int X3>    // square (BT co) x (BT ci) tile, BT = 64 or 32
 __global__ void __launch_bounds__(256) wgrad_mma_kernel(MGeom g, const float* __restrict__ x, const float* __restrict__ dy,
                                                         float* __restrict__ dw, int k_per_split) {
   constexpr int STG = 4;
@@ -401,6 +412,11 @@ static bool use_x3() {
   }
   return g_tf32_mode == 0;
 }
+// template argument X3 of the kernels: 0 single-pass TF32, 1 3xTF32 (default), 2 3xTF32 with the fast split (opt-in)
+static int x3_mode() {
+  static const bool fast = []() { const char* e = getenv("TPZ_TRAIN_SPLIT"); return e && strcmp(e, "fast") == 0; }();
+  return use_x3() ? (fast ? 2 : 1) : 0;
+}
 extern "C" int tpz_train_set_tf32(int single_pass) {
   int prev = use_x3() ? 0 : 1;
   g_tf32_mode = single_pass ? 1 : 0;
@@ -430,12 +446,18 @@ extern "C" int tpz_conv_fwd_mma(const float* x, int N, int H, int W, int Ci, con
   const long long M = (long long)N * Ho * Wo;
   if (Co % 64 == 0) {
     dim3 grid(tpz_div_up(M, GBM), Co / 64);
-    if (use_x3()) conv_mma_kernel<64, 0, true><<<grid, 256, 0, ST(stream)>>>(g, x, w_fwd_packed, bias, res, res_H, res_W, res_org, res_stride, nullptr, y, relu, 0);
-    else conv_mma_kernel<64, 0, false><<<grid, 256, 0, ST(stream)>>>(g, x, w_fwd_packed, bias, res, res_H, res_W, res_org, res_stride, nullptr, y, relu, 0);
+    switch (x3_mode()) {
+      case 1: conv_mma_kernel<64, 0, 1><<<grid, 256, 0, ST(stream)>>>(g, x, w_fwd_packed, bias, res, res_H, res_W, res_org, res_stride, nullptr, y, relu, 0); break;
+      case 2: conv_mma_kernel<64, 0, 2><<<grid, 256, 0, ST(stream)>>>(g, x, w_fwd_packed, bias, res, res_H, res_W, res_org, res_stride, nullptr, y, relu, 0); break;
+      default: conv_mma_kernel<64, 0, 0><<<grid, 256, 0, ST(stream)>>>(g, x, w_fwd_packed, bias, res, res_H, res_W, res_org, res_stride, nullptr, y, relu, 0); break;
+    }
   } else {
     dim3 grid(tpz_div_up(M, GBM), Co / 32);
-    if (use_x3()) conv_mma_kernel<32, 0, true><<<grid, 256, 0, ST(stream)>>>(g, x, w_fwd_packed, bias, res, res_H, res_W, res_org, res_stride, nullptr, y, relu, 0);
-    else conv_mma_kernel<32, 0, false><<<grid, 256, 0, ST(stream)>>>(g, x, w_fwd_packed, bias, res, res_H, res_W, res_org, res_stride, nullptr, y, relu, 0);
+    switch (x3_mode()) {
+      case 1: conv_mma_kernel<32, 0, 1><<<grid, 256, 0, ST(stream)>>>(g, x, w_fwd_packed, bias, res, res_H, res_W, res_org, res_stride, nullptr, y, relu, 0); break;
+      case 2: conv_mma_kernel<32, 0, 2><<<grid, 256, 0, ST(stream)>>>(g, x, w_fwd_packed, bias, res, res_H, res_W, res_org, res_stride, nullptr, y, relu, 0); break;
+      default: conv_mma_kernel<32, 0, 0><<<grid, 256, 0, ST(stream)>>>(g, x, w_fwd_packed, bias, res, res_H, res_W, res_org, res_stride, nullptr, y, relu, 0); break;
+    }
   }
   TPZ_CUDA(cudaGetLastError());
   return 0;
@@ -465,12 +487,18 @@ extern "C" int tpz_conv_dgrad_mma(const float* dy, int N, int Ho, int Wo, int Co
   const long long M = (long long)N * H * W;
   if (Ci % 64 == 0) {
     dim3 grid(tpz_div_up(M, GBM), Ci / 64);
-    if (use_x3()) conv_mma_kernel<64, 1, true><<<grid, 256, 0, ST(stream)>>>(g, dy, w_dg_packed, nullptr, nullptr, 0, 0, 0, 1, relu_mask, dx, 0, accumulate);
-    else conv_mma_kernel<64, 1, false><<<grid, 256, 0, ST(stream)>>>(g, dy, w_dg_packed, nullptr, nullptr, 0, 0, 0, 1, relu_mask, dx, 0, accumulate);
+    switch (x3_mode()) {
+      case 1: conv_mma_kernel<64, 1, 1><<<grid, 256, 0, ST(stream)>>>(g, dy, w_dg_packed, nullptr, nullptr, 0, 0, 0, 1, relu_mask, dx, 0, accumulate); break;
+      case 2: conv_mma_kernel<64, 1, 2><<<grid, 256, 0, ST(stream)>>>(g, dy, w_dg_packed, nullptr, nullptr, 0, 0, 0, 1, relu_mask, dx, 0, accumulate); break;
+      default: conv_mma_kernel<64, 1, 0><<<grid, 256, 0, ST(stream)>>>(g, dy, w_dg_packed, nullptr, nullptr, 0, 0, 0, 1, relu_mask, dx, 0, accumulate); break;
+    }
   } else {
     dim3 grid(tpz_div_up(M, GBM), Ci / 32);
-    if (use_x3()) conv_mma_kernel<32, 1, true><<<grid, 256, 0, ST(stream)>>>(g, dy, w_dg_packed, nullptr, nullptr, 0, 0, 0, 1, relu_mask, dx, 0, accumulate);
-    else conv_mma_kernel<32, 1, false><<<grid, 256, 0, ST(stream)>>>(g, dy, w_dg_packed, nullptr, nullptr, 0, 0, 0, 1, relu_mask, dx, 0, accumulate);
+    switch (x3_mode()) {
+      case 1: conv_mma_kernel<32, 1, 1><<<grid, 256, 0, ST(stream)>>>(g, dy, w_dg_packed, nullptr, nullptr, 0, 0, 0, 1, relu_mask, dx, 0, accumulate); break;
+      case 2: conv_mma_kernel<32, 1, 2><<<grid, 256, 0, ST(stream)>>>(g, dy, w_dg_packed, nullptr, nullptr, 0, 0, 0, 1, relu_mask, dx, 0, accumulate); break;
+      default: conv_mma_kernel<32, 1, 0><<<grid, 256, 0, ST(stream)>>>(g, dy, w_dg_packed, nullptr, nullptr, 0, 0, 0, 1, relu_mask, dx, 0, accumulate); break;
+    }
   }
   TPZ_CUDA(cudaGetLastError());
   return 0;
@@ -492,11 +520,17 @@ extern "C" int tpz_conv_wgrad_mma(const float* x, int N, int H, int W, int Ci, c
   splits = (int)((P + kps - 1) / kps);
   dim3 grid(mt, nt, taps * splits);
   if (BT == 32) {
-    if (use_x3()) wgrad_mma_kernel<32, true><<<grid, 256, 0, ST(stream)>>>(g, x, dy, dw, (int)kps);
-    else wgrad_mma_kernel<32, false><<<grid, 256, 0, ST(stream)>>>(g, x, dy, dw, (int)kps);
+    switch (x3_mode()) {
+      case 1: wgrad_mma_kernel<32, 1><<<grid, 256, 0, ST(stream)>>>(g, x, dy, dw, (int)kps); break;
+      case 2: wgrad_mma_kernel<32, 2><<<grid, 256, 0, ST(stream)>>>(g, x, dy, dw, (int)kps); break;
+      default: wgrad_mma_kernel<32, 0><<<grid, 256, 0, ST(stream)>>>(g, x, dy, dw, (int)kps); break;
+    }
   } else {
-    if (use_x3()) wgrad_mma_kernel<64, true><<<grid, 256, 0, ST(stream)>>>(g, x, dy, dw, (int)kps);
-    else wgrad_mma_kernel<64, false><<<grid, 256, 0, ST(stream)>>>(g, x, dy, dw, (int)kps);
+    switch (x3_mode()) {
+      case 1: wgrad_mma_kernel<64, 1><<<grid, 256, 0, ST(stream)>>>(g, x, dy, dw, (int)kps); break;
+      case 2: wgrad_mma_kernel<64, 2><<<grid, 256, 0, ST(stream)>>>(g, x, dy, dw, (int)kps); break;
+      default: wgrad_mma_kernel<64, 0><<<grid, 256, 0, ST(stream)>>>(g, x, dy, dw, (int)kps); break;
+    }
   }
   TPZ_CUDA(cudaGetLastError());
   return 0;
