@@ -28,7 +28,7 @@ int tpz_device_info(int* num_sms, int* cc_major, int* cc_minor);
  *   topaz/model/features/resnet.py:101-105 (BasicConv.forward), :178-204 (ResidA.forward),
  *   topaz/model/features/basic.py:101-111, topaz/model/classifier.py:64-66,
  *   topaz/denoising/models.py:130-175 (UDenoiseNet.forward), :508-564 (UDenoiseNet3D.forward).     */
-#define TPZ_TC_MAX_KB 256
+#define TPZ_TC_MAX_KB 512
 typedef struct {
   int16_t dx, dy, dz; /* input offset of this k-block's tap (tap index * dilation), elements */
   int16_t c0;         /* first input channel of the chunk                                     */
@@ -71,6 +71,16 @@ typedef struct {
   float dot_b;
   float* dot_out;          /* [N][Do][Ho][Wo] fp32 or NULL */
   const float* dot_affine; /* optional device float[2] = (shift, scale): dot_out = dot_out*scale + shift (de-normalise) */
+  const float* oscale;     /* optional [Co]: per-output-channel multiplier of the accumulator, v = acc*oscale[c] + bias[c].  The
+                              packer divides weight rows whose fp16 image would overflow / go subnormal by a power of two and
+                              puts the factor here (exact); NULL = 1 */
+  const float* range;      /* optional device float[2] = (s, 1/s) from tpz_range_scale: the activations of this network run
+                              are stored multiplied by s (a power of two chosen from max|input|, so that fp16 cannot overflow
+                              on un-normalised micrographs).  ReLU / LeakyReLU / PReLU / max-pool networks are positively
+                              homogeneous in (input, biases): the epilogue adds bias*s, the fused dot output is multiplied by
+                              1/s.  NULL = (1, 1) */
+  int out_lo;              /* 0: fp16 output.  > 0 (strict mode): every output value v is stored as the pair hi = fp16(v) at
+                              channel c and lo = fp16(v - hi) at channel c + out_lo (22 significand bits) */
 } TpzTcConvArgs;
 
 int tpz_tc_conv(const TpzTcConvArgs* host_args, void* stream);   /* dispatches: halo-resident kernel when
@@ -85,7 +95,15 @@ int tpz_tc_conv_v2(const TpzTcConvArgs* host_args, void* stream);/* halo-residen
  *   weights fp32 [Co][kd][kh][kw], optional fused 2x max-pool (`pool` = 1/2).                        */
 int tpz_conv_first(const float* x, int N, int D, int H, int W, const float* w, const float* bias, int Co,
                    int kd, int kh, int kw, int dil, int pad, float neg_slope, int pool, tpz_half* out,
-                   int out_ld, void* stream);
+                   int out_ld, const float* range, int out_lo, void* stream);
+/* tpz_range_scale: range[0] = s, range[1] = 1/s with s a power of two chosen from max|x| (device reduction, no host
+ *   synchronisation): s = 1 when max|x| <= 64 (normalised micrographs: results bit-identical to the unscaled path),
+ *   otherwise s < 1 with max|x*s| in [4, 8).  Never > 1: the biases are scaled with the activations, so a tiny input is left
+ *   alone (its activations are bias-dominated and in range).  Non-finite input gives s = 1.  `work` is a device uint32 scratch word.
+ *   The dense kernels take `range` and keep every fp16 activation scaled by s (see TpzTcConvArgs.range), which is how an
+ *   un-normalised micrograph (|x| >> 65504) is scored without overflow; the reference's fp32/TF32 path has that range
+ *   natively (classifier.py:48-66 applies no normalisation of its own). */
+int tpz_range_scale(const float* x, long long n, float* range, unsigned* work, void* stream);
 /* tpz_conv_first_tc: the same Cin = 1 convolution (2-D, dilation 1) as ONE tcgen05 kernel: each CTA builds the im2col
  *   tile of 128 output pixels in shared memory (SWIZZLE_128B K-major, generic stores + fence.proxy.async) and multiplies
  *   it with the smem-resident weights; HBM sees only the fp32 image in and the fp16 [N][Ho][Wo][Cp] map out.
@@ -93,21 +111,24 @@ int tpz_conv_first(const float* x, int N, int D, int H, int W, const float* w, c
  *   pool = 1 fuses the MaxPool2d(2) that follows the U-Net's enc1 conv (denoising/models.py:80): out is then
  *   [N][Ho/2][Wo/2][Cp] and the full-resolution map is never written. */
 int tpz_conv_first_tc(const float* x, int B, int H, int W, const tpz_half* w_packed, const float* bias, int Cp, int k,
-                      int pad, float neg_slope, int pool, tpz_half* out, void* stream);
+                      int pad, float neg_slope, int pool, tpz_half* out, const float* range, void* stream);
 int tpz_conv_first_tc_supported(int k, int Cp);
 /* tpz_im2col_first: im2col of a single-channel 2-D image (k x k taps -> channels, zero padded to ld) so that
  *   Cin = 1 convs (first BasicConv 7x7, U-Net enc1 11x11, the raw-image slice of U-Net dec1.0) run as a
- *   1-tap tensor-core GEMM through tpz_tc_conv.  out: fp16 [N][1][Ho][Wo][ld].                       */
-int tpz_im2col_first(const float* x, int N, int H, int W, int k, int pad, tpz_half* out, int ld, void* stream);
+ *   1-tap tensor-core GEMM through tpz_tc_conv.  out: fp16 [N][1][Ho][Wo][ld].  `range`: see tpz_range_scale (taps are
+ *   stored multiplied by s).  out_lo > 0 (strict mode): the fp16 rounding residuals are stored at channel t + out_lo.     */
+int tpz_im2col_first(const float* x, int N, int H, int W, int k, int pad, tpz_half* out, int ld, const float* range,
+                     int out_lo, void* stream);
 /* tpz_im2col3d_first: the 3-D analogue ('same' padding, pad = k/2): out fp16 [N][D][H][W][ld], channel t = (dz*k+dy)*k+dx;
  *   the raw-volume slice of UDenoiseNet3D dec1.0 (denoising/models.py:555) as a second tensor-core source. */
-int tpz_im2col3d_first(const float* x, int N, int D, int H, int W, int k, int pad, tpz_half* out, int ld, void* stream);
+int tpz_im2col3d_first(const float* x, int N, int D, int H, int W, int k, int pad, tpz_half* out, int ld,
+                       const float* range, int out_lo, void* stream);
 /* tpz_conv_last: Cout = 1 conv from fp16 NDHWC to dense fp32 (classifier 1x1, classifier.py:65; U-Net
  *   dec1.4, denoising/models.py:127,505).  out = (sum + bias) * out_scale + out_shift, then, if
  *   affine_stats (device float[2] = mean,std) is given, out = out*std + mean (denoise.py:295 de-normalise).               */
 int tpz_conv_last(const tpz_half* x, int N, int D, int H, int W, int C, int ld, const float* w, float bias,
                   int kd, int kh, int kw, int dil, int pad, float out_scale, float out_shift,
-                  const float* affine_stats, float* out, void* stream);
+                  const float* affine_stats, float* out, const float* range, void* stream);
 /* tpz_conv_generic: reference-quality fp32-accumulate conv on fp16 NDHWC tensors with stride support;
  *   used for validation of tpz_tc_conv and for shapes the tensor-core kernel does not cover.
  *   weights fp32 [Co][Ci][kd][kh][kw] (reference OIHW layout). Two sources are concatenated on channels. */
@@ -119,7 +140,8 @@ int tpz_conv_generic(const tpz_half* x0, int C0, int ld0, const tpz_half* x1, in
 /* ---- pooling / resampling (F.max_pool2d/3d(2), F.interpolate(mode='nearest') + torch.cat) ----
  *   denoising/models.py:82-97 (MaxPool), :140-171 (interpolate + cat).                                */
 int tpz_maxpool2(const tpz_half* x, int N, int D, int H, int W, int C, int ld, int dims, tpz_half* out,
-                 int out_ld, void* stream);
+                 int out_ld, int lo_off, void* stream);   /* lo_off > 0 (strict mode): channels [0,C) are hi parts, [lo_off,
+                                                             lo_off+C) lo parts; the maximum is taken over hi+lo */
 int tpz_upsample_nearest(const tpz_half* x, int N, int D, int H, int W, int C, int ld, int Do, int Ho, int Wo,
                          tpz_half* out, int out_ld, int out_coff, void* stream);
 

@@ -273,11 +273,13 @@ def classifier_forward(sd: Dict, x, arch: str, units: int, filled: bool, bn: boo
 # --------------------------------------------------------------------------------------
 
 def unet_forward(sd: Dict, x) -> torch.Tensor:
-    """UDenoiseNet.forward / UDenoiseNet3D.forward (denoising/models.py:130-175, 508-564).
+    """UDenoiseNet.forward / UDenoiseNetSmall.forward / UDenoiseNet3D.forward (denoising/models.py:130-175,
+    221-244, 508-564).
 
-    Dimensionality, base/top widths are inferred from the weight shapes.  Encoder: conv(same pad)
-    + LeakyReLU(0.1) + MaxPool(2) (enc6 without pool).  Decoder: nearest-upsample to the skip's
-    size, concat [upsampled, skip], two conv+LeakyReLU; dec1: three convs, last one linear.
+    Dimensionality, depth (6 encoder stages; 4 for UDenoiseNetSmall), base/top widths are inferred from the
+    state dict.  Encoder: conv(same pad) + LeakyReLU(0.1) + MaxPool(2) (last stage without pool).  Decoder:
+    nearest-upsample to the skip's size, concat [upsampled, skip], two conv+LeakyReLU; dec1: three convs, last
+    one linear.
     """
     x = _t(x)
     nd = _t(sd['enc1.0.weight']).dim() - 2
@@ -287,14 +289,15 @@ def unet_forward(sd: Dict, x) -> torch.Tensor:
         w = _t(sd[name + '.weight'])
         return _conv(h, w, _t(sd[name + '.bias']), padding=w.shape[-1] // 2)
 
+    depth = max(i for i in range(1, 10) if f'enc{i}.0.weight' in sd)
     skips = [x]
     h = x
-    for i in range(1, 6):
+    for i in range(1, depth):
         h = pool(F.leaky_relu(cv(h, f'enc{i}.0'), 0.1), 2)
         skips.append(h)
-    h = F.leaky_relu(cv(h, 'enc6.0'), 0.1)
-    # skips = [x, p1, p2, p3, p4, p5]; dec5 joins p4, ..., dec1 joins x
-    for lvl in range(5, 0, -1):
+    h = F.leaky_relu(cv(h, f'enc{depth}.0'), 0.1)
+    # skips = [x, p1, ..., p_{depth-1}]; dec_{depth-1} joins p_{depth-2}, ..., dec1 joins x
+    for lvl in range(depth - 1, 0, -1):
         skip = skips[lvl - 1]
         h = F.interpolate(h, size=tuple(skip.shape[2:]), mode='nearest')
         h = torch.cat([h, skip], 1)

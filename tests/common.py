@@ -52,6 +52,37 @@ def rel_err(y, ref):
     return float(d.max() / max(np.abs(ref).max(), 1e-30)), float(np.linalg.norm(y - ref) / max(np.linalg.norm(ref), 1e-30))
 
 
+def rel_err_dc(y, ref):
+    """DC-free parity metric for de-normalised denoiser outputs: both are taken relative to the REFERENCE mean before the
+    SURVEY 8(c) metric is applied, i.e. max|d| / max|ref - mean(ref)| and ||d|| / ||ref - mean(ref)||.  A denoised raw
+    micrograph is mean 10, std 0.1: measured against max|ref| a 1e-3 bound would allow an error of 10 % of the signal."""
+    y = np.asarray(y, dtype=np.float64); ref = np.asarray(ref, dtype=np.float64)
+    mu = ref.mean()
+    return rel_err(y - mu, ref - mu)
+
+
+def worst_elem_rel(y, ref, floor=0.1):
+    """worst element-wise relative error on |ref| > floor (nan when no element qualifies)."""
+    y = np.asarray(y, dtype=np.float64); ref = np.asarray(ref, dtype=np.float64)
+    m = np.abs(ref) > floor
+    return float((np.abs(y - ref)[m] / np.abs(ref)[m]).max()) if m.any() else float('nan')
+
+
+def check_parity(y, ref, tol, what='', dc_free=False):
+    """Assert the SURVEY 8(c) metric (max-norm and rel-L2 <= tol) and print it with the worst element-wise relative
+    error on |ref| > 0.1 (reported, not gated: single near-zero-crossing elements dominate it)."""
+    assert np.asarray(y).shape == np.asarray(ref).shape, (np.asarray(y).shape, np.asarray(ref).shape)
+    mx, l2 = (rel_err_dc if dc_free else rel_err)(y, ref)
+    if dc_free:
+        mu = float(np.asarray(ref, dtype=np.float64).mean())
+        we = worst_elem_rel(np.asarray(y, dtype=np.float64) - mu, np.asarray(ref, dtype=np.float64) - mu)
+    else:
+        we = worst_elem_rel(y, ref)
+    print(f'parity[{what}]{" dc-free" if dc_free else ""}: max-rel {mx:.2e} rel-L2 {l2:.2e} worst-elem(|ref|>0.1) {we:.2e} (tol {tol:g})')
+    assert mx < tol and l2 < tol, (what, mx, l2)
+    return mx, l2
+
+
 def dropout_masks_of(g):
     """keep-masks of the reference's nn.Dropout layers stored bit-packed in a golden (NCHW, bool)."""
     out = []

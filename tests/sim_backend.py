@@ -41,11 +41,44 @@ def _gather_lattice(src, org, d, qshape, c0, kc, lat, ph, latz=1, phz=0):
     return out
 
 
-def tc_conv(plan, srcs, out_shape, out=None, res=None, res_org=(0, 0, 0), dot_out=None, out_coff=0, tag=None, dot_affine=None):
+def _split16(v):
+    """(hi, lo) fp16 pair of an fp32 tensor: hi = fp16(v), lo = fp16(v - hi)"""
+    hi = v.half()
+    return hi, (v - hi.float()).half()
+
+
+def _store(out, sl, v, plan, out_coff):
+    """epilogue store: fp16, or the (hi, lo) halves in strict mode"""
+    if plan.split_out:
+        hi, lo = _split16(v)
+        out[sl + (slice(0, plan.Co),)] = hi
+        out[sl + (slice(plan.Co, 2 * plan.Co),)] = lo
+    else:
+        out[sl + (slice(out_coff, out_coff + plan.Co),)] = v.half()
+
+
+def range_scale(x):
+    """tpz_range_scale: (s, 1/s), s a power of two <= 1; 1 when max|x| <= 64"""
+    amax = float(x.abs().max()) if x.numel() else 0.0
+    s = 1.0
+    if math.isfinite(amax) and amax > 64.0:
+        m, e = math.frexp(np.float32(amax))
+        s = math.ldexp(1.0, max(-100, 3 - e))
+    return torch.tensor([s, 1.0 / s], dtype=torch.float32)
+
+
+def _rs(rng):
+    return (float(rng[0]), float(rng[1])) if rng is not None else (1.0, 1.0)
+
+
+def tc_conv(plan, srcs, out_shape, out=None, res=None, res_org=(0, 0, 0), dot_out=None, out_coff=0, tag=None, dot_affine=None,
+            rng=None):
     N, Do, Ho, Wo = out_shape
+    s_, inv_s = _rs(rng)
+    osc = plan.oscale if plan.oscale is not None else 1.0
     mixed = plan.lattice_z > 1 or plan.phase_sel != 0 or any(l not in (0, plan.lattice) for l in (plan.lats or [])) or any(not p for p in (plan.phases or []))
     if not mixed:
-        return _tc_conv_dense(plan, srcs, out_shape, out, res, res_org, dot_out, out_coff, dot_affine)
+        return _tc_conv_dense(plan, srcs, out_shape, out, res, res_org, dot_out, out_coff, dot_affine, rng)
     L = plan.lattice
     phases = [plan.phase_sel - 1] if plan.phase_sel else list(range(L * L))
     assert res is None and dot_out is None
@@ -62,95 +95,115 @@ def tc_conv(plan, srcs, out_shape, out=None, res=None, res_org=(0, 0, 0), dot_ou
             A = _gather_lattice(srcs[si], plan.orgs[si], (dx, dy, dz), (N, QD, QH, QW), c0, plan.KC, lat,
                                 (phx if p_on else 0, phy if p_on else 0), latz, pz if p_on else 0)
             acc += A @ plan.weights[kb].float().t()
-        v = acc + plan.bias
+        v = acc * osc + plan.bias * s_
         v = torch.where(v > 0, v, v * plan.neg_slope)
-        out[:, pz::Lz, phy::L, phx::L, out_coff:out_coff + plan.Co] = v.half()
+        _store(out, (slice(None), slice(pz, None, Lz), slice(phy, None, L), slice(phx, None, L)), v, plan, out_coff)
 
 
-def _tc_conv_dense(plan, srcs, out_shape, out, res, res_org, dot_out, out_coff, dot_affine):
+def _tc_conv_dense(plan, srcs, out_shape, out, res, res_org, dot_out, out_coff, dot_affine, rng=None):
     N, Do, Ho, Wo = out_shape
+    s_, inv_s = _rs(rng)
+    osc = plan.oscale if plan.oscale is not None else 1.0
     acc = torch.zeros((N, Do, Ho, Wo, plan.Co), dtype=torch.float32)
     for kb, (dx, dy, dz, c0, si) in enumerate(plan.kblocks):
         A = _gather(srcs[si], plan.orgs[si], (dx, dy, dz), out_shape, c0, plan.KC)
         acc += A @ plan.weights[kb].float().t()
-    v = acc + plan.bias
+    v = acc * osc + plan.bias * s_
     if res is not None:
         r = res[:, res_org[2]:res_org[2] + Do, res_org[1]:res_org[1] + Ho, res_org[0]:res_org[0] + Wo, :plan.Co].float()
         v = v + (r * plan.res_scale if plan.res_scale is not None else r)
     v = torch.where(v > 0, v, v * plan.neg_slope)
     if dot_out is not None:
-        dv = (v * plan.dot_w).sum(-1) + plan.dot_b
+        dv = (v * plan.dot_w).sum(-1) * inv_s + plan.dot_b
         if dot_affine is not None:
             dv = dv * dot_affine[1] + dot_affine[0]
         dot_out.copy_(dv)
     if out is not None:
-        out[..., out_coff:out_coff + plan.Co] = v.half()
+        _store(out, (Ellipsis,), v, plan, out_coff)
 
 
-def conv_first(x, w, bias, dil, pad, neg_slope, out_ld):
+def conv_first(x, w, bias, dil, pad, neg_slope, out_ld, rng=None, split=False):
     N, D, H, W = x.shape
     Co, kd, kh, kw = w.shape
+    s_, _ = _rs(rng)
+    x = x * s_
+    bias = bias * s_ if bias is not None else None
     if kd > 1:
         y = F.conv3d(x[:, None], w[:, None], bias, dilation=dil, padding=pad)
     else:
         y = F.conv2d(x.reshape(N * D, 1, H, W), w, bias, dilation=dil, padding=pad)
         y = y.reshape(N, D, Co, y.shape[-2], y.shape[-1]).permute(0, 2, 1, 3, 4)
-    y = torch.where(y > 0, y, y * neg_slope)
-    out = torch.zeros((N,) + tuple(y.shape[2:]) + (out_ld,), dtype=torch.float16)
-    out[..., :Co] = y.permute(0, 2, 3, 4, 1).half()
+    y = torch.where(y > 0, y, y * neg_slope).permute(0, 2, 3, 4, 1)
+    out = torch.zeros(tuple(y.shape[:4]) + (2 * out_ld if split else out_ld,), dtype=torch.float16)
+    hi, lo = _split16(y)
+    out[..., :Co] = hi
+    if split:
+        out[..., out_ld:out_ld + Co] = lo
     return out
 
 
-def conv_first_tc(x, w_packed, bias, k, pad, neg_slope, pool=False):
+def conv_first_tc(x, w_packed, bias, k, pad, neg_slope, pool=False, rng=None):
     """tpz_conv_first_tc: fp16 taps x fp16 weights, fp32 accumulate, bias + activation, fp16 NHWC out."""
     kb, cp, _ = w_packed.shape
     w = w_packed.float().permute(1, 0, 2).reshape(cp, kb * 64)[:, :k * k].reshape(cp, 1, k, k)
-    y = F.conv2d(x.half().float()[:, None], w, bias.float(), padding=pad)
+    s_, _ = _rs(rng)
+    y = F.conv2d((x * s_).half().float()[:, None], w, bias.float() * s_, padding=pad)
     y = torch.where(y > 0, y, y * neg_slope).half().float()
     if pool:
         y = F.max_pool2d(y, 2)
     return y.permute(0, 2, 3, 1)[:, None].contiguous().half()
 
 
-def im2col3d_first(x, k, ld):
+def im2col3d_first(x, k, ld, rng=None, split=False):
     N, D, H, W = x.shape
     p = k // 2
-    xp = F.pad(x, (p, p, p, p, p, p))
-    out = torch.zeros((N, D, H, W, ld), dtype=torch.float16)
+    xp = F.pad(x * _rs(rng)[0], (p, p, p, p, p, p))
+    out = torch.zeros((N, D, H, W, 2 * ld if split else ld), dtype=torch.float16)
     t = 0
     for dz in range(k):
         for dy in range(k):
             for dx in range(k):
-                out[..., t] = xp[:, dz:dz + D, dy:dy + H, dx:dx + W].half()
+                hi, lo = _split16(xp[:, dz:dz + D, dy:dy + H, dx:dx + W])
+                out[..., t] = hi
+                if split:
+                    out[..., ld + t] = lo
                 t += 1
     return out
 
 
-def im2col_first(x, k, pad, ld):
+def im2col_first(x, k, pad, ld, rng=None, split=False):
     N, H, W = x.shape
-    xp = F.pad(x, (pad, pad, pad, pad))
+    xp = F.pad(x * _rs(rng)[0], (pad, pad, pad, pad))
     Ho, Wo = H + 2 * pad - (k - 1), W + 2 * pad - (k - 1)
-    out = torch.zeros((N, 1, Ho, Wo, ld), dtype=torch.float16)
+    out = torch.zeros((N, 1, Ho, Wo, 2 * ld if split else ld), dtype=torch.float16)
     for r in range(k):
         for s in range(k):
-            out[:, 0, :, :, r * k + s] = xp[:, r:r + Ho, s:s + Wo].half()
+            hi, lo = _split16(xp[:, r:r + Ho, s:s + Wo])
+            out[:, 0, :, :, r * k + s] = hi
+            if split:
+                out[:, 0, :, :, ld + r * k + s] = lo
     return out
 
 
-def conv_last(x, c_real, w, bias, kdhw, dil, pad, stats=None, out_scale=1.0, out_shift=0.0):
+def conv_last(x, c_real, w, bias, kdhw, dil, pad, stats=None, out_scale=1.0, out_shift=0.0, rng=None):
     N, D, H, W, ld = x.shape
     kd, kh, kw = kdhw
     C = w.shape[1]
     wt = w.t().reshape(1, C, kd, kh, kw)
     xi = x[..., :C].float().permute(0, 4, 1, 2, 3)
     y = F.conv3d(xi, wt, None, dilation=dil, padding=(pad if kd > 1 else 0, pad, pad))[:, 0]
-    y = (y + bias) * out_scale + out_shift
+    y = (y * _rs(rng)[1] + bias) * out_scale + out_shift
     if stats is not None:
         y = y * stats[1] + stats[0]
     return y
 
 
-def maxpool2(x, dims):
+def maxpool2(x, dims, split=False):
+    if split:
+        C = x.shape[-1] // 2
+        v = x[..., :C].float() + x[..., C:].float()
+        y = F.max_pool3d(v.permute(0, 4, 1, 2, 3), (2 if dims == 3 else 1, 2, 2)).permute(0, 2, 3, 4, 1)
+        return torch.cat(_split16(y), dim=-1).contiguous()
     xi = x.float().permute(0, 4, 1, 2, 3)
     y = F.max_pool3d(xi, (2 if dims == 3 else 1, 2, 2))
     return y.permute(0, 2, 3, 4, 1).half().contiguous()
@@ -228,7 +281,7 @@ def to_device(t):
 
 @contextlib.contextmanager
 def patched():
-    names = ['tc_conv', 'conv_first', 'conv_first_tc', 'im2col_first', 'im2col3d_first', 'filter_f32', 'conv_last', 'maxpool2', 'upsample_nearest', 'meanstd', 'affine',
+    names = ['tc_conv', 'range_scale', 'conv_first', 'conv_first_tc', 'im2col_first', 'im2col3d_first', 'filter_f32', 'conv_last', 'maxpool2', 'upsample_nearest', 'meanstd', 'affine',
              'gemm_f32', 'gmm_sums', 'select_hist', 'to_device']
     saved = {n: getattr(ops, n) for n in names}
     saved['require_cuda'] = ops.require_cuda

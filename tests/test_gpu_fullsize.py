@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from common import gold, weights_of, rel_err
+from common import gold, weights_of, rel_err, rel_err_dc, check_parity
 from oracle import topaz_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -69,8 +69,8 @@ def test_unet_4096_patched_denoise_one_patch_vs_oracle():
     assert y.shape == (S, S) and np.isfinite(y).all()
     ref = O.denoise_call(sd, x[:ps + pad, :ps + pad])[:ps, :ps]
     got = y[:ps, :ps]
-    mx, l2 = rel_err(got, ref)
-    assert mx < TOL and l2 < TOL, (mx, l2)
+    # the denoised raw-like image is mean 10 / std 0.1: the DC-free metric holds the error to 1e-3 of the denoised SIGNAL
+    check_parity(got, ref, TOL, 'cfg3 patch (0,0) of the 4096^2 patched denoise', dc_free=True)
     yd = dn.denoise_patches_device(torch.from_numpy(x).cuda(), ps, pad).cpu().numpy()
     assert np.array_equal(yd, y)
 

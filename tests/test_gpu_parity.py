@@ -1,12 +1,16 @@
 """-m gpu parity tests: the CUDA path (through the drop-in modules -> ctypes -> C ABI) against the
-reference goldens and the CPU oracle.  Tolerance: north-star 1e-3 (max|d|/max|ref| and rel-L2) for the
-pretrained-weight cases; 3e-3 for He-random seeded weights (operand rounding 2^-11 amplified by depth)."""
+reference goldens and the CPU oracle.  Tolerance: north-star 1e-3 (max|d|/max|ref| and rel-L2) for every
+network with the reference's PRETRAINED weights in the default precision; He-random seeded weights amplify the
+2^-11 operand rounding of the default (fast) mode through 9-16 layers to 1-3e-3 -- those cases are held to 3e-3
+here and to 1e-3 in strict mode by tests/test_gpu_parity_r2.py::test_strict_mode_*.  De-normalised denoiser
+outputs (mean 10, std 0.1) use the DC-free form of the metric (common.rel_err_dc).  Every check prints the
+metric and the worst element-wise relative error on |ref| > 0.1 (run pytest with -s / -rP to see them)."""
 import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
 
-from common import gold, weights_of, seeded_state, rel_err
+from common import gold, weights_of, seeded_state, rel_err, check_parity
 from common_shapes import classifier_shapes, unet_shapes
 from oracle import topaz_oracle as O
 
@@ -28,11 +32,10 @@ def _classifier(arch, units, scaling=1, bn=False):
     return LinearClassifier(get_feature_extractor(arch, **kw))
 
 
-def _check(y, ref, tol):
-    mx, l2 = rel_err(y, ref)
-    assert np.asarray(y).shape == np.asarray(ref).shape
-    assert mx < tol and l2 < tol, (mx, l2)
-    return mx, l2
+def _check(y, ref, tol, what='', dc_free=False):
+    import inspect
+    what = what or inspect.stack()[1].function
+    return check_parity(y, ref, tol, what, dc_free=dc_free)
 
 
 def test_native_library_loaded_and_device_is_sm100():
@@ -160,10 +163,11 @@ def test_unet_pretrained_forward_and_pipeline():
     with torch.no_grad():
         y = m(torch.from_numpy(g['x']).cuda()).cpu().numpy()
         yo = m(torch.from_numpy(g['xo']).cuda()).cpu().numpy()
-    _check(y, g['y'], 2e-3); _check(yo, g['yo'], 2e-3)
+    _check(y, g['y'], TOL); _check(yo, g['yo'], TOL)
     dn = Denoise(m)
-    _check(dn._denoise(g['img'].copy()), g['y_call'], TOL)      # relative to the de-normalised image scale
-    _check(dn.denoise(g['img'].copy(), patch_size=64, padding=24), g['y_pat'], TOL)
+    # de-normalised outputs are mean 10 / std 0.1: DC-free metric (relative to the denoised SIGNAL, not to its offset)
+    _check(dn._denoise(g['img'].copy()), g['y_call'], TOL, dc_free=True)
+    _check(dn.denoise(g['img'].copy(), patch_size=64, padding=24), g['y_pat'], TOL, dc_free=True)
 
 
 def test_unet_seeded_2d_and_3d():
@@ -181,7 +185,7 @@ def test_unet_seeded_2d_and_3d():
     _check(y, g['y'], TOL_SEEDED)
     d3 = Denoise3D(m)
     yt = d3.denoise(g['tomo'].copy(), patch_size=16, padding=8, verbose=False)
-    _check(yt, g['y_tomo'], TOL_SEEDED)
+    _check(yt, g['y_tomo'], TOL_SEEDED, dc_free=True)
     # patch sharding (multi-GPU partition of the patch list) reassembles to the same volume
     n = int(np.prod([int(np.ceil(s / 16)) for s in g['tomo'].shape]))
     parts = [d3.denoise(g['tomo'].copy(), 16, 8, verbose=False, patch_range=(a, b)) for a, b in ((0, n // 2), (n // 2, n))]
@@ -217,7 +221,7 @@ def test_unet_edge_sizes(shape):
     with torch.no_grad():
         y = m(torch.from_numpy(x).cuda()).cpu().numpy()
     ref = O.unet_forward(sd, x).numpy()
-    _check(y, ref, 2e-3)
+    _check(y, ref, TOL)
 
 
 def test_variants_agree_v1_v2():
@@ -260,10 +264,10 @@ def test_denoise_image_pipeline():
     mic = g['img']
     mu, std = mic.mean(), mic.std()
     ref = std * O.denoise(sd, (mic - mu) / std, patch_size=64, padding=24) + mu
-    _check(denoise_image(mic.copy(), [dn], patch_size=64, padding=24), ref, TOL)
+    _check(denoise_image(mic.copy(), [dn], patch_size=64, padding=24), ref, TOL, dc_free=True)
     refn = O.denoise(sd, (mic - mu) / std, patch_size=64, padding=24)
     refn = (refn - refn.mean()) / refn.std()
-    _check(denoise_image(mic.copy(), [dn, dn], patch_size=64, padding=24, normalize=True), refn, 2e-3)
+    _check(denoise_image(mic.copy(), [dn, dn], patch_size=64, padding=24, normalize=True), refn, TOL)
 
 
 @pytest.mark.parametrize('H,W,r,thr', [(20, 24, 3, -np.inf), (25, 25, 2, -np.inf), (40, 6, 3, -np.inf), (6, 40, 3, -np.inf),

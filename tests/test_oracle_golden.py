@@ -230,3 +230,40 @@ def test_downsample_and_gmm_normalize_vs_reference_golden():
         assert abs(mu - g[f'n.{tag}.mu']) < 1e-5 * abs(mu) and abs(std - g[f'n.{tag}.std']) < 1e-4 * std, tag
         assert abs(pi - g[f'n.{tag}.pi']) < 1e-4
         assert np.abs(y - g[f'n.{tag}.y']).max() < 1e-3
+
+
+# ---------------------------------------------------------------- round-2 fixtures (tools/make_goldens_r2.py)
+def test_resnet16_u64_pretrained():
+    """`topaz extract`'s default model (commands/extract.py:18 -> factory.py:34-36) with its packaged weights."""
+    g = gold('resnet16_u64_pretrained'); sd = weights_of(g)
+    assert O.resnet_width(O.resnet_spec('resnet16', 64)) == int(g['width'])
+    _close(O.classifier_forward(sd, g['x'], 'resnet16', 64, filled=True).numpy(), g['y_dense'])
+    _close(O.classifier_forward(sd, g['crops'], 'resnet16', 64, filled=False).numpy(), g['y_crops'])
+
+
+def test_conv127_seeded():
+    from common_shapes import classifier_shapes
+    g = gold('cls_conv127_u16x2')
+    shapes = classifier_shapes('conv127', 16, 2, True)
+    assert list(shapes.keys()) == [str(k) for k in g['keys']]
+    sd = seeded_state(shapes, int(g['seed']))
+    _close(O.classifier_forward(sd, g['xc'], 'conv127', 16, False, True, 2).numpy(), g['yc'])
+    _close(O.classifier_forward(sd, g['xd'], 'conv127', 16, True, True, 2).numpy(), g['yd'])
+
+
+def test_unet_small_pretrained():
+    """UDenoiseNetSmall (denoising/models.py:178-244) with the packaged `unet-small` weights."""
+    g = gold('unet_small_pretrained'); sd = weights_of(g)
+    _close(O.unet_forward(sd, g['x']).numpy(), g['y'])
+    _close(O.unet_forward(sd, g['xo']).numpy(), g['yo'])
+    _close(O.denoise_call(sd, g['img']), g['y_call'])
+    _close(O.denoise(sd, g['img'], patch_size=64, padding=24), g['y_pat'])
+
+
+def test_unet3d_pretrained_10a_small_block_and_tomogram():
+    """UDenoiseNet3D with the packaged `unet-3d-10a` weights (denoising/models.py:452-564, 576-578): a 32^3 block and
+    Denoise3D.denoise on a 70x50x64 tomogram.  (The 192^3 patch of the fixture is checked against the CUDA path on the GPU;
+    the oracle needs ~20 s for it, see test_unet3d_pretrained_192_patch_oracle_windows.)"""
+    g = gold('unet3d_pretrained_10a'); sd = weights_of(g)
+    _close(O.unet_forward(sd, g['x32']).numpy(), g['y32'])
+    _close(O.denoise3d(sd, g['tomo'], 32, 16), g['y_tomo'], 5e-5)

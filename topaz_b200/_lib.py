@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libtopaz_b200.so')
-TPZ_TC_MAX_KB = 256
+TPZ_TC_MAX_KB = 512
 
 
 class TcKBlock(C.Structure):
@@ -31,6 +31,7 @@ class TpzTcConvArgs(C.Structure):
         ('res_ld', C.c_int), ('res_D', C.c_int), ('res_H', C.c_int), ('res_W', C.c_int), ('res_org', C.c_int * 3),
         ('out', C.c_void_p), ('out_ld', C.c_int), ('out_coff', C.c_int),
         ('dot_w', C.c_void_p), ('dot_b', C.c_float), ('dot_out', C.c_void_p), ('dot_affine', C.c_void_p),
+        ('oscale', C.c_void_p), ('range', C.c_void_p), ('out_lo', C.c_int),
     ]
 
 
@@ -43,19 +44,20 @@ _PROTOS = {
     'tpz_tc_conv': (_I, [C.POINTER(TpzTcConvArgs), _P]),
     'tpz_tc_conv_v1': (_I, [C.POINTER(TpzTcConvArgs), _P]),
     'tpz_tc_conv_v2': (_I, [C.POINTER(TpzTcConvArgs), _P]),
-    'tpz_conv_first': (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _I, _P]),
-    'tpz_im2col_first': (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P]),
-    'tpz_conv_last': (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _F, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P]),
+    'tpz_conv_first': (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _I, _P, _I, _P]),
+    'tpz_range_scale': (_I, [_P, _LL, _P, _P, _P]),
+    'tpz_im2col_first': (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P]),
+    'tpz_conv_last': (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _F, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P]),
     'tpz_conv_generic': (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F,
                               _P, _I, _I, _P, _I, _I, _I, _I, _P]),
-    'tpz_maxpool2': (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P]),
+    'tpz_maxpool2': (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P]),
     'tpz_upsample_nearest': (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P]),
     'tpz_meanstd': (_I, [_P, _LL, _I, _P, _P, _P]),
     'tpz_affine': (_I, [_P, _LL, _P, _I, _P, _P]),
     'tpz_sample_crops': (_I, [_I, C.c_ulonglong, C.c_ulonglong, _P, _P, _P, _P, _I, _P, _I, _P, _F, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     'tpz_make_crops': (_I, [_I, _I, _I, _P, _P, _P, _P, _P]),
-    'tpz_im2col3d_first': (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _I, _P]),
-    'tpz_conv_first_tc': (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _I, _F, _I, _P, _P]),
+    'tpz_im2col3d_first': (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P]),
+    'tpz_conv_first_tc': (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _I, _F, _I, _P, _P, _P]),
     'tpz_conv_first_tc_supported': (_I, [_I, _I]),
     'tpz_lab_umma_pair': (_I, [_P, _P, _I, _I, _P, _P, _P]),
     'tpz_gemm_f32': (_I, [_P, _LL, _I, _P, _I, _P, _P]),

@@ -19,7 +19,8 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
                                                          const float* __restrict__ w, const float* __restrict__ bias,
                                                          int Co, int kd, int kh, int kw, int dil, int pad,
                                                          float slope, __half* __restrict__ out, int out_ld, int Do,
-                                                         int Ho, int Wo, int CoPad) {
+                                                         int Ho, int Wo, int CoPad, const float* __restrict__ range,
+                                                         int out_lo) {
   extern __shared__ float sm[];
   const int tw = FT_W + (kw - 1) * dil, th = FT_H + (kh - 1) * dil;
   float* s_in = sm;                       // [kd][th][tw]
@@ -28,6 +29,7 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
   const int plane = blockIdx.z;
   const int n = plane / Do, z = plane - n * Do;
   const int x0 = blockIdx.x * FT_W, y0 = blockIdx.y * FT_H;
+  const float rs = range ? range[0] : 1.f;      // range guard (tpz_range_scale): input and bias scaled by a power of two
 
   for (int i = threadIdx.x; i < ntaps * CoPad; i += 256) {
     const int t = i / CoPad, c = i - t * CoPad;
@@ -39,7 +41,7 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
     const int gz = z - pad * (kd > 1) + q * dil, gy = y0 - pad + yy, gx = x0 - pad + xx;
     float v = 0.f;
     if (gz >= 0 && gz < D && gy >= 0 && gy < H && gx >= 0 && gx < W)
-      v = x[(((size_t)n * D + gz) * H + gy) * W + gx];
+      v = x[(((size_t)n * D + gz) * H + gy) * W + gx] * rs;
     s_in[i] = v;
   }
   __syncthreads();
@@ -82,19 +84,26 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
         const int gx = x0 + lx + pxi;
         if (gx < Wo) {
           __half* o = out + ((((size_t)n * Do + z) * Ho + gy) * Wo + gx) * out_ld + cg;
-          uint4 u[2];
+          uint4 u[2], ul[2];
           __half2* h = reinterpret_cast<__half2*>(u);
+          __half2* hl = reinterpret_cast<__half2*>(ul);
 #pragma unroll
           for (int c = 0; c < FCG; c += 2) {
-            const float b0 = (cg + c < Co && bias) ? bias[cg + c] : 0.f;
-            const float b1 = (cg + c + 1 < Co && bias) ? bias[cg + c + 1] : 0.f;
+            const float b0 = (cg + c < Co && bias) ? bias[cg + c] * rs : 0.f;
+            const float b1 = (cg + c + 1 < Co && bias) ? bias[cg + c + 1] * rs : 0.f;
             float v0 = act(acc[pxi][c] + b0, slope), v1 = act(acc[pxi][c + 1] + b1, slope);
             if (cg + c >= Co) v0 = 0.f;
             if (cg + c + 1 >= Co) v1 = 0.f;
             h[c / 2] = __floats2half2_rn(v0, v1);
+            const float2 hf = __half22float2(h[c / 2]);
+            hl[c / 2] = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
           }
           reinterpret_cast<uint4*>(o)[0] = u[0];
           reinterpret_cast<uint4*>(o)[1] = u[1];
+          if (out_lo > 0) {                         // strict mode: fp16 rounding residuals at channel c + out_lo
+            reinterpret_cast<uint4*>(o + out_lo)[0] = ul[0];
+            reinterpret_cast<uint4*>(o + out_lo)[1] = ul[1];
+          }
         }
       }
     }
@@ -107,8 +116,11 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
 // Block = 32x8 output pixels; the (8+k-1) x (32+k-1) input patch is staged in shared memory.
 // -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) im2col_first_kernel(const float* __restrict__ x, int N, int H, int W, int k, int pad,
-                                                           __half* __restrict__ out, int ld, int Ho, int Wo) {
+                                                           __half* __restrict__ out, int ld, int Ho, int Wo,
+                                                           const float* __restrict__ range, int out_lo) {
   extern __shared__ float sm_i2c[];
+  const float rs = range ? range[0] : 1.f;
+  const int old = out_lo > 0 ? 2 * ld : ld;       // channel stride of the output tensor (strict mode: hi | lo halves)
   const int tw = 32 + k - 1, th = 8 + k - 1;
   int* s_off = reinterpret_cast<int*>(sm_i2c + tw * th);      // tap -> offset inside the patch (or -1 for zero padding)
   const int n = blockIdx.z, x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
@@ -117,7 +129,7 @@ __global__ void __launch_bounds__(256) im2col_first_kernel(const float* __restri
   for (int i = threadIdx.x; i < tw * th; i += 256) {
     const int yy = i / tw, xx = i - yy * tw;
     const int gy = y0 - pad + yy, gx = x0 - pad + xx;
-    sm_i2c[i] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? x[((size_t)n * H + gy) * W + gx] : 0.f;
+    sm_i2c[i] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? x[((size_t)n * H + gy) * W + gx] * rs : 0.f;
   }
   __syncthreads();
   // consecutive threads write consecutive 16-byte chunks of a pixel's channel vector -> 512 B contiguous per warp store
@@ -129,14 +141,20 @@ __global__ void __launch_bounds__(256) im2col_first_kernel(const float* __restri
     const int gx = x0 + lx, gy = y0 + ly;
     if (gx >= Wo || gy >= Ho) continue;
     const float* bp = sm_i2c + ly * tw + lx;
-    uint4 u;
+    uint4 u, ul;
     __half2* h = reinterpret_cast<__half2*>(&u);
+    __half2* hl = reinterpret_cast<__half2*>(&ul);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int o0 = s_off[c + 2 * e], o1 = s_off[c + 2 * e + 1];
-      h[e] = __floats2half2_rn(o0 >= 0 ? bp[o0] : 0.f, o1 >= 0 ? bp[o1] : 0.f);
+      const float f0 = o0 >= 0 ? bp[o0] : 0.f, f1 = o1 >= 0 ? bp[o1] : 0.f;
+      h[e] = __floats2half2_rn(f0, f1);
+      const float2 hf = __half22float2(h[e]);
+      hl[e] = __floats2half2_rn(f0 - hf.x, f1 - hf.y);
     }
-    *reinterpret_cast<uint4*>(out + (((size_t)n * Ho + gy) * Wo + gx) * ld + c) = u;
+    __half* op = out + (((size_t)n * Ho + gy) * Wo + gx) * old + c;
+    *reinterpret_cast<uint4*>(op) = u;
+    if (out_lo > 0) *reinterpret_cast<uint4*>(op + out_lo) = ul;
   }
 }
 
@@ -149,8 +167,10 @@ __global__ void __launch_bounds__(256) im2col_first_kernel(const float* __restri
 // -------------------------------------------------------------------------------------------------
 template <int KT>   // KT > 0: compile-time kernel size (tap offsets become constants); KT = 0: runtime k
 __global__ void im2col3d_first_kernel(const float* __restrict__ x, int N, int D, int H, int W, int k_rt, int pad,
-                                      __half* __restrict__ out, int ld) {
+                                      __half* __restrict__ out, int ld, const float* __restrict__ range, int out_lo) {
   const int k = KT > 0 ? KT : k_rt;
+  const float rs = range ? range[0] : 1.f;
+  const int old = out_lo > 0 ? 2 * ld : ld;
   const int pieces = ld >> 4;
   const size_t total = (size_t)N * D * H * W * pieces;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -163,7 +183,7 @@ __global__ void im2col3d_first_kernel(const float* __restrict__ x, int N, int D,
   const int n = (int)(v / D);
   const int taps = k * k * k;
   const float* vol = x + (size_t)n * D * H * W;
-  uint32_t pk[8];
+  uint32_t pk[8], pl[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     float f[2];
@@ -174,15 +194,19 @@ __global__ void im2col3d_first_kernel(const float* __restrict__ x, int N, int D,
       if (t < taps) {
         const int dx = t % k, dy = (t / k) % k, dz = t / (k * k);
         const int ix = gx + dx - pad, iy = gy + dy - pad, iz = gz + dz - pad;
-        if (ix >= 0 && ix < W && iy >= 0 && iy < H && iz >= 0 && iz < D) val = __ldg(vol + ((size_t)iz * H + iy) * W + ix);
+        if (ix >= 0 && ix < W && iy >= 0 && iy < H && iz >= 0 && iz < D) val = __ldg(vol + ((size_t)iz * H + iy) * W + ix) * rs;
       }
       f[h] = val;
     }
     const __half2 hh = __floats2half2_rn(f[0], f[1]);
     pk[e] = *reinterpret_cast<const uint32_t*>(&hh);
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(f[0] - hf.x, f[1] - hf.y);
+    pl[e] = *reinterpret_cast<const uint32_t*>(&ll);
   }
-  ptx::st_global_256(out + ((((size_t)n * D + gz) * H + gy) * W + gx) * ld + piece * 16, pk[0], pk[1], pk[2], pk[3], pk[4],
-                     pk[5], pk[6], pk[7]);
+  __half* op = out + ((((size_t)n * D + gz) * H + gy) * W + gx) * old + piece * 16;
+  ptx::st_global_256(op, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+  if (out_lo > 0) ptx::st_global_256(op + out_lo, pl[0], pl[1], pl[2], pl[3], pl[4], pl[5], pl[6], pl[7]);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -191,7 +215,7 @@ __global__ void im2col3d_first_kernel(const float* __restrict__ x, int N, int D,
 __global__ void conv_last_kernel(const __half* __restrict__ x, int N, int D, int H, int W, int C, int ld,
                                  const float* __restrict__ w /*[taps][C]*/, float bias, int kd, int kh, int kw,
                                  int dil, int pad, float oscale, float oshift, const float* __restrict__ stats,
-                                 float* __restrict__ out) {
+                                 float* __restrict__ out, const float* __restrict__ range) {
   const size_t total = (size_t)N * D * H * W;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -226,7 +250,7 @@ __global__ void conv_last_kernel(const __half* __restrict__ x, int N, int D, int
       }
     }
   }
-  float v = (acc + bias) * oscale + oshift;
+  float v = (fmaf(acc, range ? range[1] : 1.f, bias)) * oscale + oshift;      // undo the range scale (power of two: exact)
   if (stats) v = v * stats[1] + stats[0];
   out[idx] = v;
 }
@@ -243,7 +267,8 @@ template <int C, int K>
 __global__ void __launch_bounds__(128) conv_last_tiled_kernel(const __half* __restrict__ x, int N, int H, int W, int ld,
                                                               const float* __restrict__ w /*[K*K][C]*/, float bias,
                                                               float oscale, float oshift, const float* __restrict__ stats,
-                                                              float* __restrict__ out, int tiles_x, int tiles_y) {
+                                                              float* __restrict__ out, int tiles_x, int tiles_y,
+                                                              const float* __restrict__ range) {
   constexpr int TX = 32, TY = 16, PX = TX + K - 1, PY = TY + K - 1;
   constexpr int PSTRIDE = C * 2 + 16;          // bytes per staged pixel
   constexpr int CH = C / 8;                    // 16-byte chunks per pixel
@@ -305,7 +330,7 @@ __global__ void __launch_bounds__(128) conv_last_tiled_kernel(const __half* __re
     for (int j = 0; j < 4; ++j) {
       const int oy = y0 + tg * 4 + j;
       if (ox < W && oy < H) {
-        float v = (acc[j] + bias) * oscale + oshift;
+        float v = (fmaf(acc[j], range ? range[1] : 1.f, bias)) * oscale + oshift;
         if (stats) v = v * stats[1] + stats[0];
         out[((size_t)n * H + oy) * W + ox] = v;
       }
@@ -315,7 +340,7 @@ __global__ void __launch_bounds__(128) conv_last_tiled_kernel(const __half* __re
 
 template <int C, int K>
 static int launch_conv_last_tiled(const __half* x, int N, int H, int W, int ld, const float* w, float bias, float oscale,
-                                  float oshift, const float* stats, float* out, cudaStream_t stream) {
+                                  float oshift, const float* stats, float* out, const float* range, cudaStream_t stream) {
   constexpr int TX = 32, TY = 16;
   const int smem = (TY + K - 1) * (TX + K - 1) * (C * 2 + 16) + K * K * C * (int)sizeof(float);
   static bool configured = false;
@@ -331,7 +356,7 @@ static int launch_conv_last_tiled(const __half* x, int N, int H, int W, int ld, 
   const int per_sm = (220 * 1024) / (smem + 1024) > 8 ? 8 : (220 * 1024) / (smem + 1024);
   const long long cap = (long long)sms * (per_sm < 1 ? 1 : per_sm);
   conv_last_tiled_kernel<C, K><<<(int)(ntiles < cap ? ntiles : cap), 128, smem, stream>>>(x, N, H, W, ld, w, bias, oscale,
-                                                                                       oshift, stats, out, tiles_x, tiles_y);
+                                                                                       oshift, stats, out, tiles_x, tiles_y, range);
   TPZ_CUDA(cudaGetLastError());
   return 0;
 }
@@ -410,7 +435,7 @@ __device__ __forceinline__ uint4 hmax8(uint4 a, uint4 b) {
 }
 
 __global__ void maxpool2_kernel(const __half* __restrict__ x, int N, int D, int H, int W, int C, int ld, int dims,
-                                __half* __restrict__ out, int out_ld, int Do, int Ho, int Wo) {
+                                __half* __restrict__ out, int out_ld, int Do, int Ho, int Wo, int lo_off) {
   const int cv = C / 8;
   const size_t total = (size_t)N * Do * Ho * Wo * cv;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -422,6 +447,42 @@ __global__ void maxpool2_kernel(const __half* __restrict__ x, int N, int D, int 
   const int oz = r % Do;
   const int n = r / Do;
   const int nz = (dims == 3) ? 2 : 1;
+  if (lo_off > 0) {
+    // strict mode: values are (hi, lo) fp16 pairs; the maximum is taken over hi + lo (exact in fp32) and re-split
+    float mv[8];
+    bool first = true;
+    for (int q = 0; q < nz; ++q)
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+          const int iz = (dims == 3) ? oz * 2 + q : oz;
+          const __half* px = x + ((((size_t)n * D + iz) * H + (oy * 2 + a)) * W + (ox * 2 + b)) * ld + c;
+          const uint4 vh = *reinterpret_cast<const uint4*>(px);
+          const uint4 vl = *reinterpret_cast<const uint4*>(px + lo_off);
+          const __half2* hh = reinterpret_cast<const __half2*>(&vh);
+          const __half2* hl = reinterpret_cast<const __half2*>(&vl);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 fh = __half22float2(hh[e]), fl = __half22float2(hl[e]);
+            const float v0 = fh.x + fl.x, v1 = fh.y + fl.y;
+            mv[2 * e] = first ? v0 : fmaxf(mv[2 * e], v0);
+            mv[2 * e + 1] = first ? v1 : fmaxf(mv[2 * e + 1], v1);
+          }
+          first = false;
+        }
+    uint4 oh, ol;
+    __half2* ph = reinterpret_cast<__half2*>(&oh);
+    __half2* pl = reinterpret_cast<__half2*>(&ol);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      ph[e] = __floats2half2_rn(mv[2 * e], mv[2 * e + 1]);
+      const float2 hf = __half22float2(ph[e]);
+      pl[e] = __floats2half2_rn(mv[2 * e] - hf.x, mv[2 * e + 1] - hf.y);
+    }
+    __half* op = out + ((((size_t)n * Do + oz) * Ho + oy) * Wo + ox) * out_ld + c;
+    *reinterpret_cast<uint4*>(op) = oh;
+    *reinterpret_cast<uint4*>(op + lo_off) = ol;
+    return;
+  }
   uint4 m;
   bool first = true;
   for (int q = 0; q < nz; ++q)
@@ -549,6 +610,32 @@ __global__ void filter_f32_kernel(const float* __restrict__ x, int N, int D, int
   y[idx] = acc;
 }
 
+// range guard: max|x| -> power-of-two scale (see tpz_range_scale in the header)
+__global__ void absmax_kernel(const float* __restrict__ x, long long n, unsigned* __restrict__ work) {
+  unsigned m = 0;            // bit pattern of |x|: ordered like the value for finite x; inf / NaN compare above every finite value
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = max(m, __float_as_uint(x[i]) & 0x7fffffffu);
+  for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(~0u, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(work, m);
+}
+__global__ void range_finalize_kernel(unsigned* work, float* range) {
+  const unsigned bits = *work;
+  *work = 0;                                        // ready for the next call on the same scratch word
+  float s = 1.f;
+  if (bits != 0 && bits < 0x7f800000u) {            // finite, non-zero maximum
+    const float amax = __uint_as_float(bits);
+    if (amax > 64.f) {                               // only ever scale DOWN: biases are scaled with the activations, so scaling a
+      int e;                                         // tiny input up would blow the (then dominant) bias terms out of range
+      frexpf(amax, &e);                              // amax = m * 2^e, m in [0.5, 1)  ->  amax * 2^(3-e) in [4, 8)
+      int k = 3 - e;
+      k = k < -100 ? -100 : k;
+      s = ldexpf(1.f, k);
+    }
+  }
+  range[0] = s;
+  range[1] = 1.f / s;
+}
+
 __global__ void f32_to_f16_kernel(const float* __restrict__ x, long long n, __half* __restrict__ y) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = __float2half_rn(x[i]);
@@ -562,11 +649,12 @@ __global__ void f32_to_f16_kernel(const float* __restrict__ x, long long n, __ha
 
 extern "C" int tpz_conv_first(const float* x, int N, int D, int H, int W, const float* w, const float* bias, int Co,
                               int kd, int kh, int kw, int dil, int pad, float neg_slope, int pool, tpz_half* out,
-                              int out_ld, void* stream) {
+                              int out_ld, const float* range, int out_lo, void* stream) {
   TPZ_CHECK(pool == 1, "tpz_conv_first: fused pooling not available (pool=%d)", pool);
   TPZ_CHECK(out_ld % 16 == 0, "tpz_conv_first: out_ld=%d must be a multiple of 16", out_ld);
-  const int CoPad = out_ld;  // channels [Co, out_ld) are written as zeros (channel padding of the fp16 layout)
-  TPZ_CHECK(Co <= out_ld, "tpz_conv_first: Co=%d exceeds out_ld=%d", Co, out_ld);
+  TPZ_CHECK(out_lo >= 0 && (out_lo == 0 || 2 * out_lo == out_ld), "tpz_conv_first: out_lo=%d must be 0 or out_ld/2", out_lo);
+  const int CoPad = out_lo > 0 ? out_lo : out_ld;  // channels [Co, CoPad) are written as zeros (channel padding of the fp16 layout)
+  TPZ_CHECK(Co <= CoPad, "tpz_conv_first: Co=%d exceeds the stored channels %d", Co, CoPad);
   const int Do = (kd > 1) ? D + 2 * pad - (kd - 1) * dil : D;
   const int Ho = H + 2 * pad - (kh - 1) * dil, Wo = W + 2 * pad - (kw - 1) * dil;
   TPZ_CHECK(Do > 0 && Ho > 0 && Wo > 0, "tpz_conv_first: empty output");
@@ -576,46 +664,49 @@ extern "C" int tpz_conv_first(const float* x, int N, int D, int H, int W, const 
   TPZ_CUDA(cudaFuncSetAttribute(conv_first_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(tpz_div_up(Wo, FT_W), tpz_div_up(Ho, FT_H), N * Do);
   conv_first_kernel<<<grid, 256, smem, ST(stream)>>>(x, N, D, H, W, w, bias, Co, kd, kh, kw, dil, pad, neg_slope,
-                                                     HP(out), out_ld, Do, Ho, Wo, CoPad);
+                                                     HP(out), out_ld, Do, Ho, Wo, CoPad, range, out_lo);
   TPZ_CUDA(cudaGetLastError());
   return 0;
 }
 
-extern "C" int tpz_im2col_first(const float* x, int N, int H, int W, int k, int pad, tpz_half* out, int ld, void* stream) {
+extern "C" int tpz_im2col_first(const float* x, int N, int H, int W, int k, int pad, tpz_half* out, int ld, const float* range,
+                                int out_lo, void* stream) {
+  TPZ_CHECK(out_lo == 0 || out_lo == ld, "tpz_im2col_first: out_lo=%d must be 0 or ld", out_lo);
   TPZ_CHECK(k >= 1 && k * k <= ld && ld % 8 == 0, "tpz_im2col_first: k=%d taps do not fit ld=%d", k, ld);
   const int Ho = H + 2 * pad - (k - 1), Wo = W + 2 * pad - (k - 1);
   TPZ_CHECK(Ho > 0 && Wo > 0, "tpz_im2col_first: empty output");
   TPZ_CHECK((ld & (ld - 1)) == 0, "tpz_im2col_first: ld=%d must be a power of two", ld);
   const size_t smem = (size_t)(32 + k - 1) * (8 + k - 1) * sizeof(float) + (size_t)ld * sizeof(int);
   dim3 grid(tpz_div_up(Wo, 32), tpz_div_up(Ho, 8), N);
-  im2col_first_kernel<<<grid, 256, smem, ST(stream)>>>(x, N, H, W, k, pad, HP(out), ld, Ho, Wo);
+  im2col_first_kernel<<<grid, 256, smem, ST(stream)>>>(x, N, H, W, k, pad, HP(out), ld, Ho, Wo, range, out_lo);
   TPZ_CUDA(cudaGetLastError());
   return 0;
 }
 
 extern "C" int tpz_im2col3d_first(const float* x, int N, int D, int H, int W, int k, int pad, tpz_half* out, int ld,
-                                  void* stream) {
+                                  const float* range, int out_lo, void* stream) {
+  TPZ_CHECK(out_lo == 0 || out_lo == ld, "tpz_im2col3d_first: out_lo=%d must be 0 or ld", out_lo);
   TPZ_CHECK(k >= 1 && k * k * k <= ld && ld % 16 == 0 && pad == k / 2, "tpz_im2col3d_first: k=%d pad=%d ld=%d", k, pad, ld);
   const size_t total = (size_t)N * D * H * W * (ld / 16);
   if (total == 0) return 0;
-  if (k == 3) im2col3d_first_kernel<3><<<tpz_div_up(total, 256), 256, 0, ST(stream)>>>(x, N, D, H, W, k, pad, HP(out), ld);
-  else im2col3d_first_kernel<0><<<tpz_div_up(total, 256), 256, 0, ST(stream)>>>(x, N, D, H, W, k, pad, HP(out), ld);
+  if (k == 3) im2col3d_first_kernel<3><<<tpz_div_up(total, 256), 256, 0, ST(stream)>>>(x, N, D, H, W, k, pad, HP(out), ld, range, out_lo);
+  else im2col3d_first_kernel<0><<<tpz_div_up(total, 256), 256, 0, ST(stream)>>>(x, N, D, H, W, k, pad, HP(out), ld, range, out_lo);
   TPZ_CUDA(cudaGetLastError());
   return 0;
 }
 
 extern "C" int tpz_conv_last(const tpz_half* x, int N, int D, int H, int W, int C, int ld, const float* w, float bias,
                              int kd, int kh, int kw, int dil, int pad, float out_scale, float out_shift,
-                             const float* affine_stats, float* out, void* stream) {
+                             const float* affine_stats, float* out, const float* range, void* stream) {
   TPZ_CHECK(C % 8 == 0 && ld % 8 == 0, "tpz_conv_last: C=%d / ld=%d must be multiples of 8", C, ld);
   if (kd == 1 && dil == 1 && kh == kw && pad == kh / 2 && C == 32 && (kh == 5 || kh == 3)) {     // tiled 2-D kernel
     const __half* xh = HCP(x);
-    if (kh == 5) return launch_conv_last_tiled<32, 5>(xh, N * D, H, W, ld, w, bias, out_scale, out_shift, affine_stats, out, ST(stream));
-    return launch_conv_last_tiled<32, 3>(xh, N * D, H, W, ld, w, bias, out_scale, out_shift, affine_stats, out, ST(stream));
+    if (kh == 5) return launch_conv_last_tiled<32, 5>(xh, N * D, H, W, ld, w, bias, out_scale, out_shift, affine_stats, out, range, ST(stream));
+    return launch_conv_last_tiled<32, 3>(xh, N * D, H, W, ld, w, bias, out_scale, out_shift, affine_stats, out, range, ST(stream));
   }
   const size_t total = (size_t)N * D * H * W;
   conv_last_kernel<<<tpz_div_up(total, 128), 128, 0, ST(stream)>>>(HCP(x), N, D, H, W, C, ld, w, bias, kd, kh, kw,
-                                                                   dil, pad, out_scale, out_shift, affine_stats, out);
+                                                                   dil, pad, out_scale, out_shift, affine_stats, out, range);
   TPZ_CUDA(cudaGetLastError());
   return 0;
 }
@@ -633,13 +724,14 @@ extern "C" int tpz_conv_generic(const tpz_half* x0, int C0, int ld0, const tpz_h
 }
 
 extern "C" int tpz_maxpool2(const tpz_half* x, int N, int D, int H, int W, int C, int ld, int dims, tpz_half* out,
-                            int out_ld, void* stream) {
+                            int out_ld, int lo_off, void* stream) {
+  TPZ_CHECK(lo_off >= 0 && lo_off % 8 == 0, "tpz_maxpool2: lo_off=%d must be a non-negative multiple of 8", lo_off);
   TPZ_CHECK(C % 8 == 0 && ld % 8 == 0 && out_ld % 8 == 0, "tpz_maxpool2: channel counts must be multiples of 8");
   const int Do = dims == 3 ? D / 2 : D, Ho = H / 2, Wo = W / 2;
   const size_t total = (size_t)N * Do * Ho * Wo * (C / 8);
   if (total == 0) return 0;
   maxpool2_kernel<<<tpz_div_up(total, 256), 256, 0, ST(stream)>>>(HCP(x), N, D, H, W, C, ld, dims, HP(out), out_ld,
-                                                                  Do, Ho, Wo);
+                                                                  Do, Ho, Wo, lo_off);
   TPZ_CUDA(cudaGetLastError());
   return 0;
 }
@@ -684,6 +776,16 @@ extern "C" int tpz_filter_f32(const float* x, int N, int D, int H, int W, const 
   TPZ_CUDA(cudaFuncSetAttribute(filter_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const size_t total = (size_t)N * D * H * W;
   filter_f32_kernel<<<tpz_div_up(total, 256), 256, smem, ST(stream)>>>(x, N, D, H, W, f, kd, kh, kw, bias, y);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tpz_range_scale(const float* x, long long n, float* range, unsigned* work, void* stream) {
+  TPZ_CHECK(n > 0, "tpz_range_scale: empty input");
+  int grid = tpz_div_up(n, 256 * 8);
+  if (grid > 148 * 8) grid = 148 * 8;
+  absmax_kernel<<<grid, 256, 0, ST(stream)>>>(x, n, work);
+  range_finalize_kernel<<<1, 1, 0, ST(stream)>>>(work, range);
   TPZ_CUDA(cudaGetLastError());
   return 0;
 }

@@ -29,6 +29,7 @@ struct FirstArgs {
   float slope;
   int tiles_x, tiles_y;
   int pool;               // 1: fused 2x2 max-pool (floor), out is [B][Ho/2][Wo/2][Cp]
+  const float* range;     // optional device float[2] = (s, 1/s): input and bias are multiplied by s (tpz_range_scale)
 };
 
 template <int KW>
@@ -71,7 +72,8 @@ __global__ void __launch_bounds__(128, MINB) first_tc_kernel(const FirstArgs a) 
     const uint4 v = *reinterpret_cast<const uint4*>(a.w + ((size_t)(kb * CP + n) * 64 + c * 8));
     *reinterpret_cast<uint4*>(sB + kb * B_BYTES + n * 128 + ((c ^ (n & 7)) << 4)) = v;
   }
-  for (int i = tid; i < CP; i += 128) sBias[i] = a.bias[i];
+  const float rs = a.range ? a.range[0] : 1.f;         // range guard: a power of two, so x*rs and the later 1/rs are exact
+  for (int i = tid; i < CP; i += 128) sBias[i] = a.bias[i] * rs;
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(128, MINB) first_tc_kernel(const FirstArgs a) 
       const int i = tid + e * 128;
       const int wy = i / PW, wx = i - wy * PW;
       const int iy = y0 + wy, ix = x0 + wx;
-      pre[e] = (i < PH * PW && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) ? __ldg(img + (size_t)iy * a.W + ix) : 0.f;
+      pre[e] = (i < PH * PW && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) ? __ldg(img + (size_t)iy * a.W + ix) * rs : 0.f;
     }
   };
 
@@ -283,12 +285,12 @@ int launch_first(const FirstArgs& a, cudaStream_t stream) {
 }  // namespace
 
 extern "C" int tpz_conv_first_tc(const float* x, int B, int H, int W, const tpz_half* w_packed, const float* bias, int Cp,
-                                 int k, int pad, float neg_slope, int pool, tpz_half* out, void* stream_) {
+                                 int k, int pad, float neg_slope, int pool, tpz_half* out, const float* range, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   FirstArgs a;
   a.x = x; a.B = B; a.H = H; a.W = W;
   a.w = reinterpret_cast<const __half*>(w_packed); a.bias = bias; a.out = reinterpret_cast<__half*>(out);
-  a.Ho = H + 2 * pad - (k - 1); a.Wo = W + 2 * pad - (k - 1); a.pad = pad; a.slope = neg_slope; a.pool = pool ? 1 : 0;
+  a.Ho = H + 2 * pad - (k - 1); a.Wo = W + 2 * pad - (k - 1); a.pad = pad; a.slope = neg_slope; a.pool = pool ? 1 : 0; a.range = range;
   TPZ_CHECK(a.Ho > 0 && a.Wo > 0 && B > 0, "tpz_conv_first_tc: empty output (H=%d W=%d k=%d pad=%d)", H, W, k, pad);
   a.tiles_x = tpz_div_up(a.Wo, TW); a.tiles_y = tpz_div_up(a.Ho, TH);
 #define TPZ_FIRST_CASE(KW_, CP_) if (k == KW_ && Cp == CP_) return launch_first<KW_, CP_>(a, stream);

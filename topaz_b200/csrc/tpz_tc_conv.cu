@@ -63,13 +63,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
   float* s_dotw = s_bias + 256;
+  float* s_osc = s_dotw + 256;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   for (int i = threadIdx.x; i < p.Co; i += kThreads) {
-    s_bias[i] = p.bias ? p.bias[i] : 0.f;
+    // range guard: activations are stored multiplied by range[0] (a power of two), so the bias is scaled with them
+    s_bias[i] = p.bias ? p.bias[i] * (p.range ? p.range[0] : 1.f) : 0.f;
     s_dotw[i] = p.dot_w ? p.dot_w[i] : 0.f;
+    s_osc[i] = p.oscale ? p.oscale[i] : 1.f;
   }
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.tmA[0]);
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
         const int nc = min(32, p.Co - c);
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_bias[min(c + j, 255)];
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), s_osc[min(c + j, 255)], s_bias[min(c + j, 255)]);
         if (rrow && valid) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -235,12 +238,23 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
                 *reinterpret_cast<uint4*>(orow + c + q * 16) = make_uint4(u[0], u[1], u[2], u[3]);
                 if (q * 16 + 8 < nc) *reinterpret_cast<uint4*>(orow + c + q * 16 + 8) = make_uint4(u[4], u[5], u[6], u[7]);
               }
+              if (p.out_lo > 0) {          // strict mode: residual of the fp16 rounding, lo = fp16(v - hi)
+                uint32_t ul[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&u[e]));
+                  const __half2 l = __floats2half2_rn(v[q * 16 + e * 2] - hf.x, v[q * 16 + e * 2 + 1] - hf.y);
+                  ul[e] = *reinterpret_cast<const uint32_t*>(&l);
+                }
+                *reinterpret_cast<uint4*>(orow + p.out_lo + c + q * 16) = make_uint4(ul[0], ul[1], ul[2], ul[3]);
+                if (q * 16 + 8 < nc) *reinterpret_cast<uint4*>(orow + p.out_lo + c + q * 16 + 8) = make_uint4(ul[4], ul[5], ul[6], ul[7]);
+              }
             }
           }
         }
       }
       if (p.dot_out && valid) {
-          float dv = dot + p.dot_b;
+          float dv = fmaf(dot, p.range ? p.range[1] : 1.f, p.dot_b);     // undo the range scale (exact power of two)
           if (p.dot_affine) dv = dv * p.dot_affine[1] + p.dot_affine[0];
           p.dot_out[opix] = dv;
         }
@@ -325,6 +339,8 @@ extern "C" int tpz_tc_conv_v1(const TpzTcConvArgs* a, void* stream_) {
   TPZ_CHECK(a->res == nullptr || a->res_ld % 8 == 0, "tpz_tc_conv: residual channel stride must be a multiple of 8");
   p.out = reinterpret_cast<__half*>(a->out); p.out_ld = a->out_ld; p.out_coff = a->out_coff;
   p.dot_w = a->dot_w; p.dot_b = a->dot_b; p.dot_out = a->dot_out; p.dot_affine = a->dot_affine;
+  p.oscale = a->oscale; p.range = a->range; p.out_lo = a->out_lo;
+  TPZ_CHECK(a->out_lo % 8 == 0 && a->out_lo >= 0, "tpz_tc_conv: out_lo=%d must be a non-negative multiple of 8", a->out_lo);
 
   const int rowb = a->KC * 2;
   const int stage_bytes = 128 * rowb + a->Co * rowb;

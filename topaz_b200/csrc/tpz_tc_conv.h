@@ -23,5 +23,8 @@ struct TcConvParams {
   float dot_b;
   float* dot_out;
   const float* dot_affine;
+  const float* oscale;
+  const float* range;
+  int out_lo;
   TcKBlock kb[TPZ_TC_MAX_KB];
 };

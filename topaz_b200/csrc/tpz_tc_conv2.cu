@@ -21,7 +21,7 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kTmemCols = 512;
 constexpr int T2W = 8, T2H = 32;
-constexpr int kMaxGroups = 40;
+constexpr int kMaxGroups = 64;
 constexpr int kMaxAStages = 4, kMaxBStages = 8;
 
 struct Tc2Group {
@@ -57,6 +57,9 @@ struct Tc2Params {
   float dot_b;
   float* dot_out;
   const float* dot_affine;
+  const float* oscale;
+  const float* range;
+  int out_lo;
   Tc2Group groups[kMaxGroups];
   Tc2Tap taps[TPZ_TC_MAX_KB];
 };
@@ -137,13 +140,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv2_kernel(const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
   float* s_dotw = s_bias + 256;
+  float* s_osc = s_dotw + 256;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   for (int i = threadIdx.x; i < p.Co; i += kThreads) {
-    s_bias[i] = p.bias ? p.bias[i] : 0.f;
+    // range guard: activations are stored multiplied by range[0] (a power of two), so the bias is scaled with them
+    s_bias[i] = p.bias ? p.bias[i] * (p.range ? p.range[0] : 1.f) : 0.f;
     s_dotw[i] = p.dot_w ? p.dot_w[i] : 0.f;
+    s_osc[i] = p.oscale ? p.oscale[i] : 1.f;
   }
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.tmA[0]);
@@ -343,7 +349,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv2_kernel(const __grid_cons
           const int nc = min(32, p.Co - c);
           float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_bias[min(c + j, 255)];
+          for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), s_osc[min(c + j, 255)], s_bias[min(c + j, 255)]);
           if (rrow && valid) {
             const bool wide_r = ((reinterpret_cast<uintptr_t>(rrow + c) & 31) == 0);     // full-sector 32-byte loads
 #pragma unroll
@@ -397,12 +403,23 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv2_kernel(const __grid_cons
                   *reinterpret_cast<uint4*>(orow + c + q * 16) = make_uint4(u[0], u[1], u[2], u[3]);
                   if (q * 16 + 8 < nc) *reinterpret_cast<uint4*>(orow + c + q * 16 + 8) = make_uint4(u[4], u[5], u[6], u[7]);
                 }
+                if (p.out_lo > 0) {          // strict mode: residual of the fp16 rounding, lo = fp16(v - hi)
+                  uint32_t ul[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&u[e]));
+                    const __half2 l = __floats2half2_rn(v[q * 16 + e * 2] - hf.x, v[q * 16 + e * 2 + 1] - hf.y);
+                    ul[e] = *reinterpret_cast<const uint32_t*>(&l);
+                  }
+                  *reinterpret_cast<uint4*>(orow + p.out_lo + c + q * 16) = make_uint4(ul[0], ul[1], ul[2], ul[3]);
+                  if (q * 16 + 8 < nc) *reinterpret_cast<uint4*>(orow + p.out_lo + c + q * 16 + 8) = make_uint4(ul[4], ul[5], ul[6], ul[7]);
+                }
               }
             }
           }
         }
         if (p.dot_out && valid) {
-          float dv = dot + p.dot_b;
+          float dv = fmaf(dot, p.range ? p.range[1] : 1.f, p.dot_b);     // undo the range scale (exact power of two)
           if (p.dot_affine) dv = dv * p.dot_affine[1] + p.dot_affine[0];
           p.dot_out[opix] = dv;
         }
@@ -571,6 +588,8 @@ static int launch_v2(const TpzTcConvArgs* a, cudaStream_t stream, bool dry, bool
   p.res_org[0] = a->res_org[0]; p.res_org[1] = a->res_org[1]; p.res_org[2] = a->res_org[2];
   p.out = reinterpret_cast<__half*>(a->out); p.out_ld = a->out_ld; p.out_coff = a->out_coff;
   p.dot_w = a->dot_w; p.dot_b = a->dot_b; p.dot_out = a->dot_out; p.dot_affine = a->dot_affine;
+  p.oscale = a->oscale; p.range = a->range; p.out_lo = a->out_lo;
+  TPZ_CHECK(a->out_lo % 8 == 0 && a->out_lo >= 0, "tpz_tc_conv: out_lo=%d must be a non-negative multiple of 8", a->out_lo);
 
   if (g_num_sms2 == 0) {
     int dev = 0;

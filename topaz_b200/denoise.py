@@ -73,7 +73,7 @@ class Denoise():
         if os.environ.get('TPZ_DENOISE_GRAPH', '1') == '0':
             return self._denoise_device(crop)
         graphs = self.__dict__.setdefault('_graphs', {})
-        key = (tuple(crop.shape), str(crop.device), engine._state_key(self.model))
+        key = (tuple(crop.shape), str(crop.device), engine._state_key(self.model))      # includes engine.PRECISION
         hit = graphs.get(key)
         if hit is None:
             if len(graphs) >= 8:                       # weights changed or many shapes: drop the old pools
