@@ -14,9 +14,7 @@ Multi-GPU: images are sharded one-per-rank (weak scaling), no data-path collecti
 import argparse
 import json
 import os
-import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -60,67 +58,8 @@ def load_peaks():
     return dict(tflops=1400.0, hbm=6650.0, src='fallback (B200_PROFILING.md)')
 
 
-class ClockSampler(threading.Thread):
-    """Samples SM clocks / throttle reasons during the timed region.  Uses NVML in-process (initialised before the timed
-    region): spawning `nvidia-smi` every 200 ms re-initialises NVML each time, which takes a driver-wide lock and stalls
-    the host-side CUDA calls of the end-to-end leg by tens of ms.  Falls back to nvidia-smi if pynvml is unavailable."""
-    NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-
-    def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.stop_flag, self.rows = index, False, []      # rows: (sm_mhz, sm_max_mhz, [active reason flags])
-        self.nvml = None
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            # CUDA_VISIBLE_DEVICES may renumber devices: address the GPU by the UUID torch reports
-            uuid = str(torch.cuda.get_device_properties(index).uuid)
-            uuid = uuid if uuid.startswith('GPU-') else 'GPU-' + uuid
-            try:
-                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if isinstance(uuid, str) else uuid)
-            except Exception:
-                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.nvml = pynvml
-        except Exception:
-            self.nvml = None
-
-    def _sample_nvml(self):
-        n = self.nvml
-        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
-        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
-        r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
-        flags = [bool(r & n.nvmlClocksThrottleReasonHwSlowdown), bool(r & n.nvmlClocksThrottleReasonHwThermalSlowdown),
-                 bool(r & n.nvmlClocksThrottleReasonSwThermalSlowdown), bool(r & n.nvmlClocksThrottleReasonSwPowerCap)]
-        self.rows.append((int(sm), int(mx), flags))
-
-    def _sample_smi(self):
-        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
-        out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={q}', '--format=csv,noheader,nounits'],
-                             capture_output=True, text=True, timeout=5).stdout.strip()
-        if out:
-            c = [v.strip() for v in out.split(',')]
-            if c[0].isdigit():
-                self.rows.append((int(c[0]), int(c[1]) if c[1].isdigit() else None, [v.lower().startswith('active') for v in c[2:6]]))
-
-    def run(self):
-        while not self.stop_flag:
-            try:
-                if self.nvml is not None:
-                    self._sample_nvml()
-                else:
-                    self._sample_smi()
-            except Exception:
-                pass
-            time.sleep(0.05 if self.nvml is not None else 0.2)
-
-    def summary(self):
-        if not self.rows:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['unavailable'])
-        sm = sorted(r[0] for r in self.rows)
-        reasons = [n for i, n in enumerate(self.NAMES) if any(r[2][i] for r in self.rows)]
-        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=self.rows[0][1], reasons=reasons, samples=len(self.rows),
-                    source='nvml' if self.nvml is not None else 'nvidia-smi')
+sys.path.insert(0, os.path.join(ROOT, 'tools'))
+from workloads import ClockSampler, Ctx, cfg3_denoise2d, cfg4_train, cfg5_denoise3d, gpu_library_baseline  # noqa: E402
 
 
 def pretrained_u64_state():
@@ -201,6 +140,9 @@ def main():
     ap.add_argument('--images', type=int, default=8, help='distinct synthetic micrographs cycled per rank (64 in the full job)')
     ap.add_argument('--variant', default='auto', choices=['auto', 'v1', 'v2'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--extras', default='cfg3,cfg4,cfg5,lib',
+                    help='secondary BASELINE workloads folded into the line\'s `extra` block (comma list of cfg3,cfg4,cfg4bn,cfg5,lib; "none" to skip)')
+    ap.add_argument('--tomo', type=int, default=512, help='cfg5 tomogram edge (512 = the full BASELINE size: 216 patches of 192^3)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
@@ -288,6 +230,29 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    # --- secondary workloads (BASELINE configs 3-5) and the same-GPU library baseline, each with its own clock sample ---
+    extra = {}
+    wanted = [] if args.extras == 'none' else [w for w in args.extras.split(',') if w]
+    ctx = Ctx()
+    del devimgs, host
+    torch.cuda.empty_cache()
+    for name in wanted:
+        try:
+            if name == 'cfg3':
+                extra['cfg3_unet2d_denoise'] = cfg3_denoise2d(ctx, steps=4)
+            elif name == 'cfg4':
+                extra['cfg4_ge_binomial_train'] = cfg4_train(ctx, steps=40)
+            elif name == 'cfg4bn':
+                extra['cfg4_ge_binomial_train_bn'] = cfg4_train(ctx, steps=40, bn=True)
+            elif name == 'cfg5':
+                extra['cfg5_unet3d_denoise'] = cfg5_denoise3d(ctx, size=args.tomo)
+            elif name == 'lib' and world == 1:
+                extra['gpu_library_baseline'] = gpu_library_baseline(ctx)
+        except Exception as e:      # a failing secondary workload must not lose the headline line
+            extra[name + '_error'] = f'{type(e).__name__}: {str(e)[:300]}'
+        torch.cuda.empty_cache()
+    lib = extra.get('gpu_library_baseline')
+
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -320,6 +285,23 @@ def main():
                          'peak_source': peaks['src'], 'ms_per_launch': dom_avg_ms, 'launches_timed': len(dom_ms),
                          'step_tflops': (FLOP_PER_PX_4096 * S * S / 1e12) / (ms_max / args.steps / 1e3) if S == 4096 else None},
         }
+        if lib:      # the north-star target: >= 1.5x the reference's own torch/cuDNN path on the same B200, same run
+            sp = {}
+            if 'ms' in lib.get('resnet8_u64_dense_4096', {}):
+                sp['resnet8_u64_scoring_4096'] = lib['resnet8_u64_dense_4096']['ms'] / (ms_max / args.steps)
+            c3 = extra.get('cfg3_unet2d_denoise')
+            if c3 and 'ms' in lib.get('unet2d_2048_patch', {}):
+                # Denoise.denoise(4096^2, 1024/500) = 4 crops of 2048^2 + 8 of 2048x1524 + 4 of 1524^2 = 51.04 Mpx processed
+                sp['unet2d_denoise_4096'] = (lib['unet2d_2048_patch']['ms'] * 51.04 / 4.194304) / c3['ms_per_image']
+            c4 = extra.get('cfg4_ge_binomial_train')
+            if c4 and 'train_step_u32' in lib:
+                sp['ge_binomial_train_step'] = lib['train_step_u32']['ms'] / c4['ms_per_step']
+            c5 = extra.get('cfg5_unet3d_denoise')
+            if c5 and 'ms' in lib.get('unet3d_192_patch', {}):
+                sp['unet3d_denoise_patch'] = lib['unet3d_192_patch']['ms'] / c5['ms_per_patch']
+            extra['speedup_vs_gpu_library'] = sp
+        if extra:
+            line['extra'] = extra
         if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N=1 only (the reference arm covers N>1)
             v, dt, thr = cpu_oracle_mpxs()
             line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': thr, 'kind': 'port',

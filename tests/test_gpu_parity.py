@@ -15,7 +15,7 @@ from common_shapes import classifier_shapes, unet_shapes
 from oracle import topaz_oracle as O
 
 pytestmark = pytest.mark.gpu
-TOL, TOL_SEEDED = 1e-3, 3e-3
+TOL, TOL_SEEDED = 1e-3, 2e-3      # measured on B200 in the default mode: seeded nets 4.9e-4 ... 1.7e-3 (GPUTEST log, profiles/)
 
 
 def _load(model, sd):

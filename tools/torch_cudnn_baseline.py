@@ -51,10 +51,12 @@ def resnet8_dense(u=64):
     return fwd
 
 
-def unet(nf=48, base=11, top=5):
+def unet(nf=48, base=11, top=5, dims=2):
     dev = 'cuda'
+    Conv = nn.Conv3d if dims == 3 else nn.Conv2d
+    pool = F.max_pool3d if dims == 3 else F.max_pool2d
     def cv(ci, co, k):
-        c = nn.Conv2d(ci, co, k, padding=k // 2).to(dev); return c
+        c = Conv(ci, co, k, padding=k // 2).to(dev); return c
     enc = [cv(1, nf, base)] + [cv(nf, nf, 3) for _ in range(5)]
     dec = {5: (cv(2 * nf, 2 * nf, 3), cv(2 * nf, 2 * nf, 3))}
     for l in (4, 3, 2):
@@ -66,7 +68,7 @@ def unet(nf=48, base=11, top=5):
         for i, c in enumerate(enc):
             h = F.leaky_relu(c(h), 0.1)
             if i < 5:
-                h = F.max_pool2d(h, 2); skips.append(h)
+                h = pool(h, 2); skips.append(h)
         for l in (5, 4, 3, 2):
             s = skips[l - 1]
             h = torch.cat([F.interpolate(h, size=s.shape[2:], mode='nearest'), s], 1)

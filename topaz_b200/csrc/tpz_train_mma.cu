@@ -11,8 +11,8 @@
 #include <stdlib.h>
 // X3 = 1: error-compensated 3xTF32 (fp32-level accuracy, default).  X3 = 0 (env TPZ_TRAIN_TF32=1): single-pass TF32,
 // the precision of the reference's own cuDNN path (torch.backends.cudnn.allow_tf32 = True), ~1.3x faster step.
-// X3 = 2 (env TPZ_TRAIN_SPLIT=fast, opt-in candidate, NOT yet validated on hardware): 3xTF32 with a 3-instruction operand
-// split.  On sm_100a `cvt.rna.tf32.f32` is emulated (FSETP inf/nan guard + predicated integer add of half an ulp + LOP3
+// X3 = 2 (default since round 2, validated on B200; TPZ_TRAIN_SPLIT=rna switches back to X3 = 1): 3xTF32 with a 3-instruction
+// operand split.  On sm_100a `cvt.rna.tf32.f32` is emulated (FSETP inf/nan guard + predicated integer add of half an ulp + LOP3
 // mask, `profiles/r01_sass_train_mma_s2.md`), so the default split costs 7 instructions per operand value and the hot loops
 // issue 4.4-6.8 instructions per HMMA.  The fast split rounds hi with the same add+mask but without the guard (inf stays inf;
 // NaN payloads are irrelevant here) and hands lo = x - hi to the MMA unrounded (the tensor core ignores the 13 low mantissa
@@ -414,7 +414,10 @@ static bool use_x3() {
 }
 // template argument X3 of the kernels: 0 single-pass TF32, 1 3xTF32 (default), 2 3xTF32 with the fast split (opt-in)
 static int x3_mode() {
-  static const bool fast = []() { const char* e = getenv("TPZ_TRAIN_SPLIT"); return e && strcmp(e, "fast") == 0; }();
+  // default since round 2: the 3-instruction split (validated on B200: the 47 training parity tests pass unchanged, step
+  // 3.10 -> 2.65 ms without / 3.45 -> 3.01 ms with BatchNorm, profiles/r02_bench_split_ab.jsonl); TPZ_TRAIN_SPLIT=rna selects
+  // the cvt.rna split again
+  static const bool fast = []() { const char* e = getenv("TPZ_TRAIN_SPLIT"); return !(e && strcmp(e, "rna") == 0); }();
   return use_x3() ? (fast ? 2 : 1) : 0;
 }
 extern "C" int tpz_train_set_tf32(int single_pass) {
