@@ -183,6 +183,21 @@ int tpz_conv_dgrad_mma(const float* dy, int N, int Ho, int Wo, int Co, const flo
                        void* stream);
 int tpz_conv_wgrad_mma(const float* x, int N, int H, int W, int Ci, const float* dy, int Ho, int Wo, int Co, int kh, int kw,
                        int stride, int dil, int org, float* dw, void* stream);
+/* tcgen05 versions (tpz_train_tc.cu): the same three products as error-compensated 3xTF32 on `tcgen05.mma.kind::tf32` with
+ * TMEM accumulators, for Ci % 32 == 0 and Co % 32 == 0.  Operands are split hi / lo once by the staging threads (activations,
+ * gradients) or by tpz_train_repack_tc (weights: OIHW -> forward [tap][ci/32][co][32] and dgrad [tap][co/32][ci][32], each a hi
+ * plane followed by a lo plane; `descs` as for tpz_train_repack, offsets into a packed buffer of 4 x numel per weight).
+ * Same argument meaning as the _mma entry points.  TPZ_TRAIN_FLUSH = chunks of 32 K-elements accumulated in TMEM before the
+ * round-to-nearest drain into registers (default 2; 0 = never). */
+int tpz_train_repack_tc(const float* flat_params, const void* descs, int ndesc, long long max_elems, float* packed, void* stream);
+int tpz_conv_fwd_tc(const float* x, int N, int H, int W, int Ci, const float* w_fwd_packed, const float* bias, int Co,
+                    int kh, int kw, int stride, int dil, int org, const float* res, int res_H, int res_W, int res_org,
+                    int res_stride, int relu, float* y, int Ho, int Wo, void* stream);
+int tpz_conv_dgrad_tc(const float* dy, int N, int Ho, int Wo, int Co, const float* w_dg_packed, int Ci, int kh, int kw,
+                      int stride, int dil, int org, const float* relu_mask, int accumulate, float* dx, int H, int W,
+                      void* stream);
+int tpz_conv_wgrad_tc(const float* x, int N, int H, int W, int Ci, const float* dy, int Ho, int Wo, int Co, int kh, int kw,
+                      int stride, int dil, int org, float* dw, void* stream);
 /* Cin = 1 first layer of the training net (resnet.py:294, 7x7 stride 2), valid conv, org = 0 */
 int tpz_first_fwd_f32(const float* x, int N, int H, int W, const float* w, const float* bias, int Co, int k, int stride,
                       int relu, float* y, int Ho, int Wo, void* stream);
@@ -231,6 +246,10 @@ int tpz_pu_objective_loss_grad(const float* scores, const double* labels, int B,
                                double momentum, double aux_in, int lo, int hi, float* dscores, float* out6, void* stream);
 int tpz_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
                   float beta2, float eps, int step, float l2, float grad_scale, void* stream);
+/* Same update with the step count kept on the device: *step_dev is incremented first and the bias corrections are derived
+ * from it in the kernel, so the launch can be replayed from a CUDA graph of the whole training step (methods.py). */
+int tpz_adam_step_dev(float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                      float beta2, float eps, int* step_dev, float l2, float grad_scale, void* stream);
 
 /* ---- hardware probe used by tests/bring-up (UMMA descriptor row-offset behaviour), not on the product path ---- */
 int tpz_lab_umma(const tpz_half* A, int rowsA, const tpz_half* B, int N, int shift, int sbo_rows, int base_off_mode,

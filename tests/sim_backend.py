@@ -190,7 +190,7 @@ def conv_last(x, c_real, w, bias, kdhw, dil, pad, stats=None, out_scale=1.0, out
     kd, kh, kw = kdhw
     C = w.shape[1]
     wt = w.t().reshape(1, C, kd, kh, kw)
-    xi = x[..., :C].float().permute(0, 4, 1, 2, 3)
+    xi = x[..., :C].float().permute(0, 4, 1, 2, 3)          # split inputs: C = 2 * channels, weights repeated
     y = F.conv3d(xi, wt, None, dilation=dil, padding=(pad if kd > 1 else 0, pad, pad))[:, 0]
     y = (y * _rs(rng)[1] + bias) * out_scale + out_shift
     if stats is not None:
@@ -467,7 +467,7 @@ def patched_training():
              '_crop_add': t_crop_add, '_bn_stats': t_bn_stats, '_bn_fwd': t_bn_fwd, '_bn_bwd_reduce': t_bn_bwd_reduce,
              '_bn_bwd': t_bn_bwd, '_act_fwd': t_act_fwd, '_act_bwd': t_act_bwd, '_dropout_fwd': t_dropout_fwd, '_dropout_bwd': t_dropout_bwd,
              'ge_loss_grad': t_ge_loss_grad, 'pu_objective_loss_grad': t_pu_objective, 'adam_step': t_adam_step,
-             'read_back': lambda d, h: d.tolist(), '_repack': lambda fp: None}
+             'read_back': lambda d, h: d.tolist(), '_repack': lambda fp, force=False: None}
     saved = {n: getattr(T, n) for n in names}
     try:
         for n, f in names.items():

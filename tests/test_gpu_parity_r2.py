@@ -292,3 +292,55 @@ def test_split_maxpool_and_first_layer_kernels():
                 r = ref3[:, dz:dz + 9, dy:dy + 12, dx:dx + 10]
                 assert float((col3[..., t] + col3[..., 32 + t] - r).abs().max()) <= 2.0 ** -20 * 5
                 t += 1
+
+
+def test_conv_last3d_tiled_kernel_plain_and_split_inputs():
+    """tpz_conv_last 3x3x3 (z-marching CUDA-core kernel) vs torch conv3d: plain fp16 input (C = 32) and split (hi, lo) input
+    as 64 channels with the weights repeated; ragged sizes, batch 2, fused de-normalisation."""
+    from topaz_b200 import ops
+    gen = torch.Generator().manual_seed(9)
+    w = torch.randn(27, 32, generator=gen) * 0.1
+    stats = torch.tensor([0.7, 1.9])
+    for (N, D, H, W) in [(1, 20, 37, 45), (2, 5, 16, 32), (1, 33, 70, 9)]:
+        v = torch.randn(N, D, H, W, 32, generator=gen) * 2
+        hi = v.half(); lo = (v - hi.float()).half()
+        ref_w = w.t().reshape(1, 32, 3, 3, 3)
+        ref_hi = F.conv3d(hi.float().permute(0, 4, 1, 2, 3), ref_w, None, padding=1)[:, 0] + 0.3
+        ref_full = F.conv3d((hi.float() + lo.float()).permute(0, 4, 1, 2, 3), ref_w, None, padding=1)[:, 0] + 0.3
+        y = ops.conv_last(hi.cuda(), 32, w.cuda(), 0.3, (3, 3, 3), 1, 1).cpu()
+        check_parity(y.numpy(), ref_hi.numpy(), 1e-5, f'conv_last3d plain {N}x{D}x{H}x{W}')
+        x2 = torch.cat([hi, lo], -1).cuda()
+        y2 = ops.conv_last(x2, 32, torch.cat([w, w], 1).cuda(), 0.3, (3, 3, 3), 1, 1, stats=stats.cuda()).cpu()
+        check_parity(y2.numpy(), (ref_full * stats[1] + stats[0]).numpy(), 1e-5, f'conv_last3d split {N}x{D}x{H}x{W}')
+
+
+def test_training_step_graph_replay_matches_eager():
+    """GE_binomial.step replayed from a CUDA graph (third step onwards) gives the same parameters as the eager path
+    (TPZ_TRAIN_GRAPH=0) after 6 steps, incl. the device-side Adam step count."""
+    import os
+    import torch.nn as nn
+    from topaz_b200.methods import GE_binomial
+    sd = weights_of(gold('resnet8_u32_pretrained'))
+    Y = torch.tensor([1.0] * 4 + [0.0] * 60, dtype=torch.float64).cuda()
+    Xs = [torch.from_numpy(np.random.default_rng(4100 + s).standard_normal((64, 71, 71)).astype(np.float32)).cuda() for s in range(6)]
+    res = {}
+    old = os.environ.get('TPZ_TRAIN_GRAPH')
+    try:
+        for mode in ('0', '1'):
+            os.environ['TPZ_TRAIN_GRAPH'] = mode
+            m = _load(_classifier('resnet8', 32), sd).cuda(); m.train()
+            tr = GE_binomial(m, torch.optim.Adam(m.parameters(), lr=2e-4), nn.BCEWithLogitsLoss(), 0.035)
+            outs = [tr.step(X, Y) for X in Xs]
+            st = tr.__dict__.get('_graph_state', {})
+            assert (st.get('graph') is not None) == (mode == '1'), (mode, st.get('key'))
+            res[mode] = (np.array(outs), torch.cat([p.detach().reshape(-1) for p in m.parameters()]).cpu().numpy(),
+                         tr.optim.state[next(iter(m.parameters()))]['step'].item())
+    finally:
+        if old is None:
+            os.environ.pop('TPZ_TRAIN_GRAPH', None)
+        else:
+            os.environ['TPZ_TRAIN_GRAPH'] = old
+    assert res['0'][2] == res['1'][2] == 6.0
+    np.testing.assert_allclose(res['1'][0], res['0'][0], rtol=2e-5, atol=1e-7)
+    mx, l2 = rel_err(res['1'][1], res['0'][1])
+    assert mx < 1e-5 and l2 < 1e-5, (mx, l2)          # wgrad atomics reorder fp32 sums from run to run

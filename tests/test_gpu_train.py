@@ -152,6 +152,72 @@ def test_conv_mma_kernels_match_fp32(N, H, Ci, Co, k, stride, dil, org):
     assert max(rel_err(dw.cpu(), gw)) < 5e-5
 
 
+@pytest.mark.parametrize('N,H,Ci,Co,k,stride,dil,org', [
+    (4, 33, 32, 32, 3, 1, 1, 0), (3, 31, 32, 64, 3, 2, 2, 0), (3, 27, 32, 64, 1, 2, 1, 3), (2, 11, 64, 64, 3, 1, 2, 0),
+    (2, 9, 64, 128, 5, 1, 1, 0), (300, 5, 64, 64, 3, 1, 1, 0),
+    (48, 27, 64, 128, 1, 2, 1, 3), (48, 25, 64, 128, 3, 2, 2, 0), (48, 9, 128, 256, 5, 1, 1, 0), (48, 11, 128, 128, 3, 1, 2, 0),   # resnet8_u64 layers
+    (256, 31, 32, 32, 3, 1, 1, 0),                                                                                                 # resnet8_u32 at the cfg4 minibatch
+])
+def test_conv_tc_kernels_match_fp32(N, H, Ci, Co, k, stride, dil, org):
+    """tcgen05 (kind::tf32, 3-pass) fwd / dgrad / wgrad vs torch CPU fp32, with the weights packed by tpz_train_repack_tc
+    (fp32-level accuracy expected, as for the mma.sync kernels above)."""
+    import ctypes as C
+    from topaz_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(N, Ci, H, H, generator=g)
+    w = torch.randn(Co, Ci, k, k, generator=g) * 0.1
+    b = torch.randn(Co, generator=g) * 0.1
+    xin = x[:, :, org:, org:]
+    ref = F.conv2d(xin, w, b, stride=stride, dilation=dil)
+    Ho = ref.shape[2]
+    ext = (Ho - 1) * stride + (k - 1) * dil + 1
+    xin = xin[:, :, :ext, :ext]
+    P = lambda t: C.c_void_p(t.data_ptr())
+    xd, bd = _nhwc(x).cuda(), b.cuda()
+    n = w.numel()
+    desc = np.zeros(1, dtype=[('src', '<i8'), ('fwd', '<i8'), ('dg', '<i8'), ('co', '<i4'), ('ci', '<i4'), ('taps', '<i4'), ('pad', '<i4')])
+    desc[0] = (0, 0, 2 * n, Co, Ci, k * k, 0)
+    dd = torch.from_numpy(desc.view(np.uint8).copy()).cuda()
+    packed = torch.zeros(4 * n, device='cuda')
+    wd = w.contiguous().cuda()
+    _lib.check(L.tpz_train_repack_tc(P(wd), P(dd), 1, n, P(packed), None))
+    pk = packed.cpu()
+    # the packed planes reproduce the weights: hi + lo == w, laid out [tap][ci/32][co][32] / [tap][co/32][ci][32]
+    wf = (pk[:n] + pk[n:2 * n]).reshape(k * k, Ci // 32, Co, 32).permute(2, 1, 3, 0).reshape(Co, Ci, k, k)
+    wg = (pk[2 * n:3 * n] + pk[3 * n:]).reshape(k * k, Co // 32, Ci, 32).permute(1, 3, 2, 0).reshape(Co, Ci, k, k)
+    assert torch.equal(wf, w) and torch.equal(wg, w)
+    y = torch.empty(N, Ho, Ho, Co, device='cuda')
+    res = torch.randn(N, Ho, Ho, Co, generator=g)
+    _lib.check(L.tpz_conv_fwd_tc(P(xd), N, H, H, Ci, P(packed), P(bd), Co, k, k, stride, dil, org, None, 0, 0, 0, 1, 0, P(y), Ho, Ho, None))
+    e = max(rel_err(y.cpu(), _nhwc(ref)))
+    print('conv_fwd_tc rel err', e)
+    assert e < 5e-5
+    resd = res.cuda()
+    _lib.check(L.tpz_conv_fwd_tc(P(xd), N, H, H, Ci, P(packed), P(bd), Co, k, k, stride, dil, org, P(resd), Ho, Ho, 0, 1, 1, P(y), Ho, Ho, None))
+    assert max(rel_err(y.cpu(), torch.relu(_nhwc(ref) + res))) < 5e-5
+    dy = torch.randn(N, Co, Ho, Ho, generator=g)
+    dyd = _nhwc(dy).cuda()
+    gi = torch.nn.grad.conv2d_input(tuple(xin.shape), w, dy, stride=stride, dilation=dil)
+    gref = torch.zeros_like(x); gref[:, :, org:org + ext, org:org + ext] = gi
+    dx = torch.empty(N, H, H, Ci, device='cuda')
+    _lib.check(L.tpz_conv_dgrad_tc(P(dyd), N, Ho, Ho, Co, P(packed[2 * n:]), Ci, k, k, stride, dil, org, None, 0, P(dx), H, H, None))
+    e = max(rel_err(dx.cpu(), _nhwc(gref)))
+    print('conv_dgrad_tc rel err', e)
+    assert e < 5e-5
+    mask = torch.randn(N, H, H, Ci, generator=g)
+    base = torch.randn(N, H, H, Ci, generator=g)
+    dx2 = base.clone().cuda()
+    _lib.check(L.tpz_conv_dgrad_tc(P(dyd), N, Ho, Ho, Co, P(packed[2 * n:]), Ci, k, k, stride, dil, org, P(mask.cuda()), 1, P(dx2), H, H, None))
+    assert max(rel_err(dx2.cpu(), torch.where(mask > 0, base + _nhwc(gref), torch.zeros(())))) < 5e-5
+    gw = torch.nn.grad.conv2d_weight(xin.contiguous(), tuple(w.shape), dy, stride=stride, dilation=dil)
+    dw = torch.zeros_like(w).cuda()
+    _lib.check(L.tpz_conv_wgrad_tc(P(xd), N, H, H, Ci, P(dyd), Ho, Ho, Co, k, k, stride, dil, org, P(dw), None))
+    e = max(rel_err(dw.cpu(), gw))
+    print('conv_wgrad_tc rel err', e)
+    assert e < 5e-5
+
+
 @pytest.mark.parametrize('tag', ['PN', 'PNpi', 'GE_KL', 'PU', 'PUclip'])
 def test_other_objectives_match_reference_golden(tag):
     """PN / GE_KL / PU on the GPU: loss tuples of 2 steps and updated parameters vs the reference goldens; the fused loss

@@ -11,7 +11,7 @@ from topaz_b200.denoising.models import UDenoiseNet, UDenoiseNet3D
 from topaz_b200.denoise import Denoise, Denoise3D
 if len(sys.argv) > 1 and sys.argv[1] == '3d':
     m = UDenoiseNet3D(nf=48, base_width=7, top_width=3)
-    m.load_state_dict({k: torch.from_numpy(v) for k, v in seeded_state(unet_shapes(48, 7, 3, 3), 202).items()})
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in weights_of(gold('unet3d_pretrained_10a')).items()})
     dn = Denoise3D(m)
     x = torch.from_numpy(np.random.default_rng(1).standard_normal((1, 192, 192, 192)).astype(np.float32)).cuda()
 else:

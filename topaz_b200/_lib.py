@@ -75,6 +75,10 @@ _PROTOS = {
     'tpz_conv_fwd_mma': (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P, _I, _I, _P]),
     'tpz_conv_dgrad_mma': (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P]),
     'tpz_conv_wgrad_mma': (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    'tpz_train_repack_tc': (_I, [_P, _P, _I, _LL, _P, _P]),
+    'tpz_conv_fwd_tc': (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P, _I, _I, _P]),
+    'tpz_conv_dgrad_tc': (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P]),
+    'tpz_conv_wgrad_tc': (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     'tpz_first_fwd_f32': (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P, _I, _I, _P]),
     'tpz_first_wgrad_f32': (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P]),
     'tpz_bias_grad_f32': (_I, [_P, _LL, _I, _P, _P]),
@@ -91,6 +95,7 @@ _PROTOS = {
     'tpz_ge_binomial_loss_grad': (_I, [_P, _P, _I, _D, _D, _I, _I, _P, _P, _P]),
     'tpz_pu_objective_loss_grad': (_I, [_P, _P, _I, _I, _D, _D, _D, _D, _I, _I, _P, _P, _P]),
     'tpz_adam_step': (_I, [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _I, _F, _F, _P]),
+    'tpz_adam_step_dev': (_I, [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _P, _F, _F, _P]),
     'tpz_lab_umma': (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _P]),
     'tpz_lab_umma_rate': (_I, [_I, _I, _I, _I, _I, _P, _P]),
     'tpz_lab_tma_stride': (_I, [_P, _I, _I, _I, _I, _P, _P]),

@@ -362,6 +362,135 @@ static int launch_conv_last_tiled(const __half* x, int N, int H, int W, int ld, 
 }
 
 // -------------------------------------------------------------------------------------------------
+// Cout = 1 tail conv, 3-D (UDenoiseNet3D dec1.4: 32 -> 1, 3x3x3, denoising/models.py:505).  On the tensor-core path this layer
+// is an N = 16 GEMM: 54 MMAs per 128 voxels for 0.06 TFLOP (1.1 ms per 192^3 patch, 3.0 ms with split operands).  Here: fp32
+// CUDA-core math on fp16 inputs -- exact products, so split (hi, lo) inputs are simply 2*C channels with the weights
+// repeated, and no weight split is needed.  A block owns a 16 x 32 (y, x) tile and marches along z: every input plane is
+// staged ONCE (16 channels at a time, 48-byte voxel stride = conflict-free 16-byte loads) and feeds the three output planes
+// it touches; a thread owns 4 y-adjacent outputs x 3 z-planes in flight = 12 accumulators, the 27 x 8 weights of one
+// (x-tap, 8-channel) slice live in registers, so each 16-byte shared load feeds up to 72 FMAs.
+// -------------------------------------------------------------------------------------------------
+template <int C>       // stored input channels that carry data (32: fp16; 64: hi | lo halves, weights repeated)
+__global__ void __launch_bounds__(128, 3) conv_last3d_tiled_kernel(const __half* __restrict__ x, int N, int D, int H, int W, int ld,
+                                                                   const float* __restrict__ w /*[27][C]*/, float bias,
+                                                                   const float* __restrict__ stats, const float* __restrict__ range,
+                                                                   float* __restrict__ out, int tiles_x, int tiles_y, int zchunks, int TZ) {
+  constexpr int TX = 32, TY = 16, PX = TX + 2, PY = TY + 2, PST = 48;     // staged voxel: 16 channels (32 B) + 16 B pad
+  extern __shared__ __align__(16) unsigned char smem_l3[];
+  unsigned char* tile = smem_l3;                                          // [PY][PX][PST]
+  float* sw = reinterpret_cast<float*>(smem_l3 + PY * PX * PST);          // [27][C]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 27 * C; i += 128) sw[i] = w[i];
+  const int tx = tid & 31, tg = tid >> 5;
+  long long b = blockIdx.x;
+  const int zc = (int)(b % zchunks); b /= zchunks;
+  const int tr = (int)(b % ((long long)tiles_x * tiles_y));
+  const int n = (int)(b / ((long long)tiles_x * tiles_y));
+  const int x0 = (tr % tiles_x) * TX, y0 = (tr / tiles_x) * TY;
+  const int z0 = zc * TZ, z1 = min(D, z0 + TZ);
+  const float inv_s = range ? range[1] : 1.f;
+  float acc[3][4];        // acc[k][j]: output plane (zi - 1 + k) for the input plane zi being processed, rows tg*4 + j
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[k][j] = 0.f;
+  for (int zi = z0 - 1; zi <= z1; ++zi) {
+    if (zi >= 0 && zi < D) {
+#pragma unroll 1
+      for (int c16 = 0; c16 < C; c16 += 16) {
+        __syncthreads();                                   // previous slice consumed (first pass: orders the weight staging)
+        for (int i = tid; i < PY * PX * 2; i += 128) {
+          const int half = i & 1, p = i >> 1;
+          const int wx = p % PX, wy = p / PX;
+          const int ix = x0 + wx - 1, iy = y0 + wy - 1;
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (ix >= 0 && ix < W && iy >= 0 && iy < H)
+            v = *reinterpret_cast<const uint4*>(x + ((((size_t)n * D + zi) * H + iy) * W + ix) * ld + c16 + half * 8);
+          *reinterpret_cast<uint4*>(tile + (size_t)p * PST + half * 16) = v;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int s = 0; s < 3; ++s) {
+#pragma unroll 1
+          for (int sub = 0; sub < 2; ++sub) {
+            float wr[3][3][8];                             // [z-tap q][y-tap r][channel]
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+#pragma unroll
+              for (int r = 0; r < 3; ++r) {
+                const float* wp = sw + ((q * 3 + r) * 3 + s) * C + c16 + sub * 8;
+                const float4 a = *reinterpret_cast<const float4*>(wp);
+                const float4 bq = *reinterpret_cast<const float4*>(wp + 4);
+                wr[q][r][0] = a.x; wr[q][r][1] = a.y; wr[q][r][2] = a.z; wr[q][r][3] = a.w;
+                wr[q][r][4] = bq.x; wr[q][r][5] = bq.y; wr[q][r][6] = bq.z; wr[q][r][7] = bq.w;
+              }
+            const unsigned char* col = tile + (size_t)((tg * 4) * PX + tx + s) * PST + sub * 16;
+#pragma unroll
+            for (int row = 0; row < 6; ++row) {
+              const uint4 u = *reinterpret_cast<const uint4*>(col + (size_t)row * PX * PST);
+              const __half2* h = reinterpret_cast<const __half2*>(&u);
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { const float2 t2 = __half22float2(h[e]); f[2 * e] = t2.x; f[2 * e + 1] = t2.y; }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int r = row - j;                     // output row j sees this input row through y-tap r
+                if (r >= 0 && r < 3) {
+#pragma unroll
+                  for (int k = 0; k < 3; ++k) {            // output plane zi - 1 + k sees input plane zi through z-tap q = 2 - k
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[k][j] = fmaf(f[e], wr[2 - k][r][e], acc[k][j]);
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    // output plane zi - 1 is complete once input plane zi has been added
+    const int zo = zi - 1;
+    if (zo >= z0 && zo < z1) {
+      const int ox = x0 + tx;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int oy = y0 + tg * 4 + j;
+        if (ox < W && oy < H) {
+          float v = fmaf(acc[0][j], inv_s, bias);
+          if (stats) v = v * stats[1] + stats[0];
+          out[(((size_t)n * D + zo) * H + oy) * W + ox] = v;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[0][j] = acc[1][j]; acc[1][j] = acc[2][j]; acc[2][j] = 0.f; }
+  }
+}
+
+template <int C>
+static int launch_conv_last3d(const __half* x, int N, int D, int H, int W, int ld, const float* w, float bias, const float* stats,
+                              const float* range, float* out, cudaStream_t stream) {
+  constexpr int TX = 32, TY = 16;
+  const int smem = (TY + 2) * (TX + 2) * 48 + 27 * C * (int)sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    TPZ_CUDA(cudaFuncSetAttribute(conv_last3d_tiled_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int tiles_x = tpz_div_up(W, TX), tiles_y = tpz_div_up(H, TY);
+  // z chunks: enough blocks for ~2 waves of 3 blocks per SM, at most 1/8 redundant halo planes
+  int TZ = D;
+  while (TZ > 16 && (long long)tiles_x * tiles_y * N * tpz_div_up(D, TZ) < 148 * 6) TZ = (TZ + 1) / 2;
+  const int zchunks = tpz_div_up(D, TZ);
+  const long long blocks = (long long)tiles_x * tiles_y * N * zchunks;
+  TPZ_CHECK(blocks > 0 && blocks < (1ll << 31), "tpz_conv_last: bad block count %lld", blocks);
+  conv_last3d_tiled_kernel<C><<<(unsigned)blocks, 128, smem, stream>>>(x, N, D, H, W, ld, w, bias, stats, range, out, tiles_x,
+                                                                         tiles_y, zchunks, TZ);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
 // Generic conv (validation / uncovered shapes): one thread per (output pixel, 8 output channels).
 // -------------------------------------------------------------------------------------------------
 __global__ void conv_generic_kernel(const __half* __restrict__ x0, int C0, int ld0, const __half* __restrict__ x1,
@@ -703,6 +832,10 @@ extern "C" int tpz_conv_last(const tpz_half* x, int N, int D, int H, int W, int 
     const __half* xh = HCP(x);
     if (kh == 5) return launch_conv_last_tiled<32, 5>(xh, N * D, H, W, ld, w, bias, out_scale, out_shift, affine_stats, out, range, ST(stream));
     return launch_conv_last_tiled<32, 3>(xh, N * D, H, W, ld, w, bias, out_scale, out_shift, affine_stats, out, range, ST(stream));
+  }
+  if (kd == 3 && kh == 3 && kw == 3 && dil == 1 && pad == 1 && (C == 32 || C == 64) && out_scale == 1.f && out_shift == 0.f) {
+    if (C == 32) return launch_conv_last3d<32>(HCP(x), N, D, H, W, ld, w, bias, affine_stats, range, out, ST(stream));
+    return launch_conv_last3d<64>(HCP(x), N, D, H, W, ld, w, bias, affine_stats, range, out, ST(stream));
   }
   const size_t total = (size_t)N * D * H * W;
   conv_last_kernel<<<tpz_div_up(total, 128), 128, 0, ST(stream)>>>(HCP(x), N, D, H, W, C, ld, w, bias, kd, kh, kw,

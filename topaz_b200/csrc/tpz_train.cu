@@ -515,6 +515,25 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
   }
 }
 
+// Adam with the step count kept on the device (CUDA-graph replay of a whole training step: the bias corrections must not be
+// baked into the captured launch).  step_inc_kernel advances the counter, adam_dev_kernel derives the corrections from it.
+__global__ void step_inc_kernel(int* step) { step[0] += 1; }
+__global__ void adam_dev_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                long long n, float lr, float b1, float b2, float eps, const int* __restrict__ step, float l2,
+                                float gscale) {
+  const float t = (float)step[0];
+  const float bc1 = 1.f - powf(b1, t);
+  const float bc2_sqrt = sqrtf(1.f - powf(b2, t));
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale + l2 * p[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] -= (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
+    g[i] = 0.f;
+  }
+}
+
 }  // namespace
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
@@ -654,6 +673,17 @@ extern "C" int tpz_adam_step(float* params, float* grads, float* exp_avg, float*
   int grid = tpz_div_up(n, 256 * 4); if (grid > 148 * 8) grid = 148 * 8;
   adam_kernel<<<grid, 256, 0, ST(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, bc2, l2,
                                             grad_scale);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tpz_adam_step_dev(float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                                 float beta1, float beta2, float eps, int* step_dev, float l2, float grad_scale, void* stream) {
+  TPZ_CHECK(step_dev != nullptr, "tpz_adam_step_dev: null step counter");
+  int grid = tpz_div_up(n, 256 * 4); if (grid > 148 * 8) grid = 148 * 8;
+  step_inc_kernel<<<1, 1, 0, ST(stream)>>>(step_dev);
+  adam_dev_kernel<<<grid, 256, 0, ST(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step_dev, l2,
+                                                grad_scale);
   TPZ_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,0 +1,628 @@
+// tcgen05 (5th-generation tensor core) versions of the TRAINING convolutions: forward, data-gradient and weight-gradient
+// of the strided classifier (reference call sites: `score = self.model(X)` methods.py:103, `loss.backward()` :146).
+//
+// fp32 in / fp32 out at fp32-level accuracy: error-compensated 3xTF32 on `tcgen05.mma.kind::tf32`.  Every operand value
+// x is split ONCE, by the thread that stages it, into hi = x rounded to 10 mantissa bits and lo = x - hi (exact in fp32;
+// the tensor core reads the top 19 bits of lo), and the product is accumulated as a_hi*b_hi + a_hi*b_lo + a_lo*b_hi in the
+// fp32 TMEM accumulator.  The mma.sync kernels (tpz_train_mma.cu) re-split every fragment in every warp that uses it and
+// spend 3-7 issue slots per HMMA on it; here the split costs 3 ALU ops per staged value and the MMAs are issued by one thread.
+//
+//   forward / dgrad: gather-GEMM.  M = 128 pixels of the op's OUTPUT tensor (thread m stages row m: the 32 channels of one
+//       tap of its source pixel = one 128-byte row, written hi / lo into the canonical K-major SWIZZLE_128B layout with
+//       generic stores + fence.proxy.async -- the tpz_first_tc.cu pattern), N = 32 / 64 output channels, K = (tap, 32-channel
+//       chunk).  Weights are pre-split per step by tpz_train_repack_tc into [tap][chunk][n][32] hi / lo planes and arrive by TMA.
+//   wgrad: D[(tap, ci)][co] = sum over pixels of x[p'(p, tap)][ci] * dy[p][co].  M = 128 (tap, ci) pairs, N = co tile,
+//       K = 32 output pixels per chunk; both operands are pixel-major in memory, so the staging warps transpose while they
+//       write (lane = pixel: a warp's 32 four-byte stores fill one 128-byte row, conflict-free).  Split-K over the pixels,
+//       fp32 atomics into the flat gradient (zeroed by the Adam kernel).
+//   Accumulation: the tensor core's fp32 accumulate truncates (tpz_train_mma.cu: a chain of ~430 accumulations drifts by 2e-5,
+//       enough to flip ReLU masks against the fp32 reference).  The MMA chain alternates between two TMEM accumulators every
+//       `flush` chunks and the finished one is drained into registers with round-to-nearest FADDs while the other one fills.
+#include "tpz_common.cuh"
+#include "../../include/topaz_b200.h"
+#include <stdlib.h>
+
+namespace {
+
+struct TGeom {
+  int N, H, W, Ci;   // conv input  (x / dx)
+  int Ho, Wo, Co;    // conv output (y / dy)
+  int kh, kw, stride, dil, org;
+};
+
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(ptx::smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded spin: a protocol error traps after a few seconds instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spins = 0; !mbar_try(bar, parity); ++spins)
+    if (spins > (1u << 27)) __trap();
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, TF32 operands (fp32 containers, low 13 mantissa bits ignored), fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// instruction descriptor, kind::tf32: A/B = TF32 (2), D = F32 (1), both K-major, M x N
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// hi = x rounded (half away from zero) to 10 mantissa bits, lo = x - hi (exact); finite inputs
+__device__ __forceinline__ void split1(float v, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+  lo = v - hi;
+}
+__device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
+  split1(v.x, hi.x, lo.x); split1(v.y, hi.y, lo.y); split1(v.z, hi.z, lo.z); split1(v.w, hi.w, lo.w);
+}
+
+constexpr int kStageA = 128 * 128;          // one operand plane of a stage: 128 rows x 128 B (32 fp32)
+
+// -------------------------------------------------------------------------------------------------
+// weight repack for the TMA-fed B operand: OIHW -> fwd [tap][ci/32][co][32] and dgrad [tap][co/32][ci][32], each as a hi plane
+// followed by a lo plane
+// -------------------------------------------------------------------------------------------------
+struct RepackTcDesc { long long src, dst_fwd, dst_dg; int Co, Ci, taps, pad; };
+
+__global__ void repack_tc_kernel(const float* __restrict__ flat, const RepackTcDesc* __restrict__ descs, float* __restrict__ packed) {
+  const RepackTcDesc d = descs[blockIdx.y];
+  const long long n = (long long)d.Co * d.Ci * d.taps;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int tap = i % d.taps;
+    const long long q = i / d.taps;
+    const int ci = q % d.Ci, co = q / d.Ci;
+    float hi, lo;
+    split1(flat[d.src + i], hi, lo);
+    const long long f = (((long long)tap * (d.Ci >> 5) + (ci >> 5)) * d.Co + co) * 32 + (ci & 31);
+    const long long g = (((long long)tap * (d.Co >> 5) + (co >> 5)) * d.Ci + ci) * 32 + (co & 31);
+    packed[d.dst_fwd + f] = hi; packed[d.dst_fwd + n + f] = lo;
+    packed[d.dst_dg + g] = hi; packed[d.dst_dg + n + g] = lo;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// forward / dgrad gather-GEMM
+// -------------------------------------------------------------------------------------------------
+struct FwdArgs {
+  TGeom g;
+  const float* src;       // fwd: x [N][H][W][Ci]; dgrad: dy [N][Ho][Wo][Co]
+  CUtensorMap tmB;        // packed weights: rows of 32 fp32 (declared to TMA as 64 fp16), box = BN rows
+  long long lo_rows;      // row offset of the lo plane inside the packed weight tensor
+  const float* bias; const float* res; int res_H, res_W, res_org, res_stride;
+  const float* mask; float* out; int relu, accumulate, flush;
+};
+
+template <int BN, int MODE>      // MODE 0 forward, 1 data gradient
+__global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ FwdArgs a) {
+  constexpr uint32_t IDESC = idesc_tf32(128, BN);
+  constexpr int B_BYTES = BN * 128;
+  constexpr int STAGE = 2 * kStageA + 2 * B_BYTES;          // A_hi | A_lo | B_hi | B_lo
+  constexpr int TCOLS = 2 * BN < 32 ? 32 : 2 * BN;          // two accumulators
+
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t bar_free[2], bar_b[2], bar_acc[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const TGeom& g = a.g;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int taps = g.kh * g.kw;
+  const int Cs = MODE == 0 ? g.Ci : g.Co;        // source channels (K per tap)
+  const int Nn = MODE == 0 ? g.Co : g.Ci;        // output channels
+  const int MH = MODE == 0 ? g.Ho : g.H, MW = MODE == 0 ? g.Wo : g.W;
+  const int SH = MODE == 0 ? g.H : g.Ho, SW = MODE == 0 ? g.W : g.Wo;
+  const long long Mtot = (long long)g.N * MH * MW;
+  const long long m = (long long)blockIdx.x * 128 + tid;
+  const int n0 = blockIdx.y * BN;
+  const int cchunks = Cs >> 5;
+  const int nk = taps * cchunks;
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&bar_free[s], 1); ptx::mbar_init(&bar_b[s], 1); ptx::mbar_init(&bar_acc[s], 1); }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&a.tmB);
+  }
+  if (warp == 0) ptx::tmem_alloc<TCOLS>(&tmem_base_s);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  // this thread's output pixel
+  const bool row_ok = m < Mtot;
+  int px = 0, py = 0, pn = 0;
+  if (row_ok) { px = (int)(m % MW); const long long q = m / MW; py = (int)(q % MH); pn = (int)(q / MH); }
+
+  // source pixel of (row, tap): recomputed when the tap changes
+  int t_r = 0, t_t = 0, t_c = 0;
+  long long a_off = 0;
+  bool a_ok = false;
+  auto tap_setup = [&]() {
+    bool ok = row_ok;
+    int sy = 0, sx = 0;
+    if (ok) {
+      if (MODE == 0) {
+        sy = py * g.stride + t_r * g.dil + g.org;
+        sx = px * g.stride + t_t * g.dil + g.org;
+        ok = sy >= 0 && sy < SH && sx >= 0 && sx < SW;
+      } else {
+        const int ny = py - g.org - t_r * g.dil, nx = px - g.org - t_t * g.dil;
+        ok = ny >= 0 && nx >= 0;
+        if (g.stride == 1) { sy = ny; sx = nx; }
+        else { ok = ok && (ny % g.stride) == 0 && (nx % g.stride) == 0; sy = ny / g.stride; sx = nx / g.stride; }
+        ok = ok && sy < SH && sx < SW;
+      }
+    }
+    a_ok = ok;
+    a_off = ok ? (((long long)pn * SH + sy) * SW + sx) * Cs : 0;
+  };
+  tap_setup();
+
+  // one chunk of this row: 32 fp32 = 8 x 16 B, prefetched into registers one chunk ahead
+  float4 pre[8];
+  auto load_chunk = [&]() {
+    const float4* p = reinterpret_cast<const float4*>(a.src + a_off + t_c);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) pre[c] = a_ok ? __ldg(p + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    t_c += 32;
+    if (t_c == Cs) {
+      t_c = 0;
+      if (++t_t == g.kw) { t_t = 0; ++t_r; }
+      tap_setup();
+    }
+  };
+  load_chunk();
+
+  float tot[BN];
+#pragma unroll
+  for (int j = 0; j < BN; ++j) tot[j] = 0.f;
+  const uint32_t d_hi = ptx::umma_desc_hi(1024, 2);         // SBO = 8 rows x 128 B, SWIZZLE_128B
+  const int flush = a.flush > 0 ? a.flush : (1 << 30);
+  const int sw = tid & 7;
+  uint32_t accf = 0;                                        // 0: the next MMA overwrites its accumulator
+  int cur_acc = 0, in_group = 0, groups_done = 0;
+  auto drain = [&](int acc) {                               // TMEM accumulator -> registers, round-to-nearest adds
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * BN;
+#pragma unroll
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      ptx::tmem_ld32(taddr + c0, r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) tot[c0 + j] += __uint_as_float(r[j]);
+    }
+    ptx::tc_fence_before();
+  };
+
+  for (int kc = 0; kc < nk; ++kc) {
+    const int s = kc & 1;
+    unsigned char* stage = base + (size_t)s * STAGE;
+    if (kc >= 2) mbar_wait(&bar_free[s], ((kc >> 1) - 1) & 1);       // the MMAs that read this stage (chunk kc-2) are done
+    // B: one elected thread asks TMA for the hi and lo weight blocks of this chunk
+    if (tid == 0) {
+      ptx::mbar_expect_tx(&bar_b[s], 2u * B_BYTES);
+      ptx::tma_load_2d(stage + 2 * kStageA, &a.tmB, &bar_b[s], 0, kc * Nn + n0);
+      ptx::tma_load_2d(stage + 2 * kStageA + B_BYTES, &a.tmB, &bar_b[s], 0, (int)a.lo_rows + kc * Nn + n0);
+    }
+    // A: split this row's chunk and store it (16-byte chunk c of row p lands at chunk c ^ (p & 7))
+    {
+      unsigned char* rh = stage + tid * 128;
+      unsigned char* rl = rh + kStageA;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float4 hi, lo;
+        split4(pre[c], hi, lo);
+        *reinterpret_cast<float4*>(rh + ((c ^ sw) << 4)) = hi;
+        *reinterpret_cast<float4*>(rl + ((c ^ sw) << 4)) = lo;
+      }
+    }
+    if (kc + 1 < nk) load_chunk();                          // global loads of the next chunk fly during the MMAs
+    ptx::fence_proxy_async();
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      ptx::tc_fence_after();
+      mbar_wait(&bar_b[s], (kc >> 1) & 1);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t ah = (ptx::smem_u32(stage) & 0x3FFFF) >> 4, al = ah + (kStageA >> 4);
+        const uint32_t bh = al + (kStageA >> 4), bl = bh + (B_BYTES >> 4);
+        const uint32_t d = tmem_base + cur_acc * BN;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          umma_tf32(d, al + 2 * k, d_hi, bh + 2 * k, d_hi, IDESC, accf | (uint32_t)k);      // small terms first
+          umma_tf32(d, ah + 2 * k, d_hi, bl + 2 * k, d_hi, IDESC, 1u);
+          umma_tf32(d, ah + 2 * k, d_hi, bh + 2 * k, d_hi, IDESC, 1u);
+        }
+        ptx::umma_commit(&bar_free[s]);
+        if (in_group + 1 == flush || kc + 1 == nk) ptx::umma_commit(&bar_acc[cur_acc]);
+      }
+      __syncwarp();
+    }
+    accf = 1;
+    if (++in_group == flush || kc + 1 == nk) {
+      // this accumulator's group is issued; drain the PREVIOUS group's accumulator while these MMAs run
+      if (groups_done >= 1) {
+        const int prev = cur_acc ^ 1;
+        mbar_wait(&bar_acc[prev], ((groups_done - 1) >> 1) & 1);
+        ptx::tc_fence_after();
+        drain(prev);
+      }
+      ++groups_done;
+      cur_acc ^= 1; in_group = 0; accf = 0;
+    }
+  }
+  {                                                         // last group
+    const int last = cur_acc ^ 1;
+    mbar_wait(&bar_acc[last], ((groups_done - 1) >> 1) & 1);
+    ptx::tc_fence_after();
+    drain(last);
+  }
+
+  // epilogue: this thread owns output row m, channels n0 .. n0 + BN
+  if (row_ok) {
+    long long rbase = 0;
+    if (MODE == 0 && a.res)
+      rbase = (((long long)pn * a.res_H + (py * a.res_stride + a.res_org)) * a.res_W + (px * a.res_stride + a.res_org)) * g.Co;
+    float* orow = a.out + m * Nn + n0;
+#pragma unroll
+    for (int c = 0; c < BN; c += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = tot[c + j];
+      if (MODE == 0) {
+        if (a.bias) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += __ldg(a.bias + n0 + c + j);
+        }
+        if (a.res) {
+          const float4 r0 = __ldg(reinterpret_cast<const float4*>(a.res + rbase + n0 + c));
+          const float4 r1 = __ldg(reinterpret_cast<const float4*>(a.res + rbase + n0 + c + 4));
+          v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+        }
+        if (a.relu) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+      } else {
+        if (a.accumulate) {
+          const float4 o0 = *reinterpret_cast<const float4*>(orow + c), o1 = *reinterpret_cast<const float4*>(orow + c + 4);
+          v[0] += o0.x; v[1] += o0.y; v[2] += o0.z; v[3] += o0.w; v[4] += o1.x; v[5] += o1.y; v[6] += o1.z; v[7] += o1.w;
+        }
+        if (a.mask) {
+          const float4 k0 = __ldg(reinterpret_cast<const float4*>(a.mask + m * Nn + n0 + c));
+          const float4 k1 = __ldg(reinterpret_cast<const float4*>(a.mask + m * Nn + n0 + c + 4));
+          v[0] = k0.x > 0.f ? v[0] : 0.f; v[1] = k0.y > 0.f ? v[1] : 0.f; v[2] = k0.z > 0.f ? v[2] : 0.f; v[3] = k0.w > 0.f ? v[3] : 0.f;
+          v[4] = k1.x > 0.f ? v[4] : 0.f; v[5] = k1.y > 0.f ? v[5] : 0.f; v[6] = k1.z > 0.f ? v[6] : 0.f; v[7] = k1.w > 0.f ? v[7] : 0.f;
+        }
+      }
+      ptx::st_global_256(orow + c, __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]),
+                         __float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7]));
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc<TCOLS>(tmem_base);
+}
+
+// -------------------------------------------------------------------------------------------------
+// wgrad
+// -------------------------------------------------------------------------------------------------
+struct WgArgs {
+  TGeom g;
+  const float* x; const float* dy; float* dw;
+  int k_per_split;        // output pixels per split (multiple of 32)
+  int flush;
+};
+
+template <int BN>                // co tile
+__global__ void __launch_bounds__(128) wgrad_tc_kernel(const WgArgs a) {
+  constexpr uint32_t IDESC = idesc_tf32(128, BN);
+  constexpr int B_BYTES = BN * 128;
+  constexpr int STAGE = 2 * kStageA + 2 * B_BYTES;
+  constexpr int TCOLS = 2 * BN < 32 ? 32 : 2 * BN;
+  constexpr int BQ = BN / 4;                                  // dy channels staged per warp
+
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t bar_free[2], bar_acc[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const TGeom& g = a.g;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int taps = g.kh * g.kw;
+  const int rows_total = taps * g.Ci;                         // (tap, ci) pairs = M extent
+  const int mt = blockIdx.x;                                  // M tile
+  const int co0 = blockIdx.y * BN;
+  const long long P = (long long)g.N * g.Ho * g.Wo;
+  const long long pbeg = (long long)blockIdx.z * a.k_per_split;
+  const long long pend = min(P, pbeg + a.k_per_split);
+  const int nchunks = (int)((pend - pbeg + 31) / 32);
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&bar_free[s], 1); ptx::mbar_init(&bar_acc[s], 1); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) ptx::tmem_alloc<TCOLS>(&tmem_base_s);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  // this warp stages A rows [32*warp, 32*warp + 32) of the tile = 32 consecutive ci of ONE tap (Ci % 32 == 0)
+  const int row0 = mt * 128 + warp * 32;
+  const bool warp_rows_ok = row0 < rows_total;
+  const int tap = warp_rows_ok ? row0 / g.Ci : 0, ci0 = warp_rows_ok ? row0 % g.Ci : 0;
+  const int tr = tap / g.kw, tt = tap - tr * g.kw;
+  if (!warp_rows_ok) {                                        // rows beyond the (tap, ci) range stay zero in both stages
+    for (int s = 0; s < 2; ++s)
+      for (int j = 0; j < 32; ++j) {
+        unsigned char* rh = base + (size_t)s * STAGE + (size_t)(warp * 32 + j) * 128;
+        *reinterpret_cast<float*>(rh + lane * 4) = 0.f;
+        *reinterpret_cast<float*>(rh + kStageA + lane * 4) = 0.f;
+      }
+  }
+
+  // lane = pixel of the chunk; running (n, oy, ox) of that pixel
+  long long ip = pbeg + lane;
+  int i_ox, i_oy, i_n;
+  {
+    const long long pp = ip < P ? ip : 0;
+    i_ox = (int)(pp % g.Wo); const long long q = pp / g.Wo; i_oy = (int)(q % g.Ho); i_n = (int)(q / g.Ho);
+  }
+  float4 prex[8];            // x[p'(p, tap)][ci0 .. ci0+32)
+  float4 prey[BQ / 4];       // dy[p][co0 + warp*BQ .. + BQ)
+  auto load_chunk = [&]() {
+    const bool pv = ip < pend;
+    if (warp_rows_ok) {
+      const int iy = i_oy * g.stride + tr * g.dil + g.org, ix = i_ox * g.stride + tt * g.dil + g.org;
+      const bool ok = pv && iy >= 0 && iy < g.H && ix >= 0 && ix < g.W;
+      const float4* p = reinterpret_cast<const float4*>(a.x + (((long long)i_n * g.H + iy) * g.W + ix) * g.Ci + ci0);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) prex[c] = ok ? __ldg(p + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float4* q = reinterpret_cast<const float4*>(a.dy + ip * g.Co + co0 + warp * BQ);
+#pragma unroll
+    for (int c = 0; c < BQ / 4; ++c) prey[c] = pv ? __ldg(q + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ip += 32;
+    i_ox += 32;
+    while (i_ox >= g.Wo) { i_ox -= g.Wo; if (++i_oy == g.Ho) { i_oy = 0; ++i_n; } }
+  };
+  if (nchunks > 0) load_chunk();
+
+  float tot[BN];
+#pragma unroll
+  for (int j = 0; j < BN; ++j) tot[j] = 0.f;
+  const uint32_t d_hi = ptx::umma_desc_hi(1024, 2);
+  const int flush = a.flush > 0 ? a.flush : (1 << 30);
+  uint32_t accf = 0;
+  int cur_acc = 0, in_group = 0, groups_done = 0;
+  auto drain = [&](int acc) {
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * BN;
+#pragma unroll
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      ptx::tmem_ld32(taddr + c0, r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) tot[c0 + j] += __uint_as_float(r[j]);
+    }
+    ptx::tc_fence_before();
+  };
+  // transposing store: element (row, pixel = lane) of a K-major SWIZZLE_128B tile
+  auto put = [&](unsigned char* plane, int row, float v) {
+    *reinterpret_cast<float*>(plane + (size_t)row * 128 + ((((lane >> 2) ^ (row & 7)) << 4) | ((lane & 3) << 2))) = v;
+  };
+
+  for (int kc = 0; kc < nchunks; ++kc) {
+    const int s = kc & 1;
+    unsigned char* stage = base + (size_t)s * STAGE;
+    if (kc >= 2) mbar_wait(&bar_free[s], ((kc >> 1) - 1) & 1);
+    if (warp_rows_ok) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float4 hi, lo;
+        split4(prex[c], hi, lo);
+        const int r = warp * 32 + c * 4;
+        put(stage, r, hi.x); put(stage, r + 1, hi.y); put(stage, r + 2, hi.z); put(stage, r + 3, hi.w);
+        put(stage + kStageA, r, lo.x); put(stage + kStageA, r + 1, lo.y); put(stage + kStageA, r + 2, lo.z); put(stage + kStageA, r + 3, lo.w);
+      }
+    }
+    {
+      unsigned char* bh = stage + 2 * kStageA;
+#pragma unroll
+      for (int c = 0; c < BQ / 4; ++c) {
+        float4 hi, lo;
+        split4(prey[c], hi, lo);
+        const int r = warp * BQ + c * 4;
+        put(bh, r, hi.x); put(bh, r + 1, hi.y); put(bh, r + 2, hi.z); put(bh, r + 3, hi.w);
+        put(bh + B_BYTES, r, lo.x); put(bh + B_BYTES, r + 1, lo.y); put(bh + B_BYTES, r + 2, lo.z); put(bh + B_BYTES, r + 3, lo.w);
+      }
+    }
+    if (kc + 1 < nchunks) load_chunk();
+    ptx::fence_proxy_async();
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t ah = (ptx::smem_u32(stage) & 0x3FFFF) >> 4, al = ah + (kStageA >> 4);
+        const uint32_t bh = al + (kStageA >> 4), bl = bh + (B_BYTES >> 4);
+        const uint32_t d = tmem_base + cur_acc * BN;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          umma_tf32(d, al + 2 * k, d_hi, bh + 2 * k, d_hi, IDESC, accf | (uint32_t)k);
+          umma_tf32(d, ah + 2 * k, d_hi, bl + 2 * k, d_hi, IDESC, 1u);
+          umma_tf32(d, ah + 2 * k, d_hi, bh + 2 * k, d_hi, IDESC, 1u);
+        }
+        ptx::umma_commit(&bar_free[s]);
+        if (in_group + 1 == flush || kc + 1 == nchunks) ptx::umma_commit(&bar_acc[cur_acc]);
+      }
+      __syncwarp();
+    }
+    accf = 1;
+    if (++in_group == flush || kc + 1 == nchunks) {
+      if (groups_done >= 1) {
+        const int prev = cur_acc ^ 1;
+        mbar_wait(&bar_acc[prev], ((groups_done - 1) >> 1) & 1);
+        ptx::tc_fence_after();
+        drain(prev);
+      }
+      ++groups_done;
+      cur_acc ^= 1; in_group = 0; accf = 0;
+    }
+  }
+  if (groups_done >= 1) {
+    const int last = cur_acc ^ 1;
+    mbar_wait(&bar_acc[last], ((groups_done - 1) >> 1) & 1);
+    ptx::tc_fence_after();
+    drain(last);
+  }
+  // thread `tid` holds row (tap_r, ci_r) of the tile against co0 .. co0 + BN: dw[co][ci][tap] += tot
+  const int row = mt * 128 + tid;
+  if (row < rows_total && nchunks > 0) {
+    const int tap_r = row / g.Ci, ci_r = row - tap_r * g.Ci;
+#pragma unroll
+    for (int j = 0; j < BN; ++j)
+      if (co0 + j < g.Co) atomicAdd(a.dw + ((long long)(co0 + j) * g.Ci + ci_r) * taps + tap_r, tot[j]);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc<TCOLS>(tmem_base);
+}
+
+int g_flush = -1;
+int flush_chunks() {
+  if (g_flush < 0) {
+    const char* e = getenv("TPZ_TRAIN_FLUSH");
+    g_flush = e ? atoi(e) : 2;             // chunks (of 32 K-elements x 3 passes) per accumulator before the round-to-nearest drain
+  }
+  return g_flush;
+}
+
+TGeom tgeom(int N, int H, int W, int Ci, int Ho, int Wo, int Co, int kh, int kw, int stride, int dil, int org) {
+  TGeom g; g.N = N; g.H = H; g.W = W; g.Ci = Ci; g.Ho = Ho; g.Wo = Wo; g.Co = Co; g.kh = kh; g.kw = kw;
+  g.stride = stride; g.dil = dil; g.org = org; return g;
+}
+
+template <int BN, int MODE>
+int launch_conv_tc(const FwdArgs& a, long long M, int Nn, cudaStream_t stream) {
+  constexpr int STAGE = 2 * kStageA + 2 * BN * 128;
+  const int smem = 2 * STAGE + 1024;
+  static bool configured = false;
+  if (!configured) {
+    TPZ_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid(tpz_div_up(M, 128), Nn / BN);
+  conv_tc_kernel<BN, MODE><<<grid, 128, smem, stream>>>(a);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// TMA view of a packed weight tensor: rows of 32 fp32, declared as 64 fp16 (same bytes, same 128-byte swizzle)
+int weight_tmap(CUtensorMap* tm, const float* packed, long long rows, int box_rows) {
+  uint64_t dims[2] = {64, (uint64_t)rows};
+  uint64_t strides[1] = {128};
+  uint32_t box[2] = {64, (uint32_t)box_rows};
+  uint32_t es[2] = {1, 1};
+  return tpz_encode_tmap(tm, packed, 2, dims, strides, box, es, 128);
+}
+
+}  // namespace
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int tpz_train_repack_tc(const float* flat_params, const void* descs, int ndesc, long long max_elems, float* packed,
+                                   void* stream) {
+  if (ndesc == 0) return 0;
+  dim3 grid(tpz_div_up(max_elems, 256 * 4), ndesc);
+  repack_tc_kernel<<<grid, 256, 0, ST(stream)>>>(flat_params, reinterpret_cast<const RepackTcDesc*>(descs), packed);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tpz_conv_fwd_tc(const float* x, int N, int H, int W, int Ci, const float* w_fwd_packed, const float* bias, int Co,
+                               int kh, int kw, int stride, int dil, int org, const float* res, int res_H, int res_W, int res_org,
+                               int res_stride, int relu, float* y, int Ho, int Wo, void* stream) {
+  TPZ_CHECK(Ci % 32 == 0 && Co % 32 == 0, "tpz_conv_fwd_tc: needs Ci%%32==0 and Co%%32==0 (Ci=%d Co=%d)", Ci, Co);
+  FwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.g = tgeom(N, H, W, Ci, Ho, Wo, Co, kh, kw, stride, dil, org);
+  a.src = x; a.bias = bias; a.res = res; a.res_H = res_H; a.res_W = res_W; a.res_org = res_org; a.res_stride = res_stride;
+  a.out = y; a.relu = relu; a.flush = flush_chunks();
+  const long long rows = (long long)kh * kw * (Ci / 32) * Co;
+  a.lo_rows = rows;
+  const int BN = Co % 64 == 0 ? 64 : 32;
+  int rc = weight_tmap(&a.tmB, w_fwd_packed, 2 * rows, BN);
+  if (rc) return rc;
+  const long long M = (long long)N * Ho * Wo;
+  return BN == 64 ? launch_conv_tc<64, 0>(a, M, Co, ST(stream)) : launch_conv_tc<32, 0>(a, M, Co, ST(stream));
+}
+
+extern "C" int tpz_conv_dgrad_tc(const float* dy, int N, int Ho, int Wo, int Co, const float* w_dg_packed, int Ci, int kh, int kw,
+                                 int stride, int dil, int org, const float* relu_mask, int accumulate, float* dx, int H, int W,
+                                 void* stream) {
+  TPZ_CHECK(Ci % 32 == 0 && Co % 32 == 0, "tpz_conv_dgrad_tc: needs Ci%%32==0 and Co%%32==0 (Ci=%d Co=%d)", Ci, Co);
+  FwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.g = tgeom(N, H, W, Ci, Ho, Wo, Co, kh, kw, stride, dil, org);
+  a.src = dy; a.mask = relu_mask; a.accumulate = accumulate; a.out = dx; a.flush = flush_chunks();
+  const long long rows = (long long)kh * kw * (Co / 32) * Ci;
+  a.lo_rows = rows;
+  const int BN = Ci % 64 == 0 ? 64 : 32;
+  int rc = weight_tmap(&a.tmB, w_dg_packed, 2 * rows, BN);
+  if (rc) return rc;
+  const long long M = (long long)N * H * W;
+  return BN == 64 ? launch_conv_tc<64, 1>(a, M, Ci, ST(stream)) : launch_conv_tc<32, 1>(a, M, Ci, ST(stream));
+}
+
+extern "C" int tpz_conv_wgrad_tc(const float* x, int N, int H, int W, int Ci, const float* dy, int Ho, int Wo, int Co, int kh,
+                                 int kw, int stride, int dil, int org, float* dw, void* stream) {
+  TPZ_CHECK(Ci % 32 == 0 && Co % 32 == 0, "tpz_conv_wgrad_tc: needs Ci%%32==0 and Co%%32==0 (Ci=%d Co=%d)", Ci, Co);
+  WgArgs a;
+  a.g = tgeom(N, H, W, Ci, Ho, Wo, Co, kh, kw, stride, dil, org);
+  a.x = x; a.dy = dy; a.dw = dw; a.flush = flush_chunks();
+  const long long P = (long long)N * Ho * Wo;
+  const int BN = Co % 64 == 0 ? 64 : 32;
+  const int mt = tpz_div_up((long long)kh * kw * Ci, 128), nt = Co / BN;
+  // split the pixels so that ~2 waves of 2 CTAs per SM are in flight, at least 8 chunks of 32 pixels per split
+  int splits = (148 * 4) / (mt * nt);
+  if (splits < 1) splits = 1;
+  long long kps = (P + splits - 1) / splits;
+  kps = (kps + 31) / 32 * 32;
+  if (kps < 256) kps = 256;
+  splits = (int)((P + kps - 1) / kps);
+  a.k_per_split = (int)kps;
+  dim3 grid(mt, nt, splits);
+  if (BN == 64) {
+    constexpr int smem = 2 * (2 * kStageA + 2 * 64 * 128) + 1024;
+    static bool configured = false;
+    if (!configured) { TPZ_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); configured = true; }
+    wgrad_tc_kernel<64><<<grid, 128, smem, ST(stream)>>>(a);
+  } else {
+    constexpr int smem = 2 * (2 * kStageA + 2 * 32 * 128) + 1024;
+    static bool configured = false;
+    if (!configured) { TPZ_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); configured = true; }
+    wgrad_tc_kernel<32><<<grid, 128, smem, ST(stream)>>>(a);
+  }
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -497,7 +497,8 @@ def _build_unet_plan(model, device):
             pl = ops.pack_tc_conv([ConvPart(cc.weight, _rup(cin), 1, same_org(kl), split=nl in S)], None, 16, 1.0, device,
                                   dot_w=onehot0, dot_b=float(cc.bias.detach()[0]), strict=nl in S, split_out=False)
             plan['dec'][1] = dict(last_tc=pl, up2=up2, a=pa, b=pb, onehot=onehot.contiguous().to(device), k=k, ntap_store=_tap_ld(ntap),
-                                  last_w=wl.contiguous().to(device), last_b=float(cc.bias.detach()[0]),
+                                  last_w=wl.contiguous().to(device), last_w2=torch.cat([wl, wl], dim=1).contiguous().to(device),
+                                  last_b=float(cc.bias.detach()[0]),
                                   last_k=(kl if dims == 3 else 1, kl, kl), last_pad=kl // 2, last_c=cin,
                                   last_strict=nl in S, raw_split=split.get('raw', False))
     return plan
@@ -577,14 +578,20 @@ def unet_forward(model, x: torch.Tensor, denorm_stats: Optional[torch.Tensor] = 
                 ops.tc_conv(d['a'], [up, raw], (N, D, H, W), out=o, rng=rng)
             o2 = torch.empty((N, D, H, W, d['b'].out_channels), dtype=torch.float16, device=x.device)
             ops.tc_conv(d['b'], [o], (N, D, H, W), out=o2, rng=rng)
-            last_simt = not d['last_strict'] and (LAST_MODE == 'simt' or (LAST_MODE == 'auto' and dims == 2 and d['last_w'].shape[1] == 32
-                                                                          and d['last_k'][1] in (3, 5)))
+            # Cout = 1 tail on the CUDA cores (fp32 math on the fp16 inputs): 2-D tiled kernel for 3x3 / 5x5, 3-D z-marching
+            # kernel for 3x3x3 -- the latter also takes split (hi, lo) inputs as 2*C channels with the weights repeated
+            tiled3d = dims == 3 and d['last_w'].shape[1] == 32 and d['last_k'] == (3, 3, 3)
+            if d['last_strict']:
+                last_simt = LAST_MODE != 'tc' and tiled3d
+            else:
+                last_simt = LAST_MODE == 'simt' or (LAST_MODE == 'auto' and d['last_w'].shape[1] == 32 and
+                                                    ((dims == 2 and d['last_k'][1] in (3, 5)) or tiled3d))
             if not last_simt:
                 y = torch.empty((N, D, H, W), dtype=torch.float32, device=x.device)
                 ops.tc_conv(d['last_tc'], [o2], (N, D, H, W), out=None, dot_out=y, dot_affine=denorm_stats, rng=rng)
             else:
-                y = ops.conv_last(o2, d['last_c'], d['last_w'], d['last_b'], d['last_k'], 1, d['last_pad'],
-                                  stats=denorm_stats, rng=rng)
+                y = ops.conv_last(o2, d['last_c'], d['last_w2'] if d['last_strict'] else d['last_w'], d['last_b'], d['last_k'], 1,
+                                  d['last_pad'], stats=denorm_stats, rng=rng)
     if dims == 2:
         return y.view(y.shape[0], 1, y.shape[2], y.shape[3])
     return y.view(y.shape[0], 1, y.shape[1], y.shape[2], y.shape[3])

@@ -55,11 +55,11 @@ class _Objective:
     def _loss(self, gs, gy, lo, hi, dscore, out):
         raise NotImplementedError
 
-    def _run(self, X, Y):
-        ops.require_cuda(X, 'training minibatch')
+    # ---- one training step = device-side body (forward, collectives, loss, backward, Adam) + one host read-back ----
+    def _step_body(self, X, Y):
+        """Everything of a step that runs on the device; writes the loss / metric floats to self._out.  Free of host
+        synchronisation and of step-dependent host scalars, so it can be captured into a CUDA graph."""
         model = self.model
-        if not model.training:
-            model.train()
         fp = train_engine.flat_params(model)
         score = model(X).view(-1)
         Yd = Y.to(device=score.device, dtype=torch.float64).view(-1)
@@ -67,10 +67,23 @@ class _Objective:
         dist = _dist()
         if dist is not None:
             world, rank = dist.get_world_size(), dist.get_rank()
-            gs = torch.empty(world * b, dtype=torch.float32, device=score.device)
-            gy = torch.empty(world * b, dtype=torch.float64, device=score.device)
-            dist.all_gather_into_tensor(gs, score.contiguous())
-            dist.all_gather_into_tensor(gy, Yd.contiguous())
+            if self.__dict__.get('_checked_b') != b:
+                # the gather below (and the global-minibatch BatchNorm count) assume the same shard size on every rank; an
+                # uneven last minibatch would otherwise hang or corrupt the gather.  Checked once per shard size.
+                sizes = [None] * world
+                dist.all_gather_object(sizes, int(b))
+                if any(v != b for v in sizes):
+                    raise ValueError(f'topaz_b200: data-parallel step needs equal minibatch shards on all ranks, got {sizes}')
+                self._checked_b = b
+            # ONE all-gather for logits + labels: each rank contributes [b logits | b fp64 labels viewed as 2b floats]
+            mine = torch.empty(3 * b, dtype=torch.float32, device=score.device)
+            mine[:b] = score
+            mine[b:].view(torch.float64).copy_(Yd)
+            allb = torch.empty(world * 3 * b, dtype=torch.float32, device=score.device)
+            dist.all_gather_into_tensor(allb, mine)
+            allb = allb.view(world, 3 * b)
+            gs = allb[:, :b].reshape(-1)
+            gy = allb[:, b:].contiguous().view(torch.float64).reshape(-1)
             lo, hi = rank * b, (rank + 1) * b
         else:
             gs, gy, lo, hi = score.contiguous(), Yd.contiguous(), 0, b
@@ -81,11 +94,85 @@ class _Objective:
                 self._host = self._host.pin_memory()
         dscore = torch.empty(b, dtype=torch.float32, device=score.device)
         self._loss(gs, gy, lo, hi, dscore, self._out)
-        train_engine.backward(model, dscore)
-        if dist is not None:
-            dist.all_reduce(fp.flat_g, op=dist.ReduceOp.SUM)
+        if dist is None:
+            train_engine.backward(model, dscore)
+        else:
+            # the flat gradient is laid out in forward order and produced back to front: all-reduce each finished suffix
+            # bucket asynchronously while the earlier layers are still back-propagating; Adam waits for all of them
+            works, done = [], [fp.n]
+
+            def suffix(off, final=False):
+                if off < done[0] and (final or done[0] - off >= self.bucket_elems):
+                    works.append(dist.all_reduce(fp.flat_g[off:done[0]], op=dist.ReduceOp.SUM, async_op=True))
+                    done[0] = off
+            train_engine.backward(model, dscore, on_suffix_done=suffix)
+            suffix(0, final=True)
+            for w in works:
+                w.wait()
         lr, b1, b2, eps = self._hyper()
         train_engine.adam_step(fp, lr, b1, b2, eps, self.l2)
+        return fp
+
+    bucket_elems = 1 << 16          # all-reduce buckets of >= 256 KB (the collective is latency-bound below that)
+
+    def _graph_key(self, X, Y, fp):
+        return (tuple(X.shape), X.dtype, tuple(Y.shape), Y.dtype, str(X.device), id(fp), self._hyper(), float(self.l2),
+                self._loss_key(), _dist() is not None, tuple(m.training for m in self.model.modules()))
+
+    def _loss_key(self):
+        return tuple(float(v) if isinstance(v, (int, float)) else v for v in
+                     (getattr(self, k, None) for k in ('pi', 'slack', 'momentum', 'beta')))
+
+    def _graph_ok(self, X):
+        """CUDA-graph replay of the step: on by default for single-process training (TPZ_TRAIN_GRAPH=0 disables; =dp also
+        captures the NCCL collectives of data-parallel steps).  Not with active dropout (its Philox offset advances on the
+        host) nor with an objective whose loss arguments change from step to step (GE_KL with momentum < 1)."""
+        import os
+        mode = os.environ.get('TPZ_TRAIN_GRAPH', '1')
+        if mode == '0' or not X.is_cuda:
+            return False
+        if _dist() is not None and mode != 'dp':
+            return False
+        if getattr(self, 'momentum', 1.0) < 1:
+            return False
+        return not any(isinstance(m, nn.Dropout) and m.training and m.p > 0 for m in self.model.modules())
+
+    def _run(self, X, Y):
+        ops.require_cuda(X, 'training minibatch')
+        model = self.model
+        if not model.training:
+            model.train()
+        fp = train_engine.flat_params(model)
+        st = self.__dict__.setdefault('_graph_state', dict(key=None, seen=0, graph=None))
+        key = self._graph_key(X, Y, fp) if self._graph_ok(X) else None
+        if key is None or key != st['key']:
+            st.update(key=key, seen=0, graph=None)          # new shapes / parameters / hyper-parameters: start over (eagerly)
+        if key is not None and st['graph'] is None and st['seen'] >= 2:
+            # third step with this signature: capture.  The two eager steps built the flat buffers, kernel attributes and
+            # NCCL communicators; the capture records one more real step on static copies of the minibatch.
+            try:
+                sx, sy = X.clone(), Y.clone()
+                l0 = ops.LAUNCH_COUNT
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._step_body(sx, sy)
+                fp.step -= 1                                  # capture does not execute: undo the host mirror's increment
+                st.update(graph=g, sx=sx, sy=sy, launches=ops.LAUNCH_COUNT - l0)
+            except Exception as e:
+                import sys
+                print(f'topaz_b200: CUDA-graph capture of the training step failed ({type(e).__name__}: {e}); running eagerly',
+                      file=sys.stderr)
+                torch.cuda.synchronize()
+                st.update(key=('failed',), graph=None)
+                key = None
+        if key is not None and st['graph'] is not None:
+            st['sx'].copy_(X, non_blocking=True); st['sy'].copy_(Y, non_blocking=True)
+            st['graph'].replay()
+            fp.step += 1
+            ops._count(st['launches'])
+        else:
+            self._step_body(X, Y)
+            st['seen'] += 1
         model.__dict__['_tpz_epoch'] = model.features.__dict__['_tpz_epoch'] = fp.step
         self._sync_optim_state(fp)
         return [float(v) for v in train_engine.read_back(self._out, self._host)]

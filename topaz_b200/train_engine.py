@@ -51,6 +51,7 @@ class FlatParams:
             off += k
         self.n = n
         self.step = 0
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)      # device mirror of `step` (graph-replayed Adam)
         self.ptrs = tuple(p.data_ptr() for p in self.params)
         # packed copies of the conv weights for the tensor-core training kernels (refreshed after every update)
         self.packed_off = {}
@@ -71,7 +72,45 @@ class FlatParams:
         for i, d in enumerate(descs):
             rec[i] = (d[0], d[1], d[2], d[3], d[4], d[5], 0)
         self.descs = torch.from_numpy(rec.view(_np.uint8).copy()).to(dev) if descs else None
+        # tcgen05 kernels: hi / lo planes in the TMA-friendly [tap][chunk][n][32] layout (4 x numel per eligible weight)
+        self.packed_tc_off = {}
+        descs_tc, toff, mx_tc = [], 0, 0
+        for p, off in zip(self.params, self.offsets):
+            if p.dim() == 4 and p.shape[1] % 32 == 0 and p.shape[0] % 32 == 0:
+                co, ci, kh, kw = p.shape
+                k = p.numel()
+                self.packed_tc_off[id(p)] = (toff, toff + 2 * k)
+                descs_tc.append((off, toff, toff + 2 * k, co, ci, kh * kw))
+                toff += 4 * k
+                mx_tc = max(mx_tc, k)
+        self.packed_tc = torch.empty(max(toff, 1), dtype=torch.float32, device=dev)
+        self.ndesc_tc, self.max_elems_tc = len(descs_tc), mx_tc
+        rec2 = _np.zeros(len(descs_tc), dtype=rec.dtype)
+        for i, d in enumerate(descs_tc):
+            rec2[i] = (d[0], d[1], d[2], d[3], d[4], d[5], 0)
+        self.descs_tc = torch.from_numpy(rec2.view(_np.uint8).copy()).to(dev) if descs_tc else None
         self.packed_step = -1
+        self.packed_versions = None
+        # data parallel: replicas must start from identical parameters and optimizer state (nothing else enforces it);
+        # rank 0's values win, as with torch's DistributedDataParallel
+        dist = _dp()
+        if dist is not None:
+            dist.broadcast(self.flat_p, 0)
+
+    def versions(self):
+        """in-place version counters of the parameters: load_state_dict / p.data.copy_ / a broadcast bump them"""
+        return tuple(p._version for p in self.params)
+
+    def set_step(self, step: int):
+        self.step = int(step)
+        self.step_dev.fill_(int(step))
+
+    def packed_tc_ptrs(self, w):
+        """(forward-layout, dgrad-layout) views of the tcgen05 packed copy (hi | lo planes) of conv weight `w`, or None."""
+        o = self.packed_tc_off.get(id(w))
+        if o is None:
+            return None
+        return self.packed_tc[o[0]:], self.packed_tc[o[1]:]
 
     def packed_ptrs(self, w):
         """(forward-layout, dgrad-layout) views of the packed copy of conv weight `w`, or None."""
@@ -103,21 +142,30 @@ def flat_params(model) -> FlatParams:
                 and old.n == fp.n:
             fp.flat_m.copy_(old.flat_m)
             fp.flat_v.copy_(old.flat_v)
-            fp.step = old.step
+            fp.set_step(old.step)
         model.__dict__['_tpz_flat'] = fp
     return fp
 
 
 _CUR = {'fp': None}      # FlatParams of the model whose step is running (packed weights for the mma kernels)
 USE_MMA = os.environ.get('TPZ_TRAIN_SIMT') is None
+# tcgen05 (kind::tf32, 3-pass) training convolutions for channel counts that are multiples of 32; TPZ_TRAIN_TC=0 -> mma.sync
+USE_TC = USE_MMA and os.environ.get('TPZ_TRAIN_TC', '0') == '1'
 
 
-def _repack(fp):
-    """Refresh the packed weight copies after a parameter update (one launch for all layers)."""
-    if fp.ndesc and fp.packed_step != fp.step:
+def _repack(fp, force: bool = False):
+    """Refresh the packed weight copies after a parameter update (one launch for all layers).  Stale when the optimizer
+    stepped OR a parameter was changed in place between steps (load_state_dict, p.data.copy_, a parameter broadcast):
+    the in-place version counters catch the latter."""
+    vers = fp.versions()
+    if fp.ndesc and (force or fp.packed_step != fp.step or fp.packed_versions != vers):
         ops._count(1)
         check(_lib.lib().tpz_train_repack(_p(fp.flat_p), _p(fp.descs), fp.ndesc, fp.max_elems, _p(fp.packed), _s()))
+        if USE_TC and fp.ndesc_tc:
+            ops._count(1)
+            check(_lib.lib().tpz_train_repack_tc(_p(fp.flat_p), _p(fp.descs_tc), fp.ndesc_tc, fp.max_elems_tc, _p(fp.packed_tc), _s()))
         fp.packed_step = fp.step
+        fp.packed_versions = vers
 
 
 def _packed(w):
@@ -127,6 +175,13 @@ def _packed(w):
     return fp.packed_ptrs(w)
 
 
+def _packed_tc(w):
+    fp = _CUR['fp']
+    if not USE_TC or fp is None:
+        return None
+    return fp.packed_tc_ptrs(w)
+
+
 def _conv_fwd(x, w, b, stride, dil, org, Ho, Wo, relu, res=None, res_org=0, res_stride=1):
     N, H, W, Ci = x.shape
     Co, _, kh, kw = w.shape
@@ -134,6 +189,12 @@ def _conv_fwd(x, w, b, stride, dil, org, Ho, Wo, relu, res=None, res_org=0, res_
     ops._count(1)
     if USE_MMA and Ci == 1 and Co in (32, 64) and org == 0 and dil == 1 and res is None and kh == kw:
         check(_lib.lib().tpz_first_fwd_f32(_p(x), N, H, W, _p(w), _p(b), Co, kh, stride, int(relu), _p(y), Ho, Wo, _s()))
+        return y
+    pt = _packed_tc(w)
+    if pt is not None and Ci % 32 == 0 and Co % 32 == 0:
+        check(_lib.lib().tpz_conv_fwd_tc(_p(x), N, H, W, Ci, _p(pt[0]), _p(b), Co, kh, kw, stride, dil, org, _p(res),
+                                         res.shape[1] if res is not None else 0, res.shape[2] if res is not None else 0,
+                                         res_org, res_stride, int(relu), _p(y), Ho, Wo, _s()))
         return y
     pk = _packed(w)
     if pk is not None and Ci % 16 == 0 and Co % 32 == 0:
@@ -152,6 +213,11 @@ def _conv_dgrad(dy, w, stride, dil, org, H, W, mask=None, accumulate=False, out=
     _, Ci, kh, kw = w.shape
     dx = out if out is not None else torch.empty((N, H, W, Ci), dtype=torch.float32, device=dy.device)
     ops._count(1)
+    pt = _packed_tc(w)
+    if pt is not None and Co % 32 == 0 and Ci % 32 == 0:
+        check(_lib.lib().tpz_conv_dgrad_tc(_p(dy), N, Ho, Wo, Co, _p(pt[1]), Ci, kh, kw, stride, dil, org, _p(mask),
+                                           int(accumulate), _p(dx), H, W, _s()))
+        return dx
     pk = _packed(w)
     if pk is not None and Co % 16 == 0 and Ci % 32 == 0:
         check(_lib.lib().tpz_conv_dgrad_mma(_p(dy), N, Ho, Wo, Co, _p(pk[1]), Ci, kh, kw, stride, dil, org, _p(mask),
@@ -169,6 +235,11 @@ def _conv_wgrad(x, dy, w_grad, b_grad, stride, dil, org):
     ops._count(2 if b_grad is not None else 1)
     if USE_MMA and Ci == 1 and Co in (32, 64) and org == 0 and dil == 1 and kh == kw and kh * kw <= (256 // Co) * 16:
         check(_lib.lib().tpz_first_wgrad_f32(_p(x), N, H, W, _p(dy), Ho, Wo, Co, kh, stride, _p(w_grad), _s()))
+        if b_grad is not None:
+            check(_lib.lib().tpz_bias_grad_f32(_p(dy), N * Ho * Wo, Co, _p(b_grad), _s()))
+        return
+    if USE_TC and Ci % 32 == 0 and Co % 32 == 0:
+        check(_lib.lib().tpz_conv_wgrad_tc(_p(x), N, H, W, Ci, _p(dy), Ho, Wo, Co, kh, kw, stride, dil, org, _p(w_grad), _s()))
         if b_grad is not None:
             check(_lib.lib().tpz_bias_grad_f32(_p(dy), N * Ho * Wo, Co, _p(b_grad), _s()))
         return
@@ -451,7 +522,7 @@ def classifier_forward(model, x: torch.Tensor) -> torch.Tensor:
     fp = None
     if save:
         fp = flat_params(model)         # make sure params / grads live in the flat buffers before taping pointers
-        _repack(fp)
+        _repack(fp, force=torch.cuda.is_current_stream_capturing() if x.is_cuda else False)
     _CUR['fp'] = fp
     with torch.no_grad():
         sc, tape = _forward(model.features, model.classifier, xi, save)
@@ -466,9 +537,11 @@ def features_forward(features, x: torch.Tensor) -> torch.Tensor:
     return z.permute(0, 3, 1, 2).contiguous()
 
 
-def backward(model, dscore: torch.Tensor):
+def backward(model, dscore: torch.Tensor, on_suffix_done=None):
     """Back-propagate d(loss)/d(score) ([B] fp32, device) through the taped forward; accumulates into p.grad
-    (the flat gradient buffer)."""
+    (the flat gradient buffer).  ``on_suffix_done(offset)`` is called after each block's backward with the flat-buffer
+    offset from which every gradient is final (the buffer is laid out in forward order, the backward runs in reverse):
+    data-parallel training starts the all-reduce of that suffix while earlier layers are still back-propagating."""
     tape = model.__dict__.get('_tpz_tape')
     if not tape:
         raise RuntimeError('topaz_b200: backward() without a taped forward (call model(X) in train() mode first)')
@@ -520,8 +593,28 @@ def backward(model, dscore: torch.Tensor):
                     _crop_add(dx, g, edge, s)
                 _relu_bwd(dx, x)            # x is the previous layer's ReLU output
                 g = dx
+            if on_suffix_done is not None:
+                on_suffix_done(_block_offset(fp, rec))
     model.__dict__['_tpz_tape'] = None
     return fp
+
+
+def _block_offset(fp, rec) -> int:
+    """smallest flat-buffer offset among the parameters of a tape record (incl. its BatchNorm / PReLU parameters)"""
+    ptrs = set()
+    for k in ('w', 'b', 'w0', 'b0', 'w1', 'b1', 'proj'):
+        t = rec.get(k)
+        if t is not None:
+            ptrs.add(t.data_ptr())
+    for k in ('bn', 'bn0', 'bn1'):
+        m = rec.get(k)
+        if m is not None:
+            ptrs.update(p.data_ptr() for p in m.parameters())
+    act = rec.get('act')
+    if isinstance(act, nn.PReLU):
+        ptrs.add(act.weight.data_ptr())
+    offs = [off for p, off in zip(fp.params, fp.offsets) if p.data_ptr() in ptrs]
+    return min(offs) if offs else fp.n
 
 
 def ge_loss_grad(scores, labels, pi, slack, lo, hi, dscore, out5):
@@ -539,11 +632,13 @@ def pu_objective_loss_grad(scores, labels, mode, pi, slack, momentum, aux_in, lo
 
 
 def adam_step(fp: FlatParams, lr, b1, b2, eps, l2):
-    """Fused Adam on the flat buffers + L2 term + gradient zeroing (reference methods.py:153-160)."""
+    """Fused Adam on the flat buffers + L2 term + gradient zeroing (reference methods.py:153-160).  The step count lives on
+    the device (fp.step_dev, advanced by the launch itself) so that the call can be replayed from a CUDA graph; fp.step is
+    its host mirror."""
     fp.step += 1
-    ops._count(1)
-    check(_lib.lib().tpz_adam_step(_p(fp.flat_p), _p(fp.flat_g), _p(fp.flat_m), _p(fp.flat_v), fp.n, lr, b1, b2, eps,
-                                   fp.step, float(l2), 1.0, _s()))
+    ops._count(2)
+    check(_lib.lib().tpz_adam_step_dev(_p(fp.flat_p), _p(fp.flat_g), _p(fp.flat_m), _p(fp.flat_v), fp.n, lr, b1, b2, eps,
+                                       _p(fp.step_dev), float(l2), 1.0, _s()))
 
 
 def set_tf32(single_pass: bool) -> bool:
