@@ -88,6 +88,51 @@ int tpz_tc_conv(const TpzTcConvArgs* host_args, void* stream);   /* dispatches: 
 int tpz_tc_conv_v1(const TpzTcConvArgs* host_args, void* stream);/* per-tap TMA loads (one A tile per k-block) */
 int tpz_tc_conv_v2(const TpzTcConvArgs* host_args, void* stream);/* halo-resident A tile + poly-phase lattice  */
 
+/* ---- model-level entry points: a dense ("filled") classifier network as one handle ----
+ * What a non-Python host binds to score micrographs: topaz/extract.py:224-256 (score_images: model.eval(); model.fill();
+ * per-image forward) over topaz/model/classifier.py:48-66 on ResNet8/16 (features/resnet.py:50-339) or conv31/63/127
+ * (features/basic.py:12-111).  The layer list describes the network in its FILLED geometry (strides turned into dilations,
+ * resnet.py:208-251); every parameter pointer is a DEVICE pointer in the reference's own layout (OIHW fp32), read once by
+ * tpz_model_create / tpz_model_update_weights, which fold eval-mode BatchNorm, pad channels and repack to fp16 k-blocks ON the
+ * device (no parameter ever crosses to the host; the 4-byte classifier bias is the one read-back).  The handle owns the packed
+ * weights; activations live in the caller's workspace.  One stream at a time per handle. */
+#define TPZ_LAYER_CONV 0   /* conv k x k (dilation dil0) [+ BatchNorm bn0] + activation slope0: BasicConv, conv31/63/127 layers */
+#define TPZ_LAYER_RESID 1  /* ResidA: conv0 3x3 cin->cin (dil0) [+bn0] + act slope0; conv1 3x3 cin->cout (dil1) + cropped skip
+                              (1x1 `proj` when cin != cout) [+bn1] + act slope1 (resnet.py:108-204) */
+typedef struct {
+  int kind;
+  int cin, cout;
+  int k;                     /* CONV: kernel size; RESID: 3 */
+  int dil0, dil1;
+  float slope0, slope1;      /* v > 0 ? v : v*slope (0 = ReLU; PReLU: its learned scalar) */
+  const float *w0, *b0;      /* CONV: the conv; RESID: conv0.  b may be NULL (BatchNorm models have no conv bias) */
+  const float *w1, *b1;      /* RESID: conv1 */
+  const float *proj;         /* RESID, cin != cout: [cout][cin][1][1]; NULL = identity skip */
+  const float *bn0, *bn1;    /* eval-mode BatchNorm as [4][C] = gamma, beta, running_mean, running_var; NULL = none */
+  float eps0, eps1;
+} TpzLayerDesc;
+typedef struct TpzModel TpzModel;
+/* layers[0] must be the Cin = 1 first convolution, layers[nlayers-1] a CONV whose output feeds the 1x1 classifier
+ * (cls_w [C], cls_b [1], DEVICE); `pad` = the single input padding of the filled network (width // 2, resnet.py:240-243). */
+int tpz_model_create(const TpzLayerDesc* layers, int nlayers, const float* cls_w, const float* cls_b, int pad, TpzModel** out,
+                     void* stream);
+/* Same architecture, new parameter values (and possibly new pointers): repack on the device (after optimizer steps). */
+int tpz_model_update_weights(TpzModel* model, const TpzLayerDesc* layers, int nlayers, const float* cls_w, const float* cls_b,
+                             void* stream);
+int tpz_model_destroy(TpzModel* model);
+/* Bytes of DEVICE workspace (256-byte aligned) tpz_resnet_dense_forward needs for a batch of B images H x W; -1 if the
+ * image is smaller than the receptive field allows. */
+long long tpz_workspace_bytes(const TpzModel* model, int B, int H, int W);
+/* y[B][H][W] = classifier logits of x[B][H][W] (both dense fp32 DEVICE): range scale, first layer, tensor-core convs, fused
+ * 1x1 classifier.  Asynchronous on `stream`. */
+int tpz_resnet_dense_forward(TpzModel* model, const float* x, int B, int H, int W, float* y, void* workspace,
+                             long long workspace_bytes, void* stream);
+
+/* Test hook: copies the packed fp16 weights [nkb][Co][KC] / fp32 bias [Co] of conv step `step` (launch order; -1 = the first
+ * layer) into caller-provided DEVICE buffers (either may be NULL) and reports the sizes. */
+int tpz_model_step_buffers(const TpzModel* model, int step, void* weights_out, long long weight_capacity, float* bias_out,
+                           long long* weight_elems, int* co_store, int* kc, int* nkb, void* stream);
+
 /* ---- direct (SIMT) convolutions for the thin ends and for validation ----
  * tpz_conv_first: Cin = 1 conv from a dense fp32 image, fp32 math, fused bias + activation, fp16 NDHWC out.
  *   Replaces the first BasicConv 7x7 (resnet.py:66,102), conv31/63/127 layer 0 (basic.py:47-52) and the

@@ -111,9 +111,14 @@ def _bn_train(x, sd, prefix, eps=1e-5, momentum=0.1, running=None):
     return (x - mean.view(shape)) / torch.sqrt(var.view(shape) + eps) * g.view(shape) + b.view(shape)
 
 
+PREACT_LOG = None      # tests set this to a list to record every pre-activation (margin-from-zero checks of gradient tests)
+
+
 def _act(y, relu_masks):
     """ReLU; with `relu_masks` (an iterator of 0/1 tensors in layer order) the mask is imposed instead of derived from
     y, so that a gradient check is not at the mercy of activations within rounding noise of zero."""
+    if PREACT_LOG is not None:
+        PREACT_LOG.append(y.detach())
     if relu_masks is None:
         return F.relu(y)
     return y * next(relu_masks).to(y.dtype)

@@ -35,6 +35,13 @@ class TpzTcConvArgs(C.Structure):
     ]
 
 
+class TpzLayerDesc(C.Structure):
+    _fields_ = [('kind', C.c_int), ('cin', C.c_int), ('cout', C.c_int), ('k', C.c_int), ('dil0', C.c_int), ('dil1', C.c_int),
+                ('slope0', C.c_float), ('slope1', C.c_float), ('w0', C.c_void_p), ('b0', C.c_void_p), ('w1', C.c_void_p),
+                ('b1', C.c_void_p), ('proj', C.c_void_p), ('bn0', C.c_void_p), ('bn1', C.c_void_p), ('eps0', C.c_float),
+                ('eps1', C.c_float)]
+
+
 _lib = None
 
 _I, _F, _P, _LL, _D = C.c_int, C.c_float, C.c_void_p, C.c_longlong, C.c_double
@@ -44,6 +51,12 @@ _PROTOS = {
     'tpz_tc_conv': (_I, [C.POINTER(TpzTcConvArgs), _P]),
     'tpz_tc_conv_v1': (_I, [C.POINTER(TpzTcConvArgs), _P]),
     'tpz_tc_conv_v2': (_I, [C.POINTER(TpzTcConvArgs), _P]),
+    'tpz_model_create': (_I, [C.POINTER(TpzLayerDesc), _I, _P, _P, _I, C.POINTER(C.c_void_p), _P]),
+    'tpz_model_update_weights': (_I, [_P, C.POINTER(TpzLayerDesc), _I, _P, _P, _P]),
+    'tpz_model_destroy': (_I, [_P]),
+    'tpz_model_step_buffers': (_I, [_P, _I, _P, _LL, _P, C.POINTER(_LL), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), _P]),
+    'tpz_workspace_bytes': (_LL, [_P, _I, _I, _I]),
+    'tpz_resnet_dense_forward': (_I, [_P, _P, _I, _I, _I, _P, _P, _LL, _P]),
     'tpz_conv_first': (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _I, _P, _I, _P]),
     'tpz_range_scale': (_I, [_P, _LL, _P, _P, _P]),
     'tpz_im2col_first': (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P]),

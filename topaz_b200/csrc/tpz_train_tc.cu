@@ -109,33 +109,40 @@ struct FwdArgs {
   const float* mask; float* out; int relu, accumulate, flush;
 };
 
+constexpr int kPF = 3;            // chunks of A prefetched into registers ahead of the one being staged (hides the gather latency)
+
 template <int BN, int MODE>      // MODE 0 forward, 1 data gradient
-__global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ FwdArgs a) {
+__global__ void __launch_bounds__(256, 2) conv_tc_kernel(const __grid_constant__ FwdArgs a) {
   constexpr uint32_t IDESC = idesc_tf32(128, BN);
   constexpr int B_BYTES = BN * 128;
-  constexpr int STAGE = 2 * kStageA + 2 * B_BYTES;          // A_hi | A_lo | B_hi | B_lo
+  constexpr int ASTAGE = 2 * kStageA;                       // A_hi | A_lo, two stages
+  constexpr int BSTAGE = 2 * B_BYTES;                       // B_hi | B_lo, three stages: the TMA of chunk kc+1 is issued while
+                                                            // chunk kc is staged, so its latency hides behind that work
   constexpr int TCOLS = 2 * BN < 32 ? 32 : 2 * BN;          // two accumulators
+  constexpr int HN = BN / 2;                                // output channels per thread (two threads share a row)
 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t bar_free[2], bar_b[2], bar_acc[2];
+  __shared__ __align__(8) uint64_t bar_free[2], bar_b[3], bar_acc[2];
   __shared__ uint32_t tmem_base_s;
 
   const TGeom& g = a.g;
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int row = tid & 127, half = tid >> 7;    // thread (row, half) stages 16-byte chunks 4*half .. 4*half+3 of its row
   const int taps = g.kh * g.kw;
   const int Cs = MODE == 0 ? g.Ci : g.Co;        // source channels (K per tap)
   const int Nn = MODE == 0 ? g.Co : g.Ci;        // output channels
   const int MH = MODE == 0 ? g.Ho : g.H, MW = MODE == 0 ? g.Wo : g.W;
   const int SH = MODE == 0 ? g.H : g.Ho, SW = MODE == 0 ? g.W : g.Wo;
   const long long Mtot = (long long)g.N * MH * MW;
-  const long long m = (long long)blockIdx.x * 128 + tid;
+  const long long m = (long long)blockIdx.x * 128 + row;
   const int n0 = blockIdx.y * BN;
   const int cchunks = Cs >> 5;
   const int nk = taps * cchunks;
 
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&bar_free[s], 1); ptx::mbar_init(&bar_b[s], 1); ptx::mbar_init(&bar_acc[s], 1); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&bar_free[s], 1); ptx::mbar_init(&bar_acc[s], 1); }
+    for (int s = 0; s < 3; ++s) ptx::mbar_init(&bar_b[s], 1);
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&a.tmB);
   }
@@ -144,6 +151,14 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Fw
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  unsigned char* const bbase = base + 2 * ASTAGE;
+  auto issue_b = [&](int kc) {                              // one elected thread asks TMA for the hi and lo weight blocks of chunk kc
+    unsigned char* bst = bbase + (size_t)(kc % 3) * BSTAGE;
+    ptx::mbar_expect_tx(&bar_b[kc % 3], 2u * B_BYTES);
+    ptx::tma_load_2d(bst, &a.tmB, &bar_b[kc % 3], 0, kc * Nn + n0);
+    ptx::tma_load_2d(bst + B_BYTES, &a.tmB, &bar_b[kc % 3], 0, (int)a.lo_rows + kc * Nn + n0);
+  };
+  if (tid == 0) issue_b(0);
 
   // this thread's output pixel
   const bool row_ok = m < Mtot;
@@ -171,16 +186,16 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Fw
       }
     }
     a_ok = ok;
-    a_off = ok ? (((long long)pn * SH + sy) * SW + sx) * Cs : 0;
+    a_off = ok ? (((long long)pn * SH + sy) * SW + sx) * Cs + half * 16 : 0;
   };
   tap_setup();
 
-  // one chunk of this row: 32 fp32 = 8 x 16 B, prefetched into registers one chunk ahead
-  float4 pre[8];
-  auto load_chunk = [&]() {
+  // this thread's half of one chunk of its row: 16 fp32 = 4 x 16 B, prefetched into registers kPF chunks ahead
+  float4 pre[kPF][4];
+  auto load_chunk = [&](float4 (&dst)[4]) {
     const float4* p = reinterpret_cast<const float4*>(a.src + a_off + t_c);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) pre[c] = a_ok ? __ldg(p + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < 4; ++c) dst[c] = a_ok ? __ldg(p + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     t_c += 32;
     if (t_c == Cs) {
       t_c = 0;
@@ -188,62 +203,71 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Fw
       tap_setup();
     }
   };
-  load_chunk();
-
-  float tot[BN];
 #pragma unroll
-  for (int j = 0; j < BN; ++j) tot[j] = 0.f;
+  for (int i = 0; i < kPF; ++i) {
+    if (i < nk) load_chunk(pre[i]);
+  }
+
+  float tot[HN];
+#pragma unroll
+  for (int j = 0; j < HN; ++j) tot[j] = 0.f;
   const uint32_t d_hi = ptx::umma_desc_hi(1024, 2);         // SBO = 8 rows x 128 B, SWIZZLE_128B
   const int flush = a.flush > 0 ? a.flush : (1 << 30);
-  const int sw = tid & 7;
+  const int sw = row & 7;
   uint32_t accf = 0;                                        // 0: the next MMA overwrites its accumulator
   int cur_acc = 0, in_group = 0, groups_done = 0;
-  auto drain = [&](int acc) {                               // TMEM accumulator -> registers, round-to-nearest adds
-    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * BN;
-#pragma unroll
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+  // TMEM accumulator -> registers, round-to-nearest adds.  Warp w reads lanes 32*(w%4) .. (its rows) and columns half*HN ..
+  auto drain = [&](int acc) {
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + acc * BN + half * HN;
+    if (HN == 32) {
       uint32_t r[32];
-      ptx::tmem_ld32(taddr + c0, r);
+      ptx::tmem_ld32(taddr, r);
       ptx::tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) tot[c0 + j] += __uint_as_float(r[j]);
+      for (int j = 0; j < 32; ++j) tot[j] += __uint_as_float(r[j]);
+    } else {
+      uint32_t r[16];
+      ptx::tmem_ld16(taddr, r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) tot[j] += __uint_as_float(r[j]);
     }
     ptx::tc_fence_before();
   };
 
-  for (int kc = 0; kc < nk; ++kc) {
+  // One chunk: stage `cur` (this thread's part of its row for chunk kc, loaded kPF chunks ago) and refill `cur` with the
+  // load for chunk kc + kPF.  The caller unrolls kPF chunks so that the prefetch queue is indexed at compile time: a
+  // register-to-register rotation of the queue would make every iteration wait for the newest load.
+  auto chunk_body = [&](const int kc, float4 (&cur)[4]) {
     const int s = kc & 1;
-    unsigned char* stage = base + (size_t)s * STAGE;
+    unsigned char* stage = base + (size_t)s * ASTAGE;
     if (kc >= 2) mbar_wait(&bar_free[s], ((kc >> 1) - 1) & 1);       // the MMAs that read this stage (chunk kc-2) are done
-    // B: one elected thread asks TMA for the hi and lo weight blocks of this chunk
-    if (tid == 0) {
-      ptx::mbar_expect_tx(&bar_b[s], 2u * B_BYTES);
-      ptx::tma_load_2d(stage + 2 * kStageA, &a.tmB, &bar_b[s], 0, kc * Nn + n0);
-      ptx::tma_load_2d(stage + 2 * kStageA + B_BYTES, &a.tmB, &bar_b[s], 0, (int)a.lo_rows + kc * Nn + n0);
-    }
-    // A: split this row's chunk and store it (16-byte chunk c of row p lands at chunk c ^ (p & 7))
+    // B of the NEXT chunk: its ring slot (kc+1) % 3 was last read by chunk kc-2, which the wait above has seen complete
+    if (tid == 0 && kc + 1 < nk) issue_b(kc + 1);
+    // A: split this thread's part of the row and store it (16-byte chunk c of row p lands at chunk c ^ (p & 7))
     {
-      unsigned char* rh = stage + tid * 128;
+      unsigned char* rh = stage + row * 128;
       unsigned char* rl = rh + kStageA;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         float4 hi, lo;
-        split4(pre[c], hi, lo);
-        *reinterpret_cast<float4*>(rh + ((c ^ sw) << 4)) = hi;
-        *reinterpret_cast<float4*>(rl + ((c ^ sw) << 4)) = lo;
+        split4(cur[c], hi, lo);
+        const int cc = half * 4 + c;
+        *reinterpret_cast<float4*>(rh + ((cc ^ sw) << 4)) = hi;
+        *reinterpret_cast<float4*>(rl + ((cc ^ sw) << 4)) = lo;
       }
     }
-    if (kc + 1 < nk) load_chunk();                          // global loads of the next chunk fly during the MMAs
+    if (kc + kPF < nk) load_chunk(cur);                     // flies during the next kPF chunks
     ptx::fence_proxy_async();
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 0) {
       ptx::tc_fence_after();
-      mbar_wait(&bar_b[s], (kc >> 1) & 1);
+      mbar_wait(&bar_b[kc % 3], (kc / 3) & 1);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
         const uint32_t ah = (ptx::smem_u32(stage) & 0x3FFFF) >> 4, al = ah + (kStageA >> 4);
-        const uint32_t bh = al + (kStageA >> 4), bl = bh + (B_BYTES >> 4);
+        const uint32_t bh = (ptx::smem_u32(bbase + (size_t)(kc % 3) * BSTAGE) & 0x3FFFF) >> 4, bl = bh + (B_BYTES >> 4);
         const uint32_t d = tmem_base + cur_acc * BN;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -268,6 +292,12 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Fw
       ++groups_done;
       cur_acc ^= 1; in_group = 0; accf = 0;
     }
+  };
+  for (int kc0 = 0; kc0 < nk; kc0 += kPF) {
+#pragma unroll
+    for (int u = 0; u < kPF; ++u) {
+      if (kc0 + u < nk) chunk_body(kc0 + u, pre[u]);
+    }
   }
   {                                                         // last group
     const int last = cur_acc ^ 1;
@@ -276,25 +306,26 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Fw
     drain(last);
   }
 
-  // epilogue: this thread owns output row m, channels n0 .. n0 + BN
+  // epilogue: this thread owns output row m, channels n0 + half*HN .. + HN
   if (row_ok) {
+    const int nb = n0 + half * HN;
     long long rbase = 0;
     if (MODE == 0 && a.res)
       rbase = (((long long)pn * a.res_H + (py * a.res_stride + a.res_org)) * a.res_W + (px * a.res_stride + a.res_org)) * g.Co;
-    float* orow = a.out + m * Nn + n0;
+    float* orow = a.out + m * Nn + nb;
 #pragma unroll
-    for (int c = 0; c < BN; c += 8) {
+    for (int c = 0; c < HN; c += 8) {
       float v[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = tot[c + j];
       if (MODE == 0) {
         if (a.bias) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] += __ldg(a.bias + n0 + c + j);
+          for (int j = 0; j < 8; ++j) v[j] += __ldg(a.bias + nb + c + j);
         }
         if (a.res) {
-          const float4 r0 = __ldg(reinterpret_cast<const float4*>(a.res + rbase + n0 + c));
-          const float4 r1 = __ldg(reinterpret_cast<const float4*>(a.res + rbase + n0 + c + 4));
+          const float4 r0 = __ldg(reinterpret_cast<const float4*>(a.res + rbase + nb + c));
+          const float4 r1 = __ldg(reinterpret_cast<const float4*>(a.res + rbase + nb + c + 4));
           v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
         }
         if (a.relu) {
@@ -307,8 +338,8 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Fw
           v[0] += o0.x; v[1] += o0.y; v[2] += o0.z; v[3] += o0.w; v[4] += o1.x; v[5] += o1.y; v[6] += o1.z; v[7] += o1.w;
         }
         if (a.mask) {
-          const float4 k0 = __ldg(reinterpret_cast<const float4*>(a.mask + m * Nn + n0 + c));
-          const float4 k1 = __ldg(reinterpret_cast<const float4*>(a.mask + m * Nn + n0 + c + 4));
+          const float4 k0 = __ldg(reinterpret_cast<const float4*>(a.mask + m * Nn + nb + c));
+          const float4 k1 = __ldg(reinterpret_cast<const float4*>(a.mask + m * Nn + nb + c + 4));
           v[0] = k0.x > 0.f ? v[0] : 0.f; v[1] = k0.y > 0.f ? v[1] : 0.f; v[2] = k0.z > 0.f ? v[2] : 0.f; v[3] = k0.w > 0.f ? v[3] : 0.f;
           v[4] = k1.x > 0.f ? v[4] : 0.f; v[5] = k1.y > 0.f ? v[5] : 0.f; v[6] = k1.z > 0.f ? v[6] : 0.f; v[7] = k1.w > 0.f ? v[7] : 0.f;
         }
@@ -332,13 +363,16 @@ struct WgArgs {
   int flush;
 };
 
+constexpr int kPFW = 2;           // chunks prefetched ahead in the wgrad kernel
+
 template <int BN>                // co tile
-__global__ void __launch_bounds__(128) wgrad_tc_kernel(const WgArgs a) {
+__global__ void __launch_bounds__(256, 2) wgrad_tc_kernel(const WgArgs a) {
   constexpr uint32_t IDESC = idesc_tf32(128, BN);
   constexpr int B_BYTES = BN * 128;
   constexpr int STAGE = 2 * kStageA + 2 * B_BYTES;
   constexpr int TCOLS = 2 * BN < 32 ? 32 : 2 * BN;
-  constexpr int BQ = BN / 4;                                  // dy channels staged per warp
+  constexpr int BQ = BN / 8;                                  // dy channels staged per warp (8 or 4)
+  constexpr int HN = BN / 2;
 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -347,6 +381,7 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const WgArgs a) {
 
   const TGeom& g = a.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = warp >> 2;
   const int taps = g.kh * g.kw;
   const int rows_total = taps * g.Ci;                         // (tap, ci) pairs = M extent
   const int mt = blockIdx.x;                                  // M tile
@@ -366,15 +401,15 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const WgArgs a) {
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  // this warp stages A rows [32*warp, 32*warp + 32) of the tile = 32 consecutive ci of ONE tap (Ci % 32 == 0)
-  const int row0 = mt * 128 + warp * 32;
+  // warp w stages A rows [16w, 16w + 16) of the tile = 16 consecutive ci of ONE tap (Ci % 32 == 0)
+  const int row0 = mt * 128 + warp * 16;
   const bool warp_rows_ok = row0 < rows_total;
   const int tap = warp_rows_ok ? row0 / g.Ci : 0, ci0 = warp_rows_ok ? row0 % g.Ci : 0;
   const int tr = tap / g.kw, tt = tap - tr * g.kw;
   if (!warp_rows_ok) {                                        // rows beyond the (tap, ci) range stay zero in both stages
     for (int s = 0; s < 2; ++s)
-      for (int j = 0; j < 32; ++j) {
-        unsigned char* rh = base + (size_t)s * STAGE + (size_t)(warp * 32 + j) * 128;
+      for (int j = 0; j < 16; ++j) {
+        unsigned char* rh = base + (size_t)s * STAGE + (size_t)(warp * 16 + j) * 128;
         *reinterpret_cast<float*>(rh + lane * 4) = 0.f;
         *reinterpret_cast<float*>(rh + kStageA + lane * 4) = 0.f;
       }
@@ -387,42 +422,50 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const WgArgs a) {
     const long long pp = ip < P ? ip : 0;
     i_ox = (int)(pp % g.Wo); const long long q = pp / g.Wo; i_oy = (int)(q % g.Ho); i_n = (int)(q / g.Ho);
   }
-  float4 prex[8];            // x[p'(p, tap)][ci0 .. ci0+32)
-  float4 prey[BQ / 4];       // dy[p][co0 + warp*BQ .. + BQ)
-  auto load_chunk = [&]() {
+  float4 prex[kPFW][4];          // x[p'(p, tap)][ci0 .. ci0+16)
+  float4 prey[kPFW][BQ / 4];     // dy[p][co0 + warp*BQ .. + BQ)
+  auto load_chunk = [&](float4 (&dx_)[4], float4 (&dy_)[BQ / 4]) {
     const bool pv = ip < pend;
     if (warp_rows_ok) {
       const int iy = i_oy * g.stride + tr * g.dil + g.org, ix = i_ox * g.stride + tt * g.dil + g.org;
       const bool ok = pv && iy >= 0 && iy < g.H && ix >= 0 && ix < g.W;
       const float4* p = reinterpret_cast<const float4*>(a.x + (((long long)i_n * g.H + iy) * g.W + ix) * g.Ci + ci0);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) prex[c] = ok ? __ldg(p + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < 4; ++c) dx_[c] = ok ? __ldg(p + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const float4* q = reinterpret_cast<const float4*>(a.dy + ip * g.Co + co0 + warp * BQ);
 #pragma unroll
-    for (int c = 0; c < BQ / 4; ++c) prey[c] = pv ? __ldg(q + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < BQ / 4; ++c) dy_[c] = pv ? __ldg(q + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     ip += 32;
     i_ox += 32;
     while (i_ox >= g.Wo) { i_ox -= g.Wo; if (++i_oy == g.Ho) { i_oy = 0; ++i_n; } }
   };
-  if (nchunks > 0) load_chunk();
-
-  float tot[BN];
 #pragma unroll
-  for (int j = 0; j < BN; ++j) tot[j] = 0.f;
+  for (int i = 0; i < kPFW; ++i) {
+    if (i < nchunks) load_chunk(prex[i], prey[i]);
+  }
+
+  float tot[HN];
+#pragma unroll
+  for (int j = 0; j < HN; ++j) tot[j] = 0.f;
   const uint32_t d_hi = ptx::umma_desc_hi(1024, 2);
   const int flush = a.flush > 0 ? a.flush : (1 << 30);
   uint32_t accf = 0;
   int cur_acc = 0, in_group = 0, groups_done = 0;
   auto drain = [&](int acc) {
-    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * BN;
-#pragma unroll
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + acc * BN + half * HN;
+    if (HN == 32) {
       uint32_t r[32];
-      ptx::tmem_ld32(taddr + c0, r);
+      ptx::tmem_ld32(taddr, r);
       ptx::tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) tot[c0 + j] += __uint_as_float(r[j]);
+      for (int j = 0; j < 32; ++j) tot[j] += __uint_as_float(r[j]);
+    } else {
+      uint32_t r[16];
+      ptx::tmem_ld16(taddr, r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) tot[j] += __uint_as_float(r[j]);
     }
     ptx::tc_fence_before();
   };
@@ -431,16 +474,16 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const WgArgs a) {
     *reinterpret_cast<float*>(plane + (size_t)row * 128 + ((((lane >> 2) ^ (row & 7)) << 4) | ((lane & 3) << 2))) = v;
   };
 
-  for (int kc = 0; kc < nchunks; ++kc) {
+  auto chunk_body = [&](const int kc, float4 (&curx)[4], float4 (&cury)[BQ / 4]) {
     const int s = kc & 1;
     unsigned char* stage = base + (size_t)s * STAGE;
     if (kc >= 2) mbar_wait(&bar_free[s], ((kc >> 1) - 1) & 1);
     if (warp_rows_ok) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         float4 hi, lo;
-        split4(prex[c], hi, lo);
-        const int r = warp * 32 + c * 4;
+        split4(curx[c], hi, lo);
+        const int r = warp * 16 + c * 4;
         put(stage, r, hi.x); put(stage, r + 1, hi.y); put(stage, r + 2, hi.z); put(stage, r + 3, hi.w);
         put(stage + kStageA, r, lo.x); put(stage + kStageA, r + 1, lo.y); put(stage + kStageA, r + 2, lo.z); put(stage + kStageA, r + 3, lo.w);
       }
@@ -450,13 +493,13 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const WgArgs a) {
 #pragma unroll
       for (int c = 0; c < BQ / 4; ++c) {
         float4 hi, lo;
-        split4(prey[c], hi, lo);
+        split4(cury[c], hi, lo);
         const int r = warp * BQ + c * 4;
         put(bh, r, hi.x); put(bh, r + 1, hi.y); put(bh, r + 2, hi.z); put(bh, r + 3, hi.w);
         put(bh + B_BYTES, r, lo.x); put(bh + B_BYTES, r + 1, lo.y); put(bh + B_BYTES, r + 2, lo.z); put(bh + B_BYTES, r + 3, lo.w);
       }
     }
-    if (kc + 1 < nchunks) load_chunk();
+    if (kc + kPFW < nchunks) load_chunk(curx, cury);
     ptx::fence_proxy_async();
     ptx::tc_fence_before();
     __syncthreads();
@@ -488,6 +531,12 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const WgArgs a) {
       ++groups_done;
       cur_acc ^= 1; in_group = 0; accf = 0;
     }
+  };
+  for (int kc0 = 0; kc0 < nchunks; kc0 += kPFW) {
+#pragma unroll
+    for (int u = 0; u < kPFW; ++u) {
+      if (kc0 + u < nchunks) chunk_body(kc0 + u, prex[u], prey[u]);
+    }
   }
   if (groups_done >= 1) {
     const int last = cur_acc ^ 1;
@@ -495,13 +544,15 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const WgArgs a) {
     ptx::tc_fence_after();
     drain(last);
   }
-  // thread `tid` holds row (tap_r, ci_r) of the tile against co0 .. co0 + BN: dw[co][ci][tap] += tot
-  const int row = mt * 128 + tid;
+  // thread (warp, lane) holds row (tap_r, ci_r) = tile row 32*(warp%4) + lane against co0 + half*HN .. + HN: dw[co][ci][tap] += tot
+  const int row = mt * 128 + (warp & 3) * 32 + lane;
   if (row < rows_total && nchunks > 0) {
     const int tap_r = row / g.Ci, ci_r = row - tap_r * g.Ci;
 #pragma unroll
-    for (int j = 0; j < BN; ++j)
-      if (co0 + j < g.Co) atomicAdd(a.dw + ((long long)(co0 + j) * g.Ci + ci_r) * taps + tap_r, tot[j]);
+    for (int j = 0; j < HN; ++j) {
+      const int co = co0 + half * HN + j;
+      if (co < g.Co) atomicAdd(a.dw + ((long long)co * g.Ci + ci_r) * taps + tap_r, tot[j]);
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -524,15 +575,14 @@ TGeom tgeom(int N, int H, int W, int Ci, int Ho, int Wo, int Co, int kh, int kw,
 
 template <int BN, int MODE>
 int launch_conv_tc(const FwdArgs& a, long long M, int Nn, cudaStream_t stream) {
-  constexpr int STAGE = 2 * kStageA + 2 * BN * 128;
-  const int smem = 2 * STAGE + 1024;
+  const int smem = 2 * (2 * kStageA) + 3 * (2 * BN * 128) + 1024;
   static bool configured = false;
   if (!configured) {
     TPZ_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   dim3 grid(tpz_div_up(M, 128), Nn / BN);
-  conv_tc_kernel<BN, MODE><<<grid, 128, smem, stream>>>(a);
+  conv_tc_kernel<BN, MODE><<<grid, 256, smem, stream>>>(a);
   TPZ_CUDA(cudaGetLastError());
   return 0;
 }
@@ -616,12 +666,12 @@ extern "C" int tpz_conv_wgrad_tc(const float* x, int N, int H, int W, int Ci, co
     constexpr int smem = 2 * (2 * kStageA + 2 * 64 * 128) + 1024;
     static bool configured = false;
     if (!configured) { TPZ_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); configured = true; }
-    wgrad_tc_kernel<64><<<grid, 128, smem, ST(stream)>>>(a);
+    wgrad_tc_kernel<64><<<grid, 256, smem, ST(stream)>>>(a);
   } else {
     constexpr int smem = 2 * (2 * kStageA + 2 * 32 * 128) + 1024;
     static bool configured = false;
     if (!configured) { TPZ_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); configured = true; }
-    wgrad_tc_kernel<32><<<grid, 128, smem, ST(stream)>>>(a);
+    wgrad_tc_kernel<32><<<grid, 256, smem, ST(stream)>>>(a);
   }
   TPZ_CUDA(cudaGetLastError());
   return 0;

@@ -185,6 +185,14 @@ class Denoise():
         use_patch = (patch_size > 0) and (s < x.shape[0] or s < x.shape[1])
         return self.denoise_patches(x, patch_size, padding=padding) if use_patch else self._denoise(x)
 
+    @torch.no_grad()
+    def denoise_device(self, xd: torch.Tensor, patch_size=-1, padding=128) -> torch.Tensor:
+        """``denoise`` for a device-resident fp32 micrograph, result left on the device (denoise_image keeps the whole
+        normalise -> denoise -> restore chain there)."""
+        s = patch_size + padding
+        use_patch = (patch_size > 0) and (s < xd.shape[0] or s < xd.shape[1])
+        return self.denoise_patches_device(xd, patch_size, padding) if use_patch else self._denoise_device(xd)
+
 
 class Denoise3D(Denoise):
     ''' Object for denoising tomograms (reference denoise.py:336-377). '''
@@ -235,19 +243,38 @@ class Denoise3D(Denoise):
 
 def denoise_image(mic: np.ndarray, models: List[Denoise], lowpass=1, cutoff=0, gaus=None, inv_gaus=None,
                   deconvolve=False, deconv_patch=1, patch_size=-1, padding=0, normalize=False, use_cuda=True) -> np.ndarray:
-    ''' reference denoise.py:382-416 with the optional lowpass / gaussian / deconvolve pre-filters
-    outside the hot path (off in every BASELINE config).'''
+    ''' reference denoise.py:382-416 with the optional lowpass / inverse-Gaussian / deconvolve pre-filters outside the hot path
+    (off in every BASELINE config).  The micrograph is uploaded ONCE; the outer normalisation (population mean / std,
+    denoise.py:388-389), the optional cutoff and Gaussian pre-filter, every model's (patched) forward, the average over
+    models and the final re-normalisation or scale restore (:409-414) all run on the device, and the result comes back in
+    one copy -- the reference makes four full-image numpy passes on the host around the network.'''
     if lowpass > 1 or inv_gaus is not None or deconvolve:
         raise NotImplementedError('topaz_b200: lowpass / inverse-Gaussian / deconvolve pre-filters are outside the B200 hot path')
-    mu, std = mic.mean(), mic.std()
-    x = (mic - mu) / std
-    if cutoff > 0:
-        x[(x < -cutoff) | (x > cutoff)] = 0
-    if gaus is not None:            # topaz_b200.filters.GaussianDenoise (reference denoise.py:397-398)
-        x = gaus.apply(x)
-    mic = sum([model.denoise(x, patch_size=patch_size, padding=padding) for model in models]) / len(models)
-    if normalize:
-        mic = (mic - mic.mean()) / mic.std()
-    else:
-        mic = std * mic + mu
-    return mic
+    if not use_cuda:
+        raise RuntimeError('topaz_b200: denoise_image requires use_cuda=True; this build has no CPU path')
+    dev = models[0].device
+    host = torch.from_numpy(np.ascontiguousarray(mic, dtype=np.float32))
+    stage = models[0]._pinned('img', host.shape)
+    stage.copy_(host)
+    with torch.no_grad():
+        xd = stage.to(dev, non_blocking=True)
+        stats = ops.meanstd(xd, unbiased=False)           # mic.mean(), mic.std() (numpy: population std)
+        x = ops.affine(xd, stats)                         # (mic - mu) / std
+        if cutoff > 0:
+            x = torch.where((x < -cutoff) | (x > cutoff), torch.zeros((), device=dev), x)
+        if gaus is not None:                              # topaz_b200.filters.GaussianDenoise (reference denoise.py:397-398)
+            x = gaus.forward(x[None, None])[0, 0].contiguous()
+        acc = None
+        for model in models:
+            y = model.denoise_device(x, patch_size=patch_size, padding=padding)
+            acc = y.clone() if acc is None and len(models) > 1 else (y if acc is None else acc.add_(y))
+        if len(models) > 1:
+            acc = acc / len(models)
+        if normalize:
+            out = ops.affine(acc, ops.meanstd(acc, unbiased=False))          # (mic - mic.mean()) / mic.std()
+        else:
+            out = ops.affine(acc, stats, inverse=True)                       # std * mic + mu
+        res = torch.empty(tuple(out.shape), dtype=torch.float32, pin_memory=True)
+        res.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    return res.numpy()

@@ -45,6 +45,9 @@ LAST_MODE = os.environ.get('TPZ_LAST', 'auto')
 PRECISION = os.environ.get('TPZ_PRECISION', 'strict' if os.environ.get('TPZ_STRICT', '0') == '1' else 'auto')
 # fp16 range guard (default on): activations are stored multiplied by a power of two chosen from max|input| (ops.range_scale)
 RANGE_GUARD = os.environ.get('TPZ_RANGE_GUARD', '1') != '0'
+# Dense classifier forward through the model-level C ABI (csrc/tpz_model.cu: plans + on-device weight repack in C++);
+# 'py' keeps the Python-built plans (same kernels, same packed bytes).  Strict precision always uses the Python plans.
+DENSE_ENGINE = os.environ.get('TPZ_DENSE_ENGINE', 'py')
 
 
 def _rup(c: int, m: int = 32) -> int:
@@ -300,9 +303,31 @@ def classifier_forward(model, x: torch.Tensor) -> torch.Tensor:
         return train_engine.classifier_forward(model, x)
     xi = _as_image_batch(x, 2)
     key = _state_key(model, ('dense', str(xi.device)))
+    if DENSE_ENGINE == 'c' and PRECISION != 'strict' and RANGE_GUARD and ops.TC_VARIANT == 'auto':
+        return _dense_c_model(model, key).forward(xi)
     plan = _cached(model, 'dense_cls', key, lambda: _build_dense_plan(feats, model.classifier, xi.device))
     y, _ = _run_dense(plan, xi, want_features=False)   # [B, 1(D), H, W]; the fused dot epilogue already undid the range scale
     return y.view(xi.shape[0], 1, y.shape[2], y.shape[3])
+
+
+def _dense_c_model(model, key):
+    """The model's native handle (model_abi.DenseModel), repacked on the device when a parameter changed and rebuilt when the
+    geometry did (fill()/unfill() change dilations)."""
+    from .model_abi import DenseModel
+    cache = model.__dict__.setdefault('_tpz_plans', {})
+    hit = cache.get('dense_c')
+    geom = tuple((b.get('dil'), b.get('d0'), b.get('d1')) for b in _feature_blocks(model.features, slopes=False))
+    if hit is not None and hit[0] == key:
+        return hit[2]
+    if hit is not None and hit[1] == geom:
+        hit[2].update()
+        cache['dense_c'] = (key, geom, hit[2])
+        return hit[2]
+    if hit is not None:
+        hit[2].close()
+    dm = DenseModel(model)
+    cache['dense_c'] = (key, geom, dm)
+    return dm
 
 
 def features_forward(features, x: torch.Tensor) -> torch.Tensor:

@@ -150,7 +150,7 @@ def flat_params(model) -> FlatParams:
 _CUR = {'fp': None}      # FlatParams of the model whose step is running (packed weights for the mma kernels)
 USE_MMA = os.environ.get('TPZ_TRAIN_SIMT') is None
 # tcgen05 (kind::tf32, 3-pass) training convolutions for channel counts that are multiples of 32; TPZ_TRAIN_TC=0 -> mma.sync
-USE_TC = USE_MMA and os.environ.get('TPZ_TRAIN_TC', '0') == '1'
+USE_TC = USE_MMA and os.environ.get('TPZ_TRAIN_TC', '1') == '1'
 
 
 def _repack(fp, force: bool = False):
