@@ -133,6 +133,9 @@ int tpz_resnet_dense_forward(TpzModel* model, const float* x, int B, int H, int 
 int tpz_model_step_buffers(const TpzModel* model, int step, void* weights_out, long long weight_capacity, float* bias_out,
                            long long* weight_elems, int* co_store, int* kc, int* nkb, void* stream);
 
+/* Test hook: copy of the argument block conv step `step` was last launched with. */
+int tpz_model_step_args(const TpzModel* model, int step, TpzTcConvArgs* out);
+
 /* ---- direct (SIMT) convolutions for the thin ends and for validation ----
  * tpz_conv_first: Cin = 1 conv from a dense fp32 image, fp32 math, fused bias + activation, fp16 NDHWC out.
  *   Replaces the first BasicConv 7x7 (resnet.py:66,102), conv31/63/127 layer 0 (basic.py:47-52) and the

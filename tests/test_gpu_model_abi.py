@@ -118,6 +118,7 @@ def test_c_model_path_is_bit_identical_to_python_plans(name, arch, units, scalin
         engine.DENSE_ENGINE = 'c'
         with torch.no_grad():
             y_c = m(x).cpu()
+        print(name, 'python plans vs C model: max |diff|', float((y_py - y_c).abs().max()), 'of', float(y_py.abs().max()))
         assert torch.equal(y_py, y_c), float((y_py - y_c).abs().max())
         # parameters change in place (an optimizer epoch): the handle repacks on the device and follows
         with torch.no_grad():
@@ -162,5 +163,25 @@ def test_c_model_packs_the_same_bytes_as_the_python_packer(name, arch, units, sc
         nz = int((w != p.weights).sum())
         print(f'step {i}: {tuple(w.shape)} weights max diff {dw:.3e} ({nz} fp16 values differ), bias max diff {db:.3e}')
         worst_w, worst_b = max(worst_w, dw), max(worst_b, db)
+    # the launch arguments too: k-block tables, lattice, tap grids, origins, slopes (pointers and the per-forward geometry aside)
+    import ctypes as C
+    from topaz_b200 import _lib, ops
+    x = torch.from_numpy(g['x'] if 'pretrained' in name else g['xd']).cuda()
+    with torch.no_grad():
+        dm.forward(x[:, 0].contiguous())
+    for i, st in enumerate(steps[1:]):
+        pa = ops._static_tc_args(st['plan'])
+        ca = _lib.TpzTcConvArgs()
+        _lib.check(_lib.lib().tpz_model_step_args(dm.handle, i, C.byref(ca)))
+        for f in ('nsrc', 'KC', 'nkb', 'Co', 'TW', 'TH', 'lattice', 'phase_sel', 'lattice_z', 'phase_z', 'neg_slope', 'out_lo'):
+            assert getattr(pa, f) == getattr(ca, f), (i, f, getattr(pa, f), getattr(ca, f))
+        # the fused classifier bias is a launch-time field on the Python side (ops.make_tc_args copies plan.dot_b)
+        assert C.c_float(st['plan'].dot_b).value == ca.dot_b, (i, 'dot_b', st['plan'].dot_b, ca.dot_b)
+        for j in range(pa.nkb):
+            a, b = pa.kb[j], ca.kb[j]
+            assert (a.dx, a.dy, a.dz, a.c0, a.src) == (b.dx, b.dy, b.dz, b.c0, b.src), (i, j)
+        for sidx in range(pa.nsrc):
+            a, b = pa.src[sidx], ca.src[sidx]
+            assert (a.C, tuple(a.org), a.kw, a.kh, a.lat, a.no_phase, a.lat_z) == (b.C, tuple(b.org), b.kw, b.kh, b.lat, b.no_phase, b.lat_z), (i, sidx)
     dm.close()
-    assert worst_w == 0.0 and worst_b <= 1e-6, (worst_w, worst_b)
+    assert worst_w == 0.0 and worst_b == 0.0, (worst_w, worst_b)

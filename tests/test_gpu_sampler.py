@@ -77,3 +77,44 @@ def test_sampling_statistics_and_labels():
                         rotate=False, flip=False, seed=3)
     X3, Y3 = s2.sample(B)
     assert torch.equal(Y3.cpu(), torch.from_numpy(Y)) and np.array_equal(X3.cpu().numpy(), X)   # reproducible from the seed
+
+
+def test_gpu_training_iterator_replaces_the_reference_data_loader(tmp_path):
+    """topaz_b200.training.gpu_training_iterator (what the make_data_iterators drop-in builds, reference training.py:479-503):
+    micrographs on disk + a particle table -> epoch_size minibatches (X [B, crop, crop] float32, Y [B] float64) on the device;
+    positives are drawn from the expanded discs, their crops are centred on labelled pixels, and a GE_binomial epoch runs on it."""
+    import pandas as pd
+    import torch.nn as nn
+    from topaz_b200 import mrc
+    from topaz_b200.training import gpu_training_iterator, expand_target_points
+    rng = np.random.default_rng(5)
+    paths, rows = [], []
+    for k in range(3):
+        img = (rng.standard_normal((300, 320)) * 0.1).astype(np.float32)
+        for (py, px) in rng.integers(40, 260, size=(6, 2)):
+            img[py - 3:py + 4, px - 3:px + 4] = 5.0                  # a bright blob under every particle's radius-3 disc
+            rows.append((f'mic{k}', int(px), int(py)))
+        p = str(tmp_path / f'mic{k}.mrc'); mrc.write(p, img); paths.append(p)
+    targets = pd.DataFrame(rows, columns=['image_name', 'x_coord', 'y_coord'])
+    expanded, mask_size = expand_target_points(targets, 3)
+    assert mask_size == 29 and len(expanded) == 29 * len(targets)
+    it = gpu_training_iterator([paths[:2], paths[2:]], expanded, 71, 'pn', 256, 5, balance=0.25, seed=11)
+    assert len(it) == 5 and it.batch_size == 256
+    frac, n = 0.0, 0
+    for X, Y in it:
+        assert X.is_cuda and X.dtype == torch.float32 and tuple(X.shape) == (256, 71, 71)
+        assert Y.is_cuda and Y.dtype == torch.float64 and tuple(Y.shape) == (256,)
+        centre = X[:, 35, 35]
+        pos = Y == 1
+        assert bool((centre[pos] > 2.5).all())                      # positives sit on a blob (rotation / flips keep the centre)
+        assert float((centre[~pos] > 2.5).float().mean()) < 0.05    # 'pn': unlabeled crops avoid labelled pixels
+        frac += float(pos.float().mean()); n += 1
+    assert abs(frac / n - 0.25) < 0.06
+    # one epoch of the reference's fit loop shape: step() on every minibatch
+    from topaz_b200.methods import GE_binomial
+    from topaz_b200.model.factory import get_feature_extractor
+    from topaz_b200.model.classifier import LinearClassifier
+    m = LinearClassifier(get_feature_extractor('resnet8', units=32, bn=False)).cuda(); m.train()
+    tr = GE_binomial(m, torch.optim.Adam(m.parameters(), lr=2e-4), nn.BCEWithLogitsLoss(), 0.035)
+    outs = [tr.step(X, Y.view(-1)) for X, Y in it]
+    assert len(outs) == 5 and all(np.isfinite(o).all() for o in outs)

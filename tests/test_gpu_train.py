@@ -157,6 +157,9 @@ def test_conv_mma_kernels_match_fp32(N, H, Ci, Co, k, stride, dil, org):
     (2, 9, 64, 128, 5, 1, 1, 0), (300, 5, 64, 64, 3, 1, 1, 0),
     (48, 27, 64, 128, 1, 2, 1, 3), (48, 25, 64, 128, 3, 2, 2, 0), (48, 9, 128, 256, 5, 1, 1, 0), (48, 11, 128, 128, 3, 1, 2, 0),   # resnet8_u64 layers
     (256, 31, 32, 32, 3, 1, 1, 0),                                                                                                 # resnet8_u32 at the cfg4 minibatch
+    # halo-resident kernel (stride 1, 32 -> 32): dilation 2 (largest halo), a cropped origin, 1x1, fewer tiles than SMs
+    (40, 31, 32, 32, 3, 1, 2, 0), (3, 20, 32, 32, 3, 1, 1, 2), (2, 17, 32, 32, 1, 1, 1, 1), (1, 9, 32, 32, 3, 1, 1, 0),
+    (256, 27, 32, 32, 3, 1, 1, 0),
 ])
 def test_conv_tc_kernels_match_fp32(N, H, Ci, Co, k, stride, dil, org):
     """tcgen05 (kind::tf32, 3-pass) fwd / dgrad / wgrad vs torch CPU fp32, with the weights packed by tpz_train_repack_tc

@@ -55,6 +55,7 @@ _PROTOS = {
     'tpz_model_update_weights': (_I, [_P, C.POINTER(TpzLayerDesc), _I, _P, _P, _P]),
     'tpz_model_destroy': (_I, [_P]),
     'tpz_model_step_buffers': (_I, [_P, _I, _P, _LL, _P, C.POINTER(_LL), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), _P]),
+    'tpz_model_step_args': (_I, [_P, _I, C.POINTER(TpzTcConvArgs)]),
     'tpz_workspace_bytes': (_LL, [_P, _I, _I, _I]),
     'tpz_resnet_dense_forward': (_I, [_P, _P, _I, _I, _I, _P, _P, _LL, _P]),
     'tpz_conv_first': (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _I, _P, _I, _P]),

@@ -21,7 +21,9 @@ _FUNCTION_PATCHES = {('topaz.algorithms', 'non_maximum_suppression'): ('topaz_b2
                      ('topaz.utils.image', 'downsample'): ('topaz_b200.preprocess', 'downsample'),
                      ('topaz.stats', 'normalize'): ('topaz_b200.stats', 'normalize'),
                      ('topaz.stats', 'norm_fit'): ('topaz_b200.stats', 'norm_fit'),
-                     ('topaz.stats', 'gmm_fit'): ('topaz_b200.stats', 'gmm_fit')}
+                     ('topaz.stats', 'gmm_fit'): ('topaz_b200.stats', 'gmm_fit'),
+                     # training data: crops sampled + augmented on the GPU (falls back to the reference loader without CUDA / in 3-D)
+                     ('topaz.training', 'make_data_iterators'): ('topaz_b200.training', 'make_data_iterators')}
 
 
 # names that reference modules bind with `from X import f` at import time: re-pointed when the consumer module is ALREADY

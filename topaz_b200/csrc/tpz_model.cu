@@ -20,9 +20,11 @@ inline int rup(int c, int m = 32) { return (c + m - 1) / m * m; }
 __global__ void bn_affine_kernel(const float* __restrict__ bn, float eps, int C, float* __restrict__ a, float* __restrict__ sh) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const float s = bn[c] / sqrtf(bn[3 * C + c] + eps);
+  // separately rounded operations (no FMA contraction): the same arithmetic as the Python packer's torch ops, so the folded
+  // biases -- and with them every fp16 rounding downstream -- are bit-identical between the two plan builders
+  const float s = __fdiv_rn(bn[c], __fsqrt_rn(__fadd_rn(bn[3 * C + c], eps)));
   a[c] = s;
-  sh[c] = bn[C + c] - s * bn[2 * C + c];
+  sh[c] = __fsub_rn(bn[C + c], __fmul_rn(s, bn[2 * C + c]));
 }
 // bias'[c] = b[c]*a[c] + sh[c] (each optional), zero in the channel padding
 __global__ void bias_fold_kernel(const float* __restrict__ b, const float* __restrict__ a, const float* __restrict__ sh, int C,
@@ -30,7 +32,7 @@ __global__ void bias_fold_kernel(const float* __restrict__ b, const float* __res
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= Cstore) return;
   float v = 0.f;
-  if (c < C) v = (b ? b[c] : 0.f) * (a ? a[c] : 1.f) + (sh ? sh[c] : 0.f);
+  if (c < C) v = __fadd_rn(__fmul_rn(b ? b[c] : 0.f, a ? a[c] : 1.f), sh ? sh[c] : 0.f);
   out[c] = v;
 }
 // k-blocks of one conv source: out[kb0 + tap*nchunks + chunk][co][j] = fp16(w[co][chunk*KC + j][tap] * a[co]), zero in the
@@ -264,18 +266,19 @@ extern "C" int tpz_model_update_weights(TpzModel* m, const TpzLayerDesc* layers,
   for (int li = 1; li < nlayers; ++li) steps += layers[li].kind == TPZ_LAYER_RESID ? 2 : 1;
   TPZ_CHECK(steps == m->steps.size() && layers[0].cout == m->c0 && layers[0].k == m->k0,
             "tpz_model_update_weights: layer list does not match the model");
-  // re-point the sources at the (possibly moved) parameter tensors
+  // re-point the sources at the (possibly moved) parameter tensors; activation slopes are parameters too (nn.PReLU)
+  m->slope0 = layers[0].slope0;
   size_t si = 0;
   for (int li = 1; li < nlayers; ++li) {
     const TpzLayerDesc& l = layers[li];
     if (l.kind == TPZ_LAYER_CONV) {
       Step& s = m->steps[si++];
-      s.parts[0].w = l.w0; s.bn = l.bn0; s.eps = l.eps0; s.bias_src = l.b0;
+      s.parts[0].w = l.w0; s.bn = l.bn0; s.eps = l.eps0; s.bias_src = l.b0; s.args.neg_slope = l.slope0;
     } else {
       Step& s0 = m->steps[si++];
-      s0.parts[0].w = l.w0; s0.bn = l.bn0; s0.eps = l.eps0; s0.bias_src = l.b0;
+      s0.parts[0].w = l.w0; s0.bn = l.bn0; s0.eps = l.eps0; s0.bias_src = l.b0; s0.args.neg_slope = l.slope0;
       Step& s1 = m->steps[si++];
-      s1.parts[0].w = l.w1; s1.parts[1].w = l.proj; s1.bn = l.bn1; s1.eps = l.eps1; s1.bias_src = l.b1;
+      s1.parts[0].w = l.w1; s1.parts[1].w = l.proj; s1.bn = l.bn1; s1.eps = l.eps1; s1.bias_src = l.b1; s1.args.neg_slope = l.slope1;
       TPZ_CHECK((l.proj != nullptr) == !s1.parts[1].identity, "tpz_model_update_weights: projection presence changed in layer %d", li);
     }
   }
@@ -375,5 +378,12 @@ extern "C" int tpz_model_step_buffers(const TpzModel* m, int step, void* weights
     TPZ_CUDA(cudaMemcpyAsync(weights_out, w, (size_t)n * sizeof(__half), cudaMemcpyDeviceToDevice, ST(stream)));
   }
   if (bias_out) TPZ_CUDA(cudaMemcpyAsync(bias_out, b, (size_t)co * sizeof(float), cudaMemcpyDeviceToDevice, ST(stream)));
+  return 0;
+}
+
+// Test hook: the launch-invariant argument block of conv step `step` (pointers as last used; geometry of the last forward).
+extern "C" int tpz_model_step_args(const TpzModel* m, int step, TpzTcConvArgs* out) {
+  TPZ_CHECK(m && out && step >= 0 && step < (int)m->steps.size(), "tpz_model_step_args: bad step %d", step);
+  *out = m->steps[step].args;
   return 0;
 }

@@ -32,7 +32,9 @@ __global__ void sample_params_kernel(int B, unsigned long long seed, unsigned lo
   int set = 0;
   while (set + 1 < nsets && us > set_cdf[set]) ++set;
   if (P > 0 && curand_uniform(&st) <= positive_balance) {
-    const int k = min((int)(curand_uniform(&st) * P), P - 1);
+    // 32-bit draw + multiply-high: the positives table lists every labelled PIXEL (discs are expanded) and can exceed 2^24
+    // entries, beyond which a float draw can no longer reach every index
+    const int k = (int)__umulhi(curand(&st), (unsigned)P);
     s.img = positives[3 * k]; s.cy = positives[3 * k + 1]; s.cx = positives[3 * k + 2]; s.label = 1;
   } else {
     const int n_in_set = set_begin[set + 1] - set_begin[set];

@@ -559,6 +559,235 @@ __global__ void __launch_bounds__(256, 2) wgrad_tc_kernel(const WgArgs a) {
   if (warp == 0) ptx::tmem_dealloc<TCOLS>(tmem_base);
 }
 
+// -------------------------------------------------------------------------------------------------
+// halo-resident forward / dgrad for the wide, shallow layers (stride 1, 32 -> 32 channels: r1.conv0, r1.conv1, r2.conv0 of
+// ResNet8-u32 and their data gradients -- 5 of the 8 largest launches of a training step)
+//
+// The gather-GEMM above stages one (tap, chunk) slice per block-wide barrier and re-reads every source pixel once per tap
+// (9x, from L1/L2).  Here a persistent CTA stages, per tile of 128 consecutive positions of the (zero-padded) source grid, the
+// 128 + halo source rows ONCE (coalesced 16-byte loads, split into hi / lo planes in the canonical K-major SWIZZLE_128B
+// layout); every tap is then the same tile read from a different start ROW (an operand may start at any
+// row of a swizzled tile), so a tile costs one barrier and 72 MMAs issued back to back:
+//     a_hi x [b_hi ; b_lo]  (N = 64: the hi and lo weight planes of a tap are adjacent in smem)  +  a_lo x b_hi  (N = 32).
+// All 9 x (32 x 32) weight blocks (72 KB with the lo planes) stay in shared memory for the life of the CTA.  Two smem stages
+// and two TMEM stages: the MMAs of tile i run while tile i-1 is drained / written and tile i+1 is loaded.
+// Truncating accumulate (see the header): the main term of every `group` taps has its own TMEM accumulator; the accumulators
+// are summed in registers (round-to-nearest) by the epilogue.
+// Positions are linear over the source grid Z (forward: the input itself; dgrad: dy zero-padded by (k-1)*dil + org), so a
+// tile's source rows are consecutive; outputs whose (u, v) fall outside the op's output are computed and dropped
+// (6-12 % of the rows for the 25..33-pixel feature maps of the training crops).
+// -------------------------------------------------------------------------------------------------
+constexpr int kHaloRows = 288;                   // staged source rows per tile: 128 outputs + up to 160 rows of halo
+constexpr int kHaloPlane = kHaloRows * 128;      // one plane (hi or lo) of a stage
+constexpr int kHaloMaxTaps = 9;
+constexpr int kHaloWBytes = kHaloMaxTaps * 8192; // per tap: hi 32 x 128 B | lo 32 x 128 B
+constexpr int kHaloSmem = kHaloWBytes + 2 * 2 * kHaloPlane + 1024;
+constexpr int kHaloMaxGroups = 3;                // main-term accumulators per TMEM stage (64 columns each) + 32 columns a_lo*b_hi
+
+struct HaloArgs {
+  const float* src; int N, SH, SW;      // source tensor [N][SH][SW][32]
+  int Hz, Wz, pad;                      // virtual source grid: Z[n][u][v] = src[n][u - pad][v - pad], zero outside
+  int OH, OW;                           // output [N][OH][OW][32]; position (n, u, v) of Z is an output iff u < OH and v < OW
+  int taps, rows, group, contiguous;    // rows staged per tile (multiple of 32); taps per main accumulator; Z == src
+  int roff[kHaloMaxTaps];               // source row of tap j relative to the output position (Z-linear)
+  int wrow[kHaloMaxTaps];               // first row of tap j's 32 x 32 block in the packed weight tensor
+  long long lo_rows, total;             // lo-plane row offset of the packed weights; N*Hz*Wz
+  int ntiles;
+  CUtensorMap tmB;                      // box = 32 rows
+  const float* bias; const float* res; int res_H, res_W, res_org, res_stride;
+  const float* mask; float* out; int relu, accumulate;
+};
+
+template <int MODE>              // 0 forward (bias / residual / ReLU epilogue), 1 data gradient (accumulate / mask epilogue)
+__global__ void __launch_bounds__(256, 1) conv_halo_tc_kernel(const __grid_constant__ HaloArgs a) {
+  constexpr uint32_t IDESC64 = idesc_tf32(128, 64), IDESC32 = idesc_tf32(128, 32);
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* const wsm = base;
+  unsigned char* const stages = base + kHaloWBytes;
+  __shared__ __align__(8) uint64_t bar_w, bar_mma[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    ptx::mbar_init(&bar_w, 1); ptx::mbar_init(&bar_mma[0], 1); ptx::mbar_init(&bar_mma[1], 1);
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&a.tmB);
+  }
+  if (warp == 0) ptx::tmem_alloc<512>(&tmem_base_s);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (tid == 0) {                                            // the whole weight set, once
+    ptx::mbar_expect_tx(&bar_w, (uint32_t)a.taps * 8192u);
+    for (int j = 0; j < a.taps; ++j) {
+      ptx::tma_load_2d(wsm + j * 8192, &a.tmB, &bar_w, 0, a.wrow[j]);
+      ptx::tma_load_2d(wsm + j * 8192 + 4096, &a.tmB, &bar_w, 0, (int)a.lo_rows + a.wrow[j]);
+    }
+  }
+
+  // staging: thread (jr, c) moves 16-byte piece c of rows jr, jr + 32, ...; a warp's load covers 4 rows = 512 contiguous bytes
+  const int c = tid & 7, jr = tid >> 3;
+  const float4* const src4 = reinterpret_cast<const float4*>(a.src);
+  const unsigned HWz = (unsigned)(a.Hz * a.Wz);
+  float4 pre[kHaloRows / 32];
+  auto load_tile = [&](int tile) {
+    const long long p0 = (long long)tile * 128;
+#pragma unroll
+    for (int i = 0; i < kHaloRows / 32; ++i) {
+      const int j = jr + 32 * i;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const long long p = p0 + j;
+      if (j < a.rows && p < a.total) {
+        if (a.contiguous) {
+          v = __ldg(src4 + p * 8 + c);
+        } else {
+          const unsigned pu = (unsigned)p;
+          const unsigned n = pu / HWz, rem = pu - n * HWz;
+          const unsigned u = rem / (unsigned)a.Wz, w = rem - u * (unsigned)a.Wz;
+          const int sy = (int)u - a.pad, sx = (int)w - a.pad;
+          if (sy >= 0 && sy < a.SH && sx >= 0 && sx < a.SW) v = __ldg(src4 + (((long long)n * a.SH + sy) * a.SW + sx) * 8 + c);
+        }
+      }
+      pre[i] = v;
+    }
+  };
+  auto store_tile = [&](unsigned char* stage) {
+#pragma unroll
+    for (int i = 0; i < kHaloRows / 32; ++i) {
+      const int j = jr + 32 * i;
+      if (j < a.rows) {
+        float4 hi, lo;
+        split4(pre[i], hi, lo);
+        const int off = j * 128 + ((c ^ (j & 7)) << 4);
+        *reinterpret_cast<float4*>(stage + off) = hi;
+        *reinterpret_cast<float4*>(stage + kHaloPlane + off) = lo;
+      }
+    }
+  };
+
+  const uint32_t d_hi = ptx::umma_desc_hi(1024, 2);          // SBO = 8 rows x 128 B, SWIZZLE_128B
+  const int ngroups = (a.taps + a.group - 1) / a.group;
+  auto issue_tile = [&](int s) {                             // one thread: every MMA of the tile staged in stage s
+    const uint32_t sa = ptx::smem_u32(stages + (size_t)s * 2 * kHaloPlane);
+    const uint32_t wb = ptx::smem_u32(wsm);
+    const uint32_t d = tmem_base + (uint32_t)s * 256u;
+    const uint32_t d_small = d + (uint32_t)ngroups * 64u;
+    int g = 0, in_g = 0;
+    for (int j = 0; j < a.taps; ++j) {
+      const uint32_t ah = ((sa + (uint32_t)a.roff[j] * 128u) & 0x3FFFF) >> 4, al = ah + (kHaloPlane >> 4);
+      const uint32_t bw = ((wb + (uint32_t)j * 8192u) & 0x3FFFF) >> 4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        umma_tf32(d_small, al + 2 * k, d_hi, bw + 2 * k, d_hi, IDESC32, (j | k) ? 1u : 0u);                 // a_lo x b_hi
+        umma_tf32(d + (uint32_t)g * 64u, ah + 2 * k, d_hi, bw + 2 * k, d_hi, IDESC64, (in_g | k) ? 1u : 0u);  // a_hi x [b_hi; b_lo]
+      }
+      if (++in_g == a.group) { in_g = 0; ++g; }
+    }
+  };
+
+  const int row = 32 * (warp & 3) + lane, half = warp >> 2;  // epilogue: thread (row, half) owns 16 channels of one output row
+  auto epilogue = [&](int tile, int s, int it) {
+    mbar_wait(&bar_mma[s], (uint32_t)(it >> 1) & 1u);
+    ptx::tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)s * 256u + (uint32_t)half * 16u;
+    float acc[16];
+    {
+      uint32_t r[16];
+      ptx::tmem_ld16(taddr + (uint32_t)ngroups * 64u, r);    // small terms first
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(r[j]);
+      for (int g = 0; g < ngroups; ++g) {
+        ptx::tmem_ld16(taddr + (uint32_t)g * 64u + 32u, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(r[j]);
+      }
+      for (int g = 0; g < ngroups; ++g) {
+        ptx::tmem_ld16(taddr + (uint32_t)g * 64u, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(r[j]);
+      }
+    }
+    ptx::tc_fence_before();
+    const long long q = (long long)tile * 128 + row;
+    if (q >= a.total) return;
+    const unsigned qu = (unsigned)q;
+    const unsigned n = qu / HWz, rem = qu - n * HWz;
+    const int u = (int)(rem / (unsigned)a.Wz), v = (int)(rem - (unsigned)u * (unsigned)a.Wz);
+    if (u >= a.OH || v >= a.OW) return;
+    const long long m = ((long long)n * a.OH + u) * a.OW + v;
+    const int nb = half * 16;
+    float* orow = a.out + m * 32 + nb;
+    long long rbase = 0;
+    if (MODE == 0 && a.res)
+      rbase = (((long long)n * a.res_H + (u * a.res_stride + a.res_org)) * a.res_W + (v * a.res_stride + a.res_org)) * 32;
+#pragma unroll
+    for (int c8 = 0; c8 < 16; c8 += 8) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = acc[c8 + j];
+      if (MODE == 0) {
+        if (a.bias) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += __ldg(a.bias + nb + c8 + j);
+        }
+        if (a.res) {
+          const float4 r0 = __ldg(reinterpret_cast<const float4*>(a.res + rbase + nb + c8));
+          const float4 r1 = __ldg(reinterpret_cast<const float4*>(a.res + rbase + nb + c8 + 4));
+          o[0] += r0.x; o[1] += r0.y; o[2] += r0.z; o[3] += r0.w; o[4] += r1.x; o[5] += r1.y; o[6] += r1.z; o[7] += r1.w;
+        }
+        if (a.relu) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+        }
+      } else {
+        if (a.accumulate) {
+          const float4 o0 = *reinterpret_cast<const float4*>(orow + c8), o1 = *reinterpret_cast<const float4*>(orow + c8 + 4);
+          o[0] += o0.x; o[1] += o0.y; o[2] += o0.z; o[3] += o0.w; o[4] += o1.x; o[5] += o1.y; o[6] += o1.z; o[7] += o1.w;
+        }
+        if (a.mask) {
+          const float4 k0 = __ldg(reinterpret_cast<const float4*>(a.mask + m * 32 + nb + c8));
+          const float4 k1 = __ldg(reinterpret_cast<const float4*>(a.mask + m * 32 + nb + c8 + 4));
+          o[0] = k0.x > 0.f ? o[0] : 0.f; o[1] = k0.y > 0.f ? o[1] : 0.f; o[2] = k0.z > 0.f ? o[2] : 0.f; o[3] = k0.w > 0.f ? o[3] : 0.f;
+          o[4] = k1.x > 0.f ? o[4] : 0.f; o[5] = k1.y > 0.f ? o[5] : 0.f; o[6] = k1.z > 0.f ? o[6] : 0.f; o[7] = k1.w > 0.f ? o[7] : 0.f;
+        }
+      }
+      ptx::st_global_256(orow + c8, __float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3]),
+                         __float_as_uint(o[4]), __float_as_uint(o[5]), __float_as_uint(o[6]), __float_as_uint(o[7]));
+    }
+  };
+
+  int it = 0, tile = blockIdx.x;
+  if (tile < a.ntiles) load_tile(tile);
+  for (; tile < a.ntiles; tile += gridDim.x, ++it) {
+    const int s = it & 1;
+    // stage s was last read by the MMAs of iteration it-2, which every thread saw complete in the epilogue of iteration it-1
+    store_tile(stages + (size_t)s * 2 * kHaloPlane);
+    ptx::fence_proxy_async();
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      ptx::tc_fence_after();
+      if (it == 0) mbar_wait(&bar_w, 0);
+      if (ptx::elect_one()) {
+        issue_tile(s);
+        ptx::umma_commit(&bar_mma[s]);
+      }
+      __syncwarp();
+    }
+    if (tile + (int)gridDim.x < a.ntiles) load_tile(tile + gridDim.x);   // in flight while the previous tile is written out
+    if (it > 0) epilogue(tile - gridDim.x, s ^ 1, it - 1);
+  }
+  if (it > 0) epilogue(tile - gridDim.x, (it - 1) & 1, it - 1);
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc<512>(tmem_base);
+}
+
 int g_flush = -1;
 int flush_chunks() {
   if (g_flush < 0) {
@@ -596,6 +825,86 @@ int weight_tmap(CUtensorMap* tm, const float* packed, long long rows, int box_ro
   return tpz_encode_tmap(tm, packed, 2, dims, strides, box, es, 128);
 }
 
+
+int g_halo = -1;
+bool halo_enabled() {
+  if (g_halo < 0) {
+    const char* e = getenv("TPZ_TRAIN_HALO");
+    g_halo = e ? atoi(e) : 1;
+  }
+  return g_halo != 0;
+}
+int g_sms = 0;
+int sm_count() {
+  if (!g_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sms <= 0) g_sms = 148;
+  }
+  return g_sms;
+}
+
+// Fills the geometry of the halo-resident kernel; false when the layer does not fit it (caller falls back to the gather-GEMM).
+// mode 0: forward of x [N][H][W][32] -> y [N][Ho][Wo][32]; mode 1: data gradient dy [N][Ho][Wo][32] -> dx [N][H][W][32].
+bool halo_geometry(HaloArgs& a, int mode, int N, int H, int W, int Ci, int Ho, int Wo, int Co, int kh, int kw, int stride, int dil,
+                   int org) {
+  if (!halo_enabled() || stride != 1 || Ci != 32 || Co != 32 || kh != kw || kh * kw > kHaloMaxTaps) return false;
+  const int k = kh, span = (k - 1) * dil;
+  a.N = N; a.taps = k * k;
+  if (mode == 0) {
+    a.SH = H; a.SW = W; a.OH = Ho; a.OW = Wo;
+    a.pad = org < 0 ? -org : 0;
+    const int need_h = Ho + span + org + a.pad, need_w = Wo + span + org + a.pad;
+    a.Hz = H + 2 * a.pad > need_h ? H + 2 * a.pad : need_h;
+    a.Wz = W + 2 * a.pad > need_w ? W + 2 * a.pad : need_w;
+    for (int r = 0; r < k; ++r)
+      for (int t = 0; t < k; ++t) {
+        a.roff[r * k + t] = (r * dil + org + a.pad) * a.Wz + (t * dil + org + a.pad);
+        a.wrow[r * k + t] = (r * k + t) * 32;
+      }
+  } else {
+    a.SH = Ho; a.SW = Wo; a.OH = H; a.OW = W;
+    a.pad = org + span;
+    if (a.pad < 0) return false;
+    a.Hz = H + span; a.Wz = W + span;
+    for (int r = 0; r < k; ++r)
+      for (int t = 0; t < k; ++t) {
+        a.roff[r * k + t] = ((k - 1 - r) * dil) * a.Wz + (k - 1 - t) * dil;
+        a.wrow[r * k + t] = (r * k + t) * 32;
+      }
+  }
+  int mx = 0;
+  for (int j = 0; j < a.taps; ++j) {
+    if (a.roff[j] < 0) return false;
+    if (a.roff[j] > mx) mx = a.roff[j];
+  }
+  a.rows = (128 + mx + 31) / 32 * 32;
+  if (a.rows > kHaloRows) return false;
+  a.total = (long long)N * a.Hz * a.Wz;
+  if (a.total >= (1ll << 31) - 512) return false;
+  a.ntiles = (int)((a.total + 127) / 128);
+  a.contiguous = a.pad == 0 && a.Hz == a.SH && a.Wz == a.SW;
+  int group = flush_chunks();                               // taps per main accumulator (Ci = 32: one chunk per tap)
+  if (group <= 0) group = a.taps;
+  while ((a.taps + group - 1) / group > kHaloMaxGroups) ++group;
+  a.group = group;
+  return true;
+}
+
+template <int MODE>
+int launch_halo(const HaloArgs& a, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    TPZ_CUDA(cudaFuncSetAttribute(conv_halo_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmem));
+    configured = true;
+  }
+  const int grid = a.ntiles < sm_count() ? a.ntiles : sm_count();
+  conv_halo_tc_kernel<MODE><<<grid, 256, kHaloSmem, stream>>>(a);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
@@ -613,6 +922,18 @@ extern "C" int tpz_conv_fwd_tc(const float* x, int N, int H, int W, int Ci, cons
                                int kh, int kw, int stride, int dil, int org, const float* res, int res_H, int res_W, int res_org,
                                int res_stride, int relu, float* y, int Ho, int Wo, void* stream) {
   TPZ_CHECK(Ci % 32 == 0 && Co % 32 == 0, "tpz_conv_fwd_tc: needs Ci%%32==0 and Co%%32==0 (Ci=%d Co=%d)", Ci, Co);
+  {
+    HaloArgs h;
+    memset(&h, 0, sizeof(h));
+    if (halo_geometry(h, 0, N, H, W, Ci, Ho, Wo, Co, kh, kw, stride, dil, org)) {
+      h.src = x; h.bias = bias; h.res = res; h.res_H = res_H; h.res_W = res_W; h.res_org = res_org; h.res_stride = res_stride;
+      h.out = y; h.relu = relu;
+      h.lo_rows = (long long)kh * kw * Co;
+      int rc = weight_tmap(&h.tmB, w_fwd_packed, 2 * h.lo_rows, 32);
+      if (rc) return rc;
+      return launch_halo<0>(h, ST(stream));
+    }
+  }
   FwdArgs a;
   memset(&a, 0, sizeof(a));
   a.g = tgeom(N, H, W, Ci, Ho, Wo, Co, kh, kw, stride, dil, org);
@@ -631,6 +952,17 @@ extern "C" int tpz_conv_dgrad_tc(const float* dy, int N, int Ho, int Wo, int Co,
                                  int stride, int dil, int org, const float* relu_mask, int accumulate, float* dx, int H, int W,
                                  void* stream) {
   TPZ_CHECK(Ci % 32 == 0 && Co % 32 == 0, "tpz_conv_dgrad_tc: needs Ci%%32==0 and Co%%32==0 (Ci=%d Co=%d)", Ci, Co);
+  {
+    HaloArgs h;
+    memset(&h, 0, sizeof(h));
+    if (halo_geometry(h, 1, N, H, W, Ci, Ho, Wo, Co, kh, kw, stride, dil, org)) {
+      h.src = dy; h.mask = relu_mask; h.accumulate = accumulate; h.out = dx;
+      h.lo_rows = (long long)kh * kw * Ci;
+      int rc = weight_tmap(&h.tmB, w_dg_packed, 2 * h.lo_rows, 32);
+      if (rc) return rc;
+      return launch_halo<1>(h, ST(stream));
+    }
+  }
   FwdArgs a;
   memset(&a, 0, sizeof(a));
   a.g = tgeom(N, H, W, Ci, Ho, Wo, Co, kh, kw, stride, dil, org);
