@@ -246,12 +246,28 @@ int tpz_conv_dgrad_tc(const float* dy, int N, int Ho, int Wo, int Co, const floa
                       void* stream);
 int tpz_conv_wgrad_tc(const float* x, int N, int H, int W, int Ci, const float* dy, int Ho, int Wo, int Co, int kh, int kw,
                       int stride, int dil, int org, float* dw, void* stream);
+/* Fused variants (one kernel when the halo-resident path takes the layer, the separate kernels otherwise):
+ *  tpz_conv_dgrad_tc_res : dx = mask(dgrad [+ dx] + res placed at (res_org, res_org)) -- ResidA.conv0's data gradient plus the gradient
+ *                          of the cropped identity skip (resnet.py:198-203) and the ReLU mask of the block input
+ *  tpz_conv_wgrad_tc_bias: also db[c] += sum over pixels of dy[.][c] (db may be NULL)                                                */
+int tpz_conv_dgrad_tc_res(const float* dy, int N, int Ho, int Wo, int Co, const float* w_dg_packed, int Ci, int kh, int kw, int stride,
+                          int dil, int org, const float* relu_mask, int accumulate, const float* res, int res_H, int res_W,
+                          int res_org, float* dx, int H, int W, void* stream);
+int tpz_conv_wgrad_tc_bias(const float* x, int N, int H, int W, int Ci, const float* dy, int Ho, int Wo, int Co, int kh, int kw,
+                           int stride, int dil, int org, float* dw, float* db, void* stream);
 /* Cin = 1 first layer of the training net (resnet.py:294, 7x7 stride 2), valid conv, org = 0 */
 int tpz_first_fwd_f32(const float* x, int N, int H, int W, const float* w, const float* bias, int Co, int k, int stride,
                       int relu, float* y, int Ho, int Wo, void* stream);
 int tpz_first_wgrad_f32(const float* x, int N, int H, int W, const float* dy, int Ho, int Wo, int Co, int k, int stride,
                         float* dw, void* stream);
 int tpz_bias_grad_f32(const float* dy, long long P, int C, float* db, void* stream);   /* db[c] += sum_p dy[p][c] */
+/* Classifier head in training (classifier.py:29,65: 1x1 conv C -> 1 on M pixels, x [M][C] fp32):
+ *  tpz_cls_fwd_f32: y[m] = sum_c x[m][c]*w[c] + bias[0]
+ *  tpz_cls_bwd_f32: dx[m][c] = g[m]*w[c] (zero where masked and x[m][c] <= 0: the ReLU of the layer that produced x; dx may be NULL),
+ *                   dw[c] += sum_m g[m]*x[m][c], db[0] += sum_m g[m]  (dw / db accumulate, as p.grad does) */
+int tpz_cls_fwd_f32(const float* x, long long M, int C, const float* w, const float* bias, float* y, void* stream);
+int tpz_cls_bwd_f32(const float* x, long long M, int C, const float* w, const float* g, int masked, float* dx, float* dw, float* db,
+                    void* stream);
 int tpz_relu_bwd_f32(float* dy, const float* y, long long n, void* stream);
 int tpz_crop_add_f32(float* dx, int N, int H, int W, int C, const float* g, int Ho, int Wo, int org, int stride,
                      void* stream);
@@ -298,14 +314,6 @@ int tpz_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq
  * from it in the kernel, so the launch can be replayed from a CUDA graph of the whole training step (methods.py). */
 int tpz_adam_step_dev(float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
                       float beta2, float eps, int* step_dev, float l2, float grad_scale, void* stream);
-
-/* ---- hardware probe used by tests/bring-up (UMMA descriptor row-offset behaviour), not on the product path ---- */
-int tpz_lab_umma(const tpz_half* A, int rowsA, const tpz_half* B, int N, int shift, int sbo_rows, int base_off_mode,
-                 int kc, float* D, void* stream);
-/* CTA-pair probe: tcgen05.mma.cta_group::2 (M = 256 over two CTAs of a cluster), operands by generic stores or pair TMA. */
-int tpz_lab_umma_pair(const tpz_half* A, const tpz_half* B, int N, int use_tma, float* D, int* status, void* stream);
-int tpz_lab_umma_rate(int N, int shift, int sbo_rows, int iters, int two_acc, long long* cycles, void* stream);
-int tpz_lab_tma_stride(const tpz_half* A, int rowsA, int start, int stride, int nrows, tpz_half* out, void* stream);
 
 /* ---- training-crop sampler + augmentation on the GPU ----
  * Replaces MultipleImageSetDataset.__getitem__ / MemoryMappedImage.get_crop (topaz/utils/data/memory_mapped_data.py:45-100,

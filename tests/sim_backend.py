@@ -323,7 +323,7 @@ def t_conv_fwd(x, w, b, stride, dil, org, Ho, Wo, relu, res=None, res_org=0, res
     return torch.relu(y) if relu else y
 
 
-def t_conv_dgrad(dy, w, stride, dil, org, H, W, mask=None, accumulate=False, out=None):
+def t_conv_dgrad(dy, w, stride, dil, org, H, W, mask=None, accumulate=False, out=None, res=None, res_org=0):
     N, Ho, Wo, Co = dy.shape
     k = w.shape[-1]
     need_h = (Ho - 1) * stride + (k - 1) * dil + 1
@@ -333,6 +333,8 @@ def t_conv_dgrad(dy, w, stride, dil, org, H, W, mask=None, accumulate=False, out
     dx[:, org:org + need_h, org:org + need_w] = _nhwc(gi)
     if accumulate:
         dx = dx + out
+    if res is not None:
+        dx[:, res_org:res_org + res.shape[1], res_org:res_org + res.shape[2]] += res
     if mask is not None:
         dx = torch.where(mask > 0, dx, torch.zeros_like(dx))
     if out is not None:
@@ -348,6 +350,11 @@ def t_conv_wgrad(x, dy, w_grad, b_grad, stride, dil, org):
     w_grad.add_(gw)
     if b_grad is not None:
         b_grad.add_(dy.sum((0, 1, 2)))
+
+
+def t_cls_bwd(x, g, w, w_grad, b_grad, masked):
+    t_conv_wgrad(x, g, w_grad, b_grad, 1, 1, 0)
+    return t_conv_dgrad(g, w, 1, 1, 0, x.shape[1], x.shape[2], mask=x if masked else None)
 
 
 def t_relu_bwd(dy, y):
@@ -463,7 +470,7 @@ def t_adam_step(fp, lr, b1, b2, eps, l2):
 @contextlib.contextmanager
 def patched_training():
     from topaz_b200 import train_engine as T
-    names = {'_conv_fwd': t_conv_fwd, '_conv_dgrad': t_conv_dgrad, '_conv_wgrad': t_conv_wgrad, '_relu_bwd': t_relu_bwd,
+    names = {'_conv_fwd': t_conv_fwd, '_conv_dgrad': t_conv_dgrad, '_conv_wgrad': t_conv_wgrad, '_cls_bwd': t_cls_bwd, '_relu_bwd': t_relu_bwd,
              '_crop_add': t_crop_add, '_bn_stats': t_bn_stats, '_bn_fwd': t_bn_fwd, '_bn_bwd_reduce': t_bn_bwd_reduce,
              '_bn_bwd': t_bn_bwd, '_act_fwd': t_act_fwd, '_act_bwd': t_act_bwd, '_dropout_fwd': t_dropout_fwd, '_dropout_bwd': t_dropout_bwd,
              'ge_loss_grad': t_ge_loss_grad, 'pu_objective_loss_grad': t_pu_objective, 'adam_step': t_adam_step,

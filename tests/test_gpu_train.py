@@ -160,6 +160,8 @@ def test_conv_mma_kernels_match_fp32(N, H, Ci, Co, k, stride, dil, org):
     # halo-resident kernel (stride 1, 32 -> 32): dilation 2 (largest halo), a cropped origin, 1x1, fewer tiles than SMs
     (40, 31, 32, 32, 3, 1, 2, 0), (3, 20, 32, 32, 3, 1, 1, 2), (2, 17, 32, 32, 1, 1, 1, 1), (1, 9, 32, 32, 3, 1, 1, 0),
     (256, 27, 32, 32, 3, 1, 1, 0),
+    # one-pixel outputs (the last 5x5 layer on a training crop): split-K forward + per-tap scatter dgrad; an uncovered variant
+    (256, 5, 64, 128, 5, 1, 1, 0), (40, 6, 32, 64, 3, 1, 2, 1),
 ])
 def test_conv_tc_kernels_match_fp32(N, H, Ci, Co, k, stride, dil, org):
     """tcgen05 (kind::tf32, 3-pass) fwd / dgrad / wgrad vs torch CPU fp32, with the weights packed by tpz_train_repack_tc
@@ -211,14 +213,51 @@ def test_conv_tc_kernels_match_fp32(N, H, Ci, Co, k, stride, dil, org):
     mask = torch.randn(N, H, H, Ci, generator=g)
     base = torch.randn(N, H, H, Ci, generator=g)
     dx2 = base.clone().cuda()
-    _lib.check(L.tpz_conv_dgrad_tc(P(dyd), N, Ho, Ho, Co, P(packed[2 * n:]), Ci, k, k, stride, dil, org, P(mask.cuda()), 1, P(dx2), H, H, None))
+    maskd0 = mask.cuda()
+    _lib.check(L.tpz_conv_dgrad_tc(P(dyd), N, Ho, Ho, Co, P(packed[2 * n:]), Ci, k, k, stride, dil, org, P(maskd0), 1, P(dx2), H, H, None))
     assert max(rel_err(dx2.cpu(), torch.where(mask > 0, base + _nhwc(gref), torch.zeros(())))) < 5e-5
+    if H > 4:       # fused form: + the gradient of a cropped identity skip (embedded at res_org) before the mask
+        rs = torch.randn(N, H - 2, H - 2, Ci, generator=g)
+        emb = torch.zeros(N, H, H, Ci); emb[:, 1:H - 1, 1:H - 1] = rs
+        dx3 = torch.empty(N, H, H, Ci, device='cuda')
+        maskd, rsd = mask.cuda(), rs.cuda()                # named: a temporary's block could be reused before the launch reads it
+        _lib.check(L.tpz_conv_dgrad_tc_res(P(dyd), N, Ho, Ho, Co, P(packed[2 * n:]), Ci, k, k, stride, dil, org, P(maskd), 0,
+                                           P(rsd), H - 2, H - 2, 1, P(dx3), H, H, None))
+        assert max(rel_err(dx3.cpu(), torch.where(mask > 0, _nhwc(gref) + emb, torch.zeros(())))) < 5e-5
     gw = torch.nn.grad.conv2d_weight(xin.contiguous(), tuple(w.shape), dy, stride=stride, dilation=dil)
     dw = torch.zeros_like(w).cuda()
     _lib.check(L.tpz_conv_wgrad_tc(P(xd), N, H, H, Ci, P(dyd), Ho, Ho, Co, k, k, stride, dil, org, P(dw), None))
     e = max(rel_err(dw.cpu(), gw))
     print('conv_wgrad_tc rel err', e)
     assert e < 5e-5
+    dw2 = torch.zeros_like(w).cuda(); db = torch.full((Co,), 0.5, device='cuda')
+    _lib.check(L.tpz_conv_wgrad_tc_bias(P(xd), N, H, H, Ci, P(dyd), Ho, Ho, Co, k, k, stride, dil, org, P(dw2), P(db), None))
+    assert max(rel_err(dw2.cpu(), gw)) < 5e-5
+    assert max(rel_err(db.cpu(), 0.5 + dy.sum((0, 2, 3)))) < 2e-5
+
+
+@pytest.mark.parametrize('M,C,masked', [(256, 128, True), (37, 256, False), (1000, 64, True)])
+def test_classifier_head_kernels_match_fp32(M, C, masked):
+    """tpz_cls_fwd_f32 / tpz_cls_bwd_f32 (1x1 conv C -> 1 and its fused backward) vs torch fp32."""
+    import ctypes as C_
+    from topaz_b200 import _lib
+    L = _lib.lib()
+    P = lambda t: C_.c_void_p(t.data_ptr())
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(M, C, generator=g); w = torch.randn(C, generator=g) * 0.1; b = torch.randn(1, generator=g)
+    gy = torch.randn(M, generator=g)
+    xd, wd, bd, gd = x.cuda(), w.cuda(), b.cuda(), gy.cuda()
+    y = torch.empty(M, device='cuda')
+    _lib.check(L.tpz_cls_fwd_f32(P(xd), M, C, P(wd), P(bd), P(y), None))
+    assert max(rel_err(y.cpu(), x @ w + b)) < 1e-5
+    dx = torch.empty(M, C, device='cuda'); dw = torch.full((C,), 0.5, device='cuda'); db = torch.full((1,), 0.25, device='cuda')
+    _lib.check(L.tpz_cls_bwd_f32(P(xd), M, C, P(wd), P(gd), int(masked), P(dx), P(dw), P(db), None))
+    dx_ref = gy[:, None] * w[None, :]
+    if masked:
+        dx_ref = torch.where(x > 0, dx_ref, torch.zeros(()))
+    assert torch.equal(dx.cpu(), dx_ref)
+    assert max(rel_err(dw.cpu(), 0.5 + gy @ x)) < 1e-5
+    assert abs(float(db.cpu()) - 0.25 - float(gy.sum())) < 1e-4
 
 
 @pytest.mark.parametrize('tag', ['PN', 'PNpi', 'GE_KL', 'PU', 'PUclip'])

@@ -8,6 +8,8 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 from topaz_b200 import ops
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "lab"))
+import lab
 from topaz_b200.ops import ConvPart
 
 os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
@@ -30,14 +32,14 @@ def lab():
             for shift in (0, 1, 3, 5, 13):
                 rows = torch.tensor([shift + (m // 8) * sbo + (m % 8) for m in range(128)])
                 exp = A[rows].float() @ B.float().t()
-                D = ops.lab_umma(Ad, Bd, shift, sbo, 0, kc); torch.cuda.synchronize()
+                D = lab.lab_umma(Ad, Bd, shift, sbo, 0, kc); torch.cuda.synchronize()
                 err = (D.cpu() - exp).abs().max().item() / exp.abs().max().item()
                 res[f'kc{kc}_sbo{sbo}_shift{shift}'] = err
                 log(f'lab kc={kc} sbo={sbo} shift={shift}: rel err {err:.2e}', 'OK' if err < 1e-3 else 'FAIL')
     # TMA element-stride probe: which rows land in smem?
     A = torch.arange(600).float()[:, None].repeat(1, 64).half()      # row r holds the value r
     for stride, start, nrows in ((1, 5, 20), (2, 3, 20), (4, 7, 40), (8, 2, 30)):
-        raw = ops.lab_tma_stride(A.cuda(), start, stride, nrows); torch.cuda.synchronize()
+        raw = lab.lab_tma_stride(A.cuda(), start, stride, nrows); torch.cuda.synchronize()
         got = raw.cpu().float()[:, 0].tolist()
         exp = [float(start + i * stride) for i in range(nrows)]
         ok = got == exp

@@ -3,10 +3,11 @@
 import ctypes as C, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from topaz_b200 import _lib
-from topaz_b200._lib import check
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lab'))
+import lab
+from lab import check
 
-L = _lib.lib()
+L = lab.lib()
 torch.manual_seed(0)
 for N in (64, 128, 256, 32):
     for use_tma in (0, 1):

@@ -3,8 +3,8 @@
 // an arbitrary ROW of a TMA-written 128B-swizzled tile (start address not 1024-B aligned), and with what
 // base_offset / SBO?  One CTA: TMA-load A [rows][64] and B [N][64] fp16 (SWIZZLE_128B), issue 4 MMAs
 // (K = 64) with A start = row `shift`, 8-row-group stride `sbo_rows`, write D [128][N] fp32.
-#include "tpz_common.cuh"
-#include "../../include/topaz_b200.h"
+#include "../../topaz_b200/csrc/tpz_common.cuh"
+#include "tpz_lab.h"
 
 namespace {
 __device__ __forceinline__ bool lab_try(uint64_t* bar, uint32_t parity) {
@@ -293,6 +293,78 @@ extern "C" int tpz_lab_umma_pair(const tpz_half* A, const tpz_half* B, int N, in
   lab_pair_kernel<<<2, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tmA, tmB, reinterpret_cast<const __half*>(A),
                                                                             reinterpret_cast<const __half*>(B), N, use_tma, D,
                                                                             status);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// raw probe: one tcgen05.mma on caller-built shared-memory images and descriptors (see tpz_lab.h)
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(128, 1) lab_raw_kernel(const uint4* __restrict__ imgA, int vecA, const uint4* __restrict__ imgB, int vecB,
+                                                        unsigned long long descA, unsigned long long descB, uint32_t idesc, int N,
+                                                        int kind, float* __restrict__ D) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < vecA; i += 128) reinterpret_cast<uint4*>(base)[i] = imgA[i];
+  for (int i = tid; i < vecB; i += 128) reinterpret_cast<uint4*>(base + 65536)[i] = imgB[i];
+  if (tid == 0) { ptx::mbar_init(&bar, 1); ptx::fence_barrier_init(); }
+  if (warp == 0) ptx::tmem_alloc<256>(&tmem_base_s);
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      const uint64_t rel = (uint64_t)((ptx::smem_u32(base) & 0x3FFFF) >> 4);
+      const uint64_t da = descA + rel, db = descB + rel;          // start address field: low 14 bits
+      if (kind == 0) {
+        ptx::umma_f16(tmem_base, da, db, idesc, 0u);
+      } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_base), "l"(da), "l"(db), "r"(idesc), "r"(0u)
+            : "memory");
+      }
+      ptx::umma_commit(&bar);
+    }
+    __syncwarp();
+  }
+  for (uint32_t spins = 0; !lab_try(&bar, 0); ++spins)
+    if (spins > (1u << 26)) __trap();
+  ptx::tc_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    uint32_t r[16];
+    ptx::tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, r);
+    ptx::tmem_ld_wait();
+    for (int j = 0; j < 16; ++j)
+      if (c0 + j < N) D[(size_t)tid * N + c0 + j] = __uint_as_float(r[j]);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc<256>(tmem_base);
+}
+}  // namespace
+
+extern "C" int tpz_lab_umma_raw(const void* imgA, int bytesA, const void* imgB, int bytesB, unsigned long long descA,
+                                unsigned long long descB, unsigned idesc, int N, int kind, float* D, void* stream) {
+  TPZ_CHECK(bytesA > 0 && bytesA <= 65536 && bytesA % 16 == 0 && bytesB > 0 && bytesB <= 65536 && bytesB % 16 == 0,
+            "tpz_lab_umma_raw: images must be 16..65536 bytes, multiples of 16");
+  TPZ_CHECK(N % 16 == 0 && N >= 16 && N <= 256, "tpz_lab_umma_raw: bad N");
+  const int smem = 2 * 65536 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    TPZ_CUDA(cudaFuncSetAttribute(lab_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  lab_raw_kernel<<<1, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const uint4*>(imgA), bytesA / 16,
+                                                                           reinterpret_cast<const uint4*>(imgB), bytesB / 16, descA,
+                                                                           descB, idesc, N, kind, D);
   TPZ_CUDA(cudaGetLastError());
   return 0;
 }

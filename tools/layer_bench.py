@@ -7,6 +7,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 from topaz_b200 import ops
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "lab"))
+import lab
 from topaz_b200.ops import ConvPart
 
 
@@ -15,7 +17,7 @@ def rate_probe():
     for N in (64, 128, 256):
         for (shift, sbo) in ((0, 8), (1, 8), (4, 8), (0, 10), (3, 10), (0, 16), (5, 12)):
             for two in (False, True):
-                c = ops.lab_umma_rate(N, shift, sbo, 2000, two)
+                c = lab.lab_umma_rate(N, shift, sbo, 2000, two)
                 out[f'N{N}_shift{shift}_sbo{sbo}_two{int(two)}'] = c
                 print(f'mma rate N={N} shift={shift} sbo_rows={sbo} two_acc={int(two)}: {c:.1f} cycles/MMA (ideal {N/2:.0f})')
     return out

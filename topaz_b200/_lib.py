@@ -73,7 +73,6 @@ _PROTOS = {
     'tpz_im2col3d_first': (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P]),
     'tpz_conv_first_tc': (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _I, _F, _I, _P, _P, _P]),
     'tpz_conv_first_tc_supported': (_I, [_I, _I]),
-    'tpz_lab_umma_pair': (_I, [_P, _P, _I, _I, _P, _P, _P]),
     'tpz_gemm_f32': (_I, [_P, _LL, _I, _P, _I, _P, _P]),
     'tpz_gmm_sums': (_I, [_P, _LL, C.c_double, _P, _I, _P, _P]),
     'tpz_select_hist': (_I, [_P, _LL, _I, _P, _I, _P, _P]),
@@ -93,9 +92,13 @@ _PROTOS = {
     'tpz_conv_fwd_tc': (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P, _I, _I, _P]),
     'tpz_conv_dgrad_tc': (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P]),
     'tpz_conv_wgrad_tc': (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    'tpz_conv_dgrad_tc_res': (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _I, _P, _I, _I, _P]),
+    'tpz_conv_wgrad_tc_bias': (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     'tpz_first_fwd_f32': (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P, _I, _I, _P]),
     'tpz_first_wgrad_f32': (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P]),
     'tpz_bias_grad_f32': (_I, [_P, _LL, _I, _P, _P]),
+    'tpz_cls_fwd_f32': (_I, [_P, _LL, _I, _P, _P, _P, _P]),
+    'tpz_cls_bwd_f32': (_I, [_P, _LL, _I, _P, _P, _I, _P, _P, _P, _P]),
     'tpz_relu_bwd_f32': (_I, [_P, _P, _LL, _P]),
     'tpz_crop_add_f32': (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P]),
     'tpz_bn_stats_f32': (_I, [_P, _LL, _I, _P, _P]),
@@ -110,9 +113,6 @@ _PROTOS = {
     'tpz_pu_objective_loss_grad': (_I, [_P, _P, _I, _I, _D, _D, _D, _D, _I, _I, _P, _P, _P]),
     'tpz_adam_step': (_I, [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _I, _F, _F, _P]),
     'tpz_adam_step_dev': (_I, [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _P, _F, _F, _P]),
-    'tpz_lab_umma': (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _P]),
-    'tpz_lab_umma_rate': (_I, [_I, _I, _I, _I, _I, _P, _P]),
-    'tpz_lab_tma_stride': (_I, [_P, _I, _I, _I, _I, _P, _P]),
 }
 EXPORTS = tuple(_PROTOS.keys())
 

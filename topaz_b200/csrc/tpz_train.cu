@@ -623,6 +623,76 @@ extern "C" int tpz_first_wgrad_f32(const float* x, int N, int H, int W, const fl
   return 0;
 }
 
+// ---- classifier head of the training net: 1x1 conv C -> 1 on M pixels (classifier.py:29,65; M = the minibatch on training crops).
+// The generic direct-conv kernels spend 36 + 24 us on this 64 KFLOP op (4 thread blocks); one warp per pixel / one fused backward.
+namespace {
+__global__ void cls_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, long long M, int C,
+                               float* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const long long m = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (m >= M) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + m * C);
+  float acc = 0.f;
+  for (int c = lane; c < (C >> 2); c += 32) {
+    const float4 a = __ldg(xr + c);
+    // parameters live in one flat buffer (train_engine.FlatParams): a 1-element PReLU slope before them breaks 16-byte alignment
+    const float4 k = make_float4(__ldg(w + 4 * c), __ldg(w + 4 * c + 1), __ldg(w + 4 * c + 2), __ldg(w + 4 * c + 3));
+    acc = fmaf(a.x, k.x, acc); acc = fmaf(a.y, k.y, acc); acc = fmaf(a.z, k.z, acc); acc = fmaf(a.w, k.w, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) y[m] = acc + (b ? __ldg(b) : 0.f);
+}
+// dx[m][c] = (mask: x[m][c] > 0) ? g[m]*w[c] : 0;  dw[c] += sum_m g[m]*x[m][c];  db += sum_m g[m].  Block = 8 warps x 4 rows.
+__global__ void cls_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ g, long long M, int C,
+                               int masked, float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db) {
+  extern __shared__ float s_dw[];                      // [C]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s_dw[c] = 0.f;
+  __syncthreads();
+  const long long m0 = (long long)blockIdx.x * 32 + warp * 4;
+  float gsum = 0.f;
+  for (int c4 = lane; c4 < (C >> 2); c4 += 32) {
+    const float4 k = make_float4(__ldg(w + 4 * c4), __ldg(w + 4 * c4 + 1), __ldg(w + 4 * c4 + 2), __ldg(w + 4 * c4 + 3));   // see cls_fwd_kernel
+    float4 dwv = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long m = m0 + i;
+      if (m < M) {
+        const float gm = __ldg(g + m);
+        const float4 a = __ldg(reinterpret_cast<const float4*>(x + m * C) + c4);
+        dwv.x = fmaf(gm, a.x, dwv.x); dwv.y = fmaf(gm, a.y, dwv.y); dwv.z = fmaf(gm, a.z, dwv.z); dwv.w = fmaf(gm, a.w, dwv.w);
+        float4 d = make_float4(gm * k.x, gm * k.y, gm * k.z, gm * k.w);
+        if (masked) { d.x = a.x > 0.f ? d.x : 0.f; d.y = a.y > 0.f ? d.y : 0.f; d.z = a.z > 0.f ? d.z : 0.f; d.w = a.w > 0.f ? d.w : 0.f; }
+        if (dx) reinterpret_cast<float4*>(dx + m * C)[c4] = d;
+      }
+    }
+    atomicAdd(&s_dw[4 * c4], dwv.x); atomicAdd(&s_dw[4 * c4 + 1], dwv.y); atomicAdd(&s_dw[4 * c4 + 2], dwv.z); atomicAdd(&s_dw[4 * c4 + 3], dwv.w);
+  }
+  if (lane < 4 && m0 + lane < M) gsum = __ldg(g + m0 + lane);
+#pragma unroll
+  for (int o = 2; o > 0; o >>= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
+  if (lane == 0 && db) atomicAdd(db, gsum);
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(dw + c, s_dw[c]);
+}
+}  // namespace
+
+extern "C" int tpz_cls_fwd_f32(const float* x, long long M, int C, const float* w, const float* bias, float* y, void* stream) {
+  TPZ_CHECK(C % 4 == 0 && C > 0, "tpz_cls_fwd_f32: C must be a multiple of 4 (C=%d)", C);
+  cls_fwd_kernel<<<tpz_div_up(M, 8), 256, 0, ST(stream)>>>(x, w, bias, M, C, y);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tpz_cls_bwd_f32(const float* x, long long M, int C, const float* w, const float* g, int masked, float* dx, float* dw,
+                               float* db, void* stream) {
+  TPZ_CHECK(C % 4 == 0 && C > 0 && C <= 8192, "tpz_cls_bwd_f32: C must be a multiple of 4, at most 8192 (C=%d)", C);
+  cls_bwd_kernel<<<tpz_div_up(M, 32), 256, C * sizeof(float), ST(stream)>>>(x, w, g, M, C, masked, dx, dw, db);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int tpz_bias_grad_f32(const float* dy, long long P, int C, float* db, void* stream) {
   dim3 bg(tpz_div_up(C, 32), (unsigned)(P < 4096 ? 1 : (P < 65536 ? 64 : 296)));
   bias_grad_kernel<<<bg, 256, 0, ST(stream)>>>(dy, P, C, db);

@@ -107,6 +107,12 @@ struct FwdArgs {
   long long lo_rows;      // row offset of the lo plane inside the packed weight tensor
   const float* bias; const float* res; int res_H, res_W, res_org, res_stride;
   const float* mask; float* out; int relu, accumulate, flush;
+  int lat, lat0;          // dgrad with dil % stride == 0: only positions y = lat0 + i*lat (same for x) receive gradient; the M rows
+                          // enumerate that sub-lattice (lat = 1: all positions) and the rest of dx is zero-filled by the caller
+  int ksplit;             // forward, tiny grids (the last 5x5 layer: 4 tiles x 50 chunks): blockIdx.z takes `ksplit` consecutive
+                          // (tap, chunk) blocks and adds its raw partial sums into the zero-filled output; bias / ReLU run afterwards
+  int scatter;            // dgrad of a conv whose output is ONE pixel per image (the last 5x5 layer on a training crop): every dx
+                          // pixel has exactly one valid tap, so blockIdx.y selects the tap, the rows are the images and K = Co
 };
 
 constexpr int kPF = 3;            // chunks of A prefetched into registers ahead of the one being staged (hides the gather latency)
@@ -132,13 +138,18 @@ __global__ void __launch_bounds__(256, 2) conv_tc_kernel(const __grid_constant__
   const int taps = g.kh * g.kw;
   const int Cs = MODE == 0 ? g.Ci : g.Co;        // source channels (K per tap)
   const int Nn = MODE == 0 ? g.Co : g.Ci;        // output channels
-  const int MH = MODE == 0 ? g.Ho : g.H, MW = MODE == 0 ? g.Wo : g.W;
+  const int lat = MODE == 1 ? a.lat : 1, lat0 = MODE == 1 ? a.lat0 : 0;
+  const int MH = MODE == 0 ? g.Ho : (g.H - lat0 + lat - 1) / lat, MW = MODE == 0 ? g.Wo : (g.W - lat0 + lat - 1) / lat;
   const int SH = MODE == 0 ? g.H : g.Ho, SW = MODE == 0 ? g.W : g.Wo;
-  const long long Mtot = (long long)g.N * MH * MW;
+  const bool sc = MODE == 1 && a.scatter != 0;
+  const long long Mtot = sc ? (long long)g.N : (long long)g.N * MH * MW;
   const long long m = (long long)blockIdx.x * 128 + row;
-  const int n0 = blockIdx.y * BN;
+  const int n0 = sc ? 0 : blockIdx.y * BN;
   const int cchunks = Cs >> 5;
-  const int nk = taps * cchunks;
+  const bool ks = MODE == 0 && a.ksplit > 0;
+  // first weight block and block count of this CTA (scatter: the blocks of tap blockIdx.y; split-K: a slice of all blocks)
+  const int kb0 = sc ? (int)blockIdx.y * cchunks : (ks ? (int)blockIdx.z * a.ksplit : 0);
+  const int nk = sc ? cchunks : (ks ? min(a.ksplit, taps * cchunks - kb0) : taps * cchunks);
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(&bar_free[s], 1); ptx::mbar_init(&bar_acc[s], 1); }
@@ -155,8 +166,8 @@ __global__ void __launch_bounds__(256, 2) conv_tc_kernel(const __grid_constant__
   auto issue_b = [&](int kc) {                              // one elected thread asks TMA for the hi and lo weight blocks of chunk kc
     unsigned char* bst = bbase + (size_t)(kc % 3) * BSTAGE;
     ptx::mbar_expect_tx(&bar_b[kc % 3], 2u * B_BYTES);
-    ptx::tma_load_2d(bst, &a.tmB, &bar_b[kc % 3], 0, kc * Nn + n0);
-    ptx::tma_load_2d(bst + B_BYTES, &a.tmB, &bar_b[kc % 3], 0, (int)a.lo_rows + kc * Nn + n0);
+    ptx::tma_load_2d(bst, &a.tmB, &bar_b[kc % 3], 0, (kb0 + kc) * Nn + n0);
+    ptx::tma_load_2d(bst + B_BYTES, &a.tmB, &bar_b[kc % 3], 0, (int)a.lo_rows + (kb0 + kc) * Nn + n0);
   };
   if (tid == 0) issue_b(0);
 
@@ -164,9 +175,16 @@ __global__ void __launch_bounds__(256, 2) conv_tc_kernel(const __grid_constant__
   const bool row_ok = m < Mtot;
   int px = 0, py = 0, pn = 0;
   if (row_ok) { px = (int)(m % MW); const long long q = m / MW; py = (int)(q % MH); pn = (int)(q / MH); }
+  if (MODE == 1) { px = lat0 + px * lat; py = lat0 + py * lat; }
+  int t_r = 0, t_t = 0, t_c = 0;
+  if (sc) {                                                  // rows = images; the dx pixel is the one this tap reaches from dy (0, 0)
+    t_r = (int)blockIdx.y / g.kw; t_t = (int)blockIdx.y - t_r * g.kw;
+    pn = (int)m; py = g.org + t_r * g.dil; px = g.org + t_t * g.dil;
+  }
+  if (ks) { const int tap = kb0 / cchunks; t_c = (kb0 - tap * cchunks) * 32; t_r = tap / g.kw; t_t = tap - t_r * g.kw; }
+  const long long mo = MODE == 1 ? ((long long)pn * g.H + py) * g.W + px : m;      // row of the output tensor
 
   // source pixel of (row, tap): recomputed when the tap changes
-  int t_r = 0, t_t = 0, t_c = 0;
   long long a_off = 0;
   bool a_ok = false;
   auto tap_setup = [&]() {
@@ -312,7 +330,11 @@ __global__ void __launch_bounds__(256, 2) conv_tc_kernel(const __grid_constant__
     long long rbase = 0;
     if (MODE == 0 && a.res)
       rbase = (((long long)pn * a.res_H + (py * a.res_stride + a.res_org)) * a.res_W + (px * a.res_stride + a.res_org)) * g.Co;
-    float* orow = a.out + m * Nn + nb;
+    float* orow = a.out + mo * Nn + nb;
+    if (ks) {                                                // split-K partial: raw sums, finished by bias_act_kernel
+#pragma unroll
+      for (int j = 0; j < HN; ++j) atomicAdd(orow + j, tot[j]);
+    } else
 #pragma unroll
     for (int c = 0; c < HN; c += 8) {
       float v[8];
@@ -338,8 +360,8 @@ __global__ void __launch_bounds__(256, 2) conv_tc_kernel(const __grid_constant__
           v[0] += o0.x; v[1] += o0.y; v[2] += o0.z; v[3] += o0.w; v[4] += o1.x; v[5] += o1.y; v[6] += o1.z; v[7] += o1.w;
         }
         if (a.mask) {
-          const float4 k0 = __ldg(reinterpret_cast<const float4*>(a.mask + m * Nn + nb + c));
-          const float4 k1 = __ldg(reinterpret_cast<const float4*>(a.mask + m * Nn + nb + c + 4));
+          const float4 k0 = __ldg(reinterpret_cast<const float4*>(a.mask + mo * Nn + nb + c));
+          const float4 k1 = __ldg(reinterpret_cast<const float4*>(a.mask + mo * Nn + nb + c + 4));
           v[0] = k0.x > 0.f ? v[0] : 0.f; v[1] = k0.y > 0.f ? v[1] : 0.f; v[2] = k0.z > 0.f ? v[2] : 0.f; v[3] = k0.w > 0.f ? v[3] : 0.f;
           v[4] = k1.x > 0.f ? v[4] : 0.f; v[5] = k1.y > 0.f ? v[5] : 0.f; v[6] = k1.z > 0.f ? v[6] : 0.f; v[7] = k1.w > 0.f ? v[7] : 0.f;
         }
@@ -560,21 +582,30 @@ __global__ void __launch_bounds__(256, 2) wgrad_tc_kernel(const WgArgs a) {
 }
 
 // -------------------------------------------------------------------------------------------------
-// halo-resident forward / dgrad for the wide, shallow layers (stride 1, 32 -> 32 channels: r1.conv0, r1.conv1, r2.conv0 of
-// ResNet8-u32 and their data gradients -- 5 of the 8 largest launches of a training step)
+// halo-resident forward / dgrad / wgrad for the wide, shallow layers (stride 1, 32 -> 32 channels: r1.conv0, r1.conv1,
+// r2.conv0 of ResNet8-u32 and their gradients -- 8 of the 11 largest launches of a training step)
 //
-// The gather-GEMM above stages one (tap, chunk) slice per block-wide barrier and re-reads every source pixel once per tap
+// The gather-GEMMs above stage one (tap, chunk) slice per block-wide barrier and re-read every source pixel once per tap
 // (9x, from L1/L2).  Here a persistent CTA stages, per tile of 128 consecutive positions of the (zero-padded) source grid, the
-// 128 + halo source rows ONCE (coalesced 16-byte loads, split into hi / lo planes in the canonical K-major SWIZZLE_128B
-// layout); every tap is then the same tile read from a different start ROW (an operand may start at any
-// row of a swizzled tile), so a tile costs one barrier and 72 MMAs issued back to back:
-//     a_hi x [b_hi ; b_lo]  (N = 64: the hi and lo weight planes of a tap are adjacent in smem)  +  a_lo x b_hi  (N = 32).
-// All 9 x (32 x 32) weight blocks (72 KB with the lo planes) stay in shared memory for the life of the CTA.  Two smem stages
-// and two TMEM stages: the MMAs of tile i run while tile i-1 is drained / written and tile i+1 is loaded.
-// Truncating accumulate (see the header): the main term of every `group` taps has its own TMEM accumulator; the accumulators
-// are summed in registers (round-to-nearest) by the epilogue.
-// Positions are linear over the source grid Z (forward: the input itself; dgrad: dy zero-padded by (k-1)*dil + org), so a
-// tile's source rows are consecutive; outputs whose (u, v) fall outside the op's output are computed and dropped
+// 128 + halo source rows ONCE (coalesced 16-byte loads, split into hi / lo planes, row = pixel = 128 bytes, 16-byte piece c
+// of row j stored at piece c ^ (j & 7): the canonical SWIZZLE_128B tile); every tap is then the same tile read from a
+// different start ROW (an operand may start at any row of a swizzled tile).
+//   forward / dgrad: the tile is a K-major A operand (M = 128 pixels, K = 32 channels); per tap and K = 8 step
+//       a_hi x [b_hi ; b_lo]  (N = 64: the hi and lo weight planes of a tap are adjacent in smem -> columns [main | small])
+//       a_lo x b_hi           (N = 32, accumulated into the `small` columns);
+//     all 9 x (32 x 32) weight blocks (72 KB with the lo planes) stay in shared memory for the life of the CTA.
+//   wgrad: the tile is an MN-major A operand (M = channels, K = pixels; stored in the one layout 32-bit MN-major operands have,
+//     SWIZZLE_128B_BASE32B: 4 pixel rows x 128 bytes per atom, 32-byte pieces XOR-ed with row & 3);
+//     the M = 128 rows of one MMA are the four "taps" t = 0..3 of one kernel row r, i.e. four 32-channel atoms whose start
+//     rows are dil apart (descriptor MN-atom stride = dil x 128 bytes -- overlapping atoms; t = 3 is a dummy whose result is
+//     dropped), B = the dy tile, MN-major as well (N = 64: hi plane | lo plane).  No transposing stores at all.
+// Work split: warps 0-7 load / split / store tiles and drain accumulators, warp 8 issues the MMAs; two smem stages and two
+// TMEM stages, mbarriers only (no block-wide barrier in the loop): the MMAs of tile i run while tile i-1 is drained /
+// written and tile i+1 is loaded.
+// Truncating accumulate (see the header): the main term of every `group` taps (wgrad: every tile of 128 pixels) has its own
+// TMEM accumulator; the accumulators are summed in registers (round-to-nearest).
+// Positions are linear over the source grid Z (forward / wgrad: the input itself; dgrad: dy zero-padded by (k-1)*dil + org),
+// so a tile's source rows are consecutive; outputs whose (u, v) fall outside the op's output are computed and dropped
 // (6-12 % of the rows for the 25..33-pixel feature maps of the training crops).
 // -------------------------------------------------------------------------------------------------
 constexpr int kHaloRows = 288;                   // staged source rows per tile: 128 outputs + up to 160 rows of halo
@@ -582,13 +613,15 @@ constexpr int kHaloPlane = kHaloRows * 128;      // one plane (hi or lo) of a st
 constexpr int kHaloMaxTaps = 9;
 constexpr int kHaloWBytes = kHaloMaxTaps * 8192; // per tap: hi 32 x 128 B | lo 32 x 128 B
 constexpr int kHaloSmem = kHaloWBytes + 2 * 2 * kHaloPlane + 1024;
-constexpr int kHaloMaxGroups = 3;                // main-term accumulators per TMEM stage (64 columns each) + 32 columns a_lo*b_hi
+constexpr int kHaloMaxGroups = 4;                // accumulators per TMEM stage, 64 columns each: [main 32 | small 32]
+constexpr int kHaloWorkers = 256;                // threads of warps 0-7
+constexpr int kHaloThreads = kHaloWorkers + 32;  // + the MMA warp
 
 struct HaloArgs {
   const float* src; int N, SH, SW;      // source tensor [N][SH][SW][32]
   int Hz, Wz, pad;                      // virtual source grid: Z[n][u][v] = src[n][u - pad][v - pad], zero outside
   int OH, OW;                           // output [N][OH][OW][32]; position (n, u, v) of Z is an output iff u < OH and v < OW
-  int taps, rows, group, contiguous;    // rows staged per tile (multiple of 32); taps per main accumulator; Z == src
+  int taps, rows, group, contiguous;    // rows staged per tile (multiple of 32); taps per accumulator; Z == src
   int roff[kHaloMaxTaps];               // source row of tap j relative to the output position (Z-linear)
   int wrow[kHaloMaxTaps];               // first row of tap j's 32 x 32 block in the packed weight tensor
   long long lo_rows, total;             // lo-plane row offset of the packed weights; N*Hz*Wz
@@ -596,21 +629,43 @@ struct HaloArgs {
   CUtensorMap tmB;                      // box = 32 rows
   const float* bias; const float* res; int res_H, res_W, res_org, res_stride;
   const float* mask; float* out; int relu, accumulate;
+  // wgrad only
+  const float* dy; float* dw; float* db; int dil, row0[3], kper;   // row0[r]: source row of tap (r, 0); kper: tiles per CTA between flushes (unused)
 };
 
+// (n, u, v) of a Z-linear position, advanced incrementally (one division pair per tile and thread instead of one per row)
+struct ZPos {
+  int n, u, v;
+  __device__ __forceinline__ void set(long long p, int Hz, int Wz) {
+    const unsigned pu = (unsigned)p, hw = (unsigned)(Hz * Wz);
+    const unsigned nn = pu / hw, rem = pu - nn * hw, uu = rem / (unsigned)Wz;
+    n = (int)nn; u = (int)uu; v = (int)(rem - uu * (unsigned)Wz);
+  }
+  __device__ __forceinline__ void advance(int d, int Hz, int Wz) {
+    v += d;
+    while (v >= Wz) { v -= Wz; if (++u == Hz) { u = 0; ++n; } }
+  }
+};
+
+// low half of an MN-major operand descriptor: start address and LBO (= byte stride between MN atoms)
+__device__ __forceinline__ uint32_t desc_lo_mn(uint32_t smem_addr, uint32_t atom_stride_bytes) {
+  return ((smem_addr & 0x3FFFF) >> 4) | (((atom_stride_bytes >> 4) & 0x3FFF) << 16);
+}
+
 template <int MODE>              // 0 forward (bias / residual / ReLU epilogue), 1 data gradient (accumulate / mask epilogue)
-__global__ void __launch_bounds__(256, 1) conv_halo_tc_kernel(const __grid_constant__ HaloArgs a) {
+__global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tc_kernel(const __grid_constant__ HaloArgs a) {
   constexpr uint32_t IDESC64 = idesc_tf32(128, 64), IDESC32 = idesc_tf32(128, 32);
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* const wsm = base;
   unsigned char* const stages = base + kHaloWBytes;
-  __shared__ __align__(8) uint64_t bar_w, bar_mma[2];
+  __shared__ __align__(8) uint64_t bar_w, bar_full[2], bar_mma[2];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    ptx::mbar_init(&bar_w, 1); ptx::mbar_init(&bar_mma[0], 1); ptx::mbar_init(&bar_mma[1], 1);
+    ptx::mbar_init(&bar_w, 1);
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&bar_full[s], kHaloWorkers); ptx::mbar_init(&bar_mma[s], 1); }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&a.tmB);
   }
@@ -619,172 +674,355 @@ __global__ void __launch_bounds__(256, 1) conv_halo_tc_kernel(const __grid_const
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  if (tid == 0) {                                            // the whole weight set, once
-    ptx::mbar_expect_tx(&bar_w, (uint32_t)a.taps * 8192u);
-    for (int j = 0; j < a.taps; ++j) {
-      ptx::tma_load_2d(wsm + j * 8192, &a.tmB, &bar_w, 0, a.wrow[j]);
-      ptx::tma_load_2d(wsm + j * 8192 + 4096, &a.tmB, &bar_w, 0, (int)a.lo_rows + a.wrow[j]);
-    }
-  }
-
-  // staging: thread (jr, c) moves 16-byte piece c of rows jr, jr + 32, ...; a warp's load covers 4 rows = 512 contiguous bytes
-  const int c = tid & 7, jr = tid >> 3;
-  const float4* const src4 = reinterpret_cast<const float4*>(a.src);
-  const unsigned HWz = (unsigned)(a.Hz * a.Wz);
-  float4 pre[kHaloRows / 32];
-  auto load_tile = [&](int tile) {
-    const long long p0 = (long long)tile * 128;
-#pragma unroll
-    for (int i = 0; i < kHaloRows / 32; ++i) {
-      const int j = jr + 32 * i;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      const long long p = p0 + j;
-      if (j < a.rows && p < a.total) {
-        if (a.contiguous) {
-          v = __ldg(src4 + p * 8 + c);
-        } else {
-          const unsigned pu = (unsigned)p;
-          const unsigned n = pu / HWz, rem = pu - n * HWz;
-          const unsigned u = rem / (unsigned)a.Wz, w = rem - u * (unsigned)a.Wz;
-          const int sy = (int)u - a.pad, sx = (int)w - a.pad;
-          if (sy >= 0 && sy < a.SH && sx >= 0 && sx < a.SW) v = __ldg(src4 + (((long long)n * a.SH + sy) * a.SW + sx) * 8 + c);
-        }
-      }
-      pre[i] = v;
-    }
-  };
-  auto store_tile = [&](unsigned char* stage) {
-#pragma unroll
-    for (int i = 0; i < kHaloRows / 32; ++i) {
-      const int j = jr + 32 * i;
-      if (j < a.rows) {
-        float4 hi, lo;
-        split4(pre[i], hi, lo);
-        const int off = j * 128 + ((c ^ (j & 7)) << 4);
-        *reinterpret_cast<float4*>(stage + off) = hi;
-        *reinterpret_cast<float4*>(stage + kHaloPlane + off) = lo;
-      }
-    }
-  };
-
-  const uint32_t d_hi = ptx::umma_desc_hi(1024, 2);          // SBO = 8 rows x 128 B, SWIZZLE_128B
   const int ngroups = (a.taps + a.group - 1) / a.group;
-  auto issue_tile = [&](int s) {                             // one thread: every MMA of the tile staged in stage s
-    const uint32_t sa = ptx::smem_u32(stages + (size_t)s * 2 * kHaloPlane);
+  const int stride_t = gridDim.x;
+
+  if (warp == 8) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {                                         // the whole weight set, once
+      ptx::mbar_expect_tx(&bar_w, (uint32_t)a.taps * 8192u);
+      for (int j = 0; j < a.taps; ++j) {
+        ptx::tma_load_2d(wsm + j * 8192, &a.tmB, &bar_w, 0, a.wrow[j]);
+        ptx::tma_load_2d(wsm + j * 8192 + 4096, &a.tmB, &bar_w, 0, (int)a.lo_rows + a.wrow[j]);
+      }
+    }
+    __syncwarp();
+    mbar_wait(&bar_w, 0);
+    const uint32_t d_hi = ptx::umma_desc_hi(1024, 2);        // SBO = 8 rows x 128 B, SWIZZLE_128B
     const uint32_t wb = ptx::smem_u32(wsm);
-    const uint32_t d = tmem_base + (uint32_t)s * 256u;
-    const uint32_t d_small = d + (uint32_t)ngroups * 64u;
-    int g = 0, in_g = 0;
-    for (int j = 0; j < a.taps; ++j) {
-      const uint32_t ah = ((sa + (uint32_t)a.roff[j] * 128u) & 0x3FFFF) >> 4, al = ah + (kHaloPlane >> 4);
-      const uint32_t bw = ((wb + (uint32_t)j * 8192u) & 0x3FFFF) >> 4;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        umma_tf32(d_small, al + 2 * k, d_hi, bw + 2 * k, d_hi, IDESC32, (j | k) ? 1u : 0u);                 // a_lo x b_hi
-        umma_tf32(d + (uint32_t)g * 64u, ah + 2 * k, d_hi, bw + 2 * k, d_hi, IDESC64, (in_g | k) ? 1u : 0u);  // a_hi x [b_hi; b_lo]
-      }
-      if (++in_g == a.group) { in_g = 0; ++g; }
-    }
-  };
-
-  const int row = 32 * (warp & 3) + lane, half = warp >> 2;  // epilogue: thread (row, half) owns 16 channels of one output row
-  auto epilogue = [&](int tile, int s, int it) {
-    mbar_wait(&bar_mma[s], (uint32_t)(it >> 1) & 1u);
-    ptx::tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)s * 256u + (uint32_t)half * 16u;
-    float acc[16];
-    {
-      uint32_t r[16];
-      ptx::tmem_ld16(taddr + (uint32_t)ngroups * 64u, r);    // small terms first
-      ptx::tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(r[j]);
-      for (int g = 0; g < ngroups; ++g) {
-        ptx::tmem_ld16(taddr + (uint32_t)g * 64u + 32u, r);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(r[j]);
-      }
-      for (int g = 0; g < ngroups; ++g) {
-        ptx::tmem_ld16(taddr + (uint32_t)g * 64u, r);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(r[j]);
-      }
-    }
-    ptx::tc_fence_before();
-    const long long q = (long long)tile * 128 + row;
-    if (q >= a.total) return;
-    const unsigned qu = (unsigned)q;
-    const unsigned n = qu / HWz, rem = qu - n * HWz;
-    const int u = (int)(rem / (unsigned)a.Wz), v = (int)(rem - (unsigned)u * (unsigned)a.Wz);
-    if (u >= a.OH || v >= a.OW) return;
-    const long long m = ((long long)n * a.OH + u) * a.OW + v;
-    const int nb = half * 16;
-    float* orow = a.out + m * 32 + nb;
-    long long rbase = 0;
-    if (MODE == 0 && a.res)
-      rbase = (((long long)n * a.res_H + (u * a.res_stride + a.res_org)) * a.res_W + (v * a.res_stride + a.res_org)) * 32;
-#pragma unroll
-    for (int c8 = 0; c8 < 16; c8 += 8) {
-      float o[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = acc[c8 + j];
-      if (MODE == 0) {
-        if (a.bias) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] += __ldg(a.bias + nb + c8 + j);
-        }
-        if (a.res) {
-          const float4 r0 = __ldg(reinterpret_cast<const float4*>(a.res + rbase + nb + c8));
-          const float4 r1 = __ldg(reinterpret_cast<const float4*>(a.res + rbase + nb + c8 + 4));
-          o[0] += r0.x; o[1] += r0.y; o[2] += r0.z; o[3] += r0.w; o[4] += r1.x; o[5] += r1.y; o[6] += r1.z; o[7] += r1.w;
-        }
-        if (a.relu) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
-        }
-      } else {
-        if (a.accumulate) {
-          const float4 o0 = *reinterpret_cast<const float4*>(orow + c8), o1 = *reinterpret_cast<const float4*>(orow + c8 + 4);
-          o[0] += o0.x; o[1] += o0.y; o[2] += o0.z; o[3] += o0.w; o[4] += o1.x; o[5] += o1.y; o[6] += o1.z; o[7] += o1.w;
-        }
-        if (a.mask) {
-          const float4 k0 = __ldg(reinterpret_cast<const float4*>(a.mask + m * 32 + nb + c8));
-          const float4 k1 = __ldg(reinterpret_cast<const float4*>(a.mask + m * 32 + nb + c8 + 4));
-          o[0] = k0.x > 0.f ? o[0] : 0.f; o[1] = k0.y > 0.f ? o[1] : 0.f; o[2] = k0.z > 0.f ? o[2] : 0.f; o[3] = k0.w > 0.f ? o[3] : 0.f;
-          o[4] = k1.x > 0.f ? o[4] : 0.f; o[5] = k1.y > 0.f ? o[5] : 0.f; o[6] = k1.z > 0.f ? o[6] : 0.f; o[7] = k1.w > 0.f ? o[7] : 0.f;
-        }
-      }
-      ptx::st_global_256(orow + c8, __float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3]),
-                         __float_as_uint(o[4]), __float_as_uint(o[5]), __float_as_uint(o[6]), __float_as_uint(o[7]));
-    }
-  };
-
-  int it = 0, tile = blockIdx.x;
-  if (tile < a.ntiles) load_tile(tile);
-  for (; tile < a.ntiles; tile += gridDim.x, ++it) {
-    const int s = it & 1;
-    // stage s was last read by the MMAs of iteration it-2, which every thread saw complete in the epilogue of iteration it-1
-    store_tile(stages + (size_t)s * 2 * kHaloPlane);
-    ptx::fence_proxy_async();
-    ptx::tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += stride_t, ++it) {
+      const int s = it & 1;
+      // every worker has stored tile `it` AND finished reading TMEM stage s of tile it-2 (program order before its arrive)
+      mbar_wait(&bar_full[s], (uint32_t)(it >> 1) & 1u);
       ptx::tc_fence_after();
-      if (it == 0) mbar_wait(&bar_w, 0);
       if (ptx::elect_one()) {
-        issue_tile(s);
+        const uint32_t sa = ptx::smem_u32(stages + (size_t)s * 2 * kHaloPlane);
+        const uint32_t d = tmem_base + (uint32_t)s * 256u;
+        int g = 0, in_g = 0;
+        for (int j = 0; j < a.taps; ++j) {
+          const uint32_t ah = ((sa + (uint32_t)a.roff[j] * 128u) & 0x3FFFF) >> 4, al = ah + (kHaloPlane >> 4);
+          const uint32_t bw = ((wb + (uint32_t)j * 8192u) & 0x3FFFF) >> 4;
+          const uint32_t dg = d + (uint32_t)g * 64u;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_tf32(dg, ah + 2 * k, d_hi, bw + 2 * k, d_hi, IDESC64, (in_g | k) ? 1u : 0u);   // a_hi x [b_hi; b_lo] -> [main | small]
+            umma_tf32(dg + 32u, al + 2 * k, d_hi, bw + 2 * k, d_hi, IDESC32, 1u);               // a_lo x b_hi -> small
+          }
+          if (++in_g == a.group) { in_g = 0; ++g; }
+        }
         ptx::umma_commit(&bar_mma[s]);
       }
       __syncwarp();
     }
-    if (tile + (int)gridDim.x < a.ntiles) load_tile(tile + gridDim.x);   // in flight while the previous tile is written out
-    if (it > 0) epilogue(tile - gridDim.x, s ^ 1, it - 1);
+  } else {
+    // ------------------------------ workers: stage tiles, drain and write outputs ------------------------------
+    // staging: thread (jr, c) moves 16-byte piece c of rows jr, jr + 32, ...; a warp's load covers 4 rows = 512 contiguous bytes
+    const int c = tid & 7, jr = tid >> 3;
+    const float4* const src4 = reinterpret_cast<const float4*>(a.src);
+    float4 pre[kHaloRows / 32];
+    auto load_tile = [&](int tile) {
+      const long long p0 = (long long)tile * 128 + jr;
+      if (a.contiguous) {
+#pragma unroll
+        for (int i = 0; i < kHaloRows / 32; ++i) {
+          const long long p = p0 + 32 * i;
+          pre[i] = (32 * i < a.rows && p < a.total) ? __ldg(src4 + p * 8 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      } else {
+        ZPos z;
+        z.set(p0 < a.total ? p0 : 0, a.Hz, a.Wz);
+#pragma unroll
+        for (int i = 0; i < kHaloRows / 32; ++i) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (32 * i < a.rows && p0 + 32 * i < a.total) {
+            const int sy = z.u - a.pad, sx = z.v - a.pad;
+            if (sy >= 0 && sy < a.SH && sx >= 0 && sx < a.SW) v = __ldg(src4 + (((long long)z.n * a.SH + sy) * a.SW + sx) * 8 + c);
+          }
+          pre[i] = v;
+          z.advance(32, a.Hz, a.Wz);
+        }
+      }
+    };
+    auto store_tile = [&](unsigned char* stage) {
+#pragma unroll
+      for (int i = 0; i < kHaloRows / 32; ++i) {
+        const int j = jr + 32 * i;
+        if (32 * i < a.rows) {
+          float4 hi, lo;
+          split4(pre[i], hi, lo);
+          const int off = j * 128 + ((c ^ (j & 7)) << 4);
+          *reinterpret_cast<float4*>(stage + off) = hi;
+          *reinterpret_cast<float4*>(stage + kHaloPlane + off) = lo;
+        }
+      }
+    };
+
+    const int row = 32 * (warp & 3) + lane, half = warp >> 2;   // epilogue: thread (row, half) owns 16 channels of one output row
+    const unsigned HWz = (unsigned)(a.Hz * a.Wz);
+    auto epilogue = [&](int tile, int s, int it) {
+      // output coordinates and the epilogue's global operands first: their latency hides behind the wait for the tile's MMAs
+      const long long q = (long long)tile * 128 + row;
+      bool valid = q < a.total;
+      int n = 0, u = 0, v = 0;
+      if (valid) {
+        const unsigned qu = (unsigned)q;
+        const unsigned nn = qu / HWz, rem = qu - nn * HWz;
+        n = (int)nn; u = (int)(rem / (unsigned)a.Wz); v = (int)(rem - (unsigned)u * (unsigned)a.Wz);
+        valid = u < a.OH && v < a.OW;
+      }
+      const long long m = ((long long)n * a.OH + u) * a.OW + v;
+      const int nb = half * 16;
+      float* orow = a.out + m * 32 + nb;
+      float4 pr[4], pm[4], pa[4];                              // residual, mask, previous value: 16 channels each
+      bool use_res = false;
+      if (valid) {
+        if (a.res) {
+          long long rbase;
+          if (MODE == 0) {
+            rbase = (((long long)n * a.res_H + (u * a.res_stride + a.res_org)) * a.res_W + (v * a.res_stride + a.res_org)) * 32;
+            use_res = true;
+          } else {                                             // gradient of the cropped identity skip, embedded at res_org
+            const int ry = u - a.res_org, rx = v - a.res_org;
+            use_res = ry >= 0 && ry < a.res_H && rx >= 0 && rx < a.res_W;
+            rbase = (((long long)n * a.res_H + ry) * a.res_W + rx) * 32;
+          }
+          if (use_res) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pr[j] = __ldg(reinterpret_cast<const float4*>(a.res + rbase + nb) + j);
+          }
+        }
+        if (MODE == 1 && a.mask) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) pm[j] = __ldg(reinterpret_cast<const float4*>(a.mask + m * 32 + nb) + j);
+        }
+        if (MODE == 1 && a.accumulate) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) pa[j] = *(reinterpret_cast<const float4*>(orow) + j);
+        }
+      }
+      mbar_wait(&bar_mma[s], (uint32_t)(it >> 1) & 1u);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)s * 256u + (uint32_t)half * 16u;
+      float acc[16];
+      {
+        uint32_t rs[16], rm[16];
+        ptx::tmem_ld16(taddr + 32u, rs);                      // group 0: small, main
+        ptx::tmem_ld16(taddr, rm);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(rs[j]);
+        float mainsum[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) mainsum[j] = __uint_as_float(rm[j]);
+        for (int g = 1; g < ngroups; ++g) {
+          ptx::tmem_ld16(taddr + (uint32_t)g * 64u + 32u, rs);
+          ptx::tmem_ld16(taddr + (uint32_t)g * 64u, rm);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { acc[j] += __uint_as_float(rs[j]); mainsum[j] += __uint_as_float(rm[j]); }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] += mainsum[j];
+      }
+      ptx::tc_fence_before();
+      if (!valid) return;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float o[4] = {acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]};
+        if (MODE == 0) {
+          if (a.bias) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] += __ldg(a.bias + nb + 4 * j + e);      // scalar: parameter views need not be 16-byte aligned
+          }
+          if (use_res) { o[0] += pr[j].x; o[1] += pr[j].y; o[2] += pr[j].z; o[3] += pr[j].w; }
+          if (a.relu) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
+          }
+        } else {
+          if (a.accumulate) { o[0] += pa[j].x; o[1] += pa[j].y; o[2] += pa[j].z; o[3] += pa[j].w; }
+          if (use_res) { o[0] += pr[j].x; o[1] += pr[j].y; o[2] += pr[j].z; o[3] += pr[j].w; }
+          if (a.mask) {
+            o[0] = pm[j].x > 0.f ? o[0] : 0.f; o[1] = pm[j].y > 0.f ? o[1] : 0.f; o[2] = pm[j].z > 0.f ? o[2] : 0.f; o[3] = pm[j].w > 0.f ? o[3] : 0.f;
+          }
+        }
+        acc[4 * j] = o[0]; acc[4 * j + 1] = o[1]; acc[4 * j + 2] = o[2]; acc[4 * j + 3] = o[3];
+      }
+      ptx::st_global_256(orow, __float_as_uint(acc[0]), __float_as_uint(acc[1]), __float_as_uint(acc[2]), __float_as_uint(acc[3]),
+                         __float_as_uint(acc[4]), __float_as_uint(acc[5]), __float_as_uint(acc[6]), __float_as_uint(acc[7]));
+      ptx::st_global_256(orow + 8, __float_as_uint(acc[8]), __float_as_uint(acc[9]), __float_as_uint(acc[10]), __float_as_uint(acc[11]),
+                         __float_as_uint(acc[12]), __float_as_uint(acc[13]), __float_as_uint(acc[14]), __float_as_uint(acc[15]));
+    };
+
+    int it = 0, tile = blockIdx.x;
+    if (tile < a.ntiles) load_tile(tile);
+    for (; tile < a.ntiles; tile += stride_t, ++it) {
+      const int s = it & 1;
+      // smem stage s was last read by the MMAs of tile it-2, which this thread saw complete in the epilogue of tile it-2
+      store_tile(stages + (size_t)s * 2 * kHaloPlane);
+      ptx::fence_proxy_async();                               // this thread's stores -> visible to the tensor core's (async-proxy) reads
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&bar_full[s]);                         // every worker arrives for itself (count = kHaloWorkers)
+      if (tile + stride_t < a.ntiles) load_tile(tile + stride_t);     // in flight while the previous tile is written out
+      if (it > 0) epilogue(tile - stride_t, s ^ 1, it - 1);
+    }
+    if (it > 0) epilogue(tile - stride_t, (it - 1) & 1, it - 1);
   }
-  if (it > 0) epilogue(tile - gridDim.x, (it - 1) & 1, it - 1);
   ptx::tc_fence_before();
   __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc<512>(tmem_base);
+}
+
+// wgrad on the same tiles: dw[co][ci][r][t] += sum over positions p of x[p + roff(r, t)][ci] * dy[p][co]
+constexpr int kWgDyPlane = 128 * 128;                          // dy tile: 128 positions x 32 channels, one plane
+constexpr int kWgStage = 2 * kHaloPlane + 2 * kWgDyPlane;      // x hi | x lo | dy hi | dy lo
+constexpr int kWgSmem = 2 * kWgStage + 1024;
+
+__global__ void __launch_bounds__(kHaloThreads, 1) wgrad_halo_tc_kernel(const __grid_constant__ HaloArgs a) {
+  // MN-major A and B (bits 15, 16)
+  constexpr uint32_t IDESC64 = idesc_tf32(128, 64) | (1u << 15) | (1u << 16), IDESC32 = idesc_tf32(128, 32) | (1u << 15) | (1u << 16);
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t bar_full[2], bar_mma[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_db[32];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < 32) s_db[tid] = 0.f;
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&bar_full[s], kHaloWorkers); ptx::mbar_init(&bar_mma[s], 1); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) ptx::tmem_alloc<512>(&tmem_base_s);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int stride_t = gridDim.x;
+
+  if (warp == 8) {
+    // MN-major 32-bit operands exist in ONE shared-memory layout, SWIZZLE_128B_BASE32B (layout type 1): atom = 4 K-rows (pixels) x
+    // 128 bytes, 32-byte piece q of row p stored at piece q ^ (p & 3); LBO = stride between MN atoms, SBO = stride between the
+    // two K atoms of a K = 8 step (4 rows = 512 bytes).  A's MN atoms are the taps t = 0..3: dil rows apart (overlapping atoms).
+    const uint32_t d_hi_a = ptx::umma_desc_hi(512u, 1);
+    const uint32_t d_hi_b = ptx::umma_desc_hi(512u, 1);                        // N atoms (LBO): hi plane, lo plane
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += stride_t, ++it) {
+      const int s = it & 1;
+      mbar_wait(&bar_full[s], (uint32_t)(it >> 1) & 1u);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t xs = ptx::smem_u32(base + (size_t)s * kWgStage);
+        const uint32_t ys = xs + 2 * kHaloPlane;
+        const uint32_t d = tmem_base + (uint32_t)s * 256u;
+        for (int ks = 0; ks < 16; ++ks) {                     // 8 positions per MMA
+          const uint32_t b_lo = desc_lo_mn(ys + (uint32_t)ks * 1024u, kWgDyPlane);
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const uint32_t xr = xs + ((uint32_t)a.row0[r] + 8u * ks) * 128u;
+            umma_tf32(d + r * 64u, desc_lo_mn(xr, (uint32_t)a.dil * 128u), d_hi_a, b_lo, d_hi_b, IDESC64, ks ? 1u : 0u);   // x_hi x [dy_hi | dy_lo]
+            umma_tf32(d + r * 64u + 32u, desc_lo_mn(xr + kHaloPlane, (uint32_t)a.dil * 128u), d_hi_a, b_lo, d_hi_b, IDESC32, 1u);  // x_lo x dy_hi
+          }
+        }
+        ptx::umma_commit(&bar_mma[s]);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int c = tid & 7, jr = tid >> 3;
+    const float4* const x4 = reinterpret_cast<const float4*>(a.src);
+    const float4* const dy4 = reinterpret_cast<const float4*>(a.dy);
+    float4 prex[kHaloRows / 32], prey[4];
+    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);            // bias gradient: column sums of the dy pieces this thread stages
+    auto load_tile = [&](int tile) {
+      const long long p0 = (long long)tile * 128 + jr;
+#pragma unroll
+      for (int i = 0; i < kHaloRows / 32; ++i) {
+        const long long p = p0 + 32 * i;
+        prex[i] = (32 * i < a.rows && p < a.total) ? __ldg(x4 + p * 8 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      ZPos z;
+      z.set(p0 < a.total ? p0 : 0, a.Hz, a.Wz);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p0 + 32 * i < a.total && z.u < a.OH && z.v < a.OW) v = __ldg(dy4 + (((long long)z.n * a.OH + z.u) * a.OW + z.v) * 8 + c);
+        prey[i] = v;
+        z.advance(32, a.Hz, a.Wz);
+      }
+    };
+    auto store_tile = [&](unsigned char* stage) {
+#pragma unroll
+      for (int i = 0; i < kHaloRows / 32; ++i) {
+        const int j = jr + 32 * i;
+        if (32 * i < a.rows) {
+          float4 hi, lo;
+          split4(prex[i], hi, lo);
+          const int off = j * 128 + ((c ^ ((j & 3) << 1)) << 4);     // 32-byte piece (c >> 1) ^= j & 3
+          *reinterpret_cast<float4*>(stage + off) = hi;
+          *reinterpret_cast<float4*>(stage + kHaloPlane + off) = lo;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = jr + 32 * i;
+        float4 hi, lo;
+        split4(prey[i], hi, lo);
+        bsum.x += prey[i].x; bsum.y += prey[i].y; bsum.z += prey[i].z; bsum.w += prey[i].w;
+        const int off = j * 128 + ((c ^ ((j & 3) << 1)) << 4);
+        *reinterpret_cast<float4*>(stage + 2 * kHaloPlane + off) = hi;
+        *reinterpret_cast<float4*>(stage + 2 * kHaloPlane + kWgDyPlane + off) = lo;
+      }
+    };
+    // accumulator lane m = 32*t + ci (t = tap column, 3 = dummy), columns = co; thread (m, half) keeps co half*16 .. +16 of the 3 rows r
+    const int half = warp >> 2;
+    float tot[3][16];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) tot[r][j] = 0.f;
+    auto drain = [&](int s, int it) {
+      mbar_wait(&bar_mma[s], (uint32_t)(it >> 1) & 1u);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)s * 256u + (uint32_t)half * 16u;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        uint32_t rs[16], rm[16];
+        ptx::tmem_ld16(taddr + r * 64u + 32u, rs);
+        ptx::tmem_ld16(taddr + r * 64u, rm);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) tot[r][j] += __uint_as_float(rs[j]) + __uint_as_float(rm[j]);
+      }
+      ptx::tc_fence_before();
+    };
+    int it = 0, tile = blockIdx.x;
+    if (tile < a.ntiles) load_tile(tile);
+    for (; tile < a.ntiles; tile += stride_t, ++it) {
+      const int s = it & 1;
+      store_tile(base + (size_t)s * kWgStage);
+      ptx::fence_proxy_async();                               // this thread's stores -> visible to the tensor core's (async-proxy) reads
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&bar_full[s]);                         // every worker arrives for itself (count = kHaloWorkers)
+      if (tile + stride_t < a.ntiles) load_tile(tile + stride_t);
+      if (it > 0) drain(s ^ 1, it - 1);
+    }
+    if (it > 0) drain((it - 1) & 1, it - 1);
+    const int m = 32 * (warp & 3) + lane, t = m >> 5, ci = m & 31;
+    if (it > 0 && t < 3) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) atomicAdd(a.dw + ((long long)(half * 16 + j) * 32 + ci) * 9 + r * 3 + t, tot[r][j]);
+    }
+    if (a.db) {
+      atomicAdd(&s_db[4 * c], bsum.x); atomicAdd(&s_db[4 * c + 1], bsum.y); atomicAdd(&s_db[4 * c + 2], bsum.z); atomicAdd(&s_db[4 * c + 3], bsum.w);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (a.db && tid < 32) atomicAdd(a.db + tid, s_db[tid]);
   if (warp == 0) ptx::tmem_dealloc<512>(tmem_base);
 }
 
@@ -803,14 +1041,14 @@ TGeom tgeom(int N, int H, int W, int Ci, int Ho, int Wo, int Co, int kh, int kw,
 }
 
 template <int BN, int MODE>
-int launch_conv_tc(const FwdArgs& a, long long M, int Nn, cudaStream_t stream) {
+int launch_conv_tc(const FwdArgs& a, long long M, int Nn, cudaStream_t stream, int grid_y = 0, int grid_z = 1) {
   const int smem = 2 * (2 * kStageA) + 3 * (2 * BN * 128) + 1024;
   static bool configured = false;
   if (!configured) {
     TPZ_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  dim3 grid(tpz_div_up(M, 128), Nn / BN);
+  dim3 grid(tpz_div_up(M, 128), grid_y > 0 ? grid_y : Nn / BN, grid_z);
   conv_tc_kernel<BN, MODE><<<grid, 256, smem, stream>>>(a);
   TPZ_CUDA(cudaGetLastError());
   return 0;
@@ -834,6 +1072,50 @@ bool halo_enabled() {
   }
   return g_halo != 0;
 }
+int g_halo_wg = -1;
+bool halo_wgrad_enabled() {                                  // TPZ_TRAIN_HALO_WGRAD=0: keep the transposing wgrad kernel
+  if (g_halo_wg < 0) {
+    const char* e = getenv("TPZ_TRAIN_HALO_WGRAD");
+    g_halo_wg = e ? atoi(e) : 1;
+  }
+  return g_halo_wg != 0;
+}
+int g_lat_dg = -1;
+bool lattice_dgrad_enabled() {                               // TPZ_TRAIN_LATTICE_DGRAD=0: strided dgrad over every position
+  if (g_lat_dg < 0) {
+    const char* e = getenv("TPZ_TRAIN_LATTICE_DGRAD");
+    g_lat_dg = e ? atoi(e) : 1;
+  }
+  return g_lat_dg != 0;
+}
+int g_sc_dg = -1;
+bool scatter_dgrad_enabled() {                               // TPZ_TRAIN_SCATTER_DGRAD=0: generic dgrad for one-pixel outputs too
+  if (g_sc_dg < 0) {
+    const char* e = getenv("TPZ_TRAIN_SCATTER_DGRAD");
+    g_sc_dg = e ? atoi(e) : 1;
+  }
+  return g_sc_dg != 0;
+}
+int g_ksplit = -1;
+bool ksplit_enabled() {                                      // TPZ_TRAIN_KSPLIT=0: no split-K forward
+  if (g_ksplit < 0) {
+    const char* e = getenv("TPZ_TRAIN_KSPLIT");
+    g_ksplit = e ? atoi(e) : 1;
+  }
+  return g_ksplit != 0;
+}
+// y[m][c] = act(y[m][c] + bias[c]) after a split-K forward
+__global__ void bias_act_kernel(float* __restrict__ y, const float* __restrict__ bias, long long n4, int C, int relu) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<float4*>(y)[i];
+    if (bias) {                                              // scalar loads: parameter views need not be 16-byte aligned
+      const int c = (int)((i * 4) % C);
+      v.x += __ldg(bias + c); v.y += __ldg(bias + c + 1); v.z += __ldg(bias + c + 2); v.w += __ldg(bias + c + 3);
+    }
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    reinterpret_cast<float4*>(y)[i] = v;
+  }
+}
 int g_sms = 0;
 int sm_count() {
   if (!g_sms) {
@@ -852,7 +1134,7 @@ bool halo_geometry(HaloArgs& a, int mode, int N, int H, int W, int Ci, int Ho, i
   if (!halo_enabled() || stride != 1 || Ci != 32 || Co != 32 || kh != kw || kh * kw > kHaloMaxTaps) return false;
   const int k = kh, span = (k - 1) * dil;
   a.N = N; a.taps = k * k;
-  if (mode == 0) {
+  if (mode == 0 || mode == 2) {
     a.SH = H; a.SW = W; a.OH = Ho; a.OW = Wo;
     a.pad = org < 0 ? -org : 0;
     const int need_h = Ho + span + org + a.pad, need_w = Wo + span + org + a.pad;
@@ -879,6 +1161,12 @@ bool halo_geometry(HaloArgs& a, int mode, int N, int H, int W, int Ci, int Ho, i
     if (a.roff[j] < 0) return false;
     if (a.roff[j] > mx) mx = a.roff[j];
   }
+  if (mode == 2) {                                          // wgrad: M = 128 rows = taps t = 0..3 (t = 3 dummy) of one kernel row
+    if (k != 3) return false;
+    a.dil = dil;
+    for (int r = 0; r < 3; ++r) a.row0[r] = a.roff[r * 3];
+    mx = a.row0[2] + 3 * dil;
+  }
   a.rows = (128 + mx + 31) / 32 * 32;
   if (a.rows > kHaloRows) return false;
   a.total = (long long)N * a.Hz * a.Wz;
@@ -900,7 +1188,19 @@ int launch_halo(const HaloArgs& a, cudaStream_t stream) {
     configured = true;
   }
   const int grid = a.ntiles < sm_count() ? a.ntiles : sm_count();
-  conv_halo_tc_kernel<MODE><<<grid, 256, kHaloSmem, stream>>>(a);
+  conv_halo_tc_kernel<MODE><<<grid, kHaloThreads, kHaloSmem, stream>>>(a);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_wgrad_halo(const HaloArgs& a, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    TPZ_CUDA(cudaFuncSetAttribute(wgrad_halo_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem));
+    configured = true;
+  }
+  const int grid = a.ntiles < sm_count() ? a.ntiles : sm_count();
+  wgrad_halo_tc_kernel<<<grid, kHaloThreads, kWgSmem, stream>>>(a);
   TPZ_CUDA(cudaGetLastError());
   return 0;
 }
@@ -945,7 +1245,57 @@ extern "C" int tpz_conv_fwd_tc(const float* x, int N, int H, int W, int Ci, cons
   int rc = weight_tmap(&a.tmB, w_fwd_packed, 2 * rows, BN);
   if (rc) return rc;
   const long long M = (long long)N * Ho * Wo;
+  const int tiles = tpz_div_up(M, 128) * (Co / BN), nkb = kh * kw * (Ci / 32);
+  if (res == nullptr && tiles * 8 <= sm_count() && nkb >= 16 && ksplit_enabled()) {
+    // a handful of tiles with a long K loop (the last 5x5 layer on training crops: 4 tiles x 50 blocks): split K over the SMs
+    int splits = 2 * sm_count() / tiles;
+    if (splits > nkb / 4) splits = nkb / 4;
+    a.ksplit = tpz_div_up(nkb, splits);
+    splits = tpz_div_up(nkb, a.ksplit);
+    TPZ_CUDA(cudaMemsetAsync(y, 0, (size_t)M * Co * sizeof(float), ST(stream)));
+    rc = BN == 64 ? launch_conv_tc<64, 0>(a, M, Co, ST(stream), 0, splits) : launch_conv_tc<32, 0>(a, M, Co, ST(stream), 0, splits);
+    if (rc) return rc;
+    if (bias || relu) {
+      const long long n4 = M * Co / 4;
+      bias_act_kernel<<<tpz_div_up(n4, 256) < 1184 ? tpz_div_up(n4, 256) : 1184, 256, 0, ST(stream)>>>(y, bias, n4, Co, relu);
+      TPZ_CUDA(cudaGetLastError());
+    }
+    return 0;
+  }
   return BN == 64 ? launch_conv_tc<64, 0>(a, M, Co, ST(stream)) : launch_conv_tc<32, 0>(a, M, Co, ST(stream));
+}
+
+extern "C" int tpz_crop_add_f32(float* dx, int N, int H, int W, int C, const float* g, int Ho, int Wo, int org, int stride, void* stream);
+extern "C" int tpz_relu_bwd_f32(float* dy, const float* y, long long n, void* stream);
+extern "C" int tpz_bias_grad_f32(const float* dy, long long P, int C, float* db, void* stream);
+
+extern "C" int tpz_conv_dgrad_tc(const float* dy, int N, int Ho, int Wo, int Co, const float* w_dg_packed, int Ci, int kh, int kw,
+                                 int stride, int dil, int org, const float* relu_mask, int accumulate, float* dx, int H, int W,
+                                 void* stream);
+
+// dx = mask(dgrad [+ dx] + res embedded at (res_org, res_org)): the data gradient of ResidA.conv0 together with the gradient of the
+// cropped identity skip and the ReLU mask of the block input, in one pass when the halo-resident kernel takes the layer
+extern "C" int tpz_conv_dgrad_tc_res(const float* dy, int N, int Ho, int Wo, int Co, const float* w_dg_packed, int Ci, int kh, int kw,
+                                     int stride, int dil, int org, const float* relu_mask, int accumulate, const float* res, int res_H,
+                                     int res_W, int res_org, float* dx, int H, int W, void* stream) {
+  if (res == nullptr)
+    return tpz_conv_dgrad_tc(dy, N, Ho, Wo, Co, w_dg_packed, Ci, kh, kw, stride, dil, org, relu_mask, accumulate, dx, H, W, stream);
+  TPZ_CHECK(Ci % 32 == 0 && Co % 32 == 0, "tpz_conv_dgrad_tc_res: needs Ci%%32==0 and Co%%32==0 (Ci=%d Co=%d)", Ci, Co);
+  HaloArgs h;
+  memset(&h, 0, sizeof(h));
+  if (halo_geometry(h, 1, N, H, W, Ci, Ho, Wo, Co, kh, kw, stride, dil, org)) {
+    h.src = dy; h.mask = relu_mask; h.accumulate = accumulate; h.out = dx;
+    h.res = res; h.res_H = res_H; h.res_W = res_W; h.res_org = res_org; h.res_stride = 1;
+    h.lo_rows = (long long)kh * kw * Ci;
+    int rc = weight_tmap(&h.tmB, w_dg_packed, 2 * h.lo_rows, 32);
+    if (rc) return rc;
+    return launch_halo<1>(h, ST(stream));
+  }
+  int rc = tpz_conv_dgrad_tc(dy, N, Ho, Wo, Co, w_dg_packed, Ci, kh, kw, stride, dil, org, nullptr, accumulate, dx, H, W, stream);
+  if (rc) return rc;
+  rc = tpz_crop_add_f32(dx, N, H, W, Ci, res, res_H, res_W, res_org, 1, stream);
+  if (rc) return rc;
+  return relu_mask ? tpz_relu_bwd_f32(dx, relu_mask, (long long)N * H * W * Ci, stream) : 0;
 }
 
 extern "C" int tpz_conv_dgrad_tc(const float* dy, int N, int Ho, int Wo, int Co, const float* w_dg_packed, int Ci, int kh, int kw,
@@ -972,13 +1322,57 @@ extern "C" int tpz_conv_dgrad_tc(const float* dy, int N, int Ho, int Wo, int Co,
   const int BN = Ci % 64 == 0 ? 64 : 32;
   int rc = weight_tmap(&a.tmB, w_dg_packed, 2 * rows, BN);
   if (rc) return rc;
-  const long long M = (long long)N * H * W;
-  return BN == 64 ? launch_conv_tc<64, 1>(a, M, Ci, ST(stream)) : launch_conv_tc<32, 1>(a, M, Ci, ST(stream));
+  a.lat = 1; a.lat0 = 0;
+  long long M = (long long)N * H * W;
+  if (stride > 1 && (dil % stride == 0 || (kh == 1 && kw == 1)) && org >= 0 && !(accumulate && relu_mask) && lattice_dgrad_enabled()) {
+    // every tap reaches the same residue class of positions: run the GEMM on that sub-lattice only (1/stride^2 of the rows).
+    // (accumulate AND mask together would have to mask the untouched positions too: left to the generic path)
+    a.lat = stride; a.lat0 = org % stride;
+    const int mh = (H - a.lat0 + stride - 1) / stride, mw = (W - a.lat0 + stride - 1) / stride;
+    M = (long long)N * mh * mw;
+    if (!accumulate) TPZ_CUDA(cudaMemsetAsync(dx, 0, (size_t)N * H * W * Ci * sizeof(float), ST(stream)));
+  }
+  int grid_y = 0;
+  const bool covered = org == 0 && dil == 1 && kh == H && kw == W;      // every dx pixel is reached by exactly one tap
+  if (Ho == 1 && Wo == 1 && stride == 1 && Ci == BN && org >= 0 && org + (kh - 1) * dil < H && org + (kw - 1) * dil < W &&
+      (covered || !(accumulate && relu_mask)) && scatter_dgrad_enabled()) {
+    // one source pixel per image: dx pixel (org + r*dil, org + t*dil) = dy x w[r][t]; a GEMM with M = images per tap
+    a.scatter = 1; a.lat = 1; a.lat0 = 0;
+    M = N; grid_y = kh * kw;
+    if (!accumulate && !covered) TPZ_CUDA(cudaMemsetAsync(dx, 0, (size_t)N * H * W * Ci * sizeof(float), ST(stream)));
+  }
+  return BN == 64 ? launch_conv_tc<64, 1>(a, M, Ci, ST(stream), grid_y) : launch_conv_tc<32, 1>(a, M, Ci, ST(stream), grid_y);
+}
+
+extern "C" int tpz_conv_wgrad_tc(const float* x, int N, int H, int W, int Ci, const float* dy, int Ho, int Wo, int Co, int kh,
+                                 int kw, int stride, int dil, int org, float* dw, void* stream);
+
+// weight gradient and bias gradient (db[c] += sum over pixels of dy[.][c]; db may be NULL) -- one kernel on the halo-resident path
+extern "C" int tpz_conv_wgrad_tc_bias(const float* x, int N, int H, int W, int Ci, const float* dy, int Ho, int Wo, int Co, int kh,
+                                      int kw, int stride, int dil, int org, float* dw, float* db, void* stream) {
+  TPZ_CHECK(Ci % 32 == 0 && Co % 32 == 0, "tpz_conv_wgrad_tc_bias: needs Ci%%32==0 and Co%%32==0 (Ci=%d Co=%d)", Ci, Co);
+  HaloArgs h;
+  memset(&h, 0, sizeof(h));
+  if (halo_wgrad_enabled() && halo_geometry(h, 2, N, H, W, Ci, Ho, Wo, Co, kh, kw, stride, dil, org)) {
+    h.src = x; h.dy = dy; h.dw = dw; h.db = db;
+    return launch_wgrad_halo(h, ST(stream));
+  }
+  int rc = tpz_conv_wgrad_tc(x, N, H, W, Ci, dy, Ho, Wo, Co, kh, kw, stride, dil, org, dw, stream);
+  if (rc || !db) return rc;
+  return tpz_bias_grad_f32(dy, (long long)N * Ho * Wo, Co, db, stream);
 }
 
 extern "C" int tpz_conv_wgrad_tc(const float* x, int N, int H, int W, int Ci, const float* dy, int Ho, int Wo, int Co, int kh,
                                  int kw, int stride, int dil, int org, float* dw, void* stream) {
   TPZ_CHECK(Ci % 32 == 0 && Co % 32 == 0, "tpz_conv_wgrad_tc: needs Ci%%32==0 and Co%%32==0 (Ci=%d Co=%d)", Ci, Co);
+  {
+    HaloArgs h;
+    memset(&h, 0, sizeof(h));
+    if (halo_wgrad_enabled() && halo_geometry(h, 2, N, H, W, Ci, Ho, Wo, Co, kh, kw, stride, dil, org)) {
+      h.src = x; h.dy = dy; h.dw = dw;
+      return launch_wgrad_halo(h, ST(stream));
+    }
+  }
   WgArgs a;
   a.g = tgeom(N, H, W, Ci, Ho, Wo, Co, kh, kw, stride, dil, org);
   a.x = x; a.dy = dy; a.dw = dw; a.flush = flush_chunks();

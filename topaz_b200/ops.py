@@ -470,26 +470,3 @@ def filter_f32(x: torch.Tensor, f: torch.Tensor, bias: float = 0.0) -> torch.Ten
     y = torch.empty_like(x)
     _count(1); check(_lib.lib().tpz_filter_f32(_ptr(x), N, D, H, W, _ptr(f), kd, kh, kw, float(bias), _ptr(y), _stream()))
     return y
-
-
-def lab_umma(A: torch.Tensor, B: torch.Tensor, shift: int, sbo_rows: int, base_off_mode: int, kc: int = 64) -> torch.Tensor:
-    D = torch.zeros((128, B.shape[0]), dtype=torch.float32, device=A.device)
-    check(_lib.lib().tpz_lab_umma(_ptr(A), A.shape[0], _ptr(B), B.shape[0], shift, sbo_rows, base_off_mode, kc,
-                                  _ptr(D), _stream()))
-    return D
-
-
-def lab_tma_stride(A: torch.Tensor, start: int, stride: int, nrows: int) -> torch.Tensor:
-    """Raw shared-memory image (fp16 [nrows, 64], still 128B-swizzled) of a strided TMA box load."""
-    out = torch.zeros((nrows, 64), dtype=torch.float16, device=A.device)
-    check(_lib.lib().tpz_lab_tma_stride(_ptr(A), A.shape[0], start, stride, nrows, _ptr(out), _stream()))
-    return out
-
-
-def lab_umma_rate(N: int, shift: int, sbo_rows: int, iters: int = 2000, two_acc: bool = False) -> float:
-    """SM cycles per (M=128, N, K=16) fp16 MMA for an A operand starting at row `shift` with 8-row groups
-    `sbo_rows` rows apart (hardware probe, see csrc/tpz_lab.cu)."""
-    cyc = torch.zeros(1, dtype=torch.int64, device='cuda')
-    check(_lib.lib().tpz_lab_umma_rate(N, shift, sbo_rows, iters, int(two_acc), _ptr(cyc), _stream()))
-    torch.cuda.synchronize()
-    return float(cyc.item()) / (iters * 4 * (2 if two_acc else 1))

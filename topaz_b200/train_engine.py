@@ -190,6 +190,9 @@ def _conv_fwd(x, w, b, stride, dil, org, Ho, Wo, relu, res=None, res_org=0, res_
     if USE_MMA and Ci == 1 and Co in (32, 64) and org == 0 and dil == 1 and res is None and kh == kw:
         check(_lib.lib().tpz_first_fwd_f32(_p(x), N, H, W, _p(w), _p(b), Co, kh, stride, int(relu), _p(y), Ho, Wo, _s()))
         return y
+    if USE_MMA and Co == 1 and kh == 1 and kw == 1 and stride == 1 and org == 0 and res is None and not relu and Ci % 4 == 0:
+        check(_lib.lib().tpz_cls_fwd_f32(_p(x), N * H * W, Ci, _p(w), _p(b), _p(y), _s()))       # classifier head: one warp per pixel
+        return y
     pt = _packed_tc(w)
     if pt is not None and Ci % 32 == 0 and Co % 32 == 0:
         check(_lib.lib().tpz_conv_fwd_tc(_p(x), N, H, W, Ci, _p(pt[0]), _p(b), Co, kh, kw, stride, dil, org, _p(res),
@@ -208,15 +211,27 @@ def _conv_fwd(x, w, b, stride, dil, org, Ho, Wo, relu, res=None, res_org=0, res_
     return y
 
 
-def _conv_dgrad(dy, w, stride, dil, org, H, W, mask=None, accumulate=False, out=None):
+def _conv_dgrad(dy, w, stride, dil, org, H, W, mask=None, accumulate=False, out=None, res=None, res_org=0):
+    """dx = mask(dgrad(dy) [+ out] [+ res embedded at (res_org, res_org)]); `res` is the gradient arriving through a cropped
+    identity skip (fused into the halo-resident kernel's epilogue where that kernel applies)."""
     N, Ho, Wo, Co = dy.shape
     _, Ci, kh, kw = w.shape
     dx = out if out is not None else torch.empty((N, H, W, Ci), dtype=torch.float32, device=dy.device)
     ops._count(1)
     pt = _packed_tc(w)
     if pt is not None and Co % 32 == 0 and Ci % 32 == 0:
+        if res is not None:
+            check(_lib.lib().tpz_conv_dgrad_tc_res(_p(dy), N, Ho, Wo, Co, _p(pt[1]), Ci, kh, kw, stride, dil, org, _p(mask),
+                                                   int(accumulate), _p(res), res.shape[1], res.shape[2], res_org, _p(dx), H, W, _s()))
+            return dx
         check(_lib.lib().tpz_conv_dgrad_tc(_p(dy), N, Ho, Wo, Co, _p(pt[1]), Ci, kh, kw, stride, dil, org, _p(mask),
                                            int(accumulate), _p(dx), H, W, _s()))
+        return dx
+    if res is not None:                                   # no fused form on the mma.sync / fp32 paths: three passes
+        dx = _conv_dgrad(dy, w, stride, dil, org, H, W, mask=None, accumulate=accumulate, out=out)
+        _crop_add(dx, res, res_org, 1)
+        if mask is not None:
+            _relu_bwd(dx, mask)
         return dx
     pk = _packed(w)
     if pk is not None and Co % 16 == 0 and Ci % 32 == 0:
@@ -239,9 +254,9 @@ def _conv_wgrad(x, dy, w_grad, b_grad, stride, dil, org):
             check(_lib.lib().tpz_bias_grad_f32(_p(dy), N * Ho * Wo, Co, _p(b_grad), _s()))
         return
     if USE_TC and Ci % 32 == 0 and Co % 32 == 0:
-        check(_lib.lib().tpz_conv_wgrad_tc(_p(x), N, H, W, Ci, _p(dy), Ho, Wo, Co, kh, kw, stride, dil, org, _p(w_grad), _s()))
-        if b_grad is not None:
-            check(_lib.lib().tpz_bias_grad_f32(_p(dy), N * Ho * Wo, Co, _p(b_grad), _s()))
+        # the bias gradient rides along in the halo-resident wgrad kernel (the library runs the separate reducer otherwise)
+        check(_lib.lib().tpz_conv_wgrad_tc_bias(_p(x), N, H, W, Ci, _p(dy), Ho, Wo, Co, kh, kw, stride, dil, org, _p(w_grad),
+                                                _p(b_grad), _s()))
         return
     if USE_MMA and Ci % 16 == 0 and Co % 16 == 0:
         check(_lib.lib().tpz_conv_wgrad_mma(_p(x), N, H, W, Ci, _p(dy), Ho, Wo, Co, kh, kw, stride, dil, org, _p(w_grad), _s()))
@@ -250,6 +265,19 @@ def _conv_wgrad(x, dy, w_grad, b_grad, stride, dil, org):
         return
     check(_lib.lib().tpz_conv_wgrad_f32(_p(x), N, H, W, Ci, _p(dy), Ho, Wo, Co, kh, kw, stride, dil, org, _p(w_grad),
                                         _p(b_grad), _s()))
+
+
+def _cls_bwd(x, g, w, w_grad, b_grad, masked: bool):
+    """backward of the classifier head (1x1 conv C -> 1): returns dx, accumulates w_grad / b_grad; `masked` fuses the ReLU mask of
+    the layer that produced x."""
+    N, H, W, Ci = x.shape
+    if USE_MMA and Ci % 4 == 0 and Ci <= 8192:
+        dx = torch.empty_like(x)
+        ops._count(1)
+        check(_lib.lib().tpz_cls_bwd_f32(_p(x), N * H * W, Ci, _p(w), _p(g), int(masked), _p(dx), _p(w_grad), _p(b_grad), _s()))
+        return dx
+    _conv_wgrad(x, g, w_grad, b_grad, 1, 1, 0)
+    return _conv_dgrad(g, w, 1, 1, 0, H, W, mask=x if masked else None)
 
 
 def _relu_bwd(dy, y):
@@ -560,8 +588,7 @@ def backward(model, dscore: torch.Tensor, on_suffix_done=None):
                 x = rec['x']
                 N, H, W, _ = x.shape
                 g = dscore.contiguous().view(N, H, W, 1)
-                _conv_wgrad(x, g, rec['w'].grad, rec['b'].grad, 1, 1, 0)
-                g = _conv_dgrad(g, rec['w'], 1, 1, 0, H, W, mask=x if in_relu else None)
+                g = _cls_bwd(x, g, rec['w'], rec['w'].grad, rec['b'].grad if rec['b'] is not None else None, in_relu)
             elif rec['kind'] == 'dropout':
                 g = _dropout_bwd(g, rec['mask'], rec['p'])
             elif rec['kind'] == 'conv':
@@ -585,13 +612,17 @@ def backward(model, dscore: torch.Tensor, on_suffix_done=None):
                 if rec.get('bn0') is not None:
                     dh = _bn_backward(dh, rec['c0'], rec['save0'], rec['count0'], rec['bn0'], ws)
                 _conv_wgrad(x, dh, rec['w0'].grad, rec['b0'].grad if rec['b0'] is not None else None, 1, d0, 0)
-                dx = _conv_dgrad(dh, rec['w0'], 1, d0, 0, x.shape[1], x.shape[2])
+                # dx = relu'(x) * (dgrad(conv0) + gradient through the skip); x is the previous layer's ReLU output
                 if rec['proj'] is not None:
                     _conv_wgrad(x, g, rec['proj'].grad, None, s, 1, edge)
-                    _conv_dgrad(g, rec['proj'], s, 1, edge, x.shape[1], x.shape[2], accumulate=True, out=dx)
+                    dx = _conv_dgrad(g, rec['proj'], s, 1, edge, x.shape[1], x.shape[2])
+                    dx = _conv_dgrad(dh, rec['w0'], 1, d0, 0, x.shape[1], x.shape[2], mask=x, accumulate=True, out=dx)
+                elif s == 1:
+                    dx = _conv_dgrad(dh, rec['w0'], 1, d0, 0, x.shape[1], x.shape[2], mask=x, res=g, res_org=edge)
                 else:
+                    dx = _conv_dgrad(dh, rec['w0'], 1, d0, 0, x.shape[1], x.shape[2])
                     _crop_add(dx, g, edge, s)
-                _relu_bwd(dx, x)            # x is the previous layer's ReLU output
+                    _relu_bwd(dx, x)
                 g = dx
             if on_suffix_done is not None:
                 on_suffix_done(_block_offset(fp, rec))
