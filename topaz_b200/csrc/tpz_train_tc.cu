@@ -874,6 +874,233 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tc_kernel(const __g
   if (warp == 0) ptx::tmem_dealloc<512>(tmem_base);
 }
 
+// 64 -> 64 channel variant of the forward / dgrad kernel (r3.conv0 / r3.conv1 of ResNet8-u32 and their data gradients: 160-240
+// tiles, where the gather-GEMM spends ~3 us per (tap, chunk) on barrier and TMA latency with one CTA per SM).  Same tile scheme;
+// a pixel row is two 32-channel chunks (two pairs of hi / lo planes), N = 64, so per tap, chunk and K = 8 step
+//     a_hi x [b_hi ; b_lo] (N = 128 -> columns [main 64 | small 64]),  a_lo x b_hi (N = 64 -> small).
+// The weights (9 taps x 32 KB with the lo planes) do not fit beside the tile: warp 9 streams them per tap through a 3-slot TMA
+// ring, every tile.  One smem stage and one TMEM stage (a CTA sees one or two tiles).
+constexpr int kH64Rows = 224;                      // 128 outputs + up to 96 rows of halo (33 x 33 maps with dilation 1, 11 x 11 with 2)
+constexpr int kH64Plane = kH64Rows * 128;
+constexpr int kH64Stage = 4 * kH64Plane;              // chunk 0 hi | chunk 0 lo | chunk 1 hi | chunk 1 lo
+constexpr int kH64WSlot = 32768;                      // one tap: chunk 0 (hi 64 x 128 B | lo) | chunk 1 (hi | lo)
+constexpr int kH64Smem = kH64Stage + 3 * kH64WSlot + 1024;
+constexpr int kH64Threads = 256 + 64;
+
+template <int MODE>
+__global__ void __launch_bounds__(kH64Threads, 1) conv_halo64_tc_kernel(const __grid_constant__ HaloArgs a) {
+  constexpr uint32_t IDESC128 = idesc_tf32(128, 128), IDESC64 = idesc_tf32(128, 64);
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* const stage = base;
+  unsigned char* const wring = base + kH64Stage;
+  __shared__ __align__(8) uint64_t bar_full, bar_mma, bar_wfull[3], bar_wfree[3];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    ptx::mbar_init(&bar_full, 256); ptx::mbar_init(&bar_mma, 1);
+    for (int i = 0; i < 3; ++i) { ptx::mbar_init(&bar_wfull[i], 1); ptx::mbar_init(&bar_wfree[i], 1); }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&a.tmB);
+  }
+  if (warp == 0) ptx::tmem_alloc<512>(&tmem_base_s);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int ngroups = (a.taps + a.group - 1) / a.group;
+  const int stride_t = gridDim.x;
+  const int my_tiles = (int)blockIdx.x < a.ntiles ? (a.ntiles - (int)blockIdx.x + stride_t - 1) / stride_t : 0;
+
+  if (warp == 9) {
+    // ------------------------------ weight producer: one tap (32 KB) per ring slot ------------------------------
+    if (lane == 0) {
+      const int total = my_tiles * a.taps;
+      for (int q = 0; q < total; ++q) {
+        const int slot = q % 3, j = q % a.taps;
+        if (q >= 3) mbar_wait(&bar_wfree[slot], (uint32_t)((q / 3) - 1) & 1u);
+        unsigned char* w = wring + (size_t)slot * kH64WSlot;
+        ptx::mbar_expect_tx(&bar_wfull[slot], (uint32_t)kH64WSlot);
+        for (int c = 0; c < 2; ++c) {
+          ptx::tma_load_2d(w + c * 16384, &a.tmB, &bar_wfull[slot], 0, a.wrow[j] + c * 64);
+          ptx::tma_load_2d(w + c * 16384 + 8192, &a.tmB, &bar_wfull[slot], 0, (int)a.lo_rows + a.wrow[j] + c * 64);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 8) {
+    // ------------------------------ MMA issuer ------------------------------
+    const uint32_t d_hi = ptx::umma_desc_hi(1024, 2);
+    const uint32_t sa = ptx::smem_u32(stage), wb = ptx::smem_u32(wring);
+    for (int it = 0; it < my_tiles; ++it) {
+      mbar_wait(&bar_full, (uint32_t)it & 1u);               // tile stored; every worker is done with the previous tile's TMEM
+      ptx::tc_fence_after();
+      int g = 0, in_g = 0;
+      for (int j = 0; j < a.taps; ++j) {
+        const int q = it * a.taps + j, slot = q % 3;
+        mbar_wait(&bar_wfull[slot], (uint32_t)(q / 3) & 1u);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t dg = tmem_base + (uint32_t)g * 128u;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const uint32_t ah = ((sa + (uint32_t)c * 2u * kH64Plane + (uint32_t)a.roff[j] * 128u) & 0x3FFFF) >> 4, al = ah + (kH64Plane >> 4);
+            const uint32_t bw = ((wb + (uint32_t)slot * kH64WSlot + (uint32_t)c * 16384u) & 0x3FFFF) >> 4;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_tf32(dg, ah + 2 * k, d_hi, bw + 2 * k, d_hi, IDESC128, (in_g | c | k) ? 1u : 0u);   // a_hi x [b_hi; b_lo]
+              umma_tf32(dg + 64u, al + 2 * k, d_hi, bw + 2 * k, d_hi, IDESC64, 1u);                    // a_lo x b_hi
+            }
+          }
+          ptx::umma_commit(&bar_wfree[slot]);
+          if (j + 1 == a.taps) ptx::umma_commit(&bar_mma);
+        }
+        __syncwarp();
+        if (++in_g == a.group) { in_g = 0; ++g; }
+      }
+    }
+  } else {
+    // ------------------------------ workers ------------------------------
+    // staging: thread (jr, pc) moves 16-byte piece pc (0..15: chunk pc >> 3) of rows jr, jr + 16, ...
+    const int pc = tid & 15, jr = tid >> 4;
+    const float4* const src4 = reinterpret_cast<const float4*>(a.src);
+    float4 pre[kH64Rows / 16];
+    auto load_tile = [&](int tile) {
+      const long long p0 = (long long)tile * 128 + jr;
+      if (a.contiguous) {
+#pragma unroll
+        for (int i = 0; i < kH64Rows / 16; ++i) {
+          const long long p = p0 + 16 * i;
+          pre[i] = (16 * i < a.rows && p < a.total) ? __ldg(src4 + p * 16 + pc) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      } else {
+        ZPos z;
+        z.set(p0 < a.total ? p0 : 0, a.Hz, a.Wz);
+#pragma unroll
+        for (int i = 0; i < kH64Rows / 16; ++i) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (16 * i < a.rows && p0 + 16 * i < a.total) {
+            const int sy = z.u - a.pad, sx = z.v - a.pad;
+            if (sy >= 0 && sy < a.SH && sx >= 0 && sx < a.SW) v = __ldg(src4 + (((long long)z.n * a.SH + sy) * a.SW + sx) * 16 + pc);
+          }
+          pre[i] = v;
+          z.advance(16, a.Hz, a.Wz);
+        }
+      }
+    };
+    auto store_tile = [&]() {
+      unsigned char* plane = stage + (size_t)(pc >> 3) * 2 * kH64Plane;
+#pragma unroll
+      for (int i = 0; i < kH64Rows / 16; ++i) {
+        const int j = jr + 16 * i;
+        if (16 * i < a.rows) {
+          float4 hi, lo;
+          split4(pre[i], hi, lo);
+          const int off = j * 128 + (((pc & 7) ^ (j & 7)) << 4);
+          *reinterpret_cast<float4*>(plane + off) = hi;
+          *reinterpret_cast<float4*>(plane + kH64Plane + off) = lo;
+        }
+      }
+    };
+    const int row = 32 * (warp & 3) + lane, half = warp >> 2;   // epilogue: thread (row, half) owns 32 channels of one output row
+    const unsigned HWz = (unsigned)(a.Hz * a.Wz);
+    auto epilogue = [&](int tile, int it) {
+      mbar_wait(&bar_mma, (uint32_t)it & 1u);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)half * 32u;
+      float acc[32];
+      {
+        uint32_t r[32];
+        ptx::tmem_ld32(taddr + 64u, r);                        // small terms first
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
+        for (int g = 1; g < ngroups; ++g) {
+          ptx::tmem_ld32(taddr + (uint32_t)g * 128u + 64u, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
+        }
+        for (int g = 0; g < ngroups; ++g) {
+          ptx::tmem_ld32(taddr + (uint32_t)g * 128u, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
+        }
+      }
+      ptx::tc_fence_before();
+      const long long q = (long long)tile * 128 + row;
+      if (q >= a.total) return;
+      const unsigned qu = (unsigned)q;
+      const unsigned n = qu / HWz, rem = qu - n * HWz;
+      const int u = (int)(rem / (unsigned)a.Wz), v = (int)(rem - (unsigned)u * (unsigned)a.Wz);
+      if (u >= a.OH || v >= a.OW) return;
+      const long long m = ((long long)n * a.OH + u) * a.OW + v;
+      const int nb = half * 32;
+      float* orow = a.out + m * 64 + nb;
+      long long rbase = 0;
+      bool use_res = false;
+      if (a.res) {
+        if (MODE == 0) {
+          rbase = (((long long)n * a.res_H + (u * a.res_stride + a.res_org)) * a.res_W + (v * a.res_stride + a.res_org)) * 64;
+          use_res = true;
+        } else {
+          const int ry = u - a.res_org, rx = v - a.res_org;
+          use_res = ry >= 0 && ry < a.res_H && rx >= 0 && rx < a.res_W;
+          rbase = (((long long)n * a.res_H + ry) * a.res_W + rx) * 64;
+        }
+      }
+#pragma unroll
+      for (int c8 = 0; c8 < 32; c8 += 8) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = acc[c8 + j];
+        if (MODE == 0 && a.bias) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += __ldg(a.bias + nb + c8 + j);
+        }
+        if (MODE == 1 && a.accumulate) {
+          const float4 o0 = *reinterpret_cast<const float4*>(orow + c8), o1 = *reinterpret_cast<const float4*>(orow + c8 + 4);
+          o[0] += o0.x; o[1] += o0.y; o[2] += o0.z; o[3] += o0.w; o[4] += o1.x; o[5] += o1.y; o[6] += o1.z; o[7] += o1.w;
+        }
+        if (use_res) {
+          const float4 r0 = __ldg(reinterpret_cast<const float4*>(a.res + rbase + nb + c8));
+          const float4 r1 = __ldg(reinterpret_cast<const float4*>(a.res + rbase + nb + c8 + 4));
+          o[0] += r0.x; o[1] += r0.y; o[2] += r0.z; o[3] += r0.w; o[4] += r1.x; o[5] += r1.y; o[6] += r1.z; o[7] += r1.w;
+        }
+        if (MODE == 0 && a.relu) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+        }
+        if (MODE == 1 && a.mask) {
+          const float4 k0 = __ldg(reinterpret_cast<const float4*>(a.mask + m * 64 + nb + c8));
+          const float4 k1 = __ldg(reinterpret_cast<const float4*>(a.mask + m * 64 + nb + c8 + 4));
+          o[0] = k0.x > 0.f ? o[0] : 0.f; o[1] = k0.y > 0.f ? o[1] : 0.f; o[2] = k0.z > 0.f ? o[2] : 0.f; o[3] = k0.w > 0.f ? o[3] : 0.f;
+          o[4] = k1.x > 0.f ? o[4] : 0.f; o[5] = k1.y > 0.f ? o[5] : 0.f; o[6] = k1.z > 0.f ? o[6] : 0.f; o[7] = k1.w > 0.f ? o[7] : 0.f;
+        }
+        ptx::st_global_256(orow + c8, __float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3]),
+                           __float_as_uint(o[4]), __float_as_uint(o[5]), __float_as_uint(o[6]), __float_as_uint(o[7]));
+      }
+    };
+
+    int tile = blockIdx.x;
+    if (my_tiles > 0) load_tile(tile);
+    for (int it = 0; it < my_tiles; ++it, tile += stride_t) {
+      if (it > 0) epilogue(tile - stride_t, it - 1);          // also: the previous tile's MMAs are done reading the smem stage
+      store_tile();
+      ptx::fence_proxy_async();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&bar_full);
+      if (it + 1 < my_tiles) load_tile(tile + stride_t);
+    }
+    if (my_tiles > 0) epilogue(tile - stride_t, my_tiles - 1);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc<512>(tmem_base);
+}
+
 // wgrad on the same tiles: dw[co][ci][r][t] += sum over positions p of x[p + roff(r, t)][ci] * dy[p][co]
 constexpr int kWgDyPlane = 128 * 128;                          // dy tile: 128 positions x 32 channels, one plane
 constexpr int kWgStage = 2 * kHaloPlane + 2 * kWgDyPlane;      // x hi | x lo | dy hi | dy lo
@@ -1130,8 +1357,9 @@ int sm_count() {
 // Fills the geometry of the halo-resident kernel; false when the layer does not fit it (caller falls back to the gather-GEMM).
 // mode 0: forward of x [N][H][W][32] -> y [N][Ho][Wo][32]; mode 1: data gradient dy [N][Ho][Wo][32] -> dx [N][H][W][32].
 bool halo_geometry(HaloArgs& a, int mode, int N, int H, int W, int Ci, int Ho, int Wo, int Co, int kh, int kw, int stride, int dil,
-                   int org) {
-  if (!halo_enabled() || stride != 1 || Ci != 32 || Co != 32 || kh != kw || kh * kw > kHaloMaxTaps) return false;
+                   int org, int C = 32) {
+  if (!halo_enabled() || stride != 1 || Ci != C || Co != C || kh != kw || kh * kw > kHaloMaxTaps) return false;
+  const int chunks = C / 32, max_rows = C == 32 ? kHaloRows : kH64Rows;
   const int k = kh, span = (k - 1) * dil;
   a.N = N; a.taps = k * k;
   if (mode == 0 || mode == 2) {
@@ -1143,7 +1371,7 @@ bool halo_geometry(HaloArgs& a, int mode, int N, int H, int W, int Ci, int Ho, i
     for (int r = 0; r < k; ++r)
       for (int t = 0; t < k; ++t) {
         a.roff[r * k + t] = (r * dil + org + a.pad) * a.Wz + (t * dil + org + a.pad);
-        a.wrow[r * k + t] = (r * k + t) * 32;
+        a.wrow[r * k + t] = (r * k + t) * chunks * C;
       }
   } else {
     a.SH = Ho; a.SW = Wo; a.OH = H; a.OW = W;
@@ -1153,7 +1381,7 @@ bool halo_geometry(HaloArgs& a, int mode, int N, int H, int W, int Ci, int Ho, i
     for (int r = 0; r < k; ++r)
       for (int t = 0; t < k; ++t) {
         a.roff[r * k + t] = ((k - 1 - r) * dil) * a.Wz + (k - 1 - t) * dil;
-        a.wrow[r * k + t] = (r * k + t) * 32;
+        a.wrow[r * k + t] = (r * k + t) * chunks * C;
       }
   }
   int mx = 0;
@@ -1168,14 +1396,15 @@ bool halo_geometry(HaloArgs& a, int mode, int N, int H, int W, int Ci, int Ho, i
     mx = a.row0[2] + 3 * dil;
   }
   a.rows = (128 + mx + 31) / 32 * 32;
-  if (a.rows > kHaloRows) return false;
+  if (a.rows > max_rows) return false;
   a.total = (long long)N * a.Hz * a.Wz;
   if (a.total >= (1ll << 31) - 512) return false;
   a.ntiles = (int)((a.total + 127) / 128);
   a.contiguous = a.pad == 0 && a.Hz == a.SH && a.Wz == a.SW;
-  int group = flush_chunks();                               // taps per main accumulator (Ci = 32: one chunk per tap)
-  if (group <= 0) group = a.taps;
-  while ((a.taps + group - 1) / group > kHaloMaxGroups) ++group;
+  int group = flush_chunks() / chunks;                      // taps per main accumulator (`chunks` 32-channel chunks per tap)
+  if (flush_chunks() <= 0) group = a.taps;
+  if (group < 1) group = 1;
+  while ((a.taps + group - 1) / group > (C == 32 ? kHaloMaxGroups : 3)) ++group;
   a.group = group;
   return true;
 }
@@ -1191,6 +1420,28 @@ int launch_halo(const HaloArgs& a, cudaStream_t stream) {
   conv_halo_tc_kernel<MODE><<<grid, kHaloThreads, kHaloSmem, stream>>>(a);
   TPZ_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <int MODE>
+int launch_halo64(const HaloArgs& a, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    TPZ_CUDA(cudaFuncSetAttribute(conv_halo64_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kH64Smem));
+    configured = true;
+  }
+  const int grid = a.ntiles < sm_count() ? a.ntiles : sm_count();
+  conv_halo64_tc_kernel<MODE><<<grid, kH64Threads, kH64Smem, stream>>>(a);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int g_halo64 = -1;
+bool halo64_enabled() {                                      // TPZ_TRAIN_HALO64=0: 64-channel layers stay on the gather-GEMM
+  if (g_halo64 < 0) {
+    const char* e = getenv("TPZ_TRAIN_HALO64");
+    g_halo64 = e ? atoi(e) : 1;
+  }
+  return g_halo64 != 0;
 }
 
 int launch_wgrad_halo(const HaloArgs& a, cudaStream_t stream) {
@@ -1232,6 +1483,15 @@ extern "C" int tpz_conv_fwd_tc(const float* x, int N, int H, int W, int Ci, cons
       int rc = weight_tmap(&h.tmB, w_fwd_packed, 2 * h.lo_rows, 32);
       if (rc) return rc;
       return launch_halo<0>(h, ST(stream));
+    }
+    memset(&h, 0, sizeof(h));
+    if (halo64_enabled() && halo_geometry(h, 0, N, H, W, Ci, Ho, Wo, Co, kh, kw, stride, dil, org, 64)) {
+      h.src = x; h.bias = bias; h.res = res; h.res_H = res_H; h.res_W = res_W; h.res_org = res_org; h.res_stride = res_stride;
+      h.out = y; h.relu = relu;
+      h.lo_rows = (long long)kh * kw * 2 * Co;
+      int rc = weight_tmap(&h.tmB, w_fwd_packed, 2 * h.lo_rows, 64);
+      if (rc) return rc;
+      return launch_halo64<0>(h, ST(stream));
     }
   }
   FwdArgs a;
@@ -1291,6 +1551,15 @@ extern "C" int tpz_conv_dgrad_tc_res(const float* dy, int N, int Ho, int Wo, int
     if (rc) return rc;
     return launch_halo<1>(h, ST(stream));
   }
+  memset(&h, 0, sizeof(h));
+  if (halo64_enabled() && halo_geometry(h, 1, N, H, W, Ci, Ho, Wo, Co, kh, kw, stride, dil, org, 64)) {
+    h.src = dy; h.mask = relu_mask; h.accumulate = accumulate; h.out = dx;
+    h.res = res; h.res_H = res_H; h.res_W = res_W; h.res_org = res_org; h.res_stride = 1;
+    h.lo_rows = (long long)kh * kw * 2 * Ci;
+    int rc = weight_tmap(&h.tmB, w_dg_packed, 2 * h.lo_rows, 64);
+    if (rc) return rc;
+    return launch_halo64<1>(h, ST(stream));
+  }
   int rc = tpz_conv_dgrad_tc(dy, N, Ho, Wo, Co, w_dg_packed, Ci, kh, kw, stride, dil, org, nullptr, accumulate, dx, H, W, stream);
   if (rc) return rc;
   rc = tpz_crop_add_f32(dx, N, H, W, Ci, res, res_H, res_W, res_org, 1, stream);
@@ -1311,6 +1580,14 @@ extern "C" int tpz_conv_dgrad_tc(const float* dy, int N, int Ho, int Wo, int Co,
       int rc = weight_tmap(&h.tmB, w_dg_packed, 2 * h.lo_rows, 32);
       if (rc) return rc;
       return launch_halo<1>(h, ST(stream));
+    }
+    memset(&h, 0, sizeof(h));
+    if (halo64_enabled() && halo_geometry(h, 1, N, H, W, Ci, Ho, Wo, Co, kh, kw, stride, dil, org, 64)) {
+      h.src = dy; h.mask = relu_mask; h.accumulate = accumulate; h.out = dx;
+      h.lo_rows = (long long)kh * kw * 2 * Ci;
+      int rc = weight_tmap(&h.tmB, w_dg_packed, 2 * h.lo_rows, 64);
+      if (rc) return rc;
+      return launch_halo64<1>(h, ST(stream));
     }
   }
   FwdArgs a;
