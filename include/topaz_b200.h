@@ -120,6 +120,11 @@ int tpz_model_create(const TpzLayerDesc* layers, int nlayers, const float* cls_w
 int tpz_model_update_weights(TpzModel* model, const TpzLayerDesc* layers, int nlayers, const float* cls_w, const float* cls_b,
                              void* stream);
 int tpz_model_destroy(TpzModel* model);
+/* Optional timing of the last conv step + fused classifier (the dominant kernel of a dense forward; bench.py's roofline figure):
+ * tpz_model_timing(m, 1) records a CUDA event pair around it at every forward (ring of 64), tpz_model_timing_read returns the
+ * recorded durations in ms (oldest first) and resets, tpz_model_timing(m, 0) stops. */
+int tpz_model_timing(TpzModel* m, int enable);
+int tpz_model_timing_read(TpzModel* m, float* ms, int capacity, int* count);
 /* Bytes of DEVICE workspace (256-byte aligned) tpz_resnet_dense_forward needs for a batch of B images H x W; -1 if the
  * image is smaller than the receptive field allows. */
 long long tpz_workspace_bytes(const TpzModel* model, int B, int H, int W);
@@ -260,6 +265,12 @@ int tpz_first_fwd_f32(const float* x, int N, int H, int W, const float* w, const
                       int relu, float* y, int Ho, int Wo, void* stream);
 int tpz_first_wgrad_f32(const float* x, int N, int H, int W, const float* dy, int Ho, int Wo, int Co, int k, int stride,
                         float* dw, void* stream);
+/* The same first layer on the tensor core (3xTF32, im2col tile built in shared memory; 7 x 7, Co = 32 only).  Return -1 without
+ * launching when the shape is not covered: the caller falls back to the fp32 kernels above. */
+int tpz_first_fwd_tc(const float* x, int N, int H, int W, const float* w, const float* bias, int Co, int k, int stride, int relu,
+                     float* y, int Ho, int Wo, void* stream);
+int tpz_first_wgrad_tc(const float* x, int N, int H, int W, const float* dy, int Ho, int Wo, int Co, int k, int stride, float* dw,
+                       void* stream);
 int tpz_bias_grad_f32(const float* dy, long long P, int C, float* db, void* stream);   /* db[c] += sum_p dy[p][c] */
 /* Classifier head in training (classifier.py:29,65: 1x1 conv C -> 1 on M pixels, x [M][C] fp32):
  *  tpz_cls_fwd_f32: y[m] = sum_c x[m][c]*w[c] + bias[0]

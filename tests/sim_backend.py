@@ -283,14 +283,18 @@ def to_device(t):
 def patched():
     names = ['tc_conv', 'range_scale', 'conv_first', 'conv_first_tc', 'im2col_first', 'im2col3d_first', 'filter_f32', 'conv_last', 'maxpool2', 'upsample_nearest', 'meanstd', 'affine',
              'gemm_f32', 'gmm_sums', 'select_hist', 'to_device']
+    from topaz_b200 import engine
     saved = {n: getattr(ops, n) for n in names}
     saved['require_cuda'] = ops.require_cuda
+    dense_engine = engine.DENSE_ENGINE
     try:
         for n in names:
             setattr(ops, n, globals()[n])
         ops.require_cuda = lambda t, what: None
+        engine.DENSE_ENGINE = 'py'      # the simulation replaces the layer-level wrappers; the model-level C ABI needs the GPU
         yield
     finally:
+        engine.DENSE_ENGINE = dense_engine
         for n, f in saved.items():
             setattr(ops, n, f)
 

@@ -54,6 +54,8 @@ _PROTOS = {
     'tpz_model_create': (_I, [C.POINTER(TpzLayerDesc), _I, _P, _P, _I, C.POINTER(C.c_void_p), _P]),
     'tpz_model_update_weights': (_I, [_P, C.POINTER(TpzLayerDesc), _I, _P, _P, _P]),
     'tpz_model_destroy': (_I, [_P]),
+    'tpz_model_timing': (_I, [_P, _I]),
+    'tpz_model_timing_read': (_I, [_P, _P, _I, _P]),
     'tpz_model_step_buffers': (_I, [_P, _I, _P, _LL, _P, C.POINTER(_LL), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), _P]),
     'tpz_model_step_args': (_I, [_P, _I, C.POINTER(TpzTcConvArgs)]),
     'tpz_workspace_bytes': (_LL, [_P, _I, _I, _I]),
@@ -96,6 +98,8 @@ _PROTOS = {
     'tpz_conv_wgrad_tc_bias': (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     'tpz_first_fwd_f32': (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P, _I, _I, _P]),
     'tpz_first_wgrad_f32': (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P]),
+    'tpz_first_fwd_tc': (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P, _I, _I, _P]),
+    'tpz_first_wgrad_tc': (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P]),
     'tpz_bias_grad_f32': (_I, [_P, _LL, _I, _P, _P]),
     'tpz_cls_fwd_f32': (_I, [_P, _LL, _I, _P, _P, _P, _P]),
     'tpz_cls_bwd_f32': (_I, [_P, _LL, _I, _P, _P, _I, _P, _P, _P, _P]),

@@ -98,7 +98,12 @@ struct TpzModel {
   float* dot_w = nullptr;        // [C_last_store]
   float* scratch = nullptr;      // BN affine a | sh (2 x 256 floats)
   int c_last = 0;
+  // optional per-launch timing of the LAST conv step (the dominant kernel of a dense forward): a ring of CUDA event pairs recorded
+  // on the launch stream, read back by tpz_model_timing_read (bench.py's roofline figure)
+  std::vector<cudaEvent_t> ev;   // 2 x kTimingRing when enabled
+  long long timed = 0;
 };
+constexpr int kTimingRing = 64;
 
 namespace {
 
@@ -108,6 +113,7 @@ int free_model(TpzModel* m) {
   if (!m) return 0;
   cudaFree(m->first_w16); cudaFree(m->first_w32); cudaFree(m->first_b); cudaFree(m->dot_w); cudaFree(m->scratch);
   for (auto& s : m->steps) { cudaFree(s.weights); cudaFree(s.bias); }
+  for (cudaEvent_t e : m->ev) cudaEventDestroy(e);
   delete m;
   return 0;
 }
@@ -345,8 +351,11 @@ extern "C" int tpz_resnet_dense_forward(TpzModel* m, const float* x, int B, int 
     while (nxt == cur || nxt == saved) ++nxt;
     if (s.dot) { a.out = nullptr; a.dot_out = y; }
     else { a.out = slot[nxt]; a.out_ld = s.co_store; a.out_coff = 0; a.dot_out = nullptr; }
+    const bool timed = s.dot && !m->ev.empty();
+    if (timed) cudaEventRecord(m->ev[2 * (m->timed % kTimingRing)], ST(stream));
     rc = tpz_tc_conv(&a, stream);
     if (rc) return rc;
+    if (timed) { cudaEventRecord(m->ev[2 * (m->timed % kTimingRing) + 1], ST(stream)); ++m->timed; }
     if (!s.dot) { cur = nxt; c_cur = s.co_store; }
     if (s.two_src) saved = -1;
     h = ho; w = wo;
@@ -385,5 +394,36 @@ extern "C" int tpz_model_step_buffers(const TpzModel* m, int step, void* weights
 extern "C" int tpz_model_step_args(const TpzModel* m, int step, TpzTcConvArgs* out) {
   TPZ_CHECK(m && out && step >= 0 && step < (int)m->steps.size(), "tpz_model_step_args: bad step %d", step);
   *out = m->steps[step].args;
+  return 0;
+}
+
+// Timing of the last conv step (+ fused classifier): enable != 0 starts recording an event pair around it at every forward (ring of
+// 64), 0 stops and frees the events.  tpz_model_timing_read synchronises on the recorded pairs and returns their durations in ms
+// (oldest first, at most `capacity`), then resets the counter.
+extern "C" int tpz_model_timing(TpzModel* m, int enable) {
+  TPZ_CHECK(m, "tpz_model_timing: null model");
+  for (cudaEvent_t e : m->ev) cudaEventDestroy(e);
+  m->ev.clear();
+  m->timed = 0;
+  if (enable) {
+    m->ev.resize(2 * kTimingRing);
+    for (auto& e : m->ev) TPZ_CUDA(cudaEventCreate(&e));
+  }
+  return 0;
+}
+
+extern "C" int tpz_model_timing_read(TpzModel* m, float* ms, int capacity, int* count) {
+  TPZ_CHECK(m && ms && count, "tpz_model_timing_read: bad arguments");
+  const long long n = m->timed < kTimingRing ? m->timed : kTimingRing;
+  const long long first = m->timed - n;
+  int out = 0;
+  for (long long i = first; i < m->timed && out < capacity; ++i) {
+    const int slot = (int)(i % kTimingRing);
+    TPZ_CUDA(cudaEventSynchronize(m->ev[2 * slot + 1]));
+    TPZ_CUDA(cudaEventElapsedTime(&ms[out], m->ev[2 * slot], m->ev[2 * slot + 1]));
+    ++out;
+  }
+  *count = out;
+  m->timed = 0;
   return 0;
 }

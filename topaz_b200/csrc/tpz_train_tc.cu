@@ -1253,6 +1253,220 @@ __global__ void __launch_bounds__(kHaloThreads, 1) wgrad_halo_tc_kernel(const __
   if (warp == 0) ptx::tmem_dealloc<512>(tmem_base);
 }
 
+// -------------------------------------------------------------------------------------------------
+// Cin = 1 first layer (7 x 7, stride 2 on the training crops; resnet.py:294, basic.py:47) on the tensor core.
+// The im2col row of an output pixel (49 taps, padded to 64 = two 32-tap chunks) is built directly in shared memory, split hi / lo,
+// in the operand layout the MMA wants -- K-major SWIZZLE_128B for the forward (M = pixels), MN-major SWIZZLE_128B_BASE32B for the
+// weight gradient (K = pixels).  Tiles are 128 consecutive output pixels, so y / dy rows are contiguous.  Same pipeline as the
+// halo kernels: warps 0-7 stage and drain, warp 8 issues, two smem and two TMEM stages.
+//   forward: per 32-tap chunk and K = 8 step  x_hi x [w_hi ; w_lo] (N = 64 -> [main | small]) and x_lo x w_hi (N = 32 -> small);
+//            14 MMAs per tile (the last K step of chunk 1 is all padding).
+//   wgrad:   ONE MMA per 8 pixels: the four MN atoms of A are [col_hi c0 | col_hi c1 | col_lo c0 | col_lo c1] (M = 128) and
+//            B = [dy_hi | dy_lo] (N = 64), so lanes 0-63 hold col_hi x dy_hi | col_hi x dy_lo and lanes 64-127 hold col_lo x dy_hi
+//            (| col_lo x dy_lo, dropped): all three terms of the compensated product from one instruction.
+// -------------------------------------------------------------------------------------------------
+struct FirstArgs {
+  const float* x; int N, H, W;          // [N][H][W], one channel
+  int stride, Ho, Wo;
+  const float* w; const float* bias; int relu; float* y;      // forward: w [32][49] (OIHW, Ci = 1)
+  const float* dy; float* dw;                                   // wgrad
+  long long M; int ntiles;
+};
+constexpr int kFirstK = 7, kFirstTaps = 49;
+constexpr int kFirstPlane = 128 * 128;                          // 128 pixels x 32 taps
+constexpr int kFirstFwdSmem = 16384 + 2 * 4 * kFirstPlane + 1024;
+constexpr int kFirstWgSmem = 2 * 6 * kFirstPlane + 1024;
+
+// the 32 taps of chunk C of one output pixel (taps beyond 49: zero)
+template <int C>
+__device__ __forceinline__ void first_load_taps(const float* __restrict__ xb, int W, bool ok, float (&v)[32]) {
+#pragma unroll
+  for (int e = 0; e < 32; ++e) {
+    constexpr int dummy = 0; (void)dummy;
+    const int tap = C * 32 + e;
+    v[e] = (ok && tap < kFirstTaps) ? __ldg(xb + (tap / kFirstK) * W + (tap % kFirstK)) : 0.f;
+  }
+}
+
+template <int WGRAD>
+__global__ void __launch_bounds__(kHaloThreads, 1) first_tc_train_kernel(const __grid_constant__ FirstArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // forward: [weights 16 KB: c0 hi | c0 lo | c1 hi | c1 lo (32 rows x 128 B each)] [stage: c0 hi | c0 lo | c1 hi | c1 lo] x 2
+  // wgrad:   [stage: col_hi c0 | col_hi c1 | col_lo c0 | col_lo c1 | dy_hi | dy_lo] x 2
+  unsigned char* const wsm = base;
+  unsigned char* const stages = WGRAD ? base : base + 16384;
+  constexpr int STAGE = WGRAD ? 6 * kFirstPlane : 4 * kFirstPlane;
+  __shared__ __align__(8) uint64_t bar_full[2], bar_mma[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&bar_full[s], kHaloWorkers); ptx::mbar_init(&bar_mma[s], 1); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) ptx::tmem_alloc<128>(&tmem_base_s);
+  if (!WGRAD) {                                               // weights -> K-major B operand, split hi / lo
+    for (int i = tid; i < 32 * 64; i += kHaloThreads) {
+      const int co = i >> 6, tap = i & 63;
+      float hi = 0.f, lo = 0.f;
+      if (tap < kFirstTaps) split1(__ldg(a.w + co * kFirstTaps + tap), hi, lo);
+      const int off = (tap >> 5) * 8192 + co * 128 + (((((tap & 31) >> 2) ^ (co & 7)) << 4) | ((tap & 3) << 2));
+      *reinterpret_cast<float*>(wsm + off) = hi;
+      *reinterpret_cast<float*>(wsm + 4096 + off) = lo;
+    }
+    ptx::fence_proxy_async();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int stride_t = gridDim.x;
+
+  if (warp == 8) {
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += stride_t, ++it) {
+      const int s = it & 1;
+      mbar_wait(&bar_full[s], (uint32_t)(it >> 1) & 1u);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t sa = ptx::smem_u32(stages + (size_t)s * STAGE);
+        const uint32_t d = tmem_base + (uint32_t)s * 64u;
+        if (WGRAD) {
+          constexpr uint32_t IDESC = idesc_tf32(128, 64) | (1u << 15) | (1u << 16);
+          const uint32_t d_hi = ptx::umma_desc_hi(512u, 1);
+#pragma unroll 4
+          for (int ks = 0; ks < 16; ++ks)
+            umma_tf32(d, desc_lo_mn(sa + (uint32_t)ks * 1024u, kFirstPlane), d_hi, desc_lo_mn(sa + 4u * kFirstPlane + (uint32_t)ks * 1024u, kFirstPlane),
+                      d_hi, IDESC, ks ? 1u : 0u);
+        } else {
+          constexpr uint32_t IDESC64 = idesc_tf32(128, 64), IDESC32 = idesc_tf32(128, 32);
+          const uint32_t d_hi = ptx::umma_desc_hi(1024, 2);
+          const uint32_t wb = ptx::smem_u32(wsm);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const uint32_t ah = ((sa + (uint32_t)c * 2u * kFirstPlane) & 0x3FFFF) >> 4, al = ah + (kFirstPlane >> 4);
+            const uint32_t bw = ((wb + (uint32_t)c * 8192u) & 0x3FFFF) >> 4;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (c == 1 && k == 3) continue;                 // taps 56..63: padding
+              umma_tf32(d, ah + 2 * k, d_hi, bw + 2 * k, d_hi, IDESC64, (c | k) ? 1u : 0u);
+              umma_tf32(d + 32u, al + 2 * k, d_hi, bw + 2 * k, d_hi, IDESC32, 1u);
+            }
+          }
+        }
+        ptx::umma_commit(&bar_mma[s]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // im2col: thread (row, c) builds the 32 taps of chunk c of pixel `row`
+    const int row = tid & 127, c = tid >> 7;
+    float col[32];
+    float4 prey[4];
+    const int pcy = tid & 7, jry = tid >> 3;                  // dy staging (wgrad): 16-byte piece pcy of rows jry + 32 i
+    auto load_tile = [&](int tile) {
+      const long long m = (long long)tile * 128 + row;
+      const bool ok = m < a.M;
+      const long long mm = ok ? m : 0;
+      const int ox = (int)(mm % a.Wo); const long long q = mm / a.Wo; const int oy = (int)(q % a.Ho); const int n = (int)(q / a.Ho);
+      const float* xb = a.x + ((long long)n * a.H + oy * a.stride) * a.W + ox * a.stride;
+      if (c == 0) first_load_taps<0>(xb, a.W, ok, col); else first_load_taps<1>(xb, a.W, ok, col);
+      if (WGRAD) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const long long p = (long long)tile * 128 + jry + 32 * i;
+          prey[i] = p < a.M ? __ldg(reinterpret_cast<const float4*>(a.dy) + p * 8 + pcy) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    };
+    auto store_tile = [&](unsigned char* stage) {
+      // forward: planes c0 hi, c0 lo, c1 hi, c1 lo (16-byte piece q at q ^ (row & 7)); wgrad: hi c0, hi c1, lo c0, lo c1 (32-byte piece
+      // q >> 1 at (q >> 1) ^ (row & 3))
+      unsigned char* ph = stage + (size_t)(WGRAD ? c : 2 * c) * kFirstPlane + row * 128;
+      unsigned char* pl = ph + (size_t)(WGRAD ? 2 : 1) * kFirstPlane;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float4 v = make_float4(col[4 * q], col[4 * q + 1], col[4 * q + 2], col[4 * q + 3]), hi, lo;
+        split4(v, hi, lo);
+        const int piece = WGRAD ? (q ^ ((row & 3) << 1)) : (q ^ (row & 7));
+        *reinterpret_cast<float4*>(ph + (piece << 4)) = hi;
+        *reinterpret_cast<float4*>(pl + (piece << 4)) = lo;
+      }
+      if (WGRAD) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int j = jry + 32 * i;
+          float4 hi, lo;
+          split4(prey[i], hi, lo);
+          const int off = j * 128 + ((pcy ^ ((j & 3) << 1)) << 4);
+          *reinterpret_cast<float4*>(stage + 4 * kFirstPlane + off) = hi;
+          *reinterpret_cast<float4*>(stage + 5 * kFirstPlane + off) = lo;
+        }
+      }
+    };
+    const int erow = 32 * (warp & 3) + lane, half = warp >> 2;
+    float tot[32];                                            // wgrad: running sums of this thread's 32 accumulator columns
+#pragma unroll
+    for (int j = 0; j < 32; ++j) tot[j] = 0.f;
+    auto finish = [&](int tile, int s, int it) {
+      mbar_wait(&bar_mma[s], (uint32_t)(it >> 1) & 1u);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)s * 64u;
+      if (WGRAD) {
+        uint32_t r[32];
+        ptx::tmem_ld32(taddr + (uint32_t)half * 32u, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) tot[j] += __uint_as_float(r[j]);
+        ptx::tc_fence_before();
+      } else {
+        uint32_t rm[16], rs[16];
+        ptx::tmem_ld16(taddr + 32u + (uint32_t)half * 16u, rs);
+        ptx::tmem_ld16(taddr + (uint32_t)half * 16u, rm);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        const long long m = (long long)tile * 128 + erow;
+        if (m >= a.M) return;
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          o[j] = __uint_as_float(rs[j]) + __uint_as_float(rm[j]) + (a.bias ? __ldg(a.bias + half * 16 + j) : 0.f);
+          if (a.relu) o[j] = fmaxf(o[j], 0.f);
+        }
+        float* orow = a.y + m * 32 + half * 16;
+        ptx::st_global_256(orow, __float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3]),
+                           __float_as_uint(o[4]), __float_as_uint(o[5]), __float_as_uint(o[6]), __float_as_uint(o[7]));
+        ptx::st_global_256(orow + 8, __float_as_uint(o[8]), __float_as_uint(o[9]), __float_as_uint(o[10]), __float_as_uint(o[11]),
+                           __float_as_uint(o[12]), __float_as_uint(o[13]), __float_as_uint(o[14]), __float_as_uint(o[15]));
+      }
+    };
+    int it = 0, tile = blockIdx.x;
+    if (tile < a.ntiles) load_tile(tile);
+    for (; tile < a.ntiles; tile += stride_t, ++it) {
+      const int s = it & 1;
+      store_tile(stages + (size_t)s * STAGE);
+      ptx::fence_proxy_async();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&bar_full[s]);
+      if (tile + stride_t < a.ntiles) load_tile(tile + stride_t);
+      if (it > 0) finish(tile - stride_t, s ^ 1, it - 1);
+    }
+    if (it > 0) finish(tile - stride_t, (it - 1) & 1, it - 1);
+    if (WGRAD && it > 0) {
+      // lanes 0-63: tap = lane, columns [col_hi x dy_hi | col_hi x dy_lo]; lanes 64-127: tap = lane - 64, [col_lo x dy_hi | dropped]
+      const int tap = erow & 63;
+      if (tap < kFirstTaps && !(erow >= 64 && half == 1)) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(a.dw + j * kFirstTaps + tap, tot[j]);
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc<128>(tmem_base);
+}
+
 int g_flush = -1;
 int flush_chunks() {
   if (g_flush < 0) {
@@ -1656,8 +1870,9 @@ extern "C" int tpz_conv_wgrad_tc(const float* x, int N, int H, int W, int Ci, co
   const long long P = (long long)N * Ho * Wo;
   const int BN = Co % 64 == 0 ? 64 : 32;
   const int mt = tpz_div_up((long long)kh * kw * Ci, 128), nt = Co / BN;
-  // split the pixels so that ~2 waves of 2 CTAs per SM are in flight, at least 8 chunks of 32 pixels per split
-  int splits = (148 * 4) / (mt * nt);
+  // split the pixels so that ONE wave of 2 CTAs per SM covers the layer (a second wave costs a whole CTA lifetime -- TMEM allocation,
+  // first-load latency, 8192 atomics -- on these latency-bound launches), at least 8 chunks of 32 pixels per split
+  int splits = (sm_count() * 2) / (mt * nt);
   if (splits < 1) splits = 1;
   long long kps = (P + splits - 1) / splits;
   kps = (kps + 31) / 32 * 32;
@@ -1676,6 +1891,52 @@ extern "C" int tpz_conv_wgrad_tc(const float* x, int N, int H, int W, int Ci, co
     if (!configured) { TPZ_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); configured = true; }
     wgrad_tc_kernel<32><<<grid, 256, smem, ST(stream)>>>(a);
   }
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Cin = 1, Co = 32, 7 x 7 first layer on the tensor core (see first_tc_train_kernel); returns -1 when the geometry is not covered
+// (the caller then uses the CUDA-core kernels of tpz_train.cu).
+static int g_first_tc = -1;
+static bool first_tc_enabled() {                              // TPZ_TRAIN_FIRST_TC=0: CUDA-core first layer
+  if (g_first_tc < 0) {
+    const char* e = getenv("TPZ_TRAIN_FIRST_TC");
+    g_first_tc = e ? atoi(e) : 1;
+  }
+  return g_first_tc != 0;
+}
+extern "C" int tpz_first_fwd_tc(const float* x, int N, int H, int W, const float* w, const float* bias, int Co, int k, int stride,
+                                int relu, float* y, int Ho, int Wo, void* stream) {
+  if (!first_tc_enabled() || Co != 32 || k != kFirstK || (Ho - 1) * stride + k > H || (Wo - 1) * stride + k > W) return -1;
+  FirstArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = x; a.N = N; a.H = H; a.W = W; a.stride = stride; a.Ho = Ho; a.Wo = Wo; a.w = w; a.bias = bias; a.relu = relu; a.y = y;
+  a.M = (long long)N * Ho * Wo; a.ntiles = tpz_div_up(a.M, 128);
+  static bool configured = false;
+  if (!configured) {
+    TPZ_CUDA(cudaFuncSetAttribute(first_tc_train_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFirstFwdSmem));
+    configured = true;
+  }
+  const int grid = a.ntiles < sm_count() ? a.ntiles : sm_count();
+  first_tc_train_kernel<0><<<grid, kHaloThreads, kFirstFwdSmem, ST(stream)>>>(a);
+  TPZ_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tpz_first_wgrad_tc(const float* x, int N, int H, int W, const float* dy, int Ho, int Wo, int Co, int k, int stride,
+                                  float* dw, void* stream) {
+  if (!first_tc_enabled() || Co != 32 || k != kFirstK || (Ho - 1) * stride + k > H || (Wo - 1) * stride + k > W) return -1;
+  FirstArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = x; a.N = N; a.H = H; a.W = W; a.stride = stride; a.Ho = Ho; a.Wo = Wo; a.dy = dy; a.dw = dw;
+  a.M = (long long)N * Ho * Wo; a.ntiles = tpz_div_up(a.M, 128);
+  static bool configured = false;
+  if (!configured) {
+    TPZ_CUDA(cudaFuncSetAttribute(first_tc_train_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFirstWgSmem));
+    configured = true;
+  }
+  const int grid = a.ntiles < sm_count() ? a.ntiles : sm_count();
+  first_tc_train_kernel<1><<<grid, kHaloThreads, kFirstWgSmem, ST(stream)>>>(a);
   TPZ_CUDA(cudaGetLastError());
   return 0;
 }

@@ -47,7 +47,7 @@ PRECISION = os.environ.get('TPZ_PRECISION', 'strict' if os.environ.get('TPZ_STRI
 RANGE_GUARD = os.environ.get('TPZ_RANGE_GUARD', '1') != '0'
 # Dense classifier forward through the model-level C ABI (csrc/tpz_model.cu: plans + on-device weight repack in C++);
 # 'py' keeps the Python-built plans (same kernels, same packed bytes).  Strict precision always uses the Python plans.
-DENSE_ENGINE = os.environ.get('TPZ_DENSE_ENGINE', 'py')
+DENSE_ENGINE = os.environ.get('TPZ_DENSE_ENGINE', 'c')
 
 
 def _rup(c: int, m: int = 32) -> int:

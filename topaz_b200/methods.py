@@ -124,14 +124,15 @@ class _Objective:
                      (getattr(self, k, None) for k in ('pi', 'slack', 'momentum', 'beta')))
 
     def _graph_ok(self, X):
-        """CUDA-graph replay of the step: on by default for single-process training (TPZ_TRAIN_GRAPH=0 disables; =dp also
-        captures the NCCL collectives of data-parallel steps).  Not with active dropout (its Philox offset advances on the
-        host) nor with an objective whose loss arguments change from step to step (GE_KL with momentum < 1)."""
+        """CUDA-graph replay of the step: on by default, data-parallel steps included -- the NCCL all-gather and the bucketed
+        gradient all-reduces are captured with the kernels (TPZ_TRAIN_GRAPH=0 disables; =nodp keeps data-parallel steps
+        eager).  Not with active dropout (its Philox offset advances on the host) nor with an objective whose loss arguments
+        change from step to step (GE_KL with momentum < 1)."""
         import os
         mode = os.environ.get('TPZ_TRAIN_GRAPH', '1')
         if mode == '0' or not X.is_cuda:
             return False
-        if _dist() is not None and mode != 'dp':
+        if _dist() is not None and (mode == 'nodp' or _dist().get_backend() != 'nccl'):
             return False
         if getattr(self, 'momentum', 1.0) < 1:
             return False

@@ -81,6 +81,8 @@ class DenseModel:
                 raise NotImplementedError(f"topaz_b200: layer kind {b['kind']} in the dense C model")
         cw, cb = _f32(cls.weight).reshape(-1), _f32(cls.bias).reshape(-1)
         keep += [cw, cb]
+        # kernels per forward: input range scale + first layer + one per conv step (a ResidA block is two)
+        self.n_launch = 2 + sum(2 if b['kind'] == 'resid' else 1 for b in blocks[1:])
         return descs, keep, cw, cb
 
     def _build(self, create: bool):
@@ -109,7 +111,7 @@ class DenseModel:
         y = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
         check(lib.tpz_resnet_dense_forward(self.handle, _ptr(x), B, H, W, _ptr(y), _ptr(self._ws), need,
                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
-        ops._count(3 + len(list(self.model.features.features.children())) * 2)
+        ops._count(self.n_launch)
         return y
 
     def step_buffers(self, step: int):
@@ -124,6 +126,17 @@ class DenseModel:
         bt = torch.empty(int(co.value), dtype=torch.float32, device=dev)
         check(fn(self.handle, step, _ptr(wt), int(n.value), _ptr(bt), None, None, None, None, s))
         return (wt.view(int(nkb.value), int(co.value), int(kc.value)) if wt is not None else None), bt
+
+    def timing(self, enable: bool):
+        """record CUDA events around the last conv step (+ fused classifier) of every forward"""
+        check(_lib.lib().tpz_model_timing(self.handle, int(enable)))
+
+    def timing_read(self):
+        """durations (ms) of the last conv step of the forwards since the previous read (at most 64), oldest first"""
+        buf = (C.c_float * 64)()
+        n = C.c_int()
+        check(_lib.lib().tpz_model_timing_read(self.handle, buf, 64, C.byref(n)))
+        return [float(buf[i]) for i in range(n.value)]
 
     def close(self):
         if self.handle:

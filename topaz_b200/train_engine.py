@@ -188,7 +188,11 @@ def _conv_fwd(x, w, b, stride, dil, org, Ho, Wo, relu, res=None, res_org=0, res_
     y = torch.empty((N, Ho, Wo, Co), dtype=torch.float32, device=x.device)
     ops._count(1)
     if USE_MMA and Ci == 1 and Co in (32, 64) and org == 0 and dil == 1 and res is None and kh == kw:
-        check(_lib.lib().tpz_first_fwd_f32(_p(x), N, H, W, _p(w), _p(b), Co, kh, stride, int(relu), _p(y), Ho, Wo, _s()))
+        # 7 x 7 / 32 channels: im2col tile built in shared memory + tcgen05 (returns -1 for other shapes -> CUDA-core kernel)
+        rc = _lib.lib().tpz_first_fwd_tc(_p(x), N, H, W, _p(w), _p(b), Co, kh, stride, int(relu), _p(y), Ho, Wo, _s()) if USE_TC else -1
+        if rc == -1:
+            rc = _lib.lib().tpz_first_fwd_f32(_p(x), N, H, W, _p(w), _p(b), Co, kh, stride, int(relu), _p(y), Ho, Wo, _s())
+        check(rc)
         return y
     if USE_MMA and Co == 1 and kh == 1 and kw == 1 and stride == 1 and org == 0 and res is None and not relu and Ci % 4 == 0:
         check(_lib.lib().tpz_cls_fwd_f32(_p(x), N * H * W, Ci, _p(w), _p(b), _p(y), _s()))       # classifier head: one warp per pixel
@@ -249,7 +253,10 @@ def _conv_wgrad(x, dy, w_grad, b_grad, stride, dil, org):
     kh, kw = w_grad.shape[2], w_grad.shape[3]
     ops._count(2 if b_grad is not None else 1)
     if USE_MMA and Ci == 1 and Co in (32, 64) and org == 0 and dil == 1 and kh == kw and kh * kw <= (256 // Co) * 16:
-        check(_lib.lib().tpz_first_wgrad_f32(_p(x), N, H, W, _p(dy), Ho, Wo, Co, kh, stride, _p(w_grad), _s()))
+        rc = _lib.lib().tpz_first_wgrad_tc(_p(x), N, H, W, _p(dy), Ho, Wo, Co, kh, stride, _p(w_grad), _s()) if USE_TC else -1
+        if rc == -1:
+            rc = _lib.lib().tpz_first_wgrad_f32(_p(x), N, H, W, _p(dy), Ho, Wo, Co, kh, stride, _p(w_grad), _s())
+        check(rc)
         if b_grad is not None:
             check(_lib.lib().tpz_bias_grad_f32(_p(dy), N * Ho * Wo, Co, _p(b_grad), _s()))
         return
