@@ -119,6 +119,10 @@ int tpz_model_create(const TpzLayerDesc* layers, int nlayers, const float* cls_w
 /* Same architecture, new parameter values (and possibly new pointers): repack on the device (after optimizer steps). */
 int tpz_model_update_weights(TpzModel* model, const TpzLayerDesc* layers, int nlayers, const float* cls_w, const float* cls_b,
                              void* stream);
+/* tpz_model_create / tpz_model_update_weights return TPZ_E_WEIGHT_RANGE when a (BatchNorm-folded) weight row cannot be held in fp16
+ * (max|w| > 2^14 or below 2^-10): such rows need the row-scaled plans (TpzTcConvArgs.oscale), which only the layer-granular path
+ * builds.  Non-finite weights return 3.  The handle must not be used for forward after either. */
+#define TPZ_E_WEIGHT_RANGE 4
 int tpz_model_destroy(TpzModel* model);
 /* Optional timing of the last conv step + fused classifier (the dominant kernel of a dense forward; bench.py's roofline figure):
  * tpz_model_timing(m, 1) records a CUDA event pair around it at every forward (ring of 64), tpz_model_timing_read returns the
@@ -270,7 +274,7 @@ int tpz_first_wgrad_f32(const float* x, int N, int H, int W, const float* dy, in
 int tpz_first_fwd_tc(const float* x, int N, int H, int W, const float* w, const float* bias, int Co, int k, int stride, int relu,
                      float* y, int Ho, int Wo, void* stream);
 int tpz_first_wgrad_tc(const float* x, int N, int H, int W, const float* dy, int Ho, int Wo, int Co, int k, int stride, float* dw,
-                       void* stream);
+                       float* db /* bias gradient += column sums of dy; may be NULL */, void* stream);
 int tpz_bias_grad_f32(const float* dy, long long P, int C, float* db, void* stream);   /* db[c] += sum_p dy[p][c] */
 /* Classifier head in training (classifier.py:29,65: 1x1 conv C -> 1 on M pixels, x [M][C] fp32):
  *  tpz_cls_fwd_f32: y[m] = sum_c x[m][c]*w[c] + bias[0]

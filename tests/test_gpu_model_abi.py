@@ -185,3 +185,29 @@ def test_c_model_packs_the_same_bytes_as_the_python_packer(name, arch, units, sc
             assert (a.C, tuple(a.org), a.kw, a.kh, a.lat, a.no_phase, a.lat_z) == (b.C, tuple(b.org), b.kw, b.kh, b.lat, b.no_phase, b.lat_z), (i, sidx)
     dm.close()
     assert worst_w == 0.0 and worst_b == 0.0, (worst_w, worst_b)
+
+
+def test_c_model_declines_rows_outside_the_fp16_range():
+    """A BatchNorm-folded weight row below 2^-10 (tiny gamma) or beyond 2^14 needs the per-row scale of the Python packer
+    (ops._row_scales): the C packer reports it (TPZ_E_WEIGHT_RANGE), the engine falls back to the Python plans for that parameter
+    state, and the scores stay right."""
+    from topaz_b200 import engine
+    g = gold('cls_resnet8_u16_bn')
+    sd = seeded_state(classifier_shapes('resnet8', 16, 1, True), int(g['seed']))
+    sd['features.features.1.bn0.weight'] = sd['features.features.1.bn0.weight'] * np.float32(1e-6)
+    m = _load(_classifier('resnet8', 16, 1, True), sd).cuda(); m.eval(); m.fill()
+    x = torch.from_numpy(g['xd']).cuda()
+    old = engine.DENSE_ENGINE
+    try:
+        engine.DENSE_ENGINE = 'c'
+        with torch.no_grad():
+            y_c = m(x).cpu()
+        assert m.__dict__['_tpz_plans']['dense_c'][2] is None          # declined, remembered
+        engine.DENSE_ENGINE = 'py'
+        with torch.no_grad():
+            y_py = m(x).cpu()
+    finally:
+        engine.DENSE_ENGINE = old
+    assert torch.isfinite(y_c).all() and torch.equal(y_c, y_py)
+    ref = O.classifier_forward(sd, g['xd'], 'resnet8', 16, filled=True, bn=True).numpy()
+    check_parity(y_c.numpy(), ref, 3e-3, 'BN gamma x1e-6 (row-scaled plans)')

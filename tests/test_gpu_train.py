@@ -260,8 +260,9 @@ def test_first_layer_tc_kernels_match_fp32(N, H, stride):
     dyd = _nhwc(dy).cuda()
     ext = (Ho - 1) * stride + 7
     gw = torch.nn.grad.conv2d_weight(x[:, :, :ext, :ext].contiguous(), tuple(w.shape), dy, stride=stride)
-    dw = torch.full((32, 1, 7, 7), 0.25, device='cuda')
-    assert L.tpz_first_wgrad_tc(P(xd), N, H, H, P(dyd), Ho, Ho, 32, 7, stride, P(dw), None) == 0
+    dw = torch.full((32, 1, 7, 7), 0.25, device='cuda'); db = torch.full((32,), 0.5, device='cuda')
+    assert L.tpz_first_wgrad_tc(P(xd), N, H, H, P(dyd), Ho, Ho, 32, 7, stride, P(dw), P(db), None) == 0
+    assert max(rel_err(db.cpu(), 0.5 + dy.sum((0, 2, 3)))) < 2e-5
     e = max(rel_err(dw.cpu() - 0.25, gw))
     print('first_wgrad_tc rel err', e)
     assert e < 5e-5

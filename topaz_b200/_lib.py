@@ -99,7 +99,7 @@ _PROTOS = {
     'tpz_first_fwd_f32': (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P, _I, _I, _P]),
     'tpz_first_wgrad_f32': (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P]),
     'tpz_first_fwd_tc': (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P, _I, _I, _P]),
-    'tpz_first_wgrad_tc': (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P]),
+    'tpz_first_wgrad_tc': (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
     'tpz_bias_grad_f32': (_I, [_P, _LL, _I, _P, _P]),
     'tpz_cls_fwd_f32': (_I, [_P, _LL, _I, _P, _P, _P, _P]),
     'tpz_cls_bwd_f32': (_I, [_P, _LL, _I, _P, _P, _I, _P, _P, _P, _P]),

@@ -38,7 +38,7 @@ __global__ void bias_fold_kernel(const float* __restrict__ b, const float* __res
 // k-blocks of one conv source: out[kb0 + tap*nchunks + chunk][co][j] = fp16(w[co][chunk*KC + j][tap] * a[co]), zero in the
 // channel padding.  identity = 1: the source is an identity skip (w = I, one tap).
 __global__ void pack_blocks_kernel(const float* __restrict__ w, const float* __restrict__ a, int Co, int Ci, int taps, int nchunks,
-                                   int KC, int CoStore, int identity, __half* __restrict__ out) {
+                                   int KC, int CoStore, int identity, __half* __restrict__ out, int* __restrict__ rowmax) {
   const long long total = (long long)taps * nchunks * CoStore * KC;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int j = (int)(i % KC);
@@ -50,16 +50,31 @@ __global__ void pack_blocks_kernel(const float* __restrict__ w, const float* __r
     float v = 0.f;
     if (co < Co && ci < Ci) v = (identity ? (co == ci ? 1.f : 0.f) : w[((long long)co * Ci + ci) * taps + tap]) * (a ? a[co] : 1.f);
     out[i] = __float2half_rn(v);
+    // range guard (ops._row_scales): track max|w| per output row (non-negative floats order like their bit patterns; NaN / inf
+    // have the largest patterns, so they survive the max)
+    if (rowmax && co < Co && ci < Ci && !identity) atomicMax(rowmax + co, (int)(__float_as_uint(v) & 0x7fffffffu));
   }
+}
+// flags[0] |= 1: a non-finite weight; flags[0] |= 2: a row that the fp16 image cannot hold (max|w| > 2^14 or in (0, 2^-10)): the
+// Python packer rescales such rows (TpzTcConvArgs.oscale); this packer reports them and the caller uses those plans
+__global__ void range_check_kernel(int* __restrict__ rowmax, int n, int* __restrict__ flags) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const float mx = __int_as_float(rowmax[c]);
+  rowmax[c] = 0;
+  if (!(mx <= 3.0e38f)) atomicOr(flags, 1);
+  else if (mx > 16384.f || (mx > 0.f && mx < 9.765625e-4f)) atomicOr(flags, 2);
 }
 // first layer for tpz_conv_first_tc: out[kb][n][j] = fp16(w[n][kb*64 + j] * a[n]) (tap index = kb*64 + j)
 __global__ void pack_first_kernel(const float* __restrict__ w, const float* __restrict__ a, int Co, int taps, int KB, int Cp,
-                                  __half* __restrict__ out) {
+                                  __half* __restrict__ out, int* __restrict__ rowmax) {
   const int total = KB * Cp * 64;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int j = i % 64, n = (i / 64) % Cp, kb = i / (64 * Cp);
     const int t = kb * 64 + j;
-    out[i] = __float2half_rn((n < Co && t < taps) ? w[(long long)n * taps + t] * (a ? a[n] : 1.f) : 0.f);
+    const float v = (n < Co && t < taps) ? w[(long long)n * taps + t] * (a ? a[n] : 1.f) : 0.f;
+    out[i] = __float2half_rn(v);
+    if (rowmax && n < Co && t < taps) atomicMax(rowmax + n, (int)(__float_as_uint(v) & 0x7fffffffu));
   }
 }
 // fallback first layer (tpz_conv_first, fp32 CUDA cores): w'[n][t] = w[n][t] * a[n]
@@ -96,7 +111,7 @@ struct TpzModel {
   float* first_b = nullptr;      // [Cp]
   std::vector<Step> steps;
   float* dot_w = nullptr;        // [C_last_store]
-  float* scratch = nullptr;      // BN affine a | sh (2 x 256 floats)
+  float* scratch = nullptr;      // BN affine a | sh (2 x 256 floats) | per-row max|w| of the step being packed (256) | range flags (2)
   int c_last = 0;
   // optional per-launch timing of the LAST conv step (the dominant kernel of a dense forward): a ring of CUDA event pairs recorded
   // on the launch stream, read back by tpz_model_timing_read (bench.py's roofline figure)
@@ -122,6 +137,9 @@ int free_model(TpzModel* m) {
 int pack_model(TpzModel* m, const TpzLayerDesc* L, int nlayers, const float* cls_w, const float* cls_b, cudaStream_t st) {
   float* a = m->scratch;
   float* sh = m->scratch + 256;
+  int* rowmax = reinterpret_cast<int*>(m->scratch + 512);
+  int* flags = rowmax + 256;
+  TPZ_CUDA(cudaMemsetAsync(rowmax, 0, (256 + 4) * sizeof(int), st));
   auto affine = [&](const float* bn, float eps, int C) -> bool {
     if (!bn) return false;
     bn_affine_kernel<<<tpz_div_up(C, 128), 128, 0, st>>>(bn, eps, C, a, sh);
@@ -133,7 +151,8 @@ int pack_model(TpzModel* m, const TpzLayerDesc* L, int nlayers, const float* cls
     const int taps = f.k * f.k;
     if (m->first_tc) {
       const int KB = (taps + 63) / 64;
-      pack_first_kernel<<<tpz_div_up(KB * m->c0_store * 64, 256), 256, 0, st>>>(f.w0, has ? a : nullptr, f.cout, taps, KB, m->c0_store, m->first_w16);
+      pack_first_kernel<<<tpz_div_up(KB * m->c0_store * 64, 256), 256, 0, st>>>(f.w0, has ? a : nullptr, f.cout, taps, KB, m->c0_store, m->first_w16, rowmax);
+      range_check_kernel<<<1, 256, 0, st>>>(rowmax, 256, flags);
     } else {
       scale_rows_kernel<<<tpz_div_up(f.cout * taps, 256), 256, 0, st>>>(f.w0, has ? a : nullptr, f.cout, taps, m->first_w32);
     }
@@ -146,17 +165,22 @@ int pack_model(TpzModel* m, const TpzLayerDesc* L, int nlayers, const float* cls
       const int taps = p.k * p.k, nchunks = tpz_div_up(p.ci, s.args.KC);
       const long long n = (long long)taps * nchunks * s.co_store * s.args.KC;
       pack_blocks_kernel<<<(int)(tpz_div_up(n, 256) > 148 * 16 ? 148 * 16 : tpz_div_up(n, 256)), 256, 0, st>>>(
-          p.w, has ? a : nullptr, p.co, p.ci, taps, nchunks, s.args.KC, s.co_store, p.identity ? 1 : 0, s.weights + off);
+          p.w, has ? a : nullptr, p.co, p.ci, taps, nchunks, s.args.KC, s.co_store, p.identity ? 1 : 0, s.weights + off, rowmax);
       off += n;
     }
+    range_check_kernel<<<1, 256, 0, st>>>(rowmax, 256, flags);
     bias_fold_kernel<<<tpz_div_up(s.co_store, 128), 128, 0, st>>>(s.bias_src, has ? a : nullptr, has ? sh : nullptr, s.co, s.co_store, s.bias);
   }
   pad_copy_kernel<<<tpz_div_up(rup(m->c_last), 128), 128, 0, st>>>(cls_w, m->c_last, rup(m->c_last), m->dot_w);
-  float db = 0.f;                 // the fused dot takes its bias by value: one 4-byte read-back per (re)pack
+  float db = 0.f;                 // the fused dot takes its bias by value: one 4-byte read-back per (re)pack (+ the range flags)
+  int hflags = 0;
   TPZ_CUDA(cudaMemcpyAsync(&db, cls_b, sizeof(float), cudaMemcpyDeviceToHost, st));
+  TPZ_CUDA(cudaMemcpyAsync(&hflags, flags, sizeof(int), cudaMemcpyDeviceToHost, st));
   TPZ_CUDA(cudaStreamSynchronize(st));
   m->steps.back().args.dot_b = db;
   TPZ_CUDA(cudaGetLastError());
+  if (hflags & 1) return tpz_fail(3, "topaz_b200: non-finite convolution weights (after BatchNorm folding)");
+  if (hflags & 2) return tpz_fail(TPZ_E_WEIGHT_RANGE, "tpz_model: a weight row leaves the fp16 range (needs row-scaled plans)");
   return 0;
 }
 
@@ -208,7 +232,7 @@ extern "C" int tpz_model_create(const TpzLayerDesc* layers, int nlayers, const f
   m->first_tc = f.dil0 == 1 && tpz_conv_first_tc_supported(f.k, m->c0_store);
   int rc = 0;
 #define MCHK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { free_model(m); return tpz_fail(1000 + (int)e_, "tpz_model_create: %s", cudaGetErrorString(e_)); } } while (0)
-  MCHK(cudaMalloc(&m->scratch, 512 * sizeof(float)));
+  MCHK(cudaMalloc(&m->scratch, (512 + 256 + 4) * sizeof(float)));   // BN a | sh | row maxima | range flags
   MCHK(cudaMalloc(&m->first_b, m->c0_store * sizeof(float)));
   if (m->first_tc) MCHK(cudaMalloc(&m->first_w16, (size_t)((f.k * f.k + 63) / 64) * m->c0_store * 64 * sizeof(__half)));
   else MCHK(cudaMalloc(&m->first_w32, (size_t)f.cout * f.k * f.k * sizeof(float)));

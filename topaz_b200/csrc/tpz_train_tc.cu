@@ -614,8 +614,14 @@ constexpr int kHaloMaxTaps = 9;
 constexpr int kHaloWBytes = kHaloMaxTaps * 8192; // per tap: hi 32 x 128 B | lo 32 x 128 B
 constexpr int kHaloSmem = kHaloWBytes + 2 * 2 * kHaloPlane + 1024;
 constexpr int kHaloMaxGroups = 4;                // accumulators per TMEM stage, 64 columns each: [main 32 | small 32]
-constexpr int kHaloWorkers = 256;                // threads of warps 0-7
+constexpr int kHaloWorkers = 256;                // threads of warps 0-7 (64-channel and first-layer kernels)
 constexpr int kHaloThreads = kHaloWorkers + 32;  // + the MMA warp
+// The 32-channel kernels run 16 worker warps: their tiles are bounded by the serial latency chain of a worker (global load -> split ->
+// swizzled store, then TMEM drain -> global store; tensor pipe 23-43 % busy with 8 workers, profiles/r02_ncu_train_halo.md), so the
+// same tile is spread over twice the threads (half the chain per thread, twice the warps to overlap it)
+constexpr int kHaloWorkersW = 512;
+constexpr int kHaloThreadsW = kHaloWorkersW + 32;
+constexpr int kHaloPre = (kHaloRows + 63) / 64;  // 16-byte pieces a wide worker stages per tile
 
 struct HaloArgs {
   const float* src; int N, SH, SW;      // source tensor [N][SH][SW][32]
@@ -653,7 +659,7 @@ __device__ __forceinline__ uint32_t desc_lo_mn(uint32_t smem_addr, uint32_t atom
 }
 
 template <int MODE>              // 0 forward (bias / residual / ReLU epilogue), 1 data gradient (accumulate / mask epilogue)
-__global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tc_kernel(const __grid_constant__ HaloArgs a) {
+__global__ void __launch_bounds__(kHaloThreadsW, 1) conv_halo_tc_kernel(const __grid_constant__ HaloArgs a) {
   constexpr uint32_t IDESC64 = idesc_tf32(128, 64), IDESC32 = idesc_tf32(128, 32);
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -665,7 +671,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tc_kernel(const __g
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     ptx::mbar_init(&bar_w, 1);
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&bar_full[s], kHaloWorkers); ptx::mbar_init(&bar_mma[s], 1); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&bar_full[s], kHaloWorkersW); ptx::mbar_init(&bar_mma[s], 1); }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&a.tmB);
   }
@@ -677,7 +683,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tc_kernel(const __g
   const int ngroups = (a.taps + a.group - 1) / a.group;
   const int stride_t = gridDim.x;
 
-  if (warp == 8) {
+  if (warp == kHaloWorkersW / 32) {
     // ------------------------------ MMA issuer ------------------------------
     if (lane == 0) {                                         // the whole weight set, once
       ptx::mbar_expect_tx(&bar_w, (uint32_t)a.taps * 8192u);
@@ -717,38 +723,38 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tc_kernel(const __g
     }
   } else {
     // ------------------------------ workers: stage tiles, drain and write outputs ------------------------------
-    // staging: thread (jr, c) moves 16-byte piece c of rows jr, jr + 32, ...; a warp's load covers 4 rows = 512 contiguous bytes
+    // staging: thread (jr, c) moves 16-byte piece c of rows jr, jr + 64, ...; a warp's load covers 4 rows = 512 contiguous bytes
     const int c = tid & 7, jr = tid >> 3;
     const float4* const src4 = reinterpret_cast<const float4*>(a.src);
-    float4 pre[kHaloRows / 32];
+    float4 pre[kHaloPre];
     auto load_tile = [&](int tile) {
       const long long p0 = (long long)tile * 128 + jr;
       if (a.contiguous) {
 #pragma unroll
-        for (int i = 0; i < kHaloRows / 32; ++i) {
-          const long long p = p0 + 32 * i;
-          pre[i] = (32 * i < a.rows && p < a.total) ? __ldg(src4 + p * 8 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < kHaloPre; ++i) {
+          const long long p = p0 + 64 * i;
+          pre[i] = (jr + 64 * i < a.rows && p < a.total) ? __ldg(src4 + p * 8 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       } else {
         ZPos z;
         z.set(p0 < a.total ? p0 : 0, a.Hz, a.Wz);
 #pragma unroll
-        for (int i = 0; i < kHaloRows / 32; ++i) {
+        for (int i = 0; i < kHaloPre; ++i) {
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (32 * i < a.rows && p0 + 32 * i < a.total) {
+          if (jr + 64 * i < a.rows && p0 + 64 * i < a.total) {
             const int sy = z.u - a.pad, sx = z.v - a.pad;
             if (sy >= 0 && sy < a.SH && sx >= 0 && sx < a.SW) v = __ldg(src4 + (((long long)z.n * a.SH + sy) * a.SW + sx) * 8 + c);
           }
           pre[i] = v;
-          z.advance(32, a.Hz, a.Wz);
+          z.advance(64, a.Hz, a.Wz);
         }
       }
     };
     auto store_tile = [&](unsigned char* stage) {
 #pragma unroll
-      for (int i = 0; i < kHaloRows / 32; ++i) {
-        const int j = jr + 32 * i;
-        if (32 * i < a.rows) {
+      for (int i = 0; i < kHaloPre; ++i) {
+        const int j = jr + 64 * i;
+        if (j < a.rows) {
           float4 hi, lo;
           split4(pre[i], hi, lo);
           const int off = j * 128 + ((c ^ (j & 7)) << 4);
@@ -758,7 +764,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tc_kernel(const __g
       }
     };
 
-    const int row = 32 * (warp & 3) + lane, half = warp >> 2;   // epilogue: thread (row, half) owns 16 channels of one output row
+    const int row = 32 * (warp & 3) + lane, part = warp >> 2;   // epilogue: thread (row, part) owns 8 channels of one output row
     const unsigned HWz = (unsigned)(a.Hz * a.Wz);
     auto epilogue = [&](int tile, int s, int it) {
       // output coordinates and the epilogue's global operands first: their latency hides behind the wait for the tile's MMAs
@@ -772,9 +778,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tc_kernel(const __g
         valid = u < a.OH && v < a.OW;
       }
       const long long m = ((long long)n * a.OH + u) * a.OW + v;
-      const int nb = half * 16;
+      const int nb = part * 8;
       float* orow = a.out + m * 32 + nb;
-      float4 pr[4], pm[4], pa[4];                              // residual, mask, previous value: 16 channels each
+      float4 pr[2], pm[2], pa[2];                              // residual, mask, previous value: 8 channels each
       bool use_res = false;
       if (valid) {
         if (a.res) {
@@ -788,71 +794,68 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tc_kernel(const __g
             rbase = (((long long)n * a.res_H + ry) * a.res_W + rx) * 32;
           }
           if (use_res) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) pr[j] = __ldg(reinterpret_cast<const float4*>(a.res + rbase + nb) + j);
+            pr[0] = __ldg(reinterpret_cast<const float4*>(a.res + rbase + nb));
+            pr[1] = __ldg(reinterpret_cast<const float4*>(a.res + rbase + nb) + 1);
           }
         }
         if (MODE == 1 && a.mask) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) pm[j] = __ldg(reinterpret_cast<const float4*>(a.mask + m * 32 + nb) + j);
+          pm[0] = __ldg(reinterpret_cast<const float4*>(a.mask + m * 32 + nb));
+          pm[1] = __ldg(reinterpret_cast<const float4*>(a.mask + m * 32 + nb) + 1);
         }
         if (MODE == 1 && a.accumulate) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) pa[j] = *(reinterpret_cast<const float4*>(orow) + j);
+          pa[0] = *reinterpret_cast<const float4*>(orow);
+          pa[1] = *(reinterpret_cast<const float4*>(orow) + 1);
         }
       }
       mbar_wait(&bar_mma[s], (uint32_t)(it >> 1) & 1u);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)s * 256u + (uint32_t)half * 16u;
-      float acc[16];
+      const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)s * 256u + (uint32_t)part * 8u;
+      float acc[8], mainsum[8];
       {
-        uint32_t rs[16], rm[16];
-        ptx::tmem_ld16(taddr + 32u, rs);                      // group 0: small, main
-        ptx::tmem_ld16(taddr, rm);
+        uint32_t rs[8], rm[8];
+        ptx::tmem_ld8(taddr + 32u, rs);                       // group 0: small, main
+        ptx::tmem_ld8(taddr, rm);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(rs[j]);
-        float mainsum[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) mainsum[j] = __uint_as_float(rm[j]);
+        for (int j = 0; j < 8; ++j) { acc[j] = __uint_as_float(rs[j]); mainsum[j] = __uint_as_float(rm[j]); }
         for (int g = 1; g < ngroups; ++g) {
-          ptx::tmem_ld16(taddr + (uint32_t)g * 64u + 32u, rs);
-          ptx::tmem_ld16(taddr + (uint32_t)g * 64u, rm);
+          ptx::tmem_ld8(taddr + (uint32_t)g * 64u + 32u, rs);
+          ptx::tmem_ld8(taddr + (uint32_t)g * 64u, rm);
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) { acc[j] += __uint_as_float(rs[j]); mainsum[j] += __uint_as_float(rm[j]); }
+          for (int j = 0; j < 8; ++j) { acc[j] += __uint_as_float(rs[j]); mainsum[j] += __uint_as_float(rm[j]); }
         }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] += mainsum[j];
+        for (int j = 0; j < 8; ++j) acc[j] += mainsum[j];
       }
       ptx::tc_fence_before();
       if (!valid) return;
+      if (MODE == 0) {
+        if (a.bias) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float o[4] = {acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]};
-        if (MODE == 0) {
-          if (a.bias) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) o[e] += __ldg(a.bias + nb + 4 * j + e);      // scalar: parameter views need not be 16-byte aligned
-          }
-          if (use_res) { o[0] += pr[j].x; o[1] += pr[j].y; o[2] += pr[j].z; o[3] += pr[j].w; }
-          if (a.relu) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
-          }
-        } else {
-          if (a.accumulate) { o[0] += pa[j].x; o[1] += pa[j].y; o[2] += pa[j].z; o[3] += pa[j].w; }
-          if (use_res) { o[0] += pr[j].x; o[1] += pr[j].y; o[2] += pr[j].z; o[3] += pr[j].w; }
-          if (a.mask) {
-            o[0] = pm[j].x > 0.f ? o[0] : 0.f; o[1] = pm[j].y > 0.f ? o[1] : 0.f; o[2] = pm[j].z > 0.f ? o[2] : 0.f; o[3] = pm[j].w > 0.f ? o[3] : 0.f;
-          }
+          for (int e = 0; e < 8; ++e) acc[e] += __ldg(a.bias + nb + e);           // scalar: parameter views need not be 16-byte aligned
         }
-        acc[4 * j] = o[0]; acc[4 * j + 1] = o[1]; acc[4 * j + 2] = o[2]; acc[4 * j + 3] = o[3];
+        if (use_res) {
+          acc[0] += pr[0].x; acc[1] += pr[0].y; acc[2] += pr[0].z; acc[3] += pr[0].w; acc[4] += pr[1].x; acc[5] += pr[1].y; acc[6] += pr[1].z; acc[7] += pr[1].w;
+        }
+        if (a.relu) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] = fmaxf(acc[e], 0.f);
+        }
+      } else {
+        if (a.accumulate) {
+          acc[0] += pa[0].x; acc[1] += pa[0].y; acc[2] += pa[0].z; acc[3] += pa[0].w; acc[4] += pa[1].x; acc[5] += pa[1].y; acc[6] += pa[1].z; acc[7] += pa[1].w;
+        }
+        if (use_res) {
+          acc[0] += pr[0].x; acc[1] += pr[0].y; acc[2] += pr[0].z; acc[3] += pr[0].w; acc[4] += pr[1].x; acc[5] += pr[1].y; acc[6] += pr[1].z; acc[7] += pr[1].w;
+        }
+        if (a.mask) {
+          acc[0] = pm[0].x > 0.f ? acc[0] : 0.f; acc[1] = pm[0].y > 0.f ? acc[1] : 0.f; acc[2] = pm[0].z > 0.f ? acc[2] : 0.f; acc[3] = pm[0].w > 0.f ? acc[3] : 0.f;
+          acc[4] = pm[1].x > 0.f ? acc[4] : 0.f; acc[5] = pm[1].y > 0.f ? acc[5] : 0.f; acc[6] = pm[1].z > 0.f ? acc[6] : 0.f; acc[7] = pm[1].w > 0.f ? acc[7] : 0.f;
+        }
       }
       ptx::st_global_256(orow, __float_as_uint(acc[0]), __float_as_uint(acc[1]), __float_as_uint(acc[2]), __float_as_uint(acc[3]),
                          __float_as_uint(acc[4]), __float_as_uint(acc[5]), __float_as_uint(acc[6]), __float_as_uint(acc[7]));
-      ptx::st_global_256(orow + 8, __float_as_uint(acc[8]), __float_as_uint(acc[9]), __float_as_uint(acc[10]), __float_as_uint(acc[11]),
-                         __float_as_uint(acc[12]), __float_as_uint(acc[13]), __float_as_uint(acc[14]), __float_as_uint(acc[15]));
     };
 
     int it = 0, tile = blockIdx.x;
@@ -863,7 +866,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_tc_kernel(const __g
       store_tile(stages + (size_t)s * 2 * kHaloPlane);
       ptx::fence_proxy_async();                               // this thread's stores -> visible to the tensor core's (async-proxy) reads
       ptx::tc_fence_before();
-      ptx::mbar_arrive(&bar_full[s]);                         // every worker arrives for itself (count = kHaloWorkers)
+      ptx::mbar_arrive(&bar_full[s]);                         // every worker arrives for itself (count = kHaloWorkersW)
       if (tile + stride_t < a.ntiles) load_tile(tile + stride_t);     // in flight while the previous tile is written out
       if (it > 0) epilogue(tile - stride_t, s ^ 1, it - 1);
     }
@@ -1106,7 +1109,7 @@ constexpr int kWgDyPlane = 128 * 128;                          // dy tile: 128 p
 constexpr int kWgStage = 2 * kHaloPlane + 2 * kWgDyPlane;      // x hi | x lo | dy hi | dy lo
 constexpr int kWgSmem = 2 * kWgStage + 1024;
 
-__global__ void __launch_bounds__(kHaloThreads, 1) wgrad_halo_tc_kernel(const __grid_constant__ HaloArgs a) {
+__global__ void __launch_bounds__(kHaloThreadsW, 1) wgrad_halo_tc_kernel(const __grid_constant__ HaloArgs a) {
   // MN-major A and B (bits 15, 16)
   constexpr uint32_t IDESC64 = idesc_tf32(128, 64) | (1u << 15) | (1u << 16), IDESC32 = idesc_tf32(128, 32) | (1u << 15) | (1u << 16);
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -1118,7 +1121,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) wgrad_halo_tc_kernel(const __
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid < 32) s_db[tid] = 0.f;
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&bar_full[s], kHaloWorkers); ptx::mbar_init(&bar_mma[s], 1); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&bar_full[s], kHaloWorkersW); ptx::mbar_init(&bar_mma[s], 1); }
     ptx::fence_barrier_init();
   }
   if (warp == 0) ptx::tmem_alloc<512>(&tmem_base_s);
@@ -1128,7 +1131,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) wgrad_halo_tc_kernel(const __
   const uint32_t tmem_base = tmem_base_s;
   const int stride_t = gridDim.x;
 
-  if (warp == 8) {
+  if (warp == kHaloWorkersW / 32) {
     // MN-major 32-bit operands exist in ONE shared-memory layout, SWIZZLE_128B_BASE32B (layout type 1): atom = 4 K-rows (pixels) x
     // 128 bytes, 32-byte piece q of row p stored at piece q ^ (p & 3); LBO = stride between MN atoms, SBO = stride between the
     // two K atoms of a K = 8 step (4 rows = 512 bytes).  A's MN atoms are the taps t = 0..3: dil rows apart (overlapping atoms).
@@ -1157,33 +1160,33 @@ __global__ void __launch_bounds__(kHaloThreads, 1) wgrad_halo_tc_kernel(const __
       __syncwarp();
     }
   } else {
-    const int c = tid & 7, jr = tid >> 3;
+    const int c = tid & 7, jr = tid >> 3;                     // 16 worker warps: piece c of rows jr, jr + 64, ...
     const float4* const x4 = reinterpret_cast<const float4*>(a.src);
     const float4* const dy4 = reinterpret_cast<const float4*>(a.dy);
-    float4 prex[kHaloRows / 32], prey[4];
+    float4 prex[kHaloPre], prey[2];
     float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);            // bias gradient: column sums of the dy pieces this thread stages
     auto load_tile = [&](int tile) {
       const long long p0 = (long long)tile * 128 + jr;
 #pragma unroll
-      for (int i = 0; i < kHaloRows / 32; ++i) {
-        const long long p = p0 + 32 * i;
-        prex[i] = (32 * i < a.rows && p < a.total) ? __ldg(x4 + p * 8 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < kHaloPre; ++i) {
+        const long long p = p0 + 64 * i;
+        prex[i] = (jr + 64 * i < a.rows && p < a.total) ? __ldg(x4 + p * 8 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       ZPos z;
       z.set(p0 < a.total ? p0 : 0, a.Hz, a.Wz);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 2; ++i) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p0 + 32 * i < a.total && z.u < a.OH && z.v < a.OW) v = __ldg(dy4 + (((long long)z.n * a.OH + z.u) * a.OW + z.v) * 8 + c);
+        if (p0 + 64 * i < a.total && z.u < a.OH && z.v < a.OW) v = __ldg(dy4 + (((long long)z.n * a.OH + z.u) * a.OW + z.v) * 8 + c);
         prey[i] = v;
-        z.advance(32, a.Hz, a.Wz);
+        z.advance(64, a.Hz, a.Wz);
       }
     };
     auto store_tile = [&](unsigned char* stage) {
 #pragma unroll
-      for (int i = 0; i < kHaloRows / 32; ++i) {
-        const int j = jr + 32 * i;
-        if (32 * i < a.rows) {
+      for (int i = 0; i < kHaloPre; ++i) {
+        const int j = jr + 64 * i;
+        if (j < a.rows) {
           float4 hi, lo;
           split4(prex[i], hi, lo);
           const int off = j * 128 + ((c ^ ((j & 3) << 1)) << 4);     // 32-byte piece (c >> 1) ^= j & 3
@@ -1192,8 +1195,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) wgrad_halo_tc_kernel(const __
         }
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int j = jr + 32 * i;
+      for (int i = 0; i < 2; ++i) {
+        const int j = jr + 64 * i;
         float4 hi, lo;
         split4(prey[i], hi, lo);
         bsum.x += prey[i].x; bsum.y += prey[i].y; bsum.z += prey[i].z; bsum.w += prey[i].w;
@@ -1202,26 +1205,28 @@ __global__ void __launch_bounds__(kHaloThreads, 1) wgrad_halo_tc_kernel(const __
         *reinterpret_cast<float4*>(stage + 2 * kHaloPlane + kWgDyPlane + off) = lo;
       }
     };
-    // accumulator lane m = 32*t + ci (t = tap column, 3 = dummy), columns = co; thread (m, half) keeps co half*16 .. +16 of the 3 rows r
-    const int half = warp >> 2;
-    float tot[3][16];
+    // accumulator lane m = 32*t + ci (t = tap column, 3 = dummy), columns = co; thread (m, part) keeps co part*8 .. +8 of the 3 rows r
+    const int part = warp >> 2;
+    float tot[3][8];
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int j = 0; j < 16; ++j) tot[r][j] = 0.f;
+      for (int j = 0; j < 8; ++j) tot[r][j] = 0.f;
     auto drain = [&](int s, int it) {
       mbar_wait(&bar_mma[s], (uint32_t)(it >> 1) & 1u);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)s * 256u + (uint32_t)half * 16u;
+      const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)s * 256u + (uint32_t)part * 8u;
+      uint32_t rs[3][8], rm[3][8];
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
-        uint32_t rs[16], rm[16];
-        ptx::tmem_ld16(taddr + r * 64u + 32u, rs);
-        ptx::tmem_ld16(taddr + r * 64u, rm);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) tot[r][j] += __uint_as_float(rs[j]) + __uint_as_float(rm[j]);
+        ptx::tmem_ld8(taddr + r * 64u + 32u, rs[r]);
+        ptx::tmem_ld8(taddr + r * 64u, rm[r]);
       }
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tot[r][j] += __uint_as_float(rs[r][j]) + __uint_as_float(rm[r][j]);
       ptx::tc_fence_before();
     };
     int it = 0, tile = blockIdx.x;
@@ -1231,7 +1236,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) wgrad_halo_tc_kernel(const __
       store_tile(base + (size_t)s * kWgStage);
       ptx::fence_proxy_async();                               // this thread's stores -> visible to the tensor core's (async-proxy) reads
       ptx::tc_fence_before();
-      ptx::mbar_arrive(&bar_full[s]);                         // every worker arrives for itself (count = kHaloWorkers)
+      ptx::mbar_arrive(&bar_full[s]);                         // every worker arrives for itself (count = kHaloWorkersW)
       if (tile + stride_t < a.ntiles) load_tile(tile + stride_t);
       if (it > 0) drain(s ^ 1, it - 1);
     }
@@ -1241,7 +1246,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) wgrad_halo_tc_kernel(const __
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int j = 0; j < 16; ++j) atomicAdd(a.dw + ((long long)(half * 16 + j) * 32 + ci) * 9 + r * 3 + t, tot[r][j]);
+        for (int j = 0; j < 8; ++j) atomicAdd(a.dw + ((long long)(part * 8 + j) * 32 + ci) * 9 + r * 3 + t, tot[r][j]);
     }
     if (a.db) {
       atomicAdd(&s_db[4 * c], bsum.x); atomicAdd(&s_db[4 * c + 1], bsum.y); atomicAdd(&s_db[4 * c + 2], bsum.z); atomicAdd(&s_db[4 * c + 3], bsum.w);
@@ -1269,7 +1274,7 @@ struct FirstArgs {
   const float* x; int N, H, W;          // [N][H][W], one channel
   int stride, Ho, Wo;
   const float* w; const float* bias; int relu; float* y;      // forward: w [32][49] (OIHW, Ci = 1)
-  const float* dy; float* dw;                                   // wgrad
+  const float* dy; float* dw; float* db;                        // wgrad (db: bias gradient, may be NULL)
   long long M; int ntiles;
 };
 constexpr int kFirstK = 7, kFirstTaps = 49;
@@ -1299,8 +1304,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) first_tc_train_kernel(const _
   constexpr int STAGE = WGRAD ? 6 * kFirstPlane : 4 * kFirstPlane;
   __shared__ __align__(8) uint64_t bar_full[2], bar_mma[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ float s_db[32];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < 32) s_db[tid] = 0.f;
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(&bar_full[s], kHaloWorkers); ptx::mbar_init(&bar_mma[s], 1); }
     ptx::fence_barrier_init();
@@ -1364,6 +1371,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) first_tc_train_kernel(const _
     const int row = tid & 127, c = tid >> 7;
     float col[32];
     float4 prey[4];
+    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);            // bias gradient: column sums of the dy pieces this thread stages
     const int pcy = tid & 7, jry = tid >> 3;                  // dy staging (wgrad): 16-byte piece pcy of rows jry + 32 i
     auto load_tile = [&](int tile) {
       const long long m = (long long)tile * 128 + row;
@@ -1399,6 +1407,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) first_tc_train_kernel(const _
           const int j = jry + 32 * i;
           float4 hi, lo;
           split4(prey[i], hi, lo);
+          bsum.x += prey[i].x; bsum.y += prey[i].y; bsum.z += prey[i].z; bsum.w += prey[i].w;
           const int off = j * 128 + ((pcy ^ ((j & 3) << 1)) << 4);
           *reinterpret_cast<float4*>(stage + 4 * kFirstPlane + off) = hi;
           *reinterpret_cast<float4*>(stage + 5 * kFirstPlane + off) = lo;
@@ -1461,9 +1470,13 @@ __global__ void __launch_bounds__(kHaloThreads, 1) first_tc_train_kernel(const _
         for (int j = 0; j < 32; ++j) atomicAdd(a.dw + j * kFirstTaps + tap, tot[j]);
       }
     }
+    if (WGRAD && a.db) {
+      atomicAdd(&s_db[4 * pcy], bsum.x); atomicAdd(&s_db[4 * pcy + 1], bsum.y); atomicAdd(&s_db[4 * pcy + 2], bsum.z); atomicAdd(&s_db[4 * pcy + 3], bsum.w);
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (WGRAD && a.db && tid < 32) atomicAdd(a.db + tid, s_db[tid]);
   if (warp == 0) ptx::tmem_dealloc<128>(tmem_base);
 }
 
@@ -1631,7 +1644,7 @@ int launch_halo(const HaloArgs& a, cudaStream_t stream) {
     configured = true;
   }
   const int grid = a.ntiles < sm_count() ? a.ntiles : sm_count();
-  conv_halo_tc_kernel<MODE><<<grid, kHaloThreads, kHaloSmem, stream>>>(a);
+  conv_halo_tc_kernel<MODE><<<grid, kHaloThreadsW, kHaloSmem, stream>>>(a);
   TPZ_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1665,7 +1678,7 @@ int launch_wgrad_halo(const HaloArgs& a, cudaStream_t stream) {
     configured = true;
   }
   const int grid = a.ntiles < sm_count() ? a.ntiles : sm_count();
-  wgrad_halo_tc_kernel<<<grid, kHaloThreads, kWgSmem, stream>>>(a);
+  wgrad_halo_tc_kernel<<<grid, kHaloThreadsW, kWgSmem, stream>>>(a);
   TPZ_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1924,11 +1937,11 @@ extern "C" int tpz_first_fwd_tc(const float* x, int N, int H, int W, const float
 }
 
 extern "C" int tpz_first_wgrad_tc(const float* x, int N, int H, int W, const float* dy, int Ho, int Wo, int Co, int k, int stride,
-                                  float* dw, void* stream) {
+                                  float* dw, float* db, void* stream) {
   if (!first_tc_enabled() || Co != 32 || k != kFirstK || (Ho - 1) * stride + k > H || (Wo - 1) * stride + k > W) return -1;
   FirstArgs a;
   memset(&a, 0, sizeof(a));
-  a.x = x; a.N = N; a.H = H; a.W = W; a.stride = stride; a.Ho = Ho; a.Wo = Wo; a.dy = dy; a.dw = dw;
+  a.x = x; a.N = N; a.H = H; a.W = W; a.stride = stride; a.Ho = Ho; a.Wo = Wo; a.dy = dy; a.dw = dw; a.db = db;
   a.M = (long long)N * Ho * Wo; a.ntiles = tpz_div_up(a.M, 128);
   static bool configured = false;
   if (!configured) {

@@ -304,7 +304,9 @@ def classifier_forward(model, x: torch.Tensor) -> torch.Tensor:
     xi = _as_image_batch(x, 2)
     key = _state_key(model, ('dense', str(xi.device)))
     if DENSE_ENGINE == 'c' and PRECISION != 'strict' and RANGE_GUARD and ops.TC_VARIANT == 'auto':
-        return _dense_c_model(model, key).forward(xi)
+        dm = _dense_c_model(model, key)
+        if dm is not None:               # None: a weight row needs the row-scaled plans, which only the Python packer builds
+            return dm.forward(xi)
     plan = _cached(model, 'dense_cls', key, lambda: _build_dense_plan(feats, model.classifier, xi.device))
     y, _ = _run_dense(plan, xi, want_features=False)   # [B, 1(D), H, W]; the fused dot epilogue already undid the range scale
     return y.view(xi.shape[0], 1, y.shape[2], y.shape[3])
@@ -313,19 +315,24 @@ def classifier_forward(model, x: torch.Tensor) -> torch.Tensor:
 def _dense_c_model(model, key):
     """The model's native handle (model_abi.DenseModel), repacked on the device when a parameter changed and rebuilt when the
     geometry did (fill()/unfill() change dilations)."""
-    from .model_abi import DenseModel
+    from .model_abi import DenseModel, WeightRangeError
     cache = model.__dict__.setdefault('_tpz_plans', {})
     hit = cache.get('dense_c')
     geom = tuple((b.get('dil'), b.get('d0'), b.get('d1')) for b in _feature_blocks(model.features, slopes=False))
     if hit is not None and hit[0] == key:
         return hit[2]
-    if hit is not None and hit[1] == geom:
-        hit[2].update()
-        cache['dense_c'] = (key, geom, hit[2])
-        return hit[2]
-    if hit is not None:
-        hit[2].close()
-    dm = DenseModel(model)
+    try:
+        if hit is not None and hit[1] == geom and hit[2] is not None:
+            hit[2].update()
+            cache['dense_c'] = (key, geom, hit[2])
+            return hit[2]
+        if hit is not None and hit[2] is not None:
+            hit[2].close()
+        dm = DenseModel(model)
+    except WeightRangeError:
+        if hit is not None and hit[2] is not None:
+            hit[2].close()
+        dm = None                        # remembered for this parameter state: the Python plans (ops._row_scales) take over
     cache['dense_c'] = (key, geom, dm)
     return dm
 

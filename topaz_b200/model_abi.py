@@ -15,6 +15,13 @@ from . import _lib, ops
 from ._lib import TpzLayerDesc, check
 
 
+class WeightRangeError(RuntimeError):
+    """a (BatchNorm-folded) weight row does not fit fp16 without the per-row scale only the Python packer applies"""
+
+
+E_WEIGHT_RANGE = 4      # include/topaz_b200.h TPZ_E_WEIGHT_RANGE
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -89,9 +96,12 @@ class DenseModel:
         descs, keep, cw, cb = self._describe()
         s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         if create:
-            check(_lib.lib().tpz_model_create(descs, len(descs), _ptr(cw), _ptr(cb), self.pad, C.byref(self.handle), s))
+            rc = _lib.lib().tpz_model_create(descs, len(descs), _ptr(cw), _ptr(cb), self.pad, C.byref(self.handle), s)
         else:
-            check(_lib.lib().tpz_model_update_weights(self.handle, descs, len(descs), _ptr(cw), _ptr(cb), s))
+            rc = _lib.lib().tpz_model_update_weights(self.handle, descs, len(descs), _ptr(cw), _ptr(cb), s)
+        if rc == E_WEIGHT_RANGE:
+            raise WeightRangeError(_lib.lib().tpz_last_error().decode())
+        check(rc)
         ops._count(2 * len(descs) + 4)
         del keep          # the library has read (and synchronised on) every parameter
 

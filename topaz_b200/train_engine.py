@@ -58,6 +58,8 @@ class FlatParams:
         descs, poff, mx = [], 0, 0
         for p, off in zip(self.params, self.offsets):
             if p.dim() == 4 and p.shape[1] % 16 == 0 and p.shape[0] % 16 == 0:
+                if USE_TC and p.shape[1] % 32 == 0 and p.shape[0] % 32 == 0:
+                    continue                                   # served by the tcgen05 kernels (packed_tc below): no mma.sync copy
                 co, ci, kh, kw = p.shape
                 k = p.numel()
                 self.packed_off[id(p)] = (poff, poff + k)
@@ -158,9 +160,10 @@ def _repack(fp, force: bool = False):
     stepped OR a parameter was changed in place between steps (load_state_dict, p.data.copy_, a parameter broadcast):
     the in-place version counters catch the latter."""
     vers = fp.versions()
-    if fp.ndesc and (force or fp.packed_step != fp.step or fp.packed_versions != vers):
-        ops._count(1)
-        check(_lib.lib().tpz_train_repack(_p(fp.flat_p), _p(fp.descs), fp.ndesc, fp.max_elems, _p(fp.packed), _s()))
+    if (fp.ndesc or fp.ndesc_tc) and (force or fp.packed_step != fp.step or fp.packed_versions != vers):
+        if fp.ndesc:
+            ops._count(1)
+            check(_lib.lib().tpz_train_repack(_p(fp.flat_p), _p(fp.descs), fp.ndesc, fp.max_elems, _p(fp.packed), _s()))
         if USE_TC and fp.ndesc_tc:
             ops._count(1)
             check(_lib.lib().tpz_train_repack_tc(_p(fp.flat_p), _p(fp.descs_tc), fp.ndesc_tc, fp.max_elems_tc, _p(fp.packed_tc), _s()))
@@ -253,7 +256,9 @@ def _conv_wgrad(x, dy, w_grad, b_grad, stride, dil, org):
     kh, kw = w_grad.shape[2], w_grad.shape[3]
     ops._count(2 if b_grad is not None else 1)
     if USE_MMA and Ci == 1 and Co in (32, 64) and org == 0 and dil == 1 and kh == kw and kh * kw <= (256 // Co) * 16:
-        rc = _lib.lib().tpz_first_wgrad_tc(_p(x), N, H, W, _p(dy), Ho, Wo, Co, kh, stride, _p(w_grad), _s()) if USE_TC else -1
+        rc = _lib.lib().tpz_first_wgrad_tc(_p(x), N, H, W, _p(dy), Ho, Wo, Co, kh, stride, _p(w_grad), _p(b_grad), _s()) if USE_TC else -1
+        if rc == 0:
+            return                                             # the bias gradient rode along
         if rc == -1:
             rc = _lib.lib().tpz_first_wgrad_f32(_p(x), N, H, W, _p(dy), Ho, Wo, Co, kh, stride, _p(w_grad), _s())
         check(rc)
