@@ -636,7 +636,8 @@ struct HaloArgs {
   const float* bias; const float* res; int res_H, res_W, res_org, res_stride;
   const float* mask; float* out; int relu, accumulate;
   // wgrad only
-  const float* dy; float* dw; float* db; int dil, row0[3], kper;   // row0[r]: source row of tap (r, 0); kper: tiles per CTA between flushes (unused)
+  const float* dy; float* dw; float* db; int dil, row0[3], kper;
+  int x_ld4, dy_ld4, ci_blocks, Ci_tot;   // wider layers: blockIdx.y = (32-channel block of ci, 32-channel block of co); row strides in float4   // row0[r]: source row of tap (r, 0); kper: tiles per CTA between flushes (unused)
 };
 
 // (n, u, v) of a Z-linear position, advanced incrementally (one division pair per tile and thread instead of one per row)
@@ -1161,8 +1162,9 @@ __global__ void __launch_bounds__(kHaloThreadsW, 1) wgrad_halo_tc_kernel(const _
     }
   } else {
     const int c = tid & 7, jr = tid >> 3;                     // 16 worker warps: piece c of rows jr, jr + 64, ...
-    const float4* const x4 = reinterpret_cast<const float4*>(a.src);
-    const float4* const dy4 = reinterpret_cast<const float4*>(a.dy);
+    const int cib = (int)blockIdx.y % a.ci_blocks, cob = (int)blockIdx.y / a.ci_blocks;   // this CTA's 32 x 32 block of dw
+    const float4* const x4 = reinterpret_cast<const float4*>(a.src) + cib * 8;
+    const float4* const dy4 = reinterpret_cast<const float4*>(a.dy) + cob * 8;
     float4 prex[kHaloPre], prey[2];
     float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);            // bias gradient: column sums of the dy pieces this thread stages
     auto load_tile = [&](int tile) {
@@ -1170,14 +1172,14 @@ __global__ void __launch_bounds__(kHaloThreadsW, 1) wgrad_halo_tc_kernel(const _
 #pragma unroll
       for (int i = 0; i < kHaloPre; ++i) {
         const long long p = p0 + 64 * i;
-        prex[i] = (jr + 64 * i < a.rows && p < a.total) ? __ldg(x4 + p * 8 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        prex[i] = (jr + 64 * i < a.rows && p < a.total) ? __ldg(x4 + p * a.x_ld4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       ZPos z;
       z.set(p0 < a.total ? p0 : 0, a.Hz, a.Wz);
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p0 + 64 * i < a.total && z.u < a.OH && z.v < a.OW) v = __ldg(dy4 + (((long long)z.n * a.OH + z.u) * a.OW + z.v) * 8 + c);
+        if (p0 + 64 * i < a.total && z.u < a.OH && z.v < a.OW) v = __ldg(dy4 + (((long long)z.n * a.OH + z.u) * a.OW + z.v) * a.dy_ld4 + c);
         prey[i] = v;
         z.advance(64, a.Hz, a.Wz);
       }
@@ -1246,15 +1248,15 @@ __global__ void __launch_bounds__(kHaloThreadsW, 1) wgrad_halo_tc_kernel(const _
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(a.dw + ((long long)(part * 8 + j) * 32 + ci) * 9 + r * 3 + t, tot[r][j]);
+        for (int j = 0; j < 8; ++j) atomicAdd(a.dw + ((long long)(cob * 32 + part * 8 + j) * a.Ci_tot + cib * 32 + ci) * 9 + r * 3 + t, tot[r][j]);
     }
-    if (a.db) {
+    if (a.db && cib == 0) {                                  // one ci block per co block reports the bias gradient
       atomicAdd(&s_db[4 * c], bsum.x); atomicAdd(&s_db[4 * c + 1], bsum.y); atomicAdd(&s_db[4 * c + 2], bsum.z); atomicAdd(&s_db[4 * c + 3], bsum.w);
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (a.db && tid < 32) atomicAdd(a.db + tid, s_db[tid]);
+  if (a.db && tid < 32 && (int)blockIdx.y % a.ci_blocks == 0) atomicAdd(a.db + ((int)blockIdx.y / a.ci_blocks) * 32 + tid, s_db[tid]);
   if (warp == 0) ptx::tmem_dealloc<512>(tmem_base);
 }
 
@@ -1585,7 +1587,8 @@ int sm_count() {
 // mode 0: forward of x [N][H][W][32] -> y [N][Ho][Wo][32]; mode 1: data gradient dy [N][Ho][Wo][32] -> dx [N][H][W][32].
 bool halo_geometry(HaloArgs& a, int mode, int N, int H, int W, int Ci, int Ho, int Wo, int Co, int kh, int kw, int stride, int dil,
                    int org, int C = 32) {
-  if (!halo_enabled() || stride != 1 || Ci != C || Co != C || kh != kw || kh * kw > kHaloMaxTaps) return false;
+  if (!halo_enabled() || stride != 1 || kh != kw || kh * kw > kHaloMaxTaps) return false;
+  if (mode == 2 ? (Ci % 32 != 0 || Co % 32 != 0) : (Ci != C || Co != C)) return false;   // wgrad: any multiple of 32 (32 x 32 blocks of dw)
   const int chunks = C / 32, max_rows = C == 32 ? kHaloRows : kH64Rows;
   const int k = kh, span = (k - 1) * dil;
   a.N = N; a.taps = k * k;
@@ -1621,6 +1624,7 @@ bool halo_geometry(HaloArgs& a, int mode, int N, int H, int W, int Ci, int Ho, i
     a.dil = dil;
     for (int r = 0; r < 3; ++r) a.row0[r] = a.roff[r * 3];
     mx = a.row0[2] + 3 * dil;
+    a.x_ld4 = Ci / 4; a.dy_ld4 = Co / 4; a.ci_blocks = Ci / 32; a.Ci_tot = Ci;
   }
   a.rows = (128 + mx + 31) / 32 * 32;
   if (a.rows > max_rows) return false;
@@ -1677,8 +1681,11 @@ int launch_wgrad_halo(const HaloArgs& a, cudaStream_t stream) {
     TPZ_CUDA(cudaFuncSetAttribute(wgrad_halo_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem));
     configured = true;
   }
-  const int grid = a.ntiles < sm_count() ? a.ntiles : sm_count();
-  wgrad_halo_tc_kernel<<<grid, kHaloThreadsW, kWgSmem, stream>>>(a);
+  const int nby = a.ci_blocks * (a.dy_ld4 / 8);               // 32 x 32 blocks of dw
+  int gx = sm_count() / nby;
+  if (gx < 1) gx = 1;
+  if (gx > a.ntiles) gx = a.ntiles;
+  wgrad_halo_tc_kernel<<<dim3(gx, nby), kHaloThreadsW, kWgSmem, stream>>>(a);
   TPZ_CUDA(cudaGetLastError());
   return 0;
 }
