@@ -227,18 +227,22 @@ class Denoise3D(Denoise):
                 patch_range=None) -> np.ndarray:
         """``patch_range=(start, stop)`` restricts the work to a slice of the patch list (multi-GPU sharding);
         voxels of other patches stay zero."""
-        denoised = np.zeros_like(tomo)
-        mu, std = tomo.mean(), tomo.std()
         if patch_size < 1:
+            denoised = np.zeros_like(tomo)
             denoised[:] = Denoise._denoise(self, tomo)
             return denoised
-        td = torch.from_numpy(tomo).to(self.device)
+        # The whole tomogram goes to the device once (512^3 fp32 = 537 MB); its mean / std (reference: tomo.mean(), tomo.std() on the
+        # host, ~0.3 s of numpy per call and per rank) are reduced there with fp64 accumulators and stay there: the per-patch
+        # normalise / de-normalise read them as 0-dim tensors, so no host synchronisation happens before the final copy.
+        tomo32 = np.ascontiguousarray(tomo, dtype=np.float32)
+        td = torch.from_numpy(tomo32).to(self.device)
+        stats = ops.meanstd(td, unbiased=False)               # numpy's std is the population std (ddof = 0)
+        mu32, std32 = stats[0], stats[1]
         out_d = torch.zeros_like(td)
         pz = [int(np.ceil(n / patch_size)) for n in tomo.shape]
         total = int(np.prod(pz))
         lo, hi = (0, total) if patch_range is None else patch_range
         d = patch_size + 2 * padding
-        mu32, std32 = np.float32(mu), np.float32(std)
         count = 0
         for p in range(lo, hi):
             i, j, k = (int(v) * patch_size for v in np.unravel_index(p, pz))
@@ -259,8 +263,14 @@ class Denoise3D(Denoise):
                 print(f'# [{volume_num}/{total_volumes}] {round(count*100/max(1, hi-lo))}%', file=sys.stderr, end='\r')
         if verbose:
             print(' ' * 100, file=sys.stderr, end='\r')
-        denoised[:] = out_d.cpu().numpy()
-        return denoised
+        # The result comes back through a pinned block of torch's caching host allocator and is returned as a numpy view of it (the 2-D
+        # path does the same): no pageable staging copy, no second 512 MB memcpy into a freshly zero-paged array.
+        out = torch.empty(tuple(tomo.shape), dtype=torch.float32, pin_memory=out_d.is_cuda)
+        out.copy_(out_d, non_blocking=True)
+        if out_d.is_cuda:
+            torch.cuda.current_stream().synchronize()
+        res = out.numpy()
+        return res if tomo.dtype == np.float32 else res.astype(tomo.dtype)
 
 
 def denoise_image(mic: np.ndarray, models: List[Denoise], lowpass=1, cutoff=0, gaus=None, inv_gaus=None,
