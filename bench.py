@@ -141,7 +141,7 @@ def main():
     ap.add_argument('--variant', default='auto', choices=['auto', 'v1', 'v2'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--extras', default='cfg3,cfg4,cfg5,lib',
-                    help='secondary BASELINE workloads folded into the line\'s `extra` block (comma list of cfg3,cfg4,cfg4bn,cfg5,lib; "none" to skip)')
+                    help='secondary BASELINE workloads folded into the line\'s `extra` block (comma list of cfg3,cfg4,cfg4bn,cfg4u64,cfg5,lib; "none" to skip)')
     ap.add_argument('--tomo', type=int, default=512, help='cfg5 tomogram edge (512 = the full BASELINE size: 216 patches of 192^3)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
@@ -251,6 +251,8 @@ def main():
                 extra['cfg4_ge_binomial_train'] = cfg4_train(ctx, steps=40)
             elif name == 'cfg4bn':
                 extra['cfg4_ge_binomial_train_bn'] = cfg4_train(ctx, steps=40, bn=True)
+            elif name == 'cfg4u64':
+                extra['cfg4_ge_binomial_train_u64'] = cfg4_train(ctx, steps=20, units=64)
             elif name == 'cfg5':
                 extra['cfg5_unet3d_denoise'] = cfg5_denoise3d(ctx, size=args.tomo)
             elif name == 'lib' and world == 1:
@@ -303,6 +305,12 @@ def main():
             c4 = extra.get('cfg4_ge_binomial_train')
             if c4 and 'train_step_u32' in lib:
                 sp['ge_binomial_train_step'] = lib['train_step_u32']['ms'] / c4['ms_per_step']
+            c4b = extra.get('cfg4_ge_binomial_train_bn')
+            if c4b and 'train_step_u32_bn' in lib:
+                sp['ge_binomial_train_step_bn'] = lib['train_step_u32_bn']['ms'] / c4b['ms_per_step']
+            c4u = extra.get('cfg4_ge_binomial_train_u64')
+            if c4u and 'train_step_u64' in lib:
+                sp['ge_binomial_train_step_u64'] = lib['train_step_u64']['ms'] / c4u['ms_per_step']
             c5 = extra.get('cfg5_unet3d_denoise')
             if c5 and 'ms' in lib.get('unet3d_192_patch', {}):
                 sp['unet3d_denoise_patch'] = lib['unet3d_192_patch']['ms'] / c5['ms_per_patch']

@@ -70,17 +70,18 @@ def main():
                                       n_gpus=world, ms_per_image=ms / args.steps, mpx_s=world * args.steps * 16.777216 / (ms / 1e3),
                                       tflops=world * args.steps * 29.458 / (ms / 1e3), launches_per_image=(ops.LAUNCH_COUNT - l0) / args.steps,
                                       finite=bool(np.isfinite(y).all()))))
-        elif wl in ('train', 'train_tf32', 'train_bn'):
+        elif wl in ('train', 'train_tf32', 'train_bn', 'train_u64'):
             from topaz_b200 import train_engine as _T
             _T.set_tf32(wl == 'train_tf32')
             from topaz_b200.methods import GE_binomial
             from topaz_b200.model.factory import get_feature_extractor
             from topaz_b200.model.classifier import LinearClassifier
-            m = LinearClassifier(get_feature_extractor('resnet8', units=32, bn=wl == 'train_bn'))
+            units = 64 if wl == 'train_u64' else 32
+            m = LinearClassifier(get_feature_extractor('resnet8', units=units, bn=wl == 'train_bn'))
             if wl == 'train_bn':      # the default `topaz train` model (BatchNorm on, no packaged weights): seeded He init
                 m.load_state_dict({k: torch.from_numpy(v) for k, v in seeded_state({k: tuple(v.shape) for k, v in m.state_dict().items()}, 401).items()})
             else:
-                m.load_state_dict({k: torch.from_numpy(v) for k, v in weights_of(gold('resnet8_u32_pretrained')).items()})
+                m.load_state_dict({k: torch.from_numpy(v) for k, v in weights_of(gold(f'resnet8_u{units}_pretrained')).items()})
             m.cuda(); m.train()
             tr = GE_binomial(m, torch.optim.Adam(m.parameters(), lr=2e-4), nn.BCEWithLogitsLoss(), 0.035)
             B = 256; b = B // world

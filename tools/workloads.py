@@ -282,8 +282,8 @@ def gpu_library_baseline(ctx: Ctx, with_3d: bool = True):
     if with_3d:
         best(lambda: T.unet(48, 7, 3, 3), torch.randn(1, 1, 192, 192, 192, device='cuda'), 'unet3d_192_patch', ('mvox_s', 7.077888), reps=2)
     X = torch.randn(256, 71, 71, device='cuda'); Y = torch.zeros(256, device='cuda'); Y[:16] = 1
-    for bn in (False, True):
-        net = T.TrainNet(32, bn=bn).cuda()
+    for units, bn in ((32, False), (32, True), (64, False)):
+        net = T.TrainNet(units, bn=bn).cuda()
         opt = torch.optim.Adam(net.parameters(), lr=2e-4)
 
         def step():
@@ -293,7 +293,7 @@ def gpu_library_baseline(ctx: Ctx, with_3d: bool = True):
             opt.step(); opt.zero_grad()
             return loss.item()      # the reference syncs every step (methods.py:148-165)
         ms = T.time_it(step, warm=5, reps=20)
-        out['train_step_u32' + ('_bn' if bn else '')] = dict(ms=ms, crops_s=256 / (ms / 1e3), note='simplified loss (BCE + sigmoid sum): the GE term adds ~25 ATen launches and a CPU scipy call in the reference')
+        out[f'train_step_u{units}' + ('_bn' if bn else '')] = dict(ms=ms, crops_s=256 / (ms / 1e3), note='simplified loss (BCE + sigmoid sum): the GE term adds ~25 ATen launches and a CPU scipy call in the reference')
         del net, opt
     torch.cuda.empty_cache()
     out['clocks'] = clk.finish()

@@ -884,7 +884,7 @@ __global__ void __launch_bounds__(kHaloThreadsW, 1) conv_halo_tc_kernel(const __
 //     a_hi x [b_hi ; b_lo] (N = 128 -> columns [main 64 | small 64]),  a_lo x b_hi (N = 64 -> small).
 // The weights (9 taps x 32 KB with the lo planes) do not fit beside the tile: warp 9 streams them per tap through a 3-slot TMA
 // ring, every tile.  One smem stage and one TMEM stage (a CTA sees one or two tiles).
-constexpr int kH64Rows = 224;                      // 128 outputs + up to 96 rows of halo (33 x 33 maps with dilation 1, 11 x 11 with 2)
+constexpr int kH64Rows = 256;                      // 128 outputs + up to 128 rows of halo (31 x 31 maps with dilation 2, 33 x 33 with 1)
 constexpr int kH64Plane = kH64Rows * 128;
 constexpr int kH64Stage = 4 * kH64Plane;              // chunk 0 hi | chunk 0 lo | chunk 1 hi | chunk 1 lo
 constexpr int kH64WSlot = 32768;                      // one tap: chunk 0 (hi 64 x 128 B | lo) | chunk 1 (hi | lo)
