@@ -113,7 +113,6 @@ __global__ void __launch_bounds__(128, MINB) first_tc_kernel(const FirstArgs a) 
       if (i < PH * PW) { const int wy = i / PW; sImg[wy * PWP + (i - wy * PW)] = pre[e]; }
     }
     __syncthreads();
-    if (tile + gridDim.x < ntiles) load_window(tile + gridDim.x);
     // 2. this pixel's im2col row (the A tile was last read by the previous tile's MMAs, whose completion every thread
     //    waited for before its epilogue)
     {
@@ -144,6 +143,9 @@ __global__ void __launch_bounds__(128, MINB) first_tc_kernel(const FirstArgs a) 
     ptx::fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
     ptx::tc_fence_before();
     __syncthreads();
+    // the next window is requested only now: fence.proxy.async is MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC in SASS, and the membar would wait
+    // for loads issued before it (they now fly during this tile's MMAs and epilogue instead)
+    if (tile + gridDim.x < ntiles) load_window(tile + gridDim.x);
     // 3. MMAs of this tile
     if (warp == 0) {
       ptx::tc_fence_after();

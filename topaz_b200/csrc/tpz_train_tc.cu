@@ -275,10 +275,13 @@ __global__ void __launch_bounds__(256, 2) conv_tc_kernel(const __grid_constant__
         *reinterpret_cast<float4*>(rl + ((cc ^ sw) << 4)) = lo;
       }
     }
-    if (kc + kPF < nk) load_chunk(cur);                     // flies during the next kPF chunks
+    // fence.proxy.async compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC: the membar waits for every memory operation this thread has
+    // in flight, so a prefetch issued BEFORE it is not a prefetch (measured: ~3 us per chunk, the full gather latency).  The next
+    // loads are therefore issued after the fence and the barrier.
     ptx::fence_proxy_async();
     ptx::tc_fence_before();
     __syncthreads();
+    if (kc + kPF < nk) load_chunk(cur);                     // flies during the MMA issue and the next chunk's staging
     if (warp == 0) {
       ptx::tc_fence_after();
       mbar_wait(&bar_b[kc % 3], (kc / 3) & 1);
@@ -521,10 +524,10 @@ __global__ void __launch_bounds__(256, 2) wgrad_tc_kernel(const WgArgs a) {
         put(bh + B_BYTES, r, lo.x); put(bh + B_BYTES, r + 1, lo.y); put(bh + B_BYTES, r + 2, lo.z); put(bh + B_BYTES, r + 3, lo.w);
       }
     }
-    if (kc + kPFW < nchunks) load_chunk(curx, cury);
-    ptx::fence_proxy_async();
+    ptx::fence_proxy_async();                               // see conv_tc_kernel: no loads may be in flight across this fence
     ptx::tc_fence_before();
     __syncthreads();
+    if (kc + kPFW < nchunks) load_chunk(curx, cury);
     if (warp == 0) {
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
