@@ -249,6 +249,11 @@ def main():
                 extra['cfg3_unet2d_denoise'] = cfg3_denoise2d(ctx, steps=4)
             elif name == 'cfg4':
                 extra['cfg4_ge_binomial_train'] = cfg4_train(ctx, steps=40)
+                if world > 1:      # the same step at 256 crops per GPU: separates the collectives' cost from the shrinking shard
+                    try:
+                        extra['cfg4_ge_binomial_train_weak'] = cfg4_train(ctx, steps=40, weak=True)
+                    except Exception as e:
+                        extra['cfg4_ge_binomial_train_weak_error'] = f'{type(e).__name__}: {str(e)[:300]}'
             elif name == 'cfg4bn':
                 extra['cfg4_ge_binomial_train_bn'] = cfg4_train(ctx, steps=40, bn=True)
             elif name == 'cfg4u64':

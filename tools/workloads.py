@@ -162,7 +162,9 @@ def cfg3_denoise2d(ctx: Ctx, steps: int = 4, size: int = 4096):
                 kernel_launches_per_image_eager=launches, finite=bool(np.isfinite(y).all()), unit='Mpx/s', clocks=clocks)
 
 
-def cfg4_train(ctx: Ctx, steps: int = 40, bn: bool = False, units: int = 32):
+def cfg4_train(ctx: Ctx, steps: int = 40, bn: bool = False, units: int = 32, weak: bool = False):
+    """weak=True: 256 crops PER GPU (global minibatch 256 x world) -- the step's work per rank stays that of the single-GPU
+    step, so the ratio to the N=1 time isolates what the collectives and the global loss cost."""
     import torch.nn as nn
     from common import gold, weights_of, seeded_state
     from topaz_b200 import ops
@@ -176,9 +178,9 @@ def cfg4_train(ctx: Ctx, steps: int = 40, bn: bool = False, units: int = 32):
         _load(m, weights_of(gold('resnet8_u32_pretrained' if units == 32 else 'resnet8_u64_pretrained')))
     m.cuda(); m.train()
     tr = GE_binomial(m, torch.optim.Adam(m.parameters(), lr=2e-4), nn.BCEWithLogitsLoss(), 0.035)
-    B = 256
+    B = 256 * (ctx.world if weak else 1)
     b = B // ctx.world
-    Y = torch.tensor([1.0] * 16 + [0.0] * 240, dtype=torch.float64)
+    Y = torch.tensor([1.0] * (B // 16) + [0.0] * (B - B // 16), dtype=torch.float64)
     perm = torch.randperm(B, generator=torch.Generator().manual_seed(0))       # spread positives over shards
     Xs = [torch.from_numpy(np.random.default_rng(4000 + s).standard_normal((B, 71, 71)).astype(np.float32))[perm][ctx.rank * b:(ctx.rank + 1) * b].cuda()
           for s in range(4)]
@@ -216,8 +218,8 @@ def cfg4_train(ctx: Ctx, steps: int = 40, bn: bool = False, units: int = 32):
         coll = dict(grad_allreduce_us=timed(lambda: ctx.dist.all_reduce(g)), grad_bytes=int(g.numel() * 4),
                     logits_allgather_us=timed(lambda: ctx.dist.all_gather_into_tensor(gs, sc)), logits_bytes=int(gs.numel() * 4))
     return dict(workload=f'GE_binomial.step, resnet8_u{units}' + (' + BatchNorm (training mode)' if bn else '') +
-                f', global minibatch 256 crops of 71x71 = {b} per GPU, Adam, incl. the per-step 5-float host read-back',
-                metric='crops/s', unit='crops/s', n_gpus=ctx.world, scaling='strong', steps=steps, value=steps * B / (ms / 1e3),
+                f', global minibatch {B} crops of 71x71 = {b} per GPU, Adam, incl. the per-step 5-float host read-back',
+                metric='crops/s', unit='crops/s', n_gpus=ctx.world, scaling='weak' if weak else 'strong', steps=steps, value=steps * B / (ms / 1e3),
                 ms_per_step=ms / steps, kernel_launches_per_step=launches, collectives=coll,
                 tflops_algorithmic=steps * B * 3 * (59.27e-6 if units == 32 else 230.2e-6) / (ms / 1e3),
                 last_out=[float(v) for v in out], clocks=clocks)

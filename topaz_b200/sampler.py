@@ -22,6 +22,9 @@ class GpuCropSampler:
         self.device = torch.device(device)
         self.crop = int(crop_size)
         self.big = int(np.ceil(crop_size * np.sqrt(2))) if rotate else int(crop_size)   # memory_mapped_data.py:144
+        # keep (big - crop) even so that the final crop is centred on the rotation centre.  Model widths are odd (ResNet8: 71,
+        # conv31/63/127), for which this is exactly the reference's geometry (2*(size//2)+1 window); an EVEN crop size would put the
+        # rotation centre half a pixel from the reference's (statistically equivalent augmentation, not the same pixels).
         if (self.big - self.crop) % 2:
             self.big += 1
         flat, recs, set_begin, off = [], [], [0], 0
