@@ -639,8 +639,8 @@ struct HaloArgs {
   const float* bias; const float* res; int res_H, res_W, res_org, res_stride;
   const float* mask; float* out; int relu, accumulate;
   // wgrad only
-  const float* dy; float* dw; float* db; int dil, row0[3], kper;
-  int x_ld4, dy_ld4, ci_blocks, Ci_tot;   // wider layers: blockIdx.y = (32-channel block of ci, 32-channel block of co); row strides in float4   // row0[r]: source row of tap (r, 0); kper: tiles per CTA between flushes (unused)
+  const float* dy; float* dw; float* db; int dil, row0[3];   // row0[r]: source row of tap (r, 0)
+  int x_ld4, dy_ld4, ci_blocks, Ci_tot;   // wider layers: blockIdx.y = (32-channel block of ci, 32-channel block of co); row strides in float4
 };
 
 // (n, u, v) of a Z-linear position, advanced incrementally (one division pair per tile and thread instead of one per row)
@@ -1292,7 +1292,6 @@ template <int C>
 __device__ __forceinline__ void first_load_taps(const float* __restrict__ xb, int W, bool ok, float (&v)[32]) {
 #pragma unroll
   for (int e = 0; e < 32; ++e) {
-    constexpr int dummy = 0; (void)dummy;
     const int tap = C * 32 + e;
     v[e] = (ok && tap < kFirstTaps) ? __ldg(xb + (tap / kFirstK) * W + (tap % kFirstK)) : 0.f;
   }
