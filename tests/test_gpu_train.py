@@ -161,7 +161,7 @@ def test_conv_mma_kernels_match_fp32(N, H, Ci, Co, k, stride, dil, org):
     (40, 31, 32, 32, 3, 1, 2, 0), (3, 20, 32, 32, 3, 1, 1, 2), (2, 17, 32, 32, 1, 1, 1, 1), (1, 9, 32, 32, 3, 1, 1, 0),
     (256, 27, 32, 32, 3, 1, 1, 0),
     # one-pixel outputs (the last 5x5 layer on a training crop): split-K forward + per-tap scatter dgrad; an uncovered variant
-    (256, 5, 64, 128, 5, 1, 1, 0), (40, 6, 32, 64, 3, 1, 2, 1),
+    (256, 5, 64, 128, 5, 1, 1, 0), (40, 6, 32, 64, 3, 1, 2, 1), (70, 5, 128, 256, 5, 1, 1, 0),
     # 64-channel halo-resident kernel (streamed weights): r3.conv0 / r3.conv1 at the cfg4 minibatch, a u64 first-stage map, an origin
     (256, 11, 64, 64, 3, 1, 1, 0), (256, 9, 64, 64, 3, 1, 2, 0), (6, 33, 64, 64, 3, 1, 1, 0), (5, 14, 64, 64, 3, 1, 1, 1),
 ])

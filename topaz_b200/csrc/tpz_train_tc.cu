@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256, 2) conv_tc_kernel(const __grid_constant__
   const bool sc = MODE == 1 && a.scatter != 0;
   const long long Mtot = sc ? (long long)g.N : (long long)g.N * MH * MW;
   const long long m = (long long)blockIdx.x * 128 + row;
-  const int n0 = sc ? 0 : blockIdx.y * BN;
+  const int n0 = sc ? (int)blockIdx.z * BN : (int)blockIdx.y * BN;     // scatter: blockIdx.y is the tap, blockIdx.z the N tile
   const int cchunks = Cs >> 5;
   const bool ks = MODE == 0 && a.ksplit > 0;
   // first weight block and block count of this CTA (scatter: the blocks of tap blockIdx.y; split-K: a slice of all blocks)
@@ -1847,14 +1847,15 @@ extern "C" int tpz_conv_dgrad_tc(const float* dy, int N, int Ho, int Wo, int Co,
   }
   int grid_y = 0;
   const bool covered = org == 0 && dil == 1 && kh == H && kw == W;      // every dx pixel is reached by exactly one tap
-  if (Ho == 1 && Wo == 1 && stride == 1 && Ci == BN && org >= 0 && org + (kh - 1) * dil < H && org + (kw - 1) * dil < W &&
+  int grid_z = 1;
+  if (Ho == 1 && Wo == 1 && stride == 1 && Ci % BN == 0 && org >= 0 && org + (kh - 1) * dil < H && org + (kw - 1) * dil < W &&
       (covered || !(accumulate && relu_mask)) && scatter_dgrad_enabled()) {
     // one source pixel per image: dx pixel (org + r*dil, org + t*dil) = dy x w[r][t]; a GEMM with M = images per tap
     a.scatter = 1; a.lat = 1; a.lat0 = 0;
-    M = N; grid_y = kh * kw;
+    M = N; grid_y = kh * kw; grid_z = Ci / BN;
     if (!accumulate && !covered) TPZ_CUDA(cudaMemsetAsync(dx, 0, (size_t)N * H * W * Ci * sizeof(float), ST(stream)));
   }
-  return BN == 64 ? launch_conv_tc<64, 1>(a, M, Ci, ST(stream), grid_y) : launch_conv_tc<32, 1>(a, M, Ci, ST(stream), grid_y);
+  return BN == 64 ? launch_conv_tc<64, 1>(a, M, Ci, ST(stream), grid_y, grid_z) : launch_conv_tc<32, 1>(a, M, Ci, ST(stream), grid_y, grid_z);
 }
 
 extern "C" int tpz_conv_wgrad_tc(const float* x, int N, int H, int W, int Ci, const float* dy, int Ho, int Wo, int Co, int kh,
