@@ -358,3 +358,30 @@ def test_preprocess_downsample_and_gmm_normalize_host_logic():
             assert y.dtype == np.float32 and np.abs(y - g[f'n.{tag}.y']).max() < 1e-3
             ya, mda = stats.normalize(img, method='affine')
             assert abs(mda['mu'] - img.astype(np.float64).mean()) < 1e-4 and mda['pi'] == 1
+
+
+def test_mn_major_tf32_operand_layout_matches_the_b200_probe():
+    """Hardware fact 6 as a fixture: `tests/golden/lab_mn_major_b200.json` holds, for 15 descriptor settings, the
+    shared-memory word every (row, k) of an MN-major `kind::tf32` operand was READ from on a B200 (`tools/lab_mn_major.py`, one raw
+    tcgen05.mma per setting against an identity operand).  The address rule the halo-resident weight-gradient kernels rely on --
+    SWIZZLE_128B_BASE32B: byte = start + (m / 32) * LBO + (k / 4) * SBO + (k % 4) * 128 + (m % 32) * 4, 32-byte pieces XOR-ed with
+    bits 7-8 of the address, any start row, overlapping MN atoms allowed -- reproduces every recorded address; the ordinary 128-byte
+    swizzle (layout type 2) read nothing (all zeros)."""
+    import json, re
+    rec = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'lab_mn_major_b200.json')))
+    window = 2048                                      # floats of the probe's index image that are exact in tf32
+    swz32 = lambda a: a ^ (((a >> 7) & 3) << 5)
+    checked = 0
+    for name, r in rec.items():
+        p = {k: int(v) for k, v in re.findall(r'(\w+)=(\d+)', name)}
+        got = np.array(r['got'])
+        if p.get('layout') == 2:
+            assert (got == -1).all()                   # D was all zero: the layout is not readable MN-major for 32-bit operands
+            continue
+        rows = got.shape[0]                            # A: 128 rows (M), B: N rows
+        hyp = np.array([[swz32(p['start'] + (m >> 5) * p['lbo'] + (k >> 2) * p['sbo'] + (k & 3) * 128 + (m & 31) * 4) // 4
+                         for k in range(8)] for m in range(rows)])
+        hyp[hyp >= window] = -1
+        assert np.array_equal(got, hyp), name
+        checked += 1
+    assert checked == 15
