@@ -145,6 +145,58 @@ int tpz_model_step_buffers(const TpzModel* model, int step, void* weights_out, l
 /* Test hook: copy of the argument block conv step `step` was last launched with. */
 int tpz_model_step_args(const TpzModel* model, int step, TpzTcConvArgs* out);
 
+/* ---- model-level entry points, part 2: the U-Net denoisers as one handle (tpz_unet2d_forward / tpz_unet3d_forward) ----
+ * What a non-Python host binds to denoise micrograph patches / tomogram patches: topaz/denoise.py:274-296 (Denoise._denoise:
+ * normalise, model forward, de-normalise) over topaz/denoising/models.py:74-175 (UDenoiseNet), :178-244 (UDenoiseNetSmall) and
+ * :452-564 (UDenoiseNet3D).  The description lists the network's convolutions in the reference's own parameter layout (fp32
+ * OIHW / OIDHW, DEVICE pointers; state_dict keys enc{i}.0.*, dec{l}.{0,2}.*, dec1.4.*): enc{i} = conv + LeakyReLU (+ MaxPool(2)
+ * for i < depth), dec{l} = two convs over cat[nearest-upsampled, skip p_{l-1}] (level 1: the raw image), dec1.4 the Cout = 1 tail.
+ * tpz_unet_create reads the weights once (one synchronising device-to-host copy), builds the k-block plans -- including the per-phase
+ * plans of the fused nearest-2x up-sampling -- and keeps the packed fp16 weights in the handle; activations live in the caller's
+ * workspace.  Default ("fast") precision only: fp16 operands, fp32 accumulation.  One stream at a time per handle.
+ * Returns TPZ_E_WEIGHT_RANGE / 3 like tpz_model_create. */
+#define TPZ_UNET_MAX_DEPTH 8
+typedef struct {
+  const float *w, *b;        /* [cout][cin][k]^dims fp32, bias [cout] (b may be NULL) */
+  int cout, cin, k;
+} TpzConvDesc;
+typedef struct {
+  int dims;                  /* 2 or 3 */
+  int depth;                 /* encoder stages: 6 (UDenoiseNet, UDenoiseNet3D), 4 (UDenoiseNetSmall) */
+  TpzConvDesc enc[TPZ_UNET_MAX_DEPTH];     /* enc[i-1] = enc{i}.0 */
+  TpzConvDesc dec_a[TPZ_UNET_MAX_DEPTH];   /* dec_a[l] = dec{l}.0, l = 1 .. depth-1 (entry 0 unused) */
+  TpzConvDesc dec_b[TPZ_UNET_MAX_DEPTH];   /* dec_b[l] = dec{l}.2 */
+  TpzConvDesc last;          /* dec1.4 */
+  float slope;               /* LeakyReLU slope (0.1) */
+  int host_weights;          /* test handles only: the pointers above are HOST pointers, the packed buffers stay on the host and the
+                                handle runs only under tpz_unet_set_launch_hook */
+} TpzUnetDesc;
+typedef struct TpzUnet TpzUnet;
+int tpz_unet_create(const TpzUnetDesc* desc, TpzUnet** out, void* stream);
+int tpz_unet_destroy(TpzUnet* model);
+/* Bytes of DEVICE workspace (256-byte aligned) a forward of N patches of D x H x W needs (2-D: D = 1); -1 if the patch is smaller
+ * than the pooling stages allow.  tpz_unet_launch_count: kernels launched by that forward. */
+long long tpz_unet_workspace_bytes(const TpzUnet* model, int N, int D, int H, int W);
+int tpz_unet_launch_count(const TpzUnet* model, int N, int D, int H, int W);
+/* y = model(x), x and y dense fp32 DEVICE [B][H][W] / [B][D][H][W].  denorm_stats (device float[2] = mean, std; may be NULL): the
+ * output is de-normalised, y*std + mean, inside the last kernel (denoise.py:295).  Asynchronous on `stream`. */
+int tpz_unet2d_forward(TpzUnet* model, const float* x, int B, int H, int W, const float* denorm_stats, float* y, void* workspace,
+                       long long workspace_bytes, void* stream);
+int tpz_unet3d_forward(TpzUnet* model, const float* x, int B, int D, int H, int W, const float* denorm_stats, float* y,
+                       void* workspace, long long workspace_bytes, void* stream);
+/* Test hooks.  tpz_unet_set_launch_hook(fn, user): every kernel launch of the U-Net entry points is handed to fn(user, op, args)
+ * instead of the device (fn = NULL restores the device path) -- tests/test_unet_abi.py runs the whole C++ launch sequence on the CPU
+ * simulation of the kernels this way.  args is a TpzTcConvArgs for TPZ_OP_TC_CONV and a TpzOpArgs otherwise, with the callee's
+ * arguments in declaration order: pointers in p[], ints in i[], floats in f[] (the one long long in n).
+ * tpz_unet_plan: the static argument block (weights / bias pointing at the handle's packed buffers) of one plan; which: 0 = first-layer
+ * GEMM, 1 = enc{index+2}, 2 = dec{index}.0, 3 = dec{index}.2, 4 = phase plan `phase` of dec{index}.0, 5 = tensor-core Cout = 1 tail. */
+enum { TPZ_OP_RANGE_SCALE = 0, TPZ_OP_CONV_FIRST_TC = 1, TPZ_OP_IM2COL_FIRST = 2, TPZ_OP_IM2COL3D_FIRST = 3, TPZ_OP_CONV_FIRST = 4,
+       TPZ_OP_TC_CONV = 5, TPZ_OP_MAXPOOL2 = 6, TPZ_OP_UPSAMPLE = 7, TPZ_OP_CONV_LAST = 8 };
+typedef struct { const void* p[6]; long long n; int i[16]; float f[4]; } TpzOpArgs;
+typedef int (*tpz_launch_hook)(void* user, int op, const void* args);
+int tpz_unet_set_launch_hook(tpz_launch_hook fn, void* user);
+int tpz_unet_plan(const TpzUnet* model, int which, int index, int phase, TpzTcConvArgs* args, long long* weight_elems);
+
 /* ---- direct (SIMT) convolutions for the thin ends and for validation ----
  * tpz_conv_first: Cin = 1 conv from a dense fp32 image, fp32 math, fused bias + activation, fp16 NDHWC out.
  *   Replaces the first BasicConv 7x7 (resnet.py:66,102), conv31/63/127 layer 0 (basic.py:47-52) and the

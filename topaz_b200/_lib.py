@@ -42,6 +42,24 @@ class TpzLayerDesc(C.Structure):
                 ('eps1', C.c_float)]
 
 
+class TpzConvDesc(C.Structure):
+    _fields_ = [('w', C.c_void_p), ('b', C.c_void_p), ('cout', C.c_int), ('cin', C.c_int), ('k', C.c_int)]
+
+
+TPZ_UNET_MAX_DEPTH = 8
+
+
+class TpzUnetDesc(C.Structure):
+    _fields_ = [('dims', C.c_int), ('depth', C.c_int), ('enc', TpzConvDesc * TPZ_UNET_MAX_DEPTH), ('dec_a', TpzConvDesc * TPZ_UNET_MAX_DEPTH),
+                ('dec_b', TpzConvDesc * TPZ_UNET_MAX_DEPTH), ('last', TpzConvDesc), ('slope', C.c_float), ('host_weights', C.c_int)]
+
+
+class TpzOpArgs(C.Structure):
+    _fields_ = [('p', C.c_void_p * 6), ('n', C.c_longlong), ('i', C.c_int * 16), ('f', C.c_float * 4)]
+
+
+LAUNCH_HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p)
+
 _lib = None
 
 _I, _F, _P, _LL, _D = C.c_int, C.c_float, C.c_void_p, C.c_longlong, C.c_double
@@ -60,6 +78,14 @@ _PROTOS = {
     'tpz_model_step_args': (_I, [_P, _I, C.POINTER(TpzTcConvArgs)]),
     'tpz_workspace_bytes': (_LL, [_P, _I, _I, _I]),
     'tpz_resnet_dense_forward': (_I, [_P, _P, _I, _I, _I, _P, _P, _LL, _P]),
+    'tpz_unet_create': (_I, [C.POINTER(TpzUnetDesc), C.POINTER(C.c_void_p), _P]),
+    'tpz_unet_destroy': (_I, [_P]),
+    'tpz_unet_workspace_bytes': (_LL, [_P, _I, _I, _I, _I]),
+    'tpz_unet_launch_count': (_I, [_P, _I, _I, _I, _I]),
+    'tpz_unet2d_forward': (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _LL, _P]),
+    'tpz_unet3d_forward': (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _LL, _P]),
+    'tpz_unet_set_launch_hook': (_I, [LAUNCH_HOOK, _P]),
+    'tpz_unet_plan': (_I, [_P, _I, _I, _I, C.POINTER(TpzTcConvArgs), C.POINTER(_LL)]),
     'tpz_conv_first': (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P, _I, _P, _I, _P]),
     'tpz_range_scale': (_I, [_P, _LL, _P, _P, _P]),
     'tpz_im2col_first': (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P]),

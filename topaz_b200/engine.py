@@ -48,6 +48,10 @@ RANGE_GUARD = os.environ.get('TPZ_RANGE_GUARD', '1') != '0'
 # Dense classifier forward through the model-level C ABI (csrc/tpz_model.cu: plans + on-device weight repack in C++);
 # 'py' keeps the Python-built plans (same kernels, same packed bytes).  Strict precision always uses the Python plans.
 DENSE_ENGINE = os.environ.get('TPZ_DENSE_ENGINE', 'c')
+# U-Net denoiser forward through the model-level C ABI (csrc/tpz_unet.cu: tpz_unet2d_forward / tpz_unet3d_forward): opt-in with
+# TPZ_UNET_ENGINE=c.  Same kernels, same packed bytes and the same launch sequence as the Python plans (tests/test_unet_abi.py
+# holds them bit-identical on the CPU simulation of the kernels); 'py' stays the default until the C path has run on hardware.
+UNET_ENGINE = os.environ.get('TPZ_UNET_ENGINE', 'py')
 
 
 def _rup(c: int, m: int = 32) -> int:
@@ -536,12 +540,41 @@ def _build_unet_plan(model, device):
     return plan
 
 
+def _unet_c_model(model, key):
+    """The denoiser's native handle (model_abi.UnetModel), or None where only the Python plans apply: split-operand layers
+    (strict precision, the 3-D `auto` mode), a non-default kernel selection, or a weight row that needs the row-scaled plans."""
+    from .model_abi import UnetModel, WeightRangeError
+    cache = model.__dict__.setdefault('_tpz_plans', {})
+    hit = cache.get('unet_c')
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    if hit is not None and hit[1] is not None:
+        hit[1].close()
+    um = None
+    depth = sum(1 for i in range(1, 10) if hasattr(model, f'enc{i}'))
+    dims = 3 if isinstance(model.enc1[0], nn.Conv3d) else 2
+    defaults = RANGE_GUARD and UP2_FUSED and FIRST_FUSED and LAST_MODE == 'auto' and ops.TC_VARIANT == 'auto'
+    if defaults and not _unet_precision(dims, depth)[0]:
+        try:
+            um = UnetModel(model)
+        except (WeightRangeError, NotImplementedError):
+            um = None
+    cache['unet_c'] = (key, um)
+    return um
+
+
 def unet_forward(model, x: torch.Tensor, denorm_stats: Optional[torch.Tensor] = None) -> torch.Tensor:
     """UDenoiseNet(3D).forward (reference denoising/models.py:130-175, 508-564).
     x: fp32 [N,1,(D),H,W] on device.  If ``denorm_stats`` (device float[2]) is given the output is
     de-normalised (y*std+mean) inside the last kernel (denoise.py:295)."""
     ops.require_cuda(x, 'denoiser input')
     key = _state_key(model, ('unet', str(x.device)))
+    if UNET_ENGINE == 'c':
+        um = _unet_c_model(model, key)
+        if um is not None:
+            if x.dim() != um.dims + 2 or x.shape[1] != 1:
+                raise ValueError(f'topaz_b200: expected input [N,1,{"D,H,W" if um.dims == 3 else "H,W"}], got {tuple(x.shape)}')
+            return um.forward(x, denorm_stats)
     plan = _cached(model, 'unet', key, lambda: _build_unet_plan(model, x.device))
     dims = plan['dims']
     if x.dim() != dims + 2 or x.shape[1] != 1:

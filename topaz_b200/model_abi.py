@@ -158,3 +158,116 @@ class DenseModel:
             self.close()
         except Exception:
             pass
+
+
+class UnetModel:
+    """A U-Net denoiser (UDenoiseNet / UDenoiseNetSmall / UDenoiseNet3D drop-in) as one native handle (csrc/tpz_unet.cu):
+    ``tpz_unet_create`` reads the convolutions in the reference's own layout and builds every plan in C++;
+    ``forward`` is one ``tpz_unet2d_forward`` / ``tpz_unet3d_forward`` call on a caller-owned workspace.
+    ``engine.unet_forward`` routes through it with TPZ_UNET_ENGINE=c (default precision only); the Python-built plans stay the
+    default path until this one has been run on hardware.  ``host=True`` builds a test handle on HOST tensors that runs only
+    under the launch hook (tests/test_unet_abi.py)."""
+
+    def __init__(self, model: nn.Module, host: bool = False):
+        self.model = model
+        self.host = host
+        self.handle = C.c_void_p()
+        self._ws = None
+        desc, keep = self.describe(model, host)
+        self.dims, self.depth = desc.dims, desc.depth
+        s = None if host else C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        rc = _lib.lib().tpz_unet_create(C.byref(desc), C.byref(self.handle), s)
+        if rc == E_WEIGHT_RANGE:
+            raise WeightRangeError(_lib.lib().tpz_last_error().decode())
+        check(rc)
+        del keep          # the library has copied every parameter
+
+    @staticmethod
+    def describe(model: nn.Module, host: bool = False):
+        """(TpzUnetDesc, keep-alive tensors) for the model's current parameters (enc{i}.0, dec{l}.{0,2}, dec1.4)"""
+        enc = [getattr(model, f'enc{i}') for i in range(1, 10) if hasattr(model, f'enc{i}')]
+        depth = len(enc)
+        dims = 3 if isinstance(enc[0][0], nn.Conv3d) else 2
+        if not 2 <= depth <= _lib.TPZ_UNET_MAX_DEPTH:
+            raise NotImplementedError(f'topaz_b200: U-Net depth {depth} in the C model')
+        for i, e in enumerate(enc, 1):
+            pooled = any(isinstance(c, (nn.MaxPool2d, nn.MaxPool3d)) for c in e)
+            if pooled != (i < depth):
+                raise NotImplementedError('topaz_b200: the C U-Net expects MaxPool(2) after every encoder stage but the last')
+        keep = []
+        desc = _lib.TpzUnetDesc()
+        desc.dims, desc.depth, desc.slope, desc.host_weights = dims, depth, 0.1, int(host)
+
+        def fill(d, conv):
+            w = _f32(conv.weight)
+            b = _f32(conv.bias)
+            if host:
+                w, b = w.cpu(), (b.cpu() if b is not None else None)
+            keep.extend([w, b])
+            if len(set(w.shape[2:])) != 1:
+                raise NotImplementedError('topaz_b200: the C U-Net expects cubic kernels')
+            d.w, d.b = w.data_ptr(), (b.data_ptr() if b is not None else None)
+            d.cout, d.cin, d.k = w.shape[0], w.shape[1], w.shape[-1]
+        for i, e in enumerate(enc):
+            fill(desc.enc[i], e[0])
+        for l in range(depth - 1, 0, -1):
+            dec = getattr(model, f'dec{l}')
+            fill(desc.dec_a[l], dec[0])
+            fill(desc.dec_b[l], dec[2])
+        fill(desc.last, model.dec1[4])
+        return desc, keep
+
+    def workspace_bytes(self, shape) -> int:
+        N, D, H, W = shape
+        need = _lib.lib().tpz_unet_workspace_bytes(self.handle, N, D, H, W)
+        if need < 0:
+            raise RuntimeError('topaz_b200: patch smaller than the U-Net pooling stages allow')
+        return int(need)
+
+    def launch_count(self, shape) -> int:
+        N, D, H, W = shape
+        return int(_lib.lib().tpz_unet_launch_count(self.handle, N, D, H, W))
+
+    def forward(self, x: torch.Tensor, denorm_stats=None, workspace=None) -> torch.Tensor:
+        """x: fp32 [N, 1, (D,) H, W] contiguous (device; host for a test handle) -> same shape"""
+        xi = x[:, 0].contiguous().float()
+        shape = (xi.shape[0], 1, xi.shape[1], xi.shape[2]) if self.dims == 2 else tuple(xi.shape)
+        N, D, H, W = shape
+        need = self.workspace_bytes(shape)
+        # under CUDA-graph capture the workspace must belong to the graph's own pool (its address is baked into the captured
+        # launches; a cached buffer could be re-sized -- freed -- by a later, larger patch shape while the graph still replays)
+        capturing = x.is_cuda and torch.cuda.is_current_stream_capturing()
+        ws = workspace if workspace is not None else (None if capturing else self._ws)
+        if ws is None or ws.numel() < need or ws.device != x.device:
+            raw = torch.empty(need + 256, dtype=torch.uint8, device=x.device)
+            off = (-raw.data_ptr()) % 256          # the library asks for 256-byte alignment (host allocations give 64)
+            ws = raw[off:off + need]
+            if workspace is None and not capturing:
+                self._ws = ws
+        y = torch.empty_like(xi)
+        lib = _lib.lib()
+        s = None if self.host else C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if self.dims == 2:
+            check(lib.tpz_unet2d_forward(self.handle, _ptr(xi), N, H, W, _ptr(denorm_stats), _ptr(y), _ptr(ws), ws.numel(), s))
+        else:
+            check(lib.tpz_unet3d_forward(self.handle, _ptr(xi), N, D, H, W, _ptr(denorm_stats), _ptr(y), _ptr(ws), ws.numel(), s))
+        ops._count(self.launch_count(shape))
+        return y[:, None]
+
+    def plan(self, which: int, index: int = 0, phase: int = 0):
+        """(static TpzTcConvArgs, packed weight element count) of one plan (test hook, see tpz_unet_plan)"""
+        a = _lib.TpzTcConvArgs()
+        n = C.c_longlong()
+        check(_lib.lib().tpz_unet_plan(self.handle, which, index, phase, C.byref(a), C.byref(n)))
+        return a, int(n.value)
+
+    def close(self):
+        if self.handle:
+            _lib.lib().tpz_unet_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
