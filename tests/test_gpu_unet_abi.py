@@ -86,3 +86,53 @@ def test_patched_denoise_through_the_c_handle_with_graph_replay(c_engine):
     y_c2 = d_c.denoise(img, patch_size=64, padding=24)          # second pass: graph replays only
     assert d_c.model.__dict__['_tpz_plans']['unet_c'][1] is not None
     assert np.array_equal(y_c, y_py) and np.array_equal(y_c2, y_py)
+
+
+def _write_unet_file(path, model, x, y_ref, tol):
+    """serialise a denoiser + patch + expected output the way tests/c/denoise_c.c reads them"""
+    import struct
+    from torch import nn
+    enc = [getattr(model, f'enc{i}') for i in range(1, 10) if hasattr(model, f'enc{i}')]
+    depth = len(enc)
+    dims = 3 if isinstance(enc[0][0], nn.Conv3d) else 2
+    convs = [e[0] for e in enc]
+    for l in range(depth - 1, 0, -1):
+        convs += [getattr(model, f'dec{l}')[0], getattr(model, f'dec{l}')[2]]
+    convs.append(model.dec1[4])
+    out = [struct.pack('<2i', dims, depth)]
+    for c in convs:
+        w = c.weight.detach().cpu().float()
+        out.append(struct.pack('<4i', w.shape[0], w.shape[1], w.shape[-1], int(c.bias is not None)))
+        out.append(w.numpy().astype('<f4').tobytes())
+        if c.bias is not None:
+            out.append(c.bias.detach().cpu().float().numpy().astype('<f4').tobytes())
+    x = np.ascontiguousarray(x, dtype='<f4')
+    shape = (1, 1) + x.shape if dims == 2 else (1,) + x.shape
+    out.append(struct.pack('<4i', *shape)); out.append(struct.pack('<f', tol))
+    out.append(x.tobytes()); out.append(np.ascontiguousarray(y_ref, dtype='<f4').tobytes())
+    with open(path, 'wb') as fh:
+        fh.write(b''.join(out))
+
+
+def test_plain_c_program_denoises_the_reference_golden(tmp_path):
+    """tests/c/denoise_c.c: mean/std, normalise, tpz_unet2d_forward with the de-normalising epilogue, against the reference's own
+    Denoise._denoise output (golden y_call) -- no Python, no torch in that process."""
+    import os
+    import subprocess
+    from common import ROOT
+    from topaz_b200.denoising.models import UDenoiseNet, UDenoiseNetSmall
+    exe = os.path.join(ROOT, 'build', 'denoise_c')
+    if not os.path.exists(exe):
+        import __graft_entry__ as ge
+        ge.build_c_tests()
+    for name, make in (('unet_pretrained', lambda: UDenoiseNet(base_width=11, top_width=5)),
+                       ('unet_small_pretrained', lambda: UDenoiseNetSmall(width=11, top_width=5))):
+        g = gold(name)
+        m = make()
+        m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in weights_of(g).items()})
+        path = str(tmp_path / f'{name}.bin')
+        _write_unet_file(path, m, g['img'], g['y_call'], 1e-3)
+        env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, 'topaz_b200') + ':' + os.environ.get('LD_LIBRARY_PATH', ''))
+        r = subprocess.run([exe, path], capture_output=True, text=True, env=env, timeout=300)
+        print(r.stdout.strip(), r.stderr.strip())
+        assert r.returncode == 0, (name, r.returncode, r.stdout, r.stderr)

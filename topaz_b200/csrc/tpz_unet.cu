@@ -38,6 +38,7 @@ void* g_hook_user = nullptr;
 // where the handle's packed buffers live: device memory, or (test handles, TpzUnetDesc.host_weights) plain host memory
 struct Mem {
   bool host = false;
+  cudaStream_t st = nullptr;     // uploads are ordered on the caller's stream (and complete before upload() returns)
   void* alloc(size_t bytes) const {
     void* p = nullptr;
     if (host) return malloc(bytes ? bytes : 1);
@@ -46,7 +47,7 @@ struct Mem {
   void release(void* p) const { if (host) free(p); else cudaFree(p); }
   bool upload(void* dst, const void* src, size_t bytes) const {
     if (host) { memcpy(dst, src, bytes); return true; }
-    return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st) == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess;
   }
 };
 
@@ -710,6 +711,7 @@ extern "C" int tpz_unet_create(const TpzUnetDesc* desc, TpzUnet** out, void* str
   TpzUnet* m = new (std::nothrow) TpzUnet();
   TPZ_CHECK(m != nullptr, "tpz_unet_create: out of memory");
   m->mem.host = desc->host_weights != 0;
+  m->mem.st = ST(stream);
   m->dims = desc->dims; m->depth = desc->depth; m->slope = desc->slope;
   const int rc = build_unet(m, desc, ST(stream));
   if (rc) { free_unet(m); return rc; }
