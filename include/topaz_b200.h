@@ -153,9 +153,12 @@ int tpz_model_step_args(const TpzModel* model, int step, TpzTcConvArgs* out);
  * for i < depth), dec{l} = two convs over cat[nearest-upsampled, skip p_{l-1}] (level 1: the raw image), dec1.4 the Cout = 1 tail.
  * tpz_unet_create reads the weights once (one synchronising device-to-host copy), builds the k-block plans -- including the per-phase
  * plans of the fused nearest-2x up-sampling -- and keeps the packed fp16 weights in the handle; activations live in the caller's
- * workspace.  Default ("fast") precision only: fp16 operands, fp32 accumulation.  One stream at a time per handle.
+ * workspace.  One stream at a time per handle.
  * Returns TPZ_E_WEIGHT_RANGE / 3 like tpz_model_create. */
 #define TPZ_UNET_MAX_DEPTH 8
+#define TPZ_PRECISION_FAST 0
+#define TPZ_PRECISION_AUTO 1
+#define TPZ_PRECISION_STRICT 2
 typedef struct {
   const float *w, *b;        /* [cout][cin][k]^dims fp32, bias [cout] (b may be NULL) */
   int cout, cin, k;
@@ -168,6 +171,10 @@ typedef struct {
   TpzConvDesc dec_b[TPZ_UNET_MAX_DEPTH];   /* dec_b[l] = dec{l}.2 */
   TpzConvDesc last;          /* dec1.4 */
   float slope;               /* LeakyReLU slope (0.1) */
+  int precision;             /* TPZ_PRECISION_FAST: fp16 operands, fp32 accumulation (the 11-bit significand of the reference GPU
+                                path's TF32); _STRICT: every activation / weight a (hi, lo) fp16 pair, products as hi*hi + hi*lo +
+                                lo*hi (22 bits; 3x the MMAs); _AUTO: fast, except the last four convolutions of a 3-D network, where
+                                the pretrained unet-3d models cancel ~100x (the Python engine's TPZ_PRECISION default) */
   int host_weights;          /* test handles only: the pointers above are HOST pointers, the packed buffers stay on the host and the
                                 handle runs only under tpz_unet_set_launch_hook */
 } TpzUnetDesc;

@@ -61,14 +61,29 @@ def test_unet2d_c_handle_matches_python_plans_and_goldens(c_engine):
         assert torch.equal(y_c, y_py), name
 
 
-def test_unet3d_c_handle_matches_python_plans_in_fast_precision(c_engine):
+@pytest.mark.parametrize('precision', ['auto', 'fast', 'strict'])
+def test_unet3d_c_handle_matches_python_plans(precision, c_engine):
+    """auto (the 3-D default: split operands in the last four convolutions), fast and strict"""
     from topaz_b200.denoising.models import UDenoiseNet3D
-    c_engine('py', 'fast')
+    c_engine('py', precision)
     g = gold('unet3d_seeded')
     m = _load(UDenoiseNet3D(nf=48, base_width=7, top_width=3), seeded_state(unet_shapes(48, 7, 3, 3), int(g['seed'])))
     for x in (torch.from_numpy(g['x']), torch.randn(1, 1, 32, 40, 36, generator=torch.Generator().manual_seed(5))):
         y_c, y_py = _both(m, x.cuda(), c_engine)
         assert torch.equal(y_c, y_py)
+    if precision != 'fast':
+        check_parity(_both(m, torch.from_numpy(g['x']).cuda(), c_engine)[0].cpu().numpy(), g['y'], 2e-3,
+                     f'unet3d seeded {precision} (C handle)')
+
+
+def test_unet2d_strict_c_handle_matches_python_plans(c_engine):
+    from topaz_b200.denoising.models import UDenoiseNet
+    c_engine('py', 'strict')
+    g = gold('unet_pretrained')
+    m = _load(UDenoiseNet(base_width=11, top_width=5), weights_of(g))
+    y_c, y_py = _both(m, torch.from_numpy(g['xo']).cuda(), c_engine)
+    assert torch.equal(y_c, y_py)
+    check_parity(y_c.cpu().numpy(), g['yo'], 1e-3, 'unet pretrained strict (C handle)')
 
 
 def test_patched_denoise_through_the_c_handle_with_graph_replay(c_engine):

@@ -69,24 +69,24 @@ class SimHook:
             self._t(p[3], tuple(y.shape), f16).copy_(y)
         elif op == 2:
             N, H, W, k, pad, ld, out_lo = i[0:7]
-            assert out_lo == 0
-            y = sim_backend.im2col_first(_view(p[0], (N, H, W), f32), k, pad, ld, rng=rng(2))
+            assert out_lo in (0, ld)
+            y = sim_backend.im2col_first(_view(p[0], (N, H, W), f32), k, pad, ld, rng=rng(2), split=out_lo > 0)
             self._t(p[1], tuple(y.shape), f16).copy_(y)
         elif op == 3:
             N, D, H, W, k, pad, ld, out_lo = i[0:8]
-            assert out_lo == 0 and pad == k // 2
-            y = sim_backend.im2col3d_first(_view(p[0], (N, D, H, W), f32), k, ld, rng=rng(2))
+            assert out_lo in (0, ld) and pad == k // 2
+            y = sim_backend.im2col3d_first(_view(p[0], (N, D, H, W), f32), k, ld, rng=rng(2), split=out_lo > 0)
             self._t(p[1], tuple(y.shape), f16).copy_(y)
         elif op == 4:
             N, D, H, W, Co, kd, kh, kw, dil, pad, pool, out_ld, out_lo = i[0:13]
-            assert pool == 1 and out_lo == 0
+            assert pool == 1 and (out_lo == 0 or 2 * out_lo == out_ld)
             y = sim_backend.conv_first(_view(p[0], (N, D, H, W), f32), _view(p[1], (Co, kd, kh, kw), f32), _view(p[2], (Co,), f32), dil, pad,
-                                       f[0], out_ld, rng=rng(4))
+                                       f[0], out_lo if out_lo else out_ld, rng=rng(4), split=out_lo > 0)
             self._t(p[3], tuple(y.shape), f16).copy_(y)
         elif op == 6:
             N, D, H, W, Cc, ld, dims, out_ld, lo_off = i[0:9]
-            assert Cc == ld == out_ld and lo_off == 0
-            y = sim_backend.maxpool2(_view(p[0], (N, D, H, W, ld), f16), dims)
+            assert ld == out_ld and ((lo_off == 0 and Cc == ld) or (lo_off == Cc and 2 * Cc == ld))
+            y = sim_backend.maxpool2(_view(p[0], (N, D, H, W, ld), f16), dims, split=lo_off > 0)
             self._t(p[1], tuple(y.shape), f16).copy_(y)
         elif op == 7:
             N, D, H, W, Cc, ld, Do, Ho, Wo, out_ld, coff = i[0:11]
@@ -107,7 +107,9 @@ class SimHook:
         plan = plan_of_args(a)
         srcs = [self._t(a.src[s].ptr, (a.src[s].N, a.src[s].D, a.src[s].H, a.src[s].W, a.src[s].ld), f16) for s in range(a.nsrc)]
         shape = (a.N, a.Do, a.Ho, a.Wo)
-        assert not a.res and not a.oscale and a.out_lo == 0 and a.out_coff == 0
+        assert not a.res and not a.oscale and a.out_coff == 0 and a.out_lo in (0, a.Co)
+        assert a.out_ld == (2 * a.Co if a.out_lo else a.Co) or not a.out
+        plan.split_out = a.out_lo > 0
         out = self._t(a.out, shape + (a.out_ld,), f16) if a.out else None
         dot_out = _view(a.dot_out, shape, f32) if a.dot_out else None
         dot_affine = _view(a.dot_affine, (2,), f32) if a.dot_affine else None
@@ -131,7 +133,7 @@ def plan_of_args(a) -> ops.TcConvPlan:
 
 def run_c(model, x, stats=None, check_bounds=True):
     """forward of the C++ U-Net on host tensors under the simulation hook -> (y, ops launched)"""
-    um = UnetModel(model, host=True)
+    um = UnetModel(model, host=True, precision=engine.PRECISION)
     hook = SimHook()
     lib = _lib.lib()
     shape = (x.shape[0], 1, x.shape[2], x.shape[3]) if um.dims == 2 else (x.shape[0],) + tuple(x.shape[2:])
@@ -196,7 +198,7 @@ def _assert_same_plan(c_args, n_elems, py_plan, what):
 
 def _compare_all_plans(model):
     py = engine._build_unet_plan(model, 'cpu')
-    um = UnetModel(model, host=True)
+    um = UnetModel(model, host=True, precision=engine.PRECISION)
     n = 0
     if py['first_tc'] is not None and py['first_fused'] is None:
         _assert_same_plan(*um.plan(0), py['first_tc']['plan'], 'first'); n += 1
@@ -313,16 +315,18 @@ def test_unet_c_model_refuses_what_it_cannot_run():
 
 
 def test_engine_routes_unet_forward_through_the_c_handle(monkeypatch, fast_precision):
-    """engine.unet_forward with TPZ_UNET_ENGINE=c: the handle is cached per parameter state, rebuilt when a weight changes, and
-    left aside (Python plans) where split-operand layers are requested."""
-    import functools
+    """engine.unet_forward with TPZ_UNET_ENGINE=c: the handle is cached per parameter state and precision, rebuilt when a weight
+    changes, and left aside (Python plans) under a non-default kernel selection."""
     from topaz_b200 import model_abi
     from topaz_b200.denoising.models import UDenoiseNetSmall, UDenoiseNet3D
     torch.manual_seed(3)
     m = UDenoiseNetSmall(nf=16, width=7, top_width=3).eval()
     x = torch.randn(1, 1, 32, 48)
     y_py = run_py(m, x)
-    monkeypatch.setattr(model_abi, 'UnetModel', functools.partial(UnetModel, host=True))
+    class HostUnetModel(UnetModel):
+        def __init__(self, model, precision='fast'):
+            super().__init__(model, host=True, precision=precision)
+    monkeypatch.setattr(model_abi, 'UnetModel', HostUnetModel)
     monkeypatch.setattr(engine, 'UNET_ENGINE', 'c')
     hook = SimHook()
     lib = _lib.lib()
@@ -340,14 +344,130 @@ def test_engine_routes_unet_forward_through_the_c_handle(monkeypatch, fast_preci
             assert torch.equal(y2, run_py(m, x)) and not torch.equal(y2, y_c)
             with pytest.raises(ValueError):
                 engine.unet_forward(m, x[0])
-            engine.PRECISION = 'strict'                                         # split operands: only the Python plans build them
-            n_ops = len(hook.ops)
+            engine.PRECISION = 'strict'                                         # a new precision is a new handle
             ys = engine.unet_forward(m, x)
-            assert m.__dict__['_tpz_plans']['unet_c'][1] is None and len(hook.ops) == n_ops
-            assert torch.isfinite(ys).all()
-            engine.PRECISION = 'auto'                                           # 3-D auto mode splits its last four convs
+            assert m.__dict__['_tpz_plans']['unet_c'][1] is not None
+            assert torch.equal(ys, run_py(m, x)) and not torch.equal(ys, y2)
+            engine.PRECISION = 'auto'
             m3 = UDenoiseNet3D(nf=16, base_width=3, top_width=3).eval()
-            assert engine._unet_c_model(m3, 'k') is None
+            assert engine._unet_c_model(m3, 'k') is not None
+            monkeypatch.setattr(engine, 'UP2_FUSED', False)                     # non-default kernel selection: Python plans
+            n_ops = len(hook.ops)
+            yu = engine.unet_forward(m, x)
+            assert m.__dict__['_tpz_plans']['unet_c'][1] is None and len(hook.ops) == n_ops and torch.isfinite(yu).all()
     finally:
         lib.tpz_unet_set_launch_hook(C.cast(None, _lib.LAUNCH_HOOK), None)
     assert hook.error is None, hook.error
+
+
+_DYNAMIC = ('N', 'Do', 'Ho', 'Wo', 'out_ld', 'out_coff', 'out_lo', 'dot_b', 'res_ld', 'res_D', 'res_H', 'res_W')
+_POINTERS = ('res', 'res_scale', 'out', 'dot_w', 'dot_out', 'dot_affine', 'oscale', 'range')
+
+
+def _launch_fields(a):
+    """everything a tpz_tc_conv launch passes except addresses: static block, per-launch geometry, which pointers are set"""
+    srcs = [(a.src[s].N, a.src[s].D, a.src[s].H, a.src[s].W, a.src[s].ld, bool(a.src[s].ptr)) for s in range(a.nsrc)]
+    return (_static_fields(a), srcs, tuple(getattr(a, k) for k in _DYNAMIC), tuple(a.res_org), tuple(bool(getattr(a, k)) for k in _POINTERS))
+
+
+@pytest.mark.parametrize('dims', [2, 3])
+def test_every_tc_conv_argument_block_equals_the_python_engines(dims, fast_precision, monkeypatch):
+    """The argument block of EVERY tensor-core launch -- the struct tpz_tc_conv receives -- field by field against the one
+    ops.fill_tc_args builds for the Python engine's launch at the same position (addresses excepted)."""
+    from topaz_b200.denoising.models import UDenoiseNetSmall, UDenoiseNet3D
+    torch.manual_seed(11)
+    if dims == 2:
+        m, x = UDenoiseNetSmall(nf=16, width=7, top_width=3).eval(), torch.randn(2, 1, 40, 52)     # 52/4 = 13: one odd level
+    else:
+        m, x = UDenoiseNet3D(nf=16, base_width=3, top_width=3).eval(), torch.randn(1, 1, 32, 32, 64)
+    py_blocks = []
+    with sim_backend.patched(), torch.no_grad():
+        sim_tc = ops.tc_conv
+
+        def recording_tc_conv(plan, srcs, out_shape, out=None, res=None, res_org=(0, 0, 0), dot_out=None, out_coff=0, tag=None,
+                              dot_affine=None, rng=None):
+            a = ops.fill_tc_args(plan, srcs, out_shape, out, res, res_org, dot_out, out_coff, dot_affine, rng)
+            py_blocks.append(_launch_fields(a))
+            return sim_tc(plan, srcs, out_shape, out=out, res=res, res_org=res_org, dot_out=dot_out, out_coff=out_coff, tag=tag,
+                          dot_affine=dot_affine, rng=rng)
+        monkeypatch.setattr(ops, 'tc_conv', recording_tc_conv)
+        y_py = engine.unet_forward(m, x)
+    c_blocks = []
+    real_tc = SimHook._tc_conv
+
+    def recording_hook_tc(self, a):
+        c_blocks.append(_launch_fields(a))
+        return real_tc(self, a)
+    monkeypatch.setattr(SimHook, '_tc_conv', recording_hook_tc)
+    y_c, _ = run_c(m, x)
+    assert torch.equal(y_c, y_py)
+    assert len(c_blocks) == len(py_blocks) and len(c_blocks) > 10
+    for j, (cb, pb) in enumerate(zip(c_blocks, py_blocks)):
+        assert cb == pb, f'launch {j}'
+
+
+@pytest.fixture
+def precision():
+    saved = engine.PRECISION
+
+    def set_(p):
+        engine.PRECISION = p
+    yield set_
+    engine.PRECISION = saved
+
+
+@pytest.mark.parametrize('mode', ['strict', 'auto'])
+def test_unet3d_split_operand_layers(mode, precision):
+    """strict: every layer with (hi, lo) operands; auto (the 3-D default): the last four convolutions.  Plans (tripled k-blocks,
+    doubled source channels), the (hi, lo) stores of convs / first layer / im2col / max-pool, and the Cout = 1 tail on split inputs."""
+    from topaz_b200.denoising.models import UDenoiseNet3D
+    precision(mode)
+    g = gold('unet3d_seeded')
+    m = _load(UDenoiseNet3D(nf=48, base_width=7, top_width=3), seeded_state(unet_shapes(48, 7, 3, 3), int(g['seed'])))
+    assert _compare_all_plans(m) == (0 if mode == 'strict' else 1) + 5 + 5 * 2 + 5 * 8
+    x = torch.from_numpy(g['x'])
+    yc, launched = run_c(m, x)
+    assert torch.equal(yc, run_py(m, x))
+    mx, l2 = rel_err(yc.numpy(), g['y'])
+    assert mx < 2e-3 and l2 < 2e-3, (mx, l2)
+    assert launched[1] == (4 if mode == 'strict' else 2) and launched[-1] == 8       # strict: fp32 first layer; tail on the CUDA cores
+    x2 = torch.randn(1, 1, 32, 40, 36, generator=torch.Generator().manual_seed(2))   # odd level: materialised (hi, lo) up-sampling
+    y2, _ = run_c(m, x2)
+    assert torch.equal(y2, run_py(m, x2))
+
+
+@pytest.mark.parametrize('top', [3, 7])
+def test_unet2d_strict_precision(top, precision):
+    """2-D strict: fp32 first layer with a (hi, lo) output, split pooling, split raw-image taps; 3x3 top -> the tail runs on the
+    tensor-core plan with split operands (the tiled CUDA-core tail takes plain fp16 only); 7x7 top likewise."""
+    from topaz_b200.denoising.models import UDenoiseNetSmall
+    precision('strict')
+    torch.manual_seed(top)
+    m = UDenoiseNetSmall(nf=16, width=7, top_width=top).eval()
+    _compare_all_plans(m)
+    x = torch.randn(2, 1, 40, 52)
+    yc, launched = run_c(m, x)
+    assert torch.equal(yc, run_py(m, x))
+    assert launched[1] == 4 and launched[-1] == 5
+    precision('fast')
+    yf, _ = run_c(m, x)
+    with torch.no_grad():
+        ref = torch_reference(m, x)
+    e_strict, e_fast = float((yc - ref).abs().max()), float((yf - ref).abs().max())
+    assert e_strict < 0.2 * e_fast, (e_strict, e_fast)        # the split operands buy > 5x accuracy on the same network
+
+
+def torch_reference(m, x):
+    """UDenoiseNetSmall.forward of the reference (denoising/models.py:200-244) in plain torch fp32 on the drop-in's parameters"""
+    import torch.nn.functional as F
+    act = lambda t: F.leaky_relu(t, 0.1)
+    conv = lambda c, t: F.conv2d(t, c.weight, c.bias, padding=c.weight.shape[-1] // 2)
+    p1 = F.max_pool2d(act(conv(m.enc1[0], x)), 2)
+    p2 = F.max_pool2d(act(conv(m.enc2[0], p1)), 2)
+    p3 = F.max_pool2d(act(conv(m.enc3[0], p2)), 2)
+    h = act(conv(m.enc4[0], p3))
+    for dec, skip in ((m.dec3, p2), (m.dec2, p1)):
+        h = torch.cat([F.interpolate(h, size=skip.shape[2:], mode='nearest'), skip], 1)
+        h = act(conv(dec[2], act(conv(dec[0], h))))
+    h = torch.cat([F.interpolate(h, size=x.shape[2:], mode='nearest'), x], 1)
+    return conv(m.dec1[4], act(conv(m.dec1[2], act(conv(m.dec1[0], h)))))

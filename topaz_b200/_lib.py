@@ -51,7 +51,7 @@ TPZ_UNET_MAX_DEPTH = 8
 
 class TpzUnetDesc(C.Structure):
     _fields_ = [('dims', C.c_int), ('depth', C.c_int), ('enc', TpzConvDesc * TPZ_UNET_MAX_DEPTH), ('dec_a', TpzConvDesc * TPZ_UNET_MAX_DEPTH),
-                ('dec_b', TpzConvDesc * TPZ_UNET_MAX_DEPTH), ('last', TpzConvDesc), ('slope', C.c_float), ('host_weights', C.c_int)]
+                ('dec_b', TpzConvDesc * TPZ_UNET_MAX_DEPTH), ('last', TpzConvDesc), ('slope', C.c_float), ('precision', C.c_int), ('host_weights', C.c_int)]
 
 
 class TpzOpArgs(C.Structure):

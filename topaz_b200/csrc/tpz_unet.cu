@@ -10,8 +10,9 @@
 // Reference call sites: topaz/denoising/models.py:74-175 (UDenoiseNet), :178-244 (UDenoiseNetSmall), :452-564
 // (UDenoiseNet3D); topaz/denoise.py:274-296 (Denoise._denoise: normalise, forward, de-normalise).
 //
-// Precision: the default ("fast") operands only -- fp16 activations and weights, fp32 accumulation.  The split-operand layers
-// of TPZ_PRECISION=strict / the 3-D `auto` mode stay with the Python plans (the caller checks, engine.unet_forward).
+// Precision (TpzUnetDesc.precision, the engine's TPZ_PRECISION): fast = fp16 operands / fp32 accumulation everywhere; strict = every
+// activation and weight carried as a (hi, lo) fp16 pair (22 significand bits), each product as hi*hi + hi*lo + lo*hi on the same
+// kernels; auto = fast except the last four convolutions of a 3-D network (engine._unet_precision has the measurements behind it).
 #include "tpz_common.cuh"
 #include "../../include/topaz_b200.h"
 #include <algorithm>
@@ -64,6 +65,7 @@ struct PartSpec {
   int co = 0, ci = 0, kd = 1, kh = 1, kw = 1;
   int c_store = 0, dil = 1, org[3] = {0, 0, 0}, lat = 0, lat_z = 0;
   bool phase = true;
+  bool split = false;            // the source tensor stores (hi, lo) pairs: channels [0, c_store) = hi, [c_store, 2*c_store) = lo
   float at(int o, int c, int q, int r, int s) const { return w[((((size_t)o * ci + c) * kd + q) * kh + r) * kw + s]; }
 };
 
@@ -84,13 +86,17 @@ PartSpec part_of(const HostConv& c, int c_begin, int c_end, int c_store, const i
 struct Plan {
   TpzTcConvArgs a;               // launch-invariant fields (ops._static_tc_args)
   int co_store = 0;
+  bool split_out = false;        // the output is written as (hi, lo) pairs: 2*co_store channels, lo at channel + co_store
+  int out_channels() const { return split_out ? 2 * co_store : co_store; }
   long long weight_elems = 0;
   void *w_mem = nullptr, *bias_mem = nullptr, *dotw_mem = nullptr;
 };
 
-// ops.pack_tc_conv (non-strict): OIHW fp32 -> [k-block][Co][KC] fp16, k-blocks ordered (source, tap, chunk), all-zero blocks dropped
+// ops.pack_tc_conv: OIHW fp32 -> [k-block][Co][KC] fp16, k-blocks ordered (source, tap, chunk), all-zero blocks dropped.  strict: the
+// weights are split w = w_hi + w_lo and every (tap, chunk) becomes up to three k-blocks -- x_hi*w_hi, x_hi*w_lo (dropped when w_lo
+// rounds to zero) and, for a (hi, lo) source, x_lo*w_hi reading the lo half of the source's channels
 int pack(const Mem& mem, std::vector<void*>& owned, const std::vector<PartSpec>& parts, const float* bias, int co_store, float slope,
-         int lattice, int phase_sel, int lattice_z, int phase_z, const float* dot_w, float dot_b, Plan* out) {
+         int lattice, int phase_sel, int lattice_z, int phase_z, const float* dot_w, float dot_b, bool strict, bool split_out, Plan* out) {
   Plan& P = *out;
   memset(&P.a, 0, sizeof(P.a));
   TpzTcConvArgs& a = P.a;
@@ -104,6 +110,7 @@ int pack(const Mem& mem, std::vector<void*>& owned, const std::vector<PartSpec>&
   std::vector<float> mx(co_store, 0.f);
   bool finite = true;
   for (const PartSpec& p : parts) {
+    TPZ_CHECK(strict || !p.split, "tpz_unet: a (hi, lo) source needs a strict plan");
     TPZ_CHECK(p.c_store % KC == 0 && p.ci <= p.c_store && p.co == co_real, "tpz_unet: inconsistent conv source");
     const size_t per_row = (size_t)p.ci * p.kd * p.kh * p.kw;
     for (int o = 0; o < p.co; ++o)
@@ -130,13 +137,31 @@ int pack(const Mem& mem, std::vector<void*>& owned, const std::vector<PartSpec>&
               for (int j = 0; j < KC && c0 + j < p.ci; ++j)
                 if (p.at(o, c0 + j, q, r, s) != 0.f) { any = true; break; }
             if (!any) continue;
-            TPZ_CHECK(nkb < TPZ_TC_MAX_KB, "tpz_unet: conv needs more than %d k-blocks", TPZ_TC_MAX_KB);
-            TcKBlock& kb = a.kb[nkb++];
-            kb.dx = (int16_t)(s * p.dil); kb.dy = (int16_t)(r * p.dil); kb.dz = (int16_t)(q * p.dil); kb.c0 = (int16_t)c0; kb.src = si;
-            const size_t base = wt.size();
-            wt.resize(base + (size_t)co_store * KC, 0);
-            for (int o = 0; o < p.co; ++o)
-              for (int j = 0; j < KC && c0 + j < p.ci; ++j) wt[base + (size_t)o * KC + j] = half_bits(p.at(o, c0 + j, q, r, s));
+            auto add_block = [&](int c_first, int which) -> bool {      // which: 0 = fp16(w), 1 = fp16(w - fp16(w))
+              if (nkb >= TPZ_TC_MAX_KB) return false;
+              TcKBlock& kb = a.kb[nkb++];
+              kb.dx = (int16_t)(s * p.dil); kb.dy = (int16_t)(r * p.dil); kb.dz = (int16_t)(q * p.dil); kb.c0 = (int16_t)c_first; kb.src = si;
+              const size_t base = wt.size();
+              wt.resize(base + (size_t)co_store * KC, 0);
+              for (int o = 0; o < p.co; ++o)
+                for (int j = 0; j < KC && c0 + j < p.ci; ++j) {
+                  const float v = p.at(o, c0 + j, q, r, s);
+                  wt[base + (size_t)o * KC + j] = which == 0 ? half_bits(v) : half_bits(v - __half2float(__float2half_rn(v)));
+                }
+              return true;
+            };
+            bool ok = add_block(c0, 0);                                   // x (or x_hi) * w_hi
+            if (strict) {
+              bool lo_any = false;
+              for (int o = 0; o < p.co && !lo_any; ++o)
+                for (int j = 0; j < KC && c0 + j < p.ci; ++j) {
+                  const float v = p.at(o, c0 + j, q, r, s);
+                  if (half_bits(v - __half2float(__float2half_rn(v))) & 0x7fff) { lo_any = true; break; }
+                }
+              if (lo_any) ok = ok && add_block(c0, 1);                    // x_hi * w_lo
+              if (p.split) ok = ok && add_block(c0 + p.c_store, 0);       // x_lo * w_hi
+            }
+            TPZ_CHECK(ok, "tpz_unet: conv needs more than %d k-blocks", TPZ_TC_MAX_KB);
           }
   }
   if (nkb == 0) {                // degenerate all-zero conv: keep one block so the kernel has work
@@ -149,7 +174,7 @@ int pack(const Mem& mem, std::vector<void*>& owned, const std::vector<PartSpec>&
   for (int si = 0; si < a.nsrc; ++si) {
     const PartSpec& p = parts[si];
     TpzTcSrc& s = a.src[si];
-    s.C = p.c_store; s.org[0] = p.org[0]; s.org[1] = p.org[1]; s.org[2] = p.org[2];
+    s.C = (p.split ? 2 : 1) * p.c_store; s.org[0] = p.org[0]; s.org[1] = p.org[1]; s.org[2] = p.org[2];
     s.kw = p.kw; s.kh = p.kh; s.lat = p.lat; s.no_phase = p.phase ? 0 : 1; s.lat_z = p.lat_z;
     if (!(p.kw == 1 && p.kh == 1)) {
       if (lat_auto == -1) lat_auto = p.dil; else if (lat_auto != p.dil) lat_auto = 0;
@@ -160,6 +185,7 @@ int pack(const Mem& mem, std::vector<void*>& owned, const std::vector<PartSpec>&
   a.phase_sel = phase_sel; a.lattice_z = lattice_z; a.phase_z = phase_z;
   a.neg_slope = slope;
   P.co_store = co_store;
+  P.split_out = split_out;
   P.weight_elems = (long long)wt.size();
   std::vector<float> b(co_store, 0.f);
   if (bias) for (int o = 0; o < co_real; ++o) b[o] = bias[o];
@@ -202,7 +228,8 @@ struct TpzUnet {
   std::vector<DecLevel> dec;     // index l = 1 .. depth-1
   // dec1 tail
   int k_top = 0, ntap_store = 0, last_k = 0, last_c = 0, last_cstore = 0;
-  bool last_simt = false;
+  bool last_simt = false, last_strict = false;
+  bool first_split = false, raw_split = false;     // enc1's output / the raw-image im2col stored as (hi, lo) pairs
   float last_b = 0.f;
   void* last_w = nullptr;        // [taps][last_cstore] fp32
   Plan last_tc;
@@ -237,7 +264,8 @@ int fetch_conv(const TpzConvDesc& d, int dims, bool host, cudaStream_t st, HostC
 
 // engine._up2_phase_plans: conv(cat[nearest_up2(h), other]) per output phase, straight from the half-resolution tensor h: the taps
 // of the k^dims kernel that alias onto the same half-res voxel are summed (5x5 -> 3x3, 3x3(x3) -> 2x2(x2) per phase)
-int up2_plans(TpzUnet* m, const HostConv& ca, int up_c, const std::function<PartSpec(int, int, int)>& second, std::vector<Plan>* out) {
+int up2_plans(TpzUnet* m, const HostConv& ca, int up_c, const std::function<PartSpec(int, int, int)>& second, bool strict, bool split_out,
+              std::vector<Plan>* out) {
   const int k = ca.kh, pad = k / 2, dims = m->dims, kz = ca.kd;
   const int co_store = rup(ca.co);
   out->clear();
@@ -268,12 +296,13 @@ int up2_plans(TpzUnet* m, const HostConv& ca, int up_c, const std::function<Part
                   dst = dst + ca.at(o, c, q, r, t);
                 }
         up.c_store = rup(up_c); up.dil = 1; up.org[0] = ax0; up.org[1] = ay0; up.org[2] = az0; up.lat = 1; up.lat_z = 1; up.phase = false;
+        up.split = strict;
         std::vector<PartSpec> parts;
         parts.push_back(std::move(up));
         parts.push_back(second(px, py, pz));
         out->emplace_back();
         int rc = pack(m->mem, m->owned, parts, ca.b.empty() ? nullptr : ca.b.data(), co_store, m->slope, 2, py * 2 + px + 1,
-                      dims == 3 ? 2 : 1, pz, nullptr, 0.f, &out->back());
+                      dims == 3 ? 2 : 1, pz, nullptr, 0.f, strict, split_out, &out->back());
         if (rc) return rc;
       }
     }
@@ -299,6 +328,22 @@ int build_unet(TpzUnet* m, const TpzUnetDesc* d, cudaStream_t st) {
   m->nf = nf;
   for (int i = 1; i < depth; ++i) TPZ_CHECK(enc[i].ci == enc[i - 1].co, "tpz_unet_create: encoder channel counts do not chain");
   const float slope = m->slope;
+  // engine._unet_precision: which layers run with split operands (S), and which tensors must therefore be stored as (hi, lo) pairs
+  // (a tensor is split when one of its consumers is in S)
+  const int prec = d->precision;
+  auto S_enc = [&](int i) { (void)i; return prec == 2; };
+  auto S_dec = [&](int l, int idx) { return prec == 2 || (prec == 1 && dims == 3 && ndec >= 2 && ((l == 2 && idx == 2) || l == 1)); };
+  const bool S_last = S_dec(1, 4);
+  auto split_enc = [&](int i) {                    // output of enc{i}: read by enc{i+1} and, as skip, by dec{i+1}.0
+    if (i < depth) return S_enc(i + 1) || (i + 1 <= ndec && S_dec(i + 1, 0));
+    return S_dec(ndec, 0);
+  };
+  auto split_dec = [&](int l, int idx) {           // output of dec{l}.{idx}
+    if (idx == 0) return S_dec(l, 2);
+    return l > 1 ? S_dec(l - 1, 0) : S_last;
+  };
+  m->raw_split = S_dec(1, 0);
+  m->last_strict = S_last;
   auto same_org = [&](int k, int org[3]) { org[0] = -(k / 2); org[1] = -(k / 2); org[2] = dims == 3 ? -(k / 2) : 0; };
   auto bias_of = [](const HostConv& c) { return c.b.empty() ? (const float*)nullptr : c.b.data(); };
   int org[3];
@@ -307,7 +352,9 @@ int build_unet(TpzUnet* m, const TpzUnetDesc* d, cudaStream_t st) {
   const HostConv& c1 = enc[0];
   const int k1 = c1.kh;
   m->k1 = k1;
-  if (dims == 2 && tpz_conv_first_tc_supported(k1, rup(nf))) {
+  m->first_split = split_enc(1);
+  const bool first_fp32 = S_enc(1) || m->first_split;      // Cin = 1 first conv on the fp32 CUDA-core kernel, (hi, lo) output
+  if (!first_fp32 && dims == 2 && tpz_conv_first_tc_supported(k1, rup(nf))) {
     m->first_mode = 0;                            // ops.pack_first_tc: [KB][Cp][64] fp16, tap t = r*k + s
     const int cp = rup(nf), KB = (k1 * k1 + 63) / 64;
     std::vector<uint16_t> wp((size_t)KB * cp * 64, 0);
@@ -320,7 +367,7 @@ int build_unet(TpzUnet* m, const TpzUnetDesc* d, cudaStream_t st) {
     m->owned.push_back(m->first_w16); m->owned.push_back(m->first_b);
     TPZ_CHECK(m->mem.upload(m->first_w16, wp.data(), wp.size() * 2) && m->mem.upload(m->first_b, bp.data(), bp.size() * 4),
               "tpz_unet_create: weight upload failed");
-  } else if (k1 * k1 <= 128) {
+  } else if (!first_fp32 && k1 * k1 <= 128) {
     m->first_mode = 1;                            // in-plane im2col (k*k taps -> channels) + GEMM; in 3-D the k z-taps stay taps
     const int taps = k1 * k1, ld = tap_ld(taps);
     m->first_ld = ld;
@@ -331,7 +378,7 @@ int build_unet(TpzUnet* m, const TpzUnetDesc* d, cudaStream_t st) {
     for (int o = 0; o < nf; ++o)
       for (int t = 0; t < taps; ++t)
         for (int q = 0; q < p.kd; ++q) p.w[((size_t)o * taps + t) * p.kd + q] = c1.w[((size_t)o * p.kd + q) * taps + t];
-    if ((rc = pack(m->mem, m->owned, {p}, bias_of(c1), rup(nf), slope, -1, 0, 1, 0, nullptr, 0.f, &m->first_plan))) return rc;
+    if ((rc = pack(m->mem, m->owned, {p}, bias_of(c1), rup(nf), slope, -1, 0, 1, 0, nullptr, 0.f, false, false, &m->first_plan))) return rc;
   } else {
     m->first_mode = 2;                            // fp32 CUDA-core kernel on the reference's own [Co][kd][kh][kw] weights
     std::vector<float> bp(nf, 0.f);
@@ -348,7 +395,9 @@ int build_unet(TpzUnet* m, const TpzUnetDesc* d, cudaStream_t st) {
   for (int i = 1; i < depth; ++i) {
     same_org(enc[i].kh, org);
     PartSpec p = part_of(enc[i], 0, enc[i].ci, rup(enc[i].ci), org);
-    if ((rc = pack(m->mem, m->owned, {p}, bias_of(enc[i]), rup(enc[i].co), slope, -1, 0, 1, 0, nullptr, 0.f, &m->enc[i - 1]))) return rc;
+    p.split = S_enc(i + 1);
+    if ((rc = pack(m->mem, m->owned, {p}, bias_of(enc[i]), rup(enc[i].co), slope, -1, 0, 1, 0, nullptr, 0.f, S_enc(i + 1), split_enc(i + 1),
+                   &m->enc[i - 1]))) return rc;
   }
 
   // ---- decoder ----
@@ -360,18 +409,20 @@ int build_unet(TpzUnet* m, const TpzUnetDesc* d, cudaStream_t st) {
     const int k = ca.kh, pad_k = k / 2;
     TPZ_CHECK(cb.ci == ca.co, "tpz_unet_create: decoder level %d channel counts do not chain", l);
     same_org(k, org);
+    const bool sa = S_dec(l, 0), sb = S_dec(l, 2);
     if (l > 1) {
       const int skip_c = enc[l - 2].co;
       TPZ_CHECK(ca.ci == up_c + skip_c, "tpz_unet_create: dec%d.0 takes %d channels, expected %d + %d", l, ca.ci, up_c, skip_c);
       std::vector<PartSpec> parts{part_of(ca, 0, up_c, rup(up_c), org), part_of(ca, up_c, ca.ci, rup(skip_c), org)};
-      if ((rc = pack(m->mem, m->owned, parts, bias_of(ca), rup(ca.co), slope, -1, 0, 1, 0, nullptr, 0.f, &D.a))) return rc;
+      parts[0].split = parts[1].split = sa;
+      if ((rc = pack(m->mem, m->owned, parts, bias_of(ca), rup(ca.co), slope, -1, 0, 1, 0, nullptr, 0.f, sa, split_dec(l, 0), &D.a))) return rc;
       auto second = [&](int px, int py, int pz) {
         int o2[3] = {px - pad_k, py - pad_k, dims == 3 ? pz - pad_k : 0};
         PartSpec p = part_of(ca, up_c, ca.ci, rup(skip_c), o2);
-        p.lat = 2; p.lat_z = dims == 3 ? 2 : 0; p.phase = false;
+        p.lat = 2; p.lat_z = dims == 3 ? 2 : 0; p.phase = false; p.split = sa;
         return p;
       };
-      if ((rc = up2_plans(m, ca, up_c, second, &D.up2))) return rc;
+      if ((rc = up2_plans(m, ca, up_c, second, sa, split_dec(l, 0), &D.up2))) return rc;
     } else {
       // dec1: [up-sampled (up_c channels), raw image (1 channel)]; the raw slice is a second source of k^dims im2col channels
       TPZ_CHECK(ca.ci == up_c + 1, "tpz_unet_create: dec1.0 takes %d channels, expected %d + 1", ca.ci, up_c);
@@ -388,18 +439,20 @@ int build_unet(TpzUnet* m, const TpzUnetDesc* d, cudaStream_t st) {
         return p;
       };
       std::vector<PartSpec> parts{part_of(ca, 0, up_c, rup(up_c), org), raw_part(0, 0, 0)};
-      if ((rc = pack(m->mem, m->owned, parts, bias_of(ca), rup(ca.co), slope, -1, 0, 1, 0, nullptr, 0.f, &D.a))) return rc;
+      parts[0].split = parts[1].split = sa;
+      if ((rc = pack(m->mem, m->owned, parts, bias_of(ca), rup(ca.co), slope, -1, 0, 1, 0, nullptr, 0.f, sa, split_dec(l, 0), &D.a))) return rc;
       auto second = [&](int px, int py, int pz) {
         PartSpec p = raw_part(px, py, dims == 3 ? pz : 0);
-        p.lat = 2; p.lat_z = dims == 3 ? 2 : 0; p.phase = false;
+        p.lat = 2; p.lat_z = dims == 3 ? 2 : 0; p.phase = false; p.split = sa;
         return p;
       };
-      if ((rc = up2_plans(m, ca, up_c, second, &D.up2))) return rc;
+      if ((rc = up2_plans(m, ca, up_c, second, sa, split_dec(l, 0), &D.up2))) return rc;
     }
     int orgb[3];
     same_org(cb.kh, orgb);
     PartSpec pb = part_of(cb, 0, cb.ci, rup(ca.co), orgb);
-    if ((rc = pack(m->mem, m->owned, {pb}, bias_of(cb), rup(cb.co), slope, -1, 0, 1, 0, nullptr, 0.f, &D.b))) return rc;
+    pb.split = sb;
+    if ((rc = pack(m->mem, m->owned, {pb}, bias_of(cb), rup(cb.co), slope, -1, 0, 1, 0, nullptr, 0.f, sb, split_dec(l, 2), &D.b))) return rc;
     up_c = cb.co;
   }
 
@@ -408,9 +461,12 @@ int build_unet(TpzUnet* m, const TpzUnetDesc* d, cudaStream_t st) {
   const int kl = last.kh, cin = last.ci, taps = ipow(kl, dims);
   m->last_k = kl; m->last_c = cin; m->last_cstore = rup(cin); m->last_b = last.b[0];
   {
-    std::vector<float> wl((size_t)taps * rup(cin), 0.f);            // [taps][C]: wl[t][c] = w[0][c][t]
+    // [taps][C]: wl[t][c] = w[0][c][t]; a split (hi, lo) input is read as 2*C channels with the weights repeated
+    const int cs = rup(cin), reps = S_last ? 2 : 1;
+    std::vector<float> wl((size_t)taps * cs * reps, 0.f);
     for (int c = 0; c < cin; ++c)
-      for (int t = 0; t < taps; ++t) wl[(size_t)t * rup(cin) + c] = last.w[(size_t)c * taps + t];
+      for (int t = 0; t < taps; ++t)
+        for (int h = 0; h < reps; ++h) wl[((size_t)t * reps + h) * cs + c] = last.w[(size_t)c * taps + t];
     m->last_w = m->mem.alloc(wl.size() * 4);
     TPZ_CHECK(m->last_w, "tpz_unet_create: out of memory");
     m->owned.push_back(m->last_w);
@@ -418,11 +474,13 @@ int build_unet(TpzUnet* m, const TpzUnetDesc* d, cudaStream_t st) {
   }
   // CUDA-core Cout = 1 tail where a tiled kernel exists (2-D 3x3 / 5x5, 3-D 3x3x3 on 32 channels: 1600 FLOP/px is too little for
   // the tensor-core path); elsewhere a 16-column tensor-core GEMM whose fused "dot" epilogue picks column 0
-  m->last_simt = rup(cin) == 32 && ((dims == 2 && (kl == 3 || kl == 5)) || (dims == 3 && kl == 3));
+  const bool tiled3d = dims == 3 && rup(cin) == 32 && kl == 3;      // the z-marching kernel also takes split inputs
+  m->last_simt = S_last ? tiled3d : (rup(cin) == 32 && ((dims == 2 && (kl == 3 || kl == 5)) || tiled3d));
   same_org(kl, org);
   PartSpec pl = part_of(last, 0, cin, rup(cin), org);
+  pl.split = S_last;
   const float onehot0 = 1.f;
-  if ((rc = pack(m->mem, m->owned, {pl}, nullptr, 16, 1.0f, -1, 0, 1, 0, &onehot0, last.b[0], &m->last_tc))) return rc;
+  if ((rc = pack(m->mem, m->owned, {pl}, nullptr, 16, 1.0f, -1, 0, 1, 0, &onehot0, last.b[0], S_last, false, &m->last_tc))) return rc;
   return 0;
 }
 
@@ -530,22 +588,22 @@ struct Run {
     }
     a.N = N; a.Do = D; a.Ho = H; a.Wo = W;
     a.res = nullptr; a.res_scale = nullptr;
-    if (out) { a.out = ws ? ptr(*out) : nullptr; a.out_ld = out->ld; a.out_coff = 0; }
-    else { a.out = nullptr; }
-    a.out_lo = 0;
+    if (out) { a.out = ws ? ptr(*out) : nullptr; a.out_ld = out->ld; a.out_coff = 0; a.out_lo = plan.split_out ? plan.co_store : 0; }
+    else { a.out = nullptr; a.out_lo = 0; }
     a.range = reinterpret_cast<const float*>(ws);
     if (dot_out) { a.dot_w = reinterpret_cast<const float*>(plan.dotw_mem); a.dot_out = dot_out; a.dot_affine = dot_affine; }
     else { a.dot_w = nullptr; a.dot_out = nullptr; a.dot_affine = nullptr; }
     return op(TPZ_OP_TC_CONV, &a);
   }
 
-  int pool(const Buf& in, Buf* out) {
+  int pool(const Buf& in, bool split, Buf* out) {   // split: channels are [hi | lo] halves, the maximum is over hi + lo
     const int dims = m->dims;
     *out = make(in.N, dims == 3 ? in.D / 2 : in.D, in.H / 2, in.W / 2, in.ld);
     TpzOpArgs o;
     memset(&o, 0, sizeof(o));
     o.p[0] = ws ? ptr(in) : nullptr; o.p[1] = ws ? ptr(*out) : nullptr;
-    const int v[] = {in.N, in.D, in.H, in.W, in.ld, in.ld, dims, in.ld, 0};
+    const int C = split ? in.ld / 2 : in.ld;
+    const int v[] = {in.N, in.D, in.H, in.W, C, in.ld, dims, in.ld, split ? C : 0};
     memcpy(o.i, v, sizeof(v));
     return op(TPZ_OP_MAXPOOL2, &o);
   }
@@ -581,21 +639,22 @@ struct Run {
       const int v[] = {N * D, H, W, m->k1, m->k1 / 2, m->first_ld, 0};
       memcpy(o.i, v, sizeof(v));
       if ((rc = op(TPZ_OP_IM2COL_FIRST, &o))) return rc;
-      h = make(N, D, H, W, m->first_plan.co_store);
+      h = make(N, D, H, W, m->first_plan.out_channels());
       if ((rc = conv(m->first_plan, &col, nullptr, N, D, H, W, &h, nullptr, nullptr))) return rc;
       drop(col);
     } else {
-      h = make(N, D, H, W, cp);
+      const int ld = m->first_split ? 2 * cp : cp;
+      h = make(N, D, H, W, ld);
       memset(&o, 0, sizeof(o));
       o.p[0] = x; o.p[1] = m->first_w32; o.p[2] = m->first_b; o.p[3] = ws ? ptr(h) : nullptr; o.p[4] = range;
-      const int v[] = {N, D, H, W, m->nf, dims == 3 ? m->k1 : 1, m->k1, m->k1, 1, m->k1 / 2, 1, cp, 0};
+      const int v[] = {N, D, H, W, m->nf, dims == 3 ? m->k1 : 1, m->k1, m->k1, 1, m->k1 / 2, 1, ld, m->first_split ? cp : 0};
       memcpy(o.i, v, sizeof(v));
       o.f[0] = m->slope;
       if ((rc = op(TPZ_OP_CONV_FIRST, &o))) return rc;
     }
     if (pool1 && !pooled) {
       Buf p;
-      if ((rc = pool(h, &p))) return rc;
+      if ((rc = pool(h, m->first_split, &p))) return rc;
       drop(h);
       h = p;
     }
@@ -604,11 +663,11 @@ struct Run {
     skips.push_back(h);
     for (int i = 2; i <= depth; ++i) {
       Plan& pl = m->enc[i - 2];
-      Buf out = make(h.N, h.D, h.H, h.W, pl.co_store);
+      Buf out = make(h.N, h.D, h.H, h.W, pl.out_channels());
       if ((rc = conv(pl, &h, nullptr, h.N, h.D, h.H, h.W, &out, nullptr, nullptr))) return rc;
       if (i < depth) {
         Buf p;
-        if ((rc = pool(out, &p))) return rc;
+        if ((rc = pool(out, pl.split_out, &p))) return rc;
         drop(out);
         h = p;
         skips.push_back(h);
@@ -627,20 +686,21 @@ struct Run {
         oN = other.N; oD = other.D; oH = other.H; oW = other.W;
       } else {
         oN = N; oD = D; oH = H; oW = W;
-        other = make(N, D, H, W, m->ntap_store);
+        other = make(N, D, H, W, m->raw_split ? 2 * m->ntap_store : m->ntap_store);
         memset(&o, 0, sizeof(o));
         o.p[0] = x; o.p[1] = ws ? ptr(other) : nullptr; o.p[2] = range;
+        const int lo = m->raw_split ? m->ntap_store : 0;          // (hi, lo) taps: lo half at channel t + ntap_store
         if (dims == 2) {
-          const int v[] = {N, H, W, m->k_top, m->k_top / 2, m->ntap_store, 0};
+          const int v[] = {N, H, W, m->k_top, m->k_top / 2, m->ntap_store, lo};
           memcpy(o.i, v, sizeof(v));
           if ((rc = op(TPZ_OP_IM2COL_FIRST, &o))) return rc;
         } else {
-          const int v[] = {N, D, H, W, m->k_top, m->k_top / 2, m->ntap_store, 0};
+          const int v[] = {N, D, H, W, m->k_top, m->k_top / 2, m->ntap_store, lo};
           memcpy(o.i, v, sizeof(v));
           if ((rc = op(TPZ_OP_IM2COL3D_FIRST, &o))) return rc;
         }
       }
-      Buf oa = make(oN, oD, oH, oW, L.a.co_store);
+      Buf oa = make(oN, oD, oH, oW, L.a.out_channels());
       const bool exact2 = oH == 2 * h.H && oW == 2 * h.W && (dims == 2 || oD == 2 * h.D);
       if (exact2) {
         for (Plan& ph : L.up2)                      // fused nearest-2x up-sampling: one launch per output phase, reading h itself
@@ -658,7 +718,7 @@ struct Run {
       drop(h);
       drop(other);
       if (l > 1) skips[l - 2].off = -1;
-      Buf ob = make(oN, oD, oH, oW, L.b.co_store);
+      Buf ob = make(oN, oD, oH, oW, L.b.out_channels());
       if ((rc = conv(L.b, &oa, nullptr, oN, oD, oH, oW, &ob, nullptr, nullptr))) return rc;
       drop(oa);
       h = ob;
@@ -667,7 +727,8 @@ struct Run {
     if (m->last_simt) {
       memset(&o, 0, sizeof(o));
       o.p[0] = ws ? ptr(h) : nullptr; o.p[1] = m->last_w; o.p[2] = stats; o.p[3] = y; o.p[4] = range;
-      const int v[] = {h.N, h.D, h.H, h.W, m->last_cstore, h.ld, dims == 3 ? m->last_k : 1, m->last_k, m->last_k, 1, m->last_k / 2};
+      const int v[] = {h.N, h.D, h.H, h.W, m->last_strict ? 2 * m->last_cstore : m->last_cstore, h.ld, dims == 3 ? m->last_k : 1, m->last_k,
+                       m->last_k, 1, m->last_k / 2};
       memcpy(o.i, v, sizeof(v));
       o.f[0] = m->last_b; o.f[1] = 1.f; o.f[2] = 0.f;
       if ((rc = op(TPZ_OP_CONV_LAST, &o))) return rc;
@@ -708,6 +769,8 @@ extern "C" int tpz_unet_create(const TpzUnetDesc* desc, TpzUnet** out, void* str
   TPZ_CHECK(desc && out, "tpz_unet_create: null argument");
   TPZ_CHECK((desc->dims == 2 || desc->dims == 3) && desc->depth >= 2 && desc->depth <= TPZ_UNET_MAX_DEPTH,
             "tpz_unet_create: dims %d / depth %d not supported", desc->dims, desc->depth);
+  TPZ_CHECK(desc->precision >= TPZ_PRECISION_FAST && desc->precision <= TPZ_PRECISION_STRICT, "tpz_unet_create: bad precision %d",
+            desc->precision);
   TpzUnet* m = new (std::nothrow) TpzUnet();
   TPZ_CHECK(m != nullptr, "tpz_unet_create: out of memory");
   m->mem.host = desc->host_weights != 0;

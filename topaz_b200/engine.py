@@ -541,8 +541,8 @@ def _build_unet_plan(model, device):
 
 
 def _unet_c_model(model, key):
-    """The denoiser's native handle (model_abi.UnetModel), or None where only the Python plans apply: split-operand layers
-    (strict precision, the 3-D `auto` mode), a non-default kernel selection, or a weight row that needs the row-scaled plans."""
+    """The denoiser's native handle (model_abi.UnetModel), or None where only the Python plans apply: a non-default kernel
+    selection (the TPZ_FIRST / TPZ_UP2 / TPZ_LAST / TPZ_RANGE_GUARD switches), or a weight row that needs the row-scaled plans."""
     from .model_abi import UnetModel, WeightRangeError
     cache = model.__dict__.setdefault('_tpz_plans', {})
     hit = cache.get('unet_c')
@@ -551,12 +551,10 @@ def _unet_c_model(model, key):
     if hit is not None and hit[1] is not None:
         hit[1].close()
     um = None
-    depth = sum(1 for i in range(1, 10) if hasattr(model, f'enc{i}'))
-    dims = 3 if isinstance(model.enc1[0], nn.Conv3d) else 2
     defaults = RANGE_GUARD and UP2_FUSED and FIRST_FUSED and LAST_MODE == 'auto' and ops.TC_VARIANT == 'auto'
-    if defaults and not _unet_precision(dims, depth)[0]:
+    if defaults and PRECISION in UnetModel.PRECISIONS:
         try:
-            um = UnetModel(model)
+            um = UnetModel(model, precision=PRECISION)
         except (WeightRangeError, NotImplementedError):
             um = None
     cache['unet_c'] = (key, um)

@@ -164,16 +164,19 @@ class UnetModel:
     """A U-Net denoiser (UDenoiseNet / UDenoiseNetSmall / UDenoiseNet3D drop-in) as one native handle (csrc/tpz_unet.cu):
     ``tpz_unet_create`` reads the convolutions in the reference's own layout and builds every plan in C++;
     ``forward`` is one ``tpz_unet2d_forward`` / ``tpz_unet3d_forward`` call on a caller-owned workspace.
-    ``engine.unet_forward`` routes through it with TPZ_UNET_ENGINE=c (default precision only); the Python-built plans stay the
-    default path until this one has been run on hardware.  ``host=True`` builds a test handle on HOST tensors that runs only
+    ``engine.unet_forward`` routes through it with TPZ_UNET_ENGINE=c (``precision`` = the engine's fast / auto / strict); the
+    Python-built plans stay the default path until this one has been run on hardware.  ``host=True`` builds a test handle on HOST tensors that runs only
     under the launch hook (tests/test_unet_abi.py)."""
 
-    def __init__(self, model: nn.Module, host: bool = False):
+    PRECISIONS = {'fast': 0, 'auto': 1, 'strict': 2}      # include/topaz_b200.h TPZ_PRECISION_*
+
+    def __init__(self, model: nn.Module, host: bool = False, precision: str = 'fast'):
         self.model = model
         self.host = host
         self.handle = C.c_void_p()
         self._ws = None
         desc, keep = self.describe(model, host)
+        desc.precision = self.PRECISIONS[precision]
         self.dims, self.depth = desc.dims, desc.depth
         s = None if host else C.c_void_p(torch.cuda.current_stream().cuda_stream)
         rc = _lib.lib().tpz_unet_create(C.byref(desc), C.byref(self.handle), s)
