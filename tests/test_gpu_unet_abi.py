@@ -12,7 +12,8 @@ import torch
 from common import gold, weights_of, seeded_state, check_parity
 from common_shapes import unet_shapes
 
-pytestmark = [pytest.mark.gpu,
+# collected after every other -m gpu file (alphabetical order), so a failure here cannot disturb the validated tests' CUDA context
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600),
               pytest.mark.xfail(strict=False, reason='tpz_unet*_forward: first run on hardware (written after the GPU budget was spent)')]
 
 
