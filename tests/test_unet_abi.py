@@ -471,3 +471,33 @@ def torch_reference(m, x):
         h = act(conv(dec[2], act(conv(dec[0], h))))
     h = torch.cat([F.interpolate(h, size=x.shape[2:], mode='nearest'), x], 1)
     return conv(m.dec1[4], act(conv(m.dec1[2], act(conv(m.dec1[0], h)))))
+
+
+@pytest.mark.parametrize('seed', range(10))
+def test_random_architectures_and_patch_sizes(seed, precision):
+    """Randomised depth / width / kernel sizes / patch shapes / precision: the C++ handle and the Python engine must agree bit for
+    bit on every one (also at the smallest patch the pooling stages allow, where whole levels are a single pixel)."""
+    from topaz_b200.denoising.models import _UNetBase
+    rs = np.random.RandomState(1000 + seed)
+    dims = 3 if seed % 3 == 2 else 2
+
+    class Net(_UNetBase):
+        _dims = dims
+
+        def __init__(self, nf, base, top, depth):
+            super().__init__()
+            self._build(nf, base, top, depth)
+    depth = int(rs.choice([3, 4] if dims == 3 else [3, 4, 5, 6]))     # (_build's dec1 assumes a 2*nf-channel decoder level below it)
+    nf = int(rs.choice([8, 16, 24] if dims == 3 else [8, 16, 40, 48]))
+    base = int(rs.choice([3, 5] if dims == 3 else [3, 5, 7, 9, 11]))
+    top = int(rs.choice([3] if dims == 3 else [3, 5]))
+    precision(['fast', 'auto', 'strict'][seed % 3] if dims == 3 else ['fast', 'strict'][seed % 2])
+    torch.manual_seed(seed)
+    m = Net(nf, base, top, depth).eval()
+    div = 1 << (depth - 1)
+    shapes = [tuple(int(div * rs.randint(1, 4) + rs.randint(0, div)) for _ in range(dims)), (div,) * dims]
+    for sp in shapes:
+        x = torch.randn((1 + seed % 2, 1) + sp, generator=torch.Generator().manual_seed(seed))
+        yc, _ = run_c(m, x)
+        assert torch.equal(yc, run_py(m, x)), (seed, dims, depth, nf, base, top, sp, engine.PRECISION)
+    _compare_all_plans(m)
