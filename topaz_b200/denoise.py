@@ -89,13 +89,17 @@ class Denoise():
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
                     static_out = self._denoise_device(static_in)
-                hit = (graph, static_in, static_out)
+                # the captured launches hold the ADDRESSES of the packed weights (allocated by the eager warm-up, outside the
+                # graph's pool): keep the plans / native handles they belong to alive for as long as the graph can be replayed
+                # (engine.PRECISION switched away and back would otherwise replay against freed weights)
+                keep = dict(self.model.__dict__.get('_tpz_plans', {}))
+                hit = (graph, static_in, static_out, keep)
             except Exception as e:                     # capture not possible: stay eager for this shape
                 print(f'topaz_b200: CUDA-graph capture of the denoiser failed ({type(e).__name__}: {e}); running eagerly',
                       file=sys.stderr)
-                hit = (None, None, None)
+                hit = (None, None, None, None)
             graphs[key] = hit
-        graph, static_in, static_out = hit
+        graph, static_in, static_out = hit[:3]
         if graph is None:
             return self._denoise_device(crop)
         static_in.copy_(crop)

@@ -542,21 +542,28 @@ def _build_unet_plan(model, device):
 
 def _unet_c_model(model, key):
     """The denoiser's native handle (model_abi.UnetModel), or None where only the Python plans apply: a non-default kernel
-    selection (the TPZ_FIRST / TPZ_UP2 / TPZ_LAST / TPZ_RANGE_GUARD switches), or a weight row that needs the row-scaled plans."""
+    selection (the TPZ_FIRST / TPZ_UP2 / TPZ_LAST / TPZ_RANGE_GUARD switches), or a weight row that needs the row-scaled plans.
+    One handle per (parameter state, precision); handles are kept for the life of the module -- a CUDA graph captured by
+    Denoise._denoise_crop holds the addresses of a handle's packed weights and may be replayed whenever its key recurs
+    (eval() / train() / eval(), a precision switched back), so a handle is never freed under a graph.  Denoiser parameters do not
+    change on this path (denoiser training is out of scope), so the set stays small."""
     from .model_abi import UnetModel, WeightRangeError
     cache = model.__dict__.setdefault('_tpz_plans', {})
+    defaults = bool(RANGE_GUARD and UP2_FUSED and FIRST_FUSED and LAST_MODE == 'auto' and ops.TC_VARIANT == 'auto')
+    key = (key, defaults)
     hit = cache.get('unet_c')
     if hit is not None and hit[0] == key:
         return hit[1]
-    if hit is not None and hit[1] is not None:
-        hit[1].close()
-    um = None
-    defaults = RANGE_GUARD and UP2_FUSED and FIRST_FUSED and LAST_MODE == 'auto' and ops.TC_VARIANT == 'auto'
-    if defaults and PRECISION in UnetModel.PRECISIONS:
-        try:
-            um = UnetModel(model, precision=PRECISION)
-        except (WeightRangeError, NotImplementedError):
-            um = None
+    handles = cache.setdefault('unet_c_handles', {})
+    if key not in handles:
+        um = None
+        if defaults and PRECISION in UnetModel.PRECISIONS:
+            try:
+                um = UnetModel(model, precision=PRECISION)
+            except (WeightRangeError, NotImplementedError):
+                um = None
+        handles[key] = um
+    um = handles[key]
     cache['unet_c'] = (key, um)
     return um
 
