@@ -501,3 +501,49 @@ def test_random_architectures_and_patch_sizes(seed, precision):
         yc, _ = run_c(m, x)
         assert torch.equal(yc, run_py(m, x)), (seed, dims, depth, nf, base, top, sp, engine.PRECISION)
     _compare_all_plans(m)
+
+
+import contextlib
+import os
+
+from test_dropin_reference_cli import aliased      # noqa: F401  (fixture: the reference package aliased onto the drop-in modules)
+
+
+@contextlib.contextmanager
+def c_engine_under_hook(monkeypatch):
+    """engine.unet_forward -> host-memory C handle -> launch hook -> CPU simulation, for code that only knows the nn.Modules"""
+    from topaz_b200 import model_abi
+
+    class HostUnetModel(UnetModel):
+        def __init__(self, model, precision='fast'):
+            super().__init__(model, host=True, precision=precision)
+    monkeypatch.setattr(model_abi, 'UnetModel', HostUnetModel)
+    monkeypatch.setattr(engine, 'UNET_ENGINE', 'c')
+    hook = SimHook()
+    _lib.lib().tpz_unet_set_launch_hook(hook.fn, None)
+    try:
+        yield hook
+    finally:
+        _lib.lib().tpz_unet_set_launch_hook(C.cast(None, _lib.LAUNCH_HOOK), None)
+    assert hook.error is None, hook.error
+
+
+def test_existing_unet_suite_through_the_c_handle(monkeypatch):
+    """tests/test_host_logic.py's U-Net goldens (pretrained 2-D, seeded 2-D, seeded 3-D in the default `auto` precision) with every
+    forward going through tpz_unet2d_forward / tpz_unet3d_forward"""
+    import test_host_logic as H
+    with c_engine_under_hook(monkeypatch) as hook:
+        H.test_unet_sim_pretrained_and_seeded()
+    assert hook.ops.count(0) == 4                 # four forwards, each opened by its range scale
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/topaz'), reason='reference checkout not present')
+def test_reference_pipelines_through_the_c_handle(aliased, tmp_path, monkeypatch):   # noqa: F811
+    """The UNMODIFIED reference pipeline code -- topaz.denoise.Denoise.denoise with patches, and the `topaz denoise3d` command
+    (Denoise3D -> PatchDataset crops -> model -> MRC) -- on the drop-in modules with the C handle underneath."""
+    import test_dropin_reference_cli as T
+    with c_engine_under_hook(monkeypatch) as hook:
+        T.test_reference_denoise_pipeline_runs_on_dropin_unet(None, monkeypatch)
+        n2d = hook.ops.count(0)
+        T.test_reference_denoise3d_command_runs_on_dropin_modules(None, tmp_path)
+    assert n2d >= 9 and hook.ops.count(0) > n2d    # 3 x 3 patches of the 150 x 170 micrograph, then the tomogram's patches
