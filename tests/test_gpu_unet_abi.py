@@ -71,10 +71,7 @@ def test_unet3d_c_handle_matches_python_plans(precision, c_engine):
     m = _load(UDenoiseNet3D(nf=48, base_width=7, top_width=3), seeded_state(unet_shapes(48, 7, 3, 3), int(g['seed'])))
     for x in (torch.from_numpy(g['x']), torch.randn(1, 1, 32, 40, 36, generator=torch.Generator().manual_seed(5))):
         y_c, y_py = _both(m, x.cuda(), c_engine)
-        assert torch.equal(y_c, y_py)
-    if precision != 'fast':
-        check_parity(_both(m, torch.from_numpy(g['x']).cuda(), c_engine)[0].cpu().numpy(), g['y'], 2e-3,
-                     f'unet3d seeded {precision} (C handle)')
+        assert torch.equal(y_c, y_py)        # (parity of the Python plans against the goldens: tests/test_gpu_parity*.py)
 
 
 def test_unet2d_strict_c_handle_matches_python_plans(c_engine):
